@@ -1,0 +1,98 @@
+"""ctypes binding of libdensefusion_b200.so (the C ABI declared in include/densefusion_b200.h).
+
+There is NO fallback: if the library is missing or a symbol is absent the import fails loudly, and
+every wrapper raises on a non-zero status.  torch is used for device memory and streams only."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdensefusion_b200.so")
+
+_p = ctypes.c_void_p
+_i = ctypes.c_int
+_ll = ctypes.c_longlong
+_ull = ctypes.c_ulonglong
+_f = ctypes.c_float
+
+# name -> argtypes ; must list EVERY symbol of include/densefusion_b200.h (tests/test_abi.py checks)
+SIGNATURES = {
+    "df_abi_version": [],
+    "df_features": [],
+    "df_knn": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "df_loss_forward": [_p, _p, _p, _p, _p, _p, _p, _p, _ull, _i, _f, _i, _i, _i, _i,
+                        _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "df_loss_backward": [_p, _p, _p, _p, _p, _p, _p, _p, _f, _i, _i, _p, _p, _p, _p],
+    "df_gemm_fp32": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _p, _p],
+    "df_gemm_rows_per_pool_tile": [],
+    "df_gemm_tc": [_p, _i, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _p, _i, _i, _p],
+    "df_split_tf32": [_p, _p, _p, _ll, _p],
+    "df_gather_embedding": [_p, _p, _p, _p, _ll, _ll, _ll, _i, _i, _i, _p],
+    "df_xyz_conv": [_p, _p, _p, _p, _i, _ll, _p],
+    "df_pool_finish": [_p, _p, _i, _i, _i, _i, _p],
+    "df_select_out": [_p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _ll, _p, _p, _p, _p],
+    "df_select_pose": [_p, _p, _p, _p, _i, _i, _p, _p, _p],
+    "df_cloud_transform": [_p, _p, _p, _i, _i, _p],
+    "df_pose_compose": [_p, _p, _p, _i, _p],
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA extension is mandatory (no CPU / eager fallback). "
+            "Build it with `python -m densefusion_b200.build` or __graft_entry__.build().")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing -> loud
+        fn.argtypes = args
+        fn.restype = ctypes.c_int
+    return lib
+
+
+lib = _load()
+
+
+class DFError(RuntimeError):
+    pass
+
+
+def check(status: int, what: str) -> None:
+    if status == 0:
+        return
+    if status == -1:
+        raise DFError(f"{what}: invalid argument")
+    if status == -2:
+        raise DFError(f"{what}: unsupported configuration")
+    raise DFError(f"{what}: CUDA error {status}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise DFError("densefusion_b200 kernels need CUDA tensors (there is no CPU path)")
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    """fp32 + contiguous (a no-op view when already so)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def i64c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.int64:
+        t = t.long()
+    return t if t.is_contiguous() else t.contiguous()

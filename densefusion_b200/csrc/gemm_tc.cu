@@ -1,0 +1,506 @@
+// Tensor-core mode of the dense-fusion head GEMMs: tcgen05.mma (kind::tf32) with fp32 accumulators in
+// TMEM, weights streamed by TMA, same contract and fused epilogues as gemm_simt.cu.
+//
+//   C[m,n] = act( sum_k A[m,k] W[n,k] + bias )         M tile 128 (one TMEM lane per point), N tile BN
+//
+// fp32 parity on a TF32 tensor core ("3xTF32"): x = hi + lo with hi = x & 0xffffe000 (exactly
+// representable in TF32, so the result does not depend on whether the MMA truncates or rounds) and
+// lo = x - hi (exact in fp32).  D += A_hi W_hi + A_lo W_hi + A_hi W_lo; the dropped A_lo W_lo term and
+// the TF32 rounding of the lo factors are O(2^-21) relative.  Single-pass TF32 (precision 2) issues
+// only the first product.
+//
+// Data movement (why it looks like this -- shared memory bandwidth is the binding resource for 3xTF32):
+//   * W_hi / W_lo are split ONCE at weight-pack time (df_split_tf32) and arrive by TMA into
+//     128B-swizzled K-major tiles (BK = 32 floats = one swizzle atom per row);
+//   * A never touches shared memory in the default path: the 4 worker warps own one accumulator row
+//     each, read their row's 32 floats of the k-block straight from global (128 B contiguous, full
+//     sectors), split them in registers and tcgen05.st the hi / lo halves into TMEM, from where the MMA
+//     takes its A operand (".ts" form).  An smem-staged A path (A_TMEM = false) is kept for bring-up.
+//   * one elected thread issues the MMAs; tcgen05.commit releases W stages / A stages and finally
+//     signals the epilogue; the same worker warps then read the accumulator rows back (tcgen05.ld),
+//     apply bias / per-crop bias / ReLU and either store 128 B per row chunk or reduce the columns over
+//     the rows with a shuffle butterfly (fixed order -> deterministic pooling).
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-5 workers.
+#include "df_common.cuh"
+#include "../../include/densefusion_b200.h"
+#include <cuda.h>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                       // floats per k-block = 128 B = one SW128 atom row
+constexpr int UMMA_K = 8;                    // tf32
+constexpr int NUM_THREADS = 192;
+constexpr int NUM_WORKERS = 128;
+
+struct TcParams {
+    const float* A; int lda;
+    const float* bias; int bias_crop_stride;
+    float* C; int ldc;
+    int M, N, K, relu, precise;
+    int rows_per_crop;
+    long long a_gs, bias_gs, c_gs;
+    float* pool_partial; int tiles_per_crop;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug must trap (launch error) rather than hang the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    const long long t0 = clock64();
+    uint32_t ok = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) break;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T
+__device__ __forceinline__ void umma_ss(uint32_t d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem desc]^T
+__device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+
+#define DF_R32(v) \
+    v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15], v[16], v[17],   \
+    v[18], v[19], v[20], v[21], v[22], v[23], v[24], v[25], v[26], v[27], v[28], v[29], v[30], v[31]
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
+                 "%23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+                 "%24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                   "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+                   "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+                   "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile whose rows are 128 B apart: 8-row atoms 1024 B apart (SBO),
+// LBO unused (one atom along K), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ uint32_t tf32_instr_desc(int n)
+{
+    // c_format F32 (1) @4, a/b format TF32 (2) @7/@10, K-major both, N>>3 @17, M>>4 @24
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN, bool A_TMEM>
+struct Cfg {
+    static constexpr int W_STAGES = (BN == 256) ? 3 : (A_TMEM ? 4 : 3);
+    static constexpr int A_STAGES = A_TMEM ? 4 : 3;
+    static constexpr int W_TILE_BYTES = BN * BK * 4;                 // one of hi / lo
+    static constexpr int A_TILE_BYTES = BM * BK * 4;
+    static constexpr int SMEM_W = W_STAGES * 2 * W_TILE_BYTES;
+    static constexpr int SMEM_A = A_TMEM ? 0 : A_STAGES * 2 * A_TILE_BYTES;
+    static constexpr int SMEM_POOL = 4 * BN * 4;
+    static constexpr int SMEM_BAR = 256;
+    static constexpr int SMEM_TOTAL = 1024 /*align slack*/ + SMEM_W + SMEM_A + SMEM_POOL + SMEM_BAR;
+    static constexpr int TMEM_A_COL0 = BN;                           // accumulator occupies [0, BN)
+    static constexpr int TMEM_COLS_USED = BN + (A_TMEM ? A_STAGES * 2 * BK : 0);
+    static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64 : TMEM_COLS_USED <= 128 ? 128
+                                     : TMEM_COLS_USED <= 256 ? 256 : 512;
+    static_assert(TMEM_COLS_USED <= 512, "TMEM overflow");
+    static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory overflow");
+};
+
+template <int BN, bool A_TMEM>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo, const TcParams p)
+{
+    using C = Cfg<BN, A_TMEM>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_w = smem;                                             // [W_STAGES][hi|lo][BN][32]
+    uint8_t* s_a = smem + C::SMEM_W;                                 // [A_STAGES][hi|lo][128][32]   (smem-A path)
+    float* s_pool = reinterpret_cast<float*>(smem + C::SMEM_W + C::SMEM_A);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::SMEM_W + C::SMEM_A + C::SMEM_POOL);
+    uint64_t* w_full = bars;                       // [W_STAGES]
+    uint64_t* w_empty = bars + 4;                  // [W_STAGES]
+    uint64_t* a_full = bars + 8;                   // [A_STAGES]
+    uint64_t* a_empty = bars + 12;                 // [A_STAGES]
+    uint64_t* acc_full = bars + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.z;
+    const int n0 = blockIdx.x * BN;
+    const int nkb = p.K / BK;
+
+    int row0, rows_valid, crop = 0, tile_in_crop = 0;
+    if (p.pool_partial) {
+        crop = blockIdx.y / p.tiles_per_crop;
+        tile_in_crop = blockIdx.y - crop * p.tiles_per_crop;
+        row0 = crop * p.rows_per_crop + tile_in_crop * BM;
+        rows_valid = min(BM, p.rows_per_crop - tile_in_crop * BM);
+    } else {
+        row0 = blockIdx.y * BM;
+        rows_valid = min(BM, p.M - row0);
+    }
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < C::W_STAGES; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
+        for (int i = 0; i < C::A_STAGES; ++i) { mbar_init(a_full + i, 4); mbar_init(a_empty + i, 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------- TMA producer (weights) -------------------------------
+        if (lane == 0) {
+            const uint32_t bytes = (p.precise ? 2u : 1u) * C::W_TILE_BYTES;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % C::W_STAGES;
+                const uint32_t ph = (kb / C::W_STAGES) & 1;
+                mbar_wait(w_empty + s, ph ^ 1);
+                mbar_expect_tx(w_full + s, bytes);
+                uint8_t* dst = s_w + (size_t)s * 2 * C::W_TILE_BYTES;
+                tma_load_2d(&tm_whi, dst, w_full + s, kb * BK, g * p.N + n0);
+                if (p.precise) tma_load_2d(&tm_wlo, dst + C::W_TILE_BYTES, w_full + s, kb * BK, g * p.N + n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------- MMA issuer -------------------------------------------
+        if (lane == 0) {
+            const uint32_t idesc = tf32_instr_desc(BN);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % C::W_STAGES, sa = kb % C::A_STAGES;
+                mbar_wait(w_full + s, (kb / C::W_STAGES) & 1);
+                mbar_wait(a_full + sa, (kb / C::A_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t w_hi = smem_u32(s_w + (size_t)s * 2 * C::W_TILE_BYTES);
+                const uint32_t w_lo = w_hi + C::W_TILE_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                    const uint32_t koff = ks * UMMA_K * 4;                        // bytes along K inside the atom
+                    const uint64_t bhi = sw128_desc(w_hi + koff), blo = sw128_desc(w_lo + koff);
+                    const uint32_t first = (kb | ks) != 0;
+                    if (A_TMEM) {
+                        const uint32_t a_hi = tmem_base + C::TMEM_A_COL0 + sa * 2 * BK + ks * UMMA_K;
+                        const uint32_t a_lo = a_hi + BK;
+                        umma_ts(tmem_base, a_hi, bhi, idesc, first);
+                        if (p.precise) { umma_ts(tmem_base, a_lo, bhi, idesc, 1u); umma_ts(tmem_base, a_hi, blo, idesc, 1u); }
+                    } else {
+                        const uint32_t a_hi_s = smem_u32(s_a + (size_t)sa * 2 * C::A_TILE_BYTES);
+                        const uint64_t ahi = sw128_desc(a_hi_s + koff), alo = sw128_desc(a_hi_s + C::A_TILE_BYTES + koff);
+                        umma_ss(tmem_base, ahi, bhi, idesc, first);
+                        if (p.precise) { umma_ss(tmem_base, alo, bhi, idesc, 1u); umma_ss(tmem_base, ahi, blo, idesc, 1u); }
+                    }
+                }
+                umma_commit(w_empty + s);        // frees the weight stage when these MMAs retire
+                umma_commit(a_empty + sa);       // ... and the activation stage
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        // ------------------------------- workers: A staging, then epilogue --------------------
+        const int q = warp & 3;                  // TMEM lane quarter this warp may touch
+        const int r = q * 32 + lane;             // accumulator row == tile row
+        const bool row_ok = r < rows_valid;
+        const float* arow = p.A + g * p.a_gs + (size_t)(row0 + (row_ok ? r : 0)) * p.lda;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+
+        uint32_t cur[32];
+        auto load_kb = [&](int kb) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 v = row_ok ? __ldg(reinterpret_cast<const float4*>(arow + kb * BK) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                cur[i * 4 + 0] = __float_as_uint(v.x); cur[i * 4 + 1] = __float_as_uint(v.y);
+                cur[i * 4 + 2] = __float_as_uint(v.z); cur[i * 4 + 3] = __float_as_uint(v.w);
+            }
+        };
+        load_kb(0);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int sa = kb % C::A_STAGES;
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                hi[i] = p.precise ? (cur[i] & 0xffffe000u) : cur[i];
+                lo[i] = __float_as_uint(__uint_as_float(cur[i]) - __uint_as_float(hi[i]));
+            }
+            if (kb + 1 < nkb) load_kb(kb + 1);                      // next block's loads fly during the wait + store
+            mbar_wait(a_empty + sa, ((kb / C::A_STAGES) & 1) ^ 1);
+            if (A_TMEM) {
+                tc_fence_after();
+                const uint32_t t = tmem_base + lane_base + C::TMEM_A_COL0 + sa * 2 * BK;
+                tmem_st32(t, hi);
+                if (p.precise) tmem_st32(t + BK, lo);
+                tmem_st_wait();
+                tc_fence_before();
+            } else {
+                // row r of a K-major SW128 tile: 16-byte chunk c lands at chunk (c ^ (r & 7))
+                uint8_t* base = s_a + (size_t)sa * 2 * C::A_TILE_BYTES + r * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int pc = (c ^ (r & 7)) * 16;
+                    *reinterpret_cast<uint4*>(base + pc) = make_uint4(hi[c * 4], hi[c * 4 + 1], hi[c * 4 + 2], hi[c * 4 + 3]);
+                    if (p.precise)
+                        *reinterpret_cast<uint4*>(base + C::A_TILE_BYTES + pc) =
+                            make_uint4(lo[c * 4], lo[c * 4 + 1], lo[c * 4 + 2], lo[c * 4 + 3]);
+                }
+                fence_proxy_async();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full + sa);
+        }
+
+        // ---- epilogue ----
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int row = row0 + r;
+        const float* bias = p.bias ? p.bias + g * p.bias_gs : nullptr;
+        if (bias && p.bias_crop_stride) bias += (size_t)((row_ok ? row : row0) / p.rows_per_crop) * p.bias_crop_stride;
+        float* crow = p.C ? p.C + g * p.c_gs + (size_t)row * p.ldc : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + lane_base + c * 32, v);
+            const int col = n0 + c * 32;
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float x = __uint_as_float(v[i]);
+                if (bias && col + i < p.N) x += __ldg(bias + col + i);
+                if (p.relu) x = fmaxf(x, 0.0f);
+                f[i] = x;
+            }
+            if (p.pool_partial) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = row_ok ? f[i] : 0.0f;
+                // butterfly reduce-scatter over the 32 rows of this warp: lane l ends with column l
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const bool up = (lane & off) != 0;
+#pragma unroll
+                    for (int i = 0; i < off; ++i) {
+                        const float send = up ? f[i] : f[i + off];
+                        const float keep = up ? f[i + off] : f[i];
+                        f[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
+                }
+                s_pool[q * BN + c * 32 + lane] = f[0];
+            } else if (row_ok && crow) {
+                if (col + 32 <= p.N) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<float4*>(crow + col + i * 4) = make_float4(f[i * 4], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
+                } else {
+                    for (int i = 0; i < 32; ++i)
+                        if (col + i < p.N) crow[col + i] = f[i];
+                }
+            }
+        }
+        if (p.pool_partial) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");           // the 4 worker warps only
+            const int t = threadIdx.x - 64;
+            for (int c = t; c < BN; c += NUM_WORKERS) {
+                if (n0 + c < p.N) {
+                    const float s = ((s_pool[c] + s_pool[BN + c]) + s_pool[2 * BN + c]) + s_pool[3 * BN + c];
+                    p.pool_partial[((size_t)crop * p.tiles_per_crop + tile_in_crop) * p.N + n0 + c] = s;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor (rows, K) with row pitch `ld` floats; box = 32 floats x box_rows, 128B swizzle
+bool make_map(CUtensorMap* map, const float* base, long long rows, int K, int ld, int box_rows)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, bool A_TMEM>
+int launch_tc(const CUtensorMap& mhi, const CUtensorMap& mlo, const TcParams& p, int groups, cudaStream_t s)
+{
+    using C = Cfg<BN, A_TMEM>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, A_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             C::SMEM_TOTAL);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    const int mt = p.pool_partial ? (p.M / p.rows_per_crop) * p.tiles_per_crop : (p.M + BM - 1) / BM;
+    dim3 grid((p.N + BN - 1) / BN, mt, groups);
+    gemm_tc_kernel<BN, A_TMEM><<<grid, NUM_THREADS, C::SMEM_TOTAL, s>>>(mhi, mlo, p);
+    return 0;
+}
+
+__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = x[i];
+    const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    hi[i] = h;
+    lo[i] = v - h;
+}
+
+}  // namespace
+
+extern "C" int df_split_tf32(const float* x, float* hi, float* lo, long long n, void* stream)
+{
+    if (!x || !hi || !lo || n <= 0) return DF_ERR_ARG;
+    split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, hi, lo, n);
+    DF_RETURN_LAST_ERROR();
+}
+
+extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
+                          int bias_crop_stride, float* C, int ldc, int M, int N, int K, int relu, int rows_per_crop,
+                          int groups, long long a_group_stride, long long bias_group_stride,
+                          long long c_group_stride, float* pool_partial, int precision, int variant, void* stream)
+{
+    if (!A || !W_hi || (!C && !pool_partial)) return DF_ERR_ARG;
+    if (precision != 1 && precision != 2) return DF_ERR_ARG;
+    if (precision == 1 && !W_lo) return DF_ERR_ARG;
+    if (M <= 0 || N <= 0 || K <= 0 || groups <= 0) return DF_ERR_ARG;
+    if (K % BK || lda % 4 || ldw % 4 || N % 4 || a_group_stride % 4 || bias_group_stride % 4) return DF_ERR_ARG;
+    if (((uintptr_t)A & 15) || ((uintptr_t)W_hi & 15) || ((uintptr_t)W_lo & 15)) return DF_ERR_ARG;
+    if (C && (ldc % 4 || c_group_stride % 4 || ((uintptr_t)C & 15))) return DF_ERR_ARG;
+    if ((bias_crop_stride || pool_partial) && rows_per_crop <= 0) return DF_ERR_ARG;
+    if (pool_partial && M % rows_per_crop) return DF_ERR_ARG;
+    if (groups > 1 && N % 128) return DF_ERR_UNSUPPORTED;      // group g's weight rows start at g*N: keep tiles inside a group
+
+    TcParams p;
+    p.A = A; p.lda = lda; p.bias = bias; p.bias_crop_stride = bias_crop_stride;
+    p.C = pool_partial ? nullptr : C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.relu = relu;
+    p.precise = precision == 1;
+    p.rows_per_crop = rows_per_crop > 0 ? rows_per_crop : M;
+    p.a_gs = a_group_stride; p.bias_gs = bias_group_stride; p.c_gs = c_group_stride;
+    p.pool_partial = pool_partial;
+    p.tiles_per_crop = pool_partial ? (p.rows_per_crop + BM - 1) / BM : 0;
+
+    // variant: 0 = auto (A through TMEM; BN 256 when N allows), 1 = BN128/TMEM-A, 2 = BN256/TMEM-A, 3 = BN128/smem-A
+    int v = variant;
+    if (v == 0) v = (N % 256 == 0 && groups == 1) ? 2 : 1;
+    const int bn = v == 2 ? 256 : 128;
+    if (v == 2 && groups > 1 && N % 256) return DF_ERR_UNSUPPORTED;
+    CUtensorMap mhi, mlo;
+    const long long wrows = (long long)groups * N;
+    if (!make_map(&mhi, W_hi, wrows, K, ldw, bn)) return DF_ERR_UNSUPPORTED;
+    if (!make_map(&mlo, p.precise ? W_lo : W_hi, wrows, K, ldw, bn)) return DF_ERR_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if (v == 1) rc = launch_tc<128, true>(mhi, mlo, p, groups, s);
+    else if (v == 2) rc = launch_tc<256, true>(mhi, mlo, p, groups, s);
+    else if (v == 3) rc = launch_tc<128, false>(mhi, mlo, p, groups, s);
+    else return DF_ERR_ARG;
+    if (rc) return rc;
+    DF_RETURN_LAST_ERROR();
+}

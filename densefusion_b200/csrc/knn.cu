@@ -1,0 +1,156 @@
+// K4 -- brute-force nearest neighbours, drop-in for lib/knn (reference:
+// lib/knn/src/knn_cuda_kernel.cu:31-170 + the C glue lib/knn/src/knn_pytorch.c:6-48).
+//
+// The reference materialises the full R x Q distance matrix in HBM (8*R*Q bytes of traffic) and
+// then scans each column.  Here the reference points are staged once per CTA in shared memory as
+// float4 (one broadcast LDS.128 per reference point serves every query of the warp), each thread
+// keeps KNN_QPT queries and their running minimum in registers, and nothing but the inputs and the
+// int64 indices ever touches HBM (12*R + 20*Q bytes).  Distances use the reference's FMA chain and
+// the strict '<' update, so indices are bit-identical including ties (lowest index) and NaN rows.
+#include "df_common.cuh"
+#include "../../include/densefusion_b200.h"
+
+namespace {
+
+constexpr int KNN_THREADS = 256;
+constexpr int KNN_TILE = 2048;   // reference points per shared-memory tile (32 KB as float4)
+
+// ---- D = 3, k = 1 : the path's own shape (lib/loss.py:42-47, tools/eval_linemod.py:124-128) ----
+template <int QPT>
+__global__ void __launch_bounds__(KNN_THREADS)
+knn1_d3_kernel(const float* __restrict__ ref, const float* __restrict__ query, int64_t* __restrict__ ind,
+               int R, int Q)
+{
+    __shared__ float4 s_ref[KNN_TILE];
+    const int b = blockIdx.y;
+    ref += (size_t)b * 3 * R;
+    query += (size_t)b * 3 * Q;
+    ind += (size_t)b * Q;
+
+    const int q0 = blockIdx.x * (KNN_THREADS * QPT) + threadIdx.x;
+    float qx[QPT], qy[QPT], qz[QPT], best[QPT];
+    int arg[QPT];
+    // row 0 seeds the minimum exactly like `max_dist = p_dist[0]` (knn_cuda_kernel.cu:122)
+    const float r0x = __ldg(ref), r0y = __ldg(ref + R), r0z = __ldg(ref + 2 * (size_t)R);
+#pragma unroll
+    for (int i = 0; i < QPT; ++i) {
+        const int q = q0 + i * KNN_THREADS;
+        const bool ok = q < Q;
+        qx[i] = ok ? __ldg(query + q) : 0.0f;
+        qy[i] = ok ? __ldg(query + Q + q) : 0.0f;
+        qz[i] = ok ? __ldg(query + 2 * (size_t)Q + q) : 0.0f;
+        best[i] = df::ref_ssd3(r0x, r0y, r0z, qx[i], qy[i], qz[i]);
+        arg[i] = 0;
+    }
+    for (int base = 0; base < R; base += KNN_TILE) {
+        const int n = min(KNN_TILE, R - base);
+        __syncthreads();
+        for (int r = threadIdx.x; r < n; r += KNN_THREADS)
+            s_ref[r] = make_float4(__ldg(ref + base + r), __ldg(ref + R + base + r),
+                                   __ldg(ref + 2 * (size_t)R + base + r), 0.0f);
+        __syncthreads();
+#pragma unroll 4
+        for (int r = 0; r < n; ++r) {
+            const float4 p = s_ref[r];
+#pragma unroll
+            for (int i = 0; i < QPT; ++i) {
+                const float d = df::ref_ssd3(p.x, p.y, p.z, qx[i], qy[i], qz[i]);
+                if (d < best[i]) { best[i] = d; arg[i] = base + r; }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < QPT; ++i) {
+        const int q = q0 + i * KNN_THREADS;
+        if (q < Q) ind[q] = (int64_t)arg[i] + 1;   // 1-based (knn_cuda_kernel.cu:123,163)
+    }
+}
+
+// ---- general (D, k): literal k-slot insertion of cuInsertionSort, distances on the fly ----------
+constexpr int KNN_KMAX = 64;
+
+__global__ void __launch_bounds__(128)
+knn_general_kernel(const float* __restrict__ ref, const float* __restrict__ query, int64_t* __restrict__ ind,
+                   int R, int Q, int D, int k)
+{
+    const int b = blockIdx.y;
+    ref += (size_t)b * D * R;
+    query += (size_t)b * D * Q;
+    ind += (size_t)b * k * Q;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+
+    float dist[KNN_KMAX];
+    int id[KNN_KMAX];
+    auto ssd = [&](int r) {
+        float s = 0.0f;
+        for (int d = 0; d < D; ++d) {
+            const float t = __fsub_rn(__ldg(ref + (size_t)d * R + r), __ldg(query + (size_t)d * Q + q));
+            s = __fmaf_rn(t, t, s);
+        }
+        return s;
+    };
+    // phase 1: order the first k rows (knn_cuda_kernel.cu:126-146)
+    dist[0] = ssd(0);
+    id[0] = 1;
+    float max_dist = dist[0];
+    for (int l = 1; l < k; ++l) {
+        const float curr = ssd(l);
+        dist[l] = curr;
+        if (curr < max_dist) {
+            int i = l - 1;
+            for (int a = 0; a < l - 1; ++a)
+                if (dist[a] > curr) { i = a; break; }
+            for (int j = l; j > i; --j) { dist[j] = dist[j - 1]; id[j] = id[j - 1]; }
+            dist[i] = curr;
+            id[i] = l + 1;
+        } else {
+            id[l] = l + 1;
+        }
+        max_dist = dist[l];
+    }
+    // phase 2: stream the remaining rows through the window (knn_cuda_kernel.cu:149-168)
+    for (int l = k; l < R; ++l) {
+        const float curr = ssd(l);
+        if (curr < max_dist) {
+            int i = k - 1;
+            for (int a = 0; a < k - 1; ++a)
+                if (dist[a] > curr) { i = a; break; }
+            for (int j = k - 1; j > i; --j) { dist[j] = dist[j - 1]; id[j] = id[j - 1]; }
+            dist[i] = curr;
+            id[i] = l + 1;
+            max_dist = dist[k - 1];
+        }
+    }
+    for (int j = 0; j < k; ++j) ind[(size_t)j * Q + q] = id[j];
+}
+
+}  // namespace
+
+extern "C" int df_knn(const float* ref, const float* query, int64_t* ind, int batch, int dim, int R, int Q,
+                      int k, void* stream)
+{
+    if (!ref || !query || !ind || batch <= 0 || dim <= 0 || R <= 0 || Q < 0 || k <= 0 || k > R) return DF_ERR_ARG;
+    if (batch > 65535) return DF_ERR_ARG;
+    if (Q == 0) return DF_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dim == 3 && k == 1) {
+        // enough CTAs for >= 2 waves of 148 SMs x 8 resident CTAs when Q allows, else fewer queries/thread
+        const long per_wave = 148L * 8 * KNN_THREADS;
+        if ((long)Q * batch >= 8 * per_wave) {
+            dim3 grid((Q + KNN_THREADS * 4 - 1) / (KNN_THREADS * 4), batch);
+            knn1_d3_kernel<4><<<grid, KNN_THREADS, 0, s>>>(ref, query, ind, R, Q);
+        } else if ((long)Q * batch >= 2 * per_wave) {
+            dim3 grid((Q + KNN_THREADS * 2 - 1) / (KNN_THREADS * 2), batch);
+            knn1_d3_kernel<2><<<grid, KNN_THREADS, 0, s>>>(ref, query, ind, R, Q);
+        } else {
+            dim3 grid((Q + KNN_THREADS - 1) / KNN_THREADS, batch);
+            knn1_d3_kernel<1><<<grid, KNN_THREADS, 0, s>>>(ref, query, ind, R, Q);
+        }
+    } else {
+        if (k > KNN_KMAX) return DF_ERR_UNSUPPORTED;
+        dim3 grid((Q + 127) / 128, batch);
+        knn_general_kernel<<<grid, 128, 0, s>>>(ref, query, ind, R, Q, dim, k);
+    }
+    DF_RETURN_LAST_ERROR();
+}

@@ -1,0 +1,58 @@
+"""BN-free dilated ResNet-18 trunk of the colour encoder.
+
+Kept on torch/cuDNN by design (the encoder is not one of the four
+rewritten subsystems).  Parameter names and shapes match the reference's lib/extractors.py:78-129 so
+reference checkpoints load unchanged; the construction is table-driven rather than class-per-block."""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class ResidualPair(nn.Module):
+    """Two 3x3 convolutions with an identity or 1x1-projected skip (no normalisation layers)."""
+
+    def __init__(self, cin: int, cout: int, stride: int, dilation: int, project: bool):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride=stride, padding=dilation, dilation=dilation, bias=False)
+        self.conv2 = nn.Conv2d(cout, cout, 3, stride=1, padding=dilation, dilation=dilation, bias=False)
+        self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride=stride, bias=False)) if project else None
+
+    def forward(self, x):
+        skip = x if self.downsample is None else self.downsample(x)
+        y = self.conv2(F.relu(self.conv1(x)))
+        return F.relu(y + skip)
+
+
+# (name, width, stride of the first pair, dilation of the later pairs); the first pair of a stage is
+# never dilated (lib/extractors.py:99-112 does not forward `dilation` to it).
+_STAGES = (("layer1", 64, 1, 1), ("layer2", 128, 2, 1), ("layer3", 256, 1, 2), ("layer4", 512, 1, 4))
+
+
+class ResNet18Trunk(nn.Module):
+    def __init__(self, pairs_per_stage=(2, 2, 2, 2)):
+        super().__init__()
+        self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
+        width = 64
+        for (name, cout, stride, dilation), count in zip(_STAGES, pairs_per_stage):
+            blocks = [ResidualPair(width, cout, stride, 1, stride != 1 or width != cout)]
+            blocks += [ResidualPair(cout, cout, 1, dilation, False) for _ in range(count - 1)]
+            setattr(self, name, nn.Sequential(*blocks))
+            width = cout
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                fan = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+                nn.init.normal_(m.weight, 0.0, math.sqrt(2.0 / fan))
+
+    def forward(self, x):
+        x = F.max_pool2d(F.relu(self.conv1(x)), 3, stride=2, padding=1)
+        x = self.layer2(self.layer1(x))
+        mid = self.layer3(x)
+        return self.layer4(mid), mid
+
+
+def resnet18(pretrained: bool = False) -> ResNet18Trunk:
+    return ResNet18Trunk((2, 2, 2, 2))

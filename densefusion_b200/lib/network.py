@@ -1,0 +1,179 @@
+"""Drop-in PoseNet / PoseRefineNet (reference: lib/network.py:70-132 and :170-206).
+
+Same constructor arguments, forward signatures, return shapes and state_dict keys as the reference, so
+reference checkpoints and call sites work unchanged -- but the dense-fusion head and the refiner run as
+hand-written sm_100a kernels through the C ABI (densefusion_b200.engine), not as ~25 cuDNN/cuBLAS calls.
+The colour encoder (`cnn`) stays a torch/cuDNN module.
+
+Additive API (not in the reference): `forward_batched` evaluates every crop of the batch (the reference
+returns batch element 0 only, lib/network.py:123-126) and `precision` selects the GEMM arithmetic:
+"fp32" (exact FFMA, default), "3xtf32" (tcgen05, error-compensated, fp32-parity) or "tf32".
+
+Inference only in this round: calling forward with autograd enabled on a module whose parameters require
+grad raises, it does NOT silently fall back to torch ops."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import engine, ops
+from .pspnet import PSPNet
+
+
+class _ReplicaShim(nn.Module):
+    """Keeps the `module.` segment nn.DataParallel put into the reference's checkpoint keys
+    (lib/network.py:33) without any of its scatter/gather machinery."""
+
+    def __init__(self, module: nn.Module):
+        super().__init__()
+        self.module = module
+
+    def forward(self, x):
+        return self.module(x)
+
+
+class ModifiedResnet(nn.Module):
+    def __init__(self, usegpu: bool = True):
+        super().__init__()
+        self.model = _ReplicaShim(PSPNet(sizes=(1, 2, 3, 6), psp_size=512, deep_features_size=256, backend="resnet18"))
+
+    def forward(self, x):
+        return self.model(x)
+
+
+class _FeatParams(nn.Module):
+    """Parameter container with the reference's PoseNetFeat / PoseRefineNetFeat names."""
+
+    def __init__(self, num_points: int, conv5_in: int):
+        super().__init__()
+        self.conv1 = nn.Conv1d(3, 64, 1)
+        self.conv2 = nn.Conv1d(64, 128, 1)
+        self.e_conv1 = nn.Conv1d(32, 64, 1)
+        self.e_conv2 = nn.Conv1d(64, 128, 1)
+        self.conv5 = nn.Conv1d(conv5_in, 512, 1)
+        self.conv6 = nn.Conv1d(512, 1024, 1)
+        self.num_points = num_points
+
+
+class PoseNetFeat(_FeatParams):
+    def __init__(self, num_points: int):
+        super().__init__(num_points, 256)
+
+
+class PoseRefineNetFeat(_FeatParams):
+    def __init__(self, num_points: int):
+        super().__init__(num_points, 384)
+
+
+def _no_autograd(module: nn.Module, *inputs):
+    if torch.is_grad_enabled() and (any(p.requires_grad for p in module.parameters())
+                                    or any(torch.is_tensor(t) and t.requires_grad for t in inputs)):
+        raise NotImplementedError(
+            "densefusion_b200: the fused head has no backward yet; call under torch.no_grad() "
+            "(or requires_grad_(False) the module).  There is deliberately no torch fallback.")
+
+
+class _PackedMixin:
+    precision = "fp32"
+
+    def _packed(self, cls):
+        ver = engine.param_version(self)
+        if getattr(self, "_pack_ver", None) != ver:
+            self._pack = cls(self)
+            self._pack_ver = ver
+        return self._pack
+
+    def _workspace(self, crops: int, n: int, device, towers: bool):
+        key = (crops, n, str(device))
+        ws = getattr(self, "_ws", None)
+        if ws is None or self._ws_key != key:
+            ws = engine.Workspace(crops, n, device, towers)
+            self._ws, self._ws_key = ws, key
+        return ws
+
+
+class PoseNet(nn.Module, _PackedMixin):
+    def __init__(self, num_points: int, num_obj: int):
+        super().__init__()
+        self.num_points = num_points
+        self.cnn = ModifiedResnet()
+        self.feat = PoseNetFeat(num_points)
+        for b in "rtc":
+            setattr(self, f"conv1_{b}", nn.Conv1d(1408, 640, 1))
+        for b in "rtc":
+            setattr(self, f"conv2_{b}", nn.Conv1d(640, 256, 1))
+        for b in "rtc":
+            setattr(self, f"conv3_{b}", nn.Conv1d(256, 128, 1))
+        self.conv4_r = nn.Conv1d(128, num_obj * 4, 1)   # quaternion
+        self.conv4_t = nn.Conv1d(128, num_obj * 3, 1)   # translation
+        self.conv4_c = nn.Conv1d(128, num_obj * 1, 1)   # confidence
+        self.num_obj = num_obj
+
+    # ---- head on pre-gathered embeddings (point-major), any number of crops ----
+    def head(self, x: torch.Tensor, emb_pm: torch.Tensor, obj: torch.Tensor):
+        """x (B,N,3), emb_pm (B*N,32), obj (B,)|(B,1) -> (B,N,4), (B,N,3), (B,N,1)."""
+        _no_autograd(self, x, emb_pm)
+        B, n = x.shape[0], x.shape[1]
+        if n != self.num_points:
+            raise RuntimeError(f"PoseNet was built for {self.num_points} points, got {n}")   # AvgPool1d(num_points)
+        w = self._packed(engine.PackedPoseNetHead)
+        ws = self._workspace(B, n, x.device, True)
+        dev = x.device
+        out_r = torch.empty(B, n, 4, device=dev)
+        out_t = torch.empty(B, n, 3, device=dev)
+        out_c = torch.empty(B, n, 1, device=dev)
+        engine.posenet_head_chunk(w, ws, ops.f32c(x).view(B * n, 3), emb_pm, ops.i64c(obj).view(-1), B, n,
+                                  out_r, out_t, out_c, self.precision)
+        return out_r, out_t, out_c
+
+    def forward_batched(self, img, x, choose, obj):
+        """All crops: (B,N,4), (B,N,3), (B,N,1), emb (B,32,N)."""
+        _no_autograd(self, img, x)
+        out_img = self.cnn(img)
+        emb_pm, emb_cm = ops.gather_embedding(out_img, choose)
+        r, t, c = self.head(x, emb_pm, obj)
+        return r, t, c, emb_cm
+
+    def forward(self, img, x, choose, obj):
+        """Reference contract: outputs of batch element 0 only; emb for the whole batch, detached."""
+        _no_autograd(self, img, x)
+        out_img = self.cnn(img)
+        emb_pm, emb_cm = ops.gather_embedding(out_img, choose)
+        n = x.shape[1]
+        r, t, c = self.head(x[0:1], emb_pm[:n], obj[0:1])
+        return r, t, c, emb_cm.detach()
+
+
+class PoseRefineNet(nn.Module, _PackedMixin):
+    def __init__(self, num_points: int, num_obj: int):
+        super().__init__()
+        self.num_points = num_points
+        self.feat = PoseRefineNetFeat(num_points)
+        self.conv1_r = nn.Linear(1024, 512)
+        self.conv1_t = nn.Linear(1024, 512)
+        self.conv2_r = nn.Linear(512, 128)
+        self.conv2_t = nn.Linear(512, 128)
+        self.conv3_r = nn.Linear(128, num_obj * 4)      # quaternion
+        self.conv3_t = nn.Linear(128, num_obj * 3)      # translation
+        self.num_obj = num_obj
+
+    def refine(self, x: torch.Tensor, emb_pm: torch.Tensor, obj: torch.Tensor):
+        """x (B,N,3), emb_pm (B*N,32), obj (B,) -> (B,4), (B,3) for every crop."""
+        _no_autograd(self, x, emb_pm)
+        B, n = x.shape[0], x.shape[1]
+        if n != self.num_points:
+            raise RuntimeError(f"PoseRefineNet was built for {self.num_points} points, got {n}")
+        w = self._packed(engine.PackedRefiner)
+        ws = self._workspace(B, n, x.device, False)
+        out_r = torch.empty(B, 4, device=x.device)
+        out_t = torch.empty(B, 3, device=x.device)
+        engine.refiner_chunk(w, ws, ops.f32c(x).view(B * n, 3), emb_pm, ops.i64c(obj).view(-1), B, n, out_r, out_t,
+                             self.precision)
+        return out_r, out_t
+
+    def forward(self, x, emb, obj):
+        """Reference contract: x (bs,N,3), emb (bs,32,N), obj (bs,1) -> out_rx (1,4), out_tx (1,3)."""
+        _no_autograd(self, x, emb)
+        n = x.shape[1]
+        emb_pm = ops.f32c(emb[0]).t().contiguous()          # (N,32) point-major view of crop 0
+        return self.refine(x[0:1], emb_pm, obj[0:1])

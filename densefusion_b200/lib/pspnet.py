@@ -1,0 +1,56 @@
+"""Pyramid-pooling decoder of the colour encoder (torch/cuDNN; see extractors.py for why it is not a
+hand-written kernel).  Parameter names / shapes follow lib/pspnet.py:7-77 of the reference."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import extractors
+
+
+class PSPModule(nn.Module):
+    def __init__(self, features: int, out_features: int = 1024, sizes=(1, 2, 3, 6)):
+        super().__init__()
+        self.sizes = tuple(sizes)
+        # stages.<i>.1.weight : index 0 is the (parameter-free) adaptive pooling
+        self.stages = nn.ModuleList(
+            nn.Sequential(nn.AdaptiveAvgPool2d((s, s)), nn.Conv2d(features, features, 1, bias=False)) for s in sizes)
+        self.bottleneck = nn.Conv2d(features * (len(sizes) + 1), out_features, 1)
+
+    def forward(self, feats):
+        hw = feats.shape[2:]
+        pyramid = [F.interpolate(stage(feats), size=hw, mode="bilinear", align_corners=False) for stage in self.stages]
+        return F.relu(self.bottleneck(torch.cat(pyramid + [feats], 1)))
+
+
+class PSPUpsample(nn.Module):
+    def __init__(self, cin: int, cout: int):
+        super().__init__()
+        self.conv = nn.Sequential(nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True),
+                                  nn.Conv2d(cin, cout, 3, padding=1), nn.PReLU())
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class PSPNet(nn.Module):
+    def __init__(self, n_classes=21, sizes=(1, 2, 3, 6), psp_size=512, deep_features_size=256, backend="resnet18"):
+        super().__init__()
+        self.feats = getattr(extractors, backend)()
+        self.psp = PSPModule(psp_size, 1024, sizes)
+        self.drop_1 = nn.Dropout2d(p=0.3)
+        self.up_1 = PSPUpsample(1024, 256)
+        self.up_2 = PSPUpsample(256, 64)
+        self.up_3 = PSPUpsample(64, 64)
+        self.drop_2 = nn.Dropout2d(p=0.15)
+        self.final = nn.Sequential(nn.Conv2d(64, 32, 1), nn.LogSoftmax(dim=1))
+        # unused by the pose path but part of the reference checkpoints
+        self.classifier = nn.Sequential(nn.Linear(deep_features_size, 256), nn.ReLU(), nn.Linear(256, n_classes))
+
+    def forward(self, x):
+        f, _ = self.feats(x)
+        p = self.drop_1(self.psp(f))
+        p = self.drop_2(self.up_1(p))
+        p = self.drop_2(self.up_2(p))
+        return self.final(self.up_3(p))

@@ -1,0 +1,165 @@
+"""Batched, on-device estimate -> select -> (re-express -> refine -> compose) x iters pipeline
+(subsystem (4) of BASELINE.json; reference: the per-object loop of tools/eval_ycb.py:147-233).
+
+The reference handles one object at a time and leaves the GPU 2 + 2*iters times per object.  Here a
+batch of crops (several frames' objects, grouped into (H,W) buckets for the encoder) goes through the
+whole chain without a single host round trip: the pose state is a float64 (B,7) tensor in HBM, every
+step is a kernel of the C ABI on one stream, and the fixed-shape chain can be captured in a CUDA graph.
+The result is the reference's output record per object: [qw qx qy qz tx ty tz]."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import engine, ops
+from ._C import check, lib, ptr, stream
+
+
+class PoseEstimator:
+    def __init__(self, estimator, refiner, iterations: int = 2, precision: str = "fp32", chunk_crops: int = 32,
+                 channels_last: bool = True):
+        self.estimator, self.refiner = estimator, refiner
+        self.iterations = int(iterations)
+        self.precision = precision
+        self.chunk = int(chunk_crops)
+        self.channels_last = channels_last
+        self.n = estimator.num_points
+        self.device = next(estimator.parameters()).device
+        self.w_head = engine.PackedPoseNetHead(estimator)
+        self.w_ref = engine.PackedRefiner(refiner)
+        self._ws_head = None
+        self._ws_ref = None
+        self._bufs: Dict[int, dict] = {}
+        if channels_last:
+            estimator.cnn.to(memory_format=torch.channels_last)
+
+    # ---- scratch ------------------------------------------------------------------------------
+    def _workspaces(self, crops: int):
+        c = min(crops, self.chunk)
+        if self._ws_head is None or self._ws_head.crops < c:
+            self._ws_head = engine.Workspace(c, self.n, self.device, True)
+            self._ws_ref = engine.Workspace(c, self.n, self.device, False)
+        return self._ws_head, self._ws_ref
+
+    def _buffers(self, B: int) -> dict:
+        b = self._bufs.get(B)
+        if b is None:
+            f = dict(device=self.device, dtype=torch.float32)
+            b = dict(out_r=torch.empty(B, self.n, 4, **f), out_t=torch.empty(B, self.n, 3, **f),
+                     out_c=torch.empty(B, self.n, 1, **f), pose=torch.empty(B, 7, device=self.device, dtype=torch.float64),
+                     which=torch.empty(B, device=self.device, dtype=torch.int64),
+                     new_cloud=torch.empty(B, self.n, 3, **f), r2=torch.empty(B, 4, **f), t2=torch.empty(B, 3, **f),
+                     emb_pm=torch.empty(B * self.n, 32, **f))
+            self._bufs[B] = b
+        return b
+
+    # ---- stages ---------------------------------------------------------------------------------
+    def encode(self, img: torch.Tensor, choose: torch.Tensor, emb_pm_out: torch.Tensor) -> None:
+        """Colour encoder (torch/cuDNN) + K1's gather for one (H,W) bucket; writes (b*N,32) rows."""
+        if self.channels_last:
+            img = img.contiguous(memory_format=torch.channels_last)
+        feat = self.estimator.cnn(img)
+        B, C, H, W = feat.shape
+        sb, sc, sh, sw = feat.stride()
+        if sh != W * sw:
+            feat = feat.contiguous()
+            sb, sc, sh, sw = feat.stride()
+        choose = ops.i64c(choose).view(B, -1)
+        check(lib.df_gather_embedding(ptr(feat), ptr(choose), ptr(emb_pm_out), None, sb, sc, sw, B, self.n, H * W,
+                                      stream()), "df_gather_embedding")
+
+    def head_and_refine(self, cloud: torch.Tensor, emb_pm: torch.Tensor, obj: torch.Tensor,
+                        iterations: Optional[int] = None) -> torch.Tensor:
+        """cloud (B,N,3), emb_pm (B*N,32), obj (B,) -> pose (B,7) float64.  Also leaves the un-refined
+        selection in self.last['pose0'] when iterations == 0."""
+        iters = self.iterations if iterations is None else iterations
+        B, n = cloud.shape[0], self.n
+        buf = self._buffers(B)
+        wh, wr = self._workspaces(B)
+        cloud = ops.f32c(cloud)
+        obj = ops.i64c(obj).view(-1)
+        s = stream()
+        for c0 in range(0, B, self.chunk):
+            c1 = min(B, c0 + self.chunk)
+            nb = c1 - c0
+            rows = slice(c0 * n, c1 * n)
+            x = cloud[c0:c1].view(nb * n, 3)
+            e = emb_pm[rows]
+            o = obj[c0:c1]
+            r, t, c = buf["out_r"][c0:c1], buf["out_t"][c0:c1], buf["out_c"][c0:c1]
+            engine.posenet_head_chunk(self.w_head, wh, x, e, o, nb, n, r, t, c, self.precision)
+            pose = buf["pose"][c0:c1]
+            check(lib.df_select_pose(ptr(r), ptr(t), ptr(c), ptr(x), nb, n, ptr(pose), ptr(buf["which"][c0:c1]), s),
+                  "df_select_pose")
+            nc = buf["new_cloud"][c0:c1]
+            for it in range(iters):
+                check(lib.df_cloud_transform(ptr(x), ptr(pose), ptr(nc), nb, n, s), "df_cloud_transform")
+                engine.refiner_chunk(self.w_ref, wr, nc.view(nb * n, 3), e, o, nb, n, buf["r2"][c0:c1],
+                                     buf["t2"][c0:c1], self.precision, emb_ready=it > 0)
+                check(lib.df_pose_compose(ptr(pose), ptr(buf["r2"][c0:c1]), ptr(buf["t2"][c0:c1]), nb, s),
+                      "df_pose_compose")
+        return buf["pose"]
+
+    @torch.no_grad()
+    def estimate(self, img, cloud, choose, obj, iterations: Optional[int] = None) -> torch.Tensor:
+        """One (H,W) bucket: img (B,3,H,W), cloud (B,N,3), choose (B,1,N), obj (B,)|(B,1) -> (B,7) f64."""
+        B = cloud.shape[0]
+        buf = self._buffers(B)
+        self.encode(img, choose, buf["emb_pm"])
+        return self.head_and_refine(cloud, buf["emb_pm"], obj, iterations)
+
+    @torch.no_grad()
+    def estimate_buckets(self, buckets: Sequence[dict], iterations: Optional[int] = None) -> torch.Tensor:
+        """Several (H,W) buckets (dicts with img, cloud, choose, obj) -> poses (sum B,7) in bucket order."""
+        total = sum(b["cloud"].shape[0] for b in buckets)
+        buf = self._buffers(total)
+        key = ("cat", total)
+        cat = self._bufs.get(key)
+        if cat is None:
+            cat = dict(cloud=torch.empty(total, self.n, 3, device=self.device),
+                       obj=torch.empty(total, device=self.device, dtype=torch.int64))
+            self._bufs[key] = cat
+        o = 0
+        for b in buckets:
+            nb = b["cloud"].shape[0]
+            self.encode(b["img"], b["choose"], buf["emb_pm"][o * self.n:(o + nb) * self.n])
+            cat["cloud"][o:o + nb].copy_(b["cloud"])
+            cat["obj"][o:o + nb].copy_(b["obj"].view(-1))
+            o += nb
+        return self.head_and_refine(cat["cloud"], buf["emb_pm"], cat["obj"], iterations)
+
+
+class GraphedBuckets:
+    """CUDA-graph capture of PoseEstimator.estimate_buckets for a fixed list of bucket shapes.
+    Static device inputs are refilled from (pinned) host tensors with copy_(non_blocking=True)."""
+
+    def __init__(self, est: PoseEstimator, shapes: Sequence[Tuple[int, int, int]], warmup: int = 2):
+        # shapes: (crops, H, W) per bucket
+        self.est = est
+        dev, n = est.device, est.n
+        self.static = [dict(img=torch.zeros(b, 3, h, w, device=dev),
+                            cloud=torch.zeros(b, n, 3, device=dev),
+                            choose=torch.zeros(b, 1, n, device=dev, dtype=torch.int64),
+                            obj=torch.zeros(b, device=dev, dtype=torch.int64)) for b, h, w in shapes]
+        for s in self.static:
+            s["cloud"][..., 2] = 1.0
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                est.estimate_buckets(self.static)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = est.estimate_buckets(self.static)
+
+    def load(self, host_buckets: Sequence[dict]) -> None:
+        for s, h in zip(self.static, host_buckets):
+            for k in ("img", "cloud", "choose", "obj"):
+                s[k].copy_(h[k].view(s[k].shape), non_blocking=True)
+
+    def run(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.out

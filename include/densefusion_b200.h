@@ -1,0 +1,127 @@
+/*
+ * densefusion_b200.h -- C ABI of libdensefusion_b200.so (hand-written sm_100a CUDA kernels for the
+ * DenseFusion per-pixel pose-hypothesis path).
+ *
+ * Conventions (mirroring the reference's only native interface, lib/knn/src/knn_cuda_kernel.h:14-16
+ * and lib/knn/src/knn_pytorch.h:1):
+ *   - plain pointers and sizes, no torch types; every pointer is a DEVICE pointer;
+ *   - the caller owns all buffers including outputs and scratch; nothing is retained between calls;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*), no host synchronisation, no
+ *     allocation -> every entry point is CUDA-graph capturable and re-entrant across streams;
+ *   - return 0 on success, DF_ERR_ARG (-1) / DF_ERR_UNSUPPORTED (-2) for rejected arguments, or the
+ *     positive cudaError_t of a failed launch.  Nothing throws across this boundary.
+ *   - fp32 data, int64 indices, row-major, "point-major" activations: (rows = crops*points, channels).
+ */
+#ifndef DENSEFUSION_B200_H
+#define DENSEFUSION_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ------------------------------------------------------------------------------- */
+/* ABI version and a bit mask of compiled features (bit 0: tcgen05 GEMM path). */
+int df_abi_version(void);
+int df_features(void);
+
+/* ---- K4: k nearest neighbours -----------------------------------------------------------------
+ * Replaces   int knn(THCudaTensor *ref, THCudaTensor *query, THCudaLongTensor *idx)
+ *            (lib/knn/src/knn_pytorch.h:1, lib/knn/src/knn_pytorch.c:6-48)   and
+ *            void knn_device(float*, int, float*, int, int, int, float*, long*, cudaStream_t)
+ *            (lib/knn/src/knn_cuda_kernel.h:14-16).
+ * ref (batch, dim, R), query (batch, dim, Q) dim-major fp32 -> ind (batch, k, Q) int64, 1-BASED.
+ * Bit-identical indices to the reference kernels (FMA-chain distance, strict '<', lowest index on
+ * ties, NaN never inserted).  No R x Q scratch is needed (the reference's dist_dev argument is gone).
+ * dim == 3 && k == 1 is the tiled fast path; other (dim, k <= 64) use the general kernel. */
+int df_knn(const float* ref, const float* query, int64_t* ind, int batch, int dim, int R, int Q, int k,
+           void* stream);
+
+/* ---- K3: fused ADD / ADD-S loss + hypothesis scoring + argmax selection ------------------------
+ * Replaces lib/loss.py:13-70 (pred_c != NULL, hyp_points = the cloud) and lib/loss_refiner.py:12-62
+ * (pred_c == NULL, hyp_points == NULL, P == 1), batched over B crops.
+ *   pred_r (B,P,4) un-normalised (w,x,y,z); pred_t (B,P,3); pred_c (B,P); target, model_points (B,M,3);
+ *   hyp_points (B,P,3) per-hypothesis anchor (points + pred_t); points (B,N,3) cloud to re-express;
+ *   idx (B) int64 object id; bit o of sym_mask set <=> object o is symmetric; allow_sym = 0 reproduces
+ *   Loss(..., refine=True).
+ * Outputs: loss (B), dis_sel (B) distance of the selected hypothesis, which (B) its index,
+ *   new_points (B,N,3), new_target (B,M,3); dis_all (B,P), sum_u (B,P,3), sum_um (B,P,9) are the
+ *   per-hypothesis state df_loss_backward consumes.  tickets: (B) uint32, zero before the first call
+ *   (the kernel leaves it zero).  dbg_pred (B,P,M,3) / dbg_nn (B,P,M) optional (NULL in production):
+ *   the transformed model points and the 0-based nearest-target index, for parity tests. */
+int df_loss_forward(const float* pred_r, const float* pred_t, const float* pred_c, const float* target,
+                    const float* model_points, const float* hyp_points, const float* points,
+                    const int64_t* idx, unsigned long long sym_mask, int allow_sym, float w,
+                    int B, int P, int M, int N,
+                    float* dis_all, float* sum_u, float* sum_um, float* loss, float* dis_sel,
+                    int64_t* which, float* new_points, float* new_target, unsigned int* tickets,
+                    float* dbg_pred, int* dbg_nn, void* stream);
+
+/* Gradients of  sum_b g_loss[b]*loss[b] + g_dis[b]*dis_sel[b]  w.r.t. pred_r / pred_t / pred_c
+ * (what autograd derives from lib/loss.py; the kNN indices are constants).  g_loss / g_dis may be
+ * NULL (zero).  pred_c == NULL selects the refiner-loss form. */
+int df_loss_backward(const float* pred_r, const float* pred_c, const float* dis_all, const float* sum_u,
+                     const float* sum_um, const int64_t* which, const float* g_loss, const float* g_dis,
+                     float w, int B, int P, float* g_pred_r, float* g_pred_t, float* g_pred_c, void* stream);
+
+/* ---- K1 / K2: dense-fusion head and refiner building blocks -------------------------------------
+ * C[m,n] = act(sum_k A[m,k] W[n,k] + bias[n])  (Conv1d k=1 / Linear of lib/network.py:42-49, :77-91,
+ * :139-146, :176-183).  W is the torch (out,in) weight.  K % 16 == 0, N % 4 == 0.
+ *   bias_crop_stride != 0 : bias row = bias + (m / rows_per_crop) * bias_crop_stride (folded global feature)
+ *   groups > 1            : blockIdx.z batches block-diagonal layers (r/t/c towers); *_group_stride are
+ *                           element offsets between groups for A (columns), W, bias and C (columns)
+ *   pool_partial != NULL  : C is not stored; (crops, tiles, N) column sums of act(.) over crop-aligned
+ *                           128-row tiles are written instead (tiles = ceil(rows_per_crop / 128))
+ * df_gemm_fp32: exact fp32 FFMA arithmetic.  df_gemm_tc: tcgen05/TMEM tensor-core arithmetic,
+ * precision 1 = 3xTF32 (error-compensated, fp32-parity), 2 = single-pass TF32 (looser bound). */
+int df_gemm_fp32(const float* A, int lda, const float* W, int ldw, const float* bias, int bias_crop_stride,
+                 float* C, int ldc, int M, int N, int K, int relu, int rows_per_crop, int groups,
+                 long long a_group_stride, long long w_group_stride, long long bias_group_stride,
+                 long long c_group_stride, float* pool_partial, void* stream);
+int df_gemm_rows_per_pool_tile(void);
+
+/* Tensor-core form of the same contract.  W_hi / W_lo: the weight split once by df_split_tf32
+ * (hi = w & 0xffffe000, lo = w - hi), group g's rows at g*N (stacked, pitch ldw).  precision 1 = 3xTF32
+ * (needs W_lo), 2 = single-pass TF32 (W_lo may be NULL).  K % 32 == 0.  variant 0 = auto; 1/2 = N tile
+ * 128/256 with the A operand staged through TMEM; 3 = N tile 128 with A staged through shared memory
+ * (bring-up path).  Activations A and outputs stay plain fp32: the split of A happens in registers. */
+int df_gemm_tc(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
+               int bias_crop_stride, float* C, int ldc, int M, int N, int K, int relu, int rows_per_crop,
+               int groups, long long a_group_stride, long long bias_group_stride, long long c_group_stride,
+               float* pool_partial, int precision, int variant, void* stream);
+int df_split_tf32(const float* x, float* hi, float* lo, long long n, void* stream);
+
+/* emb[b,c,n] = feat[b,c,choose[b,n]]  (lib/network.py:98-102).  feat is addressed with explicit element
+ * strides so NCHW and channels-last encoders both work.  emb_pm (B*N,32) point-major and/or emb_cm
+ * (B,32,N) reference layout; either may be NULL. */
+int df_gather_embedding(const float* feat, const int64_t* choose, float* emb_pm, float* emb_cm,
+                        long long stride_b, long long stride_c, long long stride_pix, int B, int N, int HW,
+                        void* stream);
+
+/* out[row, 0:64] = relu(W (64,3) . x[row] + bias)   -- conv1 of PoseNetFeat / PoseRefineNetFeat. */
+int df_xyz_conv(const float* x, const float* W, const float* bias, float* out, int ldo, long long rows,
+                void* stream);
+
+/* g[crop, c] = (sum_tiles partial[crop, tile, c]) / rows_per_crop  -- AvgPool1d(num_points). */
+int df_pool_finish(const float* partial, float* g, int crops, int tiles, int channels, int rows_per_crop,
+                   void* stream);
+
+/* Last tower layer for the selected object only (lib/network.py:118-130 / :198-204):
+ * h (rows, ldh) holds the 128-channel r | t | c branch activations at columns 0 / 128 / 256.
+ * out_r (rows,4), out_t (rows,3), out_c (rows) = sigmoid(.).  Wc == NULL: refiner (no confidence). */
+int df_select_out(const float* h, int ldh, const float* Wr, const float* br, const float* Wt, const float* bt,
+                  const float* Wc, const float* bc, const int64_t* obj, int rows_per_crop, int num_obj,
+                  long long rows, float* out_r, float* out_t, float* out_c, void* stream);
+
+/* ---- K5: on-device pose state for the refinement loop (tools/eval_ycb.py:193-233) ----------------
+ * pose (B,7) float64 [qw qx qy qz tx ty tz]. */
+int df_select_pose(const float* pred_r, const float* pred_t, const float* pred_c, const float* points,
+                   int B, int N, double* pose, int64_t* which, void* stream);
+int df_cloud_transform(const float* cloud, const double* pose, float* out, int B, int N, void* stream);
+int df_pose_compose(double* pose, const float* r2, const float* t2, int B, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DENSEFUSION_B200_H */
