@@ -53,7 +53,28 @@ def _load():
     return lib
 
 
-lib = _load()
+class _CountingLib:
+    """Forwards to the CDLL and counts kernel-launching entry points (bench.py reports `gpu_launches`)."""
+    _NO_LAUNCH = ("df_abi_version", "df_features", "df_gemm_rows_per_pool_tile")
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        self.launches = 0
+        for name in SIGNATURES:
+            fn = getattr(cdll, name)
+            if name in self._NO_LAUNCH:
+                setattr(self, name, fn)
+            else:
+                setattr(self, name, self._counted(fn))
+
+    def _counted(self, fn):
+        def call(*args):
+            self.launches += 1
+            return fn(*args)
+        return call
+
+
+lib = _CountingLib(_load())
 
 
 class DFError(RuntimeError):

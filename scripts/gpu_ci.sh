@@ -1,0 +1,24 @@
+#!/bin/bash
+# Run on the GPU box (under gpurun): parity tests in two processes (exact-fp32 path first, tensor-core path
+# second so that a trap in the tcgen05 bring-up cannot poison the rest), smoke, short benches.
+# Everything lands in gpurun_out/.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,driver_version,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
+TC='tensor_core or 3xtf32 or tf32'
+echo "== pytest (fp32 / non tensor-core) =="
+timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout=900 -k "not ($TC)" > gpurun_out/pytest_fp32.log 2>&1
+echo "exit $?" >> gpurun_out/pytest_fp32.log
+tail -n 25 gpurun_out/pytest_fp32.log
+echo "== pytest (tensor-core) =="
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout=600 -s -k "$TC" > gpurun_out/pytest_tc.log 2>&1
+echo "exit $?" >> gpurun_out/pytest_tc.log
+tail -n 40 gpurun_out/pytest_tc.log
+echo "== smoke =="
+timeout 600 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "exit $?" >> gpurun_out/smoke.log
+tail -n 5 gpurun_out/smoke.log
+echo "== bench fp32 =="
+timeout 900 python bench.py --precision fp32 --steps 5 --warmup 3 > gpurun_out/bench_fp32.json 2> gpurun_out/bench_fp32.err; echo "exit $?" >> gpurun_out/bench_fp32.err
+tail -c 3000 gpurun_out/bench_fp32.json; tail -n 5 gpurun_out/bench_fp32.err
+echo "== bench 3xtf32 =="
+timeout 900 python bench.py --precision 3xtf32 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_3xtf32.json 2> gpurun_out/bench_3xtf32.err; echo "exit $?" >> gpurun_out/bench_3xtf32.err
+tail -c 3000 gpurun_out/bench_3xtf32.json; tail -n 5 gpurun_out/bench_3xtf32.err

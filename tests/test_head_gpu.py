@@ -1,0 +1,143 @@
+"""K1/K2 parity: GEMM building blocks, the fused dense-fusion head and the refiner against the oracle
+(fp32 torch-CPU restatement of lib/network.py) and the reference's own outputs (tests/golden)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from densefusion_b200 import synth
+from oracle import df_oracle as O
+from util import build_nets, rel
+
+pytestmark = pytest.mark.gpu
+
+# stated bounds per arithmetic mode (max-abs error / max-abs value)
+TOL = {"fp32": 1e-4, "3xtf32": 1e-4, "tf32": 5e-3}
+
+
+def _ref_linear(x, w, b, relu):
+    y = x.double() @ w.double().t() + (0 if b is None else b.double())
+    return torch.relu(y) if relu else y
+
+
+@pytest.mark.parametrize("M,N,K", [(500, 64, 32), (1000, 128, 64), (4000, 512, 256), (777, 1920, 384),
+                                   (8, 1920, 1024), (33, 1024, 1024), (129, 128, 16)])
+def test_gemm_fp32_vs_float64(M, N, K):
+    from densefusion_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    y = ops.linear(x.cuda(), w.cuda(), b.cuda(), relu=True)
+    assert rel(y, _ref_linear(x, w, b, True)) < 2e-6
+
+
+@pytest.mark.parametrize("variant", [3, 1, 2])
+@pytest.mark.parametrize("precision", ["3xtf32", "tf32"])
+def test_gemm_tensor_core_variants(variant, precision):
+    """variant 3: A staged through shared memory; 1/2: A through TMEM with N tile 128/256."""
+    from densefusion_b200 import ops
+    g = torch.Generator().manual_seed(variant)
+    M, N, K = 1000, 512, 384
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    ops.TC_VARIANT = variant
+    try:
+        y = ops.linear(x.cuda(), w.cuda(), b.cuda(), relu=False, precision=precision)
+        torch.cuda.synchronize()
+    finally:
+        ops.TC_VARIANT = 0
+    err = rel(y, _ref_linear(x, w, b, False))
+    print(f"tc variant {variant} {precision}: rel err {err:.3e}")
+    assert err < (3e-6 if precision == "3xtf32" else 3e-3)
+
+
+def test_gemm_tensor_core_identity_layout():
+    """A = structured, W = identity: any layout / swizzle / lane mix-up shows as a permutation."""
+    from densefusion_b200 import ops
+    M, K = 256, 128
+    x = (torch.arange(M * K, dtype=torch.float32).view(M, K) % 4093) / 64.0
+    w = torch.eye(K)
+    for variant in (3, 1):
+        ops.TC_VARIANT = variant
+        try:
+            y = ops.linear(x.cuda(), w.cuda(), None, precision="3xtf32")
+            torch.cuda.synchronize()
+        finally:
+            ops.TC_VARIANT = 0
+        assert torch.equal(y.cpu(), x), f"variant {variant}: first bad index {(y.cpu() != x).nonzero()[:4].tolist()}"
+
+
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "tf32"])
+@pytest.mark.parametrize("n,o,B", [(500, 21, 3), (1000, 13, 2)])
+def test_head_vs_oracle(precision, n, o, B):
+    est, _, est_sd, _ = build_nets(n, o, seed=5)
+    est.precision = precision
+    g = torch.Generator().manual_seed(n + B)
+    x = torch.randn(B, n, 3, generator=g) * 0.05 + torch.tensor([0.0, 0.0, 0.8])
+    emb = torch.cat([synth.synth_embedding(100 + i, n) for i in range(B)], 0)            # (B,32,N)
+    obj = torch.randint(0, o, (B, 1), generator=g)
+    emb_pm = emb.permute(0, 2, 1).reshape(B * n, 32).contiguous()
+    r, t, c = est.head(x.cuda(), emb_pm.cuda(), obj.cuda())
+    worst = 0.0
+    for b in range(B):
+        with torch.no_grad():
+            rr, tt, cc = O.posenet_head(est_sd, x[b:b + 1], emb[b:b + 1], obj[b:b + 1], o)
+        errs = (rel(r[b], rr[0]), rel(t[b], tt[0]), rel(c[b], cc[0]))
+        worst = max(worst, *errs)
+        assert max(errs) < TOL[precision], f"{precision} crop {b}: {errs}"
+        if precision != "tf32":
+            margin = torch.sort(cc.view(-1), descending=True)[0]
+            if float(margin[0] - margin[1]) > 1e-5:
+                assert int(torch.argmax(c[b].view(-1))) == int(torch.argmax(cc.view(-1)))
+    print(f"head {precision} n={n}: worst rel err {worst:.3e}")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32"])
+def test_refiner_vs_oracle(precision):
+    n, o, B = 500, 21, 4
+    _, ref, _, ref_sd = build_nets(n, o, seed=6)
+    ref.precision = precision
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, n, 3, generator=g) * 0.05
+    emb = torch.cat([synth.synth_embedding(200 + i, n) for i in range(B)], 0)
+    obj = torch.randint(0, o, (B, 1), generator=g)
+    emb_pm = emb.permute(0, 2, 1).reshape(B * n, 32).contiguous()
+    r, t = ref.refine(x.cuda(), emb_pm.cuda(), obj.cuda())
+    for b in range(B):
+        with torch.no_grad():
+            rr, tt = O.refiner_forward(ref_sd, x[b:b + 1], emb[b:b + 1], obj[b:b + 1], o)
+        assert rel(r[b], rr[0]) < TOL[precision] and rel(t[b], tt[0]) < TOL[precision]
+    # reference-contract forward (bs=1, channel-major emb)
+    r1, t1 = ref(x[0:1].cuda(), emb[0:1].cuda(), obj[0:1].cuda())
+    assert tuple(r1.shape) == (1, 4) and tuple(t1.shape) == (1, 3)
+    assert torch.equal(r1[0], r[0]) or rel(r1[0], r[0]) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["c0_linemod_add", "c1_ycb_adds"])
+def test_posenet_dropin_vs_reference_golden(name):
+    """Full drop-in PoseNet.forward (torch/cuDNN encoder in fp32 + fused head) on the golden inputs."""
+    g = golden(name)
+    case, n, o, m, h, w, obj, seed, iters = [int(v) for v in g["meta"]]
+    est, ref, _, _ = build_nets(n, o, seed)
+    d = {k: v.cuda() for k, v in synth.synth_crop(case, n, m, o, (h, w), obj).items()}
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        r, t, c, emb = est(d["img"], d["points"], d["choose"], d["idx"])
+    assert tuple(r.shape) == (1, n, 4) and tuple(t.shape) == (1, n, 3) and tuple(c.shape) == (1, n, 1)
+    assert tuple(emb.shape) == (1, 32, n) and not emb.requires_grad
+    assert rel(emb, g["emb"]) < 1e-4
+    assert rel(r, g["pred_r"]) < 1e-4 and rel(t, g["pred_t"]) < 1e-4 and rel(c, g["pred_c"]) < 1e-4
+    assert int(torch.argmax(c.view(-1))) == int(g["which_max"])
+    # refiner on the reference's own training-chain inputs
+    emb_ref = torch.from_numpy(g["emb"]).cuda()
+    pts = torch.from_numpy(g["new_points"]).cuda()
+    with torch.no_grad():
+        rr, tt = ref(pts, emb_ref, d["idx"])
+    assert rel(rr, g["train_r0"]) < 1e-4 and rel(tt, g["train_t0"]) < 1e-4
+
+
+def test_forward_refuses_autograd_instead_of_falling_back():
+    from densefusion_b200.lib.network import PoseRefineNet
+    net = PoseRefineNet(500, 13).cuda()
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 500, 3, device="cuda"), torch.zeros(1, 32, 500, device="cuda"),
+            torch.zeros(1, 1, dtype=torch.long, device="cuda"))
