@@ -392,6 +392,263 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent, fully warp-specialised variant (the production path): one CTA per SM loops over output tiles.
+//   warp 0      TMA producer (W_hi / W_lo stages)
+//   warp 1      MMA issuer, TMEM owner
+//   warps 2-5   A stagers, even k-blocks   } global -> registers -> hi/lo split -> tcgen05.st (TMEM A stages)
+//   warps 6-9   A stagers, odd k-blocks    } two groups so one group's load latency hides behind the other
+//   warps 10-13 epilogue: tcgen05.ld -> bias/ReLU -> shared-memory transpose -> 128 B-per-row coalesced stores,
+//               or the column-pool butterfly
+// TMEM: two 128-column accumulators (the epilogue of tile i overlaps the MMAs of tile i+1) + 4 A stages x 64.
+// ------------------------------------------------------------------------------------------------
+constexpr int P_BN = 128;
+constexpr int P_THREADS = 448;
+constexpr int P_W_STAGES = 5;
+constexpr int P_A_STAGES = 4;
+constexpr int P_W_TILE = P_BN * BK * 4;                  // 16 KB (one of hi / lo)
+constexpr int P_STAGE_PITCH = 36;                        // floats; 16 B aligned, conflict-free float4 rows
+constexpr int P_SMEM_W = P_W_STAGES * 2 * P_W_TILE;      // 160 KB
+constexpr int P_SMEM_STAGE = 4 * 32 * P_STAGE_PITCH * 4; // 18 KB: one 32x32 transpose tile per epilogue warp
+constexpr int P_SMEM_POOL = 2 * 4 * P_BN * 4;            // 4 KB, double buffered by accumulator
+constexpr int P_SMEM_TOTAL = 1024 + P_SMEM_W + P_SMEM_STAGE + P_SMEM_POOL + 512;
+constexpr int P_TMEM_A0 = 2 * P_BN;                      // A stages start after the two accumulators
+
+struct TileCoord {
+    int g, n0, row0, rows_valid, crop, tile_in_crop;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t, int m_tiles, int n_tiles)
+{
+    TileCoord c;
+    const int per_group = m_tiles * n_tiles;
+    c.g = t / per_group;
+    const int rem = t - c.g * per_group;
+    const int mt = rem / n_tiles;
+    c.n0 = (rem - mt * n_tiles) * P_BN;
+    c.crop = 0; c.tile_in_crop = 0;
+    if (p.pool_partial) {
+        c.crop = mt / p.tiles_per_crop;
+        c.tile_in_crop = mt - c.crop * p.tiles_per_crop;
+        c.row0 = c.crop * p.rows_per_crop + c.tile_in_crop * BM;
+        c.rows_valid = min(BM, p.rows_per_crop - c.tile_in_crop * BM);
+    } else {
+        c.row0 = mt * BM;
+        c.rows_valid = min(BM, p.M - c.row0);
+    }
+    return c;
+}
+
+__global__ void __launch_bounds__(P_THREADS, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
+                          const TcParams p, const int m_tiles, const int n_tiles, const int total_tiles)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_w = smem;
+    float* s_stage = reinterpret_cast<float*>(smem + P_SMEM_W);
+    float* s_pool = reinterpret_cast<float*>(smem + P_SMEM_W + P_SMEM_STAGE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_SMEM_W + P_SMEM_STAGE + P_SMEM_POOL);
+    uint64_t* w_full = bars;                        // [8]
+    uint64_t* w_empty = bars + 8;                   // [8]
+    uint64_t* a_full = bars + 16;                   // [4]
+    uint64_t* a_empty = bars + 20;                  // [4]
+    uint64_t* acc_full = bars + 24;                 // [2]
+    uint64_t* acc_empty = bars + 26;                // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = p.K / BK;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < P_W_STAGES; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
+        for (int i = 0; i < P_A_STAGES; ++i) { mbar_init(a_full + i, 4); mbar_init(a_empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------- TMA producer -------------------------------
+        if (lane == 0) {
+            const uint32_t bytes = (p.precise ? 2u : 1u) * P_W_TILE;
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const TileCoord c = decode_tile(p, t, m_tiles, n_tiles);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % P_W_STAGES;
+                    mbar_wait(w_empty + s, ((it / P_W_STAGES) & 1) ^ 1);
+                    mbar_expect_tx(w_full + s, bytes);
+                    uint8_t* dst = s_w + (size_t)s * 2 * P_W_TILE;
+                    tma_load_2d(&tm_whi, dst, w_full + s, kb * BK, c.g * p.N + c.n0);
+                    if (p.precise) tma_load_2d(&tm_wlo, dst + P_W_TILE, w_full + s, kb * BK, c.g * p.N + c.n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------- MMA issuer ---------------------------------
+        if (lane == 0) {
+            const uint32_t idesc = tf32_instr_desc(P_BN);
+            uint32_t it = 0, ti = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+                const uint32_t ab = ti & 1;
+                mbar_wait(acc_empty + ab, ((ti >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + ab * P_BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % P_W_STAGES, sa = it % P_A_STAGES;
+                    mbar_wait(w_full + s, (it / P_W_STAGES) & 1);
+                    mbar_wait(a_full + sa, (it / P_A_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t w_hi = smem_u32(s_w + (size_t)s * 2 * P_W_TILE);
+                    const uint32_t w_lo = w_hi + P_W_TILE;
+#pragma unroll
+                    for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                        const uint32_t koff = ks * UMMA_K * 4;
+                        const uint64_t bhi = sw128_desc(w_hi + koff), blo = sw128_desc(w_lo + koff);
+                        const uint32_t a_hi = tmem_base + P_TMEM_A0 + sa * 2 * BK + ks * UMMA_K;
+                        umma_ts(acc, a_hi, bhi, idesc, (kb | ks) != 0);
+                        if (p.precise) { umma_ts(acc, a_hi + BK, bhi, idesc, 1u); umma_ts(acc, a_hi, blo, idesc, 1u); }
+                    }
+                    umma_commit(w_empty + s);
+                    umma_commit(a_empty + sa);
+                }
+                umma_commit(acc_full + ab);
+            }
+        }
+    } else if (warp < 10) {
+        // ------------------------------- A stagers (two groups) ----------------------
+        const int grp = (warp - 2) >> 2;           // 0: even k-block iterations, 1: odd
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        // flat iteration space over (tile, kb); this group takes it = grp, grp+2, ...
+        const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const uint32_t total_it = (uint32_t)my_tiles * nkb;
+        uint32_t cur[32];
+        auto issue_loads = [&](uint32_t it) {
+            const int ti = it / nkb, kb = it - ti * nkb;
+            const TileCoord c = decode_tile(p, blockIdx.x + ti * gridDim.x, m_tiles, n_tiles);
+            const bool ok = r < c.rows_valid;
+            const float* src = p.A + c.g * p.a_gs + (size_t)(c.row0 + (ok ? r : 0)) * p.lda + kb * BK;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 v = ok ? __ldg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                cur[i * 4 + 0] = __float_as_uint(v.x); cur[i * 4 + 1] = __float_as_uint(v.y);
+                cur[i * 4 + 2] = __float_as_uint(v.z); cur[i * 4 + 3] = __float_as_uint(v.w);
+            }
+        };
+        if ((uint32_t)grp < total_it) issue_loads(grp);
+        for (uint32_t it = grp; it < total_it; it += 2) {
+            const int sa = it % P_A_STAGES;
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                hi[i] = p.precise ? (cur[i] & 0xffffe000u) : cur[i];
+                lo[i] = __float_as_uint(__uint_as_float(cur[i]) - __uint_as_float(hi[i]));
+            }
+            if (it + 2 < total_it) issue_loads(it + 2);
+            mbar_wait(a_empty + sa, ((it / P_A_STAGES) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t ta = tmem_base + lane_base + P_TMEM_A0 + sa * 2 * BK;
+            tmem_st32(ta, hi);
+            if (p.precise) tmem_st32(ta + BK, lo);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full + sa);
+        }
+    } else {
+        // ------------------------------- epilogue ------------------------------------
+        const int q = warp & 3;
+        const int ew = warp - 10;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        float* stage = s_stage + ew * 32 * P_STAGE_PITCH;
+        uint32_t ti = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+            const uint32_t ab = ti & 1;
+            const TileCoord c = decode_tile(p, t, m_tiles, n_tiles);
+            const int r = q * 32 + lane;
+            const bool row_ok = r < c.rows_valid;
+            const int row = c.row0 + r;
+            const float* bias = p.bias ? p.bias + c.g * p.bias_gs : nullptr;
+            if (bias && p.bias_crop_stride) bias += (size_t)((row_ok ? row : c.row0) / p.rows_per_crop) * p.bias_crop_stride;
+            float* pool = s_pool + ab * 4 * P_BN;
+            mbar_wait(acc_full + ab, (ti >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int ch = 0; ch < P_BN / 32; ++ch) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + lane_base + ab * P_BN + ch * 32, v);
+                const int col = c.n0 + ch * 32;
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float x = __uint_as_float(v[i]);
+                    if (bias && col + i < p.N) x += __ldg(bias + col + i);
+                    if (p.relu) x = fmaxf(x, 0.0f);
+                    f[i] = x;
+                }
+                if (p.pool_partial) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = row_ok ? f[i] : 0.0f;
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const float send = up ? f[i] : f[i + off];
+                            const float keep = up ? f[i + off] : f[i];
+                            f[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    pool[q * P_BN + ch * 32 + lane] = f[0];
+                } else {
+                    // transpose through shared memory: lane == row on the way in, 8 lanes == one 128 B row segment out
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(stage + lane * P_STAGE_PITCH + j * 4) =
+                            make_float4(f[j * 4], f[j * 4 + 1], f[j * 4 + 2], f[j * 4 + 3]);
+                    __syncwarp();
+                    float* cbase = p.C + c.g * p.c_gs + (size_t)(c.row0 + q * 32) * p.ldc + col;
+                    const int rr = lane >> 3, cc = (lane & 7) * 4;
+#pragma unroll
+                    for (int ps = 0; ps < 8; ++ps) {
+                        const int lr = ps * 4 + rr;
+                        if (q * 32 + lr < c.rows_valid && col + cc < p.N) {
+                            const float4 o = *reinterpret_cast<const float4*>(stage + lr * P_STAGE_PITCH + cc);
+                            *reinterpret_cast<float4*>(cbase + (size_t)lr * p.ldc + cc) = o;
+                        }
+                    }
+                }
+            }
+            // all TMEM reads of this accumulator are complete (tcgen05.wait::ld in tmem_ld32): hand it back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + ab);
+            if (p.pool_partial) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int tt = threadIdx.x - 320;
+                if (c.n0 + tt < p.N) {
+                    const float s = ((pool[tt] + pool[P_BN + tt]) + pool[2 * P_BN + tt]) + pool[3 * P_BN + tt];
+                    p.pool_partial[((size_t)c.crop * p.tiles_per_crop + c.tile_in_crop) * p.N + c.n0 + tt] = s;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -442,6 +699,25 @@ int launch_tc(const CUtensorMap& mhi, const CUtensorMap& mlo, const TcParams& p,
     return 0;
 }
 
+int launch_persistent(const CUtensorMap& mhi, const CUtensorMap& mlo, const TcParams& p, int groups, cudaStream_t s)
+{
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaError_t e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(gemm_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_TOTAL);
+        if (e != cudaSuccess) { num_sms = 0; return (int)e; }
+    }
+    const int m_tiles = p.pool_partial ? (p.M / p.rows_per_crop) * p.tiles_per_crop : (p.M + BM - 1) / BM;
+    const int n_tiles = (p.N + P_BN - 1) / P_BN;
+    const int total = m_tiles * n_tiles * groups;
+    const int grid = total < num_sms ? total : num_sms;
+    gemm_tc_persistent_kernel<<<grid, P_THREADS, P_SMEM_TOTAL, s>>>(mhi, mlo, p, m_tiles, n_tiles, total);
+    return 0;
+}
+
 __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -486,9 +762,10 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
     p.pool_partial = pool_partial;
     p.tiles_per_crop = pool_partial ? (p.rows_per_crop + BM - 1) / BM : 0;
 
-    // variant: 0 = auto (A through TMEM; BN 256 when N allows), 1 = BN128/TMEM-A, 2 = BN256/TMEM-A, 3 = BN128/smem-A
+    // variant: 0 = auto (persistent kernel); 1 = BN128/TMEM-A, 2 = BN256/TMEM-A, 3 = BN128/smem-A (one tile per CTA,
+    // bring-up kernels); 4 = persistent warp-specialised kernel (production)
     int v = variant;
-    if (v == 0) v = (N % 256 == 0 && groups == 1) ? 2 : 1;
+    if (v == 0) v = 4;
     const int bn = v == 2 ? 256 : 128;
     if (v == 2 && groups > 1 && N % 256) return DF_ERR_UNSUPPORTED;
     CUtensorMap mhi, mlo;
@@ -500,6 +777,7 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
     if (v == 1) rc = launch_tc<128, true>(mhi, mlo, p, groups, s);
     else if (v == 2) rc = launch_tc<256, true>(mhi, mlo, p, groups, s);
     else if (v == 3) rc = launch_tc<128, false>(mhi, mlo, p, groups, s);
+    else if (v == 4) rc = launch_persistent(mhi, mlo, p, groups, s);
     else return DF_ERR_ARG;
     if (rc) return rc;
     DF_RETURN_LAST_ERROR();

@@ -29,7 +29,7 @@ knn1_d3_kernel(const float* __restrict__ ref, const float* __restrict__ query, i
 
     const int q0 = blockIdx.x * (KNN_THREADS * QPT) + threadIdx.x;
     float qx[QPT], qy[QPT], qz[QPT], best[QPT];
-    int arg[QPT];
+    int chunk[QPT];
     // row 0 seeds the minimum exactly like `max_dist = p_dist[0]` (knn_cuda_kernel.cu:122)
     const float r0x = __ldg(ref), r0y = __ldg(ref + R), r0z = __ldg(ref + 2 * (size_t)R);
 #pragma unroll
@@ -40,29 +40,24 @@ knn1_d3_kernel(const float* __restrict__ ref, const float* __restrict__ query, i
         qy[i] = ok ? __ldg(query + Q + q) : 0.0f;
         qz[i] = ok ? __ldg(query + 2 * (size_t)Q + q) : 0.0f;
         best[i] = df::ref_ssd3(r0x, r0y, r0z, qx[i], qy[i], qz[i]);
-        arg[i] = 0;
+        chunk[i] = 0;
     }
     for (int base = 0; base < R; base += KNN_TILE) {
         const int n = min(KNN_TILE, R - base);
+        const int n_pad = (n + df::NN_CHUNK - 1) / df::NN_CHUNK * df::NN_CHUNK;
         __syncthreads();
-        for (int r = threadIdx.x; r < n; r += KNN_THREADS)
-            s_ref[r] = make_float4(__ldg(ref + base + r), __ldg(ref + R + base + r),
-                                   __ldg(ref + 2 * (size_t)R + base + r), 0.0f);
+        for (int r = threadIdx.x; r < n_pad; r += KNN_THREADS)
+            s_ref[r] = r < n ? make_float4(__ldg(ref + base + r), __ldg(ref + R + base + r),
+                                           __ldg(ref + 2 * (size_t)R + base + r), 0.0f)
+                             : make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.0f);
         __syncthreads();
-#pragma unroll 4
-        for (int r = 0; r < n; ++r) {
-            const float4 p = s_ref[r];
-#pragma unroll
-            for (int i = 0; i < QPT; ++i) {
-                const float d = df::ref_ssd3(p.x, p.y, p.z, qx[i], qy[i], qz[i]);
-                if (d < best[i]) { best[i] = d; arg[i] = base + r; }
-            }
-        }
+        df::nn_scan_tile<QPT>(s_ref, n_pad, base, qx, qy, qz, best, chunk);
     }
 #pragma unroll
     for (int i = 0; i < QPT; ++i) {
         const int q = q0 + i * KNN_THREADS;
-        if (q < Q) ind[q] = (int64_t)arg[i] + 1;   // 1-based (knn_cuda_kernel.cu:123,163)
+        if (q < Q)   // 1-based (knn_cuda_kernel.cu:123,163)
+            ind[q] = (int64_t)df::nn_resolve<false>(ref, R, chunk[i], best[i], qx[i], qy[i], qz[i]) + 1;
     }
 }
 

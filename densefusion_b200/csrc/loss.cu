@@ -104,20 +104,16 @@ loss_forward_kernel(const LossParams a)
         if (sym) {
             for (int base = 0; base < M; base += LOSS_TILE) {
                 const int n = min(LOSS_TILE, M - base);
+                const int n_pad = (n + df::NN_CHUNK - 1) / df::NN_CHUNK * df::NN_CHUNK;
                 __syncthreads();
-                for (int r = tid; r < n; r += LOSS_THREADS)
-                    s_tgt[r] = make_float4(tgt[(base + r) * 3], tgt[(base + r) * 3 + 1], tgt[(base + r) * 3 + 2], 0.0f);
+                for (int r = tid; r < n_pad; r += LOSS_THREADS)
+                    s_tgt[r] = r < n ? make_float4(tgt[(base + r) * 3], tgt[(base + r) * 3 + 1], tgt[(base + r) * 3 + 2], 0.0f)
+                                     : make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, 0.0f);
                 __syncthreads();
-#pragma unroll 4
-                for (int r = 0; r < n; ++r) {
-                    const float4 t = s_tgt[r];
-#pragma unroll
-                    for (int i = 0; i < LOSS_QPT; ++i) {
-                        const float d = df::ref_ssd3(t.x, t.y, t.z, px[i], py[i], pz[i]);
-                        if (d < best[i]) { best[i] = d; arg[i] = base + r; }
-                    }
-                }
+                df::nn_scan_tile<LOSS_QPT>(s_tgt, n_pad, base, px, py, pz, best, arg);      // arg = winning chunk
             }
+#pragma unroll
+            for (int i = 0; i < LOSS_QPT; ++i) arg[i] = df::nn_resolve<true>(tgt, M, arg[i], best[i], px[i], py[i], pz[i]);
         }
 #pragma unroll
         for (int i = 0; i < LOSS_QPT; ++i) {

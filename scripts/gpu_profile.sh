@@ -2,7 +2,7 @@
 # ncu evidence (launch list + one full capture per hot kernel) and encoder-variant timings.
 mkdir -p gpurun_out
 timeout 600 python scripts/encoder_variants.py > gpurun_out/encoder_variants.log 2>&1; tail -n 6 gpurun_out/encoder_variants.log
-BENCH="python bench.py --precision 3xtf32 --steps 2 --warmup 3 --frames 4 --no-graph --no-cpu-baseline --no-extras"
+BENCH="env DF_CUDNN_BENCHMARK=0 python bench.py --precision 3xtf32 --steps 2 --warmup 3 --frames 4 --no-graph --no-cpu-baseline --no-extras"
 $BENCH > gpurun_out/plain_bench.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/ncu_bench.log 2>&1
 echo "launch list rc=$?"; wc -l gpurun_out/launches.csv

@@ -30,10 +30,10 @@ def test_gemm_fp32_vs_float64(M, N, K):
     assert rel(y, _ref_linear(x, w, b, True)) < 2e-6
 
 
-@pytest.mark.parametrize("variant", [3, 1, 2])
+@pytest.mark.parametrize("variant", [3, 1, 2, 4])
 @pytest.mark.parametrize("precision", ["3xtf32", "tf32"])
 def test_gemm_tensor_core_variants(variant, precision):
-    """variant 3: A staged through shared memory; 1/2: A through TMEM with N tile 128/256."""
+    """variant 3: A staged through shared memory; 1/2: A through TMEM with N tile 128/256; 4: persistent kernel."""
     from densefusion_b200 import ops
     g = torch.Generator().manual_seed(variant)
     M, N, K = 1000, 512, 384
@@ -55,7 +55,7 @@ def test_gemm_tensor_core_identity_layout():
     M, K = 256, 128
     x = (torch.arange(M * K, dtype=torch.float32).view(M, K) % 4093) / 64.0
     w = torch.eye(K)
-    for variant in (3, 1):
+    for variant in (3, 1, 4):
         ops.TC_VARIANT = variant
         try:
             y = ops.linear(x.cuda(), w.cuda(), None, precision="3xtf32")
@@ -63,6 +63,58 @@ def test_gemm_tensor_core_identity_layout():
         finally:
             ops.TC_VARIANT = 0
         assert torch.equal(y.cpu(), x), f"variant {variant}: first bad index {(y.cpu() != x).nonzero()[:4].tolist()}"
+
+
+@pytest.mark.parametrize("variant", [4, 1])
+def test_gemm_tensor_core_epilogues_match_fp32_kernel(variant):
+    """per-crop bias, grouped (block-diagonal) and column-pool epilogues: 3xtf32 kernel vs the exact-fp32 kernel."""
+    from densefusion_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    crops, n = 5, 500
+    rows = crops * n
+
+    def run(precision, fn):
+        ops.TC_VARIANT = variant
+        try:
+            return fn(precision)
+        finally:
+            ops.TC_VARIANT = 0
+
+    # per-crop bias
+    A = torch.randn(rows, 384, generator=g).cuda()
+    W = ops.SplitWeight((torch.randn(1920, 384, generator=g) / 20).cuda())
+    bias = torch.randn(crops, 1920, generator=g).cuda()
+
+    def percrop(prec):
+        C = torch.empty(rows, 1920, device="cuda")
+        ops.gemm(A, W, bias, C, M=rows, N=1920, K=384, lda=384, ldw=384, ldc=1920, relu=True, precision=prec,
+                 bias_crop_stride=1920, rows_per_crop=n)
+        return C
+    assert rel(run("3xtf32", percrop), percrop("fp32")) < 1e-5
+    # grouped towers
+    A3 = torch.randn(rows, 1920, generator=g).cuda()
+    W3 = ops.SplitWeight((torch.randn(3, 256, 640, generator=g) / 25).cuda())
+    b3 = torch.randn(768, generator=g).cuda()
+
+    def grouped(prec):
+        C = torch.zeros(rows, 768, device="cuda")
+        ops.gemm(A3, W3, b3, C, M=rows, N=256, K=640, lda=1920, ldw=640, ldc=768, relu=True, precision=prec, groups=3,
+                 a_gs=640, w_gs=256 * 640, bias_gs=256, c_gs=256)
+        return C
+    assert rel(run("3xtf32", grouped), grouped("fp32")) < 1e-5
+    # pooled (crop-aligned tiles, 500 = 3*128 + 116 rows)
+    A6 = torch.randn(rows, 512, generator=g).cuda()
+    W6 = ops.SplitWeight((torch.randn(1024, 512, generator=g) / 22).cuda())
+    b6 = torch.randn(1024, generator=g).cuda()
+
+    def pooled(prec):
+        part = torch.zeros(crops, 4, 1024, device="cuda")
+        ops.gemm(A6, W6, b6, None, M=rows, N=1024, K=512, lda=512, ldw=512, ldc=0, relu=True, precision=prec,
+                 rows_per_crop=n, pool_partial=part)
+        return part.sum(1)
+    got, want = run("3xtf32", pooled), pooled("fp32")
+    ref64 = torch.relu(A6.double() @ W6.w.double().t() + b6.double()).view(crops, n, 1024).sum(1)
+    assert rel(got, ref64) < 1e-5 and rel(want, ref64) < 1e-5
 
 
 @pytest.mark.parametrize("precision", ["fp32", "3xtf32", "tf32"])
