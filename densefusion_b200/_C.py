@@ -30,6 +30,7 @@ SIGNATURES = {
     "df_gemm_rows_per_pool_tile": [],
     "df_gemm_tc": [_p, _i, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _p, _i, _i, _p],
     "df_split_tf32": [_p, _p, _p, _ll, _p],
+    "df_upsample_bilinear": [_p, _p, _ll, _i, _i, _i, _i, _i, _p],
     "df_gather_embedding": [_p, _p, _p, _p, _ll, _ll, _ll, _i, _i, _i, _p],
     "df_xyz_conv": [_p, _p, _p, _p, _i, _ll, _p],
     "df_pool_finish": [_p, _p, _i, _i, _i, _i, _p],

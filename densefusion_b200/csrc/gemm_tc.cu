@@ -75,6 +75,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
+// One elected lane of a converged warp.  Issuing tcgen05.mma / TMA from an elect.sync region (instead of a
+// divergent `lane == 0` branch) lets nvcc keep descriptors in uniform registers: ~15 SASS instructions per
+// k-block instead of ~200 (waterfall loops), which was the bottleneck of the first persistent kernel
+// (profiles/r1_call4_*: issue thread saturated, tensor pipe 44%).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -473,50 +483,53 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_whi, const __gr
 
     if (warp == 0) {
         // ------------------------------- TMA producer -------------------------------
-        if (lane == 0) {
-            const uint32_t bytes = (p.precise ? 2u : 1u) * P_W_TILE;
-            uint32_t it = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const TileCoord c = decode_tile(p, t, m_tiles, n_tiles);
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % P_W_STAGES;
-                    mbar_wait(w_empty + s, ((it / P_W_STAGES) & 1) ^ 1);
+        const uint32_t bytes = (p.precise ? 2u : 1u) * P_W_TILE;
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const TileCoord c = decode_tile(p, t, m_tiles, n_tiles);
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % P_W_STAGES;
+                mbar_wait(w_empty + s, ((it / P_W_STAGES) & 1) ^ 1);
+                if (elect_one()) {
                     mbar_expect_tx(w_full + s, bytes);
                     uint8_t* dst = s_w + (size_t)s * 2 * P_W_TILE;
                     tma_load_2d(&tm_whi, dst, w_full + s, kb * BK, c.g * p.N + c.n0);
                     if (p.precise) tma_load_2d(&tm_wlo, dst + P_W_TILE, w_full + s, kb * BK, c.g * p.N + c.n0);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
         // ------------------------------- MMA issuer ---------------------------------
-        if (lane == 0) {
-            const uint32_t idesc = tf32_instr_desc(P_BN);
-            uint32_t it = 0, ti = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
-                const uint32_t ab = ti & 1;
-                mbar_wait(acc_empty + ab, ((ti >> 1) & 1) ^ 1);
+        // the whole warp walks the pipeline (uniform control flow); one elected lane issues
+        const uint32_t idesc = tf32_instr_desc(P_BN);
+        uint32_t it = 0, ti = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+            const uint32_t ab = ti & 1;
+            mbar_wait(acc_empty + ab, ((ti >> 1) & 1) ^ 1);
+            const uint32_t acc = tmem_base + ab * P_BN;
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % P_W_STAGES, sa = it % P_A_STAGES;
+                mbar_wait(w_full + s, (it / P_W_STAGES) & 1);
+                mbar_wait(a_full + sa, (it / P_A_STAGES) & 1);
                 tc_fence_after();
-                const uint32_t acc = tmem_base + ab * P_BN;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % P_W_STAGES, sa = it % P_A_STAGES;
-                    mbar_wait(w_full + s, (it / P_W_STAGES) & 1);
-                    mbar_wait(a_full + sa, (it / P_A_STAGES) & 1);
-                    tc_fence_after();
+                if (elect_one()) {
                     const uint32_t w_hi = smem_u32(s_w + (size_t)s * 2 * P_W_TILE);
-                    const uint32_t w_lo = w_hi + P_W_TILE;
+                    const uint64_t bhi0 = sw128_desc(w_hi), blo0 = sw128_desc(w_hi + P_W_TILE);
+                    const uint32_t a0 = tmem_base + P_TMEM_A0 + sa * 2 * BK;
 #pragma unroll
                     for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-                        const uint32_t koff = ks * UMMA_K * 4;
-                        const uint64_t bhi = sw128_desc(w_hi + koff), blo = sw128_desc(w_lo + koff);
-                        const uint32_t a_hi = tmem_base + P_TMEM_A0 + sa * 2 * BK + ks * UMMA_K;
+                        // +32 B along K inside the swizzle atom == +2 in the descriptor's (addr >> 4) field
+                        const uint64_t bhi = bhi0 + (uint64_t)(ks * 2), blo = blo0 + (uint64_t)(ks * 2);
+                        const uint32_t a_hi = a0 + ks * UMMA_K;
                         umma_ts(acc, a_hi, bhi, idesc, (kb | ks) != 0);
                         if (p.precise) { umma_ts(acc, a_hi + BK, bhi, idesc, 1u); umma_ts(acc, a_hi, blo, idesc, 1u); }
                     }
                     umma_commit(w_empty + s);
                     umma_commit(a_empty + sa);
+                    if (kb == nkb - 1) umma_commit(acc_full + ab);
                 }
-                umma_commit(acc_full + ab);
+                __syncwarp();
             }
         }
     } else if (warp < 10) {

@@ -9,6 +9,16 @@ import torch.nn.functional as F
 from . import extractors
 
 
+def _upsample(x, size, align_corners: bool):
+    """Bilinear resize.  CUDA inference tensors go through df_upsample_bilinear (every output element is a thread;
+    torch's NCHW kernel loops over batch x channels inside one thread per output pixel and dominated the encoder).
+    Anything that needs autograd, a CPU tensor or a non-fp32 dtype stays on torch."""
+    if x.is_cuda and x.dtype == torch.float32 and not (torch.is_grad_enabled() and x.requires_grad):
+        from .. import ops
+        return ops.upsample_bilinear(x, size, align_corners)
+    return F.interpolate(x, size=size, mode="bilinear", align_corners=align_corners)
+
+
 class PSPModule(nn.Module):
     def __init__(self, features: int, out_features: int = 1024, sizes=(1, 2, 3, 6)):
         super().__init__()
@@ -20,7 +30,7 @@ class PSPModule(nn.Module):
 
     def forward(self, feats):
         hw = feats.shape[2:]
-        pyramid = [F.interpolate(stage(feats), size=hw, mode="bilinear", align_corners=False) for stage in self.stages]
+        pyramid = [_upsample(stage(feats), hw, False) for stage in self.stages]
         return F.relu(self.bottleneck(torch.cat(pyramid + [feats], 1)))
 
 
@@ -31,7 +41,9 @@ class PSPUpsample(nn.Module):
                                   nn.Conv2d(cin, cout, 3, padding=1), nn.PReLU())
 
     def forward(self, x):
-        return self.conv(x)
+        # conv = [Upsample(x2, align_corners=True), Conv2d 3x3, PReLU]; indices kept for the checkpoint keys
+        x = _upsample(x, (x.shape[2] * 2, x.shape[3] * 2), True)
+        return self.conv[2](self.conv[1](x))
 
 
 class PSPNet(nn.Module):

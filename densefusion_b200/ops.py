@@ -228,3 +228,15 @@ def pose_compose_(pose, r2, t2):
         raise _C.DFError("pose: contiguous float64 (B,7) expected")
     check(lib.df_pose_compose(ptr(pose), ptr(r2), ptr(t2), B, stream()), "df_pose_compose")
     return pose
+
+
+# ---- encoder helper -----------------------------------------------------------------------------------
+def upsample_bilinear(x: torch.Tensor, size, align_corners: bool) -> torch.Tensor:
+    """NCHW fp32 CUDA tensor -> (N,C,size[0],size[1]); same arithmetic as F.interpolate(mode='bilinear')."""
+    need_cuda(x)
+    x = f32c(x)
+    n, c, h, w = x.shape
+    out = torch.empty(n, c, int(size[0]), int(size[1]), device=x.device, dtype=torch.float32)
+    check(lib.df_upsample_bilinear(ptr(x), ptr(out), n * c, h, w, int(size[0]), int(size[1]), 1 if align_corners else 0,
+                                   stream()), "df_upsample_bilinear")
+    return out

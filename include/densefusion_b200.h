@@ -114,6 +114,12 @@ int df_select_out(const float* h, int ldh, const float* Wr, const float* br, con
                   const float* Wc, const float* bc, const int64_t* obj, int rows_per_crop, int num_obj,
                   long long rows, float* out_r, float* out_t, float* out_c, void* stream);
 
+/* ---- encoder helper -----------------------------------------------------------------------------
+ * NCHW bilinear up-sampling (lib/pspnet.py:20-23 F.upsample(size=...), :30-34 nn.Upsample(scale_factor=2,
+ * align_corners=True)): in (planes, hin, win) -> out (planes, hout, wout), planes = batch*channels. */
+int df_upsample_bilinear(const float* in, float* out, long long planes, int hin, int win, int hout, int wout,
+                         int align_corners, void* stream);
+
 /* ---- K5: on-device pose state for the refinement loop (tools/eval_ycb.py:193-233) ----------------
  * pose (B,7) float64 [qw qx qy qz tx ty tz]. */
 int df_select_pose(const float* pred_r, const float* pred_t, const float* pred_c, const float* points,

@@ -193,3 +193,16 @@ def test_forward_refuses_autograd_instead_of_falling_back():
     with pytest.raises(NotImplementedError):
         net(torch.zeros(1, 500, 3, device="cuda"), torch.zeros(1, 32, 500, device="cuda"),
             torch.zeros(1, 1, dtype=torch.long, device="cuda"))
+
+
+@pytest.mark.parametrize("shape,size,align", [((3, 512, 10, 10), (10, 10), False), ((2, 512, 1, 1), (15, 15), False),
+                                               ((2, 64, 6, 6), (20, 20), False), ((3, 1024, 10, 10), (20, 20), True),
+                                               ((2, 64, 40, 40), (80, 80), True), ((1, 7, 5, 9), (10, 18), True)])
+def test_upsample_bilinear_matches_torch(shape, size, align):
+    from densefusion_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g)
+    want = torch.nn.functional.interpolate(x, size=size, mode="bilinear", align_corners=align)
+    got = ops.upsample_bilinear(x.cuda(), size, align)
+    assert tuple(got.shape) == tuple(want.shape)
+    assert rel(got, want) < 2e-6
