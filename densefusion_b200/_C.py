@@ -30,6 +30,15 @@ SIGNATURES = {
     "df_gemm_rows_per_pool_tile": [],
     "df_gemm_tc": [_p, _i, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _p, _i, _i, _p],
     "df_split_tf32": [_p, _p, _p, _ll, _p],
+    "df_gemm_dgrad_fp32": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _p, _i, _p],
+    "df_gemm_wgrad_fp32": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _ll, _ll, _p],
+    "df_reduce_partials": [_p, _i, _ll, _p, _i, _p],
+    "df_colsum_rows": [_p, _i, _i, _i, _i, _p, _i, _p],
+    "df_relu_mask_inplace": [_p, _p, _i, _i, _ll, _p],
+    "df_pool_backward": [_p, _p, _p, _i, _i, _ll, _p],
+    "df_select_out_backward": [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "df_gather_embedding_backward": [_p, _p, _p, _ll, _ll, _ll, _i, _i, _i, _p],
+    "df_adam_step": [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _i, _p],
     "df_upsample_bilinear": [_p, _p, _ll, _i, _i, _i, _i, _i, _p],
     "df_gather_embedding": [_p, _p, _p, _p, _ll, _ll, _ll, _i, _i, _i, _p],
     "df_xyz_conv": [_p, _p, _p, _p, _i, _ll, _p],

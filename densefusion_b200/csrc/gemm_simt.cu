@@ -25,6 +25,8 @@ struct GemmParams {
     int rows_per_crop;
     long long a_gs, w_gs, bias_gs, c_gs;
     float* pool_partial; int tiles_per_crop;
+    const float* relu_mask;       // backward: multiply by (mask[m,n] > 0); same ld / group stride as C
+    int accumulate;               // backward: C += result
 };
 
 constexpr int BK = 16;
@@ -161,6 +163,15 @@ sgemm_kernel(const GemmParams p)
                     v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
                 }
                 if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                if (p.relu_mask) {
+                    const float4 mk = __ldg(reinterpret_cast<const float4*>(p.relu_mask + g * p.c_gs + (size_t)row * p.ldc + col));
+                    v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f;
+                    v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
+                }
+                if (p.accumulate) {
+                    const float4 old = *reinterpret_cast<const float4*>(C + (size_t)row * p.ldc + col);
+                    v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+                }
                 if (p.pool_partial) {
                     colsum[gj * 4] += v.x; colsum[gj * 4 + 1] += v.y; colsum[gj * 4 + 2] += v.z; colsum[gj * 4 + 3] += v.w;
                 } else {
@@ -202,11 +213,37 @@ void launch(const GemmParams& p, int groups, cudaStream_t s)
 
 extern "C" int df_gemm_rows_per_pool_tile(void) { return 128; }
 
+static int gemm_fp32_impl(const float* A, int lda, const float* W, int ldw, const float* bias,
+                          int bias_crop_stride, float* C, int ldc, int M, int N, int K, int relu,
+                          int rows_per_crop, int groups, long long a_group_stride, long long w_group_stride,
+                          long long bias_group_stride, long long c_group_stride, float* pool_partial,
+                          const float* relu_mask, int accumulate, void* stream);
+
 extern "C" int df_gemm_fp32(const float* A, int lda, const float* W, int ldw, const float* bias,
                             int bias_crop_stride, float* C, int ldc, int M, int N, int K, int relu,
                             int rows_per_crop, int groups, long long a_group_stride, long long w_group_stride,
                             long long bias_group_stride, long long c_group_stride, float* pool_partial,
                             void* stream)
+{
+    return gemm_fp32_impl(A, lda, W, ldw, bias, bias_crop_stride, C, ldc, M, N, K, relu, rows_per_crop, groups,
+                          a_group_stride, w_group_stride, bias_group_stride, c_group_stride, pool_partial, nullptr, 0, stream);
+}
+
+// Data-gradient form: C (+)= (A . W^T) (*) [relu_mask > 0], with A = dY and W = the TRANSPOSED layer weight.
+extern "C" int df_gemm_dgrad_fp32(const float* dY, int ldy, const float* Wt, int ldw, float* dX, int ldx, int M, int N,
+                                  int K, int groups, long long dy_group_stride, long long w_group_stride,
+                                  long long dx_group_stride, const float* relu_mask, int accumulate, void* stream)
+{
+    if (!dX) return DF_ERR_ARG;
+    return gemm_fp32_impl(dY, ldy, Wt, ldw, nullptr, 0, dX, ldx, M, N, K, 0, 0, groups, dy_group_stride, w_group_stride, 0,
+                          dx_group_stride, nullptr, relu_mask, accumulate, stream);
+}
+
+static int gemm_fp32_impl(const float* A, int lda, const float* W, int ldw, const float* bias,
+                          int bias_crop_stride, float* C, int ldc, int M, int N, int K, int relu,
+                          int rows_per_crop, int groups, long long a_group_stride, long long w_group_stride,
+                          long long bias_group_stride, long long c_group_stride, float* pool_partial,
+                          const float* relu_mask, int accumulate, void* stream)
 {
     if (!A || !W || (!C && !pool_partial)) return DF_ERR_ARG;
     if (M <= 0 || N <= 0 || K <= 0 || groups <= 0) return DF_ERR_ARG;
@@ -222,6 +259,8 @@ extern "C" int df_gemm_fp32(const float* A, int lda, const float* W, int ldw, co
     p.a_gs = a_group_stride; p.w_gs = w_group_stride; p.bias_gs = bias_group_stride; p.c_gs = c_group_stride;
     p.pool_partial = pool_partial;
     p.tiles_per_crop = pool_partial ? (p.rows_per_crop + 127) / 128 : 0;
+    p.relu_mask = relu_mask; p.accumulate = accumulate;
+    if (((uintptr_t)relu_mask & 15) || (pool_partial && (relu_mask || accumulate))) return DF_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     if (pool_partial) {
         if (N % 128 == 0) launch<128, 128, 2, 2>(p, groups, s);

@@ -9,8 +9,8 @@ Additive API (not in the reference): `forward_batched` evaluates every crop of t
 returns batch element 0 only, lib/network.py:123-126) and `precision` selects the GEMM arithmetic:
 "fp32" (exact FFMA, default), "3xtf32" (tcgen05, error-compensated, fp32-parity) or "tf32".
 
-Inference only in this round: calling forward with autograd enabled on a module whose parameters require
-grad raises, it does NOT silently fall back to torch ops."""
+Training: when autograd is enabled and something requires grad, forward goes through the explicit backward
+kernels of densefusion_b200.training (exact fp32); there is no torch-op fallback on the activation path."""
 from __future__ import annotations
 
 import torch
@@ -65,12 +65,15 @@ class PoseRefineNetFeat(_FeatParams):
         super().__init__(num_points, 384)
 
 
+def _needs_grad(module: nn.Module, *inputs) -> bool:
+    return torch.is_grad_enabled() and (any(p.requires_grad for p in module.parameters())
+                                        or any(torch.is_tensor(t) and t.requires_grad for t in inputs))
+
+
 def _no_autograd(module: nn.Module, *inputs):
-    if torch.is_grad_enabled() and (any(p.requires_grad for p in module.parameters())
-                                    or any(torch.is_tensor(t) and t.requires_grad for t in inputs)):
-        raise NotImplementedError(
-            "densefusion_b200: the fused head has no backward yet; call under torch.no_grad() "
-            "(or requires_grad_(False) the module).  There is deliberately no torch fallback.")
+    if _needs_grad(module, *inputs):
+        raise RuntimeError("densefusion_b200: this entry point is inference-only (point-major embeddings carry no "
+                           "graph); use forward / forward_batched for training, or call under torch.no_grad()")
 
 
 class _PackedMixin:
@@ -127,16 +130,23 @@ class PoseNet(nn.Module, _PackedMixin):
         return out_r, out_t, out_c
 
     def forward_batched(self, img, x, choose, obj):
-        """All crops: (B,N,4), (B,N,3), (B,N,1), emb (B,32,N)."""
-        _no_autograd(self, img, x)
+        """All crops: (B,N,4), (B,N,3), (B,N,1), emb (B,32,N) detached."""
         out_img = self.cnn(img)
+        if _needs_grad(self, img, x):
+            if x.shape[1] != self.num_points:
+                raise RuntimeError(f"PoseNet was built for {self.num_points} points, got {x.shape[1]}")
+            from .. import training
+            r, t, c, emb_cm = training.posenet_head_train(self, out_img, x, choose, obj)
+            return r, t, c, emb_cm.detach()
         emb_pm, emb_cm = ops.gather_embedding(out_img, choose)
         r, t, c = self.head(x, emb_pm, obj)
         return r, t, c, emb_cm
 
     def forward(self, img, x, choose, obj):
         """Reference contract: outputs of batch element 0 only; emb for the whole batch, detached."""
-        _no_autograd(self, img, x)
+        if _needs_grad(self, img, x):
+            r, t, c, emb_cm = self.forward_batched(img, x, choose, obj)
+            return r[0:1], t[0:1], c[0:1], emb_cm
         out_img = self.cnn(img)
         emb_pm, emb_cm = ops.gather_embedding(out_img, choose)
         n = x.shape[1]
@@ -171,9 +181,18 @@ class PoseRefineNet(nn.Module, _PackedMixin):
                              self.precision)
         return out_r, out_t
 
+    def forward_batched(self, x, emb, obj):
+        """x (B,N,3), emb (B,32,N) -> (B,4), (B,3) for every crop (differentiable w.r.t. the parameters)."""
+        B, n = x.shape[0], x.shape[1]
+        emb_pm = ops.f32c(emb.detach()).permute(0, 2, 1).reshape(B * n, 32).contiguous()
+        if _needs_grad(self):
+            if n != self.num_points:
+                raise RuntimeError(f"PoseRefineNet was built for {self.num_points} points, got {n}")
+            from .. import training
+            return training.refiner_train(self, x.detach(), emb_pm, obj)
+        return self.refine(x, emb_pm, obj)
+
     def forward(self, x, emb, obj):
         """Reference contract: x (bs,N,3), emb (bs,32,N), obj (bs,1) -> out_rx (1,4), out_tx (1,3)."""
-        _no_autograd(self, x, emb)
-        n = x.shape[1]
-        emb_pm = ops.f32c(emb[0]).t().contiguous()          # (N,32) point-major view of crop 0
-        return self.refine(x[0:1], emb_pm, obj[0:1])
+        r, t = self.forward_batched(x[0:1], emb[0:1], obj[0:1])
+        return r, t

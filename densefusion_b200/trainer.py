@@ -1,0 +1,149 @@
+"""Data-parallel training step of the pose path (BASELINE.json config C4; reference: tools/train.py:131-169).
+
+The reference trains with batch size 1 and *accumulates* un-normalised gradients over `batch_size` samples before one
+Adam step (tools/train.py:159-169).  Here a rank evaluates its crops batched per (H,W) bucket, every crop's loss gets
+gradient 1 (sum semantics), and the ranks exchange gradients exactly once per optimiser step:
+
+    flat fp32 arena  [ parameters | gradients | exp_avg | exp_avg_sq ]      (views alias module.parameters())
+        backward kernels write / accumulate straight into the gradient arena
+        ONE all-reduce(SUM) of the gradient arena   (NCCL over NVLink / NVSwitch; estimator 85.8 MB, refiner 7.7 MB)
+        ONE df_adam_step launch over the parameter arena (torch.optim.Adam arithmetic, identical on every rank)
+
+Two phases as in the reference: "estimator" optimises all of PoseNet (tools/train.py:97), "refiner" runs PoseNet
+without a graph and optimises PoseRefineNet through `iteration` chained Loss_refine evaluations, each with its own
+backward (tools/train.py:156-159).  Inference needs none of this: frames shard with no collective (`shard_range`)."""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence
+
+import torch
+
+from ._C import DFError, check, lib, ptr, stream
+
+ALIGN = 64          # floats; keeps every parameter view 256-byte aligned (float4 / TMA-able)
+
+
+def shard_range(n_items: int, rank: int, world: int) -> range:
+    """Contiguous block partition of n_items over `world` ranks (first n_items % world ranks get one more)."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank / world")
+    base, extra = divmod(n_items, world)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+class FlatArena:
+    """Parameters, gradients and Adam moments of a list of nn.Parameters as four flat fp32 buffers.
+    After construction p.data and p.grad are views into the arena, so autograd accumulates in place."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params: List[torch.nn.Parameter] = [p for p in params]
+        if not self.params:
+            raise ValueError("FlatArena: no parameters")
+        dev = self.params[0].device
+        self.offsets, off = [], 0
+        for p in self.params:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise ValueError("FlatArena: fp32 parameters on one device expected")
+            self.offsets.append(off)
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.total = off
+        self.numel = sum(p.numel() for p in self.params)
+        z = lambda: torch.zeros(self.total, device=dev, dtype=torch.float32)
+        self.param, self.grad, self.exp_avg, self.exp_avg_sq = z(), z(), z(), z()
+        self.step_count = 0
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                n = p.numel()
+                self.param[o:o + n].copy_(p.detach().reshape(-1))
+                p.data = self.param[o:o + n].view(p.shape)
+                p.grad = self.grad[o:o + n].view(p.shape)
+
+    def zero_grad(self) -> None:
+        self.grad.zero_()
+        for p, o in zip(self.params, self.offsets):          # re-attach if someone set .grad = None
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+    def all_reduce(self, group=None) -> None:
+        """SUM over ranks (the reference's accumulation is un-normalised, tools/train.py:159-169)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
+
+    def adam_step(self, lr: float, betas=(0.9, 0.999), eps: float = 1e-8) -> None:
+        if not self.param.is_cuda:
+            raise DFError("FlatArena.adam_step: the optimiser step is a CUDA kernel (no CPU fallback)")
+        self.step_count += 1
+        check(lib.df_adam_step(ptr(self.param), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.total,
+                               float(lr), float(betas[0]), float(betas[1]), float(eps), self.step_count, stream()),
+              "df_adam_step")
+
+
+class DataParallelTrainer:
+    """One optimiser step per call; every rank passes its own shard of the global batch.
+
+    buckets: list of dicts of batched CUDA tensors sharing one crop size:
+        img (b,3,H,W), points (b,N,3), choose (b,1,N), idx (b,1)|(b,), target (b,M,3), model_points (b,M,3)."""
+
+    def __init__(self, estimator, refiner, num_points_mesh: int, sym_list: Sequence[int], lr: float = 1e-4,
+                 w: float = 0.015, iteration: int = 2, phase: str = "estimator", group=None):
+        from .lib.loss import Loss
+        from .lib.loss_refiner import Loss_refine
+        self.estimator, self.refiner = estimator, refiner
+        self.criterion = Loss(num_points_mesh, sym_list)
+        self.criterion_refine = Loss_refine(num_points_mesh, sym_list)
+        self.lr, self.w, self.iteration, self.group = float(lr), float(w), int(iteration), group
+        self.arena_est: Optional[FlatArena] = None
+        self.arena_ref: Optional[FlatArena] = None
+        self.set_phase(phase)
+
+    def set_phase(self, phase: str) -> None:
+        if phase not in ("estimator", "refiner"):
+            raise ValueError("phase must be 'estimator' or 'refiner'")
+        self.phase = phase
+        if phase == "estimator":
+            self.estimator.requires_grad_(True)
+            if self.arena_est is None:
+                self.arena_est = FlatArena(self.estimator.parameters())
+        else:
+            self.estimator.requires_grad_(False)        # tools/train.py:93,228: only the refiner is optimised
+            self.refiner.requires_grad_(True)
+            if self.arena_ref is None:
+                self.arena_ref = FlatArena(self.refiner.parameters())
+
+    # ---- local forward / backward (gradients land in the arena) ----
+    def _local_estimator(self, buckets):
+        loss_sum = dis_sum = 0.0
+        for b in buckets:
+            r, t, c, _ = self.estimator.forward_batched(b["img"], b["points"], b["choose"], b["idx"])
+            loss, dis, _, _ = self.criterion(r, t, c, b["target"], b["model_points"], b["idx"], b["points"], self.w, False)
+            loss.sum().backward()
+            loss_sum = loss_sum + loss.detach().sum()
+            dis_sum = dis_sum + dis.detach().sum()
+        return loss_sum, dis_sum
+
+    def _local_refiner(self, buckets):
+        loss_sum = dis_sum = 0.0
+        for b in buckets:
+            with torch.no_grad():
+                r, t, c, emb = self.estimator.forward_batched(b["img"], b["points"], b["choose"], b["idx"])
+                loss, dis, new_points, new_target = self.criterion(r, t, c, b["target"], b["model_points"], b["idx"],
+                                                                   b["points"], self.w, True)
+            for _ in range(self.iteration):
+                pr, pt = self.refiner.forward_batched(new_points, emb, b["idx"])
+                dis, new_points, new_target = self.criterion_refine(pr, pt, new_target, b["model_points"], b["idx"],
+                                                                    new_points)
+                dis.sum().backward()
+            loss_sum = loss_sum + loss.detach().sum()
+            dis_sum = dis_sum + dis.detach().sum()
+        return loss_sum, dis_sum
+
+    def step(self, buckets) -> dict:
+        arena = self.arena_est if self.phase == "estimator" else self.arena_ref
+        arena.zero_grad()
+        fn = self._local_estimator if self.phase == "estimator" else self._local_refiner
+        loss_sum, dis_sum = fn(buckets)
+        arena.all_reduce(self.group)
+        arena.adam_step(self.lr)
+        return {"loss_sum": loss_sum, "dis_sum": dis_sum}

@@ -114,6 +114,35 @@ int df_select_out(const float* h, int ldh, const float* Wr, const float* br, con
                   const float* Wc, const float* bc, const int64_t* obj, int rows_per_crop, int num_obj,
                   long long rows, float* out_r, float* out_t, float* out_c, void* stream);
 
+/* ---- backward of K1 / K2 and the optimiser step (training, config C4; tools/train.py:152-169) ------------
+ * What autograd derives from lib/network.py, as explicit kernels (exact fp32):
+ *   df_gemm_dgrad_fp32 : dX (+)= (dY . W) (*) [relu_mask > 0]; Wt is the TRANSPOSED layer weight (K_out, N_red) so the
+ *                        forward kernel is reused; relu_mask has dX's leading dimension / group stride.
+ *   df_gemm_wgrad_fp32 : partial[s][g][n,k] = sum over row slice s of dY[m, g*dy_gs+n] X[m, g*x_gs+k]
+ *   df_reduce_partials : out (+)= sum_s partial[s]  (fixed order -> deterministic)
+ *   df_colsum_rows     : out[group, c] (+)= sum_{r < rows_per_group} X[group*rows_per_group + r, c]
+ *   df_relu_mask_inplace, df_pool_backward, df_select_out_backward, df_gather_embedding_backward: see backward.cu
+ *   df_adam_step       : torch.optim.Adam (no weight decay / amsgrad) on a flat parameter arena */
+int df_gemm_dgrad_fp32(const float* dY, int ldy, const float* Wt, int ldw, float* dX, int ldx, int M, int N, int K,
+                       int groups, long long dy_group_stride, long long w_group_stride, long long dx_group_stride,
+                       const float* relu_mask, int accumulate, void* stream);
+int df_gemm_wgrad_fp32(const float* dY, int ldy, const float* X, int ldx, float* partial, int M, int N, int K,
+                       int groups, int splits, long long dy_group_stride, long long x_group_stride, void* stream);
+int df_reduce_partials(const float* partial, int splits, long long count, float* out, int accumulate, void* stream);
+int df_colsum_rows(const float* X, int ldx, int rows_per_group, int groups, int C, float* out, int accumulate,
+                   void* stream);
+int df_relu_mask_inplace(float* d, const float* act, int ld, int cols, long long rows, void* stream);
+int df_pool_backward(const float* dg, const float* h, float* dh, int rows_per_crop, int C, long long rows, void* stream);
+int df_select_out_backward(const float* g_r, const float* g_t, const float* g_c, const float* out_c, const float* h,
+                           int ldh, const float* Wr, const float* Wt, const float* Wc, const int64_t* obj,
+                           int rows_per_crop, int num_obj, long long rows, float* dh, float* gz, float* blk,
+                           float* bsum, float* dWr, float* dbr, float* dWt, float* dbt, float* dWc, float* dbc,
+                           void* stream);
+int df_gather_embedding_backward(const float* demb, const int64_t* choose, float* dfeat, long long stride_b,
+                                 long long stride_c, long long stride_pix, int B, int N, int HW, void* stream);
+int df_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                 float beta1, float beta2, float eps, int step, void* stream);
+
 /* ---- encoder helper -----------------------------------------------------------------------------
  * NCHW bilinear up-sampling (lib/pspnet.py:20-23 F.upsample(size=...), :30-34 nn.Upsample(scale_factor=2,
  * align_corners=True)): in (planes, hin, win) -> out (planes, hout, wout), planes = batch*channels. */

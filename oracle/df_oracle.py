@@ -29,6 +29,7 @@ Restated functions (reference file:line):
   quaternion_from_matrix lib/transformations.py:1281-1363 (isprecise branch + sign fix)
   select_pose / refine_pose_eval   tools/eval_ycb.py:193-233
   knn                    lib/knn/src/knn_cuda_kernel.cu:31-170 via oracle/knn_ref.c
+  estimator_gradients / refiner_gradients / adam_reference   tools/train.py:143-169 (+ torch.optim.Adam)
 """
 from __future__ import annotations
 
@@ -397,3 +398,61 @@ def estimate_and_refine(sd_est, sd_ref, img, cloud, choose, obj, num_obj, iterat
         my_r, my_t, _ = select_pose(r, t, c, cloud)
         q, tt = refine_pose_eval(sd_ref, cloud, emb, obj, num_obj, my_r, my_t, iterations)
     return np.concatenate([q, tt])
+
+
+# ----------------------------------------------------------------------------------------------
+# Training step (tools/train.py:143-169): per-sample forward + backward, gradients accumulate (SUM)
+# ----------------------------------------------------------------------------------------------
+def _leaf_state_dict(sd: dict) -> dict:
+    return {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+
+
+def estimator_gradients(sd_est: dict, crops, num_obj, num_point_mesh, sym_list, w):
+    """Estimator phase (tools/train.py:152-153, :161): for every crop (bs=1 dict with img, points, choose,
+    target, model_points, idx) loss.backward(); returns ({name: summed grad or None}, [loss], [dis])."""
+    leaf = _leaf_state_dict(sd_est)
+    losses, dists = [], []
+    for d in crops:
+        r, t, c, _ = posenet_forward(leaf, d["img"], d["points"], d["choose"], d["idx"], num_obj)
+        total, dis, _, _ = loss(r, t, c, d["target"], d["model_points"], d["idx"], d["points"], w, False,
+                                num_point_mesh, sym_list)
+        total.backward()
+        losses.append(float(total))
+        dists.append(float(dis))
+    return {k: v.grad for k, v in leaf.items()}, losses, dists
+
+
+def refiner_gradients(sd_est: dict, sd_ref: dict, crops, num_obj, num_point_mesh, sym_list, w, iteration):
+    """Refiner phase (tools/train.py:152-159): Loss(..., refine=True) then `iteration` x (refiner, Loss_refine,
+    dis.backward()); only the refiner's gradients matter (tools/train.py:93)."""
+    leaf = _leaf_state_dict(sd_ref)
+    dists = []
+    for d in crops:
+        with torch.no_grad():
+            r, t, c, emb = posenet_forward(sd_est, d["img"], d["points"], d["choose"], d["idx"], num_obj)
+            _, _, pts, tgt = loss(r, t, c, d["target"], d["model_points"], d["idx"], d["points"], w, True,
+                                  num_point_mesh, sym_list)
+        for _ in range(iteration):
+            rr, tt = refiner_forward(leaf, pts, emb, d["idx"], num_obj)
+            dis, pts, tgt = loss_refine(rr, tt, tgt, d["model_points"], d["idx"], pts, num_point_mesh, sym_list)
+            dis.backward()
+        dists.append(float(dis))
+    return {k: v.grad for k, v in leaf.items()}, dists
+
+
+def adam_reference(params: dict, grads: dict, state: dict, lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
+    """torch.optim.Adam (the reference's optimiser, tools/train.py:97) applied functionally: params / state are
+    updated in place; parameters whose gradient is None are skipped, as torch does."""
+    state["step"] = state.get("step", 0) + 1
+    k = state["step"]
+    for name, p in params.items():
+        g = grads.get(name)
+        if g is None:
+            continue
+        m = state.setdefault("m." + name, torch.zeros_like(p))
+        v = state.setdefault("v." + name, torch.zeros_like(p))
+        m.mul_(betas[0]).add_(g, alpha=1 - betas[0])
+        v.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
+        denom = (v.sqrt() / math.sqrt(1 - betas[1] ** k)).add_(eps)
+        p.addcdiv_(m, denom, value=-lr / (1 - betas[0] ** k))
+    return params

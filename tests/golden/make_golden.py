@@ -165,6 +165,71 @@ def loss_only_case(name, case, num_points, num_pt_mesh, obj, sym_list, w=0.015):
     print(name, "loss", float(loss), "dis", float(dis), "ref_dis", float(dis_r), "->", os.path.getsize(path), "bytes")
 
 
+def grad_summary(named_grads):
+    """Per-parameter summary small enough to commit: L2 norm, sum, and 32 strided samples."""
+    out = {}
+    for name, g in named_grads:
+        if g is None:
+            out["gnone." + name] = np.array(1)
+            continue
+        f = g.detach().reshape(-1).double()
+        stride = max(1, f.numel() // 32)
+        out["gnorm." + name] = np.array(float(f.norm()))
+        out["gsum." + name] = np.array(float(f.sum()))
+        out["gsamp." + name] = f[::stride][:32].float().numpy()
+    return out
+
+
+def train_case(name, cases, objs, num_points, num_obj, num_pt_mesh, hw, sym_list, seed, w=0.015, iters=2):
+    """tools/train.py:143-169 on the reference modules: gradient ACCUMULATION over bs=1 samples (no division),
+    estimator phase (loss.backward()) and refiner phase (dis.backward() inside the iteration loop), followed by the
+    reference's optimiser (torch.optim.Adam, lr 1e-4, tools/train.py:97).  eval() mode: Dropout2d off."""
+    est, refiner = build_nets(num_points, num_obj, seed)
+    crops = [synth.synth_crop(c, num_points, num_pt_mesh, num_obj, hw, o) for c, o in zip(cases, objs)]
+    crit, crit_ref = Loss(num_pt_mesh, sym_list), Loss_refine(num_pt_mesh, sym_list)
+    out = {"meta": np.array([num_points, num_obj, num_pt_mesh, hw[0], hw[1], seed, iters]), "cases": np.array(cases),
+           "objs": np.array(objs), "sym_list": np.array(sym_list), "w": np.array(w)}
+    # ---- estimator phase ----
+    opt = torch.optim.Adam(est.parameters(), lr=1e-4)
+    opt.zero_grad()
+    losses, dists = [], []
+    for d in crops:
+        pred_r, pred_t, pred_c, emb = est(d["img"], d["points"], d["choose"], d["idx"])
+        loss, dis, _, _ = crit(pred_r, pred_t, pred_c, d["target"], d["model_points"], d["idx"], d["points"], w, False)
+        loss.backward()
+        losses.append(float(loss)); dists.append(float(dis))
+    out.update(est_losses=np.array(losses), est_dis=np.array(dists))
+    out.update({"est." + k: v for k, v in grad_summary([(n, p.grad) for n, p in est.named_parameters()]).items()})
+    before = {n: p.detach().clone() for n, p in est.named_parameters()}
+    opt.step()
+    for n, p in est.named_parameters():
+        f = (p.detach() - before[n]).reshape(-1)
+        out["est.delta." + n] = f[::max(1, f.numel() // 32)][:32].numpy()
+    # ---- refiner phase (fresh estimator weights, as loaded) ----
+    est, _ = build_nets(num_points, num_obj, seed)
+    opt = torch.optim.Adam(refiner.parameters(), lr=1e-4)
+    opt.zero_grad()
+    dists = []
+    for d in crops:
+        pred_r, pred_t, pred_c, emb = est(d["img"], d["points"], d["choose"], d["idx"])
+        loss, dis, pts, tgt = crit(pred_r, pred_t, pred_c, d["target"], d["model_points"], d["idx"], d["points"], w, True)
+        for _ in range(iters):
+            rr, tt = refiner(pts, emb, d["idx"])
+            dis, pts, tgt = crit_ref(rr, tt, tgt, d["model_points"], d["idx"], pts)
+            dis.backward()
+        dists.append(float(dis))
+    out.update(ref_dis=np.array(dists))
+    out.update({"ref." + k: v for k, v in grad_summary([(n, p.grad) for n, p in refiner.named_parameters()]).items()})
+    before = {n: p.detach().clone() for n, p in refiner.named_parameters()}
+    opt.step()
+    for n, p in refiner.named_parameters():
+        f = (p.detach() - before[n]).reshape(-1)
+        out["ref.delta." + n] = f[::max(1, f.numel() // 32)][:32].numpy()
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "losses", losses, "ref dis", dists, "->", os.path.getsize(path), "bytes")
+
+
 def ply_points(path):
     """binary_little_endian PLY with `element vertex N` and three double properties."""
     raw = open(path, "rb").read()
@@ -190,6 +255,11 @@ def ply_case():
 if __name__ == "__main__":
     if "--ply-only" in sys.argv:
         ply_case()
+        sys.exit(0)
+    # C4 shape: training step (gradient accumulation over 3 samples: two objects share id 12 (symmetric), one is not)
+    train_case("c4_train_ycb", cases=[40, 41, 42], objs=[12, 3, 12], num_points=500, num_obj=21, num_pt_mesh=500,
+               hw=(80, 80), sym_list=synth.YCB_SYM, seed=4)
+    if "--train-only" in sys.argv:
         sys.exit(0)
     # C0: LineMOD PoseNet(500,13), non-symmetric object, 80x80
     full_case("c0_linemod_add", case=0, num_points=500, num_obj=13, num_pt_mesh=500, hw=(80, 80), obj=3,

@@ -187,12 +187,12 @@ def test_posenet_dropin_vs_reference_golden(name):
     assert rel(rr, g["train_r0"]) < 1e-4 and rel(tt, g["train_t0"]) < 1e-4
 
 
-def test_forward_refuses_autograd_instead_of_falling_back():
+def test_point_major_entry_points_are_inference_only():
     from densefusion_b200.lib.network import PoseRefineNet
     net = PoseRefineNet(500, 13).cuda()
-    with pytest.raises(NotImplementedError):
-        net(torch.zeros(1, 500, 3, device="cuda"), torch.zeros(1, 32, 500, device="cuda"),
-            torch.zeros(1, 1, dtype=torch.long, device="cuda"))
+    with pytest.raises(RuntimeError):
+        net.refine(torch.zeros(1, 500, 3, device="cuda"), torch.zeros(500, 32, device="cuda"),
+                   torch.zeros(1, dtype=torch.long, device="cuda"))
 
 
 @pytest.mark.parametrize("shape,size,align", [((3, 512, 10, 10), (10, 10), False), ((2, 512, 1, 1), (15, 15), False),

@@ -1,0 +1,156 @@
+"""Backward of K1/K2/K3 and the data-parallel training step (config C4) against the oracle's autograd restatement
+of tools/train.py:143-169 and the reference's own gradients (tests/golden/c4_train_ycb.npz).
+Stated bounds: gradients <= 1e-3 (max-abs / max-abs per tensor; measured values are printed), Adam deltas <= 2e-6 abs."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from densefusion_b200 import synth
+from oracle import df_oracle as O
+from test_training_cpu import _crops, _summary_close
+from util import build_nets, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _f64(x):
+    return x.detach().cpu().double()
+
+
+def test_backward_gemm_building_blocks_vs_float64():
+    from densefusion_b200 import training as T
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 1500, 256, 128
+    dY, X = torch.randn(M, N, generator=g).cuda(), torch.randn(M, K, generator=g).cuda()
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    act = torch.randn(M, K, generator=g).cuda()
+    dW = T._wgrad(dY, N, X, K, M, N, K)[0]
+    assert rel(dW, _f64(dY).t() @ _f64(X)) < 2e-6
+    dX = torch.empty(M, K, device="cuda")
+    T._dgrad(dY, N, W.t().contiguous(), N, dX, K, M, K, N, mask=act)
+    want = (_f64(dY) @ _f64(W)) * (_f64(act) > 0)
+    assert rel(dX, want) < 2e-6
+    T._dgrad(dY, N, W.t().contiguous(), N, dX, K, M, K, N, accumulate=True)
+    assert rel(dX, want + _f64(dY) @ _f64(W)) < 2e-6
+    cs = T._colsum(dY, N, 500, 3, N)
+    assert rel(cs, _f64(dY).view(3, 500, N).sum(1)) < 2e-6
+    # odd shapes: K_out = 3 (conv1 on xyz), grouped layout
+    x3 = torch.randn(M, 3, generator=g).cuda()
+    d64 = torch.randn(M, 64, generator=g).cuda()
+    assert rel(T._wgrad(d64, 64, x3, 3, M, 64, 3)[0], _f64(d64).t() @ _f64(x3)) < 2e-6
+
+
+def test_adam_kernel_vs_torch_optim():
+    from densefusion_b200.trainer import FlatArena
+    torch.manual_seed(1)
+    ps = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in ((33, 7), (1000,), (5, 5, 3))]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    arena = FlatArena(ps)
+    opt = torch.optim.Adam(qs, lr=1e-3)
+    for step in range(4):
+        arena.zero_grad()
+        opt.zero_grad()
+        for p, q in zip(ps, qs):
+            gi = torch.randn_like(q) * (10.0 ** (step - 2))
+            p.grad.copy_(gi)
+            q.grad = gi.clone()
+        arena.adam_step(1e-3)
+        opt.step()
+        for p, q in zip(ps, qs):
+            assert rel(p, q) < 1e-6
+
+
+def _device_batch(crops):
+    keys = ("img", "points", "choose", "idx", "target", "model_points")
+    return {k: torch.cat([c[k] for c in crops], 0).cuda() for k in keys}
+
+
+def _setup():
+    g = golden("c4_train_ycb")
+    crops, n, o, m, seed, iters = _crops(g)
+    sym, w = [int(s) for s in g["sym_list"]], float(g["w"])
+    est, ref, est_sd, ref_sd = build_nets(n, o, seed)
+    return g, crops, n, o, m, iters, sym, w, est, ref, est_sd, ref_sd
+
+
+def _compare(named_params, oracle_grads, tol=1e-3):
+    worst, worst_name = 0.0, ""
+    for name, p in named_params:
+        og = oracle_grads[name]
+        if og is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        e = rel(p.grad, og)
+        if e > worst:
+            worst, worst_name = e, name
+    print(f"worst gradient error {worst:.3e} at {worst_name}")
+    assert worst < tol, worst_name
+    return worst
+
+
+def test_estimator_gradients_vs_oracle_and_reference_golden():
+    from densefusion_b200.lib.loss import Loss
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g, crops, n, o, m, iters, sym, w, est, ref, est_sd, ref_sd = _setup()
+    est.requires_grad_(True)
+    b = _device_batch(crops)
+    r, t, c, emb = est.forward_batched(b["img"], b["points"], b["choose"], b["idx"])
+    assert not emb.requires_grad
+    loss, dis, _, _ = Loss(m, sym)(r, t, c, b["target"], b["model_points"], b["idx"], b["points"], w, False)
+    loss.sum().backward()
+    assert np.allclose(loss.detach().cpu().numpy(), g["est_losses"], rtol=1e-4)
+    assert np.allclose(dis.detach().cpu().numpy(), g["est_dis"], rtol=1e-4)
+    ograds, _, _ = O.estimator_gradients(est_sd, crops, o, m, sym, w)
+    _compare(est.named_parameters(), ograds)
+    print("vs reference golden:", _summary_close(g, "est.", {k: (None if p.grad is None else p.grad.detach().cpu())
+                                                                for k, p in est.named_parameters()}, rtol=1e-3))
+    # reference contract: forward() with autograd returns crop 0 only and is differentiable too
+    est.zero_grad()
+    r0, t0, c0, _ = est(b["img"][0:1], b["points"][0:1], b["choose"][0:1], b["idx"][0:1])
+    l0, _, _, _ = Loss(m, sym)(r0, t0, c0, b["target"][0:1], b["model_points"][0:1], b["idx"][0:1], b["points"][0:1], w, False)
+    l0.backward()
+    og0, _, _ = O.estimator_gradients(est_sd, crops[:1], o, m, sym, w)
+    _compare(est.named_parameters(), og0)
+
+
+def test_refiner_gradients_vs_oracle_and_reference_golden():
+    from densefusion_b200.trainer import DataParallelTrainer
+    torch.backends.cudnn.allow_tf32 = False
+    g, crops, n, o, m, iters, sym, w, est, ref, est_sd, ref_sd = _setup()
+    tr = DataParallelTrainer(est, ref, m, sym, lr=1e-4, w=w, iteration=iters, phase="refiner")
+    tr.arena_ref.zero_grad()
+    _, dis_sum = tr._local_refiner([_device_batch(crops)])
+    assert abs(float(dis_sum) - float(np.sum(g["ref_dis"]))) < 1e-4 * float(np.sum(g["ref_dis"]))
+    ograds, _ = O.refiner_gradients(est_sd, ref_sd, crops, o, m, sym, w, iters)
+    _compare(ref.named_parameters(), ograds)
+    print("vs reference golden:", _summary_close(g, "ref.", {k: p.grad.detach().cpu() for k, p in ref.named_parameters()},
+                                                 rtol=1e-3))
+
+
+@pytest.mark.parametrize("phase", ["estimator", "refiner"])
+def test_trainer_step_matches_oracle_adam(phase):
+    """Two optimiser steps (gradient accumulation over two buckets each) == the oracle's per-sample accumulation +
+    torch.optim.Adam arithmetic."""
+    from densefusion_b200.trainer import DataParallelTrainer
+    torch.backends.cudnn.allow_tf32 = False
+    g, crops, n, o, m, iters, sym, w, est, ref, est_sd, ref_sd = _setup()
+    tr = DataParallelTrainer(est, ref, m, sym, lr=1e-4, w=w, iteration=iters, phase=phase)
+    params = {k: v.clone() for k, v in (est_sd if phase == "estimator" else ref_sd).items()}
+    state = {}
+    net = est if phase == "estimator" else ref
+    for step in range(2):
+        order = crops if step == 0 else crops[::-1]
+        tr.step([_device_batch(order[:2]), _device_batch(order[2:])])
+        if phase == "estimator":
+            grads, _, _ = O.estimator_gradients(params, order, o, m, sym, w)
+        else:
+            grads, _ = O.refiner_gradients(est_sd, params, order, o, m, sym, w, iters)
+        O.adam_reference(params, grads, state, lr=1e-4)
+        frac_bad = []
+        for name, p in net.named_parameters():
+            d = (p.detach().cpu() - params[name]).abs()
+            frac_bad.append(float((d > 2e-6).float().mean()))
+        print(f"{phase} step {step}: worst fraction of weights off by > 2e-6: {max(frac_bad):.4f}")
+        assert max(frac_bad) < 0.02
