@@ -108,17 +108,19 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int split
 __global__ void __launch_bounds__(256)
 colsum_rows_kernel(const float* __restrict__ X, int ldx, int rows_per_group, int C, float* __restrict__ out, int accumulate)
 {
-    __shared__ float red[8][128];
+    // float64 accumulation: these sums (bias gradients, the per-crop gradient of the folded global feature) add
+    // thousands of terms of mixed sign; the kernel is bandwidth-bound, so the wider adds are free.
+    __shared__ double red[2][128];
     const int grp = blockIdx.y, c = blockIdx.x * 128 + (threadIdx.x & 127) ;
     const int lane_r = threadIdx.x >> 7;                    // 0..1
     const float* base = X + (size_t)grp * rows_per_group * ldx;
-    float s = 0.0f;
+    double s = 0.0;
     if (c < C)
-        for (int r = lane_r; r < rows_per_group; r += 2) s += base[(size_t)r * ldx + c];
+        for (int r = lane_r; r < rows_per_group; r += 2) s += (double)base[(size_t)r * ldx + c];
     red[lane_r][threadIdx.x & 127] = s;
     __syncthreads();
     if (threadIdx.x < 128 && c < C) {
-        const float t = red[0][threadIdx.x] + red[1][threadIdx.x];
+        const float t = (float)(red[0][threadIdx.x] + red[1][threadIdx.x]);
         float* o = out + (size_t)grp * C + c;
         *o = accumulate ? *o + t : t;
     }

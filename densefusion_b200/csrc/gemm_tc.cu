@@ -24,6 +24,7 @@
 #include "df_common.cuh"
 #include "../../include/densefusion_b200.h"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -43,134 +44,10 @@ struct TcParams {
     float* pool_partial; int tiles_per_crop;
 };
 
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// Bounded wait: a protocol bug must trap (launch error) rather than hang the GPU box.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    const uint32_t addr = smem_u32(bar);
-    const long long t0 = clock64();
-    uint32_t ok = 0;
-    while (true) {
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-        if (ok) break;
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
-}
-// One elected lane of a converged warp.  Issuing tcgen05.mma / TMA from an elect.sync region (instead of a
-// divergent `lane == 0` branch) lets nvcc keep descriptors in uniform registers: ~15 SASS instructions per
-// k-block instead of ~200 (waterfall loops), which was the bottleneck of the first persistent kernel
-// (profiles/r1_call4_*: issue thread saturated, tensor pipe 44%).
-__device__ __forceinline__ bool elect_one()
-{
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols)
-{
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols)
-{
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem desc] . B[smem desc]^T
-__device__ __forceinline__ void umma_ss(uint32_t d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
-// D[tmem] (+)= A[tmem] . B[smem desc]^T
-__device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-                 ::"r"(d), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
-
-#define DF_R32(v) \
-    v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15], v[16], v[17],   \
-    v[18], v[19], v[20], v[21], v[22], v[23], v[24], v[25], v[26], v[27], v[28], v[29], v[30], v[31]
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
-                 "%23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                 : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32])
-{
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
-                 "%24, %25, %26, %27, %28, %29, %30, %31, %32};"
-                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
-                   "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
-                   "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
-                   "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// K-major, 128B-swizzled operand tile whose rows are 128 B apart: 8-row atoms 1024 B apart (SBO),
-// LBO unused (one atom along K), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
-__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-__device__ __forceinline__ uint32_t tf32_instr_desc(int n)
-{
-    // c_format F32 (1) @4, a/b format TF32 (2) @7/@10, K-major both, N>>3 @17, M>>4 @24
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
+}  // namespace
+#include "tc_ptx.cuh"
+namespace {
+using namespace df_tc;
 
 template <int BN, bool A_TMEM>
 struct Cfg {
@@ -661,6 +538,299 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_whi, const __gr
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Generation 2 of the persistent kernel ("q"): the A operand also arrives by TMA.
+//
+// Why: in the kernel above every stager lane reads its own accumulator row straight from global memory, i.e. one
+// LDG.128 of a warp touches 32 different 128-byte lines.  The L1/tex pipe retires about one such line ("wavefront")
+// per cycle, so a 128x32 fp32 k-block costs >= 1024 cycles of LSU time -- more than the 768 cycles its twelve
+// 128x128x8 TF32 MMAs need.  That, not the tensor pipe, set the pace (profiles/r1_call6_tc_probe.txt: one TF32 pass
+// was no faster than three).  Here a stage is {A 128x32 fp32 | W_hi | W_lo}, all 128B-swizzled TMA tiles; the stagers
+// read their row back from shared memory (conflict-free LDS.128 thanks to the swizzle), split it and tcgen05.st the
+// hi / lo halves into TMEM as before.
+//
+// CTAS == 2 additionally pairs two SMs on one 256 x (2*bn_cta) tile with tcgen05.mma.cta_group::2: every CTA stages
+// its own 128 rows of A (TMEM) and HALF of the weight tile (shared memory), the tensor cores of both SMs read both
+// halves, so the L2 -> SM and shared-memory bytes per flop are halved -- the tile moves from the L2 / smem roof
+// (48 KB per 768 MMA cycles) under the tensor roof (48 KB per 1536).
+//   warp 0       TMA producer (own A rows, own half of W_hi / W_lo) -> local full[s]
+//   warp 1       MMA issuer + TMEM owner (leader CTA only issues; commits are multicast to both CTAs)
+//   warps 2-9    A stagers, two groups alternating k-blocks; arrive on the LEADER's a_full[s] (remote arrive from the peer)
+//   warps 10-17  epilogue: two warps per TMEM lane quarter, alternate 32-column chunks
+// TMEM (512 columns): accumulator(s) in [0,256), four A stages of 64 columns (hi | lo) in [256,512).
+// ------------------------------------------------------------------------------------------------
+constexpr int Q_THREADS = 18 * 32;
+constexpr int Q_STAGES = 4;
+constexpr int Q_TILE = 128 * BK * 4;                         // 16 KB: one 128-row fp32 tile of 32 k
+constexpr int Q_STAGE_BYTES = 3 * Q_TILE;                    // A | W_hi | W_lo
+constexpr int Q_SMEM_STAGES = Q_STAGES * Q_STAGE_BYTES;      // 192 KB
+constexpr int Q_SMEM_EPI = 8 * 32 * 32 * 4;                  // 32 KB: one swizzled 32x32 transpose tile per epilogue warp
+constexpr int Q_SMEM_TOTAL = 1024 + Q_SMEM_STAGES + Q_SMEM_EPI + 512;
+constexpr int Q_TMEM_A0 = 256;
+static_assert(Q_SMEM_TOTAL <= 227 * 1024, "shared memory overflow");
+
+struct QTile {
+    int g, n0, row0, rows_valid, crop, pool_tile;
+};
+
+template <int CTAS>
+__device__ __forceinline__ QTile q_decode(const TcParams& p, int t, int m_tiles, int n_tiles, int bnt, int rank)
+{
+    QTile c;
+    const int per_group = m_tiles * n_tiles;
+    c.g = t / per_group;
+    const int rem = t - c.g * per_group;
+    const int mt = rem / n_tiles;
+    c.n0 = (rem - mt * n_tiles) * bnt;
+    c.crop = 0; c.pool_tile = 0;
+    if (p.pool_partial) {
+        const int pairs_per_crop = (p.rows_per_crop + 128 * CTAS - 1) / (128 * CTAS);
+        c.crop = mt / pairs_per_crop;
+        c.pool_tile = (mt - c.crop * pairs_per_crop) * CTAS + rank;        // index of this CTA's 128-row tile in the crop
+        c.row0 = c.crop * p.rows_per_crop + c.pool_tile * 128;
+        c.rows_valid = max(0, min(128, p.rows_per_crop - c.pool_tile * 128));
+    } else {
+        c.row0 = (mt * CTAS + rank) * 128;
+        c.rows_valid = max(0, min(128, p.M - c.row0));
+    }
+    return c;
+}
+
+template <int CTAS>
+__global__ void __launch_bounds__(Q_THREADS, 1)
+gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_whi,
+                 const __grid_constant__ CUtensorMap tm_wlo, const TcParams p, const int bn_cta, const int m_tiles,
+                 const int n_tiles, const int total_tiles)
+{
+    constexpr int ACC_BUFS = CTAS == 1 ? 2 : 1;              // CTAS == 1: two 128-column accumulators
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* s_epi = reinterpret_cast<float*>(smem + Q_SMEM_STAGES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Q_SMEM_STAGES + Q_SMEM_EPI);
+    uint64_t* full = bars;                          // [4]  TMA bytes of this CTA's stage
+    uint64_t* empty = bars + 4;                     // [4]  MMAs that read the stage have retired (commit)
+    uint64_t* a_full = bars + 8;                    // [4]  A of the stage is in TMEM (all stager warps of the pair)
+    uint64_t* acc_full = bars + 12;                 // [2]
+    uint64_t* acc_empty = bars + 14;                // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;
+    const int cid = blockIdx.x / CTAS, ncl = gridDim.x / CTAS;
+    const int nkb = p.K / BK;
+    const int bnt = bn_cta * CTAS;                  // tile width = accumulator columns
+    const uint32_t w_bytes = (uint32_t)bn_cta * BK * 4;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < Q_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); mbar_init(a_full + i, 4 * CTAS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 8 * CTAS); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        if (CTAS == 2) tmem_alloc_pair(tmem_slot, 512);
+        else tmem_alloc(tmem_slot, 512);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (CTAS == 2) cluster_sync_all();              // the peer's barriers exist before anything remote touches them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------- TMA producer -------------------------------
+        const uint32_t bytes = Q_TILE + (p.precise ? 2u : 1u) * w_bytes;
+        uint32_t it = 0;
+        for (int t = cid; t < total_tiles; t += ncl) {
+            const QTile c = q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, rank);
+            const int wrow = c.g * p.N + c.n0 + rank * bn_cta;
+            const int acol = (int)(c.g * p.a_gs);
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % Q_STAGES;
+                mbar_wait(empty + s, ((it / Q_STAGES) & 1) ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(full + s, bytes);
+                    uint8_t* dst = smem + (size_t)s * Q_STAGE_BYTES;
+                    tma_load_2d(&tm_a, dst, full + s, acol + kb * BK, c.row0);
+                    tma_load_2d(&tm_whi, dst + Q_TILE, full + s, kb * BK, wrow);
+                    if (p.precise) tma_load_2d(&tm_wlo, dst + 2 * Q_TILE, full + s, kb * BK, wrow);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------- MMA issuer (leader CTA) --------------------
+        if (rank == 0) {
+            const uint32_t idesc = tf32_instr_desc(bnt, 128 * CTAS);
+            uint32_t it = 0, ti = 0;
+            for (int t = cid; t < total_tiles; t += ncl, ++ti) {
+                const uint32_t ab = ti % ACC_BUFS;
+                const uint32_t aph = ((ti / ACC_BUFS) & 1) ^ 1;
+                if (CTAS == 2) mbar_wait_cluster(acc_empty + ab, aph); else mbar_wait(acc_empty + ab, aph);
+                const uint32_t acc = tmem_base + ab * 128;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % Q_STAGES;
+                    const uint32_t ph = (it / Q_STAGES) & 1;
+                    mbar_wait(full + s, ph);
+                    if (CTAS == 2) mbar_wait_cluster(a_full + s, ph); else mbar_wait(a_full + s, ph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t w_hi = smem_u32(smem + (size_t)s * Q_STAGE_BYTES + Q_TILE);
+                        const uint64_t bhi0 = sw128_desc(w_hi), blo0 = sw128_desc(w_hi + Q_TILE);
+                        const uint32_t a0 = tmem_base + Q_TMEM_A0 + s * 2 * BK;
+#pragma unroll
+                        for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                            const uint64_t bhi = bhi0 + (uint64_t)(ks * 2), blo = blo0 + (uint64_t)(ks * 2);
+                            const uint32_t a_hi = a0 + ks * UMMA_K;
+                            const uint32_t acc_on = (kb | ks) != 0;
+                            if (CTAS == 2) {
+                                umma_ts_pair(acc, a_hi, bhi, idesc, acc_on);
+                                if (p.precise) { umma_ts_pair(acc, a_hi + BK, bhi, idesc, 1u); umma_ts_pair(acc, a_hi, blo, idesc, 1u); }
+                            } else {
+                                umma_ts(acc, a_hi, bhi, idesc, acc_on);
+                                if (p.precise) { umma_ts(acc, a_hi + BK, bhi, idesc, 1u); umma_ts(acc, a_hi, blo, idesc, 1u); }
+                            }
+                        }
+                        if (CTAS == 2) {
+                            umma_commit_pair(empty + s);
+                            if (kb == nkb - 1) umma_commit_pair(acc_full + ab);
+                        } else {
+                            umma_commit(empty + s);
+                            if (kb == nkb - 1) umma_commit(acc_full + ab);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp < 10) {
+        // ------------------------------- A stagers (two groups) ----------------------
+        const int grp = (warp - 2) >> 2;
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const int my_tiles = (total_tiles - cid + ncl - 1) / ncl;
+        const uint32_t total_it = (uint32_t)my_tiles * nkb;
+        const int sw = r & 7;
+        for (uint32_t it = grp; it < total_it; it += 2) {
+            const int s = it % Q_STAGES;
+            mbar_wait(full + s, (it / Q_STAGES) & 1);
+            // this stage's previous tenant (iteration it-4) has been consumed: its commit is what let the TMA refill it
+            const uint8_t* arow = smem + (size_t)s * Q_STAGE_BYTES + r * 128;
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 v = *reinterpret_cast<const uint4*>(arow + ((c ^ sw) << 4));
+                hi[c * 4 + 0] = v.x; hi[c * 4 + 1] = v.y; hi[c * 4 + 2] = v.z; hi[c * 4 + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const uint32_t raw = hi[i];
+                hi[i] = p.precise ? (raw & 0xffffe000u) : raw;
+                lo[i] = __float_as_uint(__uint_as_float(raw) - __uint_as_float(hi[i]));
+            }
+            tc_fence_after();
+            const uint32_t ta = tmem_base + lane_base + Q_TMEM_A0 + s * 2 * BK;
+            tmem_st32(ta, hi);
+            if (p.precise) tmem_st32(ta + BK, lo);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (CTAS == 2) mbar_arrive_remote(a_full + s, 0); else mbar_arrive(a_full + s);
+            }
+        }
+    } else {
+        // ------------------------------- epilogue (8 warps) --------------------------
+        const int ew = warp - 10;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        float* stage = s_epi + ew * 1024;
+        const int nchunks = bnt / 32;
+        uint32_t ti = 0;
+        for (int t = cid; t < total_tiles; t += ncl, ++ti) {
+            const uint32_t ab = ti % ACC_BUFS;
+            const QTile c = q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, rank);
+            const int r = q * 32 + lane;
+            const bool row_ok = r < c.rows_valid;
+            const int row = c.row0 + r;
+            const float* bias = p.bias ? p.bias + c.g * p.bias_gs : nullptr;
+            if (bias && p.bias_crop_stride) bias += (size_t)((row_ok ? row : 0) / p.rows_per_crop) * p.bias_crop_stride;
+            float* pool = s_epi + (ti & 1) * 4 * 256;          // aliases the transpose tiles (never both in one launch)
+            mbar_wait(acc_full + ab, (ti / ACC_BUFS) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int ch = half; ch < nchunks; ch += 2) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + lane_base + ab * 128 + ch * 32, v);
+                const int col = c.n0 + ch * 32;
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float x = __uint_as_float(v[i]);
+                    if (bias && col + i < p.N) x += __ldg(bias + col + i);
+                    if (p.relu) x = fmaxf(x, 0.0f);
+                    f[i] = x;
+                }
+                if (p.pool_partial) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = row_ok ? f[i] : 0.0f;
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int i = 0; i < off; ++i) {
+                            const float send = up ? f[i] : f[i + off];
+                            const float keep = up ? f[i + off] : f[i];
+                            f[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    pool[q * 256 + ch * 32 + lane] = f[0];
+                } else {
+                    // transpose through a swizzled 32x32 tile: lane == row on the way in, 8 lanes == one 128 B row out
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                            make_float4(f[j * 4], f[j * 4 + 1], f[j * 4 + 2], f[j * 4 + 3]);
+                    __syncwarp();
+                    float* cbase = p.C + c.g * p.c_gs + (size_t)(c.row0 + q * 32) * p.ldc + col;
+                    const int rr = lane >> 3, cc = lane & 7;
+#pragma unroll
+                    for (int ps = 0; ps < 8; ++ps) {
+                        const int lr = ps * 4 + rr;
+                        if (q * 32 + lr < c.rows_valid && col + cc * 4 < p.N) {
+                            const float4 o = *reinterpret_cast<const float4*>(stage + lr * 32 + ((cc ^ (lr & 7)) << 2));
+                            *reinterpret_cast<float4*>(cbase + (size_t)lr * p.ldc + cc * 4) = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (CTAS == 2) mbar_arrive_remote(acc_empty + ab, 0); else mbar_arrive(acc_empty + ab);
+            }
+            if (p.pool_partial) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 epilogue warps
+                const int tt = threadIdx.x - 320;
+                if (tt < bnt && c.n0 + tt < p.N && c.rows_valid > 0) {
+                    const float s = ((pool[tt] + pool[256 + tt]) + pool[512 + tt]) + pool[768 + tt];
+                    p.pool_partial[((size_t)c.crop * p.tiles_per_crop + c.pool_tile) * p.N + c.n0 + tt] = s;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (CTAS == 2) cluster_sync_all();              // nobody leaves while the peer may still read / signal this CTA
+    if (warp == 1) {
+        tc_fence_after();
+        if (CTAS == 2) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -731,6 +901,63 @@ int launch_persistent(const CUtensorMap& mhi, const CUtensorMap& mlo, const TcPa
     return 0;
 }
 
+template <int CTAS>
+int launch_q(const TcParams& p, const float* W_hi, const float* W_lo, int ldw, int groups, cudaStream_t s)
+{
+    static int max_clusters = 0;
+    if (!max_clusters) {
+        int dev = 0, num_sms = 0;
+        cudaGetDevice(&dev);
+        cudaError_t e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(gemm_tc_q_kernel<CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_TOTAL);
+        if (e != cudaSuccess) return (int)e;
+        int n = num_sms / CTAS;
+        if (CTAS == 2) {
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3(num_sms / 2 * 2); q.blockDim = dim3(Q_THREADS); q.dynamicSmemBytes = Q_SMEM_TOTAL;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            q.attrs = at; q.numAttrs = 1;
+            int occ = 0;
+            if (cudaOccupancyMaxActiveClusters(&occ, gemm_tc_q_kernel<CTAS>, &q) == cudaSuccess && occ > 0 && occ < n) n = occ;
+            (void)cudaGetLastError();
+        }
+        max_clusters = n;
+    }
+    // widest tile that divides N (grouped layers must not straddle groups; otherwise the tail is masked)
+    int bn_cta = 0;
+    const int cand[3] = {128, 96, 64};
+    for (int i = 0; i < 3 && !bn_cta; ++i)
+        if (p.N % (cand[i] * CTAS) == 0) bn_cta = cand[i];
+    if (!bn_cta) { if (groups > 1) return DF_ERR_UNSUPPORTED; bn_cta = 128; }
+    if (CTAS == 1 && bn_cta != 128 && groups == 1 && p.N % 128 != 0) bn_cta = 128;
+    const int bnt = bn_cta * CTAS;
+    // the A operand as a 2-D tensor: group g's columns start at g*a_gs inside the row
+    const long long a_cols = (long long)(groups - 1) * p.a_gs + p.K;
+    if (a_cols > p.lda || (groups > 1 && p.a_gs < 0)) return DF_ERR_UNSUPPORTED;
+    CUtensorMap ma, mhi, mlo;
+    if (!make_map(&ma, p.A, p.M, (int)a_cols, p.lda, 128)) return DF_ERR_UNSUPPORTED;
+    const long long wrows = (long long)groups * p.N;
+    if (!make_map(&mhi, W_hi, wrows, p.K, ldw, bn_cta)) return DF_ERR_UNSUPPORTED;
+    if (!make_map(&mlo, p.precise ? W_lo : W_hi, wrows, p.K, ldw, bn_cta)) return DF_ERR_UNSUPPORTED;
+    const int rows_per_mtile = 128 * CTAS;
+    const int m_tiles = p.pool_partial ? (p.M / p.rows_per_crop) * ((p.rows_per_crop + rows_per_mtile - 1) / rows_per_mtile)
+                                       : (p.M + rows_per_mtile - 1) / rows_per_mtile;
+    const int n_tiles = (p.N + bnt - 1) / bnt;
+    const int total = m_tiles * n_tiles * groups;
+    const int clusters = total < max_clusters ? total : max_clusters;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * CTAS); cfg.blockDim = dim3(Q_THREADS); cfg.dynamicSmemBytes = Q_SMEM_TOTAL; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_q_kernel<CTAS>, ma, mhi, mlo, p, bn_cta, m_tiles, n_tiles, total);
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
 __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -739,6 +966,18 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict
     const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
     hi[i] = h;
     lo[i] = v - h;
+}
+
+// DF_TC_VARIANT=4|5|6 overrides the automatic choice (A/B timing runs)
+int default_variant()
+{
+    static int v = 0;
+    if (!v) {
+        const char* e = getenv("DF_TC_VARIANT");
+        v = e ? atoi(e) : 0;
+        if (v < 4 || v > 6) v = 4;
+    }
+    return v;
 }
 
 }  // namespace
@@ -775,10 +1014,20 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
     p.pool_partial = pool_partial;
     p.tiles_per_crop = pool_partial ? (p.rows_per_crop + BM - 1) / BM : 0;
 
-    // variant: 0 = auto (persistent kernel); 1 = BN128/TMEM-A, 2 = BN256/TMEM-A, 3 = BN128/smem-A (one tile per CTA,
-    // bring-up kernels); 4 = persistent warp-specialised kernel (production)
+    // variant: 0 = auto; 1 = BN128/TMEM-A, 2 = BN256/TMEM-A, 3 = BN128/smem-A (one tile per CTA, bring-up kernels);
+    // 4 = persistent kernel, A read from global by the stagers; 5 = persistent, A by TMA; 6 = 5 on CTA pairs
+    // (cta_group::2, 256-row tiles)
     int v = variant;
-    if (v == 0) v = 4;
+    if (v == 0) v = default_variant();
+    if (v == 5 || v == 6) {
+        const int rc = v == 5 ? launch_q<1>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream)
+                              : launch_q<2>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream);
+        if (rc != DF_ERR_UNSUPPORTED || variant != 0) {
+            if (rc) return rc;
+            DF_RETURN_LAST_ERROR();
+        }
+        v = 4;                                   // auto mode: shapes the TMA-A form cannot address fall back to kernel 4
+    }
     const int bn = v == 2 ? 256 : 128;
     if (v == 2 && groups > 1 && N % 256) return DF_ERR_UNSUPPORTED;
     CUtensorMap mhi, mlo;

@@ -41,15 +41,12 @@ def case(name, M, N, K, precision, pooled=False, variant=0):
     print(f"{name:34s} M={M} N={N} K={K} {precision:7s} pooled={int(pooled)} v={variant}: {ms*1e3:8.1f} us  alg {tf:7.1f} TF/s  executed {tf*passes:7.1f} TF/s", flush=True)
 
 
-case("tower1 store", rows, 1920, 384, "3xtf32")
-case("tower1 pooled(no store)", rows, 1920, 384, "3xtf32", pooled=True)
-case("tower1 tf32 store", rows, 1920, 384, "tf32")
-case("tower1 tf32 pooled", rows, 1920, 384, "tf32", pooled=True)
-case("bigK store", rows, 1920, 1536, "3xtf32")
-case("bigK pooled", rows, 1920, 1536, "3xtf32", pooled=True)
-case("bigK tf32 pooled", rows, 1920, 1536, "tf32", pooled=True)
-case("conv6 pooled", rows, 1024, 512, "3xtf32", pooled=True)
-case("conv6 pooled v2(BN256 nonpers)", rows, 1024, 512, "3xtf32", pooled=True, variant=2)
-case("conv5 store", rows, 512, 256, "3xtf32")
-case("large M tower1 store", rows * 4, 1920, 384, "3xtf32")
-case("large M bigK pooled", rows * 4, 1920, 1536, "3xtf32", pooled=True)
+variants = [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else [4, 5, 6]
+for v in variants:
+    case("tower1 store", rows, 1920, 384, "3xtf32", variant=v)
+    case("tower1 tf32 store", rows, 1920, 384, "tf32", variant=v)
+    case("conv6 pooled", rows, 1024, 512, "3xtf32", pooled=True, variant=v)
+    case("conv5 store", rows, 512, 256, "3xtf32", variant=v)
+    case("bigK store", rows, 1920, 1536, "3xtf32", variant=v)
+    case("bigK tf32 store", rows, 1920, 1536, "tf32", variant=v)
+    case("large M tower1 store", rows * 4, 1920, 384, "3xtf32", variant=v)

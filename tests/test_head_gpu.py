@@ -11,6 +11,15 @@ from util import build_nets, rel
 
 pytestmark = pytest.mark.gpu
 
+import os
+
+
+def _variants(default):
+    """DF_TEST_VARIANTS=5,6 restricts the tensor-core kernel variants under test (bring-up runs in separate processes)."""
+    env = os.environ.get("DF_TEST_VARIANTS")
+    return [int(v) for v in env.split(",")] if env else default
+
+
 # stated bounds per arithmetic mode (max-abs error / max-abs value)
 TOL = {"fp32": 1e-4, "3xtf32": 1e-4, "tf32": 5e-3}
 
@@ -30,10 +39,11 @@ def test_gemm_fp32_vs_float64(M, N, K):
     assert rel(y, _ref_linear(x, w, b, True)) < 2e-6
 
 
-@pytest.mark.parametrize("variant", [3, 1, 2, 4])
+@pytest.mark.parametrize("variant", _variants([3, 1, 2, 4, 5, 6]))
 @pytest.mark.parametrize("precision", ["3xtf32", "tf32"])
 def test_gemm_tensor_core_variants(variant, precision):
-    """variant 3: A staged through shared memory; 1/2: A through TMEM with N tile 128/256; 4: persistent kernel."""
+    """variant 3: A staged through shared memory; 1/2: A through TMEM with N tile 128/256; 4: persistent kernel;
+    5: persistent with the A operand by TMA; 6: the same on CTA pairs (cta_group::2, 256-row tiles)."""
     from densefusion_b200 import ops
     g = torch.Generator().manual_seed(variant)
     M, N, K = 1000, 512, 384
@@ -55,7 +65,7 @@ def test_gemm_tensor_core_identity_layout():
     M, K = 256, 128
     x = (torch.arange(M * K, dtype=torch.float32).view(M, K) % 4093) / 64.0
     w = torch.eye(K)
-    for variant in (3, 1, 4):
+    for variant in _variants([3, 1, 4, 5, 6]):
         ops.TC_VARIANT = variant
         try:
             y = ops.linear(x.cuda(), w.cuda(), None, precision="3xtf32")
@@ -65,7 +75,7 @@ def test_gemm_tensor_core_identity_layout():
         assert torch.equal(y.cpu(), x), f"variant {variant}: first bad index {(y.cpu() != x).nonzero()[:4].tolist()}"
 
 
-@pytest.mark.parametrize("variant", [4, 1])
+@pytest.mark.parametrize("variant", _variants([4, 1, 5, 6]))
 def test_gemm_tensor_core_epilogues_match_fp32_kernel(variant):
     """per-crop bias, grouped (block-diagonal) and column-pool epilogues: 3xtf32 kernel vs the exact-fp32 kernel."""
     from densefusion_b200 import ops
@@ -115,6 +125,27 @@ def test_gemm_tensor_core_epilogues_match_fp32_kernel(variant):
     got, want = run("3xtf32", pooled), pooled("fp32")
     ref64 = torch.relu(A6.double() @ W6.w.double().t() + b6.double()).view(crops, n, 1024).sum(1)
     assert rel(got, ref64) < 1e-5 and rel(want, ref64) < 1e-5
+    # third tower layer: three groups of N = 128 (64 weight rows per CTA in the paired kernel), A is a column slice
+    A4 = torch.randn(rows, 768, generator=g).cuda()
+    W4 = ops.SplitWeight((torch.randn(3, 128, 256, generator=g) / 16).cuda())
+    b4 = torch.randn(384, generator=g).cuda()
+
+    def tower3(prec):
+        C = torch.zeros(rows, 384, device="cuda")
+        ops.gemm(A4, W4, b4, C, M=rows, N=128, K=256, lda=768, ldw=256, ldc=384, relu=True, precision=prec, groups=3,
+                 a_gs=256, w_gs=128 * 256, bias_gs=128, c_gs=128)
+        return C
+    assert rel(run("3xtf32", tower3), tower3("fp32")) < 1e-5
+    # conv5 of PoseNetFeat: A = columns 128:384 of the 384-wide point-feature buffer, M not a multiple of 256
+    pf = torch.randn(rows - 37, 384, generator=g).cuda()
+    W5 = ops.SplitWeight((torch.randn(512, 256, generator=g) / 16).cuda())
+    b5 = torch.randn(512, generator=g).cuda()
+
+    def conv5(prec):
+        C = torch.zeros(rows - 37, 512, device="cuda")
+        ops.gemm(pf[:, 128:], W5, b5, C, M=rows - 37, N=512, K=256, lda=384, ldw=256, ldc=512, relu=True, precision=prec)
+        return C
+    assert rel(run("3xtf32", conv5), conv5("fp32")) < 1e-5
 
 
 @pytest.mark.parametrize("precision", ["fp32", "3xtf32", "tf32"])
