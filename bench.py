@@ -222,7 +222,7 @@ def dominant_kernel_roofline(pipe, precision, peaks):
         peak_note = ("TF32 tcgen05 peak taken as half of the measured bf16 burst figure of MEASURED_PEAKS.json"
                      if "bf16_tflops" in peaks else "TF32 = half of the fallback 1.59 PFLOP/s bf16")
         bound = "tensor"
-        kname = "gemm_tc_kernel (tcgen05 kind::tf32, %s)" % precision
+        kname = "gemm_tc_q_kernel<2,2> (tcgen05.mma.cta_group::2 kind::tf32, TMA operands, %s)" % precision
     ach = flops / (ms * 1e-3) / 1e12
     return {"bound": bound, "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
             "traffic": None, "ms_per_launch": ms, "algorithmic_flops_per_launch": flops,

@@ -558,7 +558,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_whi, const __gr
 //   warp 1       MMA issuer + TMEM owner (leader CTA only issues; commits are multicast to both CTAs)
 //   warps 2-9    A stagers, two groups alternating k-blocks; arrive on the LEADER's a_full[s] (remote arrive from the peer)
 //   warps 10-17  epilogue: two warps per TMEM lane quarter, alternate 32-column chunks
-// TMEM (512 columns): accumulator(s) in [0,256), four A stages of 64 columns (hi | lo) in [256,512).
+// TMEM (512 columns): CTAS == 1: two 128-column accumulators in [0,256), four A stages of 64 columns (hi | lo) in
+// [256,512).  CTAS == 2: accumulators at 0 and 192 (two when the tile is <= 192 wide, so the stores of tile i overlap
+// the MMAs of tile i+1 -- 123 MB of tower-1 output cannot be left to bursts between tiles; one 256-wide accumulator
+// only for the store-free pooled epilogue), two A stages in [384,512).
 // ------------------------------------------------------------------------------------------------
 constexpr int Q_THREADS = 18 * 32;
 constexpr int Q_STAGES = 4;
@@ -567,7 +570,6 @@ constexpr int Q_STAGE_BYTES = 3 * Q_TILE;                    // A | W_hi | W_lo
 constexpr int Q_SMEM_STAGES = Q_STAGES * Q_STAGE_BYTES;      // 192 KB
 constexpr int Q_SMEM_EPI = 8 * 32 * 32 * 4;                  // 32 KB: one swizzled 32x32 transpose tile per epilogue warp
 constexpr int Q_SMEM_TOTAL = 1024 + Q_SMEM_STAGES + Q_SMEM_EPI + 512;
-constexpr int Q_TMEM_A0 = 256;
 static_assert(Q_SMEM_TOTAL <= 227 * 1024, "shared memory overflow");
 
 struct QTile {
@@ -597,13 +599,15 @@ __device__ __forceinline__ QTile q_decode(const TcParams& p, int t, int m_tiles,
     return c;
 }
 
-template <int CTAS>
+template <int CTAS, int A_STAGES>
 __global__ void __launch_bounds__(Q_THREADS, 1)
 gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_whi,
                  const __grid_constant__ CUtensorMap tm_wlo, const TcParams p, const int bn_cta, const int m_tiles,
                  const int n_tiles, const int total_tiles)
 {
-    constexpr int ACC_BUFS = CTAS == 1 ? 2 : 1;              // CTAS == 1: two 128-column accumulators
+    // A_STAGES TMEM A stages of 64 columns each at the top of TMEM; the accumulators share what is left below
+    constexpr int TMEM_A0 = 512 - A_STAGES * 64;
+    constexpr int ACC_STRIDE = TMEM_A0 / 2;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* s_epi = reinterpret_cast<float*>(smem + Q_SMEM_STAGES);
@@ -621,6 +625,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int nkb = p.K / BK;
     const int bnt = bn_cta * CTAS;                  // tile width = accumulator columns
     const uint32_t w_bytes = (uint32_t)bn_cta * BK * 4;
+    const uint32_t ACC_BUFS = bnt <= ACC_STRIDE ? 2 : 1;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < Q_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); mbar_init(a_full + i, 4 * CTAS); }
@@ -667,7 +672,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 const uint32_t ab = ti % ACC_BUFS;
                 const uint32_t aph = ((ti / ACC_BUFS) & 1) ^ 1;
                 if (CTAS == 2) mbar_wait_cluster(acc_empty + ab, aph); else mbar_wait(acc_empty + ab, aph);
-                const uint32_t acc = tmem_base + ab * 128;
+                const uint32_t acc = tmem_base + ab * ACC_STRIDE;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % Q_STAGES;
                     const uint32_t ph = (it / Q_STAGES) & 1;
@@ -677,7 +682,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     if (elect_one()) {
                         const uint32_t w_hi = smem_u32(smem + (size_t)s * Q_STAGE_BYTES + Q_TILE);
                         const uint64_t bhi0 = sw128_desc(w_hi), blo0 = sw128_desc(w_hi + Q_TILE);
-                        const uint32_t a0 = tmem_base + Q_TMEM_A0 + s * 2 * BK;
+                        const uint32_t a0 = tmem_base + TMEM_A0 + (it % A_STAGES) * 2 * BK;
 #pragma unroll
                         for (int ks = 0; ks < BK / UMMA_K; ++ks) {
                             const uint64_t bhi = bhi0 + (uint64_t)(ks * 2), blo = blo0 + (uint64_t)(ks * 2);
@@ -715,7 +720,9 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         for (uint32_t it = grp; it < total_it; it += 2) {
             const int s = it % Q_STAGES;
             mbar_wait(full + s, (it / Q_STAGES) & 1);
-            // this stage's previous tenant (iteration it-4) has been consumed: its commit is what let the TMA refill it
+            // TMEM A slot it % A_STAGES was last read by the MMAs of iteration it - A_STAGES.  With A_STAGES == Q_STAGES
+            // that is implied by full[s] (the commit that frees the slot is what let the TMA refill the stage); with
+            // fewer TMEM slots wait for that iteration's commit explicitly (same barrier the TMA producer watches).
             const uint8_t* arow = smem + (size_t)s * Q_STAGE_BYTES + r * 128;
             uint32_t hi[32], lo[32];
 #pragma unroll
@@ -729,8 +736,12 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 hi[i] = p.precise ? (raw & 0xffffe000u) : raw;
                 lo[i] = __float_as_uint(__uint_as_float(raw) - __uint_as_float(hi[i]));
             }
+            if (A_STAGES < Q_STAGES && it >= (uint32_t)A_STAGES) {      // (the loads and the split above overlap this wait)
+                const uint32_t prev = it - A_STAGES;
+                mbar_wait(empty + prev % Q_STAGES, (prev / Q_STAGES) & 1);
+            }
             tc_fence_after();
-            const uint32_t ta = tmem_base + lane_base + Q_TMEM_A0 + s * 2 * BK;
+            const uint32_t ta = tmem_base + lane_base + TMEM_A0 + (it % A_STAGES) * 2 * BK;
             tmem_st32(ta, hi);
             if (p.precise) tmem_st32(ta + BK, lo);
             tmem_st_wait();
@@ -763,7 +774,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll 1
             for (int ch = half; ch < nchunks; ch += 2) {
                 uint32_t v[32];
-                tmem_ld32(tmem_base + lane_base + ab * 128 + ch * 32, v);
+                tmem_ld32(tmem_base + lane_base + ab * ACC_STRIDE + ch * 32, v);
                 const int col = c.n0 + ch * 32;
                 float f[32];
 #pragma unroll
@@ -901,7 +912,7 @@ int launch_persistent(const CUtensorMap& mhi, const CUtensorMap& mlo, const TcPa
     return 0;
 }
 
-template <int CTAS>
+template <int CTAS, int A_STAGES>
 int launch_q(const TcParams& p, const float* W_hi, const float* W_lo, int ldw, int groups, cudaStream_t s)
 {
     static int max_clusters = 0;
@@ -910,7 +921,7 @@ int launch_q(const TcParams& p, const float* W_hi, const float* W_lo, int ldw, i
         cudaGetDevice(&dev);
         cudaError_t e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(gemm_tc_q_kernel<CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_TOTAL);
+        e = cudaFuncSetAttribute(gemm_tc_q_kernel<CTAS, A_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_TOTAL);
         if (e != cudaSuccess) return (int)e;
         int n = num_sms / CTAS;
         if (CTAS == 2) {
@@ -921,18 +932,35 @@ int launch_q(const TcParams& p, const float* W_hi, const float* W_lo, int ldw, i
             at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             q.attrs = at; q.numAttrs = 1;
             int occ = 0;
-            if (cudaOccupancyMaxActiveClusters(&occ, gemm_tc_q_kernel<CTAS>, &q) == cudaSuccess && occ > 0 && occ < n) n = occ;
+            if (cudaOccupancyMaxActiveClusters(&occ, gemm_tc_q_kernel<CTAS, A_STAGES>, &q) == cudaSuccess && occ > 0 && occ < n) n = occ;
             (void)cudaGetLastError();
         }
         max_clusters = n;
     }
-    // widest tile that divides N (grouped layers must not straddle groups; otherwise the tail is masked)
+    // Tile width.  Grouped layers must not straddle groups; otherwise a tail tile is masked.  Pairs: 192 or 128 keep two
+    // accumulators in TMEM (stores overlap the next tile); 256 only when nothing is stored (pooled epilogue).  Among the
+    // admissible widths take the one with the least work after wave quantisation (+32: fixed cost per tile).
     int bn_cta = 0;
-    const int cand[3] = {128, 96, 64};
-    for (int i = 0; i < 3 && !bn_cta; ++i)
-        if (p.N % (cand[i] * CTAS) == 0) bn_cta = cand[i];
-    if (!bn_cta) { if (groups > 1) return DF_ERR_UNSUPPORTED; bn_cta = 128; }
-    if (CTAS == 1 && bn_cta != 128 && groups == 1 && p.N % 128 != 0) bn_cta = 128;
+    const int rows_per_mtile = 128 * CTAS;
+    const int m_tiles = p.pool_partial ? (p.M / p.rows_per_crop) * ((p.rows_per_crop + rows_per_mtile - 1) / rows_per_mtile)
+                                       : (p.M + rows_per_mtile - 1) / rows_per_mtile;
+    if (CTAS == 1) {
+        bn_cta = 128;
+        if (groups > 1 && p.N % 128) return DF_ERR_UNSUPPORTED;
+    } else {
+        const int widths[3] = {256, 192, 128};
+        long long best = -1;
+        for (int i = 0; i < 3; ++i) {
+            const int w = widths[i];
+            if (w == 256 && !p.pool_partial) continue;
+            if (w == 192 && A_STAGES != 2) continue;
+            if (p.N % w != 0 && (groups > 1 || w == 256)) continue;
+            const long long tiles = (long long)m_tiles * ((p.N + w - 1) / w) * groups;
+            const long long cost = ((tiles + max_clusters - 1) / max_clusters) * (w + 32);
+            if (best < 0 || cost < best) { best = cost; bn_cta = w / 2; }
+        }
+        if (!bn_cta) return DF_ERR_UNSUPPORTED;
+    }
     const int bnt = bn_cta * CTAS;
     // the A operand as a 2-D tensor: group g's columns start at g*a_gs inside the row
     const long long a_cols = (long long)(groups - 1) * p.a_gs + p.K;
@@ -942,9 +970,6 @@ int launch_q(const TcParams& p, const float* W_hi, const float* W_lo, int ldw, i
     const long long wrows = (long long)groups * p.N;
     if (!make_map(&mhi, W_hi, wrows, p.K, ldw, bn_cta)) return DF_ERR_UNSUPPORTED;
     if (!make_map(&mlo, p.precise ? W_lo : W_hi, wrows, p.K, ldw, bn_cta)) return DF_ERR_UNSUPPORTED;
-    const int rows_per_mtile = 128 * CTAS;
-    const int m_tiles = p.pool_partial ? (p.M / p.rows_per_crop) * ((p.rows_per_crop + rows_per_mtile - 1) / rows_per_mtile)
-                                       : (p.M + rows_per_mtile - 1) / rows_per_mtile;
     const int n_tiles = (p.N + bnt - 1) / bnt;
     const int total = m_tiles * n_tiles * groups;
     const int clusters = total < max_clusters ? total : max_clusters;
@@ -954,7 +979,7 @@ int launch_q(const TcParams& p, const float* W_hi, const float* W_lo, int ldw, i
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_q_kernel<CTAS>, ma, mhi, mlo, p, bn_cta, m_tiles, n_tiles, total);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_q_kernel<CTAS, A_STAGES>, ma, mhi, mlo, p, bn_cta, m_tiles, n_tiles, total);
     return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -968,14 +993,14 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict
     lo[i] = v - h;
 }
 
-// DF_TC_VARIANT=4|5|6 overrides the automatic choice (A/B timing runs)
+// DF_TC_VARIANT=4..7 overrides the automatic choice (A/B timing runs)
 int default_variant()
 {
     static int v = 0;
     if (!v) {
         const char* e = getenv("DF_TC_VARIANT");
         v = e ? atoi(e) : 0;
-        if (v < 4 || v > 6) v = 4;
+        if (v < 4 || v > 7) v = 6;
     }
     return v;
 }
@@ -1015,13 +1040,14 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
     p.tiles_per_crop = pool_partial ? (p.rows_per_crop + BM - 1) / BM : 0;
 
     // variant: 0 = auto; 1 = BN128/TMEM-A, 2 = BN256/TMEM-A, 3 = BN128/smem-A (one tile per CTA, bring-up kernels);
-    // 4 = persistent kernel, A read from global by the stagers; 5 = persistent, A by TMA; 6 = 5 on CTA pairs
-    // (cta_group::2, 256-row tiles)
+    // 4 = persistent kernel, A read from global by the stagers; 5 = persistent, A by TMA; 6 / 7 = 5 on CTA pairs
+    // (cta_group::2, 256-row tiles) with 2 / 4 TMEM A stages (accumulators up to 192 / 128 columns double-buffered)
     int v = variant;
     if (v == 0) v = default_variant();
-    if (v == 5 || v == 6) {
-        const int rc = v == 5 ? launch_q<1>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream)
-                              : launch_q<2>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream);
+    if (v >= 5 && v <= 7) {
+        const int rc = v == 5 ? launch_q<1, 4>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream)
+                     : v == 6 ? launch_q<2, 2>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream)
+                              : launch_q<2, 4>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream);
         if (rc != DF_ERR_UNSUPPORTED || variant != 0) {
             if (rc) return rc;
             DF_RETURN_LAST_ERROR();

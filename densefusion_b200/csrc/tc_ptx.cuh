@@ -150,28 +150,18 @@ __device__ __forceinline__ void cluster_sync_all()
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive (release, cluster scope) on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+// Arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster.  Default (.release.cta)
+// semantics on purpose: the payload is TMEM / shared memory ordered by tcgen05.fence + wait::st, not global memory, and
+// a .release.cluster arrive costs MEMBAR.ALL.GPU + ERRBAR per call (measured: it paced the paired kernel at ~1400
+// cycles per k-block whatever the number of MMA passes).
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta)
 {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
-// wait with cluster-scope acquire (pairs with mbar_arrive_remote from the peer CTA)
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity)
-{
-    const uint32_t addr = smem_u32(bar);
-    const long long t0 = clock64();
-    uint32_t ok = 0;
-    while (true) {
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-        if (ok) break;
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
-}
+// Waiting side of mbar_arrive_remote: the ordinary CTA-scope wait (an .acquire.cluster wait adds CCTL.IVALL per success).
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot, uint32_t cols)
 {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");

@@ -83,9 +83,13 @@ int df_gemm_rows_per_pool_tile(void);
 
 /* Tensor-core form of the same contract.  W_hi / W_lo: the weight split once by df_split_tf32
  * (hi = w & 0xffffe000, lo = w - hi), group g's rows at g*N (stacked, pitch ldw).  precision 1 = 3xTF32
- * (needs W_lo), 2 = single-pass TF32 (W_lo may be NULL).  K % 32 == 0.  variant 0 = auto; 1/2 = N tile
- * 128/256 with the A operand staged through TMEM; 3 = N tile 128 with A staged through shared memory
- * (bring-up path).  Activations A and outputs stay plain fp32: the split of A happens in registers. */
+ * (needs W_lo), 2 = single-pass TF32 (W_lo may be NULL).  K % 32 == 0.  Activations A and outputs stay plain fp32:
+ * the hi / lo split of A happens in registers on the way into TMEM.
+ * variant 0 = auto (6, falling back to 4 for layouts a 2-D TMA tensor cannot address; env DF_TC_VARIANT overrides);
+ *   1/2 = one tile per CTA, N tile 128/256, A through TMEM;  3 = A through shared memory (bring-up);
+ *   4 = persistent warp-specialised kernel, stagers read A from global memory;
+ *   5 = persistent, A by TMA (128B-swizzled tiles), 128x128 tiles;
+ *   6/7 = 5 on CTA pairs: tcgen05.mma.cta_group::2, 256-row tiles, each CTA stages half of the weight tile. */
 int df_gemm_tc(const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
                int bias_crop_stride, float* C, int ldc, int M, int N, int K, int relu, int rows_per_crop,
                int groups, long long a_group_stride, long long bias_group_stride, long long c_group_stride,

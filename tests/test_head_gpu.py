@@ -39,7 +39,7 @@ def test_gemm_fp32_vs_float64(M, N, K):
     assert rel(y, _ref_linear(x, w, b, True)) < 2e-6
 
 
-@pytest.mark.parametrize("variant", _variants([3, 1, 2, 4, 5, 6]))
+@pytest.mark.parametrize("variant", _variants([3, 1, 2, 4, 5, 6, 7]))
 @pytest.mark.parametrize("precision", ["3xtf32", "tf32"])
 def test_gemm_tensor_core_variants(variant, precision):
     """variant 3: A staged through shared memory; 1/2: A through TMEM with N tile 128/256; 4: persistent kernel;
@@ -65,7 +65,7 @@ def test_gemm_tensor_core_identity_layout():
     M, K = 256, 128
     x = (torch.arange(M * K, dtype=torch.float32).view(M, K) % 4093) / 64.0
     w = torch.eye(K)
-    for variant in _variants([3, 1, 4, 5, 6]):
+    for variant in _variants([3, 1, 4, 5, 6, 7]):
         ops.TC_VARIANT = variant
         try:
             y = ops.linear(x.cuda(), w.cuda(), None, precision="3xtf32")
@@ -75,7 +75,7 @@ def test_gemm_tensor_core_identity_layout():
         assert torch.equal(y.cpu(), x), f"variant {variant}: first bad index {(y.cpu() != x).nonzero()[:4].tolist()}"
 
 
-@pytest.mark.parametrize("variant", _variants([4, 1, 5, 6]))
+@pytest.mark.parametrize("variant", _variants([4, 1, 5, 6, 7]))
 def test_gemm_tensor_core_epilogues_match_fp32_kernel(variant):
     """per-crop bias, grouped (block-diagonal) and column-pool epilogues: 3xtf32 kernel vs the exact-fp32 kernel."""
     from densefusion_b200 import ops
