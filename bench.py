@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--workload", default="pose", choices=["pose", "train"],
+                    help="pose: the headline metric; train: config C4, data-parallel training step (16 samples / GPU / step)")
+    ap.add_argument("--phase", default="estimator", choices=["estimator", "refiner"])
     return ap.parse_args()
 
 
@@ -383,6 +386,131 @@ def run_ours(args):
         print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------
+# config C4: data-parallel training step (tools/train.py:143-169), 16 samples per GPU per optimiser step
+# ------------------------------------------------------------------------------------------------
+TRAIN_MIX = [(80, 80)] * 6 + [(120, 120)] * 6 + [(160, 160)] * 4
+
+
+def make_train_buckets(seed: int, pin: bool):
+    from densefusion_b200 import synth
+    g = torch.Generator().manual_seed(seed)
+    buckets = []
+    for hw in sorted(set(TRAIN_MIX)):
+        b = TRAIN_MIX.count(hw)
+        img = torch.randn(b, 3, hw[0], hw[1], generator=g)
+        choose = torch.stack([torch.sort(torch.randperm(hw[0] * hw[1], generator=g)[:N_POINTS])[0] for _ in range(b)])
+        points = torch.randn(b, N_POINTS, 3, generator=g) * 0.05 + torch.tensor([0.0, 0.0, 0.8])
+        model = torch.randn(b, N_MESH, 3, generator=g) * 0.05
+        rot = torch.stack([synth.quat_to_rot(synth.random_unit_quaternion(g)) for _ in range(b)])
+        target = torch.bmm(model, rot.transpose(1, 2)) + torch.tensor([0.0, 0.0, 0.8])
+        idx = torch.randint(0, N_OBJ, (b, 1), generator=g)
+        d = dict(img=img, points=points, choose=choose.view(b, 1, N_POINTS), idx=idx, target=target.contiguous(),
+                 model_points=model)
+        if pin:
+            d = {k: v.pin_memory() for k, v in d.items()}
+        buckets.append(d)
+    return buckets
+
+
+def measure_train(dev, phase, steps, warmup, world, rank, barrier, no_graph=False):
+    """ms per optimiser step (max over ranks done by the caller) with device-resident inputs and end to end."""
+    from densefusion_b200 import synth
+    from densefusion_b200.trainer import DataParallelTrainer, GraphedTrainStep
+    est, ref, _, _ = build_modules(dev)
+    tr = DataParallelTrainer(est, ref, N_MESH, synth.YCB_SYM, lr=1e-4, w=0.015, iteration=ITERS, phase=phase)
+    host_sets = [make_train_buckets(7000 + 31 * rank + s, pin=True) for s in range(2)]
+    dev_sets = [[{k: v.to(dev) for k, v in b.items()} for b in hs] for hs in host_sets]
+    samples = sum(b["points"].shape[0] for b in host_sets[0])
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    graphed, launch = None, "stream"
+    if not no_graph:
+        try:
+            graphed = GraphedTrainStep(tr, dev_sets[0])
+            launch = "cuda_graph"
+        except Exception as e:
+            graphed, launch = None, f"stream (graph capture failed: {type(e).__name__}: {e})"[:200]
+            torch.cuda.synchronize()
+
+    def step_device(i):
+        return graphed.step(dev_sets[i & 1]) if graphed is not None else tr.step(dev_sets[i & 1])
+
+    def step_e2e(i):
+        if graphed is not None:
+            out = graphed.step(host_sets[i & 1])
+        else:
+            out = tr.step([{k: v.to(dev, non_blocking=True) for k, v in b.items()} for b in host_sets[i & 1]])
+        loss_host.copy_(out["loss_sum"].reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def timed(fn):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / steps
+
+    ms_dev = timed(step_device)
+    ms_e2e = timed(step_e2e)
+    h2d = sum(v.numel() * v.element_size() for b in host_sets[0] for v in b.values())
+    arena = tr.arena_est if phase == "estimator" else tr.arena_ref
+    return {"ms_per_step": ms_dev, "ms_per_step_e2e": ms_e2e, "samples_per_gpu": samples, "h2d_bytes_per_step": h2d,
+            "allreduce_bytes": arena.total * 4, "parameters": arena.numel, "launch": launch}
+
+
+def run_train(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --workload train: no CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = os.environ.get("DF_CUDNN_BENCHMARK", "1") == "1"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    r = measure_train(dev, args.phase, args.steps, args.warmup, world, rank, barrier, args.no_graph)
+    clocks = sampler.stop()
+    t = torch.tensor([r["ms_per_step"], r["ms_per_step_e2e"]], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    total = world * r["samples_per_gpu"]
+    if rank == 0:
+        print(json.dumps({
+            "metric": "training samples/sec (data-parallel step: forward, fused loss, backward, all-reduce SUM, Adam)",
+            "value": total / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
+            "data": "synthetic",
+            "config": {"workload": f"config C4: YCB PoseNet(500,21) {args.phase} phase, 16 samples per GPU per optimiser step "
+                                   "(6x80^2 + 6x120^2 + 4x160^2), gradient SUM semantics of tools/train.py:159-169",
+                       "global_batch": total, "phase": args.phase, "allreduce_bytes": r["allreduce_bytes"],
+                       "parameters": r["parameters"], "launch": r["launch"],
+                       "parallelism": f"dp{world}, one NCCL all-reduce per step"},
+            "clocks": clocks,
+            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": r["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e}}))
+    barrier()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def measure_extras(pipe, dev, args, peaks):
     """Per-stage numbers that explain the headline: head-only poses/s, and config C1 (ADD-S loss, 256 crops)."""
     from densefusion_b200 import ops, synth
@@ -437,5 +565,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "train":
+        run_train(a)
     else:
         run_ours(a)

@@ -39,6 +39,7 @@ SIGNATURES = {
     "df_select_out_backward": [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _i, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "df_gather_embedding_backward": [_p, _p, _p, _ll, _ll, _ll, _i, _i, _i, _p],
     "df_adam_step": [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _i, _p],
+    "df_adam_step_dev": [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _p, _p],
     "df_upsample_bilinear": [_p, _p, _ll, _i, _i, _i, _i, _i, _p],
     "df_gather_embedding": [_p, _p, _p, _p, _ll, _ll, _ll, _i, _i, _i, _p],
     "df_xyz_conv": [_p, _p, _p, _p, _i, _ll, _p],

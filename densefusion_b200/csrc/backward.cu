@@ -104,25 +104,51 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int split
     out[i] = accumulate ? out[i] + s : s;
 }
 
-// one CTA per (128-column slab, row group); 8 row-lanes x 32 column-quads, fixed-order tree
-__global__ void __launch_bounds__(256)
+// Column sums over the rows of a group.  One CTA per (32-column slab, group): 8 float4 column lanes x 128 row lanes, so
+// a (8000 x 1920) bias-gradient sum runs on 60 CTAs x 1024 threads with 16-byte loads instead of 15 CTAs walking
+// 4000 rows each (that first version was 12-31% of a training step).  float64 accumulation: these sums add thousands of
+// terms of mixed sign and the kernel is bandwidth-bound, so the wider adds are free.  Fixed-order tree -> deterministic.
+__global__ void __launch_bounds__(1024)
 colsum_rows_kernel(const float* __restrict__ X, int ldx, int rows_per_group, int C, float* __restrict__ out, int accumulate)
 {
-    // float64 accumulation: these sums (bias gradients, the per-crop gradient of the folded global feature) add
-    // thousands of terms of mixed sign; the kernel is bandwidth-bound, so the wider adds are free.
-    __shared__ double red[2][128];
-    const int grp = blockIdx.y, c = blockIdx.x * 128 + (threadIdx.x & 127) ;
-    const int lane_r = threadIdx.x >> 7;                    // 0..1
+    __shared__ double red[128][33];
+    const int grp = blockIdx.y, cq = threadIdx.x & 7, rl = threadIdx.x >> 3;
+    const int c = blockIdx.x * 32 + cq * 4;
     const float* base = X + (size_t)grp * rows_per_group * ldx;
-    double s = 0.0;
-    if (c < C)
-        for (int r = lane_r; r < rows_per_group; r += 2) s += (double)base[(size_t)r * ldx + c];
-    red[lane_r][threadIdx.x & 127] = s;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (c < C) {
+        if (c + 3 < C && (ldx & 3) == 0 && (((uintptr_t)X) & 15) == 0) {
+#pragma unroll 4
+            for (int r = rl; r < rows_per_group; r += 128) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)r * ldx + c));
+                s0 += (double)v.x; s1 += (double)v.y; s2 += (double)v.z; s3 += (double)v.w;
+            }
+        } else {
+            for (int r = rl; r < rows_per_group; r += 128) {
+                const float* q = base + (size_t)r * ldx + c;
+                s0 += (double)q[0];
+                if (c + 1 < C) s1 += (double)q[1];
+                if (c + 2 < C) s2 += (double)q[2];
+                if (c + 3 < C) s3 += (double)q[3];
+            }
+        }
+    }
+    red[rl][cq * 4 + 0] = s0; red[rl][cq * 4 + 1] = s1; red[rl][cq * 4 + 2] = s2; red[rl][cq * 4 + 3] = s3;
     __syncthreads();
-    if (threadIdx.x < 128 && c < C) {
-        const float t = (float)(red[0][threadIdx.x] + red[1][threadIdx.x]);
-        float* o = out + (size_t)grp * C + c;
-        *o = accumulate ? *o + t : t;
+    for (int half = 64; half >= 1; half >>= 1) {
+        if (rl < half) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) red[rl][cq * 4 + k] += red[rl + half][cq * 4 + k];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 32) {
+        const int cc = blockIdx.x * 32 + threadIdx.x;
+        if (cc < C) {
+            const float t = (float)red[0][threadIdx.x];
+            float* o = out + (size_t)grp * C + cc;
+            *o = accumulate ? *o + t : t;
+        }
     }
 }
 
@@ -265,6 +291,26 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     p[i] -= (lr / bc1) * (mi / denom);
 }
 
+// CUDA-graph friendly form: the step number lives in device memory (a captured launch cannot change its scalar arguments)
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                long long n, float lr, float b1, float b2, float eps, const int* __restrict__ step_ptr)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float step = (float)(*step_ptr + 1);
+    const float bc1 = 1.0f - powf(b1, step);
+    const float bc2_sqrt = sqrtf(1.0f - powf(b2, step));
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+}
+
+__global__ void bump_kernel(int* step_ptr) { *step_ptr += 1; }
+
 }  // namespace
 
 extern "C" int df_gemm_wgrad_fp32(const float* dY, int ldy, const float* X, int ldx, float* partial, int M, int N, int K,
@@ -289,7 +335,7 @@ extern "C" int df_colsum_rows(const float* X, int ldx, int rows_per_group, int g
                               void* stream)
 {
     if (!X || !out || rows_per_group <= 0 || groups <= 0 || groups > 65535 || C <= 0) return DF_ERR_ARG;
-    colsum_rows_kernel<<<dim3((C + 127) / 128, groups), 256, 0, (cudaStream_t)stream>>>(X, ldx, rows_per_group, C, out, accumulate);
+    colsum_rows_kernel<<<dim3((C + 31) / 32, groups), 1024, 0, (cudaStream_t)stream>>>(X, ldx, rows_per_group, C, out, accumulate);
     DF_RETURN_LAST_ERROR();
 }
 
@@ -346,5 +392,16 @@ extern "C" int df_adam_step(float* param, const float* grad, float* exp_avg, flo
     const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
     adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
                                                                              beta2, eps, bc1, bc2_sqrt);
+    DF_RETURN_LAST_ERROR();
+}
+
+extern "C" int df_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                                float beta1, float beta2, float eps, int* step_counter, void* stream)
+{
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !step_counter || n <= 0) return DF_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    adam_dev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                               step_counter);
+    bump_kernel<<<1, 1, 0, s>>>(step_counter);
     DF_RETURN_LAST_ERROR();
 }

@@ -9,11 +9,30 @@ import torch.nn.functional as F
 from . import extractors
 
 
+class _UpsampleFn(torch.autograd.Function):
+    """df_upsample_bilinear forward; the encoder is trained through torch/cuDNN, so its backward stays the library's
+    own aten kernel (same one F.interpolate's autograd would call)."""
+
+    @staticmethod
+    def forward(ctx, x, size, align_corners):
+        from .. import ops
+        ctx.in_shape, ctx.size, ctx.align = tuple(x.shape), (int(size[0]), int(size[1])), bool(align_corners)
+        return ops.upsample_bilinear(x, size, align_corners)
+
+    @staticmethod
+    def backward(ctx, g):
+        gi = torch.ops.aten.upsample_bilinear2d_backward(g.contiguous(), list(ctx.size), list(ctx.in_shape), ctx.align,
+                                                         None, None)
+        return gi, None, None
+
+
 def _upsample(x, size, align_corners: bool):
-    """Bilinear resize.  CUDA inference tensors go through df_upsample_bilinear (every output element is a thread;
-    torch's NCHW kernel loops over batch x channels inside one thread per output pixel and dominated the encoder).
-    Anything that needs autograd, a CPU tensor or a non-fp32 dtype stays on torch."""
-    if x.is_cuda and x.dtype == torch.float32 and not (torch.is_grad_enabled() and x.requires_grad):
+    """Bilinear resize.  CUDA fp32 tensors go through df_upsample_bilinear (every output element is a thread; torch's
+    NCHW kernel loops over batch x channels inside one thread per output pixel: 64% of the first inference step and
+    21% of a training step).  CPU tensors or other dtypes stay on torch."""
+    if x.is_cuda and x.dtype == torch.float32:
+        if torch.is_grad_enabled() and x.requires_grad:
+            return _UpsampleFn.apply(x, size, align_corners)
         from .. import ops
         return ops.upsample_bilinear(x, size, align_corners)
     return F.interpolate(x, size=size, mode="bilinear", align_corners=align_corners)

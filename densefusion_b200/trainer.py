@@ -51,7 +51,7 @@ class FlatArena:
         self.numel = sum(p.numel() for p in self.params)
         z = lambda: torch.zeros(self.total, device=dev, dtype=torch.float32)
         self.param, self.grad, self.exp_avg, self.exp_avg_sq = z(), z(), z(), z()
-        self.step_count = 0
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)      # optimiser step number, device resident
         with torch.no_grad():
             for p, o in zip(self.params, self.offsets):
                 n = p.numel()
@@ -74,10 +74,16 @@ class FlatArena:
     def adam_step(self, lr: float, betas=(0.9, 0.999), eps: float = 1e-8) -> None:
         if not self.param.is_cuda:
             raise DFError("FlatArena.adam_step: the optimiser step is a CUDA kernel (no CPU fallback)")
-        self.step_count += 1
-        check(lib.df_adam_step(ptr(self.param), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.total,
-                               float(lr), float(betas[0]), float(betas[1]), float(eps), self.step_count, stream()),
-              "df_adam_step")
+        check(lib.df_adam_step_dev(ptr(self.param), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.total,
+                                   float(lr), float(betas[0]), float(betas[1]), float(eps), ptr(self.step_dev), stream()),
+              "df_adam_step_dev")
+
+    def state(self) -> dict:
+        return {k: getattr(self, k).clone() for k in ("param", "exp_avg", "exp_avg_sq", "step_dev")}
+
+    def load_state(self, st: dict) -> None:
+        for k, v in st.items():
+            getattr(self, k).copy_(v)
 
 
 class DataParallelTrainer:
@@ -147,3 +153,40 @@ class DataParallelTrainer:
         arena.all_reduce(self.group)
         arena.adam_step(self.lr)
         return {"loss_sum": loss_sum, "dis_sum": dis_sum}
+
+
+class GraphedTrainStep:
+    """CUDA-graph capture of DataParallelTrainer.step for fixed bucket shapes: forward, fused loss, the explicit
+    backward kernels, cuDNN's encoder backward, the NCCL all-reduce and the Adam kernel replay as ONE graph launch
+    (a training step is ~1500 small launches; eager it is bound by the Python / launch path, not by the GPU).
+    Optimiser state is snapshotted around the warm-up so capturing does not advance training."""
+
+    def __init__(self, trainer: DataParallelTrainer, example_buckets, warmup: int = 3):
+        self.trainer = trainer
+        self.static = [{k: v.clone() for k, v in b.items()} for b in example_buckets]
+        arena = trainer.arena_est if trainer.phase == "estimator" else trainer.arena_ref
+        saved = arena.state()
+        dev = arena.param.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                trainer.step(self.static)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = trainer.step(self.static)
+        arena.load_state(saved)
+        arena.zero_grad()
+
+    def load(self, buckets) -> None:
+        for s, b in zip(self.static, buckets):
+            for k in s:
+                s[k].copy_(b[k], non_blocking=True)
+
+    def step(self, buckets=None) -> dict:
+        if buckets is not None:
+            self.load(buckets)
+        self.graph.replay()
+        return self.out

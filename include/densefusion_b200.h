@@ -146,6 +146,10 @@ int df_gather_embedding_backward(const float* demb, const int64_t* choose, float
                                  long long stride_c, long long stride_pix, int B, int N, int HW, void* stream);
 int df_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                  float beta1, float beta2, float eps, int step, void* stream);
+/* Same update with the step number kept on the device: uses *step_counter + 1 and then increments it, so the launch
+ * can be captured in a CUDA graph and replayed. */
+int df_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                     float beta1, float beta2, float eps, int* step_counter, void* stream);
 
 /* ---- encoder helper -----------------------------------------------------------------------------
  * NCHW bilinear up-sampling (lib/pspnet.py:20-23 F.upsample(size=...), :30-34 nn.Upsample(scale_factor=2,

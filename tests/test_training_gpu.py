@@ -205,3 +205,35 @@ def test_trainer_step_matches_oracle_adam(phase):
         print(f"{phase} step {step}: worst share of weights off by > 2e-6: head/refiner {worst['head'][0]:.4f} "
               f"({worst['head'][1]}), encoder {worst['cnn'][0]:.4f} ({worst['cnn'][1]})")
         assert worst["head"][0] < 0.02 and worst["cnn"][0] < 0.25
+
+
+@pytest.mark.parametrize("phase", ["estimator", "refiner"])
+def test_graphed_train_step_equals_eager(phase):
+    """The whole optimiser step captured in a CUDA graph (device-resident Adam step counter) replays to the same
+    parameters as eager launches, and capturing does not advance the optimiser state."""
+    from densefusion_b200.trainer import DataParallelTrainer, GraphedTrainStep
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.deterministic = True
+    try:
+        g, crops, n, o, m, iters, sym, w, est, ref, est_sd, ref_sd = _setup()
+        batches = [[_device_batch(crops[:2])], [_device_batch(crops[1:])]]
+        tr = DataParallelTrainer(est, ref, m, sym, lr=1e-4, w=w, iteration=iters, phase=phase)
+        arena = tr.arena_est if phase == "estimator" else tr.arena_ref
+        p0 = arena.param.clone()
+        gs = GraphedTrainStep(tr, batches[0])
+        assert torch.equal(arena.param, p0) and int(arena.step_dev) == 0
+        for b in batches:
+            out = gs.step(b)
+        graphed = arena.param.clone()
+        assert int(arena.step_dev) == 2 and torch.isfinite(out["loss_sum"]).all()
+        est2, ref2, _, _ = build_nets(n, o, int(g["meta"][5]))
+        tr2 = DataParallelTrainer(est2, ref2, m, sym, lr=1e-4, w=w, iteration=iters, phase=phase)
+        for b in batches:
+            tr2.step(b)
+        eager = (tr2.arena_est if phase == "estimator" else tr2.arena_ref).param
+        d = (graphed - eager).abs()
+        print(f"{phase}: graphed vs eager max diff {float(d.max()):.3e}")
+        assert float((d > 2e-6).float().mean()) < 0.01
+    finally:
+        torch.backends.cudnn.deterministic = False
