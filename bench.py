@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--encoder", default="auto", choices=["auto", "tc", "torch"],
+                    help="tc: hand-written tensor-core encoder (default with a tensor-core precision); torch: cuDNN fp32")
     ap.add_argument("--workload", default="pose", choices=["pose", "train"],
                     help="pose: the headline metric; train: config C4, data-parallel training step (16 samples / GPU / step)")
     ap.add_argument("--phase", default="estimator", choices=["estimator", "refiner"])
@@ -253,7 +255,7 @@ def run_ours(args):
     torch.backends.cudnn.benchmark = os.environ.get("DF_CUDNN_BENCHMARK", "1") == "1"
 
     est, ref, est_sd, ref_sd = build_modules(dev)
-    pipe = PoseEstimator(est, ref, iterations=ITERS, precision=args.precision, chunk_crops=args.chunk)
+    pipe = PoseEstimator(est, ref, iterations=ITERS, precision=args.precision, chunk_crops=args.chunk, encoder=args.encoder)
     # two distinct input sets per rank, alternated between steps
     host_sets = [make_host_buckets(args.frames, seed=1000 + 17 * rank + s, pin=True) for s in range(2)]
     dev_sets = [[{k: v.to(dev) for k, v in b.items()} for b in hs] for hs in host_sets]
@@ -364,7 +366,9 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": workload_name(args.frames), "num_points": N_POINTS, "num_obj": N_OBJ,
                            "refine_iterations": ITERS, "crops_per_gpu_per_step": crops_per_step,
-                           "precision": args.precision, "encoder": "torch/cuDNN strict fp32 (TF32 off), NCHW",
+                           "precision": args.precision,
+                           "encoder": ("densefusion_b200.encoder: tcgen05 implicit-GEMM convolutions, NHWC, " + args.precision)
+                           if pipe.encoder == "tc" else "torch/cuDNN strict fp32 (TF32 off), NCHW",
                            "launch": launch_mode, "chunk_crops": args.chunk,
                            "l2": "two alternating input sets; per-step working set (encoder activations > 1 GB) exceeds the 126 MB L2",
                            "parallelism": f"frames sharded over {world} GPU(s), no data-path collective"},

@@ -40,6 +40,13 @@ SIGNATURES = {
     "df_gather_embedding_backward": [_p, _p, _p, _ll, _ll, _ll, _i, _i, _i, _p],
     "df_adam_step": [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _i, _p],
     "df_adam_step_dev": [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _p, _p],
+    "df_conv_tc": [_p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p],
+    "df_enc_im2col_conv1": [_p, _p, _i, _i, _i, _i, _p],
+    "df_enc_maxpool": [_p, _p, _i, _i, _i, _i, _p],
+    "df_enc_im2col_s2": [_p, _p, _i, _i, _i, _i, _p],
+    "df_enc_adaptive_avgpool": [_p, _i, _p, _i, _i, _i, _i, _i, _p],
+    "df_enc_upsample": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "df_enc_log_softmax32": [_p, _ll, _p],
     "df_upsample_bilinear": [_p, _p, _ll, _i, _i, _i, _i, _i, _p],
     "df_gather_embedding": [_p, _p, _p, _p, _ll, _ll, _ll, _i, _i, _i, _p],
     "df_xyz_conv": [_p, _p, _p, _p, _i, _ll, _p],

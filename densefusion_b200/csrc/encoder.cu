@@ -1,0 +1,214 @@
+// NHWC helper kernels of the colour encoder (reference: lib/extractors.py:78-124, lib/pspnet.py:7-77).  The
+// convolutions themselves are implicit GEMMs on the tcgen05 kernel (df_conv_tc, gemm_tc.cu); what is left is
+// HBM-bound data movement: im2col for the three stride-2 layers, max / average pooling, bilinear resizing into a
+// channel slice of a wider buffer (the pyramid concat is never materialised separately) and the channel log-softmax.
+// All activations are channels-last so that a pixel's channels are one contiguous, float4-readable run.
+#include "df_common.cuh"
+#include "../../include/densefusion_b200.h"
+
+namespace {
+
+// conv1 (7x7, stride 2, pad 3) as a GEMM: A[pixel, c*49 + ky*7 + kx] from the NCHW image, zero-padded to ldk columns
+__global__ void __launch_bounds__(256)
+im2col_conv1_kernel(const float* __restrict__ img, float* __restrict__ A, int B, int H, int W, int Ho, int Wo, int ldk)
+{
+    const long long total = (long long)B * Ho * Wo * ldk;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % ldk);
+        const long long pix = i / ldk;
+        float v = 0.0f;
+        if (k < 147) {
+            const int c = k / 49, t = k - c * 49, ky = t / 7, kx = t - ky * 7;
+            const int xo = (int)(pix % Wo);
+            const long long r = pix / Wo;
+            const int yo = (int)(r % Ho), b = (int)(r / Ho);
+            const int y = yo * 2 - 3 + ky, x = xo * 2 - 3 + kx;
+            if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(img + (((size_t)b * 3 + c) * H + y) * W + x);
+        }
+        A[i] = v;
+    }
+}
+
+// 3x3 / stride 2 / pad 1 max pooling, NHWC, float4 over channels
+__global__ void __launch_bounds__(256)
+maxpool_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C, int Ho, int Wo)
+{
+    const int c4 = C >> 2;
+    const long long total = (long long)B * Ho * Wo * c4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cq = (int)(i % c4);
+        long long r = i / c4;
+        const int xo = (int)(r % Wo); r /= Wo;
+        const int yo = (int)(r % Ho), b = (int)(r / Ho);
+        float4 m = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int y = yo * 2 - 1 + dy;
+            if (y < 0 || y >= H) continue;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const int x = xo * 2 - 1 + dx;
+                if (x < 0 || x >= W) continue;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(in + (((size_t)b * H + y) * W + x) * C) + cq);
+                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+            }
+        }
+        reinterpret_cast<float4*>(out)[i] = m;
+    }
+}
+
+// 3x3 / stride 2 / pad 1 patches, NHWC -> A[pixel, tap*C + c]  (tap-major, like the repacked conv weights)
+__global__ void __launch_bounds__(256)
+im2col_s2_kernel(const float* __restrict__ in, float* __restrict__ A, int B, int H, int W, int C, int Ho, int Wo)
+{
+    const int c4 = C >> 2;
+    const long long total = (long long)B * Ho * Wo * 9 * c4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cq = (int)(i % c4);
+        long long r = i / c4;
+        const int tap = (int)(r % 9); r /= 9;
+        const int xo = (int)(r % Wo); r /= Wo;
+        const int yo = (int)(r % Ho), b = (int)(r / Ho);
+        const int y = yo * 2 - 1 + tap / 3, x = xo * 2 - 1 + tap % 3;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(reinterpret_cast<const float4*>(in + (((size_t)b * H + y) * W + x) * C) + cq);
+        reinterpret_cast<float4*>(A)[i] = v;
+    }
+}
+
+// nn.AdaptiveAvgPool2d((S,S)) on NHWC (pixel pitch ldi): bin i covers [floor(i*H/S), ceil((i+1)*H/S))
+__global__ void __launch_bounds__(256)
+adaptive_avgpool_kernel(const float* __restrict__ in, int ldi, float* __restrict__ out, int B, int H, int W, int C, int S)
+{
+    const long long total = (long long)B * S * S * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long r = i / C;
+        const int sx = (int)(r % S); r /= S;
+        const int sy = (int)(r % S), b = (int)(r / S);
+        const int y0 = (sy * H) / S, y1 = ((sy + 1) * H + S - 1) / S;
+        const int x0 = (sx * W) / S, x1 = ((sx + 1) * W + S - 1) / S;
+        float s = 0.0f;
+        for (int y = y0; y < y1; ++y)
+            for (int x = x0; x < x1; ++x) s += __ldg(in + (((size_t)b * H + y) * W + x) * ldi + c);
+        out[i] = s / (float)((y1 - y0) * (x1 - x0));
+    }
+}
+
+// bilinear resize NHWC (pixel pitches ldi / ldo, so the output may be a channel slice of a wider buffer); index and
+// weight arithmetic as ATen's area_pixel_compute_source_index, same as upsample.cu
+__global__ void __launch_bounds__(256)
+upsample_nhwc_kernel(const float* __restrict__ in, int ldi, float* __restrict__ out, int ldo, int B, int hin, int win,
+                     int hout, int wout, int C, float rh, float rw, int align)
+{
+    const int c4 = C >> 2;
+    const long long total = (long long)B * hout * wout * c4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cq = (int)(i % c4);
+        long long r = i / c4;
+        const int x = (int)(r % wout); r /= wout;
+        const int y = (int)(r % hout), b = (int)(r / hout);
+        float sy, sx;
+        if (align) { sy = rh * y; sx = rw * x; }
+        else {
+            sy = rh * (y + 0.5f) - 0.5f; sy = sy < 0.f ? 0.f : sy;
+            sx = rw * (x + 0.5f) - 0.5f; sx = sx < 0.f ? 0.f : sx;
+        }
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int yp = y0 < hin - 1 ? 1 : 0, xp = x0 < win - 1 ? 1 : 0;
+        const float ly1 = sy - y0, ly0 = 1.0f - ly1, lx1 = sx - x0, lx0 = 1.0f - lx1;
+        const float* p = in + (((size_t)b * hin + y0) * win + x0) * ldi + cq * 4;
+        const float4 v00 = __ldg(reinterpret_cast<const float4*>(p));
+        const float4 v01 = __ldg(reinterpret_cast<const float4*>(p + (size_t)xp * ldi));
+        const float4 v10 = __ldg(reinterpret_cast<const float4*>(p + (size_t)yp * win * ldi));
+        const float4 v11 = __ldg(reinterpret_cast<const float4*>(p + ((size_t)yp * win + xp) * ldi));
+        float4 o;
+        o.x = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
+        o.y = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
+        o.z = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
+        o.w = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
+        *reinterpret_cast<float4*>(out + (((size_t)b * hout + y) * wout + x) * ldo + cq * 4) = o;
+    }
+}
+
+// log_softmax over the 32 channels of every pixel (lib/pspnet.py:53-56), one warp per pixel, in place
+__global__ void __launch_bounds__(256)
+log_softmax32_kernel(float* __restrict__ x, long long pixels)
+{
+    const int lane = threadIdx.x & 31;
+    for (long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < pixels;
+         p += (long long)gridDim.x * (blockDim.x >> 5)) {
+        const float v = x[p * 32 + lane];
+        float m = v;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const float s = df::warp_sum(expf(v - m));
+        x[p * 32 + lane] = (v - m) - logf(s);
+    }
+}
+
+inline unsigned grid_for(long long total, int per_block)
+{
+    long long b = (total + per_block - 1) / per_block;
+    const long long cap = 148LL * 32;
+    return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+extern "C" int df_enc_im2col_conv1(const float* img, float* A, int B, int H, int W, int ldk, void* stream)
+{
+    if (!img || !A || B <= 0 || H <= 0 || W <= 0 || ldk < 147) return DF_ERR_ARG;
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    im2col_conv1_kernel<<<grid_for((long long)B * Ho * Wo * ldk, 256), 256, 0, (cudaStream_t)stream>>>(img, A, B, H, W, Ho, Wo, ldk);
+    DF_RETURN_LAST_ERROR();
+}
+
+extern "C" int df_enc_maxpool(const float* in, float* out, int B, int H, int W, int C, void* stream)
+{
+    if (!in || !out || B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3)) return DF_ERR_ARG;
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    maxpool_kernel<<<grid_for((long long)B * Ho * Wo * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, Ho, Wo);
+    DF_RETURN_LAST_ERROR();
+}
+
+extern "C" int df_enc_im2col_s2(const float* in, float* A, int B, int H, int W, int C, void* stream)
+{
+    if (!in || !A || B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3)) return DF_ERR_ARG;
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    im2col_s2_kernel<<<grid_for((long long)B * Ho * Wo * 9 * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(in, A, B, H, W, C, Ho, Wo);
+    DF_RETURN_LAST_ERROR();
+}
+
+extern "C" int df_enc_adaptive_avgpool(const float* in, int ldi, float* out, int B, int H, int W, int C, int S, void* stream)
+{
+    if (!in || !out || B <= 0 || H <= 0 || W <= 0 || C <= 0 || S <= 0 || ldi < C) return DF_ERR_ARG;
+    adaptive_avgpool_kernel<<<grid_for((long long)B * S * S * C, 256), 256, 0, (cudaStream_t)stream>>>(in, ldi, out, B, H, W, C, S);
+    DF_RETURN_LAST_ERROR();
+}
+
+extern "C" int df_enc_upsample(const float* in, int ldi, float* out, int ldo, int B, int hin, int win, int hout, int wout,
+                               int C, int align_corners, void* stream)
+{
+    if (!in || !out || B <= 0 || hin <= 0 || win <= 0 || hout <= 0 || wout <= 0 || C <= 0 || (C & 3) || (ldi & 3) || (ldo & 3))
+        return DF_ERR_ARG;
+    if (((uintptr_t)in & 15) || ((uintptr_t)out & 15)) return DF_ERR_ARG;
+    float rh, rw;
+    if (align_corners) {
+        rh = hout > 1 ? (float)(hin - 1) / (hout - 1) : 0.f;
+        rw = wout > 1 ? (float)(win - 1) / (wout - 1) : 0.f;
+    } else {
+        rh = (float)hin / hout;
+        rw = (float)win / wout;
+    }
+    upsample_nhwc_kernel<<<grid_for((long long)B * hout * wout * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(
+        in, ldi, out, ldo, B, hin, win, hout, wout, C, rh, rw, align_corners);
+    DF_RETURN_LAST_ERROR();
+}
+
+extern "C" int df_enc_log_softmax32(float* x, long long pixels, void* stream)
+{
+    if (!x || pixels <= 0) return DF_ERR_ARG;
+    log_softmax32_kernel<<<grid_for(pixels, 8), 256, 0, (cudaStream_t)stream>>>(x, pixels);
+    DF_RETURN_LAST_ERROR();
+}

@@ -42,6 +42,20 @@ struct TcParams {
     int rows_per_crop;
     long long a_gs, bias_gs, c_gs;
     float* pool_partial; int tiles_per_crop;
+    // ---- implicit-convolution form (generation-2 kernels only; conv_taps == 0: plain GEMM) ----
+    // A is an NHWC image (cB, cH, cW, K channels); an M tile is a (TB x TH x TW) patch of output pixels and the k loop
+    // walks taps x 32-channel blocks, each A tile being the patch shifted by the tap -- a 4-D TMA box whose
+    // out-of-image part is zero-filled, i.e. the convolution's zero padding costs nothing.
+    int conv_taps, conv_dil;                    // 1 or 9 (3x3, stride 1, padding == dilation)
+    int cW, cH, cB, TW, TH, TB, tiles_x, tiles_y, tiles_b;
+    const float* residual; int ldr;             // added before the activation (BasicBlock skip), same pixel order as C
+    const float* prelu;                         // relu == 2: y = x > 0 ? x : prelu[0] * x
+    // ---- chunked accumulation (generation-2 kernels): the k loop of one tile is cut into k_chunks runs of <= kbc k-blocks;
+    // every run starts a fresh TMEM accumulator and the epilogue adds the runs in fp32 (round-to-nearest) through C.
+    // Why: the tensor core truncates when it aligns the accumulator with new products, a bias that grows with the length
+    // of the chain (measured 3xTF32 error 3e-6 at K = 384 but 6.5e-5 at K = 9216); short chains keep long-K convolutions
+    // at fp32-parity.  k_chunks == 1: plain single-run accumulation.
+    int k_chunks, kbc;
 };
 
 }  // namespace
@@ -574,6 +588,7 @@ static_assert(Q_SMEM_TOTAL <= 227 * 1024, "shared memory overflow");
 
 struct QTile {
     int g, n0, row0, rows_valid, crop, pool_tile;
+    int x0, y0, b0;                              // convolution form: origin of this CTA's pixel patch
 };
 
 template <int CTAS>
@@ -586,7 +601,15 @@ __device__ __forceinline__ QTile q_decode(const TcParams& p, int t, int m_tiles,
     const int mt = rem / n_tiles;
     c.n0 = (rem - mt * n_tiles) * bnt;
     c.crop = 0; c.pool_tile = 0;
-    if (p.pool_partial) {
+    c.x0 = c.y0 = c.b0 = 0;
+    if (p.conv_taps) {
+        const int pt = mt * CTAS + rank;
+        const int tx = pt % p.tiles_x, rest = pt / p.tiles_x;
+        const int ty = rest % p.tiles_y, tb = rest / p.tiles_y;
+        c.x0 = tx * p.TW; c.y0 = ty * p.TH; c.b0 = tb * p.TB;      // tb >= tiles_b: a patch past the batch, fully masked
+        c.row0 = 0;
+        c.rows_valid = tb < p.tiles_b ? p.TW * p.TH * p.TB : 0;
+    } else if (p.pool_partial) {
         const int pairs_per_crop = (p.rows_per_crop + 128 * CTAS - 1) / (128 * CTAS);
         c.crop = mt / pairs_per_crop;
         c.pool_tile = (mt - c.crop * pairs_per_crop) * CTAS + rank;        // index of this CTA's 128-row tile in the crop
@@ -644,7 +667,9 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
     if (warp == 0) {
         // ------------------------------- TMA producer -------------------------------
-        const uint32_t bytes = Q_TILE + (p.precise ? 2u : 1u) * w_bytes;
+        const uint32_t a_bytes = p.conv_taps ? (uint32_t)(p.TW * p.TH * p.TB) * BK * 4 : (uint32_t)Q_TILE;
+        const uint32_t bytes = a_bytes + (p.precise ? 2u : 1u) * w_bytes;
+        const int cblocks = p.conv_taps ? p.K / (BK * p.conv_taps) : 1;        // 32-channel blocks per tap
         uint32_t it = 0;
         for (int t = cid; t < total_tiles; t += ncl) {
             const QTile c = q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, rank);
@@ -656,7 +681,14 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (elect_one()) {
                     mbar_expect_tx(full + s, bytes);
                     uint8_t* dst = smem + (size_t)s * Q_STAGE_BYTES;
-                    tma_load_2d(&tm_a, dst, full + s, acol + kb * BK, c.row0);
+                    if (p.conv_taps) {
+                        const int tap = kb / cblocks, cb = kb - tap * cblocks;
+                        const int dy = p.conv_taps == 9 ? (tap / 3 - 1) * p.conv_dil : 0;
+                        const int dx = p.conv_taps == 9 ? (tap % 3 - 1) * p.conv_dil : 0;
+                        tma_load_4d(&tm_a, dst, full + s, cb * BK, c.x0 + dx, c.y0 + dy, c.b0);
+                    } else {
+                        tma_load_2d(&tm_a, dst, full + s, acol + kb * BK, c.row0);
+                    }
                     tma_load_2d(&tm_whi, dst + Q_TILE, full + s, kb * BK, wrow);
                     if (p.precise) tma_load_2d(&tm_wlo, dst + 2 * Q_TILE, full + s, kb * BK, wrow);
                 }
@@ -668,12 +700,14 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (rank == 0) {
             const uint32_t idesc = tf32_instr_desc(bnt, 128 * CTAS);
             uint32_t it = 0, ti = 0;
-            for (int t = cid; t < total_tiles; t += ncl, ++ti) {
+            for (int t = cid; t < total_tiles; t += ncl) {
+              for (int kc = 0; kc < p.k_chunks; ++kc, ++ti) {
+                const int kb0 = kc * p.kbc, kb1 = min(nkb, kb0 + p.kbc);
                 const uint32_t ab = ti % ACC_BUFS;
                 const uint32_t aph = ((ti / ACC_BUFS) & 1) ^ 1;
                 if (CTAS == 2) mbar_wait_cluster(acc_empty + ab, aph); else mbar_wait(acc_empty + ab, aph);
                 const uint32_t acc = tmem_base + ab * ACC_STRIDE;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % Q_STAGES;
                     const uint32_t ph = (it / Q_STAGES) & 1;
                     mbar_wait(full + s, ph);
@@ -687,7 +721,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         for (int ks = 0; ks < BK / UMMA_K; ++ks) {
                             const uint64_t bhi = bhi0 + (uint64_t)(ks * 2), blo = blo0 + (uint64_t)(ks * 2);
                             const uint32_t a_hi = a0 + ks * UMMA_K;
-                            const uint32_t acc_on = (kb | ks) != 0;
+                            const uint32_t acc_on = (kb != kb0) || (ks != 0);
                             if (CTAS == 2) {
                                 umma_ts_pair(acc, a_hi, bhi, idesc, acc_on);
                                 if (p.precise) { umma_ts_pair(acc, a_hi + BK, bhi, idesc, 1u); umma_ts_pair(acc, a_hi, blo, idesc, 1u); }
@@ -698,14 +732,15 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         }
                         if (CTAS == 2) {
                             umma_commit_pair(empty + s);
-                            if (kb == nkb - 1) umma_commit_pair(acc_full + ab);
+                            if (kb == kb1 - 1) umma_commit_pair(acc_full + ab);
                         } else {
                             umma_commit(empty + s);
-                            if (kb == nkb - 1) umma_commit(acc_full + ab);
+                            if (kb == kb1 - 1) umma_commit(acc_full + ab);
                         }
                     }
                     __syncwarp();
                 }
+              }
             }
         }
     } else if (warp < 10) {
@@ -760,15 +795,46 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         float* stage = s_epi + ew * 1024;
         const int nchunks = bnt / 32;
         uint32_t ti = 0;
-        for (int t = cid; t < total_tiles; t += ncl, ++ti) {
+        for (int t = cid; t < total_tiles; t += ncl) {
+          for (int kc = 0; kc < p.k_chunks; ++kc, ++ti) {
+            const bool first_run = kc == 0, last_run = kc == p.k_chunks - 1;
             const uint32_t ab = ti % ACC_BUFS;
             const QTile c = q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, rank);
             const int r = q * 32 + lane;
             const bool row_ok = r < c.rows_valid;
-            const int row = c.row0 + r;
             const float* bias = p.bias ? p.bias + c.g * p.bias_gs : nullptr;
-            if (bias && p.bias_crop_stride) bias += (size_t)((row_ok ? row : 0) / p.rows_per_crop) * p.bias_crop_stride;
             float* pool = s_epi + (ti & 1) * 4 * 256;          // aliases the transpose tiles (never both in one launch)
+            // store path: after the transpose lane (rr, cc) owns 4 columns of rows ps*4 + rr, ps = 0..7, of this warp's
+            // 32 rows.  Per tile: where those rows live in C (element offset, -1 = masked) and which bias row they use.
+            const int rr = lane >> 3, cc = lane & 7;
+            int roff[8];                                       // row / pixel index, -1 = masked
+            int crop_first = 0, crop_boundary = 0x7fffffff;
+            if (!p.pool_partial) {
+                if (p.conv_taps) {
+#pragma unroll
+                    for (int ps = 0; ps < 8; ++ps) {
+                        const int R = q * 32 + ps * 4 + rr;
+                        const int rx = R % p.TW, rest = R / p.TW;
+                        const int ry = rest % p.TH, rb = rest / p.TH;
+                        const int x = c.x0 + rx, y = c.y0 + ry, b = c.b0 + rb;
+                        const bool ok = R < c.rows_valid && x < p.cW && y < p.cH && b < p.cB;
+                        roff[ps] = ok ? (b * p.cH + y) * p.cW + x : -1;
+                    }
+                } else {
+#pragma unroll
+                    for (int ps = 0; ps < 8; ++ps) {
+                        const int R = q * 32 + ps * 4 + rr;
+                        roff[ps] = R < c.rows_valid ? c.row0 + R : -1;
+                    }
+                    if (bias && p.bias_crop_stride) {
+                        crop_first = (c.row0 + q * 32) / p.rows_per_crop;
+                        crop_boundary = (crop_first + 1) * p.rows_per_crop;
+                    }
+                }
+            } else if (bias && p.bias_crop_stride) {
+                bias += (size_t)((row_ok ? c.row0 + r : 0) / p.rows_per_crop) * p.bias_crop_stride;
+            }
+            const float slope = p.relu == 2 ? __ldg(p.prelu) : 0.0f;
             mbar_wait(acc_full + ab, (ti / ACC_BUFS) & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -776,17 +842,15 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 uint32_t v[32];
                 tmem_ld32(tmem_base + lane_base + ab * ACC_STRIDE + ch * 32, v);
                 const int col = c.n0 + ch * 32;
-                float f[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float x = __uint_as_float(v[i]);
-                    if (bias && col + i < p.N) x += __ldg(bias + col + i);
-                    if (p.relu) x = fmaxf(x, 0.0f);
-                    f[i] = x;
-                }
                 if (p.pool_partial) {
+                    float f[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = row_ok ? f[i] : 0.0f;
+                    for (int i = 0; i < 32; ++i) {
+                        float x = __uint_as_float(v[i]);
+                        if (bias && col + i < p.N) x += __ldg(bias + col + i);
+                        if (p.relu) x = fmaxf(x, 0.0f);
+                        f[i] = row_ok ? x : 0.0f;
+                    }
 #pragma unroll
                     for (int off = 16; off >= 1; off >>= 1) {
                         const bool up = (lane & off) != 0;
@@ -799,21 +863,45 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     }
                     pool[q * 256 + ch * 32 + lane] = f[0];
                 } else {
-                    // transpose through a swizzled 32x32 tile: lane == row on the way in, 8 lanes == one 128 B row out
+                    // transpose through a swizzled 32x32 tile: lane == row on the way in, 8 lanes == one 128 B row out;
+                    // bias / skip connection / activation are applied on the way out (coalesced float4 reads)
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-                            make_float4(f[j * 4], f[j * 4 + 1], f[j * 4 + 2], f[j * 4 + 3]);
+                        *reinterpret_cast<uint4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                            make_uint4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
                     __syncwarp();
-                    float* cbase = p.C + c.g * p.c_gs + (size_t)(c.row0 + q * 32) * p.ldc + col;
-                    const int rr = lane >> 3, cc = lane & 7;
+                    const int cq = col + cc * 4;
+                    if (cq < p.N) {
 #pragma unroll
-                    for (int ps = 0; ps < 8; ++ps) {
-                        const int lr = ps * 4 + rr;
-                        if (q * 32 + lr < c.rows_valid && col + cc * 4 < p.N) {
-                            const float4 o = *reinterpret_cast<const float4*>(stage + lr * 32 + ((cc ^ (lr & 7)) << 2));
-                            *reinterpret_cast<float4*>(cbase + (size_t)lr * p.ldc + cc * 4) = o;
+                        for (int ps = 0; ps < 8; ++ps) {
+                            if (roff[ps] < 0) continue;
+                            const int lr = ps * 4 + rr;
+                            float4 o = *reinterpret_cast<const float4*>(stage + lr * 32 + ((cc ^ (lr & 7)) << 2));
+                            float* dst = p.C + c.g * p.c_gs + (size_t)roff[ps] * p.ldc + cq;
+                            if (!first_run) {                          // earlier runs of this tile, written by this very thread
+                                const float4 prev = *reinterpret_cast<const float4*>(dst);
+                                o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
+                            }
+                            if (!last_run) { *reinterpret_cast<float4*>(dst) = o; continue; }
+                            if (bias) {
+                                const float* brow = bias;
+                                if (p.bias_crop_stride)
+                                    brow += (size_t)(crop_first + (roff[ps] >= crop_boundary ? 1 : 0)) * p.bias_crop_stride;
+                                const float4 bv = __ldg(reinterpret_cast<const float4*>(brow + cq));
+                                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                            }
+                            if (p.residual) {
+                                const float4 rv = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)roff[ps] * p.ldr + cq));
+                                o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+                            }
+                            if (p.relu == 1) {
+                                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                            } else if (p.relu == 2) {
+                                o.x = o.x > 0.f ? o.x : slope * o.x; o.y = o.y > 0.f ? o.y : slope * o.y;
+                                o.z = o.z > 0.f ? o.z : slope * o.z; o.w = o.w > 0.f ? o.w : slope * o.w;
+                            }
+                            *reinterpret_cast<float4*>(dst) = o;
                         }
                     }
                 }
@@ -831,6 +919,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     p.pool_partial[((size_t)c.crop * p.tiles_per_crop + c.pool_tile) * p.N + c.n0 + tt] = s;
                 }
             }
+          }
         }
     }
     tc_fence_before();
@@ -912,9 +1001,33 @@ int launch_persistent(const CUtensorMap& mhi, const CUtensorMap& mlo, const TcPa
     return 0;
 }
 
-template <int CTAS, int A_STAGES>
-int launch_q(const TcParams& p, const float* W_hi, const float* W_lo, int ldw, int groups, cudaStream_t s)
+// NHWC image (B, H, W, C) with pixel pitch `ld` floats as a 4-D tensor; box = 32 channels x TW x TH x TB pixels
+bool make_map_nhwc(CUtensorMap* map, const float* base, int B, int H, int W, int C, int ld, int TW, int TH, int TB)
 {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)W * ld * 4, (cuuint64_t)H * W * ld * 4};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int CTAS, int A_STAGES>
+int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw, int groups, cudaStream_t s)
+{
+    TcParams p = p_in;
+    {   // accumulation runs of <= 18 k-blocks (K <= 576) once the chain is long enough to matter (see TcParams::k_chunks)
+        const int nkb = p.K / BK;
+        p.k_chunks = 1; p.kbc = nkb;
+        if (p.precise && !p.pool_partial && nkb > 24) {
+            p.k_chunks = (nkb + 17) / 18;
+            p.kbc = (nkb + p.k_chunks - 1) / p.k_chunks;
+            p.k_chunks = (nkb + p.kbc - 1) / p.kbc;
+        }
+    }
     static int max_clusters = 0;
     if (!max_clusters) {
         int dev = 0, num_sms = 0;
@@ -942,18 +1055,20 @@ int launch_q(const TcParams& p, const float* W_hi, const float* W_lo, int ldw, i
     // admissible widths take the one with the least work after wave quantisation (+32: fixed cost per tile).
     int bn_cta = 0;
     const int rows_per_mtile = 128 * CTAS;
-    const int m_tiles = p.pool_partial ? (p.M / p.rows_per_crop) * ((p.rows_per_crop + rows_per_mtile - 1) / rows_per_mtile)
-                                       : (p.M + rows_per_mtile - 1) / rows_per_mtile;
+    const int m_tiles = p.conv_taps ? (p.tiles_x * p.tiles_y * p.tiles_b + CTAS - 1) / CTAS
+                        : p.pool_partial ? (p.M / p.rows_per_crop) * ((p.rows_per_crop + rows_per_mtile - 1) / rows_per_mtile)
+                                         : (p.M + rows_per_mtile - 1) / rows_per_mtile;
     if (CTAS == 1) {
         bn_cta = 128;
         if (groups > 1 && p.N % 128) return DF_ERR_UNSUPPORTED;
     } else {
-        const int widths[3] = {256, 192, 128};
+        const int widths[4] = {256, 192, 128, 64};
         long long best = -1;
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < 4; ++i) {
             const int w = widths[i];
             if (w == 256 && !p.pool_partial) continue;
             if (w == 192 && A_STAGES != 2) continue;
+            if (w == 64 && p.N > 64) continue;                     // narrow layers only (64-channel decoder stages)
             if (p.N % w != 0 && (groups > 1 || w == 256)) continue;
             const long long tiles = (long long)m_tiles * ((p.N + w - 1) / w) * groups;
             const long long cost = ((tiles + max_clusters - 1) / max_clusters) * (w + 32);
@@ -964,9 +1079,11 @@ int launch_q(const TcParams& p, const float* W_hi, const float* W_lo, int ldw, i
     const int bnt = bn_cta * CTAS;
     // the A operand as a 2-D tensor: group g's columns start at g*a_gs inside the row
     const long long a_cols = (long long)(groups - 1) * p.a_gs + p.K;
-    if (a_cols > p.lda || (groups > 1 && p.a_gs < 0)) return DF_ERR_UNSUPPORTED;
+    if (!p.conv_taps && (a_cols > p.lda || (groups > 1 && p.a_gs < 0))) return DF_ERR_UNSUPPORTED;
     CUtensorMap ma, mhi, mlo;
-    if (!make_map(&ma, p.A, p.M, (int)a_cols, p.lda, 128)) return DF_ERR_UNSUPPORTED;
+    if (p.conv_taps) {
+        if (!make_map_nhwc(&ma, p.A, p.cB, p.cH, p.cW, p.K / p.conv_taps, p.lda, p.TW, p.TH, p.TB)) return DF_ERR_UNSUPPORTED;
+    } else if (!make_map(&ma, p.A, p.M, (int)a_cols, p.lda, 128)) return DF_ERR_UNSUPPORTED;
     const long long wrows = (long long)groups * p.N;
     if (!make_map(&mhi, W_hi, wrows, p.K, ldw, bn_cta)) return DF_ERR_UNSUPPORTED;
     if (!make_map(&mlo, p.precise ? W_lo : W_hi, wrows, p.K, ldw, bn_cta)) return DF_ERR_UNSUPPORTED;
@@ -1030,7 +1147,7 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
     if (pool_partial && M % rows_per_crop) return DF_ERR_ARG;
     if (groups > 1 && N % 128) return DF_ERR_UNSUPPORTED;      // group g's weight rows start at g*N: keep tiles inside a group
 
-    TcParams p;
+    TcParams p = {};
     p.A = A; p.lda = lda; p.bias = bias; p.bias_crop_stride = bias_crop_stride;
     p.C = pool_partial ? nullptr : C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.relu = relu;
     p.precise = precision == 1;
@@ -1067,6 +1184,46 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
     else if (v == 3) rc = launch_tc<128, false>(mhi, mlo, p, groups, s);
     else if (v == 4) rc = launch_persistent(mhi, mlo, p, groups, s);
     else return DF_ERR_ARG;
+    if (rc) return rc;
+    DF_RETURN_LAST_ERROR();
+}
+
+// 3x3 (stride 1, padding == dilation) or 1x1 convolution on an NHWC image as an implicit GEMM on the paired tcgen05
+// kernel: out[pixel, n] = act( sum_{tap, c} X[pixel + tap*dil, c] W[n, tap*Cin + c] + bias[n] + residual[pixel, n] ).
+extern "C" int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx, const float* W_hi, const float* W_lo,
+                          int taps, int dilation, const float* bias, const float* residual, int ldr, const float* prelu,
+                          int act, float* Y, int ldy, int Cout, int precision, void* stream)
+{
+    if (!X || !W_hi || !Y || B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return DF_ERR_ARG;
+    if (precision != 1 && precision != 2) return DF_ERR_ARG;
+    if (precision == 1 && !W_lo) return DF_ERR_ARG;
+    if ((taps != 1 && taps != 9) || dilation < 1 || act < 0 || act > 2 || (act == 2 && !prelu)) return DF_ERR_ARG;
+    if (Cin % BK || Cout % 4 || ldx % 4 || ldy % 4 || ldx < Cin || ldy < Cout || (residual && (ldr % 4 || ldr < Cout))) return DF_ERR_ARG;
+    if (((uintptr_t)X & 15) || ((uintptr_t)Y & 15) || ((uintptr_t)W_hi & 15) || ((uintptr_t)W_lo & 15) ||
+        ((uintptr_t)residual & 15) || ((uintptr_t)bias & 15))
+        return DF_ERR_ARG;
+    if ((long long)B * H * W >= (1LL << 31)) return DF_ERR_ARG;
+
+    TcParams p = {};
+    p.A = X; p.lda = ldx; p.bias = bias; p.bias_crop_stride = 0; p.C = Y; p.ldc = ldy;
+    p.M = B * H * W; p.N = Cout; p.K = taps * Cin; p.relu = act; p.precise = precision == 1;
+    p.rows_per_crop = p.M; p.a_gs = 0; p.bias_gs = 0; p.c_gs = 0; p.pool_partial = nullptr; p.tiles_per_crop = 0;
+    p.conv_taps = taps; p.conv_dil = dilation; p.cW = W; p.cH = H; p.cB = B;
+    p.residual = residual; p.ldr = ldr; p.prelu = prelu;
+    // pixel patch (TB x TH x TW <= 128 rows) with the fewest tiles; ties: wider rows (longer contiguous runs)
+    long long best_tiles = -1;
+    for (int tw = 1; tw <= (W < 128 ? W : 128); ++tw) {
+        for (int th = 1; th <= H && tw * th <= 128; ++th) {
+            int tb = 128 / (tw * th);
+            if (tb > B) tb = B;
+            const long long tiles = (long long)((W + tw - 1) / tw) * ((H + th - 1) / th) * ((B + tb - 1) / tb);
+            if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && tw > p.TW)) {
+                best_tiles = tiles; p.TW = tw; p.TH = th; p.TB = tb;
+            }
+        }
+    }
+    p.tiles_x = (W + p.TW - 1) / p.TW; p.tiles_y = (H + p.TH - 1) / p.TH; p.tiles_b = (B + p.TB - 1) / p.TB;
+    const int rc = launch_q<2, 2>(p, W_hi, W_lo, taps * Cin, 1, (cudaStream_t)stream);
     if (rc) return rc;
     DF_RETURN_LAST_ERROR();
 }

@@ -1,0 +1,189 @@
+"""Colour encoder (ModifiedResnet = BN-free dilated ResNet-18 + PSP pyramid + 3 up-sampling stages, reference:
+lib/network.py:27-37, lib/extractors.py:78-124, lib/pspnet.py:7-77) on the tensor cores -- SURVEY.md section 8f row N1.
+
+After the head moved to tcgen05 the torch/cuDNN fp32 encoder was 85-90% of the pose step.  Here every convolution is a
+GEMM on the CTA-pair tcgen05 kernel in the same error-compensated 3xTF32 arithmetic as the head (fp32 parity):
+  * 3x3 stride-1 convolutions (any dilation): implicit GEMM, the A operand is a 4-D TMA box over the NHWC activation
+    shifted by the tap -- zero padding is TMA's out-of-bounds fill, nothing is im2col'ed (df_conv_tc);
+  * 1x1 convolutions: plain GEMMs over the (pixels, channels) matrix;
+  * the three stride-2 layers (conv1 7x7, layer2.0.conv1 3x3, layer2.0.downsample 1x1) go through small im2col
+    buffers (the 1x1 one is the centre tap of the 3x3 one) and the same GEMM;
+  * skip connections, biases, ReLU / PReLU are GEMM epilogues; the pyramid concat is never materialised: layer4 and the
+    four resized pyramid levels are written straight into channel slices of one 2560-wide buffer.
+Activations are NHWC fp32; the result (B,H,W,32) log-softmax embedding is consumed by df_gather_embedding through
+explicit strides.  Inference only; training keeps the torch/cuDNN encoder (its backward is library code)."""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+
+from . import ops
+from ._C import check, lib, ptr, stream
+
+K_CONV1 = 160          # 3*7*7 = 147 padded to a multiple of 32
+
+
+def _pack_conv(w: torch.Tensor) -> ops.SplitWeight:
+    """torch (Cout,Cin,kh,kw) -> (Cout, kh*kw*Cin) tap-major, channels fastest (matches the shifted NHWC boxes)."""
+    co, ci, kh, kw = w.shape
+    sw = ops.SplitWeight(w.detach().float().permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous())
+    sw.split()
+    return sw
+
+
+class PackedEncoder:
+    def __init__(self, cnn: torch.nn.Module):
+        net = cnn.model.module                      # PSPNet behind the DataParallel-compatible shim
+        sd = {k: v.detach() for k, v in net.state_dict().items()}
+        dev = next(net.parameters()).device
+        self.device = dev
+        w1 = torch.zeros(64, K_CONV1, device=dev)
+        w1[:, :147] = sd["feats.conv1.weight"].float().reshape(64, 147)
+        self.conv1 = ops.SplitWeight(w1)
+        self.conv1.split()
+        self.blocks = []
+        for li, (name, stride, dil) in enumerate((("layer1", 1, 1), ("layer2", 2, 1), ("layer3", 1, 2), ("layer4", 1, 4))):
+            for bi in (0, 1):
+                pre = f"feats.{name}.{bi}."
+                blk = {"c1": _pack_conv(sd[pre + "conv1.weight"]), "c2": _pack_conv(sd[pre + "conv2.weight"]),
+                       "dil": 1 if bi == 0 else dil, "stride": stride if bi == 0 else 1, "down": None,
+                       "cout": sd[pre + "conv1.weight"].shape[0], "cin": sd[pre + "conv1.weight"].shape[1]}
+                if pre + "downsample.0.weight" in sd:
+                    blk["down"] = _pack_conv(sd[pre + "downsample.0.weight"])
+                self.blocks.append(blk)
+        self.stages = [_pack_conv(sd[f"psp.stages.{i}.1.weight"]) for i in range(4)]
+        self.bottleneck = _pack_conv(sd["psp.bottleneck.weight"])
+        self.bottleneck_b = sd["psp.bottleneck.bias"].float().contiguous()
+        self.ups = []
+        for u in ("up_1", "up_2", "up_3"):
+            self.ups.append({"w": _pack_conv(sd[f"{u}.conv.1.weight"]), "b": sd[f"{u}.conv.1.bias"].float().contiguous(),
+                             "a": sd[f"{u}.conv.2.weight"].float().contiguous(),
+                             "cout": sd[f"{u}.conv.1.weight"].shape[0]})
+        self.final_w = sd["final.0.weight"].float().reshape(32, 64).contiguous()
+        self.final_b = sd["final.0.bias"].float().contiguous()
+        self._ws: Dict[Tuple[int, int, int], dict] = {}
+
+    # ---- scratch: one set of NHWC buffers per bucket shape ----
+    def _workspace(self, b, H, W):
+        key = (b, H, W)
+        ws = self._ws.get(key)
+        if ws is None:
+            f = dict(device=self.device, dtype=torch.float32)
+            H2, W2 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+            H4, W4 = (H2 - 1) // 2 + 1, (W2 - 1) // 2 + 1
+            H8, W8 = (H4 - 1) // 2 + 1, (W4 - 1) // 2 + 1
+            ws = {"dims": (H2, W2, H4, W4, H8, W8)}
+            ws["a0"] = torch.empty(b * H2 * W2, K_CONV1, **f)
+            ws["c1"] = torch.empty(b, H2, W2, 64, **f)
+            ws["l1"] = [torch.empty(b, H4, W4, 64, **f) for _ in range(3)]
+            ws["a2"] = torch.empty(b * H8 * W8, 9 * 64, **f)
+            ws["l8"] = {c: [torch.empty(b, H8, W8, c, **f) for _ in range(3)] for c in (128, 256, 512)}
+            ws["cat"] = torch.empty(b, H8, W8, 2560, **f)
+            ws["pool"] = [torch.empty(b, s, s, 512, **f) for s in (1, 2, 3, 6)]
+            ws["pconv"] = [torch.empty(b, s, s, 512, **f) for s in (1, 2, 3, 6)]
+            ws["bott"] = torch.empty(b, H8, W8, 1024, **f)
+            hs = [(2 * H8, 2 * W8), (4 * H8, 4 * W8), (8 * H8, 8 * W8)]
+            ws["hs"] = hs
+            ws["up_in"] = [torch.empty(b, h, w, c, **f) for (h, w), c in zip(hs, (1024, 256, 64))]
+            ws["up_out"] = [torch.empty(b, h, w, c, **f) for (h, w), c in zip(hs, (256, 64, 64))]
+            ws["feat"] = torch.empty(b, hs[2][0], hs[2][1], 32, **f)
+            self._ws[key] = ws
+        return ws
+
+    # ---- kernels ----
+    @staticmethod
+    def _conv(x, w: ops.SplitWeight, out, *, taps, dil=1, bias=None, residual=None, prelu=None, act=1, mode=1, cin=None,
+              ldx=None, ldy=None, cout=None):
+        b, h, wd = x.shape[0], x.shape[1], x.shape[2]
+        cin = x.shape[3] if cin is None else cin
+        ldx = x.stride(2) if ldx is None else ldx
+        cout = out.shape[3] if cout is None else cout
+        ldy = out.stride(2) if ldy is None else ldy
+        hi, lo = w.split()
+        check(lib.df_conv_tc(ptr(x), b, h, wd, cin, ldx, ptr(hi), ptr(lo), taps, dil, ptr(bias), ptr(residual),
+                             0 if residual is None else residual.stride(2), ptr(prelu), act, ptr(out), ldy, cout, mode,
+                             stream()), "df_conv_tc")
+
+    def forward(self, img: torch.Tensor, precision: str = "3xtf32") -> torch.Tensor:
+        """img (b,3,H,W) fp32 CUDA (NCHW, as the reference feeds it) -> (b,H,W,32) NHWC log-softmax embedding.
+        H and W must be multiples of 8 (the reference's crops are multiples of 40)."""
+        if precision not in ("3xtf32", "tf32"):
+            raise ValueError("the tensor-core encoder runs in '3xtf32' (fp32 parity) or 'tf32'")
+        mode = ops.PRECISIONS[precision]
+        img = ops.f32c(img)
+        b, _, H, W = img.shape
+        if H % 8 or W % 8:
+            raise ValueError("encoder: crop height / width must be multiples of 8")
+        ws = self._workspace(b, H, W)
+        H2, W2, H4, W4, H8, W8 = ws["dims"]
+        s = stream()
+        # conv1 7x7/2 + ReLU, 3x3/2 max pool
+        check(lib.df_enc_im2col_conv1(ptr(img), ptr(ws["a0"]), b, H, W, K_CONV1, s), "df_enc_im2col_conv1")
+        rows = b * H2 * W2
+        ops.gemm(ws["a0"], self.conv1, None, ws["c1"], M=rows, N=64, K=K_CONV1, lda=K_CONV1, ldw=K_CONV1, ldc=64, relu=True,
+                 precision=precision)
+        x = ws["l1"][0]
+        check(lib.df_enc_maxpool(ptr(ws["c1"]), ptr(x), b, H2, W2, 64, s), "df_enc_maxpool")
+        # residual stages
+        free = [ws["l1"][1], ws["l1"][2]]
+        for bi, blk in enumerate(self.blocks):
+            cout = blk["cout"]
+            last = bi == len(self.blocks) - 1
+            if blk["stride"] == 2:
+                # layer2.0: 3x3/2 and the 1x1/2 projection both read the im2col'ed patches (projection = centre tap)
+                check(lib.df_enc_im2col_s2(ptr(x), ptr(ws["a2"]), b, H4, W4, 64, s), "df_enc_im2col_s2")
+                r8 = b * H8 * W8
+                bufs = ws["l8"][128]
+                t, skip, out = bufs[0], bufs[1], bufs[2]
+                ops.gemm(ws["a2"], blk["c1"], None, t, M=r8, N=128, K=576, lda=576, ldw=576, ldc=128, relu=True,
+                         precision=precision)
+                ops.gemm(ws["a2"][:, 256:], blk["down"], None, skip, M=r8, N=128, K=64, lda=576, ldw=64, ldc=128,
+                         relu=False, precision=precision)
+                self._conv(t, blk["c2"], out, taps=9, dil=1, residual=skip, act=1, mode=mode)
+                x, free = out, [t, skip]
+                continue
+            if cout != x.shape[3]:                                   # first block of layer3 / layer4: wider, projected skip
+                bufs = ws["l8"][cout]
+                t, skip, out = bufs[0], bufs[1], bufs[2]
+                self._conv(x, blk["down"], skip, taps=1, act=0, mode=mode)
+                self._conv(x, blk["c1"], t, taps=9, dil=blk["dil"], act=1, mode=mode)
+                self._conv(t, blk["c2"], out, taps=9, dil=blk["dil"], residual=skip, act=1, mode=mode)
+                x, free = out, [t, skip]
+                continue
+            t, out = free[0], free[1]
+            self._conv(x, blk["c1"], t, taps=9, dil=blk["dil"], act=1, mode=mode)
+            if last:                                                 # layer4 output lands in its slice of the concat
+                cat = ws["cat"]
+                self._conv(t, blk["c2"], cat[..., 2048:], taps=9, dil=blk["dil"], residual=x, act=1, mode=mode,
+                           ldy=2560, cout=512)
+            else:
+                self._conv(t, blk["c2"], out, taps=9, dil=blk["dil"], residual=x, act=1, mode=mode)
+                x, free = out, [t, x]
+        # pyramid pooling: [up(conv(pool_s(f))) for s in 1,2,3,6] + [f] -> 1x1 bottleneck + ReLU
+        cat = ws["cat"]
+        feats = cat[..., 2048:]
+        for i, sz in enumerate((1, 2, 3, 6)):
+            check(lib.df_enc_adaptive_avgpool(ptr(feats), 2560, ptr(ws["pool"][i]), b, H8, W8, 512, sz, s),
+                  "df_enc_adaptive_avgpool")
+            r = b * sz * sz
+            ops.gemm(ws["pool"][i], self.stages[i], None, ws["pconv"][i], M=r, N=512, K=512, lda=512, ldw=512, ldc=512,
+                     relu=False, precision=precision)
+            check(lib.df_enc_upsample(ptr(ws["pconv"][i]), 512, ptr(cat[..., i * 512:]), 2560, b, sz, sz, H8, W8, 512, 0, s),
+                  "df_enc_upsample")
+        r8 = b * H8 * W8
+        ops.gemm(cat, self.bottleneck, self.bottleneck_b, ws["bott"], M=r8, N=1024, K=2560, lda=2560, ldw=2560, ldc=1024,
+                 relu=True, precision=precision)
+        # three x2 bilinear (align_corners) + 3x3 conv + PReLU stages
+        x, (h, w) = ws["bott"], (H8, W8)
+        for i, up in enumerate(self.ups):
+            hh, wwd = ws["hs"][i]
+            c = x.shape[3]
+            check(lib.df_enc_upsample(ptr(x), c, ptr(ws["up_in"][i]), c, b, h, w, hh, wwd, c, 1, s), "df_enc_upsample")
+            self._conv(ws["up_in"][i], up["w"], ws["up_out"][i], taps=9, dil=1, bias=up["b"], prelu=up["a"], act=2, mode=mode)
+            x, (h, w) = ws["up_out"][i], (hh, wwd)
+        # final 1x1 (64 -> 32) + channel log-softmax
+        rows = b * h * w
+        ops.gemm(x, self.final_w, self.final_b, ws["feat"], M=rows, N=32, K=64, lda=64, ldw=64, ldc=32, relu=False)
+        check(lib.df_enc_log_softmax32(ptr(ws["feat"]), rows, s), "df_enc_log_softmax32")
+        return ws["feat"]

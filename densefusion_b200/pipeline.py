@@ -18,7 +18,7 @@ from ._C import check, lib, ptr, stream
 
 class PoseEstimator:
     def __init__(self, estimator, refiner, iterations: int = 2, precision: str = "fp32", chunk_crops: int = 32,
-                 channels_last: bool = False):
+                 channels_last: bool = False, encoder: str = "auto"):
         # channels_last=False: with TF32 disabled cuDNN's NHWC fp32 convolutions fall back to a direct kernel that
         # is 3.5x slower than the NCHW ones (profiles/r1_call2_encoder_variants.json); NHWC only pays with TF32 on.
         self.estimator, self.refiner = estimator, refiner
@@ -33,6 +33,14 @@ class PoseEstimator:
         self._ws_head = None
         self._ws_ref = None
         self._bufs: Dict[int, dict] = {}
+        # encoder: "tc" = densefusion_b200.encoder (tcgen05 implicit-GEMM convolutions, same arithmetic mode as the head),
+        # "torch" = the torch/cuDNN module; "auto" = tc whenever the head runs on the tensor cores
+        if encoder == "auto":
+            encoder = "tc" if precision in ("3xtf32", "tf32") else "torch"
+        if encoder not in ("tc", "torch"):
+            raise ValueError("encoder must be 'auto', 'tc' or 'torch'")
+        self.encoder = encoder
+        self._enc = None
         if channels_last:
             estimator.cnn.to(memory_format=torch.channels_last)
 
@@ -58,7 +66,17 @@ class PoseEstimator:
 
     # ---- stages ---------------------------------------------------------------------------------
     def encode(self, img: torch.Tensor, choose: torch.Tensor, emb_pm_out: torch.Tensor) -> None:
-        """Colour encoder (torch/cuDNN) + K1's gather for one (H,W) bucket; writes (b*N,32) rows."""
+        """Colour encoder + K1's gather for one (H,W) bucket; writes (b*N,32) rows."""
+        if self.encoder == "tc":
+            if self._enc is None:
+                from .encoder import PackedEncoder
+                self._enc = PackedEncoder(self.estimator.cnn)
+            feat = self._enc.forward(img, self.precision)                 # (B,H,W,32) channels-last
+            B, H, W, C = feat.shape
+            choose = ops.i64c(choose).view(B, -1)
+            check(lib.df_gather_embedding(ptr(feat), ptr(choose), ptr(emb_pm_out), None, H * W * C, 1, C, B, self.n, H * W,
+                                          stream()), "df_gather_embedding")
+            return
         if self.channels_last:
             img = img.contiguous(memory_format=torch.channels_last)
         feat = self.estimator.cnn(img)

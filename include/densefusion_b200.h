@@ -151,6 +151,24 @@ int df_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
 int df_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                      float beta1, float beta2, float eps, int* step_counter, void* stream);
 
+/* ---- colour encoder on the tensor cores (lib/extractors.py:78-124, lib/pspnet.py:7-77) ----
+ * Activations are NHWC.  df_conv_tc: 3x3 (stride 1, padding == dilation) or 1x1 convolution as an implicit GEMM on the
+ * CTA-pair tcgen05 kernel -- the A operand is a 4-D TMA box shifted by the tap, its out-of-image part zero-filled.
+ *   X (B,H,W,Cin) pixel pitch ldx; W_hi/W_lo (Cout, taps*Cin) tap-major repack of the torch (Cout,Cin,kh,kw) weight, split by
+ *   df_split_tf32; act 0 none / 1 ReLU / 2 PReLU(prelu[0]); residual (pixel pitch ldr) is added before the activation;
+ *   Y pixel pitch ldy (>= Cout: the output may be a channel slice of a wider buffer).  precision as df_gemm_tc.
+ * df_enc_*: the HBM-bound glue (im2col for the three stride-2 layers, pooling, resizing into a channel slice, log-softmax). */
+int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx, const float* W_hi, const float* W_lo, int taps,
+               int dilation, const float* bias, const float* residual, int ldr, const float* prelu, int act, float* Y,
+               int ldy, int Cout, int precision, void* stream);
+int df_enc_im2col_conv1(const float* img, float* A, int B, int H, int W, int ldk, void* stream);
+int df_enc_maxpool(const float* in, float* out, int B, int H, int W, int C, void* stream);
+int df_enc_im2col_s2(const float* in, float* A, int B, int H, int W, int C, void* stream);
+int df_enc_adaptive_avgpool(const float* in, int ldi, float* out, int B, int H, int W, int C, int S, void* stream);
+int df_enc_upsample(const float* in, int ldi, float* out, int ldo, int B, int hin, int win, int hout, int wout, int C,
+                    int align_corners, void* stream);
+int df_enc_log_softmax32(float* x, long long pixels, void* stream);
+
 /* ---- encoder helper -----------------------------------------------------------------------------
  * NCHW bilinear up-sampling (lib/pspnet.py:20-23 F.upsample(size=...), :30-34 nn.Upsample(scale_factor=2,
  * align_corners=True)): in (planes, hin, win) -> out (planes, hout, wout), planes = batch*channels. */

@@ -1,0 +1,133 @@
+"""Colour encoder on the tensor cores: df_conv_tc against float64 convolutions, the NHWC helper
+kernels against torch, and the whole encoder against the oracle's restatement of lib/pspnet.py + lib/extractors.py
+(which tests/test_oracle_golden.py pins to the reference's own embeddings).  Bounds (max-abs / max-abs): whole encoder 3xtf32 <= 1e-4, tf32 <= 2e-2 (25 layers of single-pass TF32); one convolution
+3xtf32 <= 2e-5 (the tensor core truncates while accumulating, see TcParams::k_chunks in gemm_tc.cu), tf32 <= 3e-3."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from densefusion_b200 import synth
+from oracle import df_oracle as O
+from util import build_nets, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,taps,dil,extras", [
+    (5, 10, 10, 256, 512, 9, 1, "relu"),            # 100-pixel maps, patches span crops
+    (3, 10, 10, 512, 512, 9, 4, "residual"),        # layer4.1: dilation 4 reaches far outside a 10x10 map
+    (2, 15, 15, 128, 256, 9, 2, "relu"),            # odd size
+    (2, 20, 12, 64, 64, 9, 1, "residual"),          # non-square, 64 output channels
+    (2, 40, 40, 256, 64, 9, 1, "prelu"),            # up_2
+    (1, 80, 80, 64, 64, 9, 1, "prelu"),             # up_3
+    (4, 10, 10, 256, 512, 1, 1, "none"),            # 1x1 projection
+    (3, 20, 20, 1024, 256, 9, 1, "prelu"),          # up_1 (K = 9216)
+])
+def test_conv_tc_vs_float64(B, H, W, Cin, Cout, taps, dil, extras):
+    from densefusion_b200.encoder import PackedEncoder, _pack_conv
+    g = torch.Generator().manual_seed(B * 1000 + H + Cin + Cout)
+    k = 3 if taps == 9 else 1
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    bias = torch.randn(Cout, generator=g) if extras == "prelu" else None
+    res = torch.randn(B, Cout, H, W, generator=g) if extras == "residual" else None
+    slope = torch.tensor([0.25])
+    want = F.conv2d(x.double(), w.double(), None if bias is None else bias.double(), padding=dil if k == 3 else 0, dilation=dil)
+    if res is not None:
+        want = want + res.double()
+    if extras in ("relu", "residual"):
+        want = torch.relu(want)
+    elif extras == "prelu":
+        want = torch.where(want > 0, want, 0.25 * want)
+    for precision, tol in (("3xtf32", 2e-5), ("tf32", 3e-3)):
+        wide = torch.full((B, H, W, Cout + 64), 7.0, device="cuda")          # output is a channel slice of a wider buffer
+        out = wide[..., 32:32 + Cout]
+        PackedEncoder._conv(_nhwc(x).cuda(), _pack_conv(w.cuda()), out, taps=taps, dil=dil,
+                            bias=None if bias is None else bias.cuda(), residual=None if res is None else _nhwc(res).cuda(),
+                            prelu=slope.cuda() if extras == "prelu" else None,
+                            act={"relu": 1, "residual": 1, "prelu": 2, "none": 0}[extras],
+                            mode={"3xtf32": 1, "tf32": 2}[precision])
+        torch.cuda.synchronize()
+        err = rel(out.permute(0, 3, 1, 2), want)
+        print(f"conv {taps}tap dil{dil} {Cin}->{Cout} {H}x{W}x{B} {precision}: {err:.3e}")
+        assert err < tol
+        assert float(wide[..., :32].min()) == 7.0 and float(wide[..., 32 + Cout:].max()) == 7.0    # neighbours untouched
+
+
+def test_encoder_helper_kernels_vs_torch():
+    from densefusion_b200._C import check, lib, ptr, stream
+    g = torch.Generator().manual_seed(2)
+    B, H, W, C = 3, 40, 24, 64
+    x = torch.randn(B, C, H, W, generator=g)
+    xn = _nhwc(x).cuda()
+    # max pool 3x3/2
+    out = torch.empty(B, H // 2, W // 2, C, device="cuda")
+    check(lib.df_enc_maxpool(ptr(xn), ptr(out), B, H, W, C, stream()), "maxpool")
+    assert torch.equal(out.permute(0, 3, 1, 2).cpu(), F.max_pool2d(x, 3, 2, 1))
+    # im2col of the 3x3/2 patches == unfold (tap-major, channels fastest)
+    A = torch.empty(B * (H // 2) * (W // 2), 9 * C, device="cuda")
+    check(lib.df_enc_im2col_s2(ptr(xn), ptr(A), B, H, W, C, stream()), "im2col_s2")
+    unf = F.unfold(x, 3, padding=1, stride=2).view(B, C, 9, -1).permute(0, 3, 2, 1).reshape(-1, 9 * C)
+    assert torch.equal(A.cpu(), unf)
+    # conv1 im2col
+    img = torch.randn(2, 3, 40, 56, generator=g)
+    A1 = torch.empty(2 * 20 * 28, 160, device="cuda")
+    check(lib.df_enc_im2col_conv1(ptr(img.cuda()), ptr(A1), 2, 40, 56, 160, stream()), "im2col_conv1")
+    unf1 = F.unfold(img, 7, padding=3, stride=2).permute(0, 2, 1).reshape(-1, 147)
+    assert torch.equal(A1[:, :147].cpu(), unf1) and float(A1[:, 147:].abs().max()) == 0.0
+    # adaptive average pooling from a channel slice of a wider buffer
+    wide = torch.randn(B, 10, 15, 96, generator=g).cuda()
+    for S in (1, 2, 3, 6):
+        o = torch.empty(B, S, S, 64, device="cuda")
+        check(lib.df_enc_adaptive_avgpool(ptr(wide[..., 32:]), 96, ptr(o), B, 10, 15, 64, S, stream()), "avgpool")
+        want = F.adaptive_avg_pool2d(wide[..., 32:].permute(0, 3, 1, 2).cpu(), (S, S))
+        assert rel(o.permute(0, 3, 1, 2), want) < 1e-6
+    # bilinear resize into a channel slice, both alignment modes
+    small = torch.randn(B, 6, 6, 64, generator=g).cuda()
+    for (ho, wo, align) in ((10, 15, False), (12, 12, True)):
+        dst = torch.zeros(B, ho, wo, 160, device="cuda")
+        check(lib.df_enc_upsample(ptr(small), 64, ptr(dst[..., 64:]), 160, B, 6, 6, ho, wo, 64, 1 if align else 0, stream()), "up")
+        want = F.interpolate(small.permute(0, 3, 1, 2).cpu(), size=(ho, wo), mode="bilinear", align_corners=align)
+        assert rel(dst[..., 64:128].permute(0, 3, 1, 2), want) < 2e-6 and float(dst[..., :64].abs().max()) == 0.0
+    # log-softmax over 32 channels
+    z = torch.randn(1000, 32, generator=g).cuda()
+    want = torch.log_softmax(z.cpu().double(), 1)
+    check(lib.df_enc_log_softmax32(ptr(z), 1000, stream()), "lsm")
+    assert rel(z, want) < 1e-6
+
+
+@pytest.mark.parametrize("precision,tol", [("3xtf32", 1e-4), ("tf32", 2e-2)])
+@pytest.mark.parametrize("b,hw", [(3, (80, 80)), (2, (120, 160)), (1, (160, 160))])
+def test_encoder_vs_oracle(precision, tol, b, hw):
+    from densefusion_b200.encoder import PackedEncoder
+    est, _, est_sd, _ = build_nets(500, 21, seed=6)
+    g = torch.Generator().manual_seed(hw[0] + b)
+    img = torch.randn(b, 3, hw[0], hw[1], generator=g)
+    enc = PackedEncoder(est.cnn)
+    feat = enc.forward(img.cuda(), precision)                      # (b,H,W,32)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        want = O.psp_encoder(est_sd, img)
+    err = rel(feat.permute(0, 3, 1, 2), want)
+    print(f"encoder {precision} {b}x{hw}: rel err {err:.3e}")
+    assert err < tol
+
+
+def test_pipeline_with_tensor_core_encoder_vs_oracle():
+    """estimate + 2 refine iterations with encoder AND head on the tensor cores (3xTF32) against the oracle's eval loop."""
+    import numpy as np
+    from densefusion_b200.pipeline import PoseEstimator
+    est, ref, est_sd, ref_sd = build_nets(500, 21, seed=0)
+    d = synth.synth_crop(7, 500, 500, 21, (80, 80), obj=12)
+    dc = {k: v.cuda() for k, v in d.items()}
+    pipe = PoseEstimator(est, ref, iterations=2, precision="3xtf32")
+    assert pipe.encoder == "tc"
+    pose = pipe.estimate(dc["img"], dc["points"], dc["choose"], dc["idx"]).cpu().numpy()[0]
+    want = O.estimate_and_refine(est_sd, ref_sd, d["img"], d["points"], d["choose"], d["idx"], 21, 2)
+    err = float(np.max(np.abs(pose - want)) / np.max(np.abs(want)))
+    print(f"pose err with tensor-core encoder: {err:.3e}")
+    assert err < 1e-4
