@@ -553,13 +553,21 @@ def measure_extras(pipe, dev, args, peaks):
     try:
         est2 = copy.deepcopy(pipe.estimator)
         pipe2 = PoseEstimator(est2, pipe.refiner, iterations=ITERS, precision=pipe.precision, chunk_crops=pipe.chunk,
-                              channels_last=True)
+                              channels_last=True, encoder="torch")
         buckets = [{k: v.to(dev) for k, v in b.items()} for b in make_host_buckets(args.frames, seed=4242, pin=False)]
         torch.backends.cudnn.allow_tf32 = True
         ms_t = time_kernel_ms(lambda: pipe2.estimate_buckets(buckets), iters=3, warm=2)
         crops = sum(b["cloud"].shape[0] for b in buckets)
-        out["whole_pipeline_with_tf32_nhwc_encoder"] = {"value": crops / (ms_t * 1e-3), "unit": UNIT, "ms_per_step": ms_t,
-                                                        "note": "encoder precision relaxed to TF32; not the parity mode"}
+        out["whole_pipeline_with_cudnn_tf32_nhwc_encoder"] = {
+            "value": crops / (ms_t * 1e-3), "unit": UNIT, "ms_per_step": ms_t,
+            "note": "library encoder (torch/cuDNN channels-last) with TF32 allowed: NOT a parity mode (embeddings off by ~1e-3); "
+                    "for comparison with the hand-written fp32-parity encoder"}
+        torch.backends.cudnn.allow_tf32 = False
+        pipe3 = PoseEstimator(copy.deepcopy(pipe.estimator), pipe.refiner, iterations=ITERS, precision=pipe.precision,
+                              chunk_crops=pipe.chunk, encoder="torch")
+        ms_c = time_kernel_ms(lambda: pipe3.estimate_buckets(buckets), iters=3, warm=2)
+        out["whole_pipeline_with_cudnn_fp32_encoder"] = {"value": crops / (ms_c * 1e-3), "unit": UNIT, "ms_per_step": ms_c,
+                                                         "note": "library encoder in strict fp32 (the round-1 default before the tensor-core encoder)"}
     finally:
         torch.backends.cudnn.allow_tf32 = False
     return out
