@@ -12,16 +12,16 @@ namespace {
 __global__ void __launch_bounds__(256)
 im2col_conv1_kernel(const float* __restrict__ img, float* __restrict__ A, int B, int H, int W, int Ho, int Wo, int ldk)
 {
-    const long long total = (long long)B * Ho * Wo * ldk;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(i % ldk);
-        const long long pix = i / ldk;
+    const unsigned total = (unsigned)B * Ho * Wo * ldk;                 // < 2^31 (checked by the launcher; no wrap in the stride loop)
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned k = i % (unsigned)ldk;
+        const unsigned pix = i / (unsigned)ldk;
         float v = 0.0f;
         if (k < 147) {
             const int c = k / 49, t = k - c * 49, ky = t / 7, kx = t - ky * 7;
-            const int xo = (int)(pix % Wo);
-            const long long r = pix / Wo;
-            const int yo = (int)(r % Ho), b = (int)(r / Ho);
+            const int xo = (int)(pix % (unsigned)Wo);
+            const unsigned r = pix / (unsigned)Wo;
+            const int yo = (int)(r % (unsigned)Ho), b = (int)(r / (unsigned)Ho);
             const int y = yo * 2 - 3 + ky, x = xo * 2 - 3 + kx;
             if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(img + (((size_t)b * 3 + c) * H + y) * W + x);
         }
@@ -101,13 +101,13 @@ __global__ void __launch_bounds__(256)
 upsample_nhwc_kernel(const float* __restrict__ in, int ldi, float* __restrict__ out, int ldo, int B, int hin, int win,
                      int hout, int wout, int C, float rh, float rw, int align)
 {
-    const int c4 = C >> 2;
-    const long long total = (long long)B * hout * wout * c4;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned c4 = C >> 2;
+    const unsigned total = (unsigned)B * hout * wout * c4;              // < 2^31 (checked by the launcher; no wrap in the stride loop)
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int cq = (int)(i % c4);
-        long long r = i / c4;
-        const int x = (int)(r % wout); r /= wout;
-        const int y = (int)(r % hout), b = (int)(r / hout);
+        unsigned r = i / c4;
+        const int x = (int)(r % (unsigned)wout); r /= (unsigned)wout;
+        const int y = (int)(r % (unsigned)hout), b = (int)(r / (unsigned)hout);
         float sy, sx;
         if (align) { sy = rh * y; sx = rw * x; }
         else {
@@ -147,6 +147,47 @@ log_softmax32_kernel(float* __restrict__ x, long long pixels)
     }
 }
 
+// Last decoder stage evaluated only where the head looks (the N `choose` pixels per crop instead of H*W):
+// A[(b*N + n), tap*C + c] = U(b, y + dy, x + dx, c) for the 3x3 neighbourhood of pixel choose[b,n] = y*W + x, where
+// U is the x2 bilinear (align_corners) up-sampling of `in` (B,h,w,C) to (H,W) = (2h,2w) and positions outside the
+// image are the convolution's zero padding.  Same interpolation arithmetic as upsample_nhwc_kernel, so the gathered
+// patches equal the dense tensor's values bit for bit.  One thread per (point, tap, 4 channels).
+__global__ void __launch_bounds__(256)
+gather_up_patches_kernel(const float* __restrict__ in, const int64_t* __restrict__ choose, float* __restrict__ A, int B, int N,
+                         int h, int w, int C, float rh, float rw)
+{
+    const unsigned c4 = C >> 2;
+    const unsigned total = (unsigned)B * N * 9 * c4;
+    const int H = 2 * h, W = 2 * w;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int cq = (int)(i % c4);
+        unsigned r = i / c4;
+        const int tap = (int)(r % 9u);
+        const unsigned pt = r / 9u;
+        const int b = (int)(pt / (unsigned)N);
+        long long pix = choose[pt];
+        pix = pix < 0 ? 0 : (pix >= (long long)H * W ? (long long)H * W - 1 : pix);
+        const int y = (int)(pix / W) + tap / 3 - 1, x = (int)(pix % W) + tap % 3 - 1;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+            const float sy = rh * y, sx = rw * x;
+            const int y0 = (int)sy, x0 = (int)sx;
+            const int yp = y0 < h - 1 ? 1 : 0, xp = x0 < w - 1 ? 1 : 0;
+            const float ly1 = sy - y0, ly0 = 1.0f - ly1, lx1 = sx - x0, lx0 = 1.0f - lx1;
+            const float* p = in + (((size_t)b * h + y0) * w + x0) * C + cq * 4;
+            const float4 v00 = __ldg(reinterpret_cast<const float4*>(p));
+            const float4 v01 = __ldg(reinterpret_cast<const float4*>(p + (size_t)xp * C));
+            const float4 v10 = __ldg(reinterpret_cast<const float4*>(p + (size_t)yp * w * C));
+            const float4 v11 = __ldg(reinterpret_cast<const float4*>(p + ((size_t)yp * w + xp) * C));
+            o.x = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
+            o.y = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
+            o.z = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
+            o.w = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
+        }
+        reinterpret_cast<float4*>(A)[i] = o;
+    }
+}
+
 inline unsigned grid_for(long long total, int per_block)
 {
     long long b = (total + per_block - 1) / per_block;
@@ -160,6 +201,7 @@ extern "C" int df_enc_im2col_conv1(const float* img, float* A, int B, int H, int
 {
     if (!img || !A || B <= 0 || H <= 0 || W <= 0 || ldk < 147) return DF_ERR_ARG;
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    if ((long long)B * Ho * Wo * ldk >= (1LL << 31)) return DF_ERR_ARG;
     im2col_conv1_kernel<<<grid_for((long long)B * Ho * Wo * ldk, 256), 256, 0, (cudaStream_t)stream>>>(img, A, B, H, W, Ho, Wo, ldk);
     DF_RETURN_LAST_ERROR();
 }
@@ -193,6 +235,7 @@ extern "C" int df_enc_upsample(const float* in, int ldi, float* out, int ldo, in
     if (!in || !out || B <= 0 || hin <= 0 || win <= 0 || hout <= 0 || wout <= 0 || C <= 0 || (C & 3) || (ldi & 3) || (ldo & 3))
         return DF_ERR_ARG;
     if (((uintptr_t)in & 15) || ((uintptr_t)out & 15)) return DF_ERR_ARG;
+    if ((long long)B * hout * wout * (C >> 2) >= (1LL << 31)) return DF_ERR_ARG;
     float rh, rw;
     if (align_corners) {
         rh = hout > 1 ? (float)(hin - 1) / (hout - 1) : 0.f;
@@ -210,5 +253,17 @@ extern "C" int df_enc_log_softmax32(float* x, long long pixels, void* stream)
 {
     if (!x || pixels <= 0) return DF_ERR_ARG;
     log_softmax32_kernel<<<grid_for(pixels, 8), 256, 0, (cudaStream_t)stream>>>(x, pixels);
+    DF_RETURN_LAST_ERROR();
+}
+
+extern "C" int df_enc_gather_up_patches(const float* in, const int64_t* choose, float* A, int B, int N, int h, int w, int C,
+                                        void* stream)
+{
+    if (!in || !choose || !A || B <= 0 || N <= 0 || h <= 0 || w <= 0 || C <= 0 || (C & 3)) return DF_ERR_ARG;
+    if ((long long)B * N * 9 * (C >> 2) >= (1LL << 31)) return DF_ERR_ARG;
+    const int H = 2 * h, W = 2 * w;
+    const float rh = H > 1 ? (float)(h - 1) / (H - 1) : 0.f, rw = W > 1 ? (float)(w - 1) / (W - 1) : 0.f;
+    gather_up_patches_kernel<<<grid_for((long long)B * N * 9 * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(
+        in, choose, A, B, N, h, w, C, rh, rw);
     DF_RETURN_LAST_ERROR();
 }

@@ -85,11 +85,19 @@ class PackedEncoder:
             ws["bott"] = torch.empty(b, H8, W8, 1024, **f)
             hs = [(2 * H8, 2 * W8), (4 * H8, 4 * W8), (8 * H8, 8 * W8)]
             ws["hs"] = hs
-            ws["up_in"] = [torch.empty(b, h, w, c, **f) for (h, w), c in zip(hs, (1024, 256, 64))]
-            ws["up_out"] = [torch.empty(b, h, w, c, **f) for (h, w), c in zip(hs, (256, 64, 64))]
-            ws["feat"] = torch.empty(b, hs[2][0], hs[2][1], 32, **f)
+            # decoder stages are allocated on first use: the sparse tail (forward_points) never needs the
+            # full-resolution third stage (1 GB per bucket of 64 crops at 160x160)
+            ws["up_in"], ws["up_out"], ws["feat"] = [None] * 3, [None] * 3, None
             self._ws[key] = ws
         return ws
+
+    def _stage_buffers(self, ws, i, b):
+        if ws["up_in"][i] is None:
+            f = dict(device=self.device, dtype=torch.float32)
+            (h, w), cin, cout = ws["hs"][i], (1024, 256, 64)[i], (256, 64, 64)[i]
+            ws["up_in"][i] = torch.empty(b, h, w, cin, **f)
+            ws["up_out"][i] = torch.empty(b, h, w, cout, **f)
+        return ws["up_in"][i], ws["up_out"][i]
 
     # ---- kernels ----
     @staticmethod
@@ -108,6 +116,46 @@ class PackedEncoder:
     def forward(self, img: torch.Tensor, precision: str = "3xtf32") -> torch.Tensor:
         """img (b,3,H,W) fp32 CUDA (NCHW, as the reference feeds it) -> (b,H,W,32) NHWC log-softmax embedding.
         H and W must be multiples of 8 (the reference's crops are multiples of 40)."""
+        x, ws, mode = self._trunk(img, precision, stages=3)
+        b, h, w = x.shape[0], x.shape[1], x.shape[2]
+        rows = b * h * w
+        if ws["feat"] is None:
+            ws["feat"] = torch.empty(b, h, w, 32, device=self.device, dtype=torch.float32)
+        ops.gemm(x, self.final_w, self.final_b, ws["feat"], M=rows, N=32, K=64, lda=64, ldw=64, ldc=32, relu=False)
+        check(lib.df_enc_log_softmax32(ptr(ws["feat"]), rows, stream()), "df_enc_log_softmax32")
+        return ws["feat"]
+
+    def forward_points(self, img: torch.Tensor, choose: torch.Tensor, emb_pm_out: torch.Tensor,
+                       precision: str = "3xtf32") -> torch.Tensor:
+        """The embedding only where the head reads it: emb_pm_out (b*N,32) = embedding at pixels choose (b,N).
+
+        The head gathers N = 500 of the H*W (6 400 .. 25 600) pixels, so the last decoder stage -- x2 up-sampling, the
+        3x3 64->64 convolution + PReLU, the 1x1 64->32 convolution and the channel log-softmax (lib/pspnet.py:34-37,
+        :53-56, lib/network.py:98-102) -- is evaluated on gathered 3x3 patches of those pixels only: identical values,
+        2-8% of the work and none of the full-resolution intermediates."""
+        x, ws, mode = self._trunk(img, precision, stages=2)             # (b, H/2, W/2, 64)
+        b, h, w = x.shape[0], x.shape[1], x.shape[2]
+        choose = ops.i64c(choose).view(b, -1)
+        n = choose.shape[1]
+        rows = b * n
+        key = ("pts", n)
+        if key not in ws:
+            f = dict(device=self.device, dtype=torch.float32)
+            ws[key] = (torch.empty(rows, 9 * 64, **f), torch.empty(rows, 64, **f))
+        patches, act = ws[key]
+        s = stream()
+        check(lib.df_enc_gather_up_patches(ptr(x), ptr(choose), ptr(patches), b, n, h, w, 64, s), "df_enc_gather_up_patches")
+        up = self.ups[2]
+        hi, lo = up["w"].split()
+        # the gathered patches as a 1 x rows "image" with 576 channels: a 1-tap convolution = GEMM with the PReLU epilogue
+        check(lib.df_conv_tc(ptr(patches), 1, 1, rows, 576, 576, ptr(hi), ptr(lo), 1, 1, ptr(up["b"]), None, 0, ptr(up["a"]),
+                             2, ptr(act), 64, 64, mode, s), "df_conv_tc")
+        ops.gemm(act, self.final_w, self.final_b, emb_pm_out, M=rows, N=32, K=64, lda=64, ldw=64, ldc=32, relu=False)
+        check(lib.df_enc_log_softmax32(ptr(emb_pm_out), rows, s), "df_enc_log_softmax32")
+        return emb_pm_out
+
+    def _trunk(self, img: torch.Tensor, precision: str, stages: int):
+        """Everything up to and including `stages` of the three up-sampling stages.  Returns (activation, workspace, mode)."""
         if precision not in ("3xtf32", "tf32"):
             raise ValueError("the tensor-core encoder runs in '3xtf32' (fp32 parity) or 'tf32'")
         mode = ops.PRECISIONS[precision]
@@ -176,14 +224,11 @@ class PackedEncoder:
                  relu=True, precision=precision)
         # three x2 bilinear (align_corners) + 3x3 conv + PReLU stages
         x, (h, w) = ws["bott"], (H8, W8)
-        for i, up in enumerate(self.ups):
+        for i, up in enumerate(self.ups[:stages]):
             hh, wwd = ws["hs"][i]
             c = x.shape[3]
-            check(lib.df_enc_upsample(ptr(x), c, ptr(ws["up_in"][i]), c, b, h, w, hh, wwd, c, 1, s), "df_enc_upsample")
-            self._conv(ws["up_in"][i], up["w"], ws["up_out"][i], taps=9, dil=1, bias=up["b"], prelu=up["a"], act=2, mode=mode)
-            x, (h, w) = ws["up_out"][i], (hh, wwd)
-        # final 1x1 (64 -> 32) + channel log-softmax
-        rows = b * h * w
-        ops.gemm(x, self.final_w, self.final_b, ws["feat"], M=rows, N=32, K=64, lda=64, ldw=64, ldc=32, relu=False)
-        check(lib.df_enc_log_softmax32(ptr(ws["feat"]), rows, s), "df_enc_log_softmax32")
-        return ws["feat"]
+            up_in, up_out = self._stage_buffers(ws, i, b)
+            check(lib.df_enc_upsample(ptr(x), c, ptr(up_in), c, b, h, w, hh, wwd, c, 1, s), "df_enc_upsample")
+            self._conv(up_in, up["w"], up_out, taps=9, dil=1, bias=up["b"], prelu=up["a"], act=2, mode=mode)
+            x, (h, w) = up_out, (hh, wwd)
+        return x, ws, mode

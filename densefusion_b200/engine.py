@@ -39,7 +39,7 @@ class PackedPoseNetHead:
         self.w6, self.b6 = ops.SplitWeight(_w2d(f.conv6.weight)), f.conv6.bias.detach().float().contiguous()
         t1 = [_w2d(getattr(net, f"conv1_{b}").weight) for b in "rtc"]
         self.w1_local = ops.SplitWeight(torch.cat([w[:, :384] for w in t1], 0))       # (1920,384)
-        self.w1_global = torch.cat([w[:, 384:] for w in t1], 0).contiguous()         # (1920,1024)
+        self.w1_global = ops.SplitWeight(torch.cat([w[:, 384:] for w in t1], 0))     # (1920,1024)
         self.b1 = torch.cat([getattr(net, f"conv1_{b}").bias.detach().float() for b in "rtc"]).contiguous()
         self.w2 = ops.SplitWeight(torch.stack([_w2d(getattr(net, f"conv2_{b}").weight) for b in "rtc"]))   # (3,256,640)
         self.b2 = torch.cat([getattr(net, f"conv2_{b}").bias.detach().float() for b in "rtc"]).contiguous()
@@ -61,9 +61,9 @@ class PackedRefiner:
         self.w_e2, self.b_e2 = ops.SplitWeight(_w2d(f.e_conv2.weight)), f.e_conv2.bias.detach().float().contiguous()
         self.w5, self.b5 = ops.SplitWeight(_w2d(f.conv5.weight)), f.conv5.bias.detach().float().contiguous()
         self.w6, self.b6 = ops.SplitWeight(_w2d(f.conv6.weight)), f.conv6.bias.detach().float().contiguous()
-        self.w1 = torch.cat([_w2d(net.conv1_r.weight), _w2d(net.conv1_t.weight)], 0).contiguous()     # (1024,1024)
+        self.w1 = ops.SplitWeight(torch.cat([_w2d(net.conv1_r.weight), _w2d(net.conv1_t.weight)], 0))     # (1024,1024)
         self.b1 = torch.cat([net.conv1_r.bias.detach().float(), net.conv1_t.bias.detach().float()]).contiguous()
-        self.w2 = torch.stack([_w2d(net.conv2_r.weight), _w2d(net.conv2_t.weight)]).contiguous()       # (2,128,512)
+        self.w2 = ops.SplitWeight(torch.stack([_w2d(net.conv2_r.weight), _w2d(net.conv2_t.weight)]))       # (2,128,512)
         self.b2 = torch.cat([net.conv2_r.bias.detach().float(), net.conv2_t.bias.detach().float()]).contiguous()
         self.w3 = [_w2d(net.conv3_r.weight).contiguous(), _w2d(net.conv3_t.weight).contiguous()]
         self.b3 = [net.conv3_r.bias.detach().float().contiguous(), net.conv3_t.bias.detach().float().contiguous()]
@@ -95,9 +95,8 @@ class Workspace:
             self.h2 = torch.empty(crops, 256, **f)
 
 
-def _point_features(w, ws: Workspace, x, emb_pm, rows, precision, do_emb=True):
+def _point_features(w, pf, x, emb_pm, rows, precision, do_emb=True):
     """pf = [relu(conv1 x) | relu(e_conv1 emb) | relu(conv2 .) | relu(e_conv2 .)]  (lib/network.py:54-60)."""
-    pf = ws.pf
     check(lib.df_xyz_conv(ptr(x), ptr(w.w_x1), ptr(w.b_x1), ptr(pf), 384, rows, stream()), "df_xyz_conv")
     if do_emb:
         ops.gemm(emb_pm, w.w_e1, w.b_e1, pf[:, 64:], M=rows, N=64, K=32, lda=32, ldw=32, ldc=384, relu=True,
@@ -109,21 +108,32 @@ def _point_features(w, ws: Workspace, x, emb_pm, rows, precision, do_emb=True):
                  precision=precision)
 
 
-def posenet_head_chunk(w: PackedPoseNetHead, ws: Workspace, x, emb_pm, obj, crops, n, out_r, out_t, out_c,
-                       precision="fp32"):
-    """x (crops*n,3), emb_pm (crops*n,32), obj (crops,) -> out_r (crops*n,4), out_t (.,3), out_c (.)."""
+# The head and the refiner are written in three phases so that a caller working through many chunks of crops can run
+# the per-crop (M = crops) GEMMs -- the folded global-feature bias and the refiner's MLP towers -- ONCE for all chunks:
+# at M = 32 they are weight-bandwidth bound launches (4 MB of weights per 2 MFLOP/row), 7% of the pose step when issued
+# per chunk.
+def head_features_chunk(w: PackedPoseNetHead, ws: Workspace, pf, x, emb_pm, crops, n, g_out, precision="fp32"):
+    """Phase A: point features into pf (crops*n,384), pooled global feature into g_out (crops,1024)."""
     rows = crops * n
-    _point_features(w, ws, x, emb_pm, rows, precision)
-    pf = ws.pf
+    _point_features(w, pf, x, emb_pm, rows, precision)
     ops.gemm(pf[:, 128:], w.w5, w.b5, ws.h5, M=rows, N=512, K=256, lda=384, ldw=256, ldc=512, relu=True,
              precision=precision)
     ops.gemm(ws.h5, w.w6, w.b6, None, M=rows, N=1024, K=512, lda=512, ldw=512, ldc=0, relu=True,
              precision=precision, rows_per_crop=n, pool_partial=ws.partial)
-    check(lib.df_pool_finish(ptr(ws.partial), ptr(ws.g), crops, ws.tiles, 1024, n, stream()), "df_pool_finish")
-    # folded global feature -> per-crop bias of the first tower layer
-    ops.gemm(ws.g, w.w1_global, w.b1, ws.gbias, M=crops, N=1920, K=1024, lda=1024, ldw=1024, ldc=1920, relu=False,
+    check(lib.df_pool_finish(ptr(ws.partial), ptr(g_out), crops, ws.tiles, 1024, n, stream()), "df_pool_finish")
+
+
+def head_global_bias(w: PackedPoseNetHead, g, gbias, crops, precision="fp32"):
+    """Phase B: folded global feature -> per-crop bias of the first tower layer, (crops,1024) -> (crops,1920)."""
+    ops.gemm(g, w.w1_global, w.b1, gbias, M=crops, N=1920, K=1024, lda=1024, ldw=1024, ldc=1920, relu=False,
              precision=precision)
-    ops.gemm(pf, w.w1_local, ws.gbias, ws.h1, M=rows, N=1920, K=384, lda=384, ldw=384, ldc=1920, relu=True,
+
+
+def head_towers_chunk(w: PackedPoseNetHead, ws: Workspace, pf, gbias, obj, crops, n, out_r, out_t, out_c,
+                      precision="fp32"):
+    """Phase C: r / t / c towers on pf with the per-crop bias, selected object's outputs."""
+    rows = crops * n
+    ops.gemm(pf, w.w1_local, gbias, ws.h1, M=rows, N=1920, K=384, lda=384, ldw=384, ldc=1920, relu=True,
              precision=precision, bias_crop_stride=1920, rows_per_crop=n)
     ops.gemm(ws.h1, w.w2, w.b2, ws.h2, M=rows, N=256, K=640, lda=1920, ldw=640, ldc=768, relu=True,
              precision=precision, groups=3, a_gs=640, w_gs=256 * 640, bias_gs=256, c_gs=256)
@@ -134,20 +144,38 @@ def posenet_head_chunk(w: PackedPoseNetHead, ws: Workspace, x, emb_pm, obj, crop
                             ptr(out_c), stream()), "df_select_out")
 
 
-def refiner_chunk(w: PackedRefiner, ws: Workspace, x, emb_pm, obj, crops, n, out_r, out_t, precision="fp32",
-                  emb_ready=False):
-    """x (crops*n,3) re-expressed cloud, emb_pm (crops*n,32) -> out_r (crops,4), out_t (crops,3).
-    emb_ready=True: columns e1|e2 of ws.pf already hold this crop batch's embedding features (they do not
-    depend on the iteration), only the xyz branch is recomputed."""
+def posenet_head_chunk(w: PackedPoseNetHead, ws: Workspace, x, emb_pm, obj, crops, n, out_r, out_t, out_c,
+                       precision="fp32"):
+    """x (crops*n,3), emb_pm (crops*n,32), obj (crops,) -> out_r (crops*n,4), out_t (.,3), out_c (.)."""
+    head_features_chunk(w, ws, ws.pf, x, emb_pm, crops, n, ws.g, precision)
+    head_global_bias(w, ws.g, ws.gbias, crops, precision)
+    head_towers_chunk(w, ws, ws.pf, ws.gbias, obj, crops, n, out_r, out_t, out_c, precision)
+
+
+def refiner_features_chunk(w: PackedRefiner, ws: Workspace, pf, x, emb_pm, crops, n, g_out, precision="fp32",
+                           emb_ready=False):
+    """x (crops*n,3) re-expressed cloud, emb_pm (crops*n,32) -> pooled feature g_out (crops,1024).
+    emb_ready=True: columns e1|e2 of pf already hold this crop batch's embedding features (they do not depend on
+    the iteration), only the xyz branch is recomputed."""
     rows = crops * n
-    _point_features(w, ws, x, emb_pm, rows, precision, do_emb=not emb_ready)
-    ops.gemm(ws.pf, w.w5, w.b5, ws.h5, M=rows, N=512, K=384, lda=384, ldw=384, ldc=512, relu=True, precision=precision)
+    _point_features(w, pf, x, emb_pm, rows, precision, do_emb=not emb_ready)
+    ops.gemm(pf, w.w5, w.b5, ws.h5, M=rows, N=512, K=384, lda=384, ldw=384, ldc=512, relu=True, precision=precision)
     ops.gemm(ws.h5, w.w6, w.b6, None, M=rows, N=1024, K=512, lda=512, ldw=512, ldc=0, relu=True,
              precision=precision, rows_per_crop=n, pool_partial=ws.partial)
-    check(lib.df_pool_finish(ptr(ws.partial), ptr(ws.g), crops, ws.tiles, 1024, n, stream()), "df_pool_finish")
-    # the MLP towers are tiny (M = crops): always exact fp32
-    ops.gemm(ws.g, w.w1, w.b1, ws.h1, M=crops, N=1024, K=1024, lda=1024, ldw=1024, ldc=1024, relu=True)
-    ops.gemm(ws.h1, w.w2, w.b2, ws.h2, M=crops, N=128, K=512, lda=1024, ldw=512, ldc=256, relu=True,
+    check(lib.df_pool_finish(ptr(ws.partial), ptr(g_out), crops, ws.tiles, 1024, n, stream()), "df_pool_finish")
+
+
+def refiner_mlp(w: PackedRefiner, g, h1, h2, obj, crops, out_r, out_t, precision="fp32"):
+    """The two MLP towers on the pooled features: g (crops,1024) -> out_r (crops,4), out_t (crops,3).
+    Below 256 rows the GEMMs stay on the exact-fp32 kernel in every mode (ops.tc_eligible)."""
+    ops.gemm(g, w.w1, w.b1, h1, M=crops, N=1024, K=1024, lda=1024, ldw=1024, ldc=1024, relu=True, precision=precision)
+    ops.gemm(h1, w.w2, w.b2, h2, M=crops, N=128, K=512, lda=1024, ldw=512, ldc=256, relu=True, precision=precision,
              groups=2, a_gs=512, w_gs=128 * 512, bias_gs=128, c_gs=128)
-    check(lib.df_select_out(ptr(ws.h2), 256, ptr(w.w3[0]), ptr(w.b3[0]), ptr(w.w3[1]), ptr(w.b3[1]), None, None,
+    check(lib.df_select_out(ptr(h2), 256, ptr(w.w3[0]), ptr(w.b3[0]), ptr(w.w3[1]), ptr(w.b3[1]), None, None,
                             ptr(obj), 1, w.num_obj, crops, ptr(out_r), ptr(out_t), None, stream()), "df_select_out")
+
+
+def refiner_chunk(w: PackedRefiner, ws: Workspace, x, emb_pm, obj, crops, n, out_r, out_t, precision="fp32",
+                  emb_ready=False):
+    refiner_features_chunk(w, ws, ws.pf, x, emb_pm, crops, n, ws.g, precision, emb_ready)
+    refiner_mlp(w, ws.g, ws.h1, ws.h2, obj, crops, out_r, out_t, precision)

@@ -60,7 +60,12 @@ class PoseEstimator:
                      out_c=torch.empty(B, self.n, 1, **f), pose=torch.empty(B, 7, device=self.device, dtype=torch.float64),
                      which=torch.empty(B, device=self.device, dtype=torch.int64),
                      new_cloud=torch.empty(B, self.n, 3, **f), r2=torch.empty(B, 4, **f), t2=torch.empty(B, 3, **f),
-                     emb_pm=torch.empty(B * self.n, 32, **f))
+                     emb_pm=torch.empty(B * self.n, 32, **f),
+                     # point features of every crop (head / refiner keep separate copies: the refiner's embedding
+                     # branch is computed once and reused by every iteration), per-crop features and MLP scratch
+                     pf_head=torch.empty(B * self.n, 384, **f), pf_ref=torch.empty(B * self.n, 384, **f),
+                     g=torch.empty(B, 1024, **f), gbias=torch.empty(B, 1920, **f),
+                     mlp1=torch.empty(B, 1024, **f), mlp2=torch.empty(B, 256, **f))
             self._bufs[B] = b
         return b
 
@@ -71,11 +76,7 @@ class PoseEstimator:
             if self._enc is None:
                 from .encoder import PackedEncoder
                 self._enc = PackedEncoder(self.estimator.cnn)
-            feat = self._enc.forward(img, self.precision)                 # (B,H,W,32) channels-last
-            B, H, W, C = feat.shape
-            choose = ops.i64c(choose).view(B, -1)
-            check(lib.df_gather_embedding(ptr(feat), ptr(choose), ptr(emb_pm_out), None, H * W * C, 1, C, B, self.n, H * W,
-                                          stream()), "df_gather_embedding")
+            self._enc.forward_points(img, choose, emb_pm_out, self.precision)
             return
         if self.channels_last:
             img = img.contiguous(memory_format=torch.channels_last)
@@ -91,8 +92,11 @@ class PoseEstimator:
 
     def head_and_refine(self, cloud: torch.Tensor, emb_pm: torch.Tensor, obj: torch.Tensor,
                         iterations: Optional[int] = None) -> torch.Tensor:
-        """cloud (B,N,3), emb_pm (B*N,32), obj (B,) -> pose (B,7) float64.  Also leaves the un-refined
-        selection in self.last['pose0'] when iterations == 0."""
+        """cloud (B,N,3), emb_pm (B*N,32), obj (B,) -> pose (B,7) float64.
+
+        Per-point layers run chunk by chunk (a chunk's activations stay L2-resident); everything with one row per
+        crop -- the folded global-feature bias, pose selection, the refiner's MLP towers, pose composition -- runs once
+        for all B crops."""
         iters = self.iterations if iterations is None else iterations
         B, n = cloud.shape[0], self.n
         buf = self._buffers(B)
@@ -100,25 +104,31 @@ class PoseEstimator:
         cloud = ops.f32c(cloud)
         obj = ops.i64c(obj).view(-1)
         s = stream()
-        for c0 in range(0, B, self.chunk):
-            c1 = min(B, c0 + self.chunk)
-            nb = c1 - c0
+        p = self.precision
+        chunks = [(c0, min(B, c0 + self.chunk)) for c0 in range(0, B, self.chunk)]
+        x_all = cloud.view(B * n, 3)
+        # ---- estimate ----
+        for c0, c1 in chunks:
             rows = slice(c0 * n, c1 * n)
-            x = cloud[c0:c1].view(nb * n, 3)
-            e = emb_pm[rows]
-            o = obj[c0:c1]
-            r, t, c = buf["out_r"][c0:c1], buf["out_t"][c0:c1], buf["out_c"][c0:c1]
-            engine.posenet_head_chunk(self.w_head, wh, x, e, o, nb, n, r, t, c, self.precision)
-            pose = buf["pose"][c0:c1]
-            check(lib.df_select_pose(ptr(r), ptr(t), ptr(c), ptr(x), nb, n, ptr(pose), ptr(buf["which"][c0:c1]), s),
-                  "df_select_pose")
-            nc = buf["new_cloud"][c0:c1]
-            for it in range(iters):
-                check(lib.df_cloud_transform(ptr(x), ptr(pose), ptr(nc), nb, n, s), "df_cloud_transform")
-                engine.refiner_chunk(self.w_ref, wr, nc.view(nb * n, 3), e, o, nb, n, buf["r2"][c0:c1],
-                                     buf["t2"][c0:c1], self.precision, emb_ready=it > 0)
-                check(lib.df_pose_compose(ptr(pose), ptr(buf["r2"][c0:c1]), ptr(buf["t2"][c0:c1]), nb, s),
-                      "df_pose_compose")
+            engine.head_features_chunk(self.w_head, wh, buf["pf_head"][rows], x_all[rows], emb_pm[rows], c1 - c0, n,
+                                       buf["g"][c0:c1], p)
+        engine.head_global_bias(self.w_head, buf["g"], buf["gbias"], B, p)
+        for c0, c1 in chunks:
+            rows = slice(c0 * n, c1 * n)
+            engine.head_towers_chunk(self.w_head, wh, buf["pf_head"][rows], buf["gbias"][c0:c1], obj[c0:c1], c1 - c0, n,
+                                     buf["out_r"][c0:c1], buf["out_t"][c0:c1], buf["out_c"][c0:c1], p)
+        check(lib.df_select_pose(ptr(buf["out_r"]), ptr(buf["out_t"]), ptr(buf["out_c"]), ptr(x_all), B, n, ptr(buf["pose"]),
+                                 ptr(buf["which"]), s), "df_select_pose")
+        # ---- refine ----
+        for it in range(iters):
+            check(lib.df_cloud_transform(ptr(x_all), ptr(buf["pose"]), ptr(buf["new_cloud"]), B, n, s), "df_cloud_transform")
+            nc = buf["new_cloud"].view(B * n, 3)
+            for c0, c1 in chunks:
+                rows = slice(c0 * n, c1 * n)
+                engine.refiner_features_chunk(self.w_ref, wr, buf["pf_ref"][rows], nc[rows], emb_pm[rows], c1 - c0, n,
+                                              buf["g"][c0:c1], p, emb_ready=it > 0)
+            engine.refiner_mlp(self.w_ref, buf["g"], buf["mlp1"], buf["mlp2"], obj, B, buf["r2"], buf["t2"], p)
+            check(lib.df_pose_compose(ptr(buf["pose"]), ptr(buf["r2"]), ptr(buf["t2"]), B, s), "df_pose_compose")
         return buf["pose"]
 
     @torch.no_grad()

@@ -168,6 +168,10 @@ int df_enc_adaptive_avgpool(const float* in, int ldi, float* out, int B, int H, 
 int df_enc_upsample(const float* in, int ldi, float* out, int ldo, int B, int hin, int win, int hout, int wout, int C,
                     int align_corners, void* stream);
 int df_enc_log_softmax32(float* x, long long pixels, void* stream);
+/* Sparse last decoder stage: the 3x3 patches of the x2-upsampled (align_corners) map `in` (B,h,w,C) around the N chosen
+ * pixels of every crop (choose (B,N), indices into the (2h x 2w) image), A (B*N, 9*C) tap-major; zero outside the image. */
+int df_enc_gather_up_patches(const float* in, const int64_t* choose, float* A, int B, int N, int h, int w, int C,
+                             void* stream);
 
 /* ---- encoder helper -----------------------------------------------------------------------------
  * NCHW bilinear up-sampling (lib/pspnet.py:20-23 F.upsample(size=...), :30-34 nn.Upsample(scale_factor=2,

@@ -117,6 +117,32 @@ def test_encoder_vs_oracle(precision, tol, b, hw):
     assert err < tol
 
 
+@pytest.mark.parametrize("b,hw", [(3, (80, 80)), (2, (120, 160))])
+def test_encoder_sparse_tail_equals_dense_gather(b, hw):
+    """forward_points (last decoder stage on gathered 3x3 patches of the chosen pixels only) == dense encoder + gather,
+    including pixels on the image border (zero padding of the 3x3 convolution) -- and both match the oracle."""
+    from densefusion_b200 import ops
+    from densefusion_b200.encoder import PackedEncoder
+    est, _, est_sd, _ = build_nets(500, 21, seed=6)
+    g = torch.Generator().manual_seed(hw[1] + b)
+    img = torch.randn(b, 3, hw[0], hw[1], generator=g)
+    H, W = hw
+    choose = torch.stack([torch.sort(torch.randperm(H * W, generator=g)[:500])[0] for _ in range(b)])
+    choose[:, 0], choose[:, 1], choose[:, 2], choose[:, 3] = 0, W - 1, (H - 1) * W, H * W - 1      # the four corners
+    enc = PackedEncoder(est.cnn)
+    dense = enc.forward(img.cuda(), "3xtf32")
+    pm_dense, _ = ops.gather_embedding(dense.permute(0, 3, 1, 2), choose.cuda(), want_cm=False)
+    pm = torch.empty(b * 500, 32, device="cuda")
+    enc.forward_points(img.cuda(), choose.cuda(), pm, "3xtf32")
+    torch.cuda.synchronize()
+    err = rel(pm, pm_dense)
+    with torch.no_grad():
+        want = O.gather_embedding(O.psp_encoder(est_sd, img), choose.view(b, 1, 500))          # (b,32,N)
+    err_o = rel(pm.view(b, 500, 32).permute(0, 2, 1), want)
+    print(f"sparse tail vs dense gather {err:.3e}; vs oracle {err_o:.3e}")
+    assert err < 1e-5 and err_o < 1e-4
+
+
 def test_pipeline_with_tensor_core_encoder_vs_oracle():
     """estimate + 2 refine iterations with encoder AND head on the tensor cores (3xTF32) against the oracle's eval loop."""
     import numpy as np
