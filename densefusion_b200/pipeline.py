@@ -41,6 +41,8 @@ class PoseEstimator:
             raise ValueError("encoder must be 'auto', 'tc' or 'torch'")
         self.encoder = encoder
         self._enc = None
+        self.concurrent_buckets = True
+        self._streams = []
         if channels_last:
             estimator.cnn.to(memory_format=torch.channels_last)
 
@@ -68,6 +70,11 @@ class PoseEstimator:
                      mlp1=torch.empty(B, 1024, **f), mlp2=torch.empty(B, 256, **f))
             self._bufs[B] = b
         return b
+
+    def _side_streams(self, k: int):
+        while len(self._streams) < k:
+            self._streams.append(torch.cuda.Stream(device=self.device))
+        return self._streams
 
     # ---- stages ---------------------------------------------------------------------------------
     def encode(self, img: torch.Tensor, choose: torch.Tensor, emb_pm_out: torch.Tensor) -> None:
@@ -150,13 +157,25 @@ class PoseEstimator:
             cat = dict(cloud=torch.empty(total, self.n, 3, device=self.device),
                        obj=torch.empty(total, device=self.device, dtype=torch.int64))
             self._bufs[key] = cat
+        # The (H,W) buckets are independent until the head: each bucket's encoder runs on its own stream (fork / join, which
+        # CUDA-graph capture records as parallel branches), so the small low-resolution layers of one bucket fill the SMs
+        # another bucket's tail leaves idle.
+        main = torch.cuda.current_stream(self.device)
+        side = self._side_streams(len(buckets))
         o = 0
-        for b in buckets:
+        for i, b in enumerate(buckets):
             nb = b["cloud"].shape[0]
-            self.encode(b["img"], b["choose"], buf["emb_pm"][o * self.n:(o + nb) * self.n])
+            st = side[i] if (self.concurrent_buckets and len(buckets) > 1) else main
+            if st is not main:
+                st.wait_stream(main)
+            with torch.cuda.stream(st):
+                self.encode(b["img"], b["choose"], buf["emb_pm"][o * self.n:(o + nb) * self.n])
             cat["cloud"][o:o + nb].copy_(b["cloud"])
             cat["obj"][o:o + nb].copy_(b["obj"].view(-1))
             o += nb
+        if self.concurrent_buckets and len(buckets) > 1:
+            for st in side[:len(buckets)]:
+                main.wait_stream(st)
         return self.head_and_refine(cat["cloud"], buf["emb_pm"], cat["obj"], iterations)
 
 
