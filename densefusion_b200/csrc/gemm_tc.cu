@@ -664,6 +664,11 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (CTAS == 2) cluster_sync_all();              // the peer's barriers exist before anything remote touches them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, cluster rendezvous) may overlap the
+    // tail of the previous kernel in the stream; global memory is only touched after the wait.  Dependents are released
+    // at once -- they block in their own griddepcontrol.wait until this grid has completed and flushed.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         // ------------------------------- TMA producer -------------------------------
@@ -1001,6 +1006,8 @@ int launch_persistent(const CUtensorMap& mhi, const CUtensorMap& mlo, const TcPa
     return 0;
 }
 
+bool use_pdl();
+
 // NHWC image (B, H, W, C) with pixel pitch `ld` floats as a 4-D tensor; box = 32 channels x TW x TH x TB pixels
 bool make_map_nhwc(CUtensorMap* map, const float* base, int B, int H, int W, int C, int ld, int TW, int TH, int TB)
 {
@@ -1092,10 +1099,12 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
     const int clusters = total < max_clusters ? total : max_clusters;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(clusters * CTAS); cfg.blockDim = dim3(Q_THREADS); cfg.dynamicSmemBytes = Q_SMEM_TOTAL; cfg.stream = s;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = use_pdl() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_q_kernel<CTAS, A_STAGES>, ma, mhi, mlo, p, bn_cta, m_tiles, n_tiles, total);
     return e == cudaSuccess ? 0 : (int)e;
 }
@@ -1108,6 +1117,17 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict
     const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
     hi[i] = h;
     lo[i] = v - h;
+}
+
+// DF_TC_PDL=0 turns programmatic dependent launch off (A/B timing runs)
+bool use_pdl()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DF_TC_PDL");
+        v = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return v == 1;
 }
 
 // DF_TC_VARIANT=4..7 overrides the automatic choice (A/B timing runs)

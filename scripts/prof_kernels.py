@@ -1,12 +1,13 @@
-"""Run each hand-written kernel a few times at its bench shape (profiling driver for ncu)."""
+"""Run each hand-written hot kernel a few times at its bench shape (profiling driver for ncu)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from densefusion_b200 import ops, synth
+from densefusion_b200.encoder import PackedEncoder, _pack_conv
 
 dev = "cuda"
 torch.manual_seed(0)
-crops, n = 32, 500
+crops, n = 128, 500
 rows = crops * n
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 
@@ -17,21 +18,31 @@ def gemm_case(M, N, K, precision, pooled=False, percrop=False, groups=1):
     W.split()
     bias = torch.randn(crops if percrop else 1, N * groups, device=dev)
     C = torch.empty(M, N * groups, device=dev)
-    part = torch.empty(crops, 4, N, device=dev) if pooled else None
+    part = torch.empty(M // n, 4, N, device=dev) if pooled else None
     for _ in range(reps):
         ops.gemm(A, W, bias, None if pooled else C, M=M, N=N, K=K, lda=K * groups, ldw=K, ldc=N * groups, relu=True,
                  precision=precision, bias_crop_stride=N * groups if percrop else 0, rows_per_crop=n, groups=groups,
                  a_gs=K, w_gs=N * K, bias_gs=N, c_gs=N, pool_partial=part)
 
 
-for prec in ("3xtf32", "fp32"):
-    gemm_case(rows, 1920, 384, prec, percrop=True)        # tower layer 1 (dominant)
-    gemm_case(rows, 1024, 512, prec, pooled=True)         # conv6 + pool
-    gemm_case(rows, 512, 256, prec)                       # conv5
-    gemm_case(rows, 256, 640, prec, groups=3)             # tower layer 2
+def conv_case(B, H, W, Cin, Cout, dil):
+    x = torch.randn(B, H, W, Cin, device=dev)
+    w = _pack_conv(torch.randn(Cout, Cin, 3, 3, device=dev) / (9 * Cin) ** 0.5)
+    out = torch.empty(B, H, W, Cout, device=dev)
+    for _ in range(reps):
+        PackedEncoder._conv(x, w, out, taps=9, dil=dil, act=1, mode=1)
+
+
+# order == order of the cases in profiles/*_ncu_full_selected.csv
+gemm_case(rows, 1920, 384, "3xtf32", percrop=True)        # 1 tower layer 1 at the bench's chunk (the roofline kernel)
+gemm_case(rows, 1024, 512, "3xtf32", pooled=True)         # 2 conv6 + pool
+gemm_case(rows, 256, 640, "3xtf32", groups=3)             # 3 tower layer 2
+conv_case(64, 40, 40, 1024, 256, 1)                       # 4 up_1 convolution, 160x160 bucket (K = 9216, 16 accumulation runs)
+conv_case(64, 20, 20, 512, 512, 4)                        # 5 layer4.1 convolution, dilation 4
+conv_case(64, 80, 80, 256, 64, 1)                         # 6 up_2 convolution (64 output channels)
 # loss (ADD-S) and kNN at config C1 shapes (32 crops)
 g = torch.Generator().manual_seed(1)
-B = crops
+B = 32
 pr = torch.randn(B, n, 4, generator=g).to(dev); pt = (torch.randn(B, n, 3, generator=g) * 0.02).to(dev)
 pc = (torch.rand(B, n, 1, generator=g) * 0.9 + 0.05).to(dev)
 model = (torch.randn(B, 500, 3, generator=g) * 0.05).to(dev); target = model + torch.tensor([0., 0., 0.8], device=dev)
