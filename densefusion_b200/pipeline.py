@@ -212,3 +212,47 @@ class GraphedBuckets:
     def run(self) -> torch.Tensor:
         self.graph.replay()
         return self.out
+
+
+class StreamingEstimator:
+    """Steady-state serving loop over fixed bucket shapes: the host->device copy of batch i+1 runs on a copy stream
+    while batch i computes (two CUDA graphs over two sets of static inputs; scratch is shared because the graphs replay
+    back to back on one stream), and the poses of batch i come back through a pinned buffer per slot.
+
+        t = se.submit(host_buckets)      # pinned host tensors: img, cloud, choose, obj per bucket
+        poses = se.result(t)             # (B,7) float64 pinned host tensor, valid until the slot is reused"""
+
+    def __init__(self, est: PoseEstimator, shapes: Sequence[Tuple[int, int, int]], slots: int = 2):
+        self.est = est
+        dev = est.device
+        self.slots = [GraphedBuckets(est, shapes) for _ in range(slots)]
+        total = sum(s[0] for s in shapes)
+        self.host_out = [torch.empty(total, 7, dtype=torch.float64).pin_memory() for _ in range(slots)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.loaded = [torch.cuda.Event() for _ in range(slots)]      # inputs of the slot are on the device
+        self.consumed = [torch.cuda.Event() for _ in range(slots)]    # the slot's graph has read its inputs (= finished)
+        self.done = [torch.cuda.Event() for _ in range(slots)]        # poses of the slot are in host memory
+        self.count = 0
+        main = torch.cuda.current_stream(dev)
+        for e in self.consumed:
+            e.record(main)
+
+    def submit(self, host_buckets: Sequence[dict]) -> int:
+        k = self.count % len(self.slots)
+        main = torch.cuda.current_stream(self.est.device)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[k])             # the previous tenant of this slot is finished
+            self.slots[k].load(host_buckets)
+            self.loaded[k].record(self.copy_stream)
+        main.wait_event(self.loaded[k])
+        out = self.slots[k].run()
+        self.consumed[k].record(main)
+        self.host_out[k].copy_(out, non_blocking=True)
+        self.done[k].record(main)
+        self.count += 1
+        return self.count - 1
+
+    def result(self, ticket: int) -> torch.Tensor:
+        k = ticket % len(self.slots)
+        self.done[k].synchronize()
+        return self.host_out[k]

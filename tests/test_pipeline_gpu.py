@@ -100,3 +100,34 @@ def test_batched_buckets_graph_and_oracle():
     assert np.array_equal(out, poses)
     out2 = graphed.run().cpu().numpy()
     assert np.array_equal(out2, poses)
+
+
+def test_streaming_estimator_equals_direct_calls():
+    """Double-buffered serving loop (H2D of batch i+1 overlapping the compute of batch i) returns, for every batch,
+    exactly the poses of a direct estimate_buckets call."""
+    import torch
+    from densefusion_b200.pipeline import PoseEstimator, StreamingEstimator
+    est, ref, _, _ = build_nets(500, 21, seed=0)
+    pipe = PoseEstimator(est, ref, iterations=2, precision="3xtf32")
+    shapes = [(2, 80, 80), (1, 120, 120)]
+
+    def host_batch(seed):
+        g = torch.Generator().manual_seed(seed)
+        out = []
+        for b, h, w in shapes:
+            out.append({"img": torch.randn(b, 3, h, w, generator=g).pin_memory(),
+                        "cloud": (torch.randn(b, 500, 3, generator=g) * 0.05 + torch.tensor([0.0, 0.0, 0.8])).pin_memory(),
+                        "choose": torch.stack([torch.sort(torch.randperm(h * w, generator=g)[:500])[0] for _ in range(b)]).view(b, 1, 500).pin_memory(),
+                        "obj": torch.randint(0, 21, (b,), generator=g).pin_memory()})
+        return out
+    batches = [host_batch(s) for s in range(5)]
+    want = [pipe.estimate_buckets([{k: v.cuda() for k, v in bk.items()} for bk in hb]).cpu().clone() for hb in batches]
+    se = StreamingEstimator(pipe, shapes)
+    tickets = [se.submit(hb) for hb in batches[:2]]
+    got = []
+    for i in range(len(batches)):
+        got.append(se.result(tickets[i]).clone())
+        if i + 2 < len(batches):
+            tickets.append(se.submit(batches[i + 2]))
+    for g_, w_ in zip(got, want):
+        assert torch.allclose(g_, w_, atol=1e-12, rtol=0), float((g_ - w_).abs().max())
