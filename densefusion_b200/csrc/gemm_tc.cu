@@ -673,7 +673,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (warp == 0) {
         // ------------------------------- TMA producer -------------------------------
         const uint32_t a_bytes = p.conv_taps ? (uint32_t)(p.TW * p.TH * p.TB) * BK * 4 : (uint32_t)Q_TILE;
-        const uint32_t bytes = a_bytes + (p.precise ? 2u : 1u) * w_bytes;
+        const uint32_t bytes = a_bytes + (p.precise ? 2u : 1u) * w_bytes;      // 3xTF32: W_hi + W_lo; hybrid: W_hi + bf16 pair tile
         const int cblocks = p.conv_taps ? p.K / (BK * p.conv_taps) : 1;        // 32-channel blocks per tap
         uint32_t it = 0;
         for (int t = cid; t < total_tiles; t += ncl) {
@@ -695,7 +695,8 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         tma_load_2d(&tm_a, dst, full + s, acol + kb * BK, c.row0);
                     }
                     tma_load_2d(&tm_whi, dst + Q_TILE, full + s, kb * BK, wrow);
-                    if (p.precise) tma_load_2d(&tm_wlo, dst + 2 * Q_TILE, full + s, kb * BK, wrow);
+                    // second weight tile: W_lo (fp32, 32 floats per row) or, hybrid, [bf16(W) x32 | bf16(W_lo) x32] = 64 bf16 per row
+                    if (p.precise) tma_load_2d(&tm_wlo, dst + 2 * Q_TILE, full + s, kb * (p.precise == 2 ? 2 * BK : BK), wrow);
                 }
                 __syncwarp();
             }
@@ -704,6 +705,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // ------------------------------- MMA issuer (leader CTA) --------------------
         if (rank == 0) {
             const uint32_t idesc = tf32_instr_desc(bnt, 128 * CTAS);
+            const uint32_t idesc_bf = bf16_instr_desc(bnt, 128 * CTAS);
             uint32_t it = 0, ti = 0;
             for (int t = cid; t < total_tiles; t += ncl) {
               for (int kc = 0; kc < p.k_chunks; ++kc, ++ti) {
@@ -729,10 +731,27 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             const uint32_t acc_on = (kb != kb0) || (ks != 0);
                             if (CTAS == 2) {
                                 umma_ts_pair(acc, a_hi, bhi, idesc, acc_on);
-                                if (p.precise) { umma_ts_pair(acc, a_hi + BK, bhi, idesc, 1u); umma_ts_pair(acc, a_hi, blo, idesc, 1u); }
+                                if (p.precise == 1) { umma_ts_pair(acc, a_hi + BK, bhi, idesc, 1u); umma_ts_pair(acc, a_hi, blo, idesc, 1u); }
                             } else {
                                 umma_ts(acc, a_hi, bhi, idesc, acc_on);
-                                if (p.precise) { umma_ts(acc, a_hi + BK, bhi, idesc, 1u); umma_ts(acc, a_hi, blo, idesc, 1u); }
+                                if (p.precise == 1) { umma_ts(acc, a_hi + BK, bhi, idesc, 1u); umma_ts(acc, a_hi, blo, idesc, 1u); }
+                            }
+                        }
+                        if (p.precise == 2) {
+                            // hybrid: the two correction terms are ~2^-11 of the main one, so bf16 operands (K = 16 per
+                            // instruction, twice the TF32 rate) keep them to 2^-20 of the result: 4 + 4 instructions per
+                            // k-block instead of 12.  TMEM A stage: [0,32) tf32 hi | [32,48) bf16(a) pairs | [48,64) bf16(a_lo);
+                            // weight tile rows: 64 B of bf16(w) then 64 B of bf16(w_lo) (descriptor +4 = +64 B).
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const uint64_t b_w = blo0 + (uint64_t)(j * 2), b_wlo = blo0 + (uint64_t)(4 + j * 2);
+                                if (CTAS == 2) {
+                                    umma_ts_bf16_pair(acc, a0 + 48 + j * 8, b_w, idesc_bf, 1u);
+                                    umma_ts_bf16_pair(acc, a0 + 32 + j * 8, b_wlo, idesc_bf, 1u);
+                                } else {
+                                    umma_ts_bf16(acc, a0 + 48 + j * 8, b_w, idesc_bf, 1u);
+                                    umma_ts_bf16(acc, a0 + 32 + j * 8, b_wlo, idesc_bf, 1u);
+                                }
                             }
                         }
                         if (CTAS == 2) {
@@ -783,7 +802,19 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             tc_fence_after();
             const uint32_t ta = tmem_base + lane_base + TMEM_A0 + (it % A_STAGES) * 2 * BK;
             tmem_st32(ta, hi);
-            if (p.precise) tmem_st32(ta + BK, lo);
+            if (p.precise == 1) tmem_st32(ta + BK, lo);
+            else if (p.precise == 2) {
+                // (the raw value is hi | low 13 bits, i.e. hi + lo exactly)
+                uint32_t pk[32];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float x0 = __uint_as_float(hi[2 * j]) + __uint_as_float(lo[2 * j]);
+                    const float x1 = __uint_as_float(hi[2 * j + 1]) + __uint_as_float(lo[2 * j + 1]);
+                    pk[j] = pack_bf16x2(x0, x1);
+                    pk[16 + j] = pack_bf16x2(__uint_as_float(lo[2 * j]), __uint_as_float(lo[2 * j + 1]));
+                }
+                tmem_st32(ta + BK, pk);
+            }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -1008,6 +1039,20 @@ int launch_persistent(const CUtensorMap& mhi, const CUtensorMap& mlo, const TcPa
 
 bool use_pdl();
 
+// hybrid mode: per weight row and 32-wide k-block 64 bf16 = [bf16(w) x32 | bf16(w - tf32_trunc(w)) x32]; row pitch 2K bf16
+bool make_map_bf16_pairs(CUtensorMap* map, const void* base, long long rows, int K, int box_rows)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)2 * K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // NHWC image (B, H, W, C) with pixel pitch `ld` floats as a 4-D tensor; box = 32 channels x TW x TH x TB pixels
 bool make_map_nhwc(CUtensorMap* map, const float* base, int B, int H, int W, int C, int ld, int TW, int TH, int TB)
 {
@@ -1093,7 +1138,10 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
     } else if (!make_map(&ma, p.A, p.M, (int)a_cols, p.lda, 128)) return DF_ERR_UNSUPPORTED;
     const long long wrows = (long long)groups * p.N;
     if (!make_map(&mhi, W_hi, wrows, p.K, ldw, bn_cta)) return DF_ERR_UNSUPPORTED;
-    if (!make_map(&mlo, p.precise ? W_lo : W_hi, wrows, p.K, ldw, bn_cta)) return DF_ERR_UNSUPPORTED;
+    if (p.precise == 2) {
+        if (ldw != p.K) return DF_ERR_UNSUPPORTED;                 // the packed pair tensor has the dense row pitch
+        if (!make_map_bf16_pairs(&mlo, W_lo, wrows, p.K, bn_cta)) return DF_ERR_UNSUPPORTED;
+    } else if (!make_map(&mlo, p.precise ? W_lo : W_hi, wrows, p.K, ldw, bn_cta)) return DF_ERR_UNSUPPORTED;
     const int n_tiles = (p.N + bnt - 1) / bnt;
     const int total = m_tiles * n_tiles * groups;
     const int clusters = total < max_clusters ? total : max_clusters;
@@ -1142,7 +1190,32 @@ int default_variant()
     return v;
 }
 
+__global__ void pack_bf16_pairs_kernel(const float* __restrict__ w, uint32_t* __restrict__ out, long long rows, int K)
+{
+    // one thread per (row, k-block, pair j): writes bf16x2 of w[2j], w[2j+1] and of their low parts
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = rows * (K / 2);
+    if (i >= total) return;
+    const long long row = i / (K / 2);
+    const int kp = (int)(i - row * (K / 2));
+    const int kb = kp / 16, j = kp - kb * 16;
+    const float x0 = w[row * K + kb * 32 + 2 * j], x1 = w[row * K + kb * 32 + 2 * j + 1];
+    const float l0 = x0 - __uint_as_float(__float_as_uint(x0) & 0xffffe000u);
+    const float l1 = x1 - __uint_as_float(__float_as_uint(x1) & 0xffffe000u);
+    uint32_t* o = out + row * K + kb * 32;                       // 64 bf16 = 32 words per k-block
+    o[j] = pack_bf16x2(x0, x1);
+    o[16 + j] = pack_bf16x2(l0, l1);
+}
+
 }  // namespace
+
+extern "C" int df_pack_bf16_pairs(const float* w, void* out, long long rows, int K, void* stream)
+{
+    if (!w || !out || rows <= 0 || K <= 0 || K % 32) return DF_ERR_ARG;
+    const long long total = rows * (K / 2);
+    pack_bf16_pairs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, (uint32_t*)out, rows, K);
+    DF_RETURN_LAST_ERROR();
+}
 
 extern "C" int df_split_tf32(const float* x, float* hi, float* lo, long long n, void* stream)
 {
@@ -1157,8 +1230,8 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
                           long long c_group_stride, float* pool_partial, int precision, int variant, void* stream)
 {
     if (!A || !W_hi || (!C && !pool_partial)) return DF_ERR_ARG;
-    if (precision != 1 && precision != 2) return DF_ERR_ARG;
-    if (precision == 1 && !W_lo) return DF_ERR_ARG;
+    if (precision < 1 || precision > 3) return DF_ERR_ARG;
+    if (precision != 2 && !W_lo) return DF_ERR_ARG;
     if (M <= 0 || N <= 0 || K <= 0 || groups <= 0) return DF_ERR_ARG;
     if (K % BK || lda % 4 || ldw % 4 || N % 4 || a_group_stride % 4 || bias_group_stride % 4) return DF_ERR_ARG;
     if (((uintptr_t)A & 15) || ((uintptr_t)W_hi & 15) || ((uintptr_t)W_lo & 15)) return DF_ERR_ARG;
@@ -1170,7 +1243,7 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
     TcParams p = {};
     p.A = A; p.lda = lda; p.bias = bias; p.bias_crop_stride = bias_crop_stride;
     p.C = pool_partial ? nullptr : C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.relu = relu;
-    p.precise = precision == 1;
+    p.precise = precision == 1 ? 1 : (precision == 3 ? 2 : 0);     // kernel-side: 0 single TF32, 1 3xTF32, 2 hybrid
     p.rows_per_crop = rows_per_crop > 0 ? rows_per_crop : M;
     p.a_gs = a_group_stride; p.bias_gs = bias_group_stride; p.c_gs = c_group_stride;
     p.pool_partial = pool_partial;
@@ -1191,6 +1264,7 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
         }
         v = 4;                                   // auto mode: shapes the TMA-A form cannot address fall back to kernel 4
     }
+    if (precision == 3) return DF_ERR_UNSUPPORTED;       // the hybrid mode exists in the generation-2 kernels only
     const int bn = v == 2 ? 256 : 128;
     if (v == 2 && groups > 1 && N % 256) return DF_ERR_UNSUPPORTED;
     CUtensorMap mhi, mlo;
@@ -1215,8 +1289,8 @@ extern "C" int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx,
                           int act, float* Y, int ldy, int Cout, int precision, void* stream)
 {
     if (!X || !W_hi || !Y || B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return DF_ERR_ARG;
-    if (precision != 1 && precision != 2) return DF_ERR_ARG;
-    if (precision == 1 && !W_lo) return DF_ERR_ARG;
+    if (precision < 1 || precision > 3) return DF_ERR_ARG;
+    if (precision != 2 && !W_lo) return DF_ERR_ARG;
     if ((taps != 1 && taps != 9) || dilation < 1 || act < 0 || act > 2 || (act == 2 && !prelu)) return DF_ERR_ARG;
     if (Cin % BK || Cout % 4 || ldx % 4 || ldy % 4 || ldx < Cin || ldy < Cout || (residual && (ldr % 4 || ldr < Cout))) return DF_ERR_ARG;
     if (((uintptr_t)X & 15) || ((uintptr_t)Y & 15) || ((uintptr_t)W_hi & 15) || ((uintptr_t)W_lo & 15) ||
@@ -1226,7 +1300,8 @@ extern "C" int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx,
 
     TcParams p = {};
     p.A = X; p.lda = ldx; p.bias = bias; p.bias_crop_stride = 0; p.C = Y; p.ldc = ldy;
-    p.M = B * H * W; p.N = Cout; p.K = taps * Cin; p.relu = act; p.precise = precision == 1;
+    p.M = B * H * W; p.N = Cout; p.K = taps * Cin; p.relu = act;
+    p.precise = precision == 1 ? 1 : (precision == 3 ? 2 : 0);
     p.rows_per_crop = p.M; p.a_gs = 0; p.bias_gs = 0; p.c_gs = 0; p.pool_partial = nullptr; p.tiles_per_crop = 0;
     p.conv_taps = taps; p.conv_dil = dilation; p.cW = W; p.cH = H; p.cB = B;
     p.residual = residual; p.ldr = ldr; p.prelu = prelu;

@@ -193,4 +193,30 @@ __device__ __forceinline__ void umma_ts_pair(uint32_t d, uint32_t a_tmem, uint64
                  ::"r"(d), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
 
+// bf16 forms (kind::f16, K = 16 per instruction) for the cheap correction terms of the hybrid precision mode
+__device__ __forceinline__ void umma_ts_bf16(uint32_t d, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_ts_bf16_pair(uint32_t d, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ uint32_t bf16_instr_desc(int n, int m = 128)
+{
+    // c_format F32 (1) @4, a/b format BF16 (1) @7/@10, K-major both, N>>3 @17, M>>4 @24
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// two fp32 -> packed bf16x2 (round to nearest even): `lo` in bits 0-15 (the lower k index), `hi` in bits 16-31
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
+{
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 }  // namespace df_tc

@@ -11,7 +11,9 @@ import torch
 from . import _C
 from ._C import check, f32c, i64c, lib, need_cuda, ptr, stream
 
-PRECISIONS = {"fp32": 0, "3xtf32": 1, "tf32": 2}
+# "hybrid": TF32 main term + the two ~2^-11 correction terms in bf16 (8 instead of 12 MMAs per k-block), fp32-parity like
+# "3xtf32"; generation-2 tensor-core kernels only
+PRECISIONS = {"fp32": 0, "3xtf32": 1, "tf32": 2, "hybrid": 3}
 
 
 def sym_mask(sym_list: Iterable[int]) -> int:
@@ -114,11 +116,21 @@ def loss_backward(pred_r, pred_c, st: LossState, g_loss, g_dis, w: float):
 # ---- K1 / K2 building blocks ------------------------------------------------------------------
 class SplitWeight:
     """A torch (N,K) [or stacked (G,N,K)] weight with its TF32 hi/lo halves for the tensor-core path."""
-    __slots__ = ("w", "hi", "lo")
+    __slots__ = ("w", "hi", "lo", "bf")
 
     def __init__(self, w: torch.Tensor):
         self.w = f32c(w.detach())
-        self.hi = self.lo = None
+        self.hi = self.lo = self.bf = None
+
+    def pairs(self):
+        """hi (TF32-exact fp32) and the packed bf16 pair tensor of the hybrid mode (same byte size as the weight)."""
+        hi, _ = self.split()
+        if self.bf is None:
+            K = self.w.shape[-1]
+            rows = self.w.numel() // K
+            self.bf = torch.empty(rows, K, device=self.w.device, dtype=torch.float32)     # 2K bf16 per row
+            check(lib.df_pack_bf16_pairs(ptr(self.w), ptr(self.bf), rows, K, stream()), "df_pack_bf16_pairs")
+        return hi, self.bf
 
     def split(self):
         if self.hi is None:
@@ -143,7 +155,7 @@ def gemm(A, W, bias, C, *, M, N, K, lda, ldw, ldc, relu, precision="fp32", bias_
     mode = PRECISIONS[precision]
     sw = W if isinstance(W, SplitWeight) else None
     if mode != 0 and sw is not None and tc_eligible(M, N, K) and (groups == 1 or w_gs == N * ldw):
-        hi, lo = sw.split()
+        hi, lo = sw.pairs() if mode == 3 else sw.split()
         st = lib.df_gemm_tc(ptr(A), lda, ptr(hi), ptr(lo), ldw, ptr(bias), bias_crop_stride, ptr(C), ldc, M, N, K,
                             1 if relu else 0, rows_per_crop, groups, a_gs, bias_gs, c_gs, ptr(pool_partial), mode,
                             TC_VARIANT, stream())

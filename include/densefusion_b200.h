@@ -95,6 +95,11 @@ int df_gemm_tc(const float* A, int lda, const float* W_hi, const float* W_lo, in
                int groups, long long a_group_stride, long long bias_group_stride, long long c_group_stride,
                float* pool_partial, int precision, int variant, void* stream);
 int df_split_tf32(const float* x, float* hi, float* lo, long long n, void* stream);
+/* precision 3 ("hybrid", generation-2 kernels / df_conv_tc only): D += A_hi W_hi in TF32 plus the two correction terms
+ * A_lo W and A W_lo in bf16 (operands ~2^-11 of the main term, so 8 mantissa bits keep them to 2^-20 of the result) --
+ * 8 MMA instructions per 32-wide k-block instead of 12, same fp32-parity bound.  W_lo then points to the packed pair
+ * tensor made by df_pack_bf16_pairs: per row and k-block 64 bf16 = [bf16(w) x32 | bf16(w - tf32(w)) x32]; needs ldw == K. */
+int df_pack_bf16_pairs(const float* w, void* out, long long rows, int K, void* stream);
 
 /* emb[b,c,n] = feat[b,c,choose[b,n]]  (lib/network.py:98-102).  feat is addressed with explicit element
  * strides so NCHW and channels-last encoders both work.  emb_pm (B*N,32) point-major and/or emb_cm

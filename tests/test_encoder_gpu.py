@@ -43,14 +43,14 @@ def test_conv_tc_vs_float64(B, H, W, Cin, Cout, taps, dil, extras):
         want = torch.relu(want)
     elif extras == "prelu":
         want = torch.where(want > 0, want, 0.25 * want)
-    for precision, tol in (("3xtf32", 2e-5), ("tf32", 3e-3)):
+    for precision, tol in (("3xtf32", 2e-5), ("hybrid", 2e-5), ("tf32", 3e-3)):
         wide = torch.full((B, H, W, Cout + 64), 7.0, device="cuda")          # output is a channel slice of a wider buffer
         out = wide[..., 32:32 + Cout]
         PackedEncoder._conv(_nhwc(x).cuda(), _pack_conv(w.cuda()), out, taps=taps, dil=dil,
                             bias=None if bias is None else bias.cuda(), residual=None if res is None else _nhwc(res).cuda(),
                             prelu=slope.cuda() if extras == "prelu" else None,
                             act={"relu": 1, "residual": 1, "prelu": 2, "none": 0}[extras],
-                            mode={"3xtf32": 1, "tf32": 2}[precision])
+                            mode={"3xtf32": 1, "tf32": 2, "hybrid": 3}[precision])
         torch.cuda.synchronize()
         err = rel(out.permute(0, 3, 1, 2), want)
         print(f"conv {taps}tap dil{dil} {Cin}->{Cout} {H}x{W}x{B} {precision}: {err:.3e}")
@@ -100,7 +100,7 @@ def test_encoder_helper_kernels_vs_torch():
     assert rel(z, want) < 1e-6
 
 
-@pytest.mark.parametrize("precision,tol", [("3xtf32", 1e-4), ("tf32", 2e-2)])
+@pytest.mark.parametrize("precision,tol", [("3xtf32", 1e-4), ("hybrid", 1e-4), ("tf32", 2e-2)])
 @pytest.mark.parametrize("b,hw", [(3, (80, 80)), (2, (120, 160)), (1, (160, 160))])
 def test_encoder_vs_oracle(precision, tol, b, hw):
     from densefusion_b200.encoder import PackedEncoder
@@ -143,17 +143,19 @@ def test_encoder_sparse_tail_equals_dense_gather(b, hw):
     assert err < 1e-5 and err_o < 1e-4
 
 
-def test_pipeline_with_tensor_core_encoder_vs_oracle():
-    """estimate + 2 refine iterations with encoder AND head on the tensor cores (3xTF32) against the oracle's eval loop."""
+@pytest.mark.parametrize("precision", ["3xtf32", "hybrid"])
+def test_pipeline_with_tensor_core_encoder_vs_oracle(precision):
+    """estimate + 2 refine iterations with encoder AND head on the tensor cores (fp32-parity modes) against the oracle's
+    eval loop."""
     import numpy as np
     from densefusion_b200.pipeline import PoseEstimator
     est, ref, est_sd, ref_sd = build_nets(500, 21, seed=0)
     d = synth.synth_crop(7, 500, 500, 21, (80, 80), obj=12)
     dc = {k: v.cuda() for k, v in d.items()}
-    pipe = PoseEstimator(est, ref, iterations=2, precision="3xtf32")
+    pipe = PoseEstimator(est, ref, iterations=2, precision=precision)
     assert pipe.encoder == "tc"
     pose = pipe.estimate(dc["img"], dc["points"], dc["choose"], dc["idx"]).cpu().numpy()[0]
     want = O.estimate_and_refine(est_sd, ref_sd, d["img"], d["points"], d["choose"], d["idx"], 21, 2)
     err = float(np.max(np.abs(pose - want)) / np.max(np.abs(want)))
-    print(f"pose err with tensor-core encoder: {err:.3e}")
+    print(f"pose err with tensor-core encoder ({precision}): {err:.3e}")
     assert err < 1e-4
