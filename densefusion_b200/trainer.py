@@ -78,6 +78,12 @@ class FlatArena:
                                    float(lr), float(betas[0]), float(betas[1]), float(eps), ptr(self.step_dev), stream()),
               "df_adam_step_dev")
 
+    def reset_optimizer(self) -> None:
+        """A fresh Adam: moments and step count back to zero (the reference builds a new optimiser on every schedule switch)."""
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self.step_dev.zero_()
+
     def state(self) -> dict:
         return {k: getattr(self, k).clone() for k in ("param", "exp_avg", "exp_avg_sq", "step_dev")}
 
@@ -117,6 +123,10 @@ class DataParallelTrainer:
             self.refiner.requires_grad_(True)
             if self.arena_ref is None:
                 self.arena_ref = FlatArena(self.refiner.parameters())
+
+    def reset_optimizer(self) -> None:
+        arena = self.arena_est if self.phase == "estimator" else self.arena_ref
+        arena.reset_optimizer()
 
     # ---- local forward / backward (gradients land in the arena) ----
     def _local_estimator(self, buckets):
