@@ -129,8 +129,26 @@ class PoseNet(nn.Module, _PackedMixin):
                                   out_r, out_t, out_c, self.precision)
         return out_r, out_t, out_c
 
+    def _embedding_tc(self, img, choose):
+        """Inference with a tensor-core precision: the hand-written encoder (densefusion_b200.encoder), embedding
+        evaluated at the chosen pixels only.  Returns point-major (B*N,32) and the reference's (B,32,N) layout."""
+        from ..encoder import PackedEncoder
+        ver = engine.param_version(self.cnn)
+        if getattr(self, "_enc_ver", None) != ver:
+            self._enc, self._enc_ver = PackedEncoder(self.cnn), ver
+        B = img.shape[0]
+        choose = ops.i64c(choose).view(B, -1)
+        pm = torch.empty(B * choose.shape[1], 32, device=img.device, dtype=torch.float32)
+        self._enc.forward_points(img, choose, pm, self.precision)
+        return pm, pm.view(B, -1, 32).permute(0, 2, 1).contiguous()
+
     def forward_batched(self, img, x, choose, obj):
         """All crops: (B,N,4), (B,N,3), (B,N,1), emb (B,32,N) detached."""
+        if self.precision != "fp32" and img.is_cuda and not _needs_grad(self, img, x) and img.shape[2] % 8 == 0 \
+                and img.shape[3] % 8 == 0:
+            emb_pm, emb_cm = self._embedding_tc(img, choose)
+            r, t, c = self.head(x, emb_pm, obj)
+            return r, t, c, emb_cm
         out_img = self.cnn(img)
         if _needs_grad(self, img, x):
             if x.shape[1] != self.num_points:

@@ -99,13 +99,17 @@ class DataParallelTrainer:
         img (b,3,H,W), points (b,N,3), choose (b,1,N), idx (b,1)|(b,), target (b,M,3), model_points (b,M,3)."""
 
     def __init__(self, estimator, refiner, num_points_mesh: int, sym_list: Sequence[int], lr: float = 1e-4,
-                 w: float = 0.015, iteration: int = 2, phase: str = "estimator", group=None):
+                 w: float = 0.015, iteration: int = 2, phase: str = "estimator", group=None,
+                 frozen_precision: str = "hybrid"):
         from .lib.loss import Loss
         from .lib.loss_refiner import Loss_refine
         self.estimator, self.refiner = estimator, refiner
         self.criterion = Loss(num_points_mesh, sym_list)
         self.criterion_refine = Loss_refine(num_points_mesh, sym_list)
         self.lr, self.w, self.iteration, self.group = float(lr), float(w), int(iteration), group
+        # arithmetic of the FROZEN estimator in the refiner phase (no gradient flows through it, tools/train.py:93):
+        # an fp32-parity tensor-core mode runs its encoder + head 4-5x faster than the exact-fp32 / cuDNN path
+        self.frozen_precision = frozen_precision
         self.arena_est: Optional[FlatArena] = None
         self.arena_ref: Optional[FlatArena] = None
         self.set_phase(phase)
@@ -116,10 +120,12 @@ class DataParallelTrainer:
         self.phase = phase
         if phase == "estimator":
             self.estimator.requires_grad_(True)
+            self.estimator.precision = "fp32"
             if self.arena_est is None:
                 self.arena_est = FlatArena(self.estimator.parameters())
         else:
             self.estimator.requires_grad_(False)        # tools/train.py:93,228: only the refiner is optimised
+            self.estimator.precision = self.frozen_precision
             self.refiner.requires_grad_(True)
             if self.arena_ref is None:
                 self.arena_ref = FlatArena(self.refiner.parameters())
