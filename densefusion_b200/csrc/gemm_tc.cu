@@ -783,17 +783,29 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             // that is implied by full[s] (the commit that frees the slot is what let the TMA refill the stage); with
             // fewer TMEM slots wait for that iteration's commit explicitly (same barrier the TMA producer watches).
             const uint8_t* arow = smem + (size_t)s * Q_STAGE_BYTES + r * 128;
-            uint32_t hi[32], lo[32];
+            // hi: TF32-exact part (raw value in single-pass mode); second[]: what goes into columns [32,64) of the TMEM stage --
+            // lo (3xTF32), or 16 words of bf16(x) pairs followed by 16 words of bf16(lo) pairs (hybrid)
+            uint32_t hi[32], second[32];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const uint4 v = *reinterpret_cast<const uint4*>(arow + ((c ^ sw) << 4));
                 hi[c * 4 + 0] = v.x; hi[c * 4 + 1] = v.y; hi[c * 4 + 2] = v.z; hi[c * 4 + 3] = v.w;
             }
+            if (p.precise == 2) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const uint32_t raw = hi[i];
-                hi[i] = p.precise ? (raw & 0xffffe000u) : raw;
-                lo[i] = __float_as_uint(__uint_as_float(raw) - __uint_as_float(hi[i]));
+                for (int j = 0; j < 16; ++j) {
+                    const float x0 = __uint_as_float(hi[2 * j]), x1 = __uint_as_float(hi[2 * j + 1]);
+                    hi[2 * j] &= 0xffffe000u; hi[2 * j + 1] &= 0xffffe000u;
+                    second[j] = pack_bf16x2(x0, x1);
+                    second[16 + j] = pack_bf16x2(x0 - __uint_as_float(hi[2 * j]), x1 - __uint_as_float(hi[2 * j + 1]));
+                }
+            } else if (p.precise == 1) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float x = __uint_as_float(hi[i]);
+                    hi[i] &= 0xffffe000u;
+                    second[i] = __float_as_uint(x - __uint_as_float(hi[i]));
+                }
             }
             if (A_STAGES < Q_STAGES && it >= (uint32_t)A_STAGES) {      // (the loads and the split above overlap this wait)
                 const uint32_t prev = it - A_STAGES;
@@ -802,19 +814,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             tc_fence_after();
             const uint32_t ta = tmem_base + lane_base + TMEM_A0 + (it % A_STAGES) * 2 * BK;
             tmem_st32(ta, hi);
-            if (p.precise == 1) tmem_st32(ta + BK, lo);
-            else if (p.precise == 2) {
-                // (the raw value is hi | low 13 bits, i.e. hi + lo exactly)
-                uint32_t pk[32];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float x0 = __uint_as_float(hi[2 * j]) + __uint_as_float(lo[2 * j]);
-                    const float x1 = __uint_as_float(hi[2 * j + 1]) + __uint_as_float(lo[2 * j + 1]);
-                    pk[j] = pack_bf16x2(x0, x1);
-                    pk[16 + j] = pack_bf16x2(__uint_as_float(lo[2 * j]), __uint_as_float(lo[2 * j + 1]));
-                }
-                tmem_st32(ta + BK, pk);
-            }
+            if (p.precise) tmem_st32(ta + BK, second);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
