@@ -49,6 +49,7 @@ SIGNATURES = {
     "df_enc_upsample": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "df_enc_log_softmax32": [_p, _ll, _p],
     "df_enc_gather_up_patches": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "df_build_crops": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, ctypes.c_uint, _p, _p, _p, _p, _p],
     "df_upsample_bilinear": [_p, _p, _ll, _i, _i, _i, _i, _i, _p],
     "df_gather_embedding": [_p, _p, _p, _p, _ll, _ll, _ll, _i, _i, _i, _p],
     "df_xyz_conv": [_p, _p, _p, _p, _i, _ll, _p],

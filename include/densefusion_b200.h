@@ -178,6 +178,15 @@ int df_enc_log_softmax32(float* x, long long pixels, void* stream);
 int df_enc_gather_up_patches(const float* in, const int64_t* choose, float* A, int B, int N, int h, int w, int C,
                              void* stream);
 
+/* ---- input preparation on the device (tools/eval_ycb.py:147-190) ---------------------
+ * One bucket of b objects whose snapped boxes share the size (h,w).  rgb (F,H,W,3) uint8, depth (F,H,W) fp32 (raw sensor
+ * units), label (F,H,W) int32, meta (b,6) int32 = frame, item id, rmin, rmax, cmin, cmax (host arrays; cam / mean_std are
+ * HOST pointers: cx cy fx fy scale / mean[3] std[3]).  Outputs: img (b,3,h,w) normalised, choose (b,N) int64 indices into
+ * the box, cloud (b,N,3), count (b) = masked pixels found (0: object lost, outputs zero). */
+int df_build_crops(const uint8_t* rgb, const float* depth, const int* label, const int* meta, int b, int H, int W, int h, int w,
+                   int N, const float* cam, const float* mean_std, unsigned seed, float* out_img, int64_t* out_choose,
+                   float* out_cloud, int* out_count, void* stream);
+
 /* ---- encoder helper -----------------------------------------------------------------------------
  * NCHW bilinear up-sampling (lib/pspnet.py:20-23 F.upsample(size=...), :30-34 nn.Upsample(scale_factor=2,
  * align_corners=True)): in (planes, hin, win) -> out (planes, hout, wout), planes = batch*channels. */

@@ -30,6 +30,7 @@ Restated functions (reference file:line):
   select_pose / refine_pose_eval   tools/eval_ycb.py:193-233
   knn                    lib/knn/src/knn_cuda_kernel.cu:31-170 via oracle/knn_ref.c
   estimator_gradients / refiner_gradients / adam_reference   tools/train.py:143-169 (+ torch.optim.Adam)
+  crop_bbox / build_crop tools/eval_ycb.py:54-91, :147-178 (numpy, like the reference)
 """
 from __future__ import annotations
 
@@ -456,3 +457,73 @@ def adam_reference(params: dict, grads: dict, state: dict, lr=1e-4, betas=(0.9, 
         denom = (v.sqrt() / math.sqrt(1 - betas[1] ** k)).add_(eps)
         p.addcdiv_(m, denom, value=-lr / (1 - betas[0] ** k))
     return params
+
+
+# ----------------------------------------------------------------------------------------------
+# Input preparation (tools/eval_ycb.py:54-91, :147-190), numpy like the reference
+# ----------------------------------------------------------------------------------------------
+_BORDER_LIST = [-1, 40, 80, 120, 160, 200, 240, 280, 320, 360, 400, 440, 480, 520, 560, 600, 640, 680]
+
+
+def crop_bbox(roi, img_width=480, img_length=640):
+    """tools/eval_ycb.py:54-91 for one PoseCNN row."""
+    rmin, rmax = int(roi[3]) + 1, int(roi[5]) - 1
+    cmin, cmax = int(roi[2]) + 1, int(roi[4]) - 1
+    ext = []
+    for e in (rmax - rmin, cmax - cmin):
+        for tt in range(len(_BORDER_LIST) - 1):
+            if _BORDER_LIST[tt] < e < _BORDER_LIST[tt + 1]:
+                e = _BORDER_LIST[tt + 1]
+                break
+        ext.append(e)
+    center = [int((rmin + rmax) / 2), int((cmin + cmax) / 2)]
+    rmin, rmax = center[0] - int(ext[0] / 2), center[0] + int(ext[0] / 2)
+    cmin, cmax = center[1] - int(ext[1] / 2), center[1] + int(ext[1] / 2)
+    if rmin < 0:
+        rmax += -rmin
+        rmin = 0
+    if cmin < 0:
+        cmax += -cmin
+        cmin = 0
+    if rmax > img_width:
+        rmin -= rmax - img_width
+        rmax = img_width
+    if cmax > img_length:
+        cmin -= cmax - img_length
+        cmax = img_length
+    return rmin, rmax, cmin, cmax
+
+
+def build_crop(img_u8, depth, label, roi, itemid, num_points, cam=(312.9869, 241.3109, 1066.778, 1067.487, 10000.0),
+               rng=None):
+    """tools/eval_ycb.py:150-178 for one object.  img_u8 (H,W,3) uint8, depth / label (H,W).  Returns
+    (cloud (N,3) f32, choose (N,) int64, img_masked (3,h,w) f32 normalised, count).  With more than num_points masked
+    pixels the reference shuffles with the global numpy RNG; pass `rng` (np.random.RandomState) to reproduce that."""
+    import numpy.ma as ma
+    H, W = depth.shape
+    xmap = np.array([[j for _ in range(W)] for j in range(H)])
+    ymap = np.array([[i for i in range(W)] for _ in range(H)])
+    cam_cx, cam_cy, cam_fx, cam_fy, cam_scale = cam
+    rmin, rmax, cmin, cmax = crop_bbox(roi, H, W)
+    mask = ma.getmaskarray(ma.masked_equal(label, itemid)) * ma.getmaskarray(ma.masked_not_equal(depth, 0))
+    choose = mask[rmin:rmax, cmin:cmax].flatten().nonzero()[0]
+    count = len(choose)
+    if count > num_points:
+        c_mask = np.zeros(count, dtype=int)
+        c_mask[:num_points] = 1
+        (rng or np.random).shuffle(c_mask)
+        choose = choose[c_mask.nonzero()]
+    else:
+        choose = np.pad(choose, (0, num_points - count), 'wrap')
+    depth_masked = depth[rmin:rmax, cmin:cmax].flatten()[choose][:, np.newaxis].astype(np.float32)
+    xmap_masked = xmap[rmin:rmax, cmin:cmax].flatten()[choose][:, np.newaxis].astype(np.float32)
+    ymap_masked = ymap[rmin:rmax, cmin:cmax].flatten()[choose][:, np.newaxis].astype(np.float32)
+    pt2 = depth_masked / np.float32(cam_scale)
+    pt0 = (ymap_masked - np.float32(cam_cx)) * pt2 / np.float32(cam_fx)
+    pt1 = (xmap_masked - np.float32(cam_cy)) * pt2 / np.float32(cam_fy)
+    cloud = np.concatenate((pt0, pt1, pt2), axis=1).astype(np.float32)
+    img_masked = np.transpose(np.array(img_u8)[:, :, :3], (2, 0, 1))[:, rmin:rmax, cmin:cmax].astype(np.float32)
+    mean = np.array([0.485, 0.456, 0.406], dtype=np.float32).reshape(3, 1, 1)
+    std = np.array([0.229, 0.224, 0.225], dtype=np.float32).reshape(3, 1, 1)
+    img_masked = (img_masked - mean) / std                      # transforms.Normalize: sub_(mean).div_(std) in fp32
+    return cloud, choose.astype(np.int64), img_masked, count
