@@ -108,6 +108,8 @@ class PackedEncoder:
         ldx = x.stride(2) if ldx is None else ldx
         cout = out.shape[3] if cout is None else cout
         ldy = out.stride(2) if ldy is None else ldy
+        if mode == 3 and cout <= 64:
+            mode = 1        # 64-wide tiles are paced by the A stagers, where the hybrid split costs more (measured +9%)
         hi, lo = w.pairs() if mode == 3 else w.split()
         check(lib.df_conv_tc(ptr(x), b, h, wd, cin, ldx, ptr(hi), ptr(lo), taps, dil, ptr(bias), ptr(residual),
                              0 if residual is None else residual.stride(2), ptr(prelu), act, ptr(out), ldy, cout, mode,
