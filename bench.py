@@ -234,6 +234,20 @@ def dominant_kernel_roofline(pipe, precision, peaks):
             " + kind::f16 bf16 corrections" if precision == "hybrid" else "", precision)
     ach = flops / (ms * 1e-3) / 1e12
     shape = f"M={rows} N=1920 K=384"
+    # what the library reaches on this GPU in single-pass TF32 (cuBLAS, 8192^3, best of 10): a measured TF32 ceiling next to
+    # the derived one (MEASURED_PEAKS.json has no TF32 figure)
+    tf32_lib = None
+    if precision != "fp32":
+        try:
+            a = torch.randn(8192, 8192, device=ws.pf.device)
+            b = torch.randn(8192, 8192, device=ws.pf.device)
+            torch.backends.cuda.matmul.allow_tf32 = True
+            best = min(time_kernel_ms(lambda: torch.matmul(a, b), iters=1, warm=1) for _ in range(10))
+            tf32_lib = 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+        except Exception:
+            tf32_lib = None
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = False
     traffic = None
     try:
         if precision != "fp32":
@@ -244,6 +258,7 @@ def dominant_kernel_roofline(pipe, precision, peaks):
             "traffic": traffic, "ms_per_launch": ms, "algorithmic_flops_per_launch": flops,
             "frac_of_mode_ceiling": ({"3xtf32": 3.0, "hybrid": 2.0}.get(precision, 1.0) * ach / peak) if precision != "fp32" else None,
             "l2": "operands + output of one launch (596 MB at the default chunk) exceed the 126 MB L2",
+            "cublas_tf32_8192_tflops": tf32_lib, "frac_vs_cublas_tf32": (ach / tf32_lib) if tf32_lib else None,
             "executed_over_algorithmic": {"3xtf32": 3.0, "hybrid": 2.0}.get(precision, 1.0), "peak_source": peak_note,
             "shape": shape}
 

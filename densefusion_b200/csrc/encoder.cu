@@ -8,24 +8,36 @@
 
 namespace {
 
-// conv1 (7x7, stride 2, pad 3) as a GEMM: A[pixel, c*49 + ky*7 + kx] from the NCHW image, zero-padded to ldk columns
+// conv1 (7x7, stride 2, pad 3) as a GEMM: A[pixel, c*49 + ky*7 + kx] from the NCHW image, zero-padded to ldk columns.
+// One thread per (pixel, 4 consecutive k): one float4 store, the (c, ky, kx) split of k comes from a constant table.
+__constant__ uint32_t c_k147[160];          // c | ky << 8 | kx << 16, 0xffffffff for the zero padding
+
 __global__ void __launch_bounds__(256)
 im2col_conv1_kernel(const float* __restrict__ img, float* __restrict__ A, int B, int H, int W, int Ho, int Wo, int ldk)
 {
-    const unsigned total = (unsigned)B * Ho * Wo * ldk;                 // < 2^31 (checked by the launcher; no wrap in the stride loop)
+    const unsigned kq_per_pix = (unsigned)ldk >> 2;
+    const unsigned total = (unsigned)B * Ho * Wo * kq_per_pix;          // < 2^31 (checked by the launcher)
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const unsigned k = i % (unsigned)ldk;
-        const unsigned pix = i / (unsigned)ldk;
-        float v = 0.0f;
-        if (k < 147) {
-            const int c = k / 49, t = k - c * 49, ky = t / 7, kx = t - ky * 7;
-            const int xo = (int)(pix % (unsigned)Wo);
-            const unsigned r = pix / (unsigned)Wo;
-            const int yo = (int)(r % (unsigned)Ho), b = (int)(r / (unsigned)Ho);
-            const int y = yo * 2 - 3 + ky, x = xo * 2 - 3 + kx;
-            if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(img + (((size_t)b * 3 + c) * H + y) * W + x);
+        const unsigned kq = i % kq_per_pix;
+        const unsigned pix = i / kq_per_pix;
+        const int xo = (int)(pix % (unsigned)Wo);
+        const unsigned r = pix / (unsigned)Wo;
+        const int yo = (int)(r % (unsigned)Ho), b = (int)(r / (unsigned)Ho);
+        const float* base = img + (size_t)b * 3 * H * W;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const unsigned k = kq * 4 + e;
+            const uint32_t t = k < 160 ? c_k147[k] : 0xffffffffu;
+            float x = 0.0f;
+            if (t != 0xffffffffu) {
+                const int c = t & 0xff, ky = (t >> 8) & 0xff, kx = (t >> 16) & 0xff;
+                const int yy = yo * 2 - 3 + ky, xx = xo * 2 - 3 + kx;
+                if (yy >= 0 && yy < H && xx >= 0 && xx < W) x = __ldg(base + ((size_t)c * H + yy) * W + xx);
+            }
+            v[e] = x;
         }
-        A[i] = v;
+        reinterpret_cast<float4*>(A)[i] = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
 
@@ -199,10 +211,20 @@ inline unsigned grid_for(long long total, int per_block)
 
 extern "C" int df_enc_im2col_conv1(const float* img, float* A, int B, int H, int W, int ldk, void* stream)
 {
-    if (!img || !A || B <= 0 || H <= 0 || W <= 0 || ldk < 147) return DF_ERR_ARG;
+    if (!img || !A || B <= 0 || H <= 0 || W <= 0 || ldk < 147 || ldk > 160 || (ldk & 3) || ((uintptr_t)A & 15)) return DF_ERR_ARG;
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     if ((long long)B * Ho * Wo * ldk >= (1LL << 31)) return DF_ERR_ARG;
-    im2col_conv1_kernel<<<grid_for((long long)B * Ho * Wo * ldk, 256), 256, 0, (cudaStream_t)stream>>>(img, A, B, H, W, Ho, Wo, ldk);
+    static bool table_done = false;
+    if (!table_done) {
+        uint32_t t[160];
+        for (int k = 0; k < 160; ++k) {
+            const int c = k / 49, r = k - c * 49;
+            t[k] = k < 147 ? (uint32_t)(c | ((r / 7) << 8) | ((r % 7) << 16)) : 0xffffffffu;
+        }
+        if (cudaMemcpyToSymbol(c_k147, t, sizeof(t)) != cudaSuccess) return DF_ERR_UNSUPPORTED;
+        table_done = true;
+    }
+    im2col_conv1_kernel<<<grid_for((long long)B * Ho * Wo * (ldk >> 2), 256), 256, 0, (cudaStream_t)stream>>>(img, A, B, H, W, Ho, Wo, ldk);
     DF_RETURN_LAST_ERROR();
 }
 

@@ -22,6 +22,7 @@ from . import ops
 from ._C import check, lib, ptr, stream
 
 K_CONV1 = 160          # 3*7*7 = 147 padded to a multiple of 32
+_NARROW_ON_3XTF32 = __import__("os").environ.get("DF_HYBRID_NARROW", "0") != "1"
 
 
 def _pack_conv(w: torch.Tensor) -> ops.SplitWeight:
@@ -108,7 +109,7 @@ class PackedEncoder:
         ldx = x.stride(2) if ldx is None else ldx
         cout = out.shape[3] if cout is None else cout
         ldy = out.stride(2) if ldy is None else ldy
-        if mode == 3 and cout <= 64:
+        if mode == 3 and cout <= 64 and _NARROW_ON_3XTF32:
             mode = 1        # 64-wide tiles are paced by the A stagers, where the hybrid split costs more (measured +9%)
         hi, lo = w.pairs() if mode == 3 else w.split()
         check(lib.df_conv_tc(ptr(x), b, h, wd, cin, ldx, ptr(hi), ptr(lo), taps, dil, ptr(bias), ptr(residual),
