@@ -1,0 +1,82 @@
+"""Training-mode convolution of the colour encoder on the tensor cores (training side).
+
+`conv2d(module, x)` stands in for `module(x)` inside lib/pspnet.py / lib/extractors.py.  For the stride-1 3x3 / 1x1
+convolutions with a multiple of 32 input channels (all but the three stride-2 layers) on CUDA with autograd on, forward
+and the data gradient run on df_conv_tc -- the implicit-GEMM tcgen05 kernel in the fp32-parity "hybrid" arithmetic:
+    y  = conv(x, W)                  weights repacked (Cout, taps*Cin), split every call (they change every step)
+    dx = conv(dy, rot180(W)^T)       same kernel, same padding / dilation (exact for stride 1)
+The weight gradient stays on the library (aten.convolution_backward, weight only) for now -- it is the one piece of the
+encoder's training step still served by cuDNN, next to the three stride-2 layers.  Activations are channels_last, i.e.
+physically the NHWC layout the kernel wants; all other encoder ops (pooling, resizing, PReLU, log-softmax) are torch ops
+that keep that layout."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .._C import check, lib, ptr, stream
+
+ENABLED = True          # module switch (tests compare against the pure torch path)
+PRECISION = "hybrid"
+
+
+def _nhwc(x: torch.Tensor) -> torch.Tensor:
+    """(B,C,H,W) -> a channels_last tensor whose storage is NHWC-contiguous."""
+    return x if x.is_contiguous(memory_format=torch.channels_last) and x.stride(1) == 1 else x.contiguous(memory_format=torch.channels_last)
+
+
+def _launch(x, packed: ops.SplitWeight, bias, cout, taps, dil, mode):
+    b, cin, h, w = x.shape
+    y = torch.empty(b, cout, h, w, device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+    hi, lo = packed.pairs() if mode == 3 else packed.split()
+    check(lib.df_conv_tc(ptr(x), b, h, w, cin, cin, ptr(hi), ptr(lo), taps, dil, ptr(bias), None, 0, None, 0, ptr(y), cout,
+                         cout, mode, stream()), "df_conv_tc")
+    return y
+
+
+class ConvTCFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, dilation):
+        x = _nhwc(x.detach().float())
+        cout, cin, k, _ = weight.shape
+        mode = ops.PRECISIONS[PRECISION]
+        w = weight.detach().float()
+        packed = ops.SplitWeight(w.permute(0, 2, 3, 1).reshape(cout, k * k * cin))
+        y = _launch(x, packed, None if bias is None else bias.detach().float().contiguous(), cout, k * k, dilation, mode)
+        ctx.save_for_backward(x, weight)
+        ctx.dilation, ctx.has_bias, ctx.mode = dilation, bias is not None, mode
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        cout, cin, k, _ = weight.shape
+        dy = _nhwc(dy.float())
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            # data gradient = convolution of dy with the 180-degree rotated, in/out-transposed kernel
+            w = weight.detach().float()
+            rot = ops.SplitWeight(w.flip(2, 3).permute(1, 2, 3, 0).reshape(cin, k * k * cout))
+            dx = _launch(dy, rot, None, cin, k * k, ctx.dilation, ctx.mode)
+        if ctx.needs_input_grad[1]:
+            pad = ctx.dilation * (k // 2)
+            dw = torch.ops.aten.convolution_backward(dy, x, weight, None, [1, 1], [pad, pad], [ctx.dilation, ctx.dilation],
+                                                     False, [0, 0], 1, [False, True, False])[1]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(dim=(0, 2, 3))
+        return dx, dw, db, None
+
+
+def eligible(m: nn.Conv2d, x: torch.Tensor) -> bool:
+    return (ENABLED and x.is_cuda and x.dtype == torch.float32 and torch.is_grad_enabled()
+            and (x.requires_grad or m.weight.requires_grad)
+            and m.stride == (1, 1) and m.groups == 1 and m.kernel_size in ((1, 1), (3, 3))
+            and m.in_channels % 32 == 0 and m.out_channels % 32 == 0
+            and m.padding == (m.dilation[0] * (m.kernel_size[0] // 2),) * 2 and m.dilation[0] == m.dilation[1])
+
+
+def conv2d(m: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
+    if eligible(m, x):
+        return ConvTCFn.apply(x, m.weight, m.bias, m.dilation[0])
+    return m(x)

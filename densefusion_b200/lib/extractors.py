@@ -11,6 +11,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .conv_tc import conv2d
+
 
 class ResidualPair(nn.Module):
     """Two 3x3 convolutions with an identity or 1x1-projected skip (no normalisation layers)."""
@@ -22,8 +24,9 @@ class ResidualPair(nn.Module):
         self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride=stride, bias=False)) if project else None
 
     def forward(self, x):
-        skip = x if self.downsample is None else self.downsample(x)
-        y = self.conv2(F.relu(self.conv1(x)))
+        # conv2d(): tensor-core forward / data gradient in training, the plain module otherwise
+        skip = x if self.downsample is None else conv2d(self.downsample[0], x)
+        y = conv2d(self.conv2, F.relu(conv2d(self.conv1, x)))
         return F.relu(y + skip)
 
 
@@ -48,6 +51,9 @@ class ResNet18Trunk(nn.Module):
                 nn.init.normal_(m.weight, 0.0, math.sqrt(2.0 / fan))
 
     def forward(self, x):
+        from . import conv_tc
+        if conv_tc.ENABLED and x.is_cuda and torch.is_grad_enabled() and self.conv1.weight.requires_grad:
+            x = x.contiguous(memory_format=torch.channels_last)     # NHWC storage for the tensor-core training convolutions
         x = F.max_pool2d(F.relu(self.conv1(x)), 3, stride=2, padding=1)
         x = self.layer2(self.layer1(x))
         mid = self.layer3(x)

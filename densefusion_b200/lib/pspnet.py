@@ -7,6 +7,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import extractors
+from .conv_tc import conv2d
 
 
 class _UpsampleFn(torch.autograd.Function):
@@ -17,6 +18,15 @@ class _UpsampleFn(torch.autograd.Function):
     def forward(ctx, x, size, align_corners):
         from .. import ops
         ctx.in_shape, ctx.size, ctx.align = tuple(x.shape), (int(size[0]), int(size[1])), bool(align_corners)
+        if x.dim() == 4 and x.shape[1] % 4 == 0 and x.shape[1] > 1 and x.is_contiguous(memory_format=torch.channels_last):
+            # channels_last activations (tensor-core training path): resize in the NHWC storage, keep the layout
+            from .._C import check, lib, ptr, stream
+            b, c, h, w = x.shape
+            out = torch.empty(b, c, ctx.size[0], ctx.size[1], device=x.device, dtype=torch.float32,
+                              memory_format=torch.channels_last)
+            check(lib.df_enc_upsample(ptr(x), c, ptr(out), c, b, h, w, ctx.size[0], ctx.size[1], c, 1 if ctx.align else 0,
+                                      stream()), "df_enc_upsample")
+            return out
         return ops.upsample_bilinear(x, size, align_corners)
 
     @staticmethod
@@ -49,8 +59,8 @@ class PSPModule(nn.Module):
 
     def forward(self, feats):
         hw = feats.shape[2:]
-        pyramid = [_upsample(stage(feats), hw, False) for stage in self.stages]
-        return F.relu(self.bottleneck(torch.cat(pyramid + [feats], 1)))
+        pyramid = [_upsample(conv2d(stage[1], stage[0](feats)), hw, False) for stage in self.stages]
+        return F.relu(conv2d(self.bottleneck, torch.cat(pyramid + [feats], 1)))
 
 
 class PSPUpsample(nn.Module):
@@ -62,7 +72,7 @@ class PSPUpsample(nn.Module):
     def forward(self, x):
         # conv = [Upsample(x2, align_corners=True), Conv2d 3x3, PReLU]; indices kept for the checkpoint keys
         x = _upsample(x, (x.shape[2] * 2, x.shape[3] * 2), True)
-        return self.conv[2](self.conv[1](x))
+        return self.conv[2](conv2d(self.conv[1], x))
 
 
 class PSPNet(nn.Module):
@@ -84,4 +94,4 @@ class PSPNet(nn.Module):
         p = self.drop_1(self.psp(f))
         p = self.drop_2(self.up_1(p))
         p = self.drop_2(self.up_2(p))
-        return self.final(self.up_3(p))
+        return self.final[1](conv2d(self.final[0], self.up_3(p)))

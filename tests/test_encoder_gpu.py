@@ -159,3 +159,36 @@ def test_pipeline_with_tensor_core_encoder_vs_oracle(precision):
     err = float(np.max(np.abs(pose - want)) / np.max(np.abs(want)))
     print(f"pose err with tensor-core encoder ({precision}): {err:.3e}")
     assert err < 1e-4
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,dil,bias", [(3, 10, 10, 256, 512, 3, 4, False), (2, 20, 20, 128, 128, 3, 1, False),
+                                                       (2, 40, 40, 256, 64, 3, 1, True), (4, 10, 10, 2560, 1024, 1, 1, True),
+                                                       (2, 80, 80, 64, 32, 1, 1, True), (3, 15, 15, 256, 256, 3, 2, False)])
+def test_training_convolution_forward_and_gradients_vs_float64(B, H, W, Cin, Cout, k, dil, bias):
+    """lib.conv_tc.ConvTCFn (tensor-core forward + data gradient, library weight gradient) against float64 autograd."""
+    import torch.nn as nn
+    from densefusion_b200.lib import conv_tc
+    g = torch.Generator().manual_seed(B + H + Cin + Cout)
+    m = nn.Conv2d(Cin, Cout, k, padding=dil * (k // 2), dilation=dil, bias=bias)
+    with torch.no_grad():
+        m.weight.copy_(torch.randn(m.weight.shape, generator=g) / (Cin * k * k) ** 0.5)
+        if bias:
+            m.bias.copy_(torch.randn(Cout, generator=g))
+    x = torch.randn(B, Cin, H, W, generator=g)
+    gy = torch.randn(B, Cout, H, W, generator=g)
+    m64 = nn.Conv2d(Cin, Cout, k, padding=dil * (k // 2), dilation=dil, bias=bias).double()
+    m64.load_state_dict({kk: v.double() for kk, v in m.state_dict().items()})
+    x64 = x.double().requires_grad_(True)
+    y64 = m64(x64)
+    y64.backward(gy.double())
+    m = m.cuda()
+    torch.backends.cudnn.allow_tf32 = False
+    xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    assert conv_tc.eligible(m, xc)
+    y = conv_tc.conv2d(m, xc)
+    y.backward(gy.cuda())
+    errs = (rel(y, y64), rel(xc.grad, x64.grad), rel(m.weight.grad, m64.weight.grad))
+    print(f"conv_tc {k}x{k} dil{dil} {Cin}->{Cout} {H}x{W}x{B}: fwd {errs[0]:.2e} dx {errs[1]:.2e} dW {errs[2]:.2e}")
+    assert errs[0] < 2e-5 and errs[1] < 2e-5 and errs[2] < 2e-2          # dW: cuDNN's fp32 weight-gradient algorithms
+    if bias:
+        assert rel(m.bias.grad, m64.bias.grad) < 1e-5
