@@ -31,6 +31,7 @@ SIGNATURES = {
     "df_gemm_tc": [_p, _i, _p, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _p, _i, _i, _p],
     "df_split_tf32": [_p, _p, _p, _ll, _p],
     "df_pack_bf16_pairs": [_p, _p, _ll, _i, _p],
+    "df_pack_conv_weight": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
     "df_gemm_dgrad_fp32": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _p, _i, _p],
     "df_gemm_wgrad_fp32": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _ll, _ll, _p],
     "df_reduce_partials": [_p, _i, _ll, _p, _i, _p],
@@ -47,6 +48,7 @@ SIGNATURES = {
     "df_enc_im2col_s2": [_p, _p, _i, _i, _i, _i, _p],
     "df_enc_adaptive_avgpool": [_p, _i, _p, _i, _i, _i, _i, _i, _p],
     "df_enc_upsample": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "df_enc_upsample_backward": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "df_enc_log_softmax32": [_p, _ll, _p],
     "df_enc_gather_up_patches": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     "df_build_crops": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, ctypes.c_uint, _p, _p, _p, _p, _p],

@@ -143,6 +143,48 @@ upsample_nhwc_kernel(const float* __restrict__ in, int ldi, float* __restrict__ 
     }
 }
 
+// Backward of upsample_nhwc_kernel in gather form (deterministic, no atomics): every INPUT pixel sums the output pixels
+// whose 2x2 bilinear footprint contains it, with the forward's own index / weight arithmetic.
+__global__ void __launch_bounds__(256)
+upsample_nhwc_backward_kernel(const float* __restrict__ gout, int ldo, float* __restrict__ gin, int ldi, int B, int hin, int win,
+                              int hout, int wout, int C, float rh, float rw, int align)
+{
+    const unsigned c4 = C >> 2;
+    const unsigned total = (unsigned)B * hin * win * c4;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int cq = (int)(i % c4);
+        unsigned r = i / c4;
+        const int x = (int)(r % (unsigned)win); r /= (unsigned)win;
+        const int y = (int)(r % (unsigned)hin), b = (int)(r / (unsigned)hin);
+        // candidate output rows / columns: source coordinate within (y-1, y+1); conservative bounds, exact test inside
+        int Y0 = 0, Y1 = hout - 1, X0 = 0, X1 = wout - 1;
+        const float off = align ? 0.0f : 0.5f;           // source = r * (out + off) - off
+        if (rh > 0.f) { Y0 = max(0, (int)floorf((y - 1 + off) / rh - off) - 1); Y1 = min(hout - 1, (int)ceilf((y + 1 + off) / rh - off) + 1); }
+        if (rw > 0.f) { X0 = max(0, (int)floorf((x - 1 + off) / rw - off) - 1); X1 = min(wout - 1, (int)ceilf((x + 1 + off) / rw - off) + 1); }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int Y = Y0; Y <= Y1; ++Y) {
+            float sy = align ? rh * Y : fmaxf(rh * (Y + 0.5f) - 0.5f, 0.f);
+            const int y0 = (int)sy;
+            const int yp = y0 < hin - 1 ? 1 : 0;
+            const float ly1 = sy - y0, ly0 = 1.0f - ly1;
+            const float wy = (y0 == y ? ly0 : 0.f) + (y0 + yp == y ? ly1 : 0.f);
+            if (wy == 0.f) continue;
+            for (int X = X0; X <= X1; ++X) {
+                float sx = align ? rw * X : fmaxf(rw * (X + 0.5f) - 0.5f, 0.f);
+                const int x0 = (int)sx;
+                const int xp = x0 < win - 1 ? 1 : 0;
+                const float lx1 = sx - x0, lx0 = 1.0f - lx1;
+                const float wx = (x0 == x ? lx0 : 0.f) + (x0 + xp == x ? lx1 : 0.f);
+                if (wx == 0.f) continue;
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gout + (((size_t)b * hout + Y) * wout + X) * ldo + cq * 4));
+                const float wgt = wy * wx;
+                acc.x += wgt * g.x; acc.y += wgt * g.y; acc.z += wgt * g.z; acc.w += wgt * g.w;
+            }
+        }
+        *reinterpret_cast<float4*>(gin + (((size_t)b * hin + y) * win + x) * ldi + cq * 4) = acc;
+    }
+}
+
 // log_softmax over the 32 channels of every pixel (lib/pspnet.py:53-56), one warp per pixel, in place
 __global__ void __launch_bounds__(256)
 log_softmax32_kernel(float* __restrict__ x, long long pixels)
@@ -287,5 +329,25 @@ extern "C" int df_enc_gather_up_patches(const float* in, const int64_t* choose, 
     const float rh = H > 1 ? (float)(h - 1) / (H - 1) : 0.f, rw = W > 1 ? (float)(w - 1) / (W - 1) : 0.f;
     gather_up_patches_kernel<<<grid_for((long long)B * N * 9 * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(
         in, choose, A, B, N, h, w, C, rh, rw);
+    DF_RETURN_LAST_ERROR();
+}
+
+extern "C" int df_enc_upsample_backward(const float* gout, int ldo, float* gin, int ldi, int B, int hin, int win, int hout,
+                                        int wout, int C, int align_corners, void* stream)
+{
+    if (!gout || !gin || B <= 0 || hin <= 0 || win <= 0 || hout <= 0 || wout <= 0 || C <= 0 || (C & 3) || (ldi & 3) || (ldo & 3))
+        return DF_ERR_ARG;
+    if (((uintptr_t)gout & 15) || ((uintptr_t)gin & 15)) return DF_ERR_ARG;
+    if ((long long)B * hin * win * (C >> 2) >= (1LL << 31)) return DF_ERR_ARG;
+    float rh, rw;
+    if (align_corners) {
+        rh = hout > 1 ? (float)(hin - 1) / (hout - 1) : 0.f;
+        rw = wout > 1 ? (float)(win - 1) / (wout - 1) : 0.f;
+    } else {
+        rh = (float)hin / hout;
+        rw = (float)win / wout;
+    }
+    upsample_nhwc_backward_kernel<<<grid_for((long long)B * hin * win * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(
+        gout, ldo, gin, ldi, B, hin, win, hout, wout, C, rh, rw, align_corners);
     DF_RETURN_LAST_ERROR();
 }

@@ -1207,7 +1207,48 @@ __global__ void pack_bf16_pairs_kernel(const float* __restrict__ w, uint32_t* __
     o[16 + j] = pack_bf16x2(l0, l1);
 }
 
+// Convolution weight (Cout, Cin, taps) -> GEMM operand (rows, taps*cols) tap-major, split for the tensor-core modes, in ONE
+// pass (training repacks every step).  rotate == 0: rows = Cout, cols = Cin (forward).  rotate == 1: rows = Cin, cols = Cout,
+// taps reversed -- the 180-degree rotated, in/out-transposed kernel of the data gradient.  One thread per two k.
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo,
+                                        uint32_t* __restrict__ pairs, int Cout, int Cin, int taps, int rotate)
+{
+    const int rows = rotate ? Cin : Cout, cols = rotate ? Cout : Cin;
+    const int K = taps * cols;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)rows * (K / 2)) return;
+    const int row = (int)(i / (K / 2)), kp = (int)(i - (long long)row * (K / 2));
+    float x[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int k = kp * 2 + e, tap = k / cols, c = k - tap * cols;
+        x[e] = rotate ? w[((size_t)c * Cin + row) * taps + (taps - 1 - tap)] : w[((size_t)row * Cin + c) * taps + tap];
+    }
+    const float h0 = __uint_as_float(__float_as_uint(x[0]) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(x[1]) & 0xffffe000u);
+    float* hrow = hi + (size_t)row * K + kp * 2;
+    hrow[0] = h0; hrow[1] = h1;
+    if (lo) { float* lrow = lo + (size_t)row * K + kp * 2; lrow[0] = x[0] - h0; lrow[1] = x[1] - h1; }
+    if (pairs) {
+        const int kb = (kp * 2) / 32, j = kp - kb * 16;
+        uint32_t* o = pairs + (size_t)row * K + kb * 32;
+        o[j] = pack_bf16x2(x[0], x[1]);
+        o[16 + j] = pack_bf16x2(x[0] - h0, x[1] - h1);
+    }
+}
+
 }  // namespace
+
+extern "C" int df_pack_conv_weight(const float* w, float* hi, float* lo, void* pairs, int Cout, int Cin, int taps, int rotate,
+                                   void* stream)
+{
+    if (!w || !hi || (!lo && !pairs) || Cout <= 0 || Cin <= 0 || taps <= 0) return DF_ERR_ARG;
+    const int cols = rotate ? Cout : Cin, rows = rotate ? Cin : Cout;
+    if ((taps * cols) % 32) return DF_ERR_ARG;
+    const long long total = (long long)rows * (taps * cols / 2);
+    pack_conv_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, hi, lo, (uint32_t*)pairs, Cout, Cin,
+                                                                                          taps, rotate);
+    DF_RETURN_LAST_ERROR();
+}
 
 extern "C" int df_pack_bf16_pairs(const float* w, void* out, long long rows, int K, void* stream)
 {

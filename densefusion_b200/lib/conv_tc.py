@@ -26,10 +26,23 @@ def _nhwc(x: torch.Tensor) -> torch.Tensor:
     return x if x.is_contiguous(memory_format=torch.channels_last) and x.stride(1) == 1 else x.contiguous(memory_format=torch.channels_last)
 
 
-def _launch(x, packed: ops.SplitWeight, bias, cout, taps, dil, mode):
+def _pack(weight: torch.Tensor, rotate: bool, mode: int):
+    """(Cout,Cin,k,k) -> the split GEMM operand of the forward (rotate=False) or data-gradient (rotate=True) convolution,
+    one launch (the weights change every optimiser step, so this runs per call)."""
+    cout, cin, k, _ = weight.shape
+    rows, kt = (cin, k * k * cout) if rotate else (cout, k * k * cin)
+    w = weight.detach().float().contiguous()
+    hi = torch.empty(rows, kt, device=w.device, dtype=torch.float32)
+    second = torch.empty(rows, kt, device=w.device, dtype=torch.float32)
+    check(lib.df_pack_conv_weight(ptr(w), ptr(hi), ptr(second) if mode != 3 else None, ptr(second) if mode == 3 else None,
+                                  cout, cin, k * k, 1 if rotate else 0, stream()), "df_pack_conv_weight")
+    return hi, second
+
+
+def _launch(x, packed, bias, cout, taps, dil, mode):
     b, cin, h, w = x.shape
     y = torch.empty(b, cout, h, w, device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
-    hi, lo = packed.pairs() if mode == 3 else packed.split()
+    hi, lo = packed
     check(lib.df_conv_tc(ptr(x), b, h, w, cin, cin, ptr(hi), ptr(lo), taps, dil, ptr(bias), None, 0, None, 0, ptr(y), cout,
                          cout, mode, stream()), "df_conv_tc")
     return y
@@ -41,8 +54,7 @@ class ConvTCFn(torch.autograd.Function):
         x = _nhwc(x.detach().float())
         cout, cin, k, _ = weight.shape
         mode = ops.PRECISIONS[PRECISION]
-        w = weight.detach().float()
-        packed = ops.SplitWeight(w.permute(0, 2, 3, 1).reshape(cout, k * k * cin))
+        packed = _pack(weight, False, mode)
         y = _launch(x, packed, None if bias is None else bias.detach().float().contiguous(), cout, k * k, dilation, mode)
         ctx.save_for_backward(x, weight)
         ctx.dilation, ctx.has_bias, ctx.mode = dilation, bias is not None, mode
@@ -56,9 +68,7 @@ class ConvTCFn(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             # data gradient = convolution of dy with the 180-degree rotated, in/out-transposed kernel
-            w = weight.detach().float()
-            rot = ops.SplitWeight(w.flip(2, 3).permute(1, 2, 3, 0).reshape(cin, k * k * cout))
-            dx = _launch(dy, rot, None, cin, k * k, ctx.dilation, ctx.mode)
+            dx = _launch(dy, _pack(weight, True, ctx.mode), None, cin, k * k, ctx.dilation, ctx.mode)
         if ctx.needs_input_grad[1]:
             pad = ctx.dilation * (k // 2)
             dw = torch.ops.aten.convolution_backward(dy, x, weight, None, [1, 1], [pad, pad], [ctx.dilation, ctx.dilation],

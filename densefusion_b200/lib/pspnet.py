@@ -31,6 +31,14 @@ class _UpsampleFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        b, c, h, w = ctx.in_shape
+        if c % 4 == 0 and c > 1 and g.is_cuda:
+            from .._C import check, lib, ptr, stream
+            g = g.float().contiguous(memory_format=torch.channels_last)
+            gi = torch.empty(b, c, h, w, device=g.device, dtype=torch.float32, memory_format=torch.channels_last)
+            check(lib.df_enc_upsample_backward(ptr(g), c, ptr(gi), c, b, h, w, ctx.size[0], ctx.size[1], c,
+                                               1 if ctx.align else 0, stream()), "df_enc_upsample_backward")
+            return gi, None, None
         gi = torch.ops.aten.upsample_bilinear2d_backward(g.contiguous(), list(ctx.size), list(ctx.in_shape), ctx.align,
                                                          None, None)
         return gi, None, None

@@ -100,6 +100,9 @@ int df_split_tf32(const float* x, float* hi, float* lo, long long n, void* strea
  * 8 MMA instructions per 32-wide k-block instead of 12, same fp32-parity bound.  W_lo then points to the packed pair
  * tensor made by df_pack_bf16_pairs: per row and k-block 64 bf16 = [bf16(w) x32 | bf16(w - tf32(w)) x32]; needs ldw == K. */
 int df_pack_bf16_pairs(const float* w, void* out, long long rows, int K, void* stream);
+/* torch convolution weight (Cout,Cin,kh,kw) -> (rows, taps*cols) tap-major GEMM operand split for the tensor-core modes in
+ * one pass: hi always, lo (3xTF32) and / or pairs (hybrid).  rotate = 1: the data-gradient kernel (rows = Cin, taps reversed). */
+int df_pack_conv_weight(const float* w, float* hi, float* lo, void* pairs, int Cout, int Cin, int taps, int rotate, void* stream);
 
 /* emb[b,c,n] = feat[b,c,choose[b,n]]  (lib/network.py:98-102).  feat is addressed with explicit element
  * strides so NCHW and channels-last encoders both work.  emb_pm (B*N,32) point-major and/or emb_cm
@@ -172,6 +175,8 @@ int df_enc_im2col_s2(const float* in, float* A, int B, int H, int W, int C, void
 int df_enc_adaptive_avgpool(const float* in, int ldi, float* out, int B, int H, int W, int C, int S, void* stream);
 int df_enc_upsample(const float* in, int ldi, float* out, int ldo, int B, int hin, int win, int hout, int wout, int C,
                     int align_corners, void* stream);
+int df_enc_upsample_backward(const float* gout, int ldo, float* gin, int ldi, int B, int hin, int win, int hout, int wout,
+                             int C, int align_corners, void* stream);      /* gather form of the resize's transpose */
 int df_enc_log_softmax32(float* x, long long pixels, void* stream);
 /* Sparse last decoder stage: the 3x3 patches of the x2-upsampled (align_corners) map `in` (B,h,w,C) around the N chosen
  * pixels of every crop (choose (B,N), indices into the (2h x 2w) image), A (B*N, 9*C) tap-major; zero outside the image. */

@@ -192,3 +192,18 @@ def test_training_convolution_forward_and_gradients_vs_float64(B, H, W, Cin, Cou
     assert errs[0] < 2e-5 and errs[1] < 2e-5 and errs[2] < 2e-2          # dW: cuDNN's fp32 weight-gradient algorithms
     if bias:
         assert rel(m.bias.grad, m64.bias.grad) < 1e-5
+
+
+@pytest.mark.parametrize("hin,win,hout,wout,align", [(10, 10, 20, 20, True), (1, 1, 15, 20, False), (2, 2, 20, 20, False),
+                                                     (3, 3, 10, 15, False), (6, 6, 20, 20, False), (15, 20, 30, 40, True)])
+def test_upsample_backward_kernel_vs_torch_autograd(hin, win, hout, wout, align):
+    from densefusion_b200._C import check, lib, ptr, stream
+    g = torch.Generator().manual_seed(hin + hout)
+    B, C = 3, 64
+    x = torch.randn(B, C, hin, win, generator=g, dtype=torch.float64, requires_grad=True)
+    gy = torch.randn(B, C, hout, wout, generator=g)
+    F.interpolate(x, size=(hout, wout), mode="bilinear", align_corners=align).backward(gy.double())
+    gy_n = gy.cuda().contiguous(memory_format=torch.channels_last)
+    gi = torch.empty(B, C, hin, win, device="cuda", memory_format=torch.channels_last)
+    check(lib.df_enc_upsample_backward(ptr(gy_n), C, ptr(gi), C, B, hin, win, hout, wout, C, 1 if align else 0, stream()), "up_bwd")
+    assert rel(gi, x.grad) < 2e-6
