@@ -44,9 +44,18 @@ def _w2(p):
     return p.detach().reshape(p.shape[0], -1).float().contiguous()
 
 
+# Arithmetic of the forward and data-gradient GEMMs: an fp32-parity tensor-core mode ("hybrid" / "3xtf32") or "fp32"
+# (exact FFMA).  Weight gradients (reductions over the rows) and everything too small for a 128-row MMA tile are always
+# exact fp32.
+PRECISION = "hybrid"
+
+
 # ---- thin kernel wrappers ----------------------------------------------------------------------------------
 def _gemm(A, W, bias, C, **kw):
-    ops.gemm(A, W, bias, C, precision="fp32", **kw)
+    if PRECISION != "fp32" and ops.tc_eligible(kw["M"], kw["N"], kw["K"]):
+        ops.gemm(A, ops.SplitWeight(W), bias, C, precision=PRECISION, **kw)
+    else:
+        ops.gemm(A, W, bias, C, precision="fp32", **kw)
 
 
 def _wgrad(dY, ldy, X, ldx, M, N, K, groups=1, dy_gs=0, x_gs=0):
@@ -60,6 +69,14 @@ def _wgrad(dY, ldy, X, ldx, M, N, K, groups=1, dy_gs=0, x_gs=0):
 
 
 def _dgrad(dY, ldy, Wt, ldw, dX, ldx, M, N, K, groups=1, dy_gs=0, w_gs=0, dx_gs=0, mask=None, accumulate=False):
+    if (PRECISION != "fp32" and not accumulate and ops.tc_eligible(M, N, K) and (groups == 1 or (w_gs == N * ldw and dx_gs == N))
+            and Wt.is_contiguous()):
+        # tensor-core data gradient; the ReLU mask of the layer below is applied by a separate element-wise pass
+        ops.gemm(dY, ops.SplitWeight(Wt), None, dX, M=M, N=N, K=K, lda=ldy, ldw=ldw, ldc=ldx, relu=False, precision=PRECISION,
+                 groups=groups, a_gs=dy_gs, w_gs=w_gs, c_gs=dx_gs)
+        if mask is not None:
+            _mask_inplace(dX, mask, ldx, N * groups, M)
+        return
     check(lib.df_gemm_dgrad_fp32(ptr(dY), ldy, ptr(Wt), ldw, ptr(dX), ldx, M, N, K, groups, dy_gs, w_gs, dx_gs, ptr(mask),
                                  1 if accumulate else 0, stream()), "df_gemm_dgrad_fp32")
 
