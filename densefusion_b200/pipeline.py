@@ -106,6 +106,10 @@ class PoseEstimator:
         for all B crops."""
         iters = self.iterations if iterations is None else iterations
         B, n = cloud.shape[0], self.n
+        if B == 0:                                   # a frame without detections: nothing to launch
+            return torch.empty(0, 7, device=self.device, dtype=torch.float64)
+        if cloud.shape[1] != n:
+            raise ValueError(f"PoseEstimator was built for {n} points per crop, got {cloud.shape[1]}")
         buf = self._buffers(B)
         wh, wr = self._workspaces(B)
         cloud = ops.f32c(cloud)
@@ -149,7 +153,10 @@ class PoseEstimator:
     @torch.no_grad()
     def estimate_buckets(self, buckets: Sequence[dict], iterations: Optional[int] = None) -> torch.Tensor:
         """Several (H,W) buckets (dicts with img, cloud, choose, obj) -> poses (sum B,7) in bucket order."""
+        buckets = [b for b in buckets if b["cloud"].shape[0] > 0]
         total = sum(b["cloud"].shape[0] for b in buckets)
+        if total == 0:
+            return torch.empty(0, 7, device=self.device, dtype=torch.float64)
         buf = self._buffers(total)
         key = ("cat", total)
         cat = self._bufs.get(key)

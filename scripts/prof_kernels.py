@@ -25,21 +25,21 @@ def gemm_case(M, N, K, precision, pooled=False, percrop=False, groups=1):
                  a_gs=K, w_gs=N * K, bias_gs=N, c_gs=N, pool_partial=part)
 
 
-def conv_case(B, H, W, Cin, Cout, dil):
+def conv_case(B, H, W, Cin, Cout, dil, mode):
     x = torch.randn(B, H, W, Cin, device=dev)
     w = _pack_conv(torch.randn(Cout, Cin, 3, 3, device=dev) / (9 * Cin) ** 0.5)
     out = torch.empty(B, H, W, Cout, device=dev)
     for _ in range(reps):
-        PackedEncoder._conv(x, w, out, taps=9, dil=dil, act=1, mode=1)
+        PackedEncoder._conv(x, w, out, taps=9, dil=dil, act=1, mode=mode)
 
 
 # order == order of the cases in profiles/*_ncu_full_selected.csv
-gemm_case(rows, 1920, 384, "3xtf32", percrop=True)        # 1 tower layer 1 at the bench's chunk (the roofline kernel)
-gemm_case(rows, 1024, 512, "3xtf32", pooled=True)         # 2 conv6 + pool
-gemm_case(rows, 256, 640, "3xtf32", groups=3)             # 3 tower layer 2
-conv_case(64, 40, 40, 1024, 256, 1)                       # 4 up_1 convolution, 160x160 bucket (K = 9216, 16 accumulation runs)
-conv_case(64, 20, 20, 512, 512, 4)                        # 5 layer4.1 convolution, dilation 4
-conv_case(64, 80, 80, 256, 64, 1)                         # 6 up_2 convolution (64 output channels)
+gemm_case(rows, 1920, 384, "hybrid", percrop=True)        # 1 tower layer 1 at the bench's chunk, bench-default arithmetic (the roofline kernel)
+gemm_case(rows, 1920, 384, "3xtf32", percrop=True)        # 2 the same in 3xTF32
+gemm_case(rows, 1024, 512, "hybrid", pooled=True)         # 3 conv6 + pool
+conv_case(64, 40, 40, 1024, 256, 1, 3)                    # 4 up_1 convolution, 160x160 bucket (K = 9216, 16 accumulation runs), hybrid
+conv_case(64, 20, 20, 512, 512, 4, 3)                     # 5 layer4.1 convolution, dilation 4, hybrid
+conv_case(64, 80, 80, 256, 64, 1, 1)                      # 6 up_2 convolution (64 output channels: stays on 3xTF32)
 # loss (ADD-S) and kNN at config C1 shapes (32 crops)
 g = torch.Generator().manual_seed(1)
 B = 32

@@ -131,3 +131,26 @@ def test_streaming_estimator_equals_direct_calls():
             tickets.append(se.submit(batches[i + 2]))
     for g_, w_ in zip(got, want):
         assert torch.allclose(g_, w_, atol=1e-12, rtol=0), float((g_ - w_).abs().max())
+
+
+def test_ragged_chunks_and_empty_inputs():
+    """B not a multiple of the chunk (last chunk ragged), one-crop buckets, empty buckets / no detections at all."""
+    import torch
+    from densefusion_b200.pipeline import PoseEstimator
+    est, ref, _, _ = build_nets(500, 21, seed=0)
+    crops = [synth.synth_crop(20 + i, 500, 500, 21, (80, 80), obj=(3 * i) % 21) for i in range(5)]
+    b = {k: torch.cat([c[k] for c in crops], 0).cuda() for k in ("img", "points", "choose", "idx")}
+    whole = PoseEstimator(est, ref, iterations=2, precision="hybrid", chunk_crops=128)
+    ragged = PoseEstimator(est, ref, iterations=2, precision="hybrid", chunk_crops=2)
+    want = whole.estimate(b["img"], b["points"], b["choose"], b["idx"]).clone()
+    got = ragged.estimate(b["img"], b["points"], b["choose"], b["idx"])
+    assert torch.allclose(got, want, atol=1e-9, rtol=0)          # chunking only changes which rows share a launch
+    single = ragged.estimate(b["img"][3:4], b["points"][3:4], b["choose"][3:4], b["idx"][3:4])
+    # a lone crop takes the exact-fp32 kernel for the GEMMs that fall below 256 rows (ops.tc_eligible): same pose within parity
+    assert float((single[0] - want[3]).abs().max()) < 1e-4 * float(want[3].abs().max())
+    empty = {"img": b["img"][:0], "cloud": b["points"][:0], "choose": b["choose"][:0], "obj": b["idx"][:0].view(-1)}
+    full = {"img": b["img"], "cloud": b["points"], "choose": b["choose"], "obj": b["idx"].view(-1)}
+    assert whole.estimate_buckets([empty]).shape == (0, 7) and whole.estimate_buckets([]).shape == (0, 7)
+    assert torch.allclose(whole.estimate_buckets([empty, full]), want, atol=1e-9, rtol=0)
+    with pytest.raises(ValueError):
+        whole.head_and_refine(b["points"][:, :400], torch.zeros(5 * 400, 32, device="cuda"), b["idx"].view(-1))
