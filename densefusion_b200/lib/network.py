@@ -165,9 +165,11 @@ class PoseNet(nn.Module, _PackedMixin):
         if _needs_grad(self, img, x):
             r, t, c, emb_cm = self.forward_batched(img, x, choose, obj)
             return r[0:1], t[0:1], c[0:1], emb_cm
-        out_img = self.cnn(img)
-        emb_pm, emb_cm = ops.gather_embedding(out_img, choose)
         n = x.shape[1]
+        if self.precision != "fp32" and img.is_cuda and img.shape[2] % 8 == 0 and img.shape[3] % 8 == 0:
+            emb_pm, emb_cm = self._embedding_tc(img, choose)          # tensor-core encoder, like forward_batched
+        else:
+            emb_pm, emb_cm = ops.gather_embedding(self.cnn(img), choose)
         r, t, c = self.head(x[0:1], emb_pm[:n], obj[0:1])
         return r, t, c, emb_cm.detach()
 
