@@ -214,16 +214,19 @@ select_out_dh_kernel(const float* __restrict__ g_r, const float* __restrict__ g_
     }
 }
 
-// one CTA per crop, thread k: blk[crop][i][k] = sum_rows gz[row,i] * h[row, branch(i)*128 + k]; bsum[crop][i] = sum gz
+// one CTA per (crop, row slice), thread k: blk[crop][slice][i][k] = sum over the slice's rows of gz[row,i] * h[row, branch(i)*128 + k];
+// bsum[crop][slice][i] = sum gz.  DF_SELECT_SPLITS slices per crop so that 16 crops still fill the machine.
 __global__ void __launch_bounds__(128)
 select_out_wgrad_kernel(const float* __restrict__ gz, const float* __restrict__ h, int ldh, int rows_per_crop,
                         float* __restrict__ blk, float* __restrict__ bsum)
 {
-    const int crop = blockIdx.x, k = threadIdx.x;
+    const int crop = blockIdx.x, sp = blockIdx.y, k = threadIdx.x;
+    const int per = (rows_per_crop + DF_SELECT_SPLITS - 1) / DF_SELECT_SPLITS;
+    const int r0 = sp * per, r1 = min(rows_per_crop, r0 + per);
     float acc[8], bs[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { acc[i] = 0.f; bs[i] = 0.f; }
-    for (int r = 0; r < rows_per_crop; ++r) {
+    for (int r = r0; r < r1; ++r) {
         const long long row = (long long)crop * rows_per_crop + r;
         const float hr = h[row * ldh + k], ht = h[row * ldh + 128 + k];
         const float hc = ldh >= 384 ? h[row * ldh + 256 + k] : 0.0f;
@@ -234,12 +237,13 @@ select_out_wgrad_kernel(const float* __restrict__ gz, const float* __restrict__ 
             bs[i] += g;
         }
     }
+    const size_t slot = (size_t)crop * DF_SELECT_SPLITS + sp;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) blk[((size_t)crop * 8 + i) * 128 + k] = acc[i];
-    if (k < 8) bsum[crop * 8 + k] = bs[k];
+    for (int i = 0; i < 8; ++i) blk[(slot * 8 + i) * 128 + k] = acc[i];
+    if (k < 8) bsum[slot * 8 + k] = bs[k];
 }
 
-// single CTA, crops in ascending order (deterministic even when several crops share an object)
+// single CTA, crops and slices in ascending order (deterministic even when several crops share an object)
 __global__ void __launch_bounds__(128)
 accumulate_selected_kernel(const float* __restrict__ blk, const float* __restrict__ bsum, const int64_t* __restrict__ obj,
                            int crops, int num_obj, float* dWr, float* dbr, float* dWt, float* dbt, float* dWc, float* dbc)
@@ -248,14 +252,21 @@ accumulate_selected_kernel(const float* __restrict__ blk, const float* __restric
     for (int c = 0; c < crops; ++c) {
         long long o = obj[c];
         o = o < 0 ? 0 : (o >= num_obj ? num_obj - 1 : o);
+        float v[8], b = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        for (int sp = 0; sp < DF_SELECT_SPLITS; ++sp) {
+            const size_t slot = (size_t)c * DF_SELECT_SPLITS + sp;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += blk[(slot * 8 + i) * 128 + k];
+            if (k < 8) b += bsum[slot * 8 + k];
+        }
         for (int i = 0; i < 8; ++i) {
-            const float v = blk[((size_t)c * 8 + i) * 128 + k];
-            if (i < 4) dWr[(o * 4 + i) * 128 + k] += v;
-            else if (i < 7) dWt[(o * 3 + (i - 4)) * 128 + k] += v;
-            else if (dWc) dWc[o * 128 + k] += v;
+            if (i < 4) dWr[(o * 4 + i) * 128 + k] += v[i];
+            else if (i < 7) dWt[(o * 3 + (i - 4)) * 128 + k] += v[i];
+            else if (dWc) dWc[o * 128 + k] += v[i];
         }
         if (k < 8) {
-            const float b = bsum[c * 8 + k];
             if (k < 4) dbr[o * 4 + k] += b;
             else if (k < 7) dbt[o * 3 + (k - 4)] += b;
             else if (dbc) dbc[o] += b;
@@ -369,7 +380,7 @@ extern "C" int df_select_out_backward(const float* g_r, const float* g_t, const 
     const int crops = (int)(rows / rows_per_crop);
     select_out_dh_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(g_r, g_t, g_c, out_c, h, ldh, Wr, Wt, Wc, obj,
                                                                     rows_per_crop, num_obj, rows, dh, gz);
-    select_out_wgrad_kernel<<<crops, 128, 0, s>>>(gz, h, ldh, rows_per_crop, blk, bsum);
+    select_out_wgrad_kernel<<<dim3(crops, DF_SELECT_SPLITS), 128, 0, s>>>(gz, h, ldh, rows_per_crop, blk, bsum);
     accumulate_selected_kernel<<<1, 128, 0, s>>>(blk, bsum, obj, crops, num_obj, dWr, dbr, dWt, dbt, dWc, dbc);
     DF_RETURN_LAST_ERROR();
 }

@@ -161,7 +161,7 @@ def _select_backward(g_r, g_t, g_c, out_c, h, ldh, Wr, Wt, Wc, obj, rows_per_cro
     dev = h.device
     crops = rows // rows_per_crop
     dh = _f(rows, ldh, dev=dev)
-    gz, blk, bsum = _f(rows, 8, dev=dev), _f(crops, 8, 128, dev=dev), _f(crops, 8, dev=dev)
+    gz, blk, bsum = _f(rows, 8, dev=dev), _f(crops, 8, 8, 128, dev=dev), _f(crops, 8, 8, dev=dev)     # DF_SELECT_SPLITS = 8
     z = lambda t: torch.zeros_like(t)
     dWr, dWt = z(Wr), z(Wt)
     dbr = torch.zeros(Wr.shape[0], device=dev)

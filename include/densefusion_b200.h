@@ -145,6 +145,7 @@ int df_colsum_rows(const float* X, int ldx, int rows_per_group, int groups, int 
                    void* stream);
 int df_relu_mask_inplace(float* d, const float* act, int ld, int cols, long long rows, void* stream);
 int df_pool_backward(const float* dg, const float* h, float* dh, int rows_per_crop, int C, long long rows, void* stream);
+#define DF_SELECT_SPLITS 8      /* row slices per crop: blk is (crops, DF_SELECT_SPLITS, 8, 128), bsum (crops, DF_SELECT_SPLITS, 8) */
 int df_select_out_backward(const float* g_r, const float* g_t, const float* g_c, const float* out_c, const float* h,
                            int ldh, const float* Wr, const float* Wt, const float* Wc, const int64_t* obj,
                            int rows_per_crop, int num_obj, long long rows, float* dh, float* gz, float* blk,
