@@ -914,6 +914,15 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     __syncwarp();
                     const int cq = col + cc * 4;
                     if (cq < p.N) {
+                        // this lane's 4 bias values: one vector, or two when the warp's 32 rows straddle a crop boundary
+                        // (loaded once per chunk -- per-row loads kept the epilogue warps waiting on L2 all the time)
+                        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                        if (bias && last_run) {
+                            const float* brow = bias + (p.bias_crop_stride ? (size_t)crop_first * p.bias_crop_stride : 0);
+                            b0 = __ldg(reinterpret_cast<const float4*>(brow + cq));
+                            if (p.bias_crop_stride && c.row0 + q * 32 + 31 >= crop_boundary && crop_boundary < p.M)
+                                b1 = __ldg(reinterpret_cast<const float4*>(brow + p.bias_crop_stride + cq));
+                        }
 #pragma unroll
                         for (int ps = 0; ps < 8; ++ps) {
                             if (roff[ps] < 0) continue;
@@ -926,10 +935,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             }
                             if (!last_run) { *reinterpret_cast<float4*>(dst) = o; continue; }
                             if (bias) {
-                                const float* brow = bias;
-                                if (p.bias_crop_stride)
-                                    brow += (size_t)(crop_first + (roff[ps] >= crop_boundary ? 1 : 0)) * p.bias_crop_stride;
-                                const float4 bv = __ldg(reinterpret_cast<const float4*>(brow + cq));
+                                const float4 bv = roff[ps] >= crop_boundary ? b1 : b0;
                                 o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
                             }
                             if (p.residual) {
