@@ -581,10 +581,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_whi, const __gr
 // only for the store-free pooled epilogue), two A stages in [384,512).
 // ------------------------------------------------------------------------------------------------
 constexpr int Q_THREADS = 18 * 32;
-constexpr int Q_STAGES = 4;
+constexpr int Q_MAX_STAGES = 8;
 constexpr int Q_TILE = 128 * BK * 4;                         // 16 KB: one 128-row fp32 tile of 32 k
-constexpr int Q_STAGE_BYTES = 3 * Q_TILE;                    // A | W_hi | W_lo
-constexpr int Q_SMEM_STAGES = Q_STAGES * Q_STAGE_BYTES;      // 192 KB
+constexpr int Q_SMEM_STAGES = 12 * Q_TILE;                   // 192 KB of operand stages: 4 x {A 16 KB | W_hi 16 | W_lo 16} for 128
+                                                             // weight rows per CTA ... 8 x {16 | 4 | 4} for 32 (deeper pipelines
+                                                             // for the narrow tiles, which are TMA-latency bound)
 constexpr int Q_SMEM_EPI = 8 * 32 * 32 * 4;                  // 32 KB: one swizzled 32x32 transpose tile per epilogue warp
 constexpr int Q_SMEM_TOTAL = 1024 + Q_SMEM_STAGES + Q_SMEM_EPI + 512;
 static_assert(Q_SMEM_TOTAL <= 227 * 1024, "shared memory overflow");
@@ -640,12 +641,12 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* s_epi = reinterpret_cast<float*>(smem + Q_SMEM_STAGES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Q_SMEM_STAGES + Q_SMEM_EPI);
-    uint64_t* full = bars;                          // [4]  TMA bytes of this CTA's stage
-    uint64_t* empty = bars + 4;                     // [4]  MMAs that read the stage have retired (commit)
-    uint64_t* a_full = bars + 8;                    // [4]  A of the stage is in TMEM (all stager warps of the pair)
-    uint64_t* acc_full = bars + 12;                 // [2]
-    uint64_t* acc_empty = bars + 14;                // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    uint64_t* full = bars;                          // [8]  TMA bytes of this CTA's stage
+    uint64_t* empty = bars + 8;                     // [8]  MMAs that read the stage have retired (commit)
+    uint64_t* a_full = bars + 16;                   // [8]  A of the stage is in TMEM (all stager warps of the pair)
+    uint64_t* acc_full = bars + 24;                 // [2]
+    uint64_t* acc_empty = bars + 26;                // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;
@@ -653,10 +654,12 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int nkb = p.K / BK;
     const int bnt = bn_cta * CTAS;                  // tile width = accumulator columns
     const uint32_t w_bytes = (uint32_t)bn_cta * BK * 4;
+    const uint32_t stage_bytes = Q_TILE + 2 * w_bytes;             // A | W_hi | W_lo (or the bf16 pair tile), all 1024-B aligned
+    const uint32_t Q_STAGES = min((uint32_t)Q_MAX_STAGES, (uint32_t)Q_SMEM_STAGES / stage_bytes);
     const uint32_t ACC_BUFS = bnt <= ACC_STRIDE ? 2 : 1;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < Q_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); mbar_init(a_full + i, 4 * CTAS); }
+        for (int i = 0; i < Q_MAX_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); mbar_init(a_full + i, 4 * CTAS); }
         for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 8 * CTAS); }
         fence_barrier_init();
     }
@@ -686,11 +689,11 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const int wrow = c.g * p.N + c.n0 + rank * bn_cta;
             const int acol = (int)(c.g * p.a_gs);
             for (int kb = 0; kb < nkb; ++kb, ++it) {
-                const int s = it % Q_STAGES;
+                const int s = (int)(it % Q_STAGES);
                 mbar_wait(empty + s, ((it / Q_STAGES) & 1) ^ 1);
                 if (elect_one()) {
                     mbar_expect_tx(full + s, bytes);
-                    uint8_t* dst = smem + (size_t)s * Q_STAGE_BYTES;
+                    uint8_t* dst = smem + (size_t)s * stage_bytes;
                     if (p.conv_taps) {
                         const int tap = kb / cblocks, cb = kb - tap * cblocks;
                         const int dy = p.conv_taps == 9 ? (tap / 3 - 1) * p.conv_dil : 0;
@@ -701,7 +704,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     }
                     tma_load_2d(&tm_whi, dst + Q_TILE, full + s, kb * BK, wrow);
                     // second weight tile: W_lo (fp32, 32 floats per row) or, hybrid, [bf16(W) x32 | bf16(W_lo) x32] = 64 bf16 per row
-                    if (p.precise) tma_load_2d(&tm_wlo, dst + 2 * Q_TILE, full + s, kb * (p.precise == 2 ? 2 * BK : BK), wrow);
+                    if (p.precise) tma_load_2d(&tm_wlo, dst + Q_TILE + w_bytes, full + s, kb * (p.precise == 2 ? 2 * BK : BK), wrow);
                 }
                 __syncwarp();
             }
@@ -720,14 +723,14 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (CTAS == 2) mbar_wait_cluster(acc_empty + ab, aph); else mbar_wait(acc_empty + ab, aph);
                 const uint32_t acc = tmem_base + ab * ACC_STRIDE;
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % Q_STAGES;
+                    const int s = (int)(it % Q_STAGES);
                     const uint32_t ph = (it / Q_STAGES) & 1;
                     mbar_wait(full + s, ph);
                     if (CTAS == 2) mbar_wait_cluster(a_full + s, ph); else mbar_wait(a_full + s, ph);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t w_hi = smem_u32(smem + (size_t)s * Q_STAGE_BYTES + Q_TILE);
-                        const uint64_t bhi0 = sw128_desc(w_hi), blo0 = sw128_desc(w_hi + Q_TILE);
+                        const uint32_t w_hi = smem_u32(smem + (size_t)s * stage_bytes + Q_TILE);
+                        const uint64_t bhi0 = sw128_desc(w_hi), blo0 = sw128_desc(w_hi + w_bytes);
                         const uint32_t a0 = tmem_base + TMEM_A0 + (it % A_STAGES) * 2 * BK;
 #pragma unroll
                         for (int ks = 0; ks < BK / UMMA_K; ++ks) {
@@ -782,12 +785,12 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const uint32_t total_it = (uint32_t)my_tiles * nkb;
         const int sw = r & 7;
         for (uint32_t it = grp; it < total_it; it += 2) {
-            const int s = it % Q_STAGES;
+            const int s = (int)(it % Q_STAGES);
             mbar_wait(full + s, (it / Q_STAGES) & 1);
             // TMEM A slot it % A_STAGES was last read by the MMAs of iteration it - A_STAGES.  With A_STAGES == Q_STAGES
             // that is implied by full[s] (the commit that frees the slot is what let the TMA refill the stage); with
             // fewer TMEM slots wait for that iteration's commit explicitly (same barrier the TMA producer watches).
-            const uint8_t* arow = smem + (size_t)s * Q_STAGE_BYTES + r * 128;
+            const uint8_t* arow = smem + (size_t)s * stage_bytes + r * 128;
             // hi: TF32-exact part (raw value in single-pass mode); second[]: what goes into columns [32,64) of the TMEM stage --
             // lo (3xTF32), or 16 words of bf16(x) pairs followed by 16 words of bf16(lo) pairs (hybrid)
             uint32_t hi[32], second[32];
