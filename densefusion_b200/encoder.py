@@ -14,6 +14,7 @@ Activations are NHWC fp32; the result (B,H,W,32) log-softmax embedding is consum
 explicit strides.  Inference only; training keeps the torch/cuDNN encoder (its backward is library code)."""
 from __future__ import annotations
 
+import os
 from typing import Dict, Tuple
 
 import torch
@@ -22,7 +23,7 @@ from . import ops
 from ._C import check, lib, ptr, stream
 
 K_CONV1 = 160          # 3*7*7 = 147 padded to a multiple of 32
-_NARROW_ON_3XTF32 = __import__("os").environ.get("DF_HYBRID_NARROW", "0") != "1"
+_NARROW_ON_3XTF32 = os.environ.get("DF_HYBRID_NARROW", "0") != "1"     # A/B knob for the rule in PackedEncoder._conv
 
 
 def _pack_conv(w: torch.Tensor) -> ops.SplitWeight:
