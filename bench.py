@@ -52,11 +52,16 @@ def parse():
     ap.add_argument("--workload", default="pose", choices=["pose", "train"],
                     help="pose: the headline metric; train: config C4, data-parallel training step (16 samples / GPU / step)")
     ap.add_argument("--phase", default="estimator", choices=["estimator", "refiner"])
-    return ap.parse_args()
+    ap.add_argument("--num-points", type=int, default=500,
+                    help="points per crop: 500 = the configuration the metric is quoted on; 1000 = the reference's YCB setting (config C2 variant)")
+    args = ap.parse_args()
+    global N_POINTS
+    N_POINTS = args.num_points
+    return args
 
 
 def workload_name(frames):
-    return (f"YCB PoseNet(500,21) + {ITERS} PoseRefineNet iterations (eval_ycb pipeline), {frames} synthetic frames x 8 "
+    return (f"YCB PoseNet({N_POINTS},21) + {ITERS} PoseRefineNet iterations (eval_ycb pipeline), {frames} synthetic frames x 8 "
             f"objects per GPU per step, crops 3x80^2+3x120^2+2x160^2, CNN encoder included")
 
 
@@ -568,7 +573,7 @@ def run_train(args):
             "value": total / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
             "data": "synthetic",
-            "config": {"workload": f"config C4: YCB PoseNet(500,21) {args.phase} phase, 16 samples per GPU per optimiser step "
+            "config": {"workload": f"config C4: YCB PoseNet({N_POINTS},21) {args.phase} phase, 16 samples per GPU per optimiser step "
                                    "(6x80^2 + 6x120^2 + 4x160^2), gradient SUM semantics of tools/train.py:159-169",
                        "global_batch": total, "phase": args.phase, "allreduce_bytes": r["allreduce_bytes"],
                        "parameters": r["parameters"], "launch": r["launch"],

@@ -47,6 +47,9 @@ SIGNATURES = {
     "df_enc_maxpool": [_p, _p, _i, _i, _i, _i, _p],
     "df_enc_im2col_s2": [_p, _p, _i, _i, _i, _i, _p],
     "df_enc_adaptive_avgpool": [_p, _i, _p, _i, _i, _i, _i, _i, _p],
+    "df_enc_pyramid_pool": [_p, _i, _p, _i, _i, _i, _i, _p],
+    "df_enc_pyramid_sum": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "df_enc_upconv_finish": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "df_enc_upsample": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "df_enc_upsample_backward": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "df_enc_log_softmax32": [_p, _ll, _p],

@@ -8,8 +8,13 @@ GEMM on the CTA-pair tcgen05 kernel in the same error-compensated 3xTF32 arithme
   * 1x1 convolutions: plain GEMMs over the (pixels, channels) matrix;
   * the three stride-2 layers (conv1 7x7, layer2.0.conv1 3x3, layer2.0.downsample 1x1) go through small im2col
     buffers (the 1x1 one is the centre tap of the 3x3 one) and the same GEMM;
-  * skip connections, biases, ReLU / PReLU are GEMM epilogues; the pyramid concat is never materialised: layer4 and the
-    four resized pyramid levels are written straight into channel slices of one 2560-wide buffer.
+  * skip connections, biases, ReLU / PReLU are GEMM epilogues;
+  * the decoder stages (x2 resize + 3x3 convolution + PReLU) are evaluated at their LOW resolution: a 1x1 convolution commutes
+    with the bilinear resize, so x . [W_tap0 .. W_tap8] is one GEMM over a quarter of the pixels and df_enc_upconv_finish sums
+    the nine shifted bilinear samples (4x fewer FLOPs on what were the two most expensive layers, no resized maps);
+  * the pyramid (PSP) module is folded: 1x1 convolutions commute with the bilinear resize, so the four pooled branches are
+    multiplied by (bottleneck slice x stage weight) at 50 cells per crop, resized and summed by one kernel, and enter the
+    bottleneck GEMM as its residual operand -- K = 512 instead of 2560 at full resolution and no 2560-wide concat.
 Activations are NHWC fp32; the result (B,H,W,32) log-softmax embedding is consumed by df_gather_embedding through
 explicit strides.  Inference only; training keeps the torch/cuDNN encoder (its backward is library code)."""
 from __future__ import annotations
@@ -54,14 +59,26 @@ class PackedEncoder:
                 if pre + "downsample.0.weight" in sd:
                     blk["down"] = _pack_conv(sd[pre + "downsample.0.weight"])
                 self.blocks.append(blk)
-        self.stages = [_pack_conv(sd[f"psp.stages.{i}.1.weight"]) for i in range(4)]
-        self.bottleneck = _pack_conv(sd["psp.bottleneck.weight"])
         self.bottleneck_b = sd["psp.bottleneck.bias"].float().contiguous()
+        # folded pyramid: bottleneck slice x stage convolution, multiplied once in fp64 (see encoder.cu, "folded pyramid")
+        wb = sd["psp.bottleneck.weight"].double().reshape(1024, 2560)
+        self.pyramid = []
+        for i in range(4):
+            sw = ops.SplitWeight((wb[:, 512 * i:512 * (i + 1)] @ sd[f"psp.stages.{i}.1.weight"].double().reshape(512, 512)).float().contiguous())
+            sw.split()
+            self.pyramid.append(sw)
+        self.bottleneck_f = ops.SplitWeight(wb[:, 2048:].float().contiguous())
+        self.bottleneck_f.split()
         self.ups = []
         for u in ("up_1", "up_2", "up_3"):
-            self.ups.append({"w": _pack_conv(sd[f"{u}.conv.1.weight"]), "b": sd[f"{u}.conv.1.bias"].float().contiguous(),
-                             "a": sd[f"{u}.conv.2.weight"].float().contiguous(),
-                             "cout": sd[f"{u}.conv.1.weight"].shape[0]})
+            w = sd[f"{u}.conv.1.weight"]
+            co, ci = w.shape[0], w.shape[1]
+            # "wz": the nine taps stacked along the OUTPUT axis, (9*Cout, Cin) -- the low-resolution GEMM of the folded stage
+            wz = ops.SplitWeight(w.detach().float().permute(2, 3, 0, 1).reshape(9 * co, ci).contiguous())
+            wz.split()
+            self.ups.append({"wz": wz, "b": sd[f"{u}.conv.1.bias"].float().contiguous(),
+                             "a": sd[f"{u}.conv.2.weight"].float().contiguous(), "cout": co})
+        self.ups[2]["w"] = _pack_conv(sd["up_3.conv.1.weight"])       # (Cout, 9*Cin): the sparse tail's patch GEMM
         self.final_w = sd["final.0.weight"].float().reshape(32, 64).contiguous()
         self.final_b = sd["final.0.bias"].float().contiguous()
         self._ws: Dict[Tuple[int, int, int], dict] = {}
@@ -81,10 +98,10 @@ class PackedEncoder:
             ws["l1"] = [torch.empty(b, H4, W4, 64, **f) for _ in range(3)]
             ws["a2"] = torch.empty(b * H8 * W8, 9 * 64, **f)
             ws["l8"] = {c: [torch.empty(b, H8, W8, c, **f) for _ in range(3)] for c in (128, 256, 512)}
-            ws["cat"] = torch.empty(b, H8, W8, 2560, **f)
-            ws["pool"] = [torch.empty(b, s, s, 512, **f) for s in (1, 2, 3, 6)]
-            ws["pconv"] = [torch.empty(b, s, s, 512, **f) for s in (1, 2, 3, 6)]
             ws["bott"] = torch.empty(b, H8, W8, 1024, **f)
+            ws["pyr_pool"] = torch.empty(50 * b, 512, **f)
+            ws["pyr_y"] = torch.empty(50 * b, 1024, **f)
+            ws["pyr_sum"] = torch.empty(b, H8, W8, 1024, **f)
             hs = [(2 * H8, 2 * W8), (4 * H8, 4 * W8), (8 * H8, 8 * W8)]
             ws["hs"] = hs
             # decoder stages are allocated on first use: the sparse tail (forward_points) never needs the
@@ -96,8 +113,8 @@ class PackedEncoder:
     def _stage_buffers(self, ws, i, b):
         if ws["up_in"][i] is None:
             f = dict(device=self.device, dtype=torch.float32)
-            (h, w), cin, cout = ws["hs"][i], (1024, 256, 64)[i], (256, 64, 64)[i]
-            ws["up_in"][i] = torch.empty(b, h, w, cin, **f)
+            (h, w), cout = ws["hs"][i], (256, 64, 64)[i]
+            ws["up_in"][i] = torch.empty(b, h // 2, w // 2, 9 * cout, **f)      # Z: the nine tap products at the low resolution
             ws["up_out"][i] = torch.empty(b, h, w, cout, **f)
         return ws["up_in"][i], ws["up_out"][i]
 
@@ -181,7 +198,6 @@ class PackedEncoder:
         free = [ws["l1"][1], ws["l1"][2]]
         for bi, blk in enumerate(self.blocks):
             cout = blk["cout"]
-            last = bi == len(self.blocks) - 1
             if blk["stride"] == 2:
                 # layer2.0: 3x3/2 and the 1x1/2 projection both read the im2col'ed patches (projection = centre tap)
                 check(lib.df_enc_im2col_s2(ptr(x), ptr(ws["a2"]), b, H4, W4, 64, s), "df_enc_im2col_s2")
@@ -205,34 +221,30 @@ class PackedEncoder:
                 continue
             t, out = free[0], free[1]
             self._conv(x, blk["c1"], t, taps=9, dil=blk["dil"], act=1, mode=mode)
-            if last:                                                 # layer4 output lands in its slice of the concat
-                cat = ws["cat"]
-                self._conv(t, blk["c2"], cat[..., 2048:], taps=9, dil=blk["dil"], residual=x, act=1, mode=mode,
-                           ldy=2560, cout=512)
-            else:
-                self._conv(t, blk["c2"], out, taps=9, dil=blk["dil"], residual=x, act=1, mode=mode)
-                x, free = out, [t, x]
-        # pyramid pooling: [up(conv(pool_s(f))) for s in 1,2,3,6] + [f] -> 1x1 bottleneck + ReLU
-        cat = ws["cat"]
-        feats = cat[..., 2048:]
+            self._conv(t, blk["c2"], out, taps=9, dil=blk["dil"], residual=x, act=1, mode=mode)
+            x, free = out, [t, x]
+        # pyramid pooling (lib/pspnet.py:17-24): relu(Wb . cat[up(S_s . pool_s(f)) for s in 1,2,3,6; f] + bias)
+        #   = relu(Wb_f . f + bias + sum_s up((Wb_s S_s) . pool_s(f))): the pooled branches are evaluated at 50 cells per crop
+        #   and only the 512 channels of f go through the full-resolution GEMM (K = 512 instead of 2560)
+        feats = x
+        check(lib.df_enc_pyramid_pool(ptr(feats), 512, ptr(ws["pyr_pool"]), b, H8, W8, 512, s), "df_enc_pyramid_pool")
+        row = 0
         for i, sz in enumerate((1, 2, 3, 6)):
-            check(lib.df_enc_adaptive_avgpool(ptr(feats), 2560, ptr(ws["pool"][i]), b, H8, W8, 512, sz, s),
-                  "df_enc_adaptive_avgpool")
             r = b * sz * sz
-            ops.gemm(ws["pool"][i], self.stages[i], None, ws["pconv"][i], M=r, N=512, K=512, lda=512, ldw=512, ldc=512,
-                     relu=False, precision=precision)
-            check(lib.df_enc_upsample(ptr(ws["pconv"][i]), 512, ptr(cat[..., i * 512:]), 2560, b, sz, sz, H8, W8, 512, 0, s),
-                  "df_enc_upsample")
-        r8 = b * H8 * W8
-        ops.gemm(cat, self.bottleneck, self.bottleneck_b, ws["bott"], M=r8, N=1024, K=2560, lda=2560, ldw=2560, ldc=1024,
-                 relu=True, precision=precision)
-        # three x2 bilinear (align_corners) + 3x3 conv + PReLU stages
+            ops.gemm(ws["pyr_pool"][row:], self.pyramid[i], None, ws["pyr_y"][row:], M=r, N=1024, K=512, lda=512, ldw=512,
+                     ldc=1024, relu=False, precision=precision)
+            row += r
+        check(lib.df_enc_pyramid_sum(ptr(ws["pyr_y"]), ptr(ws["pyr_sum"]), 1024, b, H8, W8, 1024, s), "df_enc_pyramid_sum")
+        self._conv(feats, self.bottleneck_f, ws["bott"], taps=1, bias=self.bottleneck_b, residual=ws["pyr_sum"], act=1, mode=mode)
+        # three decoder stages (x2 bilinear resize, align_corners; 3x3 convolution; PReLU), each evaluated at its LOW resolution:
+        # conv3x3(up(x)) = sum_tap shift_tap(up(W_tap . x)) -- one GEMM x . [W_0..W_8] over a quarter of the pixels, then
+        # df_enc_upconv_finish sums the nine shifted bilinear samples, adds the bias and applies PReLU (4x fewer FLOPs, no resized map)
         x, (h, w) = ws["bott"], (H8, W8)
         for i, up in enumerate(self.ups[:stages]):
-            hh, wwd = ws["hs"][i]
-            c = x.shape[3]
-            up_in, up_out = self._stage_buffers(ws, i, b)
-            check(lib.df_enc_upsample(ptr(x), c, ptr(up_in), c, b, h, w, hh, wwd, c, 1, s), "df_enc_upsample")
-            self._conv(up_in, up["w"], up_out, taps=9, dil=1, bias=up["b"], prelu=up["a"], act=2, mode=mode)
-            x, (h, w) = up_out, (hh, wwd)
+            c, cout = x.shape[3], up["cout"]
+            z, up_out = self._stage_buffers(ws, i, b)
+            ops.gemm(x, up["wz"], None, z, M=b * h * w, N=9 * cout, K=c, lda=c, ldw=c, ldc=9 * cout, relu=False, precision=precision)
+            check(lib.df_enc_upconv_finish(ptr(z), 9 * cout, ptr(up["b"]), ptr(up["a"]), ptr(up_out), cout, b, h, w, cout, s),
+                  "df_enc_upconv_finish")
+            x, (h, w) = up_out, ws["hs"][i]
         return x, ws, mode

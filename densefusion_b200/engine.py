@@ -167,7 +167,8 @@ def refiner_features_chunk(w: PackedRefiner, ws: Workspace, pf, x, emb_pm, crops
 
 def refiner_mlp(w: PackedRefiner, g, h1, h2, obj, crops, out_r, out_t, precision="fp32"):
     """The two MLP towers on the pooled features: g (crops,1024) -> out_r (crops,4), out_t (crops,3).
-    Below 256 rows the GEMMs stay on the exact-fp32 kernel in every mode (ops.tc_eligible)."""
+    The 1024x1024 layer runs on the tensor cores at any row count; the small second layer stays on the exact-fp32 kernel below
+    256 rows (ops.tc_eligible)."""
     ops.gemm(g, w.w1, w.b1, h1, M=crops, N=1024, K=1024, lda=1024, ldw=1024, ldc=1024, relu=True, precision=precision)
     ops.gemm(h1, w.w2, w.b2, h2, M=crops, N=128, K=512, lda=1024, ldw=512, ldc=256, relu=True, precision=precision,
              groups=2, a_gs=512, w_gs=128 * 512, bias_gs=128, c_gs=128)

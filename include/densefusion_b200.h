@@ -174,6 +174,16 @@ int df_enc_im2col_conv1(const float* img, float* A, int B, int H, int W, int ldk
 int df_enc_maxpool(const float* in, float* out, int B, int H, int W, int C, void* stream);
 int df_enc_im2col_s2(const float* in, float* A, int B, int H, int W, int C, void* stream);
 int df_enc_adaptive_avgpool(const float* in, int ldi, float* out, int B, int H, int W, int C, int S, void* stream);
+/* Folded pyramid (lib/pspnet.py:17-24): the four adaptive average pools (1,2,3,6) of `in` (B,H,W,C; pixel pitch ldi) in one
+   pass -> out (50 B, C) stage-major (rows [B x 1 | B x 4 | B x 9 | B x 36]); and out[b,y,x,:] = Y[b,:] + sum_s bilinear(Y cells of s) resized to
+   H x W (align_corners = False) -- the pooled branches after their (bottleneck . stage) products, summed at full resolution. */
+int df_enc_pyramid_pool(const float* in, int ldi, float* out, int B, int H, int W, int C, void* stream);
+int df_enc_pyramid_sum(const float* Y, float* out, int ldo, int B, int H, int W, int C, void* stream);
+/* Decoder stage (lib/pspnet.py:27-37: x2 bilinear resize, align_corners; 3x3 convolution; PReLU) evaluated at the low
+   resolution: Z (B,h,w,>=9*C; pixel pitch ldz) = x . [W_tap0 .. W_tap8] (one GEMM, tap-major columns); this call sums the nine
+   shifted bilinear samples of Z per output pixel, adds `bias` (may be NULL) and applies PReLU(prelu[0]) -> out (B,2h,2w,C). */
+int df_enc_upconv_finish(const float* Z, int ldz, const float* bias, const float* prelu, float* out, int ldo, int B, int h, int w,
+                         int C, void* stream);
 int df_enc_upsample(const float* in, int ldi, float* out, int ldo, int B, int hin, int win, int hout, int wout, int C,
                     int align_corners, void* stream);
 int df_enc_upsample_backward(const float* gout, int ldo, float* gin, int ldi, int B, int hin, int win, int hout, int wout,

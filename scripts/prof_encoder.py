@@ -34,7 +34,7 @@ def gemm(A, W, b, C, **k):
 
 E.PackedEncoder._conv = staticmethod(conv)
 ops.gemm = gemm
-for name in ("df_enc_im2col_conv1", "df_enc_maxpool", "df_enc_im2col_s2", "df_enc_adaptive_avgpool", "df_enc_upsample", "df_enc_log_softmax32"):
+for name in ("df_enc_im2col_conv1", "df_enc_maxpool", "df_enc_im2col_s2", "df_enc_pyramid_pool", "df_enc_pyramid_sum", "df_enc_upsample", "df_enc_log_softmax32"):
     f = getattr(lib, name)
     setattr(lib, name, (lambda f, name: lambda *a: timed((name,), f, *a))(f, name))
 

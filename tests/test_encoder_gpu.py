@@ -86,6 +86,31 @@ def test_encoder_helper_kernels_vs_torch():
         check(lib.df_enc_adaptive_avgpool(ptr(wide[..., 32:]), 96, ptr(o), B, 10, 15, 64, S, stream()), "avgpool")
         want = F.adaptive_avg_pool2d(wide[..., 32:].permute(0, 3, 1, 2).cpu(), (S, S))
         assert rel(o.permute(0, 3, 1, 2), want) < 1e-6
+    # folded pyramid: the four pools in one pass (stage-major rows), and the sum of their bilinear resizes
+    pooled = torch.empty(50 * B, 64, device="cuda")
+    check(lib.df_enc_pyramid_pool(ptr(wide[..., 32:]), 96, ptr(pooled), B, 10, 15, 64, stream()), "pyramid_pool")
+    src = wide[..., 32:].permute(0, 3, 1, 2).cpu()
+    row, want_sum = 0, torch.zeros(B, 64, 10, 15)
+    for S in (1, 2, 3, 6):
+        want = F.adaptive_avg_pool2d(src, (S, S))
+        got = pooled[row:row + B * S * S].view(B, S, S, 64).permute(0, 3, 1, 2)
+        assert rel(got, want) < 1e-6
+        want_sum += F.interpolate(want, size=(10, 15), mode="bilinear", align_corners=False)
+        row += B * S * S
+    summed = torch.zeros(B, 10, 15, 96, device="cuda")
+    check(lib.df_enc_pyramid_sum(ptr(pooled), ptr(summed[..., 16:]), 96, B, 10, 15, 64, stream()), "pyramid_sum")
+    assert rel(summed[..., 16:80].permute(0, 3, 1, 2), want_sum) < 2e-6
+    assert float(summed[..., :16].abs().max()) == 0.0 and float(summed[..., 80:].abs().max()) == 0.0
+    # decoder stage at the low resolution: tap products (here in fp64 on the host) + df_enc_upconv_finish
+    #   == PReLU(conv3x3(resize x2 (align_corners)) + bias)
+    xl, wt = torch.randn(2, 32, 6, 9, generator=g), torch.randn(16, 32, 3, 3, generator=g) * 0.1
+    bs, slope = torch.randn(16, generator=g), torch.tensor([0.25])
+    want = F.prelu(F.conv2d(F.interpolate(xl, scale_factor=2, mode="bilinear", align_corners=True), wt, bs, padding=1), slope)
+    z = (_nhwc(xl).reshape(-1, 32).double() @ wt.permute(2, 3, 0, 1).reshape(144, 32).double().T).float().view(2, 6, 9, 144).cuda()
+    o = torch.empty(2, 12, 18, 16, device="cuda")
+    bs_d, slope_d = bs.cuda(), slope.cuda()                  # (named: a temporary would be freed before the launch)
+    check(lib.df_enc_upconv_finish(ptr(z), 144, ptr(bs_d), ptr(slope_d), ptr(o), 16, 2, 6, 9, 16, stream()), "upconv_finish")
+    assert rel(o.permute(0, 3, 1, 2), want) < 5e-6
     # bilinear resize into a channel slice, both alignment modes
     small = torch.randn(B, 6, 6, 64, generator=g).cuda()
     for (ho, wo, align) in ((10, 15, False), (12, 12, True)):

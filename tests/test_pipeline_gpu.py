@@ -146,7 +146,7 @@ def test_ragged_chunks_and_empty_inputs():
     got = ragged.estimate(b["img"], b["points"], b["choose"], b["idx"])
     assert torch.allclose(got, want, atol=1e-9, rtol=0)          # chunking only changes which rows share a launch
     single = ragged.estimate(b["img"][3:4], b["points"][3:4], b["choose"][3:4], b["idx"][3:4])
-    # a lone crop takes the exact-fp32 kernel for the GEMMs that fall below 256 rows (ops.tc_eligible): same pose within parity
+    # a lone crop takes the exact-fp32 kernel for the small-weight GEMMs that fall below 256 rows (ops.tc_eligible): same pose within parity
     assert float((single[0] - want[3]).abs().max()) < 1e-4 * float(want[3].abs().max())
     empty = {"img": b["img"][:0], "cloud": b["points"][:0], "choose": b["choose"][:0], "obj": b["idx"][:0].view(-1)}
     full = {"img": b["img"], "cloud": b["points"], "choose": b["choose"], "obj": b["idx"].view(-1)}
