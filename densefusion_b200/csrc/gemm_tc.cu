@@ -593,7 +593,34 @@ static_assert(Q_SMEM_TOTAL <= 227 * 1024, "shared memory overflow");
 struct QTile {
     int g, n0, row0, rows_valid, crop, pool_tile;
     int x0, y0, b0;                              // convolution form: origin of this CTA's pixel patch
+    uint32_t taps;                               // convolution form: taps the CTA pair has to visit (bit ky*3 + kx)
 };
+
+// Taps of a 3x3 convolution that can reach the image from a TH x TW patch at (x0, y0): with dilation d the tap (ky, kx)
+// reads rows y + (ky-1)*d, so a patch within d of the top edge never sees ky = 0 etc.  Skipped taps are whole k-block
+// runs the pair neither loads nor multiplies (layer4 at dilation 4 on a 10x10 map: half of all tap visits).
+__device__ __forceinline__ void q_patch(const TcParams& p, int pt, int& tx, int& ty, int& tb)
+{
+    // batch fastest: the two patches of a CTA pair normally sit at the same (x0, y0) of neighbouring crop groups and need the
+    // same taps (measured against x-fastest with the union of two neighbouring patches: 3-8% on the dilated layers)
+    tb = pt % p.tiles_b;
+    const int rest = pt / p.tiles_b;
+    tx = rest % p.tiles_x; ty = rest / p.tiles_x;
+}
+
+__device__ __forceinline__ uint32_t q_tap_mask(const TcParams& p, int x0, int y0)
+{
+    if (p.conv_taps != 9) return 1u;
+    const int yh = min(y0 + p.TH, p.cH) - 1, xh = min(x0 + p.TW, p.cW) - 1;
+    uint32_t my = 0, mx = 0;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const int d = (t - 1) * p.conv_dil;
+        if (yh + d >= 0 && y0 + d < p.cH) my |= 1u << t;
+        if (xh + d >= 0 && x0 + d < p.cW) mx |= 1u << t;
+    }
+    return ((my & 1u) ? mx : 0u) | ((my & 2u) ? mx << 3 : 0u) | ((my & 4u) ? mx << 6 : 0u);
+}
 
 template <int CTAS>
 __device__ __forceinline__ QTile q_decode(const TcParams& p, int t, int m_tiles, int n_tiles, int bnt, int rank)
@@ -607,14 +634,20 @@ __device__ __forceinline__ QTile q_decode(const TcParams& p, int t, int m_tiles,
     else { mt = rem / n_tiles; nt = rem - mt * n_tiles; }                  // ... or the activation rows
     c.n0 = nt * bnt;
     c.crop = 0; c.pool_tile = 0;
-    c.x0 = c.y0 = c.b0 = 0;
+    c.x0 = c.y0 = c.b0 = 0; c.taps = 1u;
     if (p.conv_taps) {
         const int pt = mt * CTAS + rank;
-        const int tx = pt % p.tiles_x, rest = pt / p.tiles_x;
-        const int ty = rest % p.tiles_y, tb = rest / p.tiles_y;
-        c.x0 = tx * p.TW; c.y0 = ty * p.TH; c.b0 = tb * p.TB;      // tb >= tiles_b: a patch past the batch, fully masked
+        int tx, ty, tb;
+        q_patch(p, pt, tx, ty, tb);
+        c.x0 = tx * p.TW; c.y0 = ty * p.TH; c.b0 = tb * p.TB;      // a patch past the last one is fully masked
         c.row0 = 0;
-        c.rows_valid = tb < p.tiles_b ? p.TW * p.TH * p.TB : 0;
+        c.rows_valid = (ty < p.tiles_y && tb < p.tiles_b) ? p.TW * p.TH * p.TB : 0;
+        c.taps = 0;
+#pragma unroll
+        for (int r = 0; r < CTAS; ++r) {                           // union over the pair: one MMA stream serves both patches
+            q_patch(p, mt * CTAS + r, tx, ty, tb);
+            if (ty < p.tiles_y && tb < p.tiles_b) c.taps |= q_tap_mask(p, tx * p.TW, ty * p.TH);
+        }
     } else if (p.pool_partial) {
         const int pairs_per_crop = (p.rows_per_crop + 128 * CTAS - 1) / (128 * CTAS);
         c.crop = mt / pairs_per_crop;
@@ -688,16 +721,24 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const QTile c = q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, rank);
             const int wrow = c.g * p.N + c.n0 + rank * bn_cta;
             const int acol = (int)(c.g * p.a_gs);
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int nkb_t = p.conv_taps ? __popc(c.taps) * cblocks : nkb;
+            uint64_t tap_list = 0;                                              // the taps the pair visits, 4 bits each, in order
+            for (int tap = 8; tap >= 0; --tap)
+                if ((c.taps >> tap) & 1u) tap_list = (tap_list << 4) | (uint64_t)tap;
+            int cb = 0;
+            for (int j = 0; j < nkb_t; ++j, ++it) {
                 const int s = (int)(it % Q_STAGES);
                 mbar_wait(empty + s, ((it / Q_STAGES) & 1) ^ 1);
                 if (elect_one()) {
                     mbar_expect_tx(full + s, bytes);
                     uint8_t* dst = smem + (size_t)s * stage_bytes;
+                    int kb = j;                                                 // k-block of the weight matrix
                     if (p.conv_taps) {
-                        const int tap = kb / cblocks, cb = kb - tap * cblocks;
-                        const int dy = p.conv_taps == 9 ? (tap / 3 - 1) * p.conv_dil : 0;
-                        const int dx = p.conv_taps == 9 ? (tap % 3 - 1) * p.conv_dil : 0;
+                        const int tap = (int)(tap_list & 15u);
+                        const int ky = tap / 3, kx = tap - ky * 3;
+                        const int dy = p.conv_taps == 9 ? (ky - 1) * p.conv_dil : 0;
+                        const int dx = p.conv_taps == 9 ? (kx - 1) * p.conv_dil : 0;
+                        kb = tap * cblocks + cb;
                         tma_load_4d(&tm_a, dst, full + s, cb * BK, c.x0 + dx, c.y0 + dy, c.b0);
                     } else {
                         tma_load_2d(&tm_a, dst, full + s, acol + kb * BK, c.row0);
@@ -706,6 +747,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     // second weight tile: W_lo (fp32, 32 floats per row) or, hybrid, [bf16(W) x32 | bf16(W_lo) x32] = 64 bf16 per row
                     if (p.precise) tma_load_2d(&tm_wlo, dst + Q_TILE + w_bytes, full + s, kb * (p.precise == 2 ? 2 * BK : BK), wrow);
                 }
+                if (++cb == cblocks) { cb = 0; tap_list >>= 4; }
                 __syncwarp();
             }
         }
@@ -715,9 +757,12 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const uint32_t idesc = tf32_instr_desc(bnt, 128 * CTAS);
             const uint32_t idesc_bf = bf16_instr_desc(bnt, 128 * CTAS);
             uint32_t it = 0, ti = 0;
+            const int cblocks = p.conv_taps ? p.K / (BK * p.conv_taps) : 1;
             for (int t = cid; t < total_tiles; t += ncl) {
-              for (int kc = 0; kc < p.k_chunks; ++kc, ++ti) {
-                const int kb0 = kc * p.kbc, kb1 = min(nkb, kb0 + p.kbc);
+              const int nkb_t = p.conv_taps == 9 ? __popc(q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, 0).taps) * cblocks : nkb;
+              const int runs = (nkb_t + p.kbc - 1) / p.kbc;
+              for (int kc = 0; kc < runs; ++kc, ++ti) {
+                const int kb0 = kc * p.kbc, kb1 = min(nkb_t, kb0 + p.kbc);
                 const uint32_t ab = ti % ACC_BUFS;
                 const uint32_t aph = ((ti / ACC_BUFS) & 1) ^ 1;
                 if (CTAS == 2) mbar_wait_cluster(acc_empty + ab, aph); else mbar_wait(acc_empty + ab, aph);
@@ -782,7 +827,15 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int r = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const int my_tiles = (total_tiles - cid + ncl - 1) / ncl;
-        const uint32_t total_it = (uint32_t)my_tiles * nkb;
+        uint32_t total_it = (uint32_t)my_tiles * nkb;
+        if (p.conv_taps == 9) {                                          // tiles near the border visit fewer taps
+            const int cblocks = p.K / (BK * 9);
+            total_it = 0;
+            for (int t = cid + lane * ncl; t < total_tiles; t += 32 * ncl)
+                total_it += __popc(q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, 0).taps) * cblocks;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) total_it += __shfl_xor_sync(0xffffffffu, total_it, off);
+        }
         const int sw = r & 7;
         for (uint32_t it = grp; it < total_it; it += 2) {
             const int s = (int)(it % Q_STAGES);
@@ -840,10 +893,11 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int nchunks = bnt / 32;
         uint32_t ti = 0;
         for (int t = cid; t < total_tiles; t += ncl) {
-          for (int kc = 0; kc < p.k_chunks; ++kc, ++ti) {
-            const bool first_run = kc == 0, last_run = kc == p.k_chunks - 1;
+          const QTile c = q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, rank);
+          const int runs = p.conv_taps == 9 ? (__popc(c.taps) * (p.K / (BK * 9)) + p.kbc - 1) / p.kbc : p.k_chunks;
+          for (int kc = 0; kc < runs; ++kc, ++ti) {
+            const bool first_run = kc == 0, last_run = kc == runs - 1;
             const uint32_t ab = ti % ACC_BUFS;
-            const QTile c = q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, rank);
             const int r = q * 32 + lane;
             const bool row_ok = r < c.rows_valid;
             const float* bias = p.bias ? p.bias + c.g * p.bias_gs : nullptr;
@@ -1365,15 +1419,26 @@ extern "C" int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx,
     p.rows_per_crop = p.M; p.a_gs = 0; p.bias_gs = 0; p.c_gs = 0; p.pool_partial = nullptr; p.tiles_per_crop = 0;
     p.conv_taps = taps; p.conv_dil = dilation; p.cW = W; p.cH = H; p.cB = B;
     p.residual = residual; p.ldr = ldr; p.prelu = prelu;
-    // pixel patch (TB x TH x TW <= 128 rows) with the fewest tiles; ties: wider rows (longer contiguous runs)
-    long long best_tiles = -1;
+    // pixel patch (TB x TH x TW <= 128 rows) with the fewest tap visits = patches x the taps each can reach (q_tap_mask: small
+    // patches of a dilated layer skip the taps that only see padding); ties: wider rows (longer contiguous runs)
+    auto reach = [&](int extent, int t) {                  // sum over the patches along one axis of the taps (of 3) they reach
+        if (taps != 9) return (extent + t - 1) / t;
+        int sum = 0;
+        for (int o = 0; o < extent; o += t) {
+            const int hi = (o + t < extent ? o + t : extent) - 1;
+            for (int k = -1; k <= 1; ++k) sum += (hi + k * dilation >= 0 && o + k * dilation < extent) ? 1 : 0;
+        }
+        return sum;
+    };
+    long long best_cost = -1;
     for (int tw = 1; tw <= (W < 128 ? W : 128); ++tw) {
+        const int rx = reach(W, tw);
         for (int th = 1; th <= H && tw * th <= 128; ++th) {
             int tb = 128 / (tw * th);
             if (tb > B) tb = B;
-            const long long tiles = (long long)((W + tw - 1) / tw) * ((H + th - 1) / th) * ((B + tb - 1) / tb);
-            if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && tw > p.TW)) {
-                best_tiles = tiles; p.TW = tw; p.TH = th; p.TB = tb;
+            const long long cost = (long long)rx * reach(H, th) * ((B + tb - 1) / tb);
+            if (best_cost < 0 || cost < best_cost || (cost == best_cost && tw > p.TW)) {
+                best_cost = cost; p.TW = tw; p.TH = th; p.TB = tb;
             }
         }
     }

@@ -26,6 +26,9 @@ def _nhwc(x):
     (1, 80, 80, 64, 64, 9, 1, "prelu"),             # up_3
     (4, 10, 10, 256, 512, 1, 1, "none"),            # 1x1 projection
     (3, 20, 20, 1024, 256, 9, 1, "prelu"),          # up_1 (K = 9216)
+    (5, 20, 20, 512, 512, 9, 4, "residual"),        # layer4.1 on a 160 px crop: border patches skip taps, odd patch count
+    (7, 15, 15, 512, 512, 9, 4, "relu"),            # ... 120 px crop (3x3 patches)
+    (33, 10, 10, 256, 256, 9, 2, "relu"),           # ... layer3.1, two crop groups per patch position
 ])
 def test_conv_tc_vs_float64(B, H, W, Cin, Cout, taps, dil, extras):
     from densefusion_b200.encoder import PackedEncoder, _pack_conv
