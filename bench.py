@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("DF_PRECISION", "hybrid"), choices=["fp32", "3xtf32", "tf32", "hybrid"])
+    ap.add_argument("--precision", default=os.environ.get("DF_PRECISION", "hybrid"), choices=["fp32", "3xtf32", "tf32", "hybrid", "hybrid16"])
     ap.add_argument("--frames", type=int, default=32, help="frames (of 8 objects) per GPU per step")
     ap.add_argument("--chunk", type=int, default=128, help="crops per head chunk (measured 16: 21.7 ms, 32: 20.7, 64: 20.3, 128: 20.05 per step)")
     ap.add_argument("--no-graph", action="store_true")
@@ -235,8 +235,8 @@ def dominant_kernel_roofline(pipe, precision, peaks):
         peak_note = ("TF32 tcgen05 peak taken as half of the measured bf16 burst figure of MEASURED_PEAKS.json"
                      if "bf16_tflops" in peaks else "TF32 = half of the fallback 1.59 PFLOP/s bf16")
         bound = "tensor"
-        kname = "gemm_tc_q_kernel<2,2> (tcgen05.mma.cta_group::2 kind::tf32%s, TMA operands, %s)" % (
-            " + kind::f16 bf16 corrections" if precision == "hybrid" else "", precision)
+        kinds = {"hybrid": "kind::tf32 + kind::f16 bf16 corrections", "hybrid16": "kind::f16: fp16 main term + bf16 corrections"}
+        kname = "gemm_tc_q_kernel<2,2> (tcgen05.mma.cta_group::2 %s, TMA operands, %s)" % (kinds.get(precision, "kind::tf32"), precision)
     ach = flops / (ms * 1e-3) / 1e12
     shape = f"M={rows} N=1920 K=384"
     # what the library reaches on this GPU in single-pass TF32 (cuBLAS, 8192^3, best of 10): a measured TF32 ceiling next to
@@ -261,10 +261,10 @@ def dominant_kernel_roofline(pipe, precision, peaks):
         traffic = None
     return {"bound": bound, "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
             "traffic": traffic, "ms_per_launch": ms, "algorithmic_flops_per_launch": flops,
-            "frac_of_mode_ceiling": ({"3xtf32": 3.0, "hybrid": 2.0}.get(precision, 1.0) * ach / peak) if precision != "fp32" else None,
+            "frac_of_mode_ceiling": ({"3xtf32": 3.0, "hybrid": 2.0, "hybrid16": 1.5}.get(precision, 1.0) * ach / peak) if precision != "fp32" else None,
             "l2": "operands + output of one launch (596 MB at the default chunk) exceed the 126 MB L2",
             "cublas_tf32_8192_tflops": tf32_lib, "frac_vs_cublas_tf32": (ach / tf32_lib) if tf32_lib else None,
-            "executed_over_algorithmic": {"3xtf32": 3.0, "hybrid": 2.0}.get(precision, 1.0), "peak_source": peak_note,
+            "executed_over_algorithmic": {"3xtf32": 3.0, "hybrid": 2.0, "hybrid16": 1.5}.get(precision, 1.0), "peak_source": peak_note,
             "shape": shape}
 
 
@@ -430,6 +430,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": {"fp32": "fp32", "hybrid": "fp32 (fp32-parity tensor-core GEMMs: TF32 main term + bf16 correction terms, fp32 accumulate)",
+                          "hybrid16": "fp32 (fp32-parity tensor-core GEMMs: fp16 main term + bf16 correction terms, fp32 accumulate)",
                           "3xtf32": "fp32 (fp32-parity tensor-core GEMMs: 3xTF32, fp32 accumulate)",
                           "tf32": "tf32 (single-pass tensor-core GEMMs, fp32 accumulate; looser bound)"}[args.precision],
                 "data": "synthetic",

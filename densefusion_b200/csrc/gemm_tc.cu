@@ -743,9 +743,10 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     } else {
                         tma_load_2d(&tm_a, dst, full + s, acol + kb * BK, c.row0);
                     }
-                    tma_load_2d(&tm_whi, dst + Q_TILE, full + s, kb * BK, wrow);
-                    // second weight tile: W_lo (fp32, 32 floats per row) or, hybrid, [bf16(W) x32 | bf16(W_lo) x32] = 64 bf16 per row
-                    if (p.precise) tma_load_2d(&tm_wlo, dst + Q_TILE + w_bytes, full + s, kb * (p.precise == 2 ? 2 * BK : BK), wrow);
+                    // first weight tile: 32 fp32 per row (TF32 hi part), or, hybrid16, [fp16(W) x32 | bf16(W) x32] = 64 halves per row
+                    tma_load_2d(&tm_whi, dst + Q_TILE, full + s, kb * (p.precise == 3 ? 2 * BK : BK), wrow);
+                    // second weight tile: W_lo (fp32), or [bf16(W) x32 | bf16(W_lo) x32] (hybrid), or [bf16(W_lo) x32 | 0] (hybrid16)
+                    if (p.precise) tma_load_2d(&tm_wlo, dst + Q_TILE + w_bytes, full + s, kb * (p.precise >= 2 ? 2 * BK : BK), wrow);
                 }
                 if (++cb == cblocks) { cb = 0; tap_list >>= 4; }
                 __syncwarp();
@@ -756,6 +757,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (rank == 0) {
             const uint32_t idesc = tf32_instr_desc(bnt, 128 * CTAS);
             const uint32_t idesc_bf = bf16_instr_desc(bnt, 128 * CTAS);
+            const uint32_t idesc_h = f16_instr_desc(bnt, 128 * CTAS);
             uint32_t it = 0, ti = 0;
             const int cblocks = p.conv_taps ? p.K / (BK * p.conv_taps) : 1;
             for (int t = cid; t < total_tiles; t += ncl) {
@@ -777,6 +779,26 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         const uint32_t w_hi = smem_u32(smem + (size_t)s * stage_bytes + Q_TILE);
                         const uint64_t bhi0 = sw128_desc(w_hi), blo0 = sw128_desc(w_hi + w_bytes);
                         const uint32_t a0 = tmem_base + TMEM_A0 + (it % A_STAGES) * 2 * BK;
+                        if (p.precise == 3) {
+                            // hybrid16: the main term on fp16 operands (11 significant bits like TF32, K = 16 per instruction:
+                            // half the tensor time), the two correction terms on bf16 as in the hybrid mode -- 2 + 4
+                            // instructions per k-block.  TMEM A stage: [0,16) fp16(a) pairs | [32,48) bf16(a) | [48,64)
+                            // bf16(a - fp16(a)); weight tile 1 rows: fp16(w) then bf16(w); tile 2 rows: bf16(w - fp16(w)).
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const uint64_t b_h = bhi0 + (uint64_t)(j * 2), b_w = bhi0 + (uint64_t)(4 + j * 2), b_wlo = blo0 + (uint64_t)(j * 2);
+                                const uint32_t acc_on = (kb != kb0) || (j != 0);
+                                if (CTAS == 2) {
+                                    umma_ts_bf16_pair(acc, a0 + j * 8, b_h, idesc_h, acc_on);
+                                    umma_ts_bf16_pair(acc, a0 + 48 + j * 8, b_w, idesc_bf, 1u);
+                                    umma_ts_bf16_pair(acc, a0 + 32 + j * 8, b_wlo, idesc_bf, 1u);
+                                } else {
+                                    umma_ts_bf16(acc, a0 + j * 8, b_h, idesc_h, acc_on);
+                                    umma_ts_bf16(acc, a0 + 48 + j * 8, b_w, idesc_bf, 1u);
+                                    umma_ts_bf16(acc, a0 + 32 + j * 8, b_wlo, idesc_bf, 1u);
+                                }
+                            }
+                        } else {
 #pragma unroll
                         for (int ks = 0; ks < BK / UMMA_K; ++ks) {
                             const uint64_t bhi = bhi0 + (uint64_t)(ks * 2), blo = blo0 + (uint64_t)(ks * 2);
@@ -789,6 +811,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                 umma_ts(acc, a_hi, bhi, idesc, acc_on);
                                 if (p.precise == 1) { umma_ts(acc, a_hi + BK, bhi, idesc, 1u); umma_ts(acc, a_hi, blo, idesc, 1u); }
                             }
+                        }
                         }
                         if (p.precise == 2) {
                             // hybrid: the two correction terms are ~2^-11 of the main one, so bf16 operands (K = 16 per
@@ -852,7 +875,20 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 const uint4 v = *reinterpret_cast<const uint4*>(arow + ((c ^ sw) << 4));
                 hi[c * 4 + 0] = v.x; hi[c * 4 + 1] = v.y; hi[c * 4 + 2] = v.z; hi[c * 4 + 3] = v.w;
             }
-            if (p.precise == 2) {
+            if (p.precise == 3) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float x0 = __uint_as_float(hi[2 * j]), x1 = __uint_as_float(hi[2 * j + 1]);
+                    const uint32_t h = pack_f16x2_sat(x0, x1);
+                    float f0, f1;
+                    unpack_f16x2(h, f0, f1);
+                    second[j] = pack_bf16x2(x0, x1);
+                    second[16 + j] = pack_bf16x2(x0 - f0, x1 - f1);
+                    hi[j] = h;                                     // (j <= 2j: the words read above are never overwritten early)
+                }
+#pragma unroll
+                for (int j = 16; j < 32; ++j) hi[j] = 0u;
+            } else if (p.precise == 2) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float x0 = __uint_as_float(hi[2 * j]), x1 = __uint_as_float(hi[2 * j + 1]);
@@ -1210,11 +1246,17 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
         if (!make_map_nhwc(&ma, p.A, p.cB, p.cH, p.cW, p.K / p.conv_taps, p.lda, p.TW, p.TH, p.TB)) return DF_ERR_UNSUPPORTED;
     } else if (!make_map(&ma, p.A, p.M, (int)a_cols, p.lda, 128)) return DF_ERR_UNSUPPORTED;
     const long long wrows = (long long)groups * p.N;
-    if (!make_map(&mhi, W_hi, wrows, p.K, ldw, bn_cta)) return DF_ERR_UNSUPPORTED;
-    if (p.precise == 2) {
-        if (ldw != p.K) return DF_ERR_UNSUPPORTED;                 // the packed pair tensor has the dense row pitch
-        if (!make_map_bf16_pairs(&mlo, W_lo, wrows, p.K, bn_cta)) return DF_ERR_UNSUPPORTED;
-    } else if (!make_map(&mlo, p.precise ? W_lo : W_hi, wrows, p.K, ldw, bn_cta)) return DF_ERR_UNSUPPORTED;
+    if (p.precise == 3) {                                          // hybrid16: both weight operands are packed 16-bit pair tensors
+        if (ldw != p.K) return DF_ERR_UNSUPPORTED;
+        if (!make_map_bf16_pairs(&mhi, W_hi, wrows, p.K, bn_cta) || !make_map_bf16_pairs(&mlo, W_lo, wrows, p.K, bn_cta))
+            return DF_ERR_UNSUPPORTED;
+    } else {
+        if (!make_map(&mhi, W_hi, wrows, p.K, ldw, bn_cta)) return DF_ERR_UNSUPPORTED;
+        if (p.precise == 2) {
+            if (ldw != p.K) return DF_ERR_UNSUPPORTED;             // the packed pair tensor has the dense row pitch
+            if (!make_map_bf16_pairs(&mlo, W_lo, wrows, p.K, bn_cta)) return DF_ERR_UNSUPPORTED;
+        } else if (!make_map(&mlo, p.precise ? W_lo : W_hi, wrows, p.K, ldw, bn_cta)) return DF_ERR_UNSUPPORTED;
+    }
     const int n_tiles = (p.N + bnt - 1) / bnt;
     const int total = m_tiles * n_tiles * groups;
     const int clusters = total < max_clusters ? total : max_clusters;
@@ -1280,6 +1322,29 @@ __global__ void pack_bf16_pairs_kernel(const float* __restrict__ w, uint32_t* __
     o[16 + j] = pack_bf16x2(l0, l1);
 }
 
+// hybrid16 mode: t1 = per row and k-block [fp16(w) x32 | bf16(w) x32], t2 = [bf16(w - fp16(w)) x32 | 0 x32]; fp16 saturates
+// at +-65504 and the remainder (as for values below fp16's normal range) moves into the correction term
+__global__ void pack_f16_pairs_kernel(const float* __restrict__ w, uint32_t* __restrict__ t1, uint32_t* __restrict__ t2,
+                                      long long rows, int K)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = rows * (K / 2);
+    if (i >= total) return;
+    const long long row = i / (K / 2);
+    const int kp = (int)(i - row * (K / 2));
+    const int kb = kp / 16, j = kp - kb * 16;
+    const float x0 = w[row * K + kb * 32 + 2 * j], x1 = w[row * K + kb * 32 + 2 * j + 1];
+    const uint32_t h = pack_f16x2_sat(x0, x1);
+    float f0, f1;
+    unpack_f16x2(h, f0, f1);
+    uint32_t* o1 = t1 + row * K + kb * 32;
+    uint32_t* o2 = t2 + row * K + kb * 32;
+    o1[j] = h;
+    o1[16 + j] = pack_bf16x2(x0, x1);
+    o2[j] = pack_bf16x2(x0 - f0, x1 - f1);
+    o2[16 + j] = 0u;
+}
+
 // Convolution weight (Cout, Cin, taps) -> GEMM operand (rows, taps*cols) tap-major, split for the tensor-core modes, in ONE
 // pass (training repacks every step).  rotate == 0: rows = Cout, cols = Cin (forward).  rotate == 1: rows = Cin, cols = Cout,
 // taps reversed -- the 180-degree rotated, in/out-transposed kernel of the data gradient.  One thread per two k.
@@ -1331,6 +1396,14 @@ extern "C" int df_pack_bf16_pairs(const float* w, void* out, long long rows, int
     DF_RETURN_LAST_ERROR();
 }
 
+extern "C" int df_pack_f16_pairs(const float* w, void* t1, void* t2, long long rows, int K, void* stream)
+{
+    if (!w || !t1 || !t2 || rows <= 0 || K <= 0 || K % 32) return DF_ERR_ARG;
+    const long long total = rows * (K / 2);
+    pack_f16_pairs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, (uint32_t*)t1, (uint32_t*)t2, rows, K);
+    DF_RETURN_LAST_ERROR();
+}
+
 extern "C" int df_split_tf32(const float* x, float* hi, float* lo, long long n, void* stream)
 {
     if (!x || !hi || !lo || n <= 0) return DF_ERR_ARG;
@@ -1344,7 +1417,7 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
                           long long c_group_stride, float* pool_partial, int precision, int variant, void* stream)
 {
     if (!A || !W_hi || (!C && !pool_partial)) return DF_ERR_ARG;
-    if (precision < 1 || precision > 3) return DF_ERR_ARG;
+    if (precision < 1 || precision > 4) return DF_ERR_ARG;
     if (precision != 2 && !W_lo) return DF_ERR_ARG;
     if (M <= 0 || N <= 0 || K <= 0 || groups <= 0) return DF_ERR_ARG;
     if (K % BK || lda % 4 || ldw % 4 || N % 4 || a_group_stride % 4 || bias_group_stride % 4) return DF_ERR_ARG;
@@ -1357,7 +1430,7 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
     TcParams p = {};
     p.A = A; p.lda = lda; p.bias = bias; p.bias_crop_stride = bias_crop_stride;
     p.C = pool_partial ? nullptr : C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.relu = relu;
-    p.precise = precision == 1 ? 1 : (precision == 3 ? 2 : 0);     // kernel-side: 0 single TF32, 1 3xTF32, 2 hybrid
+    p.precise = precision == 1 ? 1 : (precision == 3 ? 2 : (precision == 4 ? 3 : 0));     // kernel-side: 0 single TF32, 1 3xTF32, 2 hybrid, 3 hybrid16
     p.rows_per_crop = rows_per_crop > 0 ? rows_per_crop : M;
     p.a_gs = a_group_stride; p.bias_gs = bias_group_stride; p.c_gs = c_group_stride;
     p.pool_partial = pool_partial;
@@ -1378,7 +1451,7 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
         }
         v = 4;                                   // auto mode: shapes the TMA-A form cannot address fall back to kernel 4
     }
-    if (precision == 3) return DF_ERR_UNSUPPORTED;       // the hybrid mode exists in the generation-2 kernels only
+    if (precision >= 3) return DF_ERR_UNSUPPORTED;       // the hybrid modes exist in the generation-2 kernels only
     const int bn = v == 2 ? 256 : 128;
     if (v == 2 && groups > 1 && N % 256) return DF_ERR_UNSUPPORTED;
     CUtensorMap mhi, mlo;
@@ -1403,7 +1476,7 @@ extern "C" int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx,
                           int act, float* Y, int ldy, int Cout, int precision, void* stream)
 {
     if (!X || !W_hi || !Y || B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return DF_ERR_ARG;
-    if (precision < 1 || precision > 3) return DF_ERR_ARG;
+    if (precision < 1 || precision > 4) return DF_ERR_ARG;
     if (precision != 2 && !W_lo) return DF_ERR_ARG;
     if ((taps != 1 && taps != 9) || dilation < 1 || act < 0 || act > 2 || (act == 2 && !prelu)) return DF_ERR_ARG;
     if (Cin % BK || Cout % 4 || ldx % 4 || ldy % 4 || ldx < Cin || ldy < Cout || (residual && (ldr % 4 || ldr < Cout))) return DF_ERR_ARG;
@@ -1415,7 +1488,7 @@ extern "C" int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx,
     TcParams p = {};
     p.A = X; p.lda = ldx; p.bias = bias; p.bias_crop_stride = 0; p.C = Y; p.ldc = ldy;
     p.M = B * H * W; p.N = Cout; p.K = taps * Cin; p.relu = act;
-    p.precise = precision == 1 ? 1 : (precision == 3 ? 2 : 0);
+    p.precise = precision == 1 ? 1 : (precision == 3 ? 2 : (precision == 4 ? 3 : 0));
     p.rows_per_crop = p.M; p.a_gs = 0; p.bias_gs = 0; p.c_gs = 0; p.pool_partial = nullptr; p.tiles_per_crop = 0;
     p.conv_taps = taps; p.conv_dil = dilation; p.cW = W; p.cH = H; p.cB = B;
     p.residual = residual; p.ldr = ldr; p.prelu = prelu;

@@ -211,6 +211,22 @@ __device__ __forceinline__ uint32_t bf16_instr_desc(int n, int m = 128)
     // c_format F32 (1) @4, a/b format BF16 (1) @7/@10, K-major both, N>>3 @17, M>>4 @24
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+__device__ __forceinline__ uint32_t f16_instr_desc(int n, int m = 128)
+{
+    // kind::f16 with fp16 operands: c_format F32 (1) @4, a/b format F16 (0) @7/@10
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// two fp32 -> packed fp16x2, round to nearest even, saturating at +-65504 (no infinities): `lo` in bits 0-15
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi)
+{
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void unpack_f16x2(uint32_t v, float& lo, float& hi)
+{
+    asm("{ .reg .b16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h; }" : "=f"(lo), "=f"(hi) : "r"(v));
+}
 // two fp32 -> packed bf16x2 (round to nearest even): `lo` in bits 0-15 (the lower k index), `hi` in bits 16-31
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
 {

@@ -127,9 +127,9 @@ class PackedEncoder:
         ldx = x.stride(2) if ldx is None else ldx
         cout = out.shape[3] if cout is None else cout
         ldy = out.stride(2) if ldy is None else ldy
-        if mode == 3 and cout <= 64 and _NARROW_ON_3XTF32:
+        if mode >= 3 and cout <= 64 and _NARROW_ON_3XTF32:
             mode = 1        # 64-wide tiles are paced by the A stagers, where the hybrid split costs more (measured +9%)
-        hi, lo = w.pairs() if mode == 3 else w.split()
+        hi, lo = w.operands(mode)
         check(lib.df_conv_tc(ptr(x), b, h, wd, cin, ldx, ptr(hi), ptr(lo), taps, dil, ptr(bias), ptr(residual),
                              0 if residual is None else residual.stride(2), ptr(prelu), act, ptr(out), ldy, cout, mode,
                              stream()), "df_conv_tc")
@@ -167,7 +167,7 @@ class PackedEncoder:
         s = stream()
         check(lib.df_enc_gather_up_patches(ptr(x), ptr(choose), ptr(patches), b, n, h, w, 64, s), "df_enc_gather_up_patches")
         up = self.ups[2]
-        hi, lo = up["w"].pairs() if mode == 3 else up["w"].split()
+        hi, lo = up["w"].operands(mode)
         # the gathered patches as a 1 x rows "image" with 576 channels: a 1-tap convolution = GEMM with the PReLU epilogue
         check(lib.df_conv_tc(ptr(patches), 1, 1, rows, 576, 576, ptr(hi), ptr(lo), 1, 1, ptr(up["b"]), None, 0, ptr(up["a"]),
                              2, ptr(act), 64, 64, mode, s), "df_conv_tc")
@@ -177,8 +177,8 @@ class PackedEncoder:
 
     def _trunk(self, img: torch.Tensor, precision: str, stages: int):
         """Everything up to and including `stages` of the three up-sampling stages.  Returns (activation, workspace, mode)."""
-        if precision not in ("3xtf32", "tf32", "hybrid"):
-            raise ValueError("the tensor-core encoder runs in '3xtf32' / 'hybrid' (fp32 parity) or 'tf32'")
+        if precision not in ("3xtf32", "tf32", "hybrid", "hybrid16"):
+            raise ValueError("the tensor-core encoder runs in '3xtf32' / 'hybrid' / 'hybrid16' (fp32 parity) or 'tf32'")
         mode = ops.PRECISIONS[precision]
         img = ops.f32c(img)
         b, _, H, W = img.shape

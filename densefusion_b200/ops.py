@@ -13,7 +13,7 @@ from ._C import check, f32c, i64c, lib, need_cuda, ptr, stream
 
 # "hybrid": TF32 main term + the two ~2^-11 correction terms in bf16 (8 instead of 12 MMAs per k-block), fp32-parity like
 # "3xtf32"; generation-2 tensor-core kernels only
-PRECISIONS = {"fp32": 0, "3xtf32": 1, "tf32": 2, "hybrid": 3}
+PRECISIONS = {"fp32": 0, "3xtf32": 1, "tf32": 2, "hybrid": 3, "hybrid16": 4}
 
 
 def sym_mask(sym_list: Iterable[int]) -> int:
@@ -116,11 +116,27 @@ def loss_backward(pred_r, pred_c, st: LossState, g_loss, g_dis, w: float):
 # ---- K1 / K2 building blocks ------------------------------------------------------------------
 class SplitWeight:
     """A torch (N,K) [or stacked (G,N,K)] weight with its TF32 hi/lo halves for the tensor-core path."""
-    __slots__ = ("w", "hi", "lo", "bf")
+    __slots__ = ("w", "hi", "lo", "bf", "h16")
 
     def __init__(self, w: torch.Tensor):
         self.w = f32c(w.detach())
-        self.hi = self.lo = self.bf = None
+        self.hi = self.lo = self.bf = self.h16 = None
+
+    def operands(self, mode: int):
+        """The two weight operands df_gemm_tc / df_conv_tc expect for a PRECISIONS code (1 3xtf32, 2 tf32, 3 hybrid, 4 hybrid16)."""
+        return self.pairs16() if mode == 4 else (self.pairs() if mode == 3 else self.split())
+
+    def pairs16(self):
+        """The two packed 16-bit tensors of the hybrid16 mode ([fp16(w) | bf16(w)] and [bf16(w - fp16(w)) | 0] per k-block)."""
+        if self.h16 is None:
+            need_cuda(self.w)
+            K = self.w.shape[-1]
+            rows = self.w.numel() // K
+            t1 = torch.empty(rows, K, device=self.w.device, dtype=torch.float32)
+            t2 = torch.empty(rows, K, device=self.w.device, dtype=torch.float32)
+            check(lib.df_pack_f16_pairs(ptr(self.w), ptr(t1), ptr(t2), rows, K, stream()), "df_pack_f16_pairs")
+            self.h16 = (t1, t2)
+        return self.h16
 
     def pairs(self):
         """hi (TF32-exact fp32) and the packed bf16 pair tensor of the hybrid mode (same byte size as the weight)."""
@@ -157,7 +173,7 @@ def gemm(A, W, bias, C, *, M, N, K, lda, ldw, ldc, relu, precision="fp32", bias_
     mode = PRECISIONS[precision]
     sw = W if isinstance(W, SplitWeight) else None
     if mode != 0 and sw is not None and tc_eligible(M, N, K) and (groups == 1 or w_gs == N * ldw):
-        hi, lo = sw.pairs() if mode == 3 else sw.split()
+        hi, lo = sw.operands(mode)
         st = lib.df_gemm_tc(ptr(A), lda, ptr(hi), ptr(lo), ldw, ptr(bias), bias_crop_stride, ptr(C), ldc, M, N, K,
                             1 if relu else 0, rows_per_crop, groups, a_gs, bias_gs, c_gs, ptr(pool_partial), mode,
                             TC_VARIANT, stream())

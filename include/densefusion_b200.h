@@ -100,6 +100,12 @@ int df_split_tf32(const float* x, float* hi, float* lo, long long n, void* strea
  * 8 MMA instructions per 32-wide k-block instead of 12, same fp32-parity bound.  W_lo then points to the packed pair
  * tensor made by df_pack_bf16_pairs: per row and k-block 64 bf16 = [bf16(w) x32 | bf16(w - tf32(w)) x32]; needs ldw == K. */
 int df_pack_bf16_pairs(const float* w, void* out, long long rows, int K, void* stream);
+/* precision 4 ("hybrid16", same kernels): the main term on fp16 operands (11 significant bits like TF32, but K = 16 per
+ * instruction: half the tensor time) plus the same two bf16 correction terms -- 6 instructions per k-block.  fp16 saturates at
+ * +-65504 and flushes below 6e-8; what it drops is carried exactly by the correction terms (a - fp16(a) in bf16), so the bound
+ * stays 2^-20 per product.  W_hi / W_lo then point to the two packed tensors made by df_pack_f16_pairs: per row and k-block
+ * t1 = [fp16(w) x32 | bf16(w) x32], t2 = [bf16(w - fp16(w)) x32 | 0 x32] (each the byte size of the weight); needs ldw == K. */
+int df_pack_f16_pairs(const float* w, void* t1, void* t2, long long rows, int K, void* stream);
 /* torch convolution weight (Cout,Cin,kh,kw) -> (rows, taps*cols) tap-major GEMM operand split for the tensor-core modes in
  * one pass: hi always, lo (3xTF32) and / or pairs (hybrid).  rotate = 1: the data-gradient kernel (rows = Cin, taps reversed). */
 int df_pack_conv_weight(const float* w, float* hi, float* lo, void* pairs, int Cout, int Cin, int taps, int rotate, void* stream);

@@ -21,7 +21,7 @@ def _variants(default):
 
 
 # stated bounds per arithmetic mode (max-abs error / max-abs value)
-TOL = {"fp32": 1e-4, "3xtf32": 1e-4, "hybrid": 1e-4, "tf32": 5e-3}
+TOL = {"fp32": 1e-4, "3xtf32": 1e-4, "hybrid": 1e-4, "hybrid16": 1e-4, "tf32": 5e-3}
 
 
 def _ref_linear(x, w, b, relu):
@@ -40,15 +40,15 @@ def test_gemm_fp32_vs_float64(M, N, K):
 
 
 @pytest.mark.parametrize("variant", _variants([3, 1, 2, 4, 5, 6, 7]))
-@pytest.mark.parametrize("precision", ["3xtf32", "tf32", "hybrid"])
+@pytest.mark.parametrize("precision", ["3xtf32", "tf32", "hybrid", "hybrid16"])
 def test_gemm_tensor_core_variants(variant, precision):
     """variant 3: A staged through shared memory; 1/2: A through TMEM with N tile 128/256; 4: persistent kernel;
     5: persistent with the A operand by TMA; 6: the same on CTA pairs (cta_group::2, 256-row tiles)."""
     from densefusion_b200 import ops
     g = torch.Generator().manual_seed(variant)
     M, N, K = 1000, 512, 384
-    if precision == "hybrid" and variant < 5:
-        pytest.skip("the hybrid mode exists in the generation-2 kernels (variants 5-7) only")
+    if precision.startswith("hybrid") and variant < 5:
+        pytest.skip("the hybrid modes exist in the generation-2 kernels (variants 5-7) only")
     x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
     ops.TC_VARIANT = variant
     try:
@@ -150,7 +150,7 @@ def test_gemm_tensor_core_epilogues_match_fp32_kernel(variant):
     assert rel(run("3xtf32", conv5), conv5("fp32")) < 1e-5
 
 
-@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "tf32", "hybrid"])
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "tf32", "hybrid", "hybrid16"])
 @pytest.mark.parametrize("n,o,B", [(500, 21, 3), (1000, 13, 2)])
 def test_head_vs_oracle(precision, n, o, B):
     est, _, est_sd, _ = build_nets(n, o, seed=5)
