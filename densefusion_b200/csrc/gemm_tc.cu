@@ -714,7 +714,8 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (warp == 0) {
         // ------------------------------- TMA producer -------------------------------
         const uint32_t a_bytes = p.conv_taps ? (uint32_t)(p.TW * p.TH * p.TB) * BK * 4 : (uint32_t)Q_TILE;
-        const uint32_t bytes = a_bytes + (p.precise ? 2u : 1u) * w_bytes;      // 3xTF32: W_hi + W_lo; hybrid: W_hi + bf16 pair tile
+        // 3xTF32: W_hi + W_lo; hybrid: W_hi + bf16 pair tile; hybrid16: pair tile + a half-width (64 B rows) correction tile
+        const uint32_t bytes = a_bytes + (p.precise == 3 ? w_bytes + w_bytes / 2 : (p.precise ? 2u : 1u) * w_bytes);
         const int cblocks = p.conv_taps ? p.K / (BK * p.conv_taps) : 1;        // 32-channel blocks per tap
         uint32_t it = 0;
         for (int t = cid; t < total_tiles; t += ncl) {
@@ -745,8 +746,8 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     }
                     // first weight tile: 32 fp32 per row (TF32 hi part), or, hybrid16, [fp16(W) x32 | bf16(W) x32] = 64 halves per row
                     tma_load_2d(&tm_whi, dst + Q_TILE, full + s, kb * (p.precise == 3 ? 2 * BK : BK), wrow);
-                    // second weight tile: W_lo (fp32), or [bf16(W) x32 | bf16(W_lo) x32] (hybrid), or [bf16(W_lo) x32 | 0] (hybrid16)
-                    if (p.precise) tma_load_2d(&tm_wlo, dst + Q_TILE + w_bytes, full + s, kb * (p.precise >= 2 ? 2 * BK : BK), wrow);
+                    // second weight tile: W_lo (fp32), or [bf16(W) x32 | bf16(W_lo) x32] (hybrid), or bf16(W_lo) x32 in 64-byte rows (hybrid16)
+                    if (p.precise) tma_load_2d(&tm_wlo, dst + Q_TILE + w_bytes, full + s, kb * (p.precise == 2 ? 2 * BK : BK), wrow);
                 }
                 if (++cb == cblocks) { cb = 0; tap_list >>= 4; }
                 __syncwarp();
@@ -783,10 +784,11 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             // hybrid16: the main term on fp16 operands (11 significant bits like TF32, K = 16 per instruction:
                             // half the tensor time), the two correction terms on bf16 as in the hybrid mode -- 2 + 4
                             // instructions per k-block.  TMEM A stage: [0,16) fp16(a) pairs | [32,48) bf16(a) | [48,64)
-                            // bf16(a - fp16(a)); weight tile 1 rows: fp16(w) then bf16(w); tile 2 rows: bf16(w - fp16(w)).
+                            // bf16(a - fp16(a)); weight tile 1 rows: fp16(w) then bf16(w); tile 2 (64-byte rows, 64B swizzle): bf16(w - fp16(w)).
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
-                                const uint64_t b_h = bhi0 + (uint64_t)(j * 2), b_w = bhi0 + (uint64_t)(4 + j * 2), b_wlo = blo0 + (uint64_t)(j * 2);
+                                const uint64_t b_h = bhi0 + (uint64_t)(j * 2), b_w = bhi0 + (uint64_t)(4 + j * 2);
+                                const uint64_t b_wlo = sw64_desc(w_hi + w_bytes) + (uint64_t)(j * 2);
                                 const uint32_t acc_on = (kb != kb0) || (j != 0);
                                 if (CTAS == 2) {
                                     umma_ts_bf16_pair(acc, a0 + j * 8, b_h, idesc_h, acc_on);
@@ -1157,6 +1159,20 @@ bool make_map_bf16_pairs(CUtensorMap* map, const void* base, long long rows, int
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// hybrid16 mode, second operand: K bf16 per weight row (bf16(w - fp16(w))); box = 32 bf16 (64 B) x box_rows, 64B swizzle
+bool make_map_bf16_rows64(CUtensorMap* map, const void* base, long long rows, int K, int box_rows)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // NHWC image (B, H, W, C) with pixel pitch `ld` floats as a 4-D tensor; box = 32 channels x TW x TH x TB pixels
 bool make_map_nhwc(CUtensorMap* map, const float* base, int B, int H, int W, int C, int ld, int TW, int TH, int TB)
 {
@@ -1248,7 +1264,7 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
     const long long wrows = (long long)groups * p.N;
     if (p.precise == 3) {                                          // hybrid16: both weight operands are packed 16-bit pair tensors
         if (ldw != p.K) return DF_ERR_UNSUPPORTED;
-        if (!make_map_bf16_pairs(&mhi, W_hi, wrows, p.K, bn_cta) || !make_map_bf16_pairs(&mlo, W_lo, wrows, p.K, bn_cta))
+        if (!make_map_bf16_pairs(&mhi, W_hi, wrows, p.K, bn_cta) || !make_map_bf16_rows64(&mlo, W_lo, wrows, p.K, bn_cta))
             return DF_ERR_UNSUPPORTED;
     } else {
         if (!make_map(&mhi, W_hi, wrows, p.K, ldw, bn_cta)) return DF_ERR_UNSUPPORTED;
@@ -1322,7 +1338,7 @@ __global__ void pack_bf16_pairs_kernel(const float* __restrict__ w, uint32_t* __
     o[16 + j] = pack_bf16x2(l0, l1);
 }
 
-// hybrid16 mode: t1 = per row and k-block [fp16(w) x32 | bf16(w) x32], t2 = [bf16(w - fp16(w)) x32 | 0 x32]; fp16 saturates
+// hybrid16 mode: t1 = per row and k-block [fp16(w) x32 | bf16(w) x32], t2 = bf16(w - fp16(w)) row-major (rows, K); fp16 saturates
 // at +-65504 and the remainder (as for values below fp16's normal range) moves into the correction term
 __global__ void pack_f16_pairs_kernel(const float* __restrict__ w, uint32_t* __restrict__ t1, uint32_t* __restrict__ t2,
                                       long long rows, int K)
@@ -1337,12 +1353,9 @@ __global__ void pack_f16_pairs_kernel(const float* __restrict__ w, uint32_t* __r
     const uint32_t h = pack_f16x2_sat(x0, x1);
     float f0, f1;
     unpack_f16x2(h, f0, f1);
-    uint32_t* o1 = t1 + row * K + kb * 32;
-    uint32_t* o2 = t2 + row * K + kb * 32;
-    o1[j] = h;
-    o1[16 + j] = pack_bf16x2(x0, x1);
-    o2[j] = pack_bf16x2(x0 - f0, x1 - f1);
-    o2[16 + j] = 0u;
+    t1[row * K + kb * 32 + j] = h;
+    t1[row * K + kb * 32 + 16 + j] = pack_bf16x2(x0, x1);
+    t2[i] = pack_bf16x2(x0 - f0, x1 - f1);                       // plain row-major bf16 (rows, K)
 }
 
 // Convolution weight (Cout, Cin, taps) -> GEMM operand (rows, taps*cols) tap-major, split for the tensor-core modes, in ONE

@@ -137,6 +137,17 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr)
     return d;
 }
 
+// K-major tile of 64-byte rows, 64B-swizzled (TMA SWIZZLE_64B): 8-row groups are 512 B apart
+__device__ __forceinline__ uint64_t sw64_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+
 __device__ __forceinline__ uint32_t tf32_instr_desc(int n, int m = 128)
 {
     // c_format F32 (1) @4, a/b format TF32 (2) @7/@10, K-major both, N>>3 @17, M>>4 @24

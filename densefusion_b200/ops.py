@@ -127,13 +127,13 @@ class SplitWeight:
         return self.pairs16() if mode == 4 else (self.pairs() if mode == 3 else self.split())
 
     def pairs16(self):
-        """The two packed 16-bit tensors of the hybrid16 mode ([fp16(w) | bf16(w)] and [bf16(w - fp16(w)) | 0] per k-block)."""
+        """The two packed 16-bit tensors of the hybrid16 mode ([fp16(w) | bf16(w)] per k-block, and bf16(w - fp16(w)) row-major)."""
         if self.h16 is None:
             need_cuda(self.w)
             K = self.w.shape[-1]
             rows = self.w.numel() // K
             t1 = torch.empty(rows, K, device=self.w.device, dtype=torch.float32)
-            t2 = torch.empty(rows, K, device=self.w.device, dtype=torch.float32)
+            t2 = torch.empty(rows, K // 2, device=self.w.device, dtype=torch.float32)        # K bf16 per row
             check(lib.df_pack_f16_pairs(ptr(self.w), ptr(t1), ptr(t2), rows, K, stream()), "df_pack_f16_pairs")
             self.h16 = (t1, t2)
         return self.h16

@@ -104,7 +104,7 @@ int df_pack_bf16_pairs(const float* w, void* out, long long rows, int K, void* s
  * instruction: half the tensor time) plus the same two bf16 correction terms -- 6 instructions per k-block.  fp16 saturates at
  * +-65504 and flushes below 6e-8; what it drops is carried exactly by the correction terms (a - fp16(a) in bf16), so the bound
  * stays 2^-20 per product.  W_hi / W_lo then point to the two packed tensors made by df_pack_f16_pairs: per row and k-block
- * t1 = [fp16(w) x32 | bf16(w) x32], t2 = [bf16(w - fp16(w)) x32 | 0 x32] (each the byte size of the weight); needs ldw == K. */
+ * t1 = [fp16(w) x32 | bf16(w) x32] (the byte size of the weight), t2 = bf16(w - fp16(w)) row-major (half of it); needs ldw == K. */
 int df_pack_f16_pairs(const float* w, void* t1, void* t2, long long rows, int K, void* stream);
 /* torch convolution weight (Cout,Cin,kh,kw) -> (rows, taps*cols) tap-major GEMM operand split for the tensor-core modes in
  * one pass: hi always, lo (3xTF32) and / or pairs (hybrid).  rotate = 1: the data-gradient kernel (rows = Cin, taps reversed). */
