@@ -33,6 +33,7 @@ SIGNATURES = {
     "df_pack_bf16_pairs": [_p, _p, _ll, _i, _p],
     "df_pack_f16_pairs": [_p, _p, _p, _ll, _i, _p],
     "df_pack_conv_weight": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "df_pack_conv_weight16": [_p, _p, _p, _i, _i, _i, _i, _p],
     "df_gemm_dgrad_fp32": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _p, _i, _p],
     "df_gemm_wgrad_fp32": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _ll, _ll, _p],
     "df_reduce_partials": [_p, _i, _ll, _p, _i, _p],

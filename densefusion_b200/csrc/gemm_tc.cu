@@ -1387,7 +1387,42 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, float* __re
     }
 }
 
+// the same repacking for the hybrid16 mode: t1 = [fp16(w) x32 | bf16(w) x32] per k-block, t2 = bf16(w - fp16(w)) row-major
+__global__ void pack_conv_weight16_kernel(const float* __restrict__ w, uint32_t* __restrict__ t1, uint32_t* __restrict__ t2,
+                                          int Cout, int Cin, int taps, int rotate)
+{
+    const int rows = rotate ? Cin : Cout, cols = rotate ? Cout : Cin;
+    const int K = taps * cols;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)rows * (K / 2)) return;
+    const int row = (int)(i / (K / 2)), kp = (int)(i - (long long)row * (K / 2));
+    float x[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int k = kp * 2 + e, tap = k / cols, c = k - tap * cols;
+        x[e] = rotate ? w[((size_t)c * Cin + row) * taps + (taps - 1 - tap)] : w[((size_t)row * Cin + c) * taps + tap];
+    }
+    const uint32_t h = pack_f16x2_sat(x[0], x[1]);
+    float f0, f1;
+    unpack_f16x2(h, f0, f1);
+    const int kb = (kp * 2) / 32, j = kp - kb * 16;
+    t1[(size_t)row * K + kb * 32 + j] = h;
+    t1[(size_t)row * K + kb * 32 + 16 + j] = pack_bf16x2(x[0], x[1]);
+    t2[i] = pack_bf16x2(x[0] - f0, x[1] - f1);
+}
+
 }  // namespace
+
+extern "C" int df_pack_conv_weight16(const float* w, void* t1, void* t2, int Cout, int Cin, int taps, int rotate, void* stream)
+{
+    if (!w || !t1 || !t2 || Cout <= 0 || Cin <= 0 || taps <= 0) return DF_ERR_ARG;
+    const int cols = rotate ? Cout : Cin, rows = rotate ? Cin : Cout;
+    if ((taps * cols) % 32) return DF_ERR_ARG;
+    const long long total = (long long)rows * (taps * cols / 2);
+    pack_conv_weight16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, (uint32_t*)t1, (uint32_t*)t2, Cout,
+                                                                                            Cin, taps, rotate);
+    DF_RETURN_LAST_ERROR();
+}
 
 extern "C" int df_pack_conv_weight(const float* w, float* hi, float* lo, void* pairs, int Cout, int Cin, int taps, int rotate,
                                    void* stream)

@@ -2,7 +2,7 @@
 
 `conv2d(module, x)` stands in for `module(x)` inside lib/pspnet.py / lib/extractors.py.  For the stride-1 3x3 / 1x1
 convolutions with a multiple of 32 input channels (all but the three stride-2 layers) on CUDA with autograd on, forward
-and the data gradient run on df_conv_tc -- the implicit-GEMM tcgen05 kernel in the fp32-parity "hybrid" arithmetic:
+and the data gradient run on df_conv_tc -- the implicit-GEMM tcgen05 kernel in the fp32-parity "hybrid16" arithmetic:
     y  = conv(x, W)                  weights repacked (Cout, taps*Cin), split every call (they change every step)
     dx = conv(dy, rot180(W)^T)       same kernel, same padding / dilation (exact for stride 1)
 The weight gradient stays on the library (aten.convolution_backward, weight only) for now -- it is the one piece of the
@@ -18,7 +18,7 @@ from .. import ops
 from .._C import check, lib, ptr, stream
 
 ENABLED = True          # module switch (tests compare against the pure torch path)
-PRECISION = "hybrid"
+PRECISION = "hybrid16"
 
 
 def _nhwc(x: torch.Tensor) -> torch.Tensor:
@@ -33,6 +33,11 @@ def _pack(weight: torch.Tensor, rotate: bool, mode: int):
     rows, kt = (cin, k * k * cout) if rotate else (cout, k * k * cin)
     w = weight.detach().float().contiguous()
     hi = torch.empty(rows, kt, device=w.device, dtype=torch.float32)
+    if mode == 4:                                           # hybrid16: [fp16(w) | bf16(w)] per k-block and bf16(w - fp16(w))
+        second = torch.empty(rows, kt // 2, device=w.device, dtype=torch.float32)
+        check(lib.df_pack_conv_weight16(ptr(w), ptr(hi), ptr(second), cout, cin, k * k, 1 if rotate else 0, stream()),
+              "df_pack_conv_weight16")
+        return hi, second
     second = torch.empty(rows, kt, device=w.device, dtype=torch.float32)
     check(lib.df_pack_conv_weight(ptr(w), ptr(hi), ptr(second) if mode != 3 else None, ptr(second) if mode == 3 else None,
                                   cout, cin, k * k, 1 if rotate else 0, stream()), "df_pack_conv_weight")

@@ -44,10 +44,10 @@ def _w2(p):
     return p.detach().reshape(p.shape[0], -1).float().contiguous()
 
 
-# Arithmetic of the forward and data-gradient GEMMs: an fp32-parity tensor-core mode ("hybrid" / "3xtf32") or "fp32"
+# Arithmetic of the forward and data-gradient GEMMs: an fp32-parity tensor-core mode ("hybrid16" / "hybrid" / "3xtf32") or "fp32"
 # (exact FFMA).  Weight gradients (reductions over the rows) and everything too small for a 128-row MMA tile are always
 # exact fp32.
-PRECISION = "hybrid"
+PRECISION = "hybrid16"
 
 
 # ---- thin kernel wrappers ----------------------------------------------------------------------------------

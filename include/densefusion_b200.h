@@ -109,6 +109,8 @@ int df_pack_f16_pairs(const float* w, void* t1, void* t2, long long rows, int K,
 /* torch convolution weight (Cout,Cin,kh,kw) -> (rows, taps*cols) tap-major GEMM operand split for the tensor-core modes in
  * one pass: hi always, lo (3xTF32) and / or pairs (hybrid).  rotate = 1: the data-gradient kernel (rows = Cin, taps reversed). */
 int df_pack_conv_weight(const float* w, float* hi, float* lo, void* pairs, int Cout, int Cin, int taps, int rotate, void* stream);
+/* ... and for precision 4: the two packed tensors of df_pack_f16_pairs, from the torch convolution weight in one pass. */
+int df_pack_conv_weight16(const float* w, void* t1, void* t2, int Cout, int Cin, int taps, int rotate, void* stream);
 
 /* emb[b,c,n] = feat[b,c,choose[b,n]]  (lib/network.py:98-102).  feat is addressed with explicit element
  * strides so NCHW and channels-last encoders both work.  emb_pm (B*N,32) point-major and/or emb_cm

@@ -22,6 +22,9 @@ tail -c 3000 gpurun_out/bench_fp32.json; tail -n 5 gpurun_out/bench_fp32.err
 echo "== bench 3xtf32 =="
 timeout 900 python bench.py --precision 3xtf32 --steps 5 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/bench_3xtf32.json 2> gpurun_out/bench_3xtf32.err; echo "exit $?" >> gpurun_out/bench_3xtf32.err
 tail -c 1500 gpurun_out/bench_3xtf32.json; tail -n 5 gpurun_out/bench_3xtf32.err
-echo "== bench (default: hybrid) =="
+echo "== bench hybrid =="
+timeout 900 python bench.py --precision hybrid --steps 5 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/bench_hybrid.json 2> gpurun_out/bench_hybrid.err; echo "exit $?" >> gpurun_out/bench_hybrid.err
+tail -c 1500 gpurun_out/bench_hybrid.json; tail -n 5 gpurun_out/bench_hybrid.err
+echo "== bench (default: hybrid16) =="
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "exit $?" >> gpurun_out/bench_default.err
 tail -c 4000 gpurun_out/bench_default.json; tail -n 5 gpurun_out/bench_default.err

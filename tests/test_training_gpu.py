@@ -109,7 +109,7 @@ def torch_encoder():
     from densefusion_b200.lib import conv_tc
     conv_tc.ENABLED, training.PRECISION = False, "fp32"
     yield
-    conv_tc.ENABLED, training.PRECISION = True, "hybrid"
+    conv_tc.ENABLED, training.PRECISION = True, "hybrid16"
 
 
 # With the encoder's convolutions on the tensor cores (default) the features the head sees carry the 3e-5 embedding error
