@@ -1196,11 +1196,16 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
         if (order < 0) { const char* e = getenv("DF_TC_TILE_ORDER"); order = e ? atoi(e) : 0; }
         p.m_fastest = order;
     }
-    {   // accumulation runs of <= 18 k-blocks (K <= 576) once the chain is long enough to matter (see TcParams::k_chunks)
+    {   // accumulation runs once the chain is long enough to matter (see TcParams::k_chunks).  What grows the truncation bias
+        // is the number of MMA instructions chained on one accumulator, so the run length is set in instructions: <= 216
+        // (18 k-blocks of 3xTF32 at 12 per k-block, 27 of hybrid at 8, 36 of hybrid16 at 6).
+        static const int run_steps = getenv("DF_TC_RUN_STEPS") ? atoi(getenv("DF_TC_RUN_STEPS")) : 216;
+        const int per_kb = p.precise == 1 ? 12 : (p.precise == 2 ? 8 : 6);
+        const int run_kb = run_steps / per_kb > 0 ? run_steps / per_kb : 1;
         const int nkb = p.K / BK;
         p.k_chunks = 1; p.kbc = nkb;
-        if (p.precise && !p.pool_partial && nkb > 24) {
-            p.k_chunks = (nkb + 17) / 18;
+        if (p.precise && !p.pool_partial && nkb > run_kb + run_kb / 3) {
+            p.k_chunks = (nkb + run_kb - 1) / run_kb;
             p.kbc = (nkb + p.k_chunks - 1) / p.k_chunks;
             p.k_chunks = (nkb + p.kbc - 1) / p.kbc;
         }
