@@ -10,6 +10,6 @@ DF_NCU=1 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.s
 echo "launch list rc=$?"; wc -l gpurun_out/launches.csv
 python scripts/summarize_launches.py gpurun_out/launches.csv > gpurun_out/launch_list_step.json; head -c 1500 gpurun_out/launch_list_step.json
 timeout 200 python scripts/prof_kernels.py 3 > gpurun_out/plain_prof.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gemm_tc_q_kernel|loss_forward_kernel|knn1_d3_kernel' \
-    -c 8 -o gpurun_out/prof_kernels python scripts/prof_kernels.py 1 > gpurun_out/ncu_prof.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gemm_tc_q_kernel|upconv_finish_kernel|loss_forward_kernel|knn1_d3_kernel' \
+    -c 11 -o gpurun_out/prof_kernels python scripts/prof_kernels.py 1 > gpurun_out/ncu_prof.log 2>&1
 echo "full capture rc=$?"; ls -la gpurun_out/*.ncu-rep

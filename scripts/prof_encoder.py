@@ -7,6 +7,7 @@ from densefusion_b200 import ops, encoder as E
 from densefusion_b200._C import lib
 
 dev = torch.device("cuda", 0)
+precision = sys.argv[1] if len(sys.argv) > 1 else "hybrid16"
 est, ref, _, _ = bench.build_modules(dev)
 enc = E.PackedEncoder(est.cnn)
 records = []
@@ -34,17 +35,17 @@ def gemm(A, W, b, C, **k):
 
 E.PackedEncoder._conv = staticmethod(conv)
 ops.gemm = gemm
-for name in ("df_enc_im2col_conv1", "df_enc_maxpool", "df_enc_im2col_s2", "df_enc_pyramid_pool", "df_enc_pyramid_sum", "df_enc_upsample", "df_enc_log_softmax32"):
+for name in ("df_enc_im2col_conv1", "df_enc_maxpool", "df_enc_im2col_s2", "df_enc_pyramid_pool", "df_enc_pyramid_sum", "df_enc_upconv_finish", "df_enc_upsample", "df_enc_log_softmax32"):
     f = getattr(lib, name)
     setattr(lib, name, (lambda f, name: lambda *a: timed((name,), f, *a))(f, name))
 
 for b, hw in ((96, 80), (96, 120), (64, 160)):
     img = torch.randn(b, 3, hw, hw, device=dev)
     for _ in range(2):
-        enc.forward(img)
+        enc.forward(img, precision)
     torch.cuda.synchronize()
     records.clear()
-    enc.forward(img)
+    enc.forward(img, precision)
     torch.cuda.synchronize()
     tot = sum(e0.elapsed_time(e1) for _, e0, e1 in records)
     print(f"\n# bucket {b} x {hw}x{hw}: {tot:.3f} ms over {len(records)} launches")

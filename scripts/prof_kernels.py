@@ -33,13 +33,30 @@ def conv_case(B, H, W, Cin, Cout, dil, mode):
         PackedEncoder._conv(x, w, out, taps=9, dil=dil, act=1, mode=mode)
 
 
-# order == order of the cases in profiles/*_ncu_full_selected.csv
-gemm_case(rows, 1920, 384, "hybrid", percrop=True)        # 1 tower layer 1 at the bench's chunk, bench-default arithmetic (the roofline kernel)
-gemm_case(rows, 1920, 384, "3xtf32", percrop=True)        # 2 the same in 3xTF32
-gemm_case(rows, 1024, 512, "hybrid", pooled=True)         # 3 conv6 + pool
-conv_case(64, 40, 40, 1024, 256, 1, 3)                    # 4 up_1 convolution, 160x160 bucket (K = 9216, 16 accumulation runs), hybrid
-conv_case(64, 20, 20, 512, 512, 4, 3)                     # 5 layer4.1 convolution, dilation 4, hybrid
-conv_case(64, 80, 80, 256, 64, 1, 1)                      # 6 up_2 convolution (64 output channels: stays on 3xTF32)
+def finish_case(B, h, w, C):
+    from densefusion_b200._C import check, lib, ptr, stream
+    z = torch.randn(B, h, w, 9 * C, device=dev)
+    bias, slope = torch.randn(C, device=dev), torch.full((1,), 0.25, device=dev)
+    out = torch.empty(B, 2 * h, 2 * w, C, device=dev)
+    for _ in range(reps):
+        check(lib.df_enc_upconv_finish(ptr(z), 9 * C, ptr(bias), ptr(slope), ptr(out), C, B, h, w, C, stream()), "upconv_finish")
+
+
+# order == order of the cases in profiles/*_ncu_full_selected.csv (labels: CASES)
+CASES = ["tower1 M=64000 N=1920 K=384 per-crop bias, hybrid16 (bench roofline kernel)", "the same, hybrid", "the same, 3xtf32",
+         "conv6 M=64000 N=1024 K=512 pooled, hybrid16", "up_1 at the low resolution: GEMM M=25600 N=2304 K=1024, hybrid16",
+         "layer4.1 conv 3x3 dil 4 512->512 on 64x20x20 (tap skipping), hybrid16", "layer4.0 conv 3x3 dil 1 512->512 on 64x20x20, hybrid16",
+         "layer1 conv 3x3 64->64 on 64x40x40 (64 output channels: 3xTF32)", "up_1 finish: 9 shifted bilinear samples, 64x20x20 -> 64x40x40x256",
+         "ADD-S loss, 32 crops", "kNN R=500 Q=2e6"]
+gemm_case(rows, 1920, 384, "hybrid16", percrop=True)
+gemm_case(rows, 1920, 384, "hybrid", percrop=True)
+gemm_case(rows, 1920, 384, "3xtf32", percrop=True)
+gemm_case(rows, 1024, 512, "hybrid16", pooled=True)
+gemm_case(25600, 2304, 1024, "hybrid16")
+conv_case(64, 20, 20, 512, 512, 4, 4)
+conv_case(64, 20, 20, 512, 512, 1, 4)
+conv_case(64, 40, 40, 64, 64, 1, 1)
+finish_case(64, 20, 20, 256)
 # loss (ADD-S) and kNN at config C1 shapes (32 crops)
 g = torch.Generator().manual_seed(1)
 B = 32
@@ -56,3 +73,5 @@ for _ in range(reps):
     ops.knn(ref, qry, 1)
 torch.cuda.synchronize()
 print("ok")
+if len(sys.argv) > 2:
+    print("\n".join(CASES))
