@@ -647,9 +647,17 @@ def measure_extras(pipe, dev, args, peaks):
 
 if __name__ == "__main__":
     a = parse()
+    # stdout carries exactly ONE JSON line: while the bench runs, file descriptor 1 points at stderr, so anything a library
+    # writes to the process's stdout (NCCL prints its version banner there at every debug level >= VERSION) cannot precede it;
+    # Python's own print() goes to the real stdout through a separate handle.
+    sys.stdout.flush()
+    _real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_real, "w", buffering=1)
     if a.impl == "reference":
         run_reference(a)
     elif a.workload == "train":
         run_train(a)
     else:
         run_ours(a)
+    sys.stdout.flush()
