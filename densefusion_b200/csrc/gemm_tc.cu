@@ -56,6 +56,7 @@ struct TcParams {
     // of the chain (measured 3xTF32 error 3e-6 at K = 384 but 6.5e-5 at K = 9216); short chains keep long-K convolutions
     // at fp32-parity.  k_chunks == 1: plain single-run accumulation.
     int k_chunks, kbc;
+    int run_steps;                              // host side only: MMA instructions per accumulation run, 0 = default
     int m_fastest;                              // tile order of the persistent loop (q_decode).  Default 0 = n fastest: the clusters
                                                 // running at one time share activation rows; measured 12% faster at M = 64000 /
                                                 // K = 1536 than sharing the weight tile (env DF_TC_TILE_ORDER=1)
@@ -1199,7 +1200,10 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
     {   // accumulation runs once the chain is long enough to matter (see TcParams::k_chunks).  What grows the truncation bias
         // is the number of MMA instructions chained on one accumulator, so the run length is set in instructions: <= 216
         // (18 k-blocks of 3xTF32 at 12 per k-block, 27 of hybrid at 8, 36 of hybrid16 at 6).
-        static const int run_steps = getenv("DF_TC_RUN_STEPS") ? atoi(getenv("DF_TC_RUN_STEPS")) : 216;
+        // Inference default 216; the training path asks for 108 (precision bits 8..15): the truncation is a BIAS, which the
+        // sums over pixels of a weight gradient amplify (layer4.1.conv1 gradient error 9e-4 at 108, 5.9e-3 at 216, measured).
+        static const int env_steps = getenv("DF_TC_RUN_STEPS") ? atoi(getenv("DF_TC_RUN_STEPS")) : 216;
+        const int run_steps = p.run_steps > 0 ? p.run_steps : env_steps;
         const int per_kb = p.precise == 1 ? 12 : (p.precise == 2 ? 8 : 6);
         const int run_kb = run_steps / per_kb > 0 ? run_steps / per_kb : 1;
         const int nkb = p.K / BK;
@@ -1470,6 +1474,8 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
                           long long c_group_stride, float* pool_partial, int precision, int variant, void* stream)
 {
     if (!A || !W_hi || (!C && !pool_partial)) return DF_ERR_ARG;
+    const int run_units = (precision >> 8) & 0xff;                  // accumulation-run length in units of 12 MMA instructions
+    precision &= 0xff;
     if (precision < 1 || precision > 4) return DF_ERR_ARG;
     if (precision != 2 && !W_lo) return DF_ERR_ARG;
     if (M <= 0 || N <= 0 || K <= 0 || groups <= 0) return DF_ERR_ARG;
@@ -1484,6 +1490,7 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
     p.A = A; p.lda = lda; p.bias = bias; p.bias_crop_stride = bias_crop_stride;
     p.C = pool_partial ? nullptr : C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.relu = relu;
     p.precise = precision == 1 ? 1 : (precision == 3 ? 2 : (precision == 4 ? 3 : 0));     // kernel-side: 0 single TF32, 1 3xTF32, 2 hybrid, 3 hybrid16
+    p.run_steps = run_units * 12;
     p.rows_per_crop = rows_per_crop > 0 ? rows_per_crop : M;
     p.a_gs = a_group_stride; p.bias_gs = bias_group_stride; p.c_gs = c_group_stride;
     p.pool_partial = pool_partial;
@@ -1529,6 +1536,8 @@ extern "C" int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx,
                           int act, float* Y, int ldy, int Cout, int precision, void* stream)
 {
     if (!X || !W_hi || !Y || B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return DF_ERR_ARG;
+    const int run_units = (precision >> 8) & 0xff;
+    precision &= 0xff;
     if (precision < 1 || precision > 4) return DF_ERR_ARG;
     if (precision != 2 && !W_lo) return DF_ERR_ARG;
     if ((taps != 1 && taps != 9) || dilation < 1 || act < 0 || act > 2 || (act == 2 && !prelu)) return DF_ERR_ARG;
@@ -1542,6 +1551,7 @@ extern "C" int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx,
     p.A = X; p.lda = ldx; p.bias = bias; p.bias_crop_stride = 0; p.C = Y; p.ldc = ldy;
     p.M = B * H * W; p.N = Cout; p.K = taps * Cin; p.relu = act;
     p.precise = precision == 1 ? 1 : (precision == 3 ? 2 : (precision == 4 ? 3 : 0));
+    p.run_steps = run_units * 12;
     p.rows_per_crop = p.M; p.a_gs = 0; p.bias_gs = 0; p.c_gs = 0; p.pool_partial = nullptr; p.tiles_per_crop = 0;
     p.conv_taps = taps; p.conv_dil = dilation; p.cW = W; p.cH = H; p.cB = B;
     p.residual = residual; p.ldr = ldr; p.prelu = prelu;

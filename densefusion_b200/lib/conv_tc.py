@@ -26,9 +26,39 @@ def _nhwc(x: torch.Tensor) -> torch.Tensor:
     return x if x.is_contiguous(memory_format=torch.channels_last) and x.stride(1) == 1 else x.contiguous(memory_format=torch.channels_last)
 
 
+# Packed operands of the current optimiser step, keyed by (weight storage, rotate, mode).  The weights only change in the
+# optimiser, so inside one step (several crop-size buckets, forward + backward) every weight is packed once per form instead
+# of once per call.  Off by default: only the trainer, which knows where a step begins, switches it on (`weight_cache`).
+_cache = None
+
+
+class weight_cache:
+    """Context manager around ONE optimiser step's forward + backward: packed convolution weights are reused inside it."""
+
+    def __enter__(self):
+        global _cache
+        self.prev, _cache = _cache, {}
+        return self
+
+    def __exit__(self, *exc):
+        global _cache
+        _cache = self.prev
+        return False
+
+
 def _pack(weight: torch.Tensor, rotate: bool, mode: int):
     """(Cout,Cin,k,k) -> the split GEMM operand of the forward (rotate=False) or data-gradient (rotate=True) convolution,
-    one launch (the weights change every optimiser step, so this runs per call)."""
+    one launch (the weights change every optimiser step, so this runs per call unless a `weight_cache` is active)."""
+    if _cache is not None:
+        key = (weight.data_ptr(), tuple(weight.shape), rotate, mode)
+        hit = _cache.get(key)
+        if hit is None:
+            hit = _cache[key] = _pack_now(weight, rotate, mode)
+        return hit
+    return _pack_now(weight, rotate, mode)
+
+
+def _pack_now(weight: torch.Tensor, rotate: bool, mode: int):
     cout, cin, k, _ = weight.shape
     rows, kt = (cin, k * k * cout) if rotate else (cout, k * k * cin)
     w = weight.detach().float().contiguous()
@@ -49,7 +79,7 @@ def _launch(x, packed, bias, cout, taps, dil, mode):
     y = torch.empty(b, cout, h, w, device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
     hi, lo = packed
     check(lib.df_conv_tc(ptr(x), b, h, w, cin, cin, ptr(hi), ptr(lo), taps, dil, ptr(bias), None, 0, None, 0, ptr(y), cout,
-                         cout, mode, stream()), "df_conv_tc")
+                         cout, mode | ops.SHORT_RUNS, stream()), "df_conv_tc")
     return y
 
 

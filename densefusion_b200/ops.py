@@ -166,8 +166,11 @@ def tc_eligible(M: int, N: int, K: int) -> bool:
     return (M >= 256 or N * K >= 512 * 512) and K % 32 == 0 and K >= 64 and N % 64 == 0
 
 
+SHORT_RUNS = 9 << 8     # precision flag of df_gemm_tc / df_conv_tc: accumulation runs of 108 MMA instructions (training path)
+
+
 def gemm(A, W, bias, C, *, M, N, K, lda, ldw, ldc, relu, precision="fp32", bias_crop_stride=0, rows_per_crop=0,
-         groups=1, a_gs=0, w_gs=0, bias_gs=0, c_gs=0, pool_partial=None):
+         groups=1, a_gs=0, w_gs=0, bias_gs=0, c_gs=0, pool_partial=None, short_runs=False):
     """Raw strided GEMM launch on pre-allocated buffers (see df_gemm_fp32 / df_gemm_tc in the header).
     W: tensor or SplitWeight."""
     mode = PRECISIONS[precision]
@@ -175,8 +178,8 @@ def gemm(A, W, bias, C, *, M, N, K, lda, ldw, ldc, relu, precision="fp32", bias_
     if mode != 0 and sw is not None and tc_eligible(M, N, K) and (groups == 1 or w_gs == N * ldw):
         hi, lo = sw.operands(mode)
         st = lib.df_gemm_tc(ptr(A), lda, ptr(hi), ptr(lo), ldw, ptr(bias), bias_crop_stride, ptr(C), ldc, M, N, K,
-                            1 if relu else 0, rows_per_crop, groups, a_gs, bias_gs, c_gs, ptr(pool_partial), mode,
-                            TC_VARIANT, stream())
+                            1 if relu else 0, rows_per_crop, groups, a_gs, bias_gs, c_gs, ptr(pool_partial),
+                            mode | (SHORT_RUNS if short_runs else 0), TC_VARIANT, stream())
         check(st, "df_gemm_tc")
         return
     Wt = sw.w if sw is not None else W

@@ -19,6 +19,7 @@ from typing import Iterable, List, Optional, Sequence
 import torch
 
 from ._C import DFError, check, lib, ptr, stream
+from .lib import conv_tc
 
 ALIGN = 64          # floats; keeps every parameter view 256-byte aligned (float4 / TMA-able)
 
@@ -165,7 +166,8 @@ class DataParallelTrainer:
         arena = self.arena_est if self.phase == "estimator" else self.arena_ref
         arena.zero_grad()
         fn = self._local_estimator if self.phase == "estimator" else self._local_refiner
-        loss_sum, dis_sum = fn(buckets)
+        with conv_tc.weight_cache():             # every convolution weight is packed once per step, not once per bucket
+            loss_sum, dis_sum = fn(buckets)
         arena.all_reduce(self.group)
         arena.adam_step(self.lr)
         return {"loss_sum": loss_sum, "dis_sum": dis_sum}

@@ -53,7 +53,7 @@ PRECISION = "hybrid16"
 # ---- thin kernel wrappers ----------------------------------------------------------------------------------
 def _gemm(A, W, bias, C, **kw):
     if PRECISION != "fp32" and ops.tc_eligible(kw["M"], kw["N"], kw["K"]):
-        ops.gemm(A, ops.SplitWeight(W), bias, C, precision=PRECISION, **kw)
+        ops.gemm(A, ops.SplitWeight(W), bias, C, precision=PRECISION, short_runs=True, **kw)
     else:
         ops.gemm(A, W, bias, C, precision="fp32", **kw)
 
@@ -73,7 +73,7 @@ def _dgrad(dY, ldy, Wt, ldw, dX, ldx, M, N, K, groups=1, dy_gs=0, w_gs=0, dx_gs=
             and Wt.is_contiguous()):
         # tensor-core data gradient; the ReLU mask of the layer below is applied by a separate element-wise pass
         ops.gemm(dY, ops.SplitWeight(Wt), None, dX, M=M, N=N, K=K, lda=ldy, ldw=ldw, ldc=ldx, relu=False, precision=PRECISION,
-                 groups=groups, a_gs=dy_gs, w_gs=w_gs, c_gs=dx_gs)
+                 groups=groups, a_gs=dy_gs, w_gs=w_gs, c_gs=dx_gs, short_runs=True)
         if mask is not None:
             _mask_inplace(dX, mask, ldx, N * groups, M)
         return

@@ -106,6 +106,10 @@ int df_pack_bf16_pairs(const float* w, void* out, long long rows, int K, void* s
  * stays 2^-20 per product.  W_hi / W_lo then point to the two packed tensors made by df_pack_f16_pairs: per row and k-block
  * t1 = [fp16(w) x32 | bf16(w) x32] (the byte size of the weight), t2 = bf16(w - fp16(w)) row-major (half of it); needs ldw == K. */
 int df_pack_f16_pairs(const float* w, void* t1, void* t2, long long rows, int K, void* stream);
+/* Accumulation runs: long k loops are cut into runs on fresh accumulators, summed in fp32 through C (the tensor core
+ * truncates while accumulating; the bias grows with the number of chained instructions).  Default 216 MMA instructions per
+ * run; bits 8..15 of `precision` (df_gemm_tc and df_conv_tc) select another length in units of 12 instructions -- the
+ * training path passes 9 (108): weight gradients sum that bias over all pixels. */
 /* torch convolution weight (Cout,Cin,kh,kw) -> (rows, taps*cols) tap-major GEMM operand split for the tensor-core modes in
  * one pass: hi always, lo (3xTF32) and / or pairs (hybrid).  rotate = 1: the data-gradient kernel (rows = Cin, taps reversed). */
 int df_pack_conv_weight(const float* w, float* hi, float* lo, void* pairs, int Cout, int Cin, int taps, int rotate, void* stream);
