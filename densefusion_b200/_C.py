@@ -34,6 +34,8 @@ SIGNATURES = {
     "df_pack_f16_pairs": [_p, _p, _p, _ll, _i, _p],
     "df_pack_conv_weight": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
     "df_pack_conv_weight16": [_p, _p, _p, _i, _i, _i, _i, _p],
+    "df_conv_wgrad_tc": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
+    "df_conv_wgrad_scratch_floats": [_i, _i, _i, _i, _i, _i, _i],
     "df_gemm_dgrad_fp32": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _p, _i, _p],
     "df_gemm_wgrad_fp32": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _ll, _ll, _p],
     "df_reduce_partials": [_p, _i, _ll, _p, _i, _p],
@@ -77,13 +79,13 @@ def _load():
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing -> loud
         fn.argtypes = args
-        fn.restype = ctypes.c_int
+        fn.restype = ctypes.c_longlong if name == "df_conv_wgrad_scratch_floats" else ctypes.c_int
     return lib
 
 
 class _CountingLib:
     """Forwards to the CDLL and counts kernel-launching entry points (bench.py reports `gpu_launches`)."""
-    _NO_LAUNCH = ("df_abi_version", "df_features", "df_gemm_rows_per_pool_tile")
+    _NO_LAUNCH = ("df_abi_version", "df_features", "df_gemm_rows_per_pool_tile", "df_conv_wgrad_scratch_floats")
 
     def __init__(self, cdll):
         self._cdll = cdll

@@ -57,6 +57,10 @@ struct TcParams {
     // at fp32-parity.  k_chunks == 1: plain single-run accumulation.
     int k_chunks, kbc;
     int run_steps;                              // host side only: MMA instructions per accumulation run, 0 = default
+    // ---- weight-gradient form (df_conv_wgrad_tc): output column n = tap * wk_rows + ci multiplies row ci of the W operand
+    // read wk_shift[tap] elements further along k (a 3x3 tap is an offset in the zero-padded, flattened pixel axis) ----
+    int wk_rows;                                // 0: off
+    int wk_shift[9], wk_row0[9];                // per tap: k offset (a multiple of 4 elements: TMA boxes start 16-byte aligned) and first row
     int m_fastest;                              // tile order of the persistent loop (q_decode).  Default 0 = n fastest: the clusters
                                                 // running at one time share activation rows; measured 12% faster at M = 64000 /
                                                 // K = 1536 than sharing the weight tile (env DF_TC_TILE_ORDER=1)
@@ -721,7 +725,14 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         uint32_t it = 0;
         for (int t = cid; t < total_tiles; t += ncl) {
             const QTile c = q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, rank);
-            const int wrow = c.g * p.N + c.n0 + rank * bn_cta;
+            int wrow = c.g * p.N + c.n0 + rank * bn_cta;
+            int wk0 = 0;                                                       // k offset of the W operand (weight-gradient form)
+            if (p.wk_rows) {                                                   // groups = slices of the reduction axis (split-K)
+                wrow = c.n0 + rank * bn_cta;
+                const int tap = wrow / p.wk_rows;
+                wk0 = p.wk_shift[tap] + c.g * p.K;
+                wrow += p.wk_row0[tap] - tap * p.wk_rows;
+            }
             const int acol = (int)(c.g * p.a_gs);
             const int nkb_t = p.conv_taps ? __popc(c.taps) * cblocks : nkb;
             uint64_t tap_list = 0;                                              // the taps the pair visits, 4 bits each, in order
@@ -746,9 +757,9 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         tma_load_2d(&tm_a, dst, full + s, acol + kb * BK, c.row0);
                     }
                     // first weight tile: 32 fp32 per row (TF32 hi part), or, hybrid16, [fp16(W) x32 | bf16(W) x32] = 64 halves per row
-                    tma_load_2d(&tm_whi, dst + Q_TILE, full + s, kb * (p.precise == 3 ? 2 * BK : BK), wrow);
+                    tma_load_2d(&tm_whi, dst + Q_TILE, full + s, kb * (p.precise == 3 ? 2 * BK : BK) + wk0, wrow);
                     // second weight tile: W_lo (fp32), or [bf16(W) x32 | bf16(W_lo) x32] (hybrid), or bf16(W_lo) x32 in 64-byte rows (hybrid16)
-                    if (p.precise) tma_load_2d(&tm_wlo, dst + Q_TILE + w_bytes, full + s, kb * (p.precise == 2 ? 2 * BK : BK), wrow);
+                    if (p.precise) tma_load_2d(&tm_wlo, dst + Q_TILE + w_bytes, full + s, kb * (p.precise == 2 ? 2 * BK : BK) + wk0, wrow);
                 }
                 if (++cb == cblocks) { cb = 0; tap_list >>= 4; }
                 __syncwarp();
@@ -1247,6 +1258,8 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
     if (CTAS == 1) {
         bn_cta = 128;
         if (groups > 1 && p.N % 128) return DF_ERR_UNSUPPORTED;
+    } else if (p.wk_rows) {
+        bn_cta = 64;                                               // every CTA's half tile stays inside one tap (wk_rows % 64 == 0)
     } else {
         const int widths[4] = {256, 192, 128, 64};
         long long best = -1;
@@ -1270,8 +1283,10 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
     if (p.conv_taps) {
         if (!make_map_nhwc(&ma, p.A, p.cB, p.cH, p.cW, p.K / p.conv_taps, p.lda, p.TW, p.TH, p.TB)) return DF_ERR_UNSUPPORTED;
     } else if (!make_map(&ma, p.A, p.M, (int)a_cols, p.lda, 128)) return DF_ERR_UNSUPPORTED;
-    const long long wrows = (long long)groups * p.N;
-    if (p.precise == 3) {                                          // hybrid16: both weight operands are packed 16-bit pair tensors
+    const long long wrows = p.wk_rows ? (long long)p.wk_rows * (p.N / p.wk_rows == 9 ? 3 : 1) : (long long)groups * p.N;
+    if (p.wk_rows) {                                               // weight-gradient form: W spans every k slice (row length ldw)
+        if (!make_map(&mhi, W_hi, wrows, ldw, ldw, bn_cta) || !make_map(&mlo, W_lo, wrows, ldw, ldw, bn_cta)) return DF_ERR_UNSUPPORTED;
+    } else if (p.precise == 3) {                                   // hybrid16: both weight operands are packed 16-bit pair tensors
         if (ldw != p.K) return DF_ERR_UNSUPPORTED;
         if (!make_map_bf16_pairs(&mhi, W_hi, wrows, p.K, bn_cta) || !make_map_bf16_rows64(&mlo, W_lo, wrows, p.K, bn_cta))
             return DF_ERR_UNSUPPORTED;
@@ -1420,7 +1435,128 @@ __global__ void pack_conv_weight16_kernel(const float* __restrict__ w, uint32_t*
     t2[i] = pack_bf16x2(x[0] - f0, x[1] - f1);
 }
 
+// NHWC activation (B,H,W,C; pixel pitch ld) -> channel-major rows over the zero-padded, flattened pixel axis:
+// out[c][k] = padded input at flat position k, where position (b*(H+2d) + y+d)*Wp + x+d holds in[b,y,x,c] (Wp >= W+2d) and
+// everything else up to the row length Ppad is zero.  `copies` == 3 writes three planes (plane stride `plane`), plane kx read
+// (kx-1)*d positions further -- the horizontal tap offsets of a 3x3 weight gradient.  With `lo` every value is split for
+// 3xTF32 (out = TF32-exact part, lo = remainder).  32-pixel x 32-channel tiles (+ d pixels of halo on both sides) through
+// shared memory: reads run along the channels, writes along the pixels; the input is read once for all planes.
+__global__ void __launch_bounds__(256)
+cmajor_pad_kernel(const float* __restrict__ in, int ld, float* __restrict__ out, float* __restrict__ lo, int B, int H, int W,
+                  int C, int d, int Wp, int Ppad, int copies, long long plane)
+{
+    __shared__ float tile[40][33];                                 // 32 + 2 * 4 rows: dilation <= 4
+    const int Hp = H + 2 * d;
+    const int halo = copies == 3 ? d : 0;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32 + 2 * halo; j += 8) {
+        const int pp = p0 - halo + j, c = c0 + tx;
+        float v = 0.0f;
+        if (pp >= 0 && pp < B * Hp * Wp && c < C) {
+            const int x = pp % Wp - d, r = pp / Wp, y = r % Hp - d, b = r / Hp;
+            if (x >= 0 && x < W && y >= 0 && y < H) v = __ldg(in + (((size_t)b * H + y) * W + x) * ld + c);
+        }
+        tile[j][tx] = v;
+    }
+    __syncthreads();
+    if (p0 + tx >= Ppad) return;
+    for (int kx = 0; kx < copies; ++kx) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = c0 + ty + i * 8;
+            if (c >= C) continue;
+            const float v = tile[tx + kx * halo][ty + i * 8];
+            const size_t o = (size_t)kx * plane + (size_t)c * Ppad + p0 + tx;
+            if (lo) {
+                const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+                out[o] = h;
+                lo[o] = v - h;
+            } else {
+                out[o] = v;
+            }
+        }
+    }
+}
+
 }  // namespace
+
+// Weight gradient of a stride-1 3x3 (padding == dilation) or 1x1 convolution on the tensor cores:
+//   dW[co, tap*Cin + ci] = sum_p dY[p, co] * X[p + offset(tap), ci]
+// as ONE 3xTF32 GEMM whose reduction runs over the pixels: both operands are first rewritten channel-major over the
+// zero-padded, flattened pixel axis (cmajor_pad_kernel), where a tap is a plain offset along k -- the W-operand TMA box of
+// output-column block (tap, ci..) simply starts wk_shift[tap] elements further (out-of-range parts are zero-filled), and the
+// zero borders of dY make every product that would wrap into a neighbouring row or image vanish.
+// TMA boxes must start 16-byte aligned, so only offsets that are multiples of 4 elements can be taken at load time: the padded
+// row length Wp is rounded up to a multiple of 4 (vertical tap offsets (ky-1)*d*Wp), and the horizontal tap offset (kx-1)*d is
+// baked into three pre-shifted copies of X (rows kx*Cin + ci of the W operand).
+// Split-K: the reduction runs over thousands of pixels while the output (Cout x taps*Cin) is a few dozen tiles, so the pixel
+// axis is cut into S slices (GEMM groups: A column offset and W k offset g*Kg, partial outputs summed by df_reduce_partials in
+// fixed order) until about two waves of CTA pairs are busy.
+struct WgradGeom { int d, Wp, Ppad, S, Kg, copies; };
+
+static inline WgradGeom wgrad_geometry(int B, int H, int W, int Cin, int Cout, int taps, int dilation)
+{
+    WgradGeom g;
+    g.d = taps == 9 ? dilation : 0;
+    g.copies = taps == 9 ? 3 : 1;
+    g.Wp = taps == 9 ? (W + 2 * g.d + 3) / 4 * 4 : W;
+    const long long P = (long long)B * (H + 2 * g.d) * g.Wp;
+    const int nkb = (int)((P + 31) / 32);
+    const long long tiles = (long long)((Cout + 255) / 256) * ((taps * Cin + 127) / 128);
+    int S = (int)((148 + tiles - 1) / tiles);
+    if (S > nkb / 8) S = nkb / 8;
+    if (S < 1) S = 1;
+    const int kbs = (nkb + S - 1) / S;                 // k-blocks per slice
+    g.S = (nkb + kbs - 1) / kbs;
+    g.Kg = kbs * 32;
+    g.Ppad = g.S * g.Kg;
+    return g;
+}
+
+extern "C" long long df_conv_wgrad_scratch_floats(int B, int H, int W, int Cin, int Cout, int taps, int dilation)
+{
+    const WgradGeom g = wgrad_geometry(B, H, W, Cin, Cout, taps, dilation);
+    return (long long)g.Ppad * ((long long)Cout + 2LL * g.copies * Cin) + (g.S > 1 ? (long long)g.S * Cout * taps * Cin : 0);
+}
+
+extern "C" int df_conv_wgrad_tc(const float* X, int ldx, const float* dY, int ldy, int B, int H, int W, int Cin, int Cout, int taps,
+                                int dilation, float* scratch, float* dW, void* stream)
+{
+    if (!X || !dY || !scratch || !dW || B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return DF_ERR_ARG;
+    if ((taps != 1 && taps != 9) || dilation < 1 || Cin % 64 || Cout % 4 || ldx < Cin || ldy < Cout) return DF_ERR_ARG;
+    if (((uintptr_t)scratch & 15) || ((uintptr_t)dW & 15)) return DF_ERR_ARG;
+    if ((long long)B * (H + 2 * dilation) * (W + 2 * dilation + 3) >= (1LL << 30)) return DF_ERR_ARG;
+    const WgradGeom g = wgrad_geometry(B, H, W, Cin, Cout, taps, dilation);
+    const int d = g.d, Wp = g.Wp, Ppad = g.Ppad, copies = g.copies;
+    float* dyT = scratch;
+    float* xhi = dyT + (size_t)Cout * Ppad;
+    float* xlo = xhi + (size_t)copies * Cin * Ppad;
+    float* part = xlo + (size_t)copies * Cin * Ppad;                       // S partial outputs (S > 1)
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d > 4) return DF_ERR_UNSUPPORTED;                                  // (halo rows of the transpose tile)
+    cmajor_pad_kernel<<<dim3(Ppad / 32, (Cout + 31) / 32), 256, 0, s>>>(dY, ldy, dyT, nullptr, B, H, W, Cout, d, Wp, Ppad, 1, 0);
+    cmajor_pad_kernel<<<dim3(Ppad / 32, (Cin + 31) / 32), 256, 0, s>>>(X, ldx, xhi, xlo, B, H, W, Cin, d, Wp, Ppad, copies,
+                                                                     (long long)Cin * Ppad);
+
+    const long long out_floats = (long long)Cout * taps * Cin;
+    TcParams p = {};
+    p.A = dyT; p.lda = Ppad; p.bias = nullptr; p.bias_crop_stride = 0; p.C = g.S > 1 ? part : dW; p.ldc = taps * Cin;
+    p.M = Cout; p.N = taps * Cin; p.K = g.Kg; p.relu = 0; p.precise = 1;
+    p.rows_per_crop = p.M; p.a_gs = g.Kg; p.bias_gs = 0; p.c_gs = out_floats; p.pool_partial = nullptr; p.tiles_per_crop = 0;
+    p.wk_rows = Cin;
+    for (int t = 0; t < taps; ++t) {
+        p.wk_shift[t] = taps == 9 ? (t / 3 - 1) * d * Wp : 0;
+        p.wk_row0[t] = taps == 9 ? (t % 3) * Cin : 0;
+    }
+    int rc = launch_q<2, 2>(p, xhi, xlo, Ppad, g.S, s);
+    if (rc) return rc;
+    if (g.S > 1) {
+        rc = df_reduce_partials(part, g.S, out_floats, dW, 0, stream);
+        if (rc) return rc;
+    }
+    DF_RETURN_LAST_ERROR();
+}
 
 extern "C" int df_pack_conv_weight16(const float* w, void* t1, void* t2, int Cout, int Cin, int taps, int rotate, void* stream)
 {

@@ -5,8 +5,8 @@ convolutions with a multiple of 32 input channels (all but the three stride-2 la
 and the data gradient run on df_conv_tc -- the implicit-GEMM tcgen05 kernel in the fp32-parity "hybrid16" arithmetic:
     y  = conv(x, W)                  weights repacked (Cout, taps*Cin), split every call (they change every step)
     dx = conv(dy, rot180(W)^T)       same kernel, same padding / dilation (exact for stride 1)
-The weight gradient stays on the library (aten.convolution_backward, weight only) for now -- it is the one piece of the
-encoder's training step still served by cuDNN, next to the three stride-2 layers.  Activations are channels_last, i.e.
+    dW = dy^T x_shifted              df_conv_wgrad_tc: one 3xTF32 GEMM whose reduction runs over the zero-padded pixel axis
+Only the three stride-2 layers (and Cin < 64) still go to the library (aten.convolution / convolution_backward).  Activations are channels_last, i.e.
 physically the NHWC layout the kernel wants; all other encoder ops (pooling, resizing, PReLU, log-softmax) are torch ops
 that keep that layout."""
 from __future__ import annotations
@@ -18,6 +18,7 @@ from .. import ops
 from .._C import check, lib, ptr, stream
 
 ENABLED = True          # module switch (tests compare against the pure torch path)
+WGRAD_TC = True         # weight gradients on df_conv_wgrad_tc (3xTF32 GEMM over the pixels); False: aten.convolution_backward
 PRECISION = "hybrid16"
 
 
@@ -83,6 +84,18 @@ def _launch(x, packed, bias, cout, taps, dil, mode):
     return y
 
 
+def _wgrad_tc(x, dy, cout, cin, taps, dil):
+    """dW (Cout,Cin,k,k) from channels_last x (B,Cin,H,W) and dy (B,Cout,H,W): df_conv_wgrad_tc + the tap-major -> torch reorder."""
+    b, _, h, w = x.shape
+    n = int(lib.df_conv_wgrad_scratch_floats(b, h, w, cin, cout, taps, dil))
+    scratch = torch.empty(n, device=x.device, dtype=torch.float32)
+    out = torch.empty(cout, taps * cin, device=x.device, dtype=torch.float32)
+    check(lib.df_conv_wgrad_tc(ptr(x), cin, ptr(dy), cout, b, h, w, cin, cout, taps, dil, ptr(scratch), ptr(out), stream()),
+          "df_conv_wgrad_tc")
+    k = 3 if taps == 9 else 1
+    return out.view(cout, taps, cin).permute(0, 2, 1).reshape(cout, cin, k, k)
+
+
 class ConvTCFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, dilation):
@@ -104,7 +117,9 @@ class ConvTCFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             # data gradient = convolution of dy with the 180-degree rotated, in/out-transposed kernel
             dx = _launch(dy, _pack(weight, True, ctx.mode), None, cin, k * k, ctx.dilation, ctx.mode)
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and WGRAD_TC and cin % 64 == 0:
+            dw = _wgrad_tc(x, dy, cout, cin, k * k, ctx.dilation)
+        elif ctx.needs_input_grad[1]:
             pad = ctx.dilation * (k // 2)
             dw = torch.ops.aten.convolution_backward(dy, x, weight, None, [1, 1], [pad, pad], [ctx.dilation, ctx.dilation],
                                                      False, [0, 0], 1, [False, True, False])[1]

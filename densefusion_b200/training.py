@@ -58,7 +58,19 @@ def _gemm(A, W, bias, C, **kw):
         ops.gemm(A, W, bias, C, precision="fp32", **kw)
 
 
+WGRAD_TC = True         # weight gradients of the wide layers on df_conv_wgrad_tc (3xTF32 GEMM over the rows)
+
+
 def _wgrad(dY, ldy, X, ldx, M, N, K, groups=1, dy_gs=0, x_gs=0):
+    if WGRAD_TC and PRECISION != "fp32" and K % 64 == 0 and N % 4 == 0 and M >= 256:
+        # dW[g] (N,K) = dY[:, g]^T X[:, g]: the rows are the "pixels" of a 1x1 convolution's weight gradient
+        out = _f(groups, N, K, dev=dY.device)
+        n = int(lib.df_conv_wgrad_scratch_floats(1, 1, M, K, N, 1, 1))
+        scratch = _f(n, dev=dY.device)
+        for g in range(groups):
+            check(lib.df_conv_wgrad_tc(X.data_ptr() + 4 * g * x_gs, ldx, dY.data_ptr() + 4 * g * dy_gs, ldy, 1, 1, M, K, N, 1, 1,
+                                       ptr(scratch), ptr(out[g]), stream()), "df_conv_wgrad_tc")
+        return out
     splits = max(1, min(32, M // 256))
     part = _f(splits, groups, N, K, dev=dY.device)
     check(lib.df_gemm_wgrad_fp32(ptr(dY), ldy, ptr(X), ldx, ptr(part), M, N, K, groups, splits, dy_gs, x_gs, stream()),

@@ -115,6 +115,12 @@ int df_pack_f16_pairs(const float* w, void* t1, void* t2, long long rows, int K,
 int df_pack_conv_weight(const float* w, float* hi, float* lo, void* pairs, int Cout, int Cin, int taps, int rotate, void* stream);
 /* ... and for precision 4: the two packed tensors of df_pack_f16_pairs, from the torch convolution weight in one pass. */
 int df_pack_conv_weight16(const float* w, void* t1, void* t2, int Cout, int Cin, int taps, int rotate, void* stream);
+/* Weight gradient of a stride-1 3x3 (padding == dilation) / 1x1 convolution (training; replaces cuDNN's wgrad):
+ * dW (Cout, taps*Cin) tap-major = sum over pixels of dY (B,H,W,Cout; pitch ldy) x shifted X (B,H,W,Cin; pitch ldx), one 3xTF32
+ * GEMM over the zero-padded, flattened pixel axis.  Cin % 64 == 0; `scratch` holds df_conv_wgrad_scratch_floats() floats. */
+long long df_conv_wgrad_scratch_floats(int B, int H, int W, int Cin, int Cout, int taps, int dilation);
+int df_conv_wgrad_tc(const float* X, int ldx, const float* dY, int ldy, int B, int H, int W, int Cin, int Cout, int taps,
+                     int dilation, float* scratch, float* dW, void* stream);
 
 /* emb[b,c,n] = feat[b,c,choose[b,n]]  (lib/network.py:98-102).  feat is addressed with explicit element
  * strides so NCHW and channels-last encoders both work.  emb_pm (B*N,32) point-major and/or emb_cm

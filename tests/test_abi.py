@@ -10,7 +10,7 @@ from util import ROOT
 def header_functions():
     src = open(os.path.join(ROOT, "include", "densefusion_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\bint\s+(df_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(?:int|long long)\s+(df_\w+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol():

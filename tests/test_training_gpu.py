@@ -25,7 +25,13 @@ def test_backward_gemm_building_blocks_vs_float64():
     dY, X = torch.randn(M, N, generator=g).cuda(), torch.randn(M, K, generator=g).cuda()
     W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
     act = torch.randn(M, K, generator=g).cuda()
-    dW = T._wgrad(dY, N, X, K, M, N, K)[0]
+    dW = T._wgrad(dY, N, X, K, M, N, K)[0]                          # tensor-core path (3xTF32 GEMM over the rows, split-K)
+    assert rel(dW, _f64(dY).t() @ _f64(X)) < 1e-5
+    T.WGRAD_TC = False
+    try:
+        dW = T._wgrad(dY, N, X, K, M, N, K)[0]                      # exact-fp32 kernel
+    finally:
+        T.WGRAD_TC = True
     assert rel(dW, _f64(dY).t() @ _f64(X)) < 2e-6
     dX = torch.empty(M, K, device="cuda")
     T._dgrad(dY, N, W.t().contiguous(), N, dX, K, M, K, N, mask=act)
@@ -278,3 +284,37 @@ def test_graphed_train_step_equals_eager(phase):
         assert float((d > 2e-6).float().mean()) < 0.01
     finally:
         torch.backends.cudnn.deterministic = False
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,taps,dil", [
+    (3, 10, 10, 256, 512, 9, 4),        # layer4.1: dilation 4, taps reach over the padded borders
+    (2, 15, 15, 128, 64, 9, 2),         # odd size, few output channels (one partial M tile)
+    (2, 20, 12, 64, 64, 9, 1),          # non-square
+    (4, 10, 10, 512, 1024, 1, 1),       # 1x1 (bottleneck-like)
+    (1, 1, 2500, 384, 1920, 1, 1),      # the head's form: rows as the pixels of a 1x1 convolution (tower layer 1)
+    (1, 1, 999, 64, 128, 1, 1),         # row count that is not a multiple of 32
+])
+def test_conv_wgrad_tc_vs_float64(B, H, W, Cin, Cout, taps, dil):
+    """df_conv_wgrad_tc (3xTF32 GEMM over the zero-padded pixel axis) against float64 autograd."""
+    import torch.nn.functional as F
+    from densefusion_b200._C import check, lib, ptr, stream
+    g = torch.Generator().manual_seed(B * 100 + H + Cin + Cout + taps)
+    k = 3 if taps == 9 else 1
+    x = torch.randn(B, Cin, H, W, generator=g)
+    dy = torch.randn(B, Cout, H, W, generator=g)
+    w = torch.zeros(Cout, Cin, k, k, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(x.double(), w, padding=dil * (k // 2), dilation=dil)
+    (y * dy.double()).sum().backward()
+    # operands as channel slices of wider NHWC buffers (pixel pitch > channels)
+    xw = torch.zeros(B, H, W, Cin + 32); xw[..., 16:16 + Cin] = x.permute(0, 2, 3, 1)
+    dw_ = torch.zeros(B, H, W, Cout + 8); dw_[..., 4:4 + Cout] = dy.permute(0, 2, 3, 1)
+    xw, dw_ = xw.cuda(), dw_.cuda()
+    n = int(lib.df_conv_wgrad_scratch_floats(B, H, W, Cin, Cout, taps, dil))
+    scratch = torch.empty(n, device="cuda")
+    out = torch.empty(Cout, taps * Cin, device="cuda")
+    check(lib.df_conv_wgrad_tc(ptr(xw[..., 16:]), Cin + 32, ptr(dw_[..., 4:]), Cout + 8, B, H, W, Cin, Cout, taps, dil, ptr(scratch),
+                               ptr(out), stream()), "df_conv_wgrad_tc")
+    got = out.view(Cout, taps, Cin).permute(0, 2, 1).reshape(Cout, Cin, k, k)
+    err = rel(got, w.grad)
+    print(f"wgrad_tc {taps}tap dil{dil} {Cin}->{Cout} {B}x{H}x{W}: {err:.3e}")
+    assert err < 1e-5
