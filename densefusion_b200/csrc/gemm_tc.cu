@@ -1446,18 +1446,24 @@ cmajor_pad_kernel(const float* __restrict__ in, int ld, float* __restrict__ out,
                   int C, int d, int Wp, int Ppad, int copies, long long plane)
 {
     __shared__ float tile[40][33];                                 // 32 + 2 * 4 rows: dilation <= 4
+    __shared__ int src[40];                                        // source pixel of every tile row, -1 = padding (decoded once per block)
     const int Hp = H + 2 * d;
     const int halo = copies == 3 ? d : 0;
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int j = ty; j < 32 + 2 * halo; j += 8) {
-        const int pp = p0 - halo + j, c = c0 + tx;
-        float v = 0.0f;
-        if (pp >= 0 && pp < B * Hp * Wp && c < C) {
+    if (threadIdx.x < 32 + 2 * halo) {
+        const int pp = p0 - halo + (int)threadIdx.x;
+        int q = -1;
+        if (pp >= 0 && pp < B * Hp * Wp) {
             const int x = pp % Wp - d, r = pp / Wp, y = r % Hp - d, b = r / Hp;
-            if (x >= 0 && x < W && y >= 0 && y < H) v = __ldg(in + (((size_t)b * H + y) * W + x) * ld + c);
+            if (x >= 0 && x < W && y >= 0 && y < H) q = (b * H + y) * W + x;
         }
-        tile[j][tx] = v;
+        src[threadIdx.x] = q;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32 + 2 * halo; j += 8) {
+        const int q = src[j], c = c0 + tx;
+        tile[j][tx] = (q >= 0 && c < C) ? __ldg(in + (size_t)q * ld + c) : 0.0f;
     }
     __syncthreads();
     if (p0 + tx >= Ppad) return;
