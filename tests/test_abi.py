@@ -77,3 +77,21 @@ def test_state_dict_keys_equal_reference_when_available():
             if k == "lib" or k.startswith("lib."):
                 del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_wgrad_scratch_size_is_a_pure_host_function():
+    """df_conv_wgrad_scratch_floats: geometry only (padded row length a multiple of 4, pixel axis cut into 32-aligned
+    slices, three pre-shifted hi/lo planes of X for 3x3, the split-K partial outputs) -- callable without a GPU."""
+    from densefusion_b200 import _C
+    f = _C.lib.df_conv_wgrad_scratch_floats
+    # 1x1: no padding, one plane pair of X; P = 4*10*10 = 400 -> 13 k-blocks, too short to split
+    n = f(4, 10, 10, 512, 1024, 1, 1)
+    assert n == 416 * (1024 + 2 * 512)
+    # 3x3 dilation 4 on 10x10: padded rows of 20 (18 -> multiple of 4), 3 shifted hi/lo planes, split-K partials on top
+    B, H, W, cin, cout, d = 6, 10, 10, 512, 512, 4
+    n = f(B, H, W, cin, cout, 9, d)
+    P = B * (H + 2 * d) * 20
+    planes = cout + 2 * 3 * cin
+    assert n >= ((P + 31) // 32 * 32) * planes and (n - 0) % 32 == 0
+    # monotone in every extent
+    assert f(B + 1, H, W, cin, cout, 9, d) > n and f(B, H, W, cin, 2 * cout, 9, d) > n
