@@ -50,6 +50,7 @@ SIGNATURES = {
     "df_enc_im2col_conv1": [_p, _p, _i, _i, _i, _i, _p],
     "df_enc_maxpool": [_p, _p, _i, _i, _i, _i, _p],
     "df_enc_im2col_s2": [_p, _p, _i, _i, _i, _i, _p],
+    "df_enc_col2im_s2": [_p, _p, _i, _i, _i, _i, _p],
     "df_enc_adaptive_avgpool": [_p, _i, _p, _i, _i, _i, _i, _i, _p],
     "df_enc_pyramid_pool": [_p, _i, _p, _i, _i, _i, _i, _p],
     "df_enc_pyramid_sum": [_p, _p, _i, _i, _i, _i, _i, _p],

@@ -12,13 +12,13 @@ namespace {
 // One thread per (pixel, 4 consecutive k): one float4 store.  The (c, ky, kx) split of k comes from a table that each block
 // copies from constant to shared memory: the lanes of a warp index it with 32 different k, which the constant cache would
 // serialise (measured: 470 -> 90 us for 64 crops of 160x160).
-__constant__ uint32_t c_k147[160];          // c | ky << 8 | kx << 16, 0xffffffff for the zero padding
+__constant__ uint32_t c_k147[192];          // c | ky << 8 | kx << 16, 0xffffffff for the zero padding
 
 __global__ void __launch_bounds__(256)
 im2col_conv1_kernel(const float* __restrict__ img, float* __restrict__ A, int B, int H, int W, int Ho, int Wo, int ldk)
 {
-    __shared__ uint32_t s_k[160];
-    if (threadIdx.x < 160) s_k[threadIdx.x] = c_k147[threadIdx.x];
+    __shared__ uint32_t s_k[192];
+    if (threadIdx.x < 192) s_k[threadIdx.x] = c_k147[threadIdx.x];
     __syncthreads();
     const unsigned kq_per_pix = (unsigned)ldk >> 2;
     const unsigned total = (unsigned)B * Ho * Wo * kq_per_pix;          // < 2^31 (checked by the launcher)
@@ -33,7 +33,7 @@ im2col_conv1_kernel(const float* __restrict__ img, float* __restrict__ A, int B,
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const unsigned k = kq * 4 + e;
-            const uint32_t t = k < 160 ? s_k[k] : 0xffffffffu;
+            const uint32_t t = k < 192 ? s_k[k] : 0xffffffffu;
             float x = 0.0f;
             if (t != 0xffffffffu) {
                 const int c = t & 0xff, ky = (t >> 8) & 0xff, kx = (t >> 16) & 0xff;
@@ -90,6 +90,36 @@ im2col_s2_kernel(const float* __restrict__ in, float* __restrict__ A, int B, int
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(reinterpret_cast<const float4*>(in + (((size_t)b * H + y) * W + x) * C) + cq);
         reinterpret_cast<float4*>(A)[i] = v;
+    }
+}
+
+// Transpose of im2col_s2 in gather form (deterministic, no atomics) -- the data gradient of a 3x3 / stride 2 / pad 1
+// convolution from dA[pixel_out, tap*C + c]: input pixel (y, x) collects tap (ky, kx) of output pixel ((y+1-ky)/2, (x+1-kx)/2)
+// wherever those are integers inside the output map.
+__global__ void __launch_bounds__(256)
+col2im_s2_kernel(const float* __restrict__ dA, float* __restrict__ dx, int B, int H, int W, int C, int Ho, int Wo)
+{
+    const int c4 = C >> 2;
+    const long long total = (long long)B * H * W * c4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cq = (int)(i % c4);
+        long long r = i / c4;
+        const int x = (int)(r % W); r /= W;
+        const int y = (int)(r % H), b = (int)(r / H);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int ty = y + 1 - ky;
+            if (ty < 0 || (ty & 1) || (ty >> 1) >= Ho) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int tx = x + 1 - kx;
+                if (tx < 0 || (tx & 1) || (tx >> 1) >= Wo) continue;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(dA + ((((size_t)b * Ho + (ty >> 1)) * Wo + (tx >> 1)) * 9 + ky * 3 + kx) * C) + cq);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        reinterpret_cast<float4*>(dx)[i] = acc;
     }
 }
 
@@ -380,13 +410,13 @@ inline unsigned grid_for(long long total, int per_block)
 
 extern "C" int df_enc_im2col_conv1(const float* img, float* A, int B, int H, int W, int ldk, void* stream)
 {
-    if (!img || !A || B <= 0 || H <= 0 || W <= 0 || ldk < 147 || ldk > 160 || (ldk & 3) || ((uintptr_t)A & 15)) return DF_ERR_ARG;
+    if (!img || !A || B <= 0 || H <= 0 || W <= 0 || ldk < 147 || ldk > 192 || (ldk & 3) || ((uintptr_t)A & 15)) return DF_ERR_ARG;
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     if ((long long)B * Ho * Wo * ldk >= (1LL << 31)) return DF_ERR_ARG;
     static bool table_done = false;
     if (!table_done) {
-        uint32_t t[160];
-        for (int k = 0; k < 160; ++k) {
+        uint32_t t[192];
+        for (int k = 0; k < 192; ++k) {
             const int c = k / 49, r = k - c * 49;
             t[k] = k < 147 ? (uint32_t)(c | ((r / 7) << 8) | ((r % 7) << 16)) : 0xffffffffu;
         }
@@ -410,6 +440,15 @@ extern "C" int df_enc_im2col_s2(const float* in, float* A, int B, int H, int W, 
     if (!in || !A || B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3)) return DF_ERR_ARG;
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     im2col_s2_kernel<<<grid_for((long long)B * Ho * Wo * 9 * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(in, A, B, H, W, C, Ho, Wo);
+    DF_RETURN_LAST_ERROR();
+}
+
+extern "C" int df_enc_col2im_s2(const float* dA, float* dx, int B, int H, int W, int C, void* stream)
+{
+    if (!dA || !dx || B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3)) return DF_ERR_ARG;
+    if (((uintptr_t)dA & 15) || ((uintptr_t)dx & 15)) return DF_ERR_ARG;
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    col2im_s2_kernel<<<grid_for((long long)B * H * W * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(dA, dx, B, H, W, C, Ho, Wo);
     DF_RETURN_LAST_ERROR();
 }
 

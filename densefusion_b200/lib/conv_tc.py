@@ -11,6 +11,8 @@ physically the NHWC layout the kernel wants; all other encoder ops (pooling, res
 that keep that layout."""
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -19,6 +21,10 @@ from .._C import check, lib, ptr, stream
 
 ENABLED = True          # module switch (tests compare against the pure torch path)
 WGRAD_TC = True         # weight gradients on df_conv_wgrad_tc (3xTF32 GEMM over the pixels); False: aten.convolution_backward
+# The three stride-2 layers as explicit patch matrices (ConvS2Fn).  EXPERIMENTAL, off by default (torch / cuDNN serve them):
+# parity-tested against float64 and correct in eager training steps at the bench's bucket sizes, but the one attempt to replay
+# the whole step as a CUDA graph with it ended in an illegal address that is not root-caused yet (DF_STRIDE2_TC=1 to try).
+STRIDE2_TC = os.environ.get("DF_STRIDE2_TC", "0") == "1"
 PRECISION = "hybrid16"
 
 
@@ -128,6 +134,98 @@ class ConvTCFn(torch.autograd.Function):
         return dx, dw, db, None
 
 
+K_CONV1 = 192           # 3*7*7 = 147 im2col columns, zero-padded to a multiple of 64 (df_conv_wgrad_tc wants Cin % 64 == 0)
+
+
+class ConvS2Fn(torch.autograd.Function):
+    """The three stride-2 convolutions (conv1 7x7/2 on the NCHW image, layer2.0.conv1 3x3/2 and its 1x1/2 projection on
+    channels_last activations) as explicit patch matrices: y = A W^T with A = im2col(x) (df_enc_im2col_conv1 /
+    df_enc_im2col_s2 / the even pixels), dW = dy^T A (df_conv_wgrad_tc), dx = col2im(dy W) (df_enc_col2im_s2)."""
+
+    @staticmethod
+    def _patches(x, k):
+        b, cin, h, w = x.shape
+        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        m = b * ho * wo
+        if k == 7:
+            x = x.detach().float().contiguous()                             # the 3-channel image, NCHW as the reference feeds it
+            a = torch.empty(m, K_CONV1, device=x.device, dtype=torch.float32)
+            check(lib.df_enc_im2col_conv1(ptr(x), ptr(a), b, h, w, K_CONV1, stream()), "df_enc_im2col_conv1")
+        elif k == 3:
+            xn = _nhwc(x.detach().float())
+            a = torch.empty(m, 9 * cin, device=x.device, dtype=torch.float32)
+            check(lib.df_enc_im2col_s2(ptr(xn), ptr(a), b, h, w, cin, stream()), "df_enc_im2col_s2")
+        else:
+            a = x.detach().float()[:, :, ::2, ::2].permute(0, 2, 3, 1).reshape(m, cin).contiguous()
+        return a, ho, wo
+
+    @staticmethod
+    def _matrix(weight):
+        cout, cin, k, _ = weight.shape
+        w = weight.detach().float()
+        if k == 7:
+            wm = torch.zeros(cout, K_CONV1, device=w.device, dtype=torch.float32)
+            wm[:, :147] = w.reshape(cout, 147)
+            return wm
+        return w.permute(0, 2, 3, 1).reshape(cout, k * k * cin).contiguous()   # tap-major, channels fastest (as im2col_s2)
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        cout, cin, k, _ = weight.shape
+        b = x.shape[0]
+        a, ho, wo = ConvS2Fn._patches(x, k)
+        wm = ConvS2Fn._matrix(weight)
+        y = torch.empty(b * ho * wo, cout, device=x.device, dtype=torch.float32)
+        ops.gemm(a, ops.SplitWeight(wm), None, y, M=a.shape[0], N=cout, K=a.shape[1], lda=a.shape[1], ldw=a.shape[1], ldc=cout,
+                 relu=False, precision=PRECISION, short_runs=True)
+        ctx.save_for_backward(a, weight)
+        ctx.in_shape = tuple(x.shape)
+        return y.view(b, ho, wo, cout).permute(0, 3, 1, 2)                   # channels_last storage, NCHW shape
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, weight = ctx.saved_tensors
+        cout, cin, k, _ = weight.shape
+        b, _, h, w = ctx.in_shape
+        m, kk = a.shape
+        dy2 = dy.float().permute(0, 2, 3, 1).reshape(m, cout).contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[1]:
+            n = int(lib.df_conv_wgrad_scratch_floats(1, 1, m, kk, cout, 1, 1))
+            scratch = torch.empty(n, device=a.device, dtype=torch.float32)
+            dwm = torch.empty(cout, kk, device=a.device, dtype=torch.float32)
+            check(lib.df_conv_wgrad_tc(ptr(a), kk, ptr(dy2), cout, 1, 1, m, kk, cout, 1, 1, ptr(scratch), ptr(dwm), stream()),
+                  "df_conv_wgrad_tc")
+            dw = dwm[:, :147].reshape(cout, cin, 7, 7) if k == 7 else dwm.view(cout, k, k, cin).permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[0]:
+            da = torch.empty(m, kk, device=a.device, dtype=torch.float32)
+            wt = ConvS2Fn._matrix(weight).t().contiguous()                      # (K, Cout): dA = dy W
+            ops.gemm(dy2, ops.SplitWeight(wt), None, da, M=m, N=kk, K=cout, lda=cout, ldw=cout, ldc=kk, relu=False,
+                     precision=PRECISION, short_runs=True)
+            dxn = torch.empty(b, h, w, cin, device=a.device, dtype=torch.float32)
+            if k == 3:
+                check(lib.df_enc_col2im_s2(ptr(da), ptr(dxn), b, h, w, cin, stream()), "df_enc_col2im_s2")
+            else:
+                dxn.zero_()
+                dxn[:, ::2, ::2, :] = da.view(b, (h - 1) // 2 + 1, (w - 1) // 2 + 1, cin)
+            dx = dxn.permute(0, 3, 1, 2)
+        return dx, dw
+
+
+def eligible_s2(m: nn.Conv2d, x: torch.Tensor) -> bool:
+    """conv1 7x7/2 (pad 3, 3 input channels), 3x3/2 (pad 1) and 1x1/2 without bias, training mode, on CUDA."""
+    if not (STRIDE2_TC and ENABLED and x.is_cuda and x.dtype == torch.float32 and torch.is_grad_enabled()
+            and (x.requires_grad or m.weight.requires_grad) and m.stride == (2, 2) and m.groups == 1 and m.bias is None
+            and m.dilation == (1, 1) and m.out_channels % 64 == 0):
+        return False
+    k = m.kernel_size
+    if k == (7, 7):
+        return m.padding == (3, 3) and m.in_channels == 3 and not x.requires_grad
+    if k == (3, 3):
+        return m.padding == (1, 1) and m.in_channels % 64 == 0
+    return k == (1, 1) and m.padding == (0, 0) and m.in_channels % 64 == 0
+
+
 def eligible(m: nn.Conv2d, x: torch.Tensor) -> bool:
     return (ENABLED and x.is_cuda and x.dtype == torch.float32 and torch.is_grad_enabled()
             and (x.requires_grad or m.weight.requires_grad)
@@ -139,4 +237,6 @@ def eligible(m: nn.Conv2d, x: torch.Tensor) -> bool:
 def conv2d(m: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
     if eligible(m, x):
         return ConvTCFn.apply(x, m.weight, m.bias, m.dilation[0])
+    if eligible_s2(m, x):
+        return ConvS2Fn.apply(x, m.weight)
     return m(x)

@@ -54,7 +54,7 @@ class ResNet18Trunk(nn.Module):
         from . import conv_tc
         if conv_tc.ENABLED and x.is_cuda and torch.is_grad_enabled() and self.conv1.weight.requires_grad:
             x = x.contiguous(memory_format=torch.channels_last)     # NHWC storage for the tensor-core training convolutions
-        x = F.max_pool2d(F.relu(self.conv1(x)), 3, stride=2, padding=1)
+        x = F.max_pool2d(F.relu(conv2d(self.conv1, x)), 3, stride=2, padding=1)
         x = self.layer2(self.layer1(x))
         mid = self.layer3(x)
         return self.layer4(mid), mid

@@ -191,6 +191,7 @@ int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx, const floa
 int df_enc_im2col_conv1(const float* img, float* A, int B, int H, int W, int ldk, void* stream);
 int df_enc_maxpool(const float* in, float* out, int B, int H, int W, int C, void* stream);
 int df_enc_im2col_s2(const float* in, float* A, int B, int H, int W, int C, void* stream);
+int df_enc_col2im_s2(const float* dA, float* dx, int B, int H, int W, int C, void* stream);   /* transpose of df_enc_im2col_s2 (training) */
 int df_enc_adaptive_avgpool(const float* in, int ldi, float* out, int B, int H, int W, int C, int S, void* stream);
 /* Folded pyramid (lib/pspnet.py:17-24): the four adaptive average pools (1,2,3,6) of `in` (B,H,W,C; pixel pitch ldi) in one
    pass -> out (50 B, C) stage-major (rows [B x 1 | B x 4 | B x 9 | B x 36]); and out[b,y,x,:] = Y[b,:] + sum_s bilinear(Y cells of s) resized to

@@ -235,3 +235,36 @@ def test_upsample_backward_kernel_vs_torch_autograd(hin, win, hout, wout, align)
     gi = torch.empty(B, C, hin, win, device="cuda", memory_format=torch.channels_last)
     check(lib.df_enc_upsample_backward(ptr(gy_n), C, ptr(gi), C, B, hin, win, hout, wout, C, 1 if align else 0, stream()), "up_bwd")
     assert rel(gi, x.grad) < 2e-6
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", [(2, 40, 56, 3, 64, 7), (3, 20, 20, 64, 128, 3), (2, 30, 22, 64, 128, 3),
+                                              (3, 20, 20, 64, 128, 1), (1, 15, 11, 64, 128, 1)])
+def test_stride2_convolutions_forward_and_gradients_vs_float64(B, H, W, Cin, Cout, k):
+    """lib.conv_tc.ConvS2Fn (im2col + tensor-core GEMM, col2im, tensor-core weight gradient) against float64 autograd."""
+    import torch.nn as nn
+    from densefusion_b200.lib import conv_tc
+    g = torch.Generator().manual_seed(B + H + Cin + k)
+    m = nn.Conv2d(Cin, Cout, k, stride=2, padding=k // 2, bias=False)
+    with torch.no_grad():
+        m.weight.copy_(torch.randn(m.weight.shape, generator=g) / (Cin * k * k) ** 0.5)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    m64 = nn.Conv2d(Cin, Cout, k, stride=2, padding=k // 2, bias=False).double()
+    m64.weight.data.copy_(m.weight.data.double())
+    x64 = x.double().requires_grad_(k != 7)
+    y64 = m64(x64)
+    dy = torch.randn(y64.shape, generator=g)
+    (y64 * dy.double()).sum().backward()
+    m = m.cuda()
+    xc = x.cuda().requires_grad_(k != 7)
+    old = conv_tc.STRIDE2_TC
+    conv_tc.STRIDE2_TC = True
+    try:
+        assert conv_tc.eligible_s2(m, xc)
+        y = conv_tc.conv2d(m, xc)
+        (y * dy.cuda()).sum().backward()
+    finally:
+        conv_tc.STRIDE2_TC = old
+    torch.cuda.synchronize()
+    e = [rel(y, y64), rel(m.weight.grad, m64.weight.grad)] + ([rel(xc.grad, x64.grad)] if k != 7 else [])
+    print(f"conv_s2 {k}x{k} {Cin}->{Cout} {H}x{W}x{B}: " + " ".join(f"{v:.2e}" for v in e))
+    assert max(e) < 2e-5
