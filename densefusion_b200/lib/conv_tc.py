@@ -22,8 +22,9 @@ from .._C import check, lib, ptr, stream
 ENABLED = True          # module switch (tests compare against the pure torch path)
 WGRAD_TC = True         # weight gradients on df_conv_wgrad_tc (3xTF32 GEMM over the pixels); False: aten.convolution_backward
 # The three stride-2 layers as explicit patch matrices (ConvS2Fn).  EXPERIMENTAL, off by default (torch / cuDNN serve them):
-# parity-tested against float64 and correct in eager training steps at the bench's bucket sizes, but the one attempt to replay
-# the whole step as a CUDA graph with it ended in an illegal address that is not root-caused yet (DF_STRIDE2_TC=1 to try).
+# parity-tested against float64 and correct in eager training steps on the default stream at the bench's bucket sizes, but
+# GraphedTrainStep's warm-up (the same eager step on a side stream) reproducibly ends in an illegal address inside layer2 that
+# is not root-caused yet (independent of programmatic dependent launch).  DF_STRIDE2_TC=1 to try.
 STRIDE2_TC = os.environ.get("DF_STRIDE2_TC", "0") == "1"
 PRECISION = "hybrid16"
 
