@@ -9,16 +9,19 @@
 namespace {
 
 // conv1 (7x7, stride 2, pad 3) as a GEMM: A[pixel, c*49 + ky*7 + kx] from the NCHW image, zero-padded to ldk columns.
-// One thread per (pixel, 4 consecutive k): one float4 store.  The (c, ky, kx) split of k comes from a table that each block
-// copies from constant to shared memory: the lanes of a warp index it with 32 different k, which the constant cache would
-// serialise (measured: 470 -> 90 us for 64 crops of 160x160).
-__constant__ uint32_t c_k147[192];          // c | ky << 8 | kx << 16, 0xffffffff for the zero padding
-
+// One thread per (pixel, 4 consecutive k): one float4 store.  The (c, ky, kx) split of k comes from a table every block
+// builds in shared memory (c | ky << 8 | kx << 16, 0xffffffff for the zero padding): the lanes of a warp index it with 32
+// different k, which a __constant__ table would serialise (measured 470 -> 130 us for 64 crops of 160x160) -- and a constant
+// table needs a host upload whose DMA from pageable memory may still be in flight when the first kernel on a non-blocking
+// stream reads it.
 __global__ void __launch_bounds__(256)
 im2col_conv1_kernel(const float* __restrict__ img, float* __restrict__ A, int B, int H, int W, int Ho, int Wo, int ldk)
 {
     __shared__ uint32_t s_k[192];
-    if (threadIdx.x < 192) s_k[threadIdx.x] = c_k147[threadIdx.x];
+    if (threadIdx.x < 192) {
+        const int k = threadIdx.x, c = k / 49, r = k - c * 49;
+        s_k[k] = k < 147 ? (uint32_t)(c | ((r / 7) << 8) | ((r % 7) << 16)) : 0xffffffffu;
+    }
     __syncthreads();
     const unsigned kq_per_pix = (unsigned)ldk >> 2;
     const unsigned total = (unsigned)B * Ho * Wo * kq_per_pix;          // < 2^31 (checked by the launcher)
@@ -413,16 +416,6 @@ extern "C" int df_enc_im2col_conv1(const float* img, float* A, int B, int H, int
     if (!img || !A || B <= 0 || H <= 0 || W <= 0 || ldk < 147 || ldk > 192 || (ldk & 3) || ((uintptr_t)A & 15)) return DF_ERR_ARG;
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     if ((long long)B * Ho * Wo * ldk >= (1LL << 31)) return DF_ERR_ARG;
-    static bool table_done = false;
-    if (!table_done) {
-        uint32_t t[192];
-        for (int k = 0; k < 192; ++k) {
-            const int c = k / 49, r = k - c * 49;
-            t[k] = k < 147 ? (uint32_t)(c | ((r / 7) << 8) | ((r % 7) << 16)) : 0xffffffffu;
-        }
-        if (cudaMemcpyToSymbol(c_k147, t, sizeof(t)) != cudaSuccess) return DF_ERR_UNSUPPORTED;
-        table_done = true;
-    }
     im2col_conv1_kernel<<<grid_for((long long)B * Ho * Wo * (ldk >> 2), 256), 256, 0, (cudaStream_t)stream>>>(img, A, B, H, W, Ho, Wo, ldk);
     DF_RETURN_LAST_ERROR();
 }
