@@ -21,10 +21,11 @@ from .._C import check, lib, ptr, stream
 
 ENABLED = True          # module switch (tests compare against the pure torch path)
 WGRAD_TC = True         # weight gradients on df_conv_wgrad_tc (3xTF32 GEMM over the pixels); False: aten.convolution_backward
-# The three stride-2 layers as explicit patch matrices (ConvS2Fn).  EXPERIMENTAL, off by default (torch / cuDNN serve them):
-# parity-tested against float64 and correct in eager training steps on the default stream at the bench's bucket sizes, but
-# GraphedTrainStep's warm-up (the same eager step on a side stream) reproducibly ends in an illegal address inside layer2 that
-# is not root-caused yet (independent of programmatic dependent launch).  DF_STRIDE2_TC=1 to try.
+# The three stride-2 layers as explicit patch matrices (ConvS2Fn).  EXPERIMENTAL, off by default (torch / cuDNN serve them).
+# Status: parity-tested against float64 (tests/test_encoder_gpu.py); the encoder's forward + backward with it passes on the
+# default AND on a side stream at every bench crop size under CUDA_LAUNCH_BLOCKING=1 (scripts/s2_probe.py); the data-parallel
+# step's eager warm-up on a side stream nevertheless ends, asynchronously, in an illegal address reported inside layer2 --
+# with or without programmatic dependent launch.  Not root-caused (next: bisect with a synchronisation after every op).
 STRIDE2_TC = os.environ.get("DF_STRIDE2_TC", "0") == "1"
 PRECISION = "hybrid16"
 
