@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("DF_PRECISION", "hybrid16"), choices=["fp32", "3xtf32", "tf32", "hybrid", "hybrid16"])
+    ap.add_argument("--precision", default=os.environ.get("DF_PRECISION", "hybrid16"), choices=["fp32", "3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16p"])
     ap.add_argument("--frames", type=int, default=32, help="frames (of 8 objects) per GPU per step")
     ap.add_argument("--chunk", type=int, default=128, help="crops per head chunk (measured 16: 21.7 ms, 32: 20.7, 64: 20.3, 128: 20.05 per step)")
     ap.add_argument("--no-graph", action="store_true")
@@ -431,6 +431,7 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": {"fp32": "fp32", "hybrid": "fp32 (fp32-parity tensor-core GEMMs: TF32 main term + bf16 correction terms, fp32 accumulate)",
                           "hybrid16": "fp32 (fp32-parity tensor-core GEMMs: fp16 main term + bf16 correction terms, fp32 accumulate)",
+                          "hybrid16p": "fp32 (fp32-parity tensor-core GEMMs: fp16 main term + bf16 correction terms, fp32 accumulate)",
                           "3xtf32": "fp32 (fp32-parity tensor-core GEMMs: 3xTF32, fp32 accumulate)",
                           "tf32": "tf32 (single-pass tensor-core GEMMs, fp32 accumulate; looser bound)"}[args.precision],
                 "data": "synthetic",

@@ -123,8 +123,14 @@ def check(status: int, what: str) -> None:
 
 
 def ptr(t):
-    """Device pointer of a tensor (None -> NULL)."""
-    return None if t is None else t.data_ptr()
+    """Device pointer of a tensor (None -> NULL).  Kernels launch on the CURRENT device's current stream (see stream()), so a
+    CUDA tensor living on another device is an error here rather than an illegal address inside the kernel."""
+    if t is None:
+        return None
+    if t.is_cuda and t.device.index != torch.cuda.current_device():
+        raise DFError(f"tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                      "call torch.cuda.set_device(...) / use torch.cuda.device(...) around densefusion_b200 calls")
+    return t.data_ptr()
 
 
 def stream() -> int:

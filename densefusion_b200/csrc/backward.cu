@@ -308,9 +308,10 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float step = (float)(*step_ptr + 1);
-    const float bc1 = 1.0f - powf(b1, step);
-    const float bc2_sqrt = sqrtf(1.0f - powf(b2, step));
+    // bias corrections in double like torch.optim.Adam (python floats): fp32 powf deviates by ~1e-5 relative in the first steps
+    const double step = (double)(*step_ptr + 1);
+    const float bc1 = (float)(1.0 - pow((double)b1, step));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, step));
     const float gi = g[i];
     const float mi = b1 * m[i] + (1.0f - b1) * gi;
     const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
@@ -399,8 +400,8 @@ extern "C" int df_adam_step(float* param, const float* grad, float* exp_avg, flo
                             float beta1, float beta2, float eps, int step, void* stream)
 {
     if (!param || !grad || !exp_avg || !exp_avg_sq || n <= 0 || step <= 0) return DF_ERR_ARG;
-    const float bc1 = 1.0f - powf(beta1, (float)step);
-    const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+    const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
     adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
                                                                              beta2, eps, bc1, bc2_sqrt);
     DF_RETURN_LAST_ERROR();

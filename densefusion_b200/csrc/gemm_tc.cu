@@ -1,26 +1,17 @@
-// Tensor-core mode of the dense-fusion head GEMMs: tcgen05.mma (kind::tf32) with fp32 accumulators in
-// TMEM, weights streamed by TMA, same contract and fused epilogues as gemm_simt.cu.
+// Tensor-core GEMM / implicit-GEMM convolution of the pose path: tcgen05.mma with fp32 accumulators in TMEM, operands
+// by TMA, persistent warp-specialised CTAs (or CTA pairs, cta_group::2), same contract and fused epilogues as gemm_simt.cu.
 //
-//   C[m,n] = act( sum_k A[m,k] W[n,k] + bias )         M tile 128 (one TMEM lane per point), N tile BN
+//   C[m,n] = act( sum_k A[m,k] W[n,k] + bias )         M tile 128 rows per CTA (one TMEM lane per row)
 //
-// fp32 parity on a TF32 tensor core ("3xTF32"): x = hi + lo with hi = x & 0xffffe000 (exactly
-// representable in TF32, so the result does not depend on whether the MMA truncates or rounds) and
-// lo = x - hi (exact in fp32).  D += A_hi W_hi + A_lo W_hi + A_hi W_lo; the dropped A_lo W_lo term and
-// the TF32 rounding of the lo factors are O(2^-21) relative.  Single-pass TF32 (precision 2) issues
-// only the first product.
+// fp32 parity on 11-bit tensor-core operands: x = hi + lo, D += A_hi W_hi + A_lo W_hi + A_hi W_lo (the dropped A_lo W_lo term
+// is O(2^-22) relative).  "3xtf32": hi = x & 0xffffe000, all three products kind::tf32.  "hybrid": the two correction terms
+// with bf16 operands (kind::f16).  "hybrid16": the main term on fp16 operands as well (see gemm_tc_q_kernel).  "tf32": the
+// first product only (stated looser bound).
 //
-// Data movement (why it looks like this -- shared memory bandwidth is the binding resource for 3xTF32):
-//   * W_hi / W_lo are split ONCE at weight-pack time (df_split_tf32) and arrive by TMA into
-//     128B-swizzled K-major tiles (BK = 32 floats = one swizzle atom per row);
-//   * A never touches shared memory in the default path: the 4 worker warps own one accumulator row
-//     each, read their row's 32 floats of the k-block straight from global (128 B contiguous, full
-//     sectors), split them in registers and tcgen05.st the hi / lo halves into TMEM, from where the MMA
-//     takes its A operand (".ts" form).  An smem-staged A path (A_TMEM = false) is kept for bring-up.
-//   * one elected thread issues the MMAs; tcgen05.commit releases W stages / A stages and finally
-//     signals the epilogue; the same worker warps then read the accumulator rows back (tcgen05.ld),
-//     apply bias / per-crop bias / ReLU and either store 128 B per row chunk or reduce the columns over
-//     the rows with a shuffle butterfly (fixed order -> deterministic pooling).
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2-5 workers.
+// The A operand is split in registers by stager warps and written to TMEM (tcgen05.st; the MMA reads it in .ts form), the
+// weight operand is either split once at pack time (df_split_tf32 / df_pack_*) or, RAW_W, on chip from the fp32 matrix.
+// The first two kernel generations of round 1 (one tile per CTA; persistent with A read straight from global memory) are
+// gone: they were superseded by gemm_tc_q_kernel on every shape (DESIGN.md section 4 keeps their measurements).
 #include "df_common.cuh"
 #include "../../include/densefusion_b200.h"
 #include <cuda.h>
@@ -31,8 +22,6 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 32;                       // floats per k-block = 128 B = one SW128 atom row
 constexpr int UMMA_K = 8;                    // tf32
-constexpr int NUM_THREADS = 192;
-constexpr int NUM_WORKERS = 128;
 
 struct TcParams {
     const float* A; int lda;
@@ -71,496 +60,6 @@ struct TcParams {
 namespace {
 using namespace df_tc;
 
-template <int BN, bool A_TMEM>
-struct Cfg {
-    static constexpr int W_STAGES = (BN == 256) ? 3 : (A_TMEM ? 4 : 3);
-    static constexpr int A_STAGES = A_TMEM ? 4 : 3;
-    static constexpr int W_TILE_BYTES = BN * BK * 4;                 // one of hi / lo
-    static constexpr int A_TILE_BYTES = BM * BK * 4;
-    static constexpr int SMEM_W = W_STAGES * 2 * W_TILE_BYTES;
-    static constexpr int SMEM_A = A_TMEM ? 0 : A_STAGES * 2 * A_TILE_BYTES;
-    static constexpr int SMEM_POOL = 4 * BN * 4;
-    static constexpr int SMEM_BAR = 256;
-    static constexpr int SMEM_TOTAL = 1024 /*align slack*/ + SMEM_W + SMEM_A + SMEM_POOL + SMEM_BAR;
-    static constexpr int TMEM_A_COL0 = BN;                           // accumulator occupies [0, BN)
-    static constexpr int TMEM_COLS_USED = BN + (A_TMEM ? A_STAGES * 2 * BK : 0);
-    static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64 : TMEM_COLS_USED <= 128 ? 128
-                                     : TMEM_COLS_USED <= 256 ? 256 : 512;
-    static_assert(TMEM_COLS_USED <= 512, "TMEM overflow");
-    static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory overflow");
-};
-
-template <int BN, bool A_TMEM>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo, const TcParams p)
-{
-    using C = Cfg<BN, A_TMEM>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* s_w = smem;                                             // [W_STAGES][hi|lo][BN][32]
-    uint8_t* s_a = smem + C::SMEM_W;                                 // [A_STAGES][hi|lo][128][32]   (smem-A path)
-    float* s_pool = reinterpret_cast<float*>(smem + C::SMEM_W + C::SMEM_A);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::SMEM_W + C::SMEM_A + C::SMEM_POOL);
-    uint64_t* w_full = bars;                       // [W_STAGES]
-    uint64_t* w_empty = bars + 4;                  // [W_STAGES]
-    uint64_t* a_full = bars + 8;                   // [A_STAGES]
-    uint64_t* a_empty = bars + 12;                 // [A_STAGES]
-    uint64_t* acc_full = bars + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = blockIdx.z;
-    const int n0 = blockIdx.x * BN;
-    const int nkb = p.K / BK;
-
-    int row0, rows_valid, crop = 0, tile_in_crop = 0;
-    if (p.pool_partial) {
-        crop = blockIdx.y / p.tiles_per_crop;
-        tile_in_crop = blockIdx.y - crop * p.tiles_per_crop;
-        row0 = crop * p.rows_per_crop + tile_in_crop * BM;
-        rows_valid = min(BM, p.rows_per_crop - tile_in_crop * BM);
-    } else {
-        row0 = blockIdx.y * BM;
-        rows_valid = min(BM, p.M - row0);
-    }
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < C::W_STAGES; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
-        for (int i = 0; i < C::A_STAGES; ++i) { mbar_init(a_full + i, 4); mbar_init(a_empty + i, 1); }
-        mbar_init(acc_full, 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ------------------------------- TMA producer (weights) -------------------------------
-        if (lane == 0) {
-            const uint32_t bytes = (p.precise ? 2u : 1u) * C::W_TILE_BYTES;
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % C::W_STAGES;
-                const uint32_t ph = (kb / C::W_STAGES) & 1;
-                mbar_wait(w_empty + s, ph ^ 1);
-                mbar_expect_tx(w_full + s, bytes);
-                uint8_t* dst = s_w + (size_t)s * 2 * C::W_TILE_BYTES;
-                tma_load_2d(&tm_whi, dst, w_full + s, kb * BK, g * p.N + n0);
-                if (p.precise) tma_load_2d(&tm_wlo, dst + C::W_TILE_BYTES, w_full + s, kb * BK, g * p.N + n0);
-            }
-        }
-    } else if (warp == 1) {
-        // ------------------------------- MMA issuer -------------------------------------------
-        if (lane == 0) {
-            const uint32_t idesc = tf32_instr_desc(BN);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % C::W_STAGES, sa = kb % C::A_STAGES;
-                mbar_wait(w_full + s, (kb / C::W_STAGES) & 1);
-                mbar_wait(a_full + sa, (kb / C::A_STAGES) & 1);
-                tc_fence_after();
-                const uint32_t w_hi = smem_u32(s_w + (size_t)s * 2 * C::W_TILE_BYTES);
-                const uint32_t w_lo = w_hi + C::W_TILE_BYTES;
-#pragma unroll
-                for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-                    const uint32_t koff = ks * UMMA_K * 4;                        // bytes along K inside the atom
-                    const uint64_t bhi = sw128_desc(w_hi + koff), blo = sw128_desc(w_lo + koff);
-                    const uint32_t first = (kb | ks) != 0;
-                    if (A_TMEM) {
-                        const uint32_t a_hi = tmem_base + C::TMEM_A_COL0 + sa * 2 * BK + ks * UMMA_K;
-                        const uint32_t a_lo = a_hi + BK;
-                        umma_ts(tmem_base, a_hi, bhi, idesc, first);
-                        if (p.precise) { umma_ts(tmem_base, a_lo, bhi, idesc, 1u); umma_ts(tmem_base, a_hi, blo, idesc, 1u); }
-                    } else {
-                        const uint32_t a_hi_s = smem_u32(s_a + (size_t)sa * 2 * C::A_TILE_BYTES);
-                        const uint64_t ahi = sw128_desc(a_hi_s + koff), alo = sw128_desc(a_hi_s + C::A_TILE_BYTES + koff);
-                        umma_ss(tmem_base, ahi, bhi, idesc, first);
-                        if (p.precise) { umma_ss(tmem_base, alo, bhi, idesc, 1u); umma_ss(tmem_base, ahi, blo, idesc, 1u); }
-                    }
-                }
-                umma_commit(w_empty + s);        // frees the weight stage when these MMAs retire
-                umma_commit(a_empty + sa);       // ... and the activation stage
-            }
-            umma_commit(acc_full);
-        }
-    } else {
-        // ------------------------------- workers: A staging, then epilogue --------------------
-        const int q = warp & 3;                  // TMEM lane quarter this warp may touch
-        const int r = q * 32 + lane;             // accumulator row == tile row
-        const bool row_ok = r < rows_valid;
-        const float* arow = p.A + g * p.a_gs + (size_t)(row0 + (row_ok ? r : 0)) * p.lda;
-        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-
-        uint32_t cur[32];
-        auto load_kb = [&](int kb) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float4 v = row_ok ? __ldg(reinterpret_cast<const float4*>(arow + kb * BK) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                cur[i * 4 + 0] = __float_as_uint(v.x); cur[i * 4 + 1] = __float_as_uint(v.y);
-                cur[i * 4 + 2] = __float_as_uint(v.z); cur[i * 4 + 3] = __float_as_uint(v.w);
-            }
-        };
-        load_kb(0);
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int sa = kb % C::A_STAGES;
-            uint32_t hi[32], lo[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                hi[i] = p.precise ? (cur[i] & 0xffffe000u) : cur[i];
-                lo[i] = __float_as_uint(__uint_as_float(cur[i]) - __uint_as_float(hi[i]));
-            }
-            if (kb + 1 < nkb) load_kb(kb + 1);                      // next block's loads fly during the wait + store
-            mbar_wait(a_empty + sa, ((kb / C::A_STAGES) & 1) ^ 1);
-            if (A_TMEM) {
-                tc_fence_after();
-                const uint32_t t = tmem_base + lane_base + C::TMEM_A_COL0 + sa * 2 * BK;
-                tmem_st32(t, hi);
-                if (p.precise) tmem_st32(t + BK, lo);
-                tmem_st_wait();
-                tc_fence_before();
-            } else {
-                // row r of a K-major SW128 tile: 16-byte chunk c lands at chunk (c ^ (r & 7))
-                uint8_t* base = s_a + (size_t)sa * 2 * C::A_TILE_BYTES + r * 128;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int pc = (c ^ (r & 7)) * 16;
-                    *reinterpret_cast<uint4*>(base + pc) = make_uint4(hi[c * 4], hi[c * 4 + 1], hi[c * 4 + 2], hi[c * 4 + 3]);
-                    if (p.precise)
-                        *reinterpret_cast<uint4*>(base + C::A_TILE_BYTES + pc) =
-                            make_uint4(lo[c * 4], lo[c * 4 + 1], lo[c * 4 + 2], lo[c * 4 + 3]);
-                }
-                fence_proxy_async();
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a_full + sa);
-        }
-
-        // ---- epilogue ----
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
-        const int row = row0 + r;
-        const float* bias = p.bias ? p.bias + g * p.bias_gs : nullptr;
-        if (bias && p.bias_crop_stride) bias += (size_t)((row_ok ? row : row0) / p.rows_per_crop) * p.bias_crop_stride;
-        float* crow = p.C ? p.C + g * p.c_gs + (size_t)row * p.ldc : nullptr;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + lane_base + c * 32, v);
-            const int col = n0 + c * 32;
-            float f[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                float x = __uint_as_float(v[i]);
-                if (bias && col + i < p.N) x += __ldg(bias + col + i);
-                if (p.relu) x = fmaxf(x, 0.0f);
-                f[i] = x;
-            }
-            if (p.pool_partial) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = row_ok ? f[i] : 0.0f;
-                // butterfly reduce-scatter over the 32 rows of this warp: lane l ends with column l
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    const bool up = (lane & off) != 0;
-#pragma unroll
-                    for (int i = 0; i < off; ++i) {
-                        const float send = up ? f[i] : f[i + off];
-                        const float keep = up ? f[i + off] : f[i];
-                        f[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                    }
-                }
-                s_pool[q * BN + c * 32 + lane] = f[0];
-            } else if (row_ok && crow) {
-                if (col + 32 <= p.N) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        *reinterpret_cast<float4*>(crow + col + i * 4) = make_float4(f[i * 4], f[i * 4 + 1], f[i * 4 + 2], f[i * 4 + 3]);
-                } else {
-                    for (int i = 0; i < 32; ++i)
-                        if (col + i < p.N) crow[col + i] = f[i];
-                }
-            }
-        }
-        if (p.pool_partial) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");           // the 4 worker warps only
-            const int t = threadIdx.x - 64;
-            for (int c = t; c < BN; c += NUM_WORKERS) {
-                if (n0 + c < p.N) {
-                    const float s = ((s_pool[c] + s_pool[BN + c]) + s_pool[2 * BN + c]) + s_pool[3 * BN + c];
-                    p.pool_partial[((size_t)crop * p.tiles_per_crop + tile_in_crop) * p.N + n0 + c] = s;
-                }
-            }
-        }
-        tc_fence_before();
-    }
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, C::TMEM_COLS);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Persistent, fully warp-specialised variant (the production path): one CTA per SM loops over output tiles.
-//   warp 0      TMA producer (W_hi / W_lo stages)
-//   warp 1      MMA issuer, TMEM owner
-//   warps 2-5   A stagers, even k-blocks   } global -> registers -> hi/lo split -> tcgen05.st (TMEM A stages)
-//   warps 6-9   A stagers, odd k-blocks    } two groups so one group's load latency hides behind the other
-//   warps 10-13 epilogue: tcgen05.ld -> bias/ReLU -> shared-memory transpose -> 128 B-per-row coalesced stores,
-//               or the column-pool butterfly
-// TMEM: two 128-column accumulators (the epilogue of tile i overlaps the MMAs of tile i+1) + 4 A stages x 64.
-// ------------------------------------------------------------------------------------------------
-constexpr int P_BN = 128;
-constexpr int P_THREADS = 448;
-constexpr int P_W_STAGES = 5;
-constexpr int P_A_STAGES = 4;
-constexpr int P_W_TILE = P_BN * BK * 4;                  // 16 KB (one of hi / lo)
-constexpr int P_STAGE_PITCH = 36;                        // floats; 16 B aligned, conflict-free float4 rows
-constexpr int P_SMEM_W = P_W_STAGES * 2 * P_W_TILE;      // 160 KB
-constexpr int P_SMEM_STAGE = 4 * 32 * P_STAGE_PITCH * 4; // 18 KB: one 32x32 transpose tile per epilogue warp
-constexpr int P_SMEM_POOL = 2 * 4 * P_BN * 4;            // 4 KB, double buffered by accumulator
-constexpr int P_SMEM_TOTAL = 1024 + P_SMEM_W + P_SMEM_STAGE + P_SMEM_POOL + 512;
-constexpr int P_TMEM_A0 = 2 * P_BN;                      // A stages start after the two accumulators
-
-struct TileCoord {
-    int g, n0, row0, rows_valid, crop, tile_in_crop;
-};
-
-__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t, int m_tiles, int n_tiles)
-{
-    TileCoord c;
-    const int per_group = m_tiles * n_tiles;
-    c.g = t / per_group;
-    const int rem = t - c.g * per_group;
-    const int mt = rem / n_tiles;
-    c.n0 = (rem - mt * n_tiles) * P_BN;
-    c.crop = 0; c.tile_in_crop = 0;
-    if (p.pool_partial) {
-        c.crop = mt / p.tiles_per_crop;
-        c.tile_in_crop = mt - c.crop * p.tiles_per_crop;
-        c.row0 = c.crop * p.rows_per_crop + c.tile_in_crop * BM;
-        c.rows_valid = min(BM, p.rows_per_crop - c.tile_in_crop * BM);
-    } else {
-        c.row0 = mt * BM;
-        c.rows_valid = min(BM, p.M - c.row0);
-    }
-    return c;
-}
-
-__global__ void __launch_bounds__(P_THREADS, 1)
-gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
-                          const TcParams p, const int m_tiles, const int n_tiles, const int total_tiles)
-{
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* s_w = smem;
-    float* s_stage = reinterpret_cast<float*>(smem + P_SMEM_W);
-    float* s_pool = reinterpret_cast<float*>(smem + P_SMEM_W + P_SMEM_STAGE);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_SMEM_W + P_SMEM_STAGE + P_SMEM_POOL);
-    uint64_t* w_full = bars;                        // [8]
-    uint64_t* w_empty = bars + 8;                   // [8]
-    uint64_t* a_full = bars + 16;                   // [4]
-    uint64_t* a_empty = bars + 20;                  // [4]
-    uint64_t* acc_full = bars + 24;                 // [2]
-    uint64_t* acc_empty = bars + 26;                // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nkb = p.K / BK;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < P_W_STAGES; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
-        for (int i = 0; i < P_A_STAGES; ++i) { mbar_init(a_full + i, 4); mbar_init(a_empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ------------------------------- TMA producer -------------------------------
-        const uint32_t bytes = (p.precise ? 2u : 1u) * P_W_TILE;
-        uint32_t it = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const TileCoord c = decode_tile(p, t, m_tiles, n_tiles);
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
-                const int s = it % P_W_STAGES;
-                mbar_wait(w_empty + s, ((it / P_W_STAGES) & 1) ^ 1);
-                if (elect_one()) {
-                    mbar_expect_tx(w_full + s, bytes);
-                    uint8_t* dst = s_w + (size_t)s * 2 * P_W_TILE;
-                    tma_load_2d(&tm_whi, dst, w_full + s, kb * BK, c.g * p.N + c.n0);
-                    if (p.precise) tma_load_2d(&tm_wlo, dst + P_W_TILE, w_full + s, kb * BK, c.g * p.N + c.n0);
-                }
-                __syncwarp();
-            }
-        }
-    } else if (warp == 1) {
-        // ------------------------------- MMA issuer ---------------------------------
-        // the whole warp walks the pipeline (uniform control flow); one elected lane issues
-        const uint32_t idesc = tf32_instr_desc(P_BN);
-        uint32_t it = 0, ti = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
-            const uint32_t ab = ti & 1;
-            mbar_wait(acc_empty + ab, ((ti >> 1) & 1) ^ 1);
-            const uint32_t acc = tmem_base + ab * P_BN;
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
-                const int s = it % P_W_STAGES, sa = it % P_A_STAGES;
-                mbar_wait(w_full + s, (it / P_W_STAGES) & 1);
-                mbar_wait(a_full + sa, (it / P_A_STAGES) & 1);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t w_hi = smem_u32(s_w + (size_t)s * 2 * P_W_TILE);
-                    const uint64_t bhi0 = sw128_desc(w_hi), blo0 = sw128_desc(w_hi + P_W_TILE);
-                    const uint32_t a0 = tmem_base + P_TMEM_A0 + sa * 2 * BK;
-#pragma unroll
-                    for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-                        // +32 B along K inside the swizzle atom == +2 in the descriptor's (addr >> 4) field
-                        const uint64_t bhi = bhi0 + (uint64_t)(ks * 2), blo = blo0 + (uint64_t)(ks * 2);
-                        const uint32_t a_hi = a0 + ks * UMMA_K;
-                        umma_ts(acc, a_hi, bhi, idesc, (kb | ks) != 0);
-                        if (p.precise) { umma_ts(acc, a_hi + BK, bhi, idesc, 1u); umma_ts(acc, a_hi, blo, idesc, 1u); }
-                    }
-                    umma_commit(w_empty + s);
-                    umma_commit(a_empty + sa);
-                    if (kb == nkb - 1) umma_commit(acc_full + ab);
-                }
-                __syncwarp();
-            }
-        }
-    } else if (warp < 10) {
-        // ------------------------------- A stagers (two groups) ----------------------
-        const int grp = (warp - 2) >> 2;           // 0: even k-block iterations, 1: odd
-        const int q = warp & 3;
-        const int r = q * 32 + lane;
-        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        // flat iteration space over (tile, kb); this group takes it = grp, grp+2, ...
-        const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-        const uint32_t total_it = (uint32_t)my_tiles * nkb;
-        uint32_t cur[32];
-        auto issue_loads = [&](uint32_t it) {
-            const int ti = it / nkb, kb = it - ti * nkb;
-            const TileCoord c = decode_tile(p, blockIdx.x + ti * gridDim.x, m_tiles, n_tiles);
-            const bool ok = r < c.rows_valid;
-            const float* src = p.A + c.g * p.a_gs + (size_t)(c.row0 + (ok ? r : 0)) * p.lda + kb * BK;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 v = ok ? __ldg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                cur[i * 4 + 0] = __float_as_uint(v.x); cur[i * 4 + 1] = __float_as_uint(v.y);
-                cur[i * 4 + 2] = __float_as_uint(v.z); cur[i * 4 + 3] = __float_as_uint(v.w);
-            }
-        };
-        if ((uint32_t)grp < total_it) issue_loads(grp);
-        for (uint32_t it = grp; it < total_it; it += 2) {
-            const int sa = it % P_A_STAGES;
-            uint32_t hi[32], lo[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                hi[i] = p.precise ? (cur[i] & 0xffffe000u) : cur[i];
-                lo[i] = __float_as_uint(__uint_as_float(cur[i]) - __uint_as_float(hi[i]));
-            }
-            if (it + 2 < total_it) issue_loads(it + 2);
-            mbar_wait(a_empty + sa, ((it / P_A_STAGES) & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t ta = tmem_base + lane_base + P_TMEM_A0 + sa * 2 * BK;
-            tmem_st32(ta, hi);
-            if (p.precise) tmem_st32(ta + BK, lo);
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a_full + sa);
-        }
-    } else {
-        // ------------------------------- epilogue ------------------------------------
-        const int q = warp & 3;
-        const int ew = warp - 10;
-        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        float* stage = s_stage + ew * 32 * P_STAGE_PITCH;
-        uint32_t ti = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
-            const uint32_t ab = ti & 1;
-            const TileCoord c = decode_tile(p, t, m_tiles, n_tiles);
-            const int r = q * 32 + lane;
-            const bool row_ok = r < c.rows_valid;
-            const int row = c.row0 + r;
-            const float* bias = p.bias ? p.bias + c.g * p.bias_gs : nullptr;
-            if (bias && p.bias_crop_stride) bias += (size_t)((row_ok ? row : c.row0) / p.rows_per_crop) * p.bias_crop_stride;
-            float* pool = s_pool + ab * 4 * P_BN;
-            mbar_wait(acc_full + ab, (ti >> 1) & 1);
-            tc_fence_after();
-#pragma unroll 1
-            for (int ch = 0; ch < P_BN / 32; ++ch) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + lane_base + ab * P_BN + ch * 32, v);
-                const int col = c.n0 + ch * 32;
-                float f[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float x = __uint_as_float(v[i]);
-                    if (bias && col + i < p.N) x += __ldg(bias + col + i);
-                    if (p.relu) x = fmaxf(x, 0.0f);
-                    f[i] = x;
-                }
-                if (p.pool_partial) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = row_ok ? f[i] : 0.0f;
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) {
-                        const bool up = (lane & off) != 0;
-#pragma unroll
-                        for (int i = 0; i < off; ++i) {
-                            const float send = up ? f[i] : f[i + off];
-                            const float keep = up ? f[i + off] : f[i];
-                            f[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                        }
-                    }
-                    pool[q * P_BN + ch * 32 + lane] = f[0];
-                } else {
-                    // transpose through shared memory: lane == row on the way in, 8 lanes == one 128 B row segment out
-                    __syncwarp();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<float4*>(stage + lane * P_STAGE_PITCH + j * 4) =
-                            make_float4(f[j * 4], f[j * 4 + 1], f[j * 4 + 2], f[j * 4 + 3]);
-                    __syncwarp();
-                    float* cbase = p.C + c.g * p.c_gs + (size_t)(c.row0 + q * 32) * p.ldc + col;
-                    const int rr = lane >> 3, cc = (lane & 7) * 4;
-#pragma unroll
-                    for (int ps = 0; ps < 8; ++ps) {
-                        const int lr = ps * 4 + rr;
-                        if (q * 32 + lr < c.rows_valid && col + cc < p.N) {
-                            const float4 o = *reinterpret_cast<const float4*>(stage + lr * P_STAGE_PITCH + cc);
-                            *reinterpret_cast<float4*>(cbase + (size_t)lr * p.ldc + cc) = o;
-                        }
-                    }
-                }
-            }
-            // all TMEM reads of this accumulator are complete (tcgen05.wait::ld in tmem_ld32): hand it back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + ab);
-            if (p.pool_partial) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int tt = threadIdx.x - 320;
-                if (c.n0 + tt < p.N) {
-                    const float s = ((pool[tt] + pool[P_BN + tt]) + pool[2 * P_BN + tt]) + pool[3 * P_BN + tt];
-                    p.pool_partial[((size_t)c.crop * p.tiles_per_crop + c.tile_in_crop) * p.N + c.n0 + tt] = s;
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
-    }
-}
-
-
 // ------------------------------------------------------------------------------------------------
 // Generation 2 of the persistent kernel ("q"): the A operand also arrives by TMA.
 //
@@ -586,6 +85,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tm_whi, const __gr
 // only for the store-free pooled epilogue), two A stages in [384,512).
 // ------------------------------------------------------------------------------------------------
 constexpr int Q_THREADS = 18 * 32;
+constexpr int Q_SPLIT_THREADS = 2 * 32;                      // RAW_W: two more warps split the fp32 weight tile on chip
+constexpr int Q_PLANES = 4;                                  // RAW_W: depth of the operand-plane / a_full / mma_done rings
 constexpr int Q_MAX_STAGES = 8;
 constexpr int Q_TILE = 128 * BK * 4;                         // 16 KB: one 128-row fp32 tile of 32 k
 constexpr int Q_SMEM_STAGES = 12 * Q_TILE;                   // 192 KB of operand stages: 4 x {A 16 KB | W_hi 16 | W_lo 16} for 128
@@ -666,8 +167,8 @@ __device__ __forceinline__ QTile q_decode(const TcParams& p, int t, int m_tiles,
     return c;
 }
 
-template <int CTAS, int A_STAGES>
-__global__ void __launch_bounds__(Q_THREADS, 1)
+template <int CTAS, int A_STAGES, bool RAW_W>
+__global__ void __launch_bounds__(RAW_W ? Q_THREADS + Q_SPLIT_THREADS : Q_THREADS, 1)
 gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_whi,
                  const __grid_constant__ CUtensorMap tm_wlo, const TcParams p, const int bn_cta, const int m_tiles,
                  const int n_tiles, const int total_tiles)
@@ -685,6 +186,13 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     uint64_t* acc_full = bars + 24;                 // [2]
     uint64_t* acc_empty = bars + 26;                // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+    // RAW_W (hybrid16 with the weight split on chip): the weight tile arrives as fp32 (4 instead of 6 bytes per element through
+    // the SM's fabric port, which bounds this kernel: profiles/r2_l2_ingest_probe.txt) and two splitter warps write the three
+    // 16-bit operand planes the MMAs read.  Stage s = {A | W fp32} is then read by threads only, so `empty[s]` counts the
+    // consumers (4 stager warps + 2 splitter warps) and the TMA may refill it while the MMAs of that k-block are still
+    // running; what the MMAs pin instead are the plane slot and the TMEM A slot of iteration `it`, released by mma_done[it & 3].
+    uint64_t* w_full = bars + 30;                   // [4]  operand planes of the iteration are written (splitter warps of the pair)
+    uint64_t* mma_done = bars + 34;                 // [4]  MMAs of the iteration have retired (commit)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;
@@ -692,13 +200,17 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int nkb = p.K / BK;
     const int bnt = bn_cta * CTAS;                  // tile width = accumulator columns
     const uint32_t w_bytes = (uint32_t)bn_cta * BK * 4;
-    const uint32_t stage_bytes = Q_TILE + 2 * w_bytes;             // A | W_hi | W_lo (or the bf16 pair tile), all 1024-B aligned
-    const uint32_t Q_STAGES = min((uint32_t)Q_MAX_STAGES, (uint32_t)Q_SMEM_STAGES / stage_bytes);
+    const uint32_t stage_bytes = RAW_W ? Q_TILE + w_bytes : Q_TILE + 2 * w_bytes;   // A | W_hi | W_lo (or the bf16 pair tile), all 1024-B aligned
+    const uint32_t plane_bytes = w_bytes + w_bytes / 2;            // RAW_W: [fp16(w) | bf16(w)] 128-byte rows, then bf16(w - fp16(w)) 64-byte rows
+    const uint32_t Q_STAGES = RAW_W ? min((uint32_t)Q_MAX_STAGES, ((uint32_t)Q_SMEM_STAGES - Q_PLANES * plane_bytes) / stage_bytes)
+                                    : min((uint32_t)Q_MAX_STAGES, (uint32_t)Q_SMEM_STAGES / stage_bytes);
+    uint8_t* planes = smem + (size_t)Q_STAGES * stage_bytes;
     const uint32_t ACC_BUFS = bnt <= ACC_STRIDE ? 2 : 1;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < Q_MAX_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); mbar_init(a_full + i, 4 * CTAS); }
+        for (int i = 0; i < Q_MAX_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, RAW_W ? 6 : 1); mbar_init(a_full + i, 4 * CTAS); }
         for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 8 * CTAS); }
+        for (int i = 0; i < Q_PLANES; ++i) { mbar_init(w_full + i, 2 * CTAS); mbar_init(mma_done + i, 1); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -720,7 +232,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // ------------------------------- TMA producer -------------------------------
         const uint32_t a_bytes = p.conv_taps ? (uint32_t)(p.TW * p.TH * p.TB) * BK * 4 : (uint32_t)Q_TILE;
         // 3xTF32: W_hi + W_lo; hybrid: W_hi + bf16 pair tile; hybrid16: pair tile + a half-width (64 B rows) correction tile
-        const uint32_t bytes = a_bytes + (p.precise == 3 ? w_bytes + w_bytes / 2 : (p.precise ? 2u : 1u) * w_bytes);
+        const uint32_t bytes = a_bytes + (RAW_W ? w_bytes : p.precise == 3 ? w_bytes + w_bytes / 2 : (p.precise ? 2u : 1u) * w_bytes);
         const int cblocks = p.conv_taps ? p.K / (BK * p.conv_taps) : 1;        // 32-channel blocks per tap
         uint32_t it = 0;
         for (int t = cid; t < total_tiles; t += ncl) {
@@ -757,9 +269,10 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         tma_load_2d(&tm_a, dst, full + s, acol + kb * BK, c.row0);
                     }
                     // first weight tile: 32 fp32 per row (TF32 hi part), or, hybrid16, [fp16(W) x32 | bf16(W) x32] = 64 halves per row
-                    tma_load_2d(&tm_whi, dst + Q_TILE, full + s, kb * (p.precise == 3 ? 2 * BK : BK) + wk0, wrow);
+                    // (RAW_W: the fp32 weights themselves, 32 per row)
+                    tma_load_2d(&tm_whi, dst + Q_TILE, full + s, kb * (!RAW_W && p.precise == 3 ? 2 * BK : BK) + wk0, wrow);
                     // second weight tile: W_lo (fp32), or [bf16(W) x32 | bf16(W_lo) x32] (hybrid), or bf16(W_lo) x32 in 64-byte rows (hybrid16)
-                    if (p.precise) tma_load_2d(&tm_wlo, dst + Q_TILE + w_bytes, full + s, kb * (p.precise == 2 ? 2 * BK : BK) + wk0, wrow);
+                    if (!RAW_W && p.precise) tma_load_2d(&tm_wlo, dst + Q_TILE + w_bytes, full + s, kb * (p.precise == 2 ? 2 * BK : BK) + wk0, wrow);
                 }
                 if (++cb == cblocks) { cb = 0; tap_list >>= 4; }
                 __syncwarp();
@@ -783,13 +296,15 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (CTAS == 2) mbar_wait_cluster(acc_empty + ab, aph); else mbar_wait(acc_empty + ab, aph);
                 const uint32_t acc = tmem_base + ab * ACC_STRIDE;
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = (int)(it % Q_STAGES);
-                    const uint32_t ph = (it / Q_STAGES) & 1;
-                    mbar_wait(full + s, ph);
+                    const int s = RAW_W ? (int)(it & (Q_PLANES - 1)) : (int)(it % Q_STAGES);
+                    const uint32_t ph = RAW_W ? (it / Q_PLANES) & 1 : (it / Q_STAGES) & 1;
+                    if (RAW_W) mbar_wait(w_full + s, ph);          // (implies full[]: the splitters waited for the TMA bytes)
+                    else mbar_wait(full + s, ph);
                     if (CTAS == 2) mbar_wait_cluster(a_full + s, ph); else mbar_wait(a_full + s, ph);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t w_hi = smem_u32(smem + (size_t)s * stage_bytes + Q_TILE);
+                        const uint32_t w_hi = RAW_W ? smem_u32(planes + (size_t)s * plane_bytes)
+                                                    : smem_u32(smem + (size_t)s * stage_bytes + Q_TILE);
                         const uint64_t bhi0 = sw128_desc(w_hi), blo0 = sw128_desc(w_hi + w_bytes);
                         const uint32_t a0 = tmem_base + TMEM_A0 + (it % A_STAGES) * 2 * BK;
                         if (p.precise == 3) {
@@ -844,11 +359,12 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                 }
                             }
                         }
+                        uint64_t* done = RAW_W ? mma_done + s : empty + s;
                         if (CTAS == 2) {
-                            umma_commit_pair(empty + s);
+                            umma_commit_pair(done);
                             if (kb == kb1 - 1) umma_commit_pair(acc_full + ab);
                         } else {
-                            umma_commit(empty + s);
+                            umma_commit(done);
                             if (kb == kb1 - 1) umma_commit(acc_full + ab);
                         }
                     }
@@ -857,12 +373,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               }
             }
         }
-    } else if (warp < 10) {
-        // ------------------------------- A stagers (two groups) ----------------------
-        const int grp = (warp - 2) >> 2;
-        const int q = warp & 3;
-        const int r = q * 32 + lane;
-        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    } else if (warp < 10 || (RAW_W && warp >= 18)) {
         const int my_tiles = (total_tiles - cid + ncl - 1) / ncl;
         uint32_t total_it = (uint32_t)my_tiles * nkb;
         if (p.conv_taps == 9) {                                          // tiles near the border visit fewer taps
@@ -873,6 +384,64 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) total_it += __shfl_xor_sync(0xffffffffu, total_it, off);
         }
+        if (RAW_W && warp >= 18) {
+            // ------------------------------- weight splitters (RAW_W, two warps) ---------
+            // unit = half a weight row (16 fp32 -> 8 fp16 pairs, 8 bf16 pairs, 8 bf16 pairs of the remainders); a warp's 32 lanes take
+            // 32 consecutive rows of one half, so the swizzled 16-byte reads and writes of a quarter warp hit 8 different bank groups
+            const int tid2 = (warp - 18) * 32 + lane;
+            const int upt = bn_cta >> 5;
+            for (uint32_t it = 0; it < total_it; ++it) {
+                const int s = (int)(it % Q_STAGES), m = (int)(it & (Q_PLANES - 1));
+                mbar_wait(full + s, (it / Q_STAGES) & 1);
+                if (it >= (uint32_t)Q_PLANES) mbar_wait(mma_done + m, ((it / Q_PLANES) & 1) ^ 1);     // plane slot m: MMAs of it - 4 retired
+                const uint8_t* wraw = smem + (size_t)s * stage_bytes + Q_TILE;
+                uint8_t* p1 = planes + (size_t)m * plane_bytes;
+                uint8_t* p2 = p1 + w_bytes;
+                for (int j = 0; j < upt; ++j) {
+                    const int u = j * 64 + tid2;
+                    const int half = u >= bn_cta ? 1 : 0;
+                    const int r = u - half * bn_cta;
+                    const int sw = r & 7, sw2 = (r >> 1) & 3;
+                    uint32_t h16[8], b16[8], l16[8];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(wraw + r * 128 + (((half * 4 + c) ^ sw) << 4));
+                        const float x0 = __uint_as_float(v.x), x1 = __uint_as_float(v.y), x2 = __uint_as_float(v.z), x3 = __uint_as_float(v.w);
+                        float f0, f1, f2, f3;
+                        h16[2 * c] = pack_f16x2_sat(x0, x1);
+                        h16[2 * c + 1] = pack_f16x2_sat(x2, x3);
+                        unpack_f16x2(h16[2 * c], f0, f1);
+                        unpack_f16x2(h16[2 * c + 1], f2, f3);
+                        b16[2 * c] = pack_bf16x2(x0, x1);
+                        b16[2 * c + 1] = pack_bf16x2(x2, x3);
+                        l16[2 * c] = pack_bf16x2(x0 - f0, x1 - f1);
+                        l16[2 * c + 1] = pack_bf16x2(x2 - f2, x3 - f3);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        *reinterpret_cast<uint4*>(p1 + r * 128 + (((2 * half + c) ^ sw) << 4)) =
+                            make_uint4(h16[4 * c], h16[4 * c + 1], h16[4 * c + 2], h16[4 * c + 3]);
+                        *reinterpret_cast<uint4*>(p1 + r * 128 + (((4 + 2 * half + c) ^ sw) << 4)) =
+                            make_uint4(b16[4 * c], b16[4 * c + 1], b16[4 * c + 2], b16[4 * c + 3]);
+                        *reinterpret_cast<uint4*>(p2 + r * 64 + (((2 * half + c) ^ sw2) << 4)) =
+                            make_uint4(l16[4 * c], l16[4 * c + 1], l16[4 * c + 2], l16[4 * c + 3]);
+                    }
+                }
+                // generic-proxy writes -> visible to the MMAs (async proxy).  The shared::cta form on purpose: the unqualified
+                // fence.proxy.async costs a MEMBAR.ALL.GPU per k-block (measured: tower-1 0.56 ms instead of 0.30)
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(empty + s);
+                    if (CTAS == 2) mbar_arrive_remote(w_full + m, 0); else mbar_arrive(w_full + m);
+                }
+            }
+        } else {
+        // ------------------------------- A stagers (two groups) ----------------------
+        const int grp = (warp - 2) >> 2;
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const int sw = r & 7;
         for (uint32_t it = grp; it < total_it; it += 2) {
             const int s = (int)(it % Q_STAGES);
@@ -918,7 +487,14 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     second[i] = __float_as_uint(x - __uint_as_float(hi[i]));
                 }
             }
-            if (A_STAGES < Q_STAGES && it >= (uint32_t)A_STAGES) {      // (the loads and the split above overlap this wait)
+            if (RAW_W) {
+                __syncwarp();                                           // the row is in registers: hand the stage back to the TMA
+                if (lane == 0) mbar_arrive(empty + s);
+                if (it >= (uint32_t)A_STAGES) {
+                    const uint32_t prev = it - A_STAGES;
+                    mbar_wait(mma_done + (prev & (Q_PLANES - 1)), (prev / Q_PLANES) & 1);
+                }
+            } else if (A_STAGES < Q_STAGES && it >= (uint32_t)A_STAGES) {      // (the loads and the split above overlap this wait)
                 const uint32_t prev = it - A_STAGES;
                 mbar_wait(empty + prev % Q_STAGES, (prev / Q_STAGES) & 1);
             }
@@ -930,8 +506,10 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (CTAS == 2) mbar_arrive_remote(a_full + s, 0); else mbar_arrive(a_full + s);
+                uint64_t* af = a_full + (RAW_W ? (int)(it & (Q_PLANES - 1)) : s);
+                if (CTAS == 2) mbar_arrive_remote(af, 0); else mbar_arrive(af);
             }
+        }
         }
     } else {
         // ------------------------------- epilogue (8 warps) --------------------------
@@ -1119,42 +697,6 @@ bool make_map(CUtensorMap* map, const float* base, long long rows, int K, int ld
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, bool A_TMEM>
-int launch_tc(const CUtensorMap& mhi, const CUtensorMap& mlo, const TcParams& p, int groups, cudaStream_t s)
-{
-    using C = Cfg<BN, A_TMEM>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, A_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             C::SMEM_TOTAL);
-        if (e != cudaSuccess) return (int)e;
-        attr_done = true;
-    }
-    const int mt = p.pool_partial ? (p.M / p.rows_per_crop) * p.tiles_per_crop : (p.M + BM - 1) / BM;
-    dim3 grid((p.N + BN - 1) / BN, mt, groups);
-    gemm_tc_kernel<BN, A_TMEM><<<grid, NUM_THREADS, C::SMEM_TOTAL, s>>>(mhi, mlo, p);
-    return 0;
-}
-
-int launch_persistent(const CUtensorMap& mhi, const CUtensorMap& mlo, const TcParams& p, int groups, cudaStream_t s)
-{
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaError_t e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(gemm_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_TOTAL);
-        if (e != cudaSuccess) { num_sms = 0; return (int)e; }
-    }
-    const int m_tiles = p.pool_partial ? (p.M / p.rows_per_crop) * p.tiles_per_crop : (p.M + BM - 1) / BM;
-    const int n_tiles = (p.N + P_BN - 1) / P_BN;
-    const int total = m_tiles * n_tiles * groups;
-    const int grid = total < num_sms ? total : num_sms;
-    gemm_tc_persistent_kernel<<<grid, P_THREADS, P_SMEM_TOTAL, s>>>(mhi, mlo, p, m_tiles, n_tiles, total);
-    return 0;
-}
-
 bool use_pdl();
 
 // hybrid mode: per weight row and 32-wide k-block 64 bf16 = [bf16(w) x32 | bf16(w - tf32_trunc(w)) x32]; row pitch 2K bf16
@@ -1199,9 +741,10 @@ bool make_map_nhwc(CUtensorMap* map, const float* base, int B, int H, int W, int
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int CTAS, int A_STAGES>
+template <int CTAS, int A_STAGES, bool RAW_W = false>
 int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw, int groups, cudaStream_t s)
 {
+    constexpr int THREADS = RAW_W ? Q_THREADS + Q_SPLIT_THREADS : Q_THREADS;
     TcParams p = p_in;
     {
         static int order = -1;
@@ -1231,18 +774,18 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
         cudaGetDevice(&dev);
         cudaError_t e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(gemm_tc_q_kernel<CTAS, A_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_TOTAL);
+        e = cudaFuncSetAttribute(gemm_tc_q_kernel<CTAS, A_STAGES, RAW_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_TOTAL);
         if (e != cudaSuccess) return (int)e;
         int n = num_sms / CTAS;
         if (CTAS == 2) {
             cudaLaunchConfig_t q = {};
-            q.gridDim = dim3(num_sms / 2 * 2); q.blockDim = dim3(Q_THREADS); q.dynamicSmemBytes = Q_SMEM_TOTAL;
+            q.gridDim = dim3(num_sms / 2 * 2); q.blockDim = dim3(THREADS); q.dynamicSmemBytes = Q_SMEM_TOTAL;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             q.attrs = at; q.numAttrs = 1;
             int occ = 0;
-            if (cudaOccupancyMaxActiveClusters(&occ, gemm_tc_q_kernel<CTAS, A_STAGES>, &q) == cudaSuccess && occ > 0 && occ < n) n = occ;
+            if (cudaOccupancyMaxActiveClusters(&occ, gemm_tc_q_kernel<CTAS, A_STAGES, RAW_W>, &q) == cudaSuccess && occ > 0 && occ < n) n = occ;
             (void)cudaGetLastError();
         }
         max_clusters = n;
@@ -1286,6 +829,10 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
     const long long wrows = p.wk_rows ? (long long)p.wk_rows * (p.N / p.wk_rows == 9 ? 3 : 1) : (long long)groups * p.N;
     if (p.wk_rows) {                                               // weight-gradient form: W spans every k slice (row length ldw)
         if (!make_map(&mhi, W_hi, wrows, ldw, ldw, bn_cta) || !make_map(&mlo, W_lo, wrows, ldw, ldw, bn_cta)) return DF_ERR_UNSUPPORTED;
+    } else if (RAW_W) {                                            // hybrid16, weights split on chip: the fp32 matrix itself
+        if (p.precise != 3) return DF_ERR_UNSUPPORTED;
+        if (!make_map(&mhi, W_hi, wrows, p.K, ldw, bn_cta)) return DF_ERR_UNSUPPORTED;
+        mlo = mhi;
     } else if (p.precise == 3) {                                   // hybrid16: both weight operands are packed 16-bit pair tensors
         if (ldw != p.K) return DF_ERR_UNSUPPORTED;
         if (!make_map_bf16_pairs(&mhi, W_hi, wrows, p.K, bn_cta) || !make_map_bf16_rows64(&mlo, W_lo, wrows, p.K, bn_cta))
@@ -1301,14 +848,14 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
     const int total = m_tiles * n_tiles * groups;
     const int clusters = total < max_clusters ? total : max_clusters;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(clusters * CTAS); cfg.blockDim = dim3(Q_THREADS); cfg.dynamicSmemBytes = Q_SMEM_TOTAL; cfg.stream = s;
+    cfg.gridDim = dim3(clusters * CTAS); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = Q_SMEM_TOTAL; cfg.stream = s;
     cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CTAS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = use_pdl() ? 2 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_q_kernel<CTAS, A_STAGES>, ma, mhi, mlo, p, bn_cta, m_tiles, n_tiles, total);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_q_kernel<CTAS, A_STAGES, RAW_W>, ma, mhi, mlo, p, bn_cta, m_tiles, n_tiles, total);
     return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -1340,7 +887,7 @@ int default_variant()
     if (!v) {
         const char* e = getenv("DF_TC_VARIANT");
         v = e ? atoi(e) : 0;
-        if (v < 4 || v > 7) v = 6;
+        if (v < 5 || v > 7) v = 6;
     }
     return v;
 }
@@ -1401,7 +948,8 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, float* __re
     }
     const float h0 = __uint_as_float(__float_as_uint(x[0]) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(x[1]) & 0xffffe000u);
     float* hrow = hi + (size_t)row * K + kp * 2;
-    hrow[0] = h0; hrow[1] = h1;
+    const bool raw = !lo && !pairs;                              // plain fp32 repack (hybrid16 with the split on chip)
+    hrow[0] = raw ? x[0] : h0; hrow[1] = raw ? x[1] : h1;
     if (lo) { float* lrow = lo + (size_t)row * K + kp * 2; lrow[0] = x[0] - h0; lrow[1] = x[1] - h1; }
     if (pairs) {
         const int kb = (kp * 2) / 32, j = kp - kb * 16;
@@ -1578,7 +1126,7 @@ extern "C" int df_pack_conv_weight16(const float* w, void* t1, void* t2, int Cou
 extern "C" int df_pack_conv_weight(const float* w, float* hi, float* lo, void* pairs, int Cout, int Cin, int taps, int rotate,
                                    void* stream)
 {
-    if (!w || !hi || (!lo && !pairs) || Cout <= 0 || Cin <= 0 || taps <= 0) return DF_ERR_ARG;
+    if (!w || !hi || Cout <= 0 || Cin <= 0 || taps <= 0) return DF_ERR_ARG;      // lo == pairs == NULL: hi = the repacked fp32 weights
     const int cols = rotate ? Cout : Cin, rows = rotate ? Cin : Cout;
     if ((taps * cols) % 32) return DF_ERR_ARG;
     const long long total = (long long)rows * (taps * cols / 2);
@@ -1618,8 +1166,8 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
     if (!A || !W_hi || (!C && !pool_partial)) return DF_ERR_ARG;
     const int run_units = (precision >> 8) & 0xff;                  // accumulation-run length in units of 12 MMA instructions
     precision &= 0xff;
-    if (precision < 1 || precision > 4) return DF_ERR_ARG;
-    if (precision != 2 && !W_lo) return DF_ERR_ARG;
+    if (precision < 1 || precision > 5) return DF_ERR_ARG;
+    if (precision != 2 && precision != 5 && !W_lo) return DF_ERR_ARG;
     if (M <= 0 || N <= 0 || K <= 0 || groups <= 0) return DF_ERR_ARG;
     if (K % BK || lda % 4 || ldw % 4 || N % 4 || a_group_stride % 4 || bias_group_stride % 4) return DF_ERR_ARG;
     if (((uintptr_t)A & 15) || ((uintptr_t)W_hi & 15) || ((uintptr_t)W_lo & 15)) return DF_ERR_ARG;
@@ -1631,43 +1179,26 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
     TcParams p = {};
     p.A = A; p.lda = lda; p.bias = bias; p.bias_crop_stride = bias_crop_stride;
     p.C = pool_partial ? nullptr : C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.relu = relu;
-    p.precise = precision == 1 ? 1 : (precision == 3 ? 2 : (precision == 4 ? 3 : 0));     // kernel-side: 0 single TF32, 1 3xTF32, 2 hybrid, 3 hybrid16
+    p.precise = precision == 1 ? 1 : (precision == 3 ? 2 : (precision >= 4 ? 3 : 0));     // kernel-side: 0 single TF32, 1 3xTF32, 2 hybrid, 3 hybrid16
     p.run_steps = run_units * 12;
     p.rows_per_crop = rows_per_crop > 0 ? rows_per_crop : M;
     p.a_gs = a_group_stride; p.bias_gs = bias_group_stride; p.c_gs = c_group_stride;
     p.pool_partial = pool_partial;
     p.tiles_per_crop = pool_partial ? (p.rows_per_crop + BM - 1) / BM : 0;
 
-    // variant: 0 = auto; 1 = BN128/TMEM-A, 2 = BN256/TMEM-A, 3 = BN128/smem-A (one tile per CTA, bring-up kernels);
-    // 4 = persistent kernel, A read from global by the stagers; 5 = persistent, A by TMA; 6 / 7 = 5 on CTA pairs
-    // (cta_group::2, 256-row tiles) with 2 / 4 TMEM A stages (accumulators up to 192 / 128 columns double-buffered)
+    // variant: 0 = auto (6); 5 = one CTA per tile; 6 / 7 = CTA pairs (cta_group::2, 256-row tiles) with 2 / 4 TMEM A stages
+    // (accumulators up to 192 / 128 columns double-buffered).  5 and 7 are kept for A/B measurements (DF_TC_VARIANT).
     int v = variant;
     if (v == 0) v = default_variant();
-    if (v >= 5 && v <= 7) {
-        const int rc = v == 5 ? launch_q<1, 4>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream)
-                     : v == 6 ? launch_q<2, 2>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream)
-                              : launch_q<2, 4>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream);
-        if (rc != DF_ERR_UNSUPPORTED || variant != 0) {
-            if (rc) return rc;
-            DF_RETURN_LAST_ERROR();
-        }
-        v = 4;                                   // auto mode: shapes the TMA-A form cannot address fall back to kernel 4
-    }
-    if (precision >= 3) return DF_ERR_UNSUPPORTED;       // the hybrid modes exist in the generation-2 kernels only
-    const int bn = v == 2 ? 256 : 128;
-    if (v == 2 && groups > 1 && N % 256) return DF_ERR_UNSUPPORTED;
-    CUtensorMap mhi, mlo;
-    const long long wrows = (long long)groups * N;
-    if (!make_map(&mhi, W_hi, wrows, K, ldw, bn)) return DF_ERR_UNSUPPORTED;
-    if (!make_map(&mlo, p.precise ? W_lo : W_hi, wrows, K, ldw, bn)) return DF_ERR_UNSUPPORTED;
-    cudaStream_t s = (cudaStream_t)stream;
     int rc;
-    if (v == 1) rc = launch_tc<128, true>(mhi, mlo, p, groups, s);
-    else if (v == 2) rc = launch_tc<256, true>(mhi, mlo, p, groups, s);
-    else if (v == 3) rc = launch_tc<128, false>(mhi, mlo, p, groups, s);
-    else if (v == 4) rc = launch_persistent(mhi, mlo, p, groups, s);
+    if (precision == 5) {                        // hybrid16 arithmetic, W_hi = the fp32 weights (split on chip): CTA-pair kernel only
+        if (variant != 0 && variant != 6) return DF_ERR_UNSUPPORTED;
+        rc = launch_q<2, 2, true>(p, W_hi, W_hi, ldw, groups, (cudaStream_t)stream);
+    } else if (v == 5) rc = launch_q<1, 4>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream);
+    else if (v == 6) rc = launch_q<2, 2>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream);
+    else if (v == 7) rc = launch_q<2, 4>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream);
     else return DF_ERR_ARG;
-    if (rc) return rc;
+    if (rc) return rc;                           // DF_ERR_UNSUPPORTED: a shape the TMA boxes cannot address (the caller runs df_gemm_fp32)
     DF_RETURN_LAST_ERROR();
 }
 
@@ -1680,8 +1211,8 @@ extern "C" int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx,
     if (!X || !W_hi || !Y || B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return DF_ERR_ARG;
     const int run_units = (precision >> 8) & 0xff;
     precision &= 0xff;
-    if (precision < 1 || precision > 4) return DF_ERR_ARG;
-    if (precision != 2 && !W_lo) return DF_ERR_ARG;
+    if (precision < 1 || precision > 5) return DF_ERR_ARG;
+    if (precision != 2 && precision != 5 && !W_lo) return DF_ERR_ARG;
     if ((taps != 1 && taps != 9) || dilation < 1 || act < 0 || act > 2 || (act == 2 && !prelu)) return DF_ERR_ARG;
     if (Cin % BK || Cout % 4 || ldx % 4 || ldy % 4 || ldx < Cin || ldy < Cout || (residual && (ldr % 4 || ldr < Cout))) return DF_ERR_ARG;
     if (((uintptr_t)X & 15) || ((uintptr_t)Y & 15) || ((uintptr_t)W_hi & 15) || ((uintptr_t)W_lo & 15) ||
@@ -1692,7 +1223,7 @@ extern "C" int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx,
     TcParams p = {};
     p.A = X; p.lda = ldx; p.bias = bias; p.bias_crop_stride = 0; p.C = Y; p.ldc = ldy;
     p.M = B * H * W; p.N = Cout; p.K = taps * Cin; p.relu = act;
-    p.precise = precision == 1 ? 1 : (precision == 3 ? 2 : (precision == 4 ? 3 : 0));
+    p.precise = precision == 1 ? 1 : (precision == 3 ? 2 : (precision >= 4 ? 3 : 0));
     p.run_steps = run_units * 12;
     p.rows_per_crop = p.M; p.a_gs = 0; p.bias_gs = 0; p.c_gs = 0; p.pool_partial = nullptr; p.tiles_per_crop = 0;
     p.conv_taps = taps; p.conv_dil = dilation; p.cW = W; p.cH = H; p.cB = B;
@@ -1721,7 +1252,8 @@ extern "C" int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx,
         }
     }
     p.tiles_x = (W + p.TW - 1) / p.TW; p.tiles_y = (H + p.TH - 1) / p.TH; p.tiles_b = (B + p.TB - 1) / p.TB;
-    const int rc = launch_q<2, 2>(p, W_hi, W_lo, taps * Cin, 1, (cudaStream_t)stream);
+    const int rc = precision == 5 ? launch_q<2, 2, true>(p, W_hi, W_hi, taps * Cin, 1, (cudaStream_t)stream)
+                                  : launch_q<2, 2>(p, W_hi, W_lo, taps * Cin, 1, (cudaStream_t)stream);
     if (rc) return rc;
     DF_RETURN_LAST_ERROR();
 }

@@ -1,16 +1,21 @@
 """Drop-in PoseNet / PoseRefineNet (reference: lib/network.py:70-132 and :170-206).
 
-Same constructor arguments, forward signatures, return shapes and state_dict keys as the reference, so
-reference checkpoints and call sites work unchanged -- but the dense-fusion head and the refiner run as
-hand-written sm_100a kernels through the C ABI (densefusion_b200.engine), not as ~25 cuDNN/cuBLAS calls.
-The colour encoder (`cnn`) stays a torch/cuDNN module.
+Same constructor arguments, forward signatures, return shapes and state_dict keys as the reference, so reference
+checkpoints and call sites (tools/eval_ycb.py:192,212; tools/train.py:152-158) work unchanged -- but the colour encoder,
+the dense-fusion head and the refiner run as hand-written sm_100a kernels through the C ABI (densefusion_b200.encoder /
+engine), not as ~60 cuDNN / cuBLAS calls.
 
-Additive API (not in the reference): `forward_batched` evaluates every crop of the batch (the reference
-returns batch element 0 only, lib/network.py:123-126) and `precision` selects the GEMM arithmetic:
-"fp32" (exact FFMA, default), "3xtf32" (tcgen05, error-compensated, fp32-parity) or "tf32".
+Additive API (not in the reference): `forward_batched` evaluates every crop of the batch (the reference returns batch
+element 0 only, lib/network.py:123-126) and the attribute `precision` selects the GEMM arithmetic:
+    "hybrid16" (default)  tcgen05, fp16 main term + bf16 correction terms, fp32 accumulate: fp32 parity (<= 1e-4 on poses,
+                          measured 2-3e-5) for operands inside fp16's range; "hybrid" / "3xtf32": the same bound with no
+                          range restriction; "tf32": single pass, stated looser bound; "fp32": exact FFMA kernels and the
+                          torch/cuDNN strict-fp32 encoder (parity-check mode).
+Inference (eval() mode, no autograd) with a tensor-core precision uses densefusion_b200.encoder; a train()-mode module keeps
+the module graph of lib/pspnet.py (Dropout2d active) with its convolutions on lib/conv_tc.py.
 
-Training: when autograd is enabled and something requires grad, forward goes through the explicit backward
-kernels of densefusion_b200.training (exact fp32); there is no torch-op fallback on the activation path."""
+Training: when autograd is enabled and something requires grad, forward goes through the explicit backward kernels of
+densefusion_b200.training (arithmetic: training.PRECISION); there is no torch-op fallback on the activation path."""
 from __future__ import annotations
 
 import torch
@@ -77,7 +82,7 @@ def _no_autograd(module: nn.Module, *inputs):
 
 
 class _PackedMixin:
-    precision = "fp32"
+    precision = "hybrid16"
 
     def _packed(self, cls):
         ver = engine.param_version(self)
@@ -129,6 +134,12 @@ class PoseNet(nn.Module, _PackedMixin):
                                   out_r, out_t, out_c, self.precision)
         return out_r, out_t, out_c
 
+    def _tc_encoder_ok(self, img) -> bool:
+        """The hand-written inference encoder applies: a tensor-core precision, CUDA, crop sides that are multiples of 8, and the
+        module in eval() mode -- it has no Dropout2d (lib/pspnet.py:46,52), so a train()-mode estimator keeps the module graph."""
+        return (self.precision != "fp32" and img.is_cuda and not self.training and img.shape[2] % 8 == 0
+                and img.shape[3] % 8 == 0)
+
     def _embedding_tc(self, img, choose):
         """Inference with a tensor-core precision: the hand-written encoder (densefusion_b200.encoder), embedding
         evaluated at the chosen pixels only.  Returns point-major (B*N,32) and the reference's (B,32,N) layout."""
@@ -144,8 +155,7 @@ class PoseNet(nn.Module, _PackedMixin):
 
     def forward_batched(self, img, x, choose, obj):
         """All crops: (B,N,4), (B,N,3), (B,N,1), emb (B,32,N) detached."""
-        if self.precision != "fp32" and img.is_cuda and not _needs_grad(self, img, x) and img.shape[2] % 8 == 0 \
-                and img.shape[3] % 8 == 0:
+        if self._tc_encoder_ok(img) and not _needs_grad(self, img, x):
             emb_pm, emb_cm = self._embedding_tc(img, choose)
             r, t, c = self.head(x, emb_pm, obj)
             return r, t, c, emb_cm
@@ -166,7 +176,7 @@ class PoseNet(nn.Module, _PackedMixin):
             r, t, c, emb_cm = self.forward_batched(img, x, choose, obj)
             return r[0:1], t[0:1], c[0:1], emb_cm
         n = x.shape[1]
-        if self.precision != "fp32" and img.is_cuda and img.shape[2] % 8 == 0 and img.shape[3] % 8 == 0:
+        if self._tc_encoder_ok(img):
             emb_pm, emb_cm = self._embedding_tc(img, choose)          # tensor-core encoder, like forward_batched
         else:
             emb_pm, emb_cm = ops.gather_embedding(self.cnn(img), choose)

@@ -13,7 +13,11 @@ from ._C import check, f32c, i64c, lib, need_cuda, ptr, stream
 
 # "hybrid": TF32 main term + the two ~2^-11 correction terms in bf16 (8 instead of 12 MMAs per k-block), fp32-parity like
 # "3xtf32"; generation-2 tensor-core kernels only
-PRECISIONS = {"fp32": 0, "3xtf32": 1, "tf32": 2, "hybrid": 3, "hybrid16": 4}
+# "hybrid16": fp16 main term + bf16 correction terms (6 MMAs per k-block); the weight operand is the fp32 matrix itself, split
+# into its three 16-bit planes on chip (4 instead of 6 bytes per weight element through the SM's fabric port, the resource that
+# bounds the kernel).  "hybrid16p": the same arithmetic, bit for bit, with the planes packed once on the host side of the launch
+# (the round-1 form, kept for A/B measurements and as the cross-check of the on-chip split).
+PRECISIONS = {"fp32": 0, "3xtf32": 1, "tf32": 2, "hybrid": 3, "hybrid16p": 4, "hybrid16": 5}
 
 
 def sym_mask(sym_list: Iterable[int]) -> int:
@@ -123,7 +127,11 @@ class SplitWeight:
         self.hi = self.lo = self.bf = self.h16 = None
 
     def operands(self, mode: int):
-        """The two weight operands df_gemm_tc / df_conv_tc expect for a PRECISIONS code (1 3xtf32, 2 tf32, 3 hybrid, 4 hybrid16)."""
+        """The two weight operands df_gemm_tc / df_conv_tc expect for a PRECISIONS code (1 3xtf32, 2 tf32, 3 hybrid, 4 hybrid16p,
+        5 hybrid16: the fp32 weights themselves)."""
+        if mode == 5:
+            need_cuda(self.w)
+            return self.w, self.w
         return self.pairs16() if mode == 4 else (self.pairs() if mode == 3 else self.split())
 
     def pairs16(self):
@@ -180,8 +188,9 @@ def gemm(A, W, bias, C, *, M, N, K, lda, ldw, ldc, relu, precision="fp32", bias_
         st = lib.df_gemm_tc(ptr(A), lda, ptr(hi), ptr(lo), ldw, ptr(bias), bias_crop_stride, ptr(C), ldc, M, N, K,
                             1 if relu else 0, rows_per_crop, groups, a_gs, bias_gs, c_gs, ptr(pool_partial),
                             mode | (SHORT_RUNS if short_runs else 0), TC_VARIANT, stream())
-        check(st, "df_gemm_tc")
-        return
+        if st != -2:                 # -2: a shape the TMA boxes cannot address -> the exact-fp32 kernel below, like tc_eligible
+            check(st, "df_gemm_tc")
+            return
     Wt = sw.w if sw is not None else W
     st = lib.df_gemm_fp32(ptr(A), lda, ptr(Wt), ldw, ptr(bias), bias_crop_stride, ptr(C), ldc, M, N, K,
                           1 if relu else 0, rows_per_crop, groups, a_gs, w_gs, bias_gs, c_gs,

@@ -28,15 +28,16 @@ class PoseEstimator:
         self.channels_last = channels_last
         self.n = estimator.num_points
         self.device = next(estimator.parameters()).device
-        self.w_head = engine.PackedPoseNetHead(estimator)
-        self.w_ref = engine.PackedRefiner(refiner)
+        self._w_ver = None
+        self._retired = []            # workspaces / packed weights a captured CUDA graph may still point to: never freed
+        self.refresh()
         self._ws_head = None
         self._ws_ref = None
         self._bufs: Dict[int, dict] = {}
         # encoder: "tc" = densefusion_b200.encoder (tcgen05 implicit-GEMM convolutions, same arithmetic mode as the head),
         # "torch" = the torch/cuDNN module; "auto" = tc whenever the head runs on the tensor cores
         if encoder == "auto":
-            encoder = "tc" if precision in ("3xtf32", "tf32", "hybrid", "hybrid16") else "torch"
+            encoder = "tc" if precision in ("3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16p") else "torch"
         if encoder not in ("tc", "torch"):
             raise ValueError("encoder must be 'auto', 'tc' or 'torch'")
         self.encoder = encoder
@@ -46,10 +47,28 @@ class PoseEstimator:
         if channels_last:
             estimator.cnn.to(memory_format=torch.channels_last)
 
+    # ---- weights ------------------------------------------------------------------------------
+    def refresh(self) -> bool:
+        """Re-pack the GEMM operands when the modules' parameters changed (load_state_dict, an optimiser step).  Called at the
+        start of every eager estimate; CUDA graphs captured earlier keep replaying the weights they were captured with (their
+        packed tensors stay alive in `_retired`) -- re-capture after a refresh that returns True."""
+        ver = (engine.param_version(self.estimator), engine.param_version(self.refiner))
+        if ver == self._w_ver:
+            return False
+        if self._w_ver is not None:
+            self._retired.append((self.w_head, self.w_ref, getattr(self, "_enc", None)))
+            self._enc = None
+        self.w_head = engine.PackedPoseNetHead(self.estimator)
+        self.w_ref = engine.PackedRefiner(self.refiner)
+        self._w_ver = ver
+        return True
+
     # ---- scratch ------------------------------------------------------------------------------
     def _workspaces(self, crops: int):
         c = min(crops, self.chunk)
         if self._ws_head is None or self._ws_head.crops < c:
+            if self._ws_head is not None:          # a captured graph has the old buffers' addresses baked in: keep them allocated
+                self._retired.append((self._ws_head, self._ws_ref))
             self._ws_head = engine.Workspace(c, self.n, self.device, True)
             self._ws_ref = engine.Workspace(c, self.n, self.device, False)
         return self._ws_head, self._ws_ref
@@ -146,6 +165,8 @@ class PoseEstimator:
     def estimate(self, img, cloud, choose, obj, iterations: Optional[int] = None) -> torch.Tensor:
         """One (H,W) bucket: img (B,3,H,W), cloud (B,N,3), choose (B,1,N), obj (B,)|(B,1) -> (B,7) f64."""
         B = cloud.shape[0]
+        if not torch.cuda.is_current_stream_capturing():
+            self.refresh()
         buf = self._buffers(B)
         self.encode(img, choose, buf["emb_pm"])
         return self.head_and_refine(cloud, buf["emb_pm"], obj, iterations)
@@ -157,6 +178,8 @@ class PoseEstimator:
         total = sum(b["cloud"].shape[0] for b in buckets)
         if total == 0:
             return torch.empty(0, 7, device=self.device, dtype=torch.float64)
+        if not torch.cuda.is_current_stream_capturing():
+            self.refresh()
         buf = self._buffers(total)
         key = ("cat", total)
         cat = self._bufs.get(key)

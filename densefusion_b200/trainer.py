@@ -72,12 +72,19 @@ class FlatArena:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
 
+    def mark_updated(self) -> None:
+        """The arena was written through a raw pointer (optimiser kernel, graph replay, load_state): neither data_ptr() nor
+        ._version of the parameters changes by itself, so bump the versions -- engine.param_version keys the packed-weight
+        caches of PoseNet / PoseRefineNet / the encoder on them, and a stale cache would evaluate old weights."""
+        torch.autograd.graph.increment_version(self.params)
+
     def adam_step(self, lr: float, betas=(0.9, 0.999), eps: float = 1e-8) -> None:
         if not self.param.is_cuda:
             raise DFError("FlatArena.adam_step: the optimiser step is a CUDA kernel (no CPU fallback)")
         check(lib.df_adam_step_dev(ptr(self.param), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.total,
                                    float(lr), float(betas[0]), float(betas[1]), float(eps), ptr(self.step_dev), stream()),
               "df_adam_step_dev")
+        self.mark_updated()
 
     def reset_optimizer(self) -> None:
         """A fresh Adam: moments and step count back to zero (the reference builds a new optimiser on every schedule switch)."""
@@ -91,6 +98,7 @@ class FlatArena:
     def load_state(self, st: dict) -> None:
         for k, v in st.items():
             getattr(self, k).copy_(v)
+        self.mark_updated()
 
 
 class DataParallelTrainer:
@@ -207,4 +215,6 @@ class GraphedTrainStep:
         if buckets is not None:
             self.load(buckets)
         self.graph.replay()
+        arena = self.trainer.arena_est if self.trainer.phase == "estimator" else self.trainer.arena_ref
+        arena.mark_updated()                 # the replayed Adam kernel changed the weights behind autograd's back
         return self.out

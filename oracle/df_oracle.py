@@ -404,6 +404,61 @@ def estimate_and_refine(sd_est, sd_ref, img, cloud, choose, obj, num_obj, iterat
 # ----------------------------------------------------------------------------------------------
 # Training step (tools/train.py:143-169): per-sample forward + backward, gradients accumulate (SUM)
 # ----------------------------------------------------------------------------------------------
+def posenet_state_shapes(num_obj: int) -> dict:
+    """Parameter names and shapes of the reference PoseNet's state_dict (lib/network.py:27-37,40-49,73-91; lib/pspnet.py:40-60;
+    lib/extractors.py:78-103), as a static table: lets a caller build synthetic weights without constructing any module."""
+    sh = {"cnn.model.module.feats.conv1.weight": (64, 3, 7, 7)}
+    cin = 64
+    for li, cout in enumerate((64, 128, 256, 512), 1):
+        for bi in (0, 1):
+            pre = f"cnn.model.module.feats.layer{li}.{bi}."
+            sh[pre + "conv1.weight"] = (cout, cin if bi == 0 else cout, 3, 3)
+            sh[pre + "conv2.weight"] = (cout, cout, 3, 3)
+            if bi == 0 and cin != cout:
+                sh[pre + "downsample.0.weight"] = (cout, cin, 1, 1)
+        cin = cout
+    for i in range(4):
+        sh[f"cnn.model.module.psp.stages.{i}.1.weight"] = (512, 512, 1, 1)
+    sh["cnn.model.module.psp.bottleneck.weight"] = (1024, 2560, 1, 1)
+    sh["cnn.model.module.psp.bottleneck.bias"] = (1024,)
+    for name, co, ci in (("up_1", 256, 1024), ("up_2", 64, 256), ("up_3", 64, 64)):
+        sh[f"cnn.model.module.{name}.conv.1.weight"] = (co, ci, 3, 3)
+        sh[f"cnn.model.module.{name}.conv.1.bias"] = (co,)
+        sh[f"cnn.model.module.{name}.conv.2.weight"] = (1,)
+    sh["cnn.model.module.final.0.weight"] = (32, 64, 1, 1)
+    sh["cnn.model.module.final.0.bias"] = (32,)
+    sh["cnn.model.module.classifier.0.weight"] = (256, 256)
+    sh["cnn.model.module.classifier.0.bias"] = (256,)
+    sh["cnn.model.module.classifier.2.weight"] = (21, 256)
+    sh["cnn.model.module.classifier.2.bias"] = (21,)
+    for name, co, ci in (("conv1", 64, 3), ("conv2", 128, 64), ("e_conv1", 64, 32), ("e_conv2", 128, 64), ("conv5", 512, 256),
+                         ("conv6", 1024, 512)):
+        sh[f"feat.{name}.weight"] = (co, ci, 1)
+        sh[f"feat.{name}.bias"] = (co,)
+    for layer, co, ci in ((1, 640, 1408), (2, 256, 640), (3, 128, 256)):
+        for b in "rtc":
+            sh[f"conv{layer}_{b}.weight"] = (co, ci, 1)
+            sh[f"conv{layer}_{b}.bias"] = (co,)
+    for b, k in (("r", 4), ("t", 3), ("c", 1)):
+        sh[f"conv4_{b}.weight"] = (num_obj * k, 128, 1)
+        sh[f"conv4_{b}.bias"] = (num_obj * k,)
+    return sh
+
+
+def refiner_state_shapes(num_obj: int) -> dict:
+    """The same for PoseRefineNet (lib/network.py:134-146,170-183)."""
+    sh = {}
+    for name, co, ci in (("conv1", 64, 3), ("conv2", 128, 64), ("e_conv1", 64, 32), ("e_conv2", 128, 64), ("conv5", 512, 384),
+                         ("conv6", 1024, 512)):
+        sh[f"feat.{name}.weight"] = (co, ci, 1)
+        sh[f"feat.{name}.bias"] = (co,)
+    for b, k in (("r", 4), ("t", 3)):
+        sh[f"conv1_{b}.weight"], sh[f"conv1_{b}.bias"] = (512, 1024), (512,)
+        sh[f"conv2_{b}.weight"], sh[f"conv2_{b}.bias"] = (128, 512), (128,)
+        sh[f"conv3_{b}.weight"], sh[f"conv3_{b}.bias"] = (num_obj * k, 128), (num_obj * k,)
+    return sh
+
+
 def _leaf_state_dict(sd: dict) -> dict:
     return {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
 

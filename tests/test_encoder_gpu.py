@@ -53,7 +53,7 @@ def test_conv_tc_vs_float64(B, H, W, Cin, Cout, taps, dil, extras):
                             bias=None if bias is None else bias.cuda(), residual=None if res is None else _nhwc(res).cuda(),
                             prelu=slope.cuda() if extras == "prelu" else None,
                             act={"relu": 1, "residual": 1, "prelu": 2, "none": 0}[extras],
-                            mode={"3xtf32": 1, "tf32": 2, "hybrid": 3, "hybrid16": 4}[precision])
+                            mode=ops.PRECISIONS[precision])
         torch.cuda.synchronize()
         err = rel(out.permute(0, 3, 1, 2), want)
         print(f"conv {taps}tap dil{dil} {Cin}->{Cout} {H}x{W}x{B} {precision}: {err:.3e}")

@@ -102,6 +102,38 @@ def test_batched_buckets_graph_and_oracle():
     assert np.array_equal(out2, poses)
 
 
+@pytest.mark.parametrize("n,precision", [(500, "hybrid16"), (1000, "hybrid16"), (500, "hybrid")])
+def test_mixed_buckets_graphed_tensor_core_vs_oracle(n, precision):
+    """The bench's configuration in small: three crop-size buckets, the default tensor-core arithmetic, chunked head, side
+    streams per bucket, CUDA-graph replay -- every pose against the oracle's estimate + 2 refine iterations (<= 1e-4 in the
+    max-norm of the 7-vector and element-wise with an absolute floor), also at the reference's N = 1000 points."""
+    from densefusion_b200.pipeline import GraphedBuckets, PoseEstimator
+    from util import rel_elementwise
+    o, m = 21, 500
+    est, ref, est_sd, ref_sd = build_nets(n, o, seed=11)
+    sizes = [(80, 80), (120, 120), (160, 160)]
+    counts = [3, 2, 2]
+    buckets_cpu = [synth.batch_crops(range(70 + 10 * i, 70 + 10 * i + c), num_points=n, num_pt_mesh=m, num_obj=o, hw=hw)
+                   for i, (hw, c) in enumerate(zip(sizes, counts))]
+    pipe = PoseEstimator(est, ref, iterations=2, precision=precision, chunk_crops=4)       # 7 crops -> 2 chunks
+    graphed = GraphedBuckets(pipe, [(c, h, w) for c, (h, w) in zip(counts, sizes)])
+    host = [dict(img=b["img"].pin_memory(), cloud=b["points"].pin_memory(), choose=b["choose"].pin_memory(),
+                 obj=b["idx"].view(-1).pin_memory()) for b in buckets_cpu]
+    graphed.load(host)
+    poses = graphed.run().cpu().numpy().copy()
+    assert poses.shape == (sum(counts), 7)
+    k, worst = 0, 0.0
+    for b in buckets_cpu:
+        for i in range(b["points"].shape[0]):
+            want = O.estimate_and_refine(est_sd, ref_sd, b["img"][i:i + 1], b["points"][i:i + 1], b["choose"][i:i + 1],
+                                         b["idx"][i:i + 1], o, 2)
+            e, ee = rel(poses[k], want), rel_elementwise(poses[k], want, floor=1e-2)
+            worst = max(worst, e)
+            assert e < 1e-4 and ee < 2e-3, (k, e, ee, poses[k], want)
+            k += 1
+    print(f"graphed mixed buckets {precision} n={n}: worst pose error {worst:.3e}")
+
+
 def test_streaming_estimator_equals_direct_calls():
     """Double-buffered serving loop (H2D of batch i+1 overlapping the compute of batch i) returns, for every batch,
     exactly the poses of a direct estimate_buckets call."""

@@ -254,6 +254,38 @@ def test_trainer_step_matches_oracle_adam(phase, torch_encoder):
         assert worst["head"][0] < 0.02 and worst["cnn"][0] < 0.25
 
 
+@pytest.mark.parametrize("graphed", [False, True])
+def test_packed_weight_caches_follow_the_optimizer(graphed):
+    """The optimiser writes the parameter arena through a raw pointer (and, graphed, from a replayed launch): data_ptr() and
+    ._version of the parameters would not move, so FlatArena bumps the versions itself.  step -> eval -> step -> eval: every
+    evaluation through the cached packed weights must equal a freshly built module loaded with the current state_dict."""
+    from densefusion_b200.lib.network import PoseRefineNet
+    from densefusion_b200.trainer import DataParallelTrainer, GraphedTrainStep
+    torch.backends.cudnn.allow_tf32 = False
+    g, crops, n, o, m, iters, sym, w, est, ref, est_sd, ref_sd = _setup()
+    est.eval()
+    tr = DataParallelTrainer(est, ref, m, sym, lr=1e-3, w=w, iteration=iters, phase="refiner")
+    batch = [_device_batch(crops)]
+    step = GraphedTrainStep(tr, batch).step if graphed else tr.step
+    gen = torch.Generator().manual_seed(3)
+    x = (torch.randn(2, n, 3, generator=gen) * 0.05).cuda()
+    emb_pm = torch.cat([synth.synth_embedding(300 + i, n) for i in range(2)], 0).permute(0, 2, 1).reshape(2 * n, 32).contiguous().cuda()
+    obj = torch.tensor([3, 12]).cuda()
+    def evaluate(net):
+        with torch.no_grad():
+            return [t.clone() for t in net.refine(x, emb_pm, obj)]
+    prev = evaluate(ref)                                                 # builds the packed-weight cache
+    for it in range(2):
+        step(batch)
+        got = evaluate(ref)
+        fresh = PoseRefineNet(n, o).cuda().eval().requires_grad_(False)
+        fresh.load_state_dict(ref.state_dict())
+        want = evaluate(fresh)
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1]), f"stale packed weights after step {it + 1}"
+        assert not torch.equal(got[0], prev[0])                          # the step did change the weights
+        prev = got
+
+
 @pytest.mark.parametrize("phase", ["estimator", "refiner"])
 def test_graphed_train_step_equals_eager(phase):
     """The whole optimiser step captured in a CUDA graph (device-resident Adam step counter) replays to the same

@@ -15,6 +15,15 @@ def rel(a, b):
     return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-30))
 
 
+def rel_elementwise(a, b, floor=1e-3):
+    """max_i |a_i - b_i| / max(|b_i|, floor * max|b|): element-wise relative error with an absolute floor, so that outputs near
+    zero (e.g. pred_t offsets) are not judged against the largest entry of the tensor only."""
+    a = a.detach().cpu().double().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    b = b.detach().cpu().double().numpy() if torch.is_tensor(b) else np.asarray(b, dtype=np.float64)
+    den = np.maximum(np.abs(b), floor * (np.max(np.abs(b)) + 1e-30))
+    return float(np.max(np.abs(a - b) / den))
+
+
 def build_nets(num_points, num_obj, seed, device="cuda"):
     """Drop-in modules loaded with the by-name synthetic weights (same values the golden script loaded into
     the reference modules)."""
