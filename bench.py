@@ -41,16 +41,18 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("DF_PRECISION", "hybrid16"), choices=["fp32", "3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16p"])
+    ap.add_argument("--precision", default=os.environ.get("DF_PRECISION", "hybrid16"), choices=["fp32", "3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16w"])
     ap.add_argument("--frames", type=int, default=32, help="frames (of 8 objects) per GPU per step")
     ap.add_argument("--chunk", type=int, default=128, help="crops per head chunk (measured 16: 21.7 ms, 32: 20.7, 64: 20.3, 128: 20.05 per step)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed configuration")
     ap.add_argument("--encoder", default="auto", choices=["auto", "tc", "torch"],
                     help="tc: hand-written tensor-core encoder (default with a tensor-core precision); torch: cuDNN fp32")
-    ap.add_argument("--workload", default="pose", choices=["pose", "train"],
-                    help="pose: the headline metric; train: config C4, data-parallel training step (16 samples / GPU / step)")
+    ap.add_argument("--workload", default="pose", choices=["pose", "train", "c0", "c1"],
+                    help="pose: the headline metric; train: config C4, data-parallel training step (16 samples / GPU / step); "
+                         "c0: LineMOD batch-1 per-stage latencies (CPU port beside the GPU drop-ins); c1: PoseNet forward + ADD-S loss, 256 crops")
     ap.add_argument("--phase", default="estimator", choices=["estimator", "refiner"])
     ap.add_argument("--num-points", type=int, default=500,
                     help="points per crop: 500 = the configuration the metric is quoted on; 1000 = the reference's YCB setting (config C2 variant)")
@@ -60,9 +62,17 @@ def parse():
     return args
 
 
-def workload_name(frames):
-    return (f"YCB PoseNet({N_POINTS},21) + {ITERS} PoseRefineNet iterations (eval_ycb pipeline), {frames} synthetic frames x 8 "
-            f"objects per GPU per step, crops 3x80^2+3x120^2+2x160^2, CNN encoder included")
+def workload_name():
+    return (f"YCB PoseNet({N_POINTS},21) + {ITERS} PoseRefineNet iterations (eval_ycb pipeline), synthetic frames x 8 objects, "
+            f"crops 3x80^2+3x120^2+2x160^2 per frame, CNN encoder included")
+
+
+def workload_config(frames, world):
+    """The workload description shared verbatim by both arms (everything implementation-specific lives in `impl_config`)."""
+    return {"workload": workload_name(), "num_points": N_POINTS, "num_obj": N_OBJ, "refine_iterations": ITERS,
+            "frames_per_gpu_per_step": frames, "crops_per_gpu_per_step": frames * len(CROP_MIX),
+            "l2": "two alternating input sets per rank; the per-step working set (> 1 GB of encoder activations) exceeds the 126 MB L2",
+            "parallelism": f"frames sharded over {world} GPU(s), no data-path collective"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -87,12 +97,19 @@ def make_host_buckets(frames: int, seed: int, pin: bool):
     return buckets
 
 
+def synthetic_state_dicts(num_obj=None):
+    """Random-init weights by parameter name.  Needs neither the product modules nor the CUDA library: the shape table is the
+    oracle's static restatement of the reference state_dict (the reference arm must not load libdensefusion_b200.so)."""
+    from densefusion_b200 import synth              # torch-only module of the package (no ctypes import)
+    from oracle import df_oracle as O
+    o = N_OBJ if num_obj is None else num_obj
+    return synth.synth_state_dict(O.posenet_state_shapes(o), 0), synth.synth_state_dict(O.refiner_state_shapes(o), 1)
+
+
 def build_modules(device):
-    from densefusion_b200 import synth
     from densefusion_b200.lib.network import PoseNet, PoseRefineNet
     est, ref = PoseNet(N_POINTS, N_OBJ), PoseRefineNet(N_POINTS, N_OBJ)
-    est_sd = synth.synth_state_dict(synth.shapes_of(est), 0)
-    ref_sd = synth.synth_state_dict(synth.shapes_of(ref), 1)
+    est_sd, ref_sd = synthetic_state_dicts()
     est.load_state_dict(est_sd)
     ref.load_state_dict(ref_sd)
     est.eval().requires_grad_(False)
@@ -167,14 +184,16 @@ def cpu_pose_rate(est_sd, ref_sd, frames: int, warm: int = 1):
 
 
 def run_reference(args):
+    """The reference's path on the host cores (oracle port; the reference's Python cannot travel to the GPU box), same workload
+    as our arm: every step is the same `--frames` frames of 8 objects.  Imports nothing that loads libdensefusion_b200.so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    _, _, est_sd, ref_sd = build_modules(None)
-    frames_per_step = 8           # 64 poses ~ 1.4 s of CPU work per step on 16 cores: the default run stays under a minute
+    est_sd, ref_sd = synthetic_state_dicts()
+    frames_per_step = args.frames
     for _ in range(args.warmup):
-        cpu_pose_rate(est_sd, ref_sd, frames_per_step, warm=0)
+        cpu_pose_rate(est_sd, ref_sd, 1, warm=0)             # warm-up: one frame per warm-up step (thread pools, allocator)
     t0 = time.perf_counter()
     poses = 0
     for _ in range(args.steps):
@@ -182,12 +201,14 @@ def run_reference(args):
         poses += n
     dt = time.perf_counter() - t0
     val = poses / dt
-    sample = f"{frames_per_step} frame x 8 objects per step, {args.steps} steps"
+    sample = (f"{frames_per_step} frames x 8 objects = {frames_per_step * len(CROP_MIX)} poses per step, {args.steps} timed steps "
+              f"({dt:.1f} s), warm-up steps of one frame each")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": workload_name(args.frames), "reference_impl": "oracle port (torch-CPU fp32) of the "
-                       "reference's Python path; the reference itself is Python and cannot travel to the GPU box"},
+            "config": workload_config(frames_per_step, args.gpus),
+            "impl_config": {"reference_impl": "oracle port (torch-CPU fp32 + float64 host pose algebra) of the reference's Python "
+                                              "path; rank 0 only, all host threads", "threads": torch.get_num_threads()},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -209,9 +230,82 @@ def time_kernel_ms(fn, iters=20, warm=3):
     return e0.elapsed_time(e1) / iters
 
 
-def dominant_kernel_roofline(pipe, precision, peaks):
-    """Live timing of the dominant kernel of the step: the first tower layer (conv1_{r,t,c} on the 384 local
-    channels, N=1920) over one chunk -- 36.7% of the head's MACs."""
+PASSES = {"3xtf32": 3.0, "hybrid": 2.0, "hybrid16": 1.5, "hybrid16w": 1.5, "tf32": 1.0}     # executed TF32-equivalent MMA time per algorithmic flop
+INGEST_B_PER_CLK_SM = 30.9          # measured: profiles/r2_l2_ingest_probe.json (TMA bytes per clock one SM can take in)
+
+
+def measured_peaks(dev):
+    """Denominators measured live on this GPU: cuBLAS TF32 (8192^3, best of 10) and an FFMA-only kernel (df_probe_ffma)."""
+    from densefusion_b200._C import lib, ptr
+    out = {}
+    try:
+        a = torch.randn(8192, 8192, device=dev)
+        b = torch.randn(8192, 8192, device=dev)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        best = min(time_kernel_ms(lambda: torch.matmul(a, b), iters=1, warm=1) for _ in range(10))
+        out["cublas_tf32_tflops"] = 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+        del a, b
+    except Exception:
+        out["cublas_tf32_tflops"] = None
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = False
+    sink = torch.zeros(4, device=dev)
+    flops = [0]
+
+    def probe():
+        flops[0] = int(lib.df_probe_ffma(ptr(sink), 148 * 16, 4096, torch.cuda.current_stream().cuda_stream))
+    ms = min(time_kernel_ms(probe, iters=3, warm=1) for _ in range(3))
+    out["ffma_tflops"] = flops[0] / (ms * 1e-3) / 1e12 if flops[0] > 0 else None
+    return out
+
+
+def time_weighted_roofline(pipe, dev_set, precision, peaks, live):
+    """Every tensor-core launch of ONE pose step, bracketed by CUDA events in eager single-stream mode: sum of the multiply-adds
+    actually executed on real rows (GEMMs: M N K; convolutions: df_conv_tc_macs, i.e. without the skipped all-padding taps)
+    over the sum of the launch durations."""
+    from densefusion_b200 import _C
+    prev = pipe.concurrent_buckets
+    pipe.concurrent_buckets = False
+    try:
+        for _ in range(2):
+            pipe.estimate_buckets(dev_set)
+        torch.cuda.synchronize()
+        _C.lib.timer = []
+        pipe.estimate_buckets(dev_set)
+        torch.cuda.synchronize()
+        rec, _C.lib.timer = _C.lib.timer, None
+    finally:
+        _C.lib.timer = None
+        pipe.concurrent_buckets = prev
+    flops = ms = 0.0
+    per = []
+    for name, args, e0, e1, rc in rec:
+        if rc != 0:
+            continue
+        t = e0.elapsed_time(e1)
+        if name == "df_gemm_tc":
+            f = 2.0 * args[9] * args[10] * args[11] * args[14]
+            what = f"gemm M={args[9]} N={args[10]} K={args[11]} g={args[14]}"
+        else:
+            f = 2.0 * int(_C.lib.df_conv_tc_macs(args[1], args[2], args[3], args[4], args[17], args[8], args[9]))
+            what = f"conv {args[1]}x{args[2]}x{args[3]} {args[4]}->{args[17]} taps={args[8]} dil={args[9]}"
+        flops += f
+        ms += t
+        per.append((t, f, what))
+    per.sort(reverse=True)
+    ach = flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+    tf32_peak = live.get("cublas_tf32_tflops") or peaks.get("bf16_tflops", 1590.0) / 2.0
+    return {"launches": len(per), "ms_sum": ms, "executed_flops": flops, "achieved": ach, "unit": "TFLOP/s",
+            "peak": tf32_peak, "frac": ach / tf32_peak,
+            "frac_of_bf16_sustained_in_mma_time": PASSES.get(precision, 1.0) * 2.0 * ach / peaks.get("bf16_tflops_sustained", 1403.9),
+            "top": [{"ms": round(t, 4), "tflops": round(f / (t * 1e-3) / 1e12, 1), "launch": w} for t, f, w in per[:6]],
+            "note": "eager, single stream, CUDA events around every df_gemm_tc / df_conv_tc launch of one step; flops = executed "
+                    "multiply-adds x 2 on real rows (skipped all-padding taps not counted); peak = cuBLAS TF32 measured in this run"}
+
+
+def dominant_kernel_roofline(pipe, precision, peaks, live):
+    """Live timing of the bench's reference kernel: the first tower layer (conv1_{r,t,c} on the 384 local channels, N=1920)
+    over one chunk, the largest single GEMM of the head."""
     from densefusion_b200 import engine, ops
     crops, n = pipe.chunk, pipe.n
     rows = crops * n
@@ -225,47 +319,45 @@ def dominant_kernel_roofline(pipe, precision, peaks):
                  precision=precision, bias_crop_stride=1920, rows_per_crop=n)
     ms = time_kernel_ms(run)
     flops = 2.0 * rows * 1920 * 384
+    tf32_lib = live.get("cublas_tf32_tflops")
     if precision == "fp32":
-        peak = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
-        peak_note = "fp32 FFMA pipe, 148 SM x 128 lanes x 2 x max SM clock (no measured fp32 figure in MEASURED_PEAKS.json)"
-        bound = "tensor"
+        peak = live.get("ffma_tflops") or 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+        peak_note = "fp32 FFMA pipe measured in this run (df_probe_ffma)" if live.get("ffma_tflops") else "fp32 FFMA pipe, nominal"
         kname = "sgemm_kernel<128,128> (fp32 FFMA)"
     else:
-        peak = peaks.get("bf16_tflops", 1590.0) / 2.0
-        peak_note = ("TF32 tcgen05 peak taken as half of the measured bf16 burst figure of MEASURED_PEAKS.json"
-                     if "bf16_tflops" in peaks else "TF32 = half of the fallback 1.59 PFLOP/s bf16")
-        bound = "tensor"
-        kinds = {"hybrid": "kind::tf32 + kind::f16 bf16 corrections", "hybrid16": "kind::f16: fp16 main term + bf16 corrections"}
+        peak = tf32_lib or peaks.get("bf16_tflops", 1590.0) / 2.0
+        peak_note = ("TF32 tensor peak = cuBLAS TF32 8192^3 measured in this run (MEASURED_PEAKS.json has no TF32 figure; its bf16 burst / 2 "
+                     f"would be {peaks.get('bf16_tflops', 1590.0) / 2.0:.1f})") if tf32_lib else "TF32 = half of the bf16 burst figure"
+        kinds = {"hybrid": "kind::tf32 + kind::f16 bf16 corrections", "hybrid16": "kind::f16: fp16 main term + bf16 corrections",
+                 "hybrid16w": "kind::f16: fp16 main term + bf16 corrections, weights split on chip"}
         kname = "gemm_tc_q_kernel<2,2> (tcgen05.mma.cta_group::2 %s, TMA operands, %s)" % (kinds.get(precision, "kind::tf32"), precision)
     ach = flops / (ms * 1e-3) / 1e12
     shape = f"M={rows} N=1920 K=384"
-    # what the library reaches on this GPU in single-pass TF32 (cuBLAS, 8192^3, best of 10): a measured TF32 ceiling next to
-    # the derived one (MEASURED_PEAKS.json has no TF32 figure)
-    tf32_lib = None
-    if precision != "fp32":
-        try:
-            a = torch.randn(8192, 8192, device=ws.pf.device)
-            b = torch.randn(8192, 8192, device=ws.pf.device)
-            torch.backends.cuda.matmul.allow_tf32 = True
-            best = min(time_kernel_ms(lambda: torch.matmul(a, b), iters=1, warm=1) for _ in range(10))
-            tf32_lib = 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
-        except Exception:
-            tf32_lib = None
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = False
     traffic = None
     try:
         if precision != "fp32":
             traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))[shape]["bytes"]
     except Exception:
         traffic = None
-    return {"bound": bound, "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-            "traffic": traffic, "ms_per_launch": ms, "algorithmic_flops_per_launch": flops,
-            "frac_of_mode_ceiling": ({"3xtf32": 3.0, "hybrid": 2.0, "hybrid16": 1.5}.get(precision, 1.0) * ach / peak) if precision != "fp32" else None,
-            "l2": "operands + output of one launch (596 MB at the default chunk) exceed the 126 MB L2",
-            "cublas_tf32_8192_tflops": tf32_lib, "frac_vs_cublas_tf32": (ach / tf32_lib) if tf32_lib else None,
-            "executed_over_algorithmic": {"3xtf32": 3.0, "hybrid": 2.0, "hybrid16": 1.5}.get(precision, 1.0), "peak_source": peak_note,
-            "shape": shape}
+    out = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+           "traffic": traffic, "ms_per_launch": ms, "algorithmic_flops_per_launch": flops,
+           "l2": "operands + output of one launch (596 MB at the default chunk) exceed the 126 MB L2",
+           "cublas_tf32_8192_tflops": tf32_lib, "ffma_tflops_measured": live.get("ffma_tflops"),
+           "executed_over_algorithmic": PASSES.get(precision, 1.0), "peak_source": peak_note, "shape": shape}
+    if precision in ("hybrid16", "hybrid16w", "hybrid", "3xtf32"):
+        # What actually binds this kernel (profiles/r2_l2_ingest_probe.txt): an SM takes in at most ~31 B per clock from L2 --
+        # with any number of SMs streaming, any stage depth, multicast or not -- and a 256 x 192 tile step of 32 k needs
+        # 16 KB of A + the CTA's half of the weight tile: the k-block cannot be shorter than those bytes / 31, whatever the MMAs need.
+        wb = {"hybrid16": 6.0, "hybrid16w": 4.0, "hybrid": 8.0, "3xtf32": 8.0}[precision]
+        bytes_kb = 128 * 32 * 4 + 96 * 32 * wb
+        clk = peaks.get("sm_max_mhz", 1965.0) * 1e6
+        kb_per_cta = (rows / 256.0) * (1920 / 192.0) * (384 / 32) / 74.0
+        t_min = kb_per_cta * bytes_kb / INGEST_B_PER_CLK_SM / clk
+        out["ingest_roof"] = {"bytes_per_cta_per_kblock": bytes_kb, "measured_port_B_per_clk_per_sm": INGEST_B_PER_CLK_SM,
+                              "min_ms_at_max_clock": t_min * 1e3, "frac": t_min * 1e3 / ms,
+                              "note": "fraction of the SM fabric-port roof (time the operand bytes need at the measured ingest rate "
+                                      "/ measured time); see profiles/r2_l2_ingest_probe.txt"}
+    return out
 
 
 def run_ours(args):
@@ -390,6 +482,28 @@ def run_ours(args):
     chk = step_device(0).cpu()
     assert torch.isfinite(chk).all() and torch.allclose(chk[:, :4].norm(dim=1), torch.ones(crops_per_step, dtype=torch.float64), atol=1e-6)
 
+    def parity_vs_oracle(samples=32):
+        """Outside the timed region: the poses of the exact timed configuration (graph replay, all buckets, chunked head,
+        bench precision) for `samples` crops spread over the buckets against the oracle's estimate + refine on the same inputs."""
+        from oracle import df_oracle as O
+        poses = step_device(0).cpu().numpy()
+        flat = [(bi, i) for bi, b in enumerate(host_sets[0]) for i in range(b["cloud"].shape[0])]
+        stride = max(1, len(flat) // samples)
+        picks = list(range(0, len(flat), stride))[:samples]
+        worst, worst_at = 0.0, -1
+        torch.set_num_threads(os.cpu_count() or 1)
+        for k in picks:
+            bi, i = flat[k]
+            b = host_sets[0][bi]
+            want = O.estimate_and_refine(est_sd, ref_sd, b["img"][i:i + 1], b["cloud"][i:i + 1], b["choose"][i:i + 1],
+                                         b["obj"][i].view(1, 1), N_OBJ, ITERS)
+            e = float(np.max(np.abs(poses[k] - want)) / np.max(np.abs(want)))
+            if e > worst:
+                worst, worst_at = e, k
+        return {"parity_max_rel": worst, "crops_checked": len(picks), "worst_crop": worst_at, "bound": 1e-4,
+                "norm": "max |pose - oracle| / max |oracle| over the 7-vector [qw qx qy qz tx ty tz]",
+                "against": "oracle.estimate_and_refine (torch-CPU fp32 + float64 pose algebra) on the identical host inputs"}
+
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = _C.lib.launches
@@ -416,10 +530,14 @@ def run_ours(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        roof = dominant_kernel_roofline(pipe, args.precision, peaks)
+        live = measured_peaks(dev)
+        roof = dominant_kernel_roofline(pipe, args.precision, peaks, live)
+        if args.precision != "fp32" and pipe.encoder == "tc":
+            roof["time_weighted"] = time_weighted_roofline(pipe, dev_sets[0], args.precision, peaks, live)
+        parity = parity_vs_oracle() if not args.no_parity else None
         extras = {}
         if not args.no_extras:
-            extras = measure_extras(pipe, dev, args, peaks)
+            extras = measure_extras(pipe, dev, args, peaks, live)
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             torch.set_num_threads(os.cpu_count() or 1)
@@ -431,18 +549,15 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": {"fp32": "fp32", "hybrid": "fp32 (fp32-parity tensor-core GEMMs: TF32 main term + bf16 correction terms, fp32 accumulate)",
                           "hybrid16": "fp32 (fp32-parity tensor-core GEMMs: fp16 main term + bf16 correction terms, fp32 accumulate)",
-                          "hybrid16p": "fp32 (fp32-parity tensor-core GEMMs: fp16 main term + bf16 correction terms, fp32 accumulate)",
+                          "hybrid16w": "fp32 (fp32-parity tensor-core GEMMs: fp16 main term + bf16 correction terms, fp32 accumulate)",
                           "3xtf32": "fp32 (fp32-parity tensor-core GEMMs: 3xTF32, fp32 accumulate)",
                           "tf32": "tf32 (single-pass tensor-core GEMMs, fp32 accumulate; looser bound)"}[args.precision],
                 "data": "synthetic",
-                "config": {"workload": workload_name(args.frames), "num_points": N_POINTS, "num_obj": N_OBJ,
-                           "refine_iterations": ITERS, "crops_per_gpu_per_step": crops_per_step,
-                           "precision": args.precision,
-                           "encoder": ("densefusion_b200.encoder: tcgen05 implicit-GEMM convolutions, NHWC, " + args.precision)
-                           if pipe.encoder == "tc" else "torch/cuDNN strict fp32 (TF32 off), NCHW",
-                           "launch": launch_mode, "chunk_crops": args.chunk,
-                           "l2": "two alternating input sets; per-step working set (encoder activations > 1 GB) exceeds the 126 MB L2",
-                           "parallelism": f"frames sharded over {world} GPU(s), no data-path collective"},
+                "config": workload_config(args.frames, world),
+                "impl_config": {"precision": args.precision,
+                                "encoder": ("densefusion_b200.encoder: tcgen05 implicit-GEMM convolutions, NHWC, " + args.precision)
+                                if pipe.encoder == "tc" else "torch/cuDNN strict fp32 (TF32 off), NCHW",
+                                "launch": launch_mode, "chunk_crops": args.chunk},
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps,
@@ -451,6 +566,9 @@ def run_ours(args):
                 "gpu_launches": launches_per_step * args.steps,
                 "gpu_launches_per_step": launches_per_step,
                 "roofline": roof}
+        if parity:
+            line["parity"] = parity
+            line["parity_max_rel"] = parity["parity_max_rel"]
         if cpu:
             line["cpu_baseline"] = cpu
         if extras:
@@ -461,6 +579,8 @@ def run_ours(args):
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line))
+        if line.get("parity") and line["parity"]["parity_max_rel"] > 1e-4 and args.precision != "tf32":
+            raise SystemExit(f"bench.py: parity check failed: {line['parity']}")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -588,7 +708,177 @@ def run_train(args):
         dist.destroy_process_group()
 
 
-def measure_extras(pipe, dev, args, peaks):
+
+# ------------------------------------------------------------------------------------------------
+# configs C0 / C1 of BASELINE.json: parity-test shapes, reported beside the headline
+# ------------------------------------------------------------------------------------------------
+def _stats_ms(fn, warm=3, iters=20, sync=None):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if sync:
+            sync()
+        t0 = time.perf_counter()
+        fn()
+        if sync:
+            sync()
+        ts.append((time.perf_counter() - t0) * 1e3)
+    ts.sort()
+    return {"median_ms": ts[len(ts) // 2], "p10_ms": ts[len(ts) // 10], "p90_ms": ts[(9 * len(ts)) // 10]}
+
+
+def run_c0(args):
+    """Config C0: LineMOD PoseNet(500,13) forward + non-symmetric ADD Loss, batch 1 (80x80 and 120x120 crops), plus the full
+    estimate + 2 refine pose.  Per-stage CPU breakdown (oracle port, all host threads) beside the drop-in modules on the GPU."""
+    from densefusion_b200 import synth
+    from oracle import df_oracle as O
+    n, o, m = 500, 13, 500
+    est_sd, ref_sd = synthetic_state_dicts(o)
+    torch.set_num_threads(os.cpu_count() or 1)
+    out = {"metric": "LineMOD single-crop latency: PoseNet forward + ADD Loss, and estimate + 2 refine iterations (config C0)",
+           "unit": "ms", "higher_is_better": False, "n_gpus": 1, "steps": 20, "warmup": 3, "scaling": "weak", "vs_baseline": None,
+           "dtype": "fp32", "data": "synthetic", "config": {"workload": "LineMOD PoseNet(num_points=500, num_obj=13), batch 1, "
+                                                                        "non-symmetric object, num_pt_mesh=500, w=0.015"},
+           "crops": {}}
+    gpu = torch.cuda.is_available()
+    if gpu:
+        from densefusion_b200.lib.loss import Loss
+        from densefusion_b200.lib.loss_refiner import Loss_refine
+        from densefusion_b200.lib.network import PoseNet, PoseRefineNet
+        from densefusion_b200.pipeline import PoseEstimator
+        dev = torch.device("cuda", 0)
+        torch.cuda.set_device(0)
+        est, ref = PoseNet(n, o), PoseRefineNet(n, o)
+        est.load_state_dict(est_sd); ref.load_state_dict(ref_sd)
+        est.eval().requires_grad_(False).to(dev); ref.eval().requires_grad_(False).to(dev)
+        est.precision = ref.precision = args.precision
+        crit, crit_r = Loss(m, synth.LINEMOD_SYM), Loss_refine(m, synth.LINEMOD_SYM)
+        pipe = PoseEstimator(est, ref, iterations=ITERS, precision=args.precision)
+    for hw in ((80, 80), (120, 120)):
+        d = synth.synth_crop(31, n, m, o, hw, obj=3)
+        with torch.no_grad():
+            feat = O.psp_encoder(est_sd, d["img"])
+            emb = O.gather_embedding(feat, d["choose"])
+            r, t, c = O.posenet_head(est_sd, d["points"], emb, d["idx"], o)
+            _, _, new_pts, new_tgt = O.loss(r, t, c, d["target"], d["model_points"], d["idx"], d["points"], 0.015, True, m, synth.LINEMOD_SYM)
+            r2, t2 = O.refiner_forward(ref_sd, new_pts, emb, d["idx"], o)
+
+            def ng(fn):
+                def w():
+                    with torch.no_grad():
+                        fn()
+                return w
+            cpu = {"cnn": _stats_ms(ng(lambda: O.psp_encoder(est_sd, d["img"]))),
+                   "head": _stats_ms(ng(lambda: O.posenet_head(est_sd, d["points"], emb, d["idx"], o))),
+                   "loss_add": _stats_ms(ng(lambda: O.loss(r, t, c, d["target"], d["model_points"], d["idx"], d["points"], 0.015, False, m, synth.LINEMOD_SYM))),
+                   "refiner": _stats_ms(ng(lambda: O.refiner_forward(ref_sd, new_pts, emb, d["idx"], o))),
+                   "loss_refine": _stats_ms(ng(lambda: O.loss_refine(r2, t2, new_tgt, d["model_points"], d["idx"], new_pts, m, synth.LINEMOD_SYM))),
+                   "pose_estimate_plus_2_refine": _stats_ms(lambda: O.estimate_and_refine(est_sd, ref_sd, d["img"], d["points"], d["choose"], d["idx"], o, ITERS))}
+        entry = {"cpu_oracle_port": cpu, "cpu_threads": torch.get_num_threads()}
+        if gpu:
+            dc = {k: v.to(dev) for k, v in d.items()}
+            sync = torch.cuda.synchronize
+            with torch.no_grad():
+                rg, tg, cg, embg = est(dc["img"], dc["points"], dc["choose"], dc["idx"])
+                _, _, npg, ntg = crit(rg, tg, cg, dc["target"], dc["model_points"], dc["idx"], dc["points"], 0.015, True)
+                r2g, t2g = ref(npg, embg, dc["idx"])
+                g = {"posenet_forward": _stats_ms(lambda: est(dc["img"], dc["points"], dc["choose"], dc["idx"]), sync=sync),
+                     "loss_add": _stats_ms(lambda: crit(rg, tg, cg, dc["target"], dc["model_points"], dc["idx"], dc["points"], 0.015, False), sync=sync),
+                     "refiner": _stats_ms(lambda: ref(npg, embg, dc["idx"]), sync=sync),
+                     "loss_refine": _stats_ms(lambda: crit_r(r2g, t2g, ntg, dc["model_points"], dc["idx"], npg), sync=sync),
+                     "pose_estimate_plus_2_refine": _stats_ms(lambda: pipe.estimate(dc["img"], dc["points"], dc["choose"], dc["idx"]), sync=sync)}
+                pose = pipe.estimate(dc["img"], dc["points"], dc["choose"], dc["idx"]).cpu().numpy()[0]
+            want = O.estimate_and_refine(est_sd, ref_sd, d["img"], d["points"], d["choose"], d["idx"], o, ITERS)
+            entry["gpu_drop_in_modules"] = g
+            entry["parity_pose_rel"] = float(np.max(np.abs(pose - want)) / np.max(np.abs(want)))
+            entry["note"] = "GPU numbers are host-timed eager latencies of ONE crop (launch-bound: ~60-170 launches per call), precision " + args.precision
+        out["crops"][f"{hw[0]}x{hw[1]}"] = entry
+    key = "gpu_drop_in_modules" if gpu else "cpu_oracle_port"
+    out["value"] = out["crops"]["80x80"][key]["pose_estimate_plus_2_refine"]["median_ms"]
+    out["ms_per_step"] = out["value"]
+    c80 = out["crops"]["80x80"]["cpu_oracle_port"]
+    out["cpu_baseline"] = {"value": c80["pose_estimate_plus_2_refine"]["median_ms"], "unit": "ms", "cores": torch.get_num_threads(),
+                           "kind": "port", "sample": "20 timed single-crop calls per stage after 3 warm-up calls, 80x80 crop"}
+    print(json.dumps(out))
+
+
+def run_c1(args):
+    """Config C1: YCB PoseNet(500,21) forward (encoder + head) + ADD-S Loss through the kNN kernel, 256 crops of symmetric
+    objects on one GPU: one combined line, with the fused loss against the measured fp32-issue roof."""
+    from densefusion_b200 import ops, synth
+    from densefusion_b200.lib.loss import Loss
+    from oracle import df_oracle as O
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --workload c1: no CUDA device (no CPU fallback)")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    est, _, est_sd, _ = build_modules(dev)
+    est.precision = args.precision
+    crit = Loss(N_MESH, synth.YCB_SYM)
+    g = torch.Generator().manual_seed(77)
+    buckets = []
+    for hw, b in (((80, 80), 96), ((120, 120), 96), ((160, 160), 64)):
+        img = torch.randn(b, 3, hw[0], hw[1], generator=g)
+        choose = torch.stack([torch.sort(torch.randperm(hw[0] * hw[1], generator=g)[:N_POINTS])[0] for _ in range(b)]).view(b, 1, N_POINTS)
+        points = torch.randn(b, N_POINTS, 3, generator=g) * 0.05 + torch.tensor([0.0, 0.0, 0.8])
+        model = torch.randn(b, N_MESH, 3, generator=g) * 0.05
+        rot = torch.stack([synth.quat_to_rot(synth.random_unit_quaternion(g)) for _ in range(b)])
+        target = (torch.bmm(model, rot.transpose(1, 2)) + torch.tensor([0.0, 0.0, 0.8])).contiguous()
+        idx = torch.tensor(synth.YCB_SYM)[torch.randint(0, len(synth.YCB_SYM), (b,), generator=g)].view(b, 1)
+        buckets.append(dict(img=img, points=points, choose=choose, model_points=model, target=target, idx=idx))
+    dbk = [{k: v.to(dev) for k, v in b.items()} for b in buckets]
+    crops = sum(b["img"].shape[0] for b in buckets)
+    loss_ms = [0.0]
+
+    def step():
+        with torch.no_grad():
+            outs = []
+            for b in dbk:
+                r, t, c, _ = est.forward_batched(b["img"], b["points"], b["choose"], b["idx"])
+                outs.append(crit(r, t, c, b["target"], b["model_points"], b["idx"], b["points"], 0.015, False))
+            return outs
+
+    def loss_only(preds):
+        with torch.no_grad():
+            for b, (r, t, c) in zip(dbk, preds):
+                crit(r, t, c, b["target"], b["model_points"], b["idx"], b["points"], 0.015, False)
+    with torch.no_grad():
+        preds = [est.forward_batched(b["img"], b["points"], b["choose"], b["idx"])[:3] for b in dbk]
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms = time_kernel_ms(step, iters=args.steps, warm=max(args.warmup, 3))
+    clocks = sampler.stop()
+    ms_loss = time_kernel_ms(lambda: loss_only(preds), iters=args.steps, warm=3)
+    live = measured_peaks(dev)
+    # parity of a few crops against the oracle (loss and selected distance)
+    outs = step()
+    worst = 0.0
+    for bi in range(len(buckets)):
+        b = buckets[bi]
+        for i in (0, b["img"].shape[0] - 1):
+            with torch.no_grad():
+                r, t, c, _ = O.posenet_forward(est_sd, b["img"][i:i + 1], b["points"][i:i + 1], b["choose"][i:i + 1], b["idx"][i:i + 1], N_OBJ)
+                l, dsel, _, _ = O.loss(r, t, c, b["target"][i:i + 1], b["model_points"][i:i + 1], b["idx"][i:i + 1], b["points"][i:i + 1],
+                                       0.015, False, N_MESH, synth.YCB_SYM)
+            worst = max(worst, abs(float(outs[bi][0][i]) - float(l)) / abs(float(l)), abs(float(outs[bi][1][i]) - float(dsel)) / abs(float(dsel)))
+    pairs = float(crops) * N_POINTS * N_MESH * N_MESH
+    ffma = live.get("ffma_tflops")
+    roof = {"bound": "fp32 issue (fma pipe) of the fused ADD-S loss; HBM is negligible (46 KB per crop)", "kernel": "loss_forward_kernel (K3 + K4 fused)",
+            "ms_per_256_crops": ms_loss, "pair_evals_per_s": pairs / (ms_loss * 1e-3), "ffma_tflops_measured": ffma,
+            "achieved": pairs * 6 * 2 / (ms_loss * 1e-3) / 1e12, "peak": ffma, "unit": "TFLOP/s (fma-pipe instructions x 2)",
+            "frac": (pairs * 6 * 2 / (ms_loss * 1e-3) / 1e12 / ffma) if ffma else None, "traffic": None}
+    print(json.dumps({"metric": "crops/sec: PoseNet forward + ADD-S Loss (kNN R=500, Q=250000 per crop), config C1", "value": crops / (ms * 1e-3),
+                      "unit": "crops/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "fp32 (fp32-parity tensor-core GEMMs, fp32 loss)", "data": "synthetic",
+                      "config": {"workload": "YCB PoseNet(500,21) forward + ADD-S Loss, 256 crops (96x80^2 + 96x120^2 + 64x160^2) of symmetric objects, 1 GPU",
+                                 "precision": args.precision}, "clocks": clocks, "loss_share_of_step": ms_loss / ms,
+                      "parity_max_rel_loss_and_dis": worst, "roofline": roof}))
+    if worst > 1e-4:
+        raise SystemExit(f"bench.py c1: parity check failed ({worst:.3e})")
+
+
+def measure_extras(pipe, dev, args, peaks, live=None):
     """Per-stage numbers that explain the headline: head-only poses/s, and config C1 (ADD-S loss, 256 crops)."""
     from densefusion_b200 import ops, synth
     out = {}
@@ -618,6 +908,15 @@ def measure_extras(pipe, dev, args, peaks):
     out["c1_adds_loss_256_crops"] = {"ms": ms_s, "crops_per_s": B / (ms_s * 1e-3), "pair_evals_per_s": pairs / (ms_s * 1e-3),
                                      "algorithmic_bytes": B * 46e3, "hbm_gbs": B * 46e3 / (ms_s * 1e-3) / 1e9,
                                      "fp32_lane_ops_per_s": pairs * 9 / (ms_s * 1e-3)}
+    ffma = (live or {}).get("ffma_tflops")
+    if ffma:
+        # K3 / K4 are bound by fp32 instruction issue, not HBM: per (hypothesis point, reference) pair the kernel issues 3 FADD +
+        # 3 FFMA/FMUL on the fma pipe and ~1 FMNMX3 slot; the measured FFMA-only rate (df_probe_ffma) is the denominator
+        inst_peak = ffma * 1e12 / 2.0
+        out["c1_adds_loss_256_crops"]["fp32_roofline"] = {
+            "bound": "fp32 issue (fma pipe)", "ffma_tflops_measured": ffma,
+            "fma_pipe_frac": pairs * 6 / (ms_s * 1e-3) / inst_peak, "issue_slot_frac": pairs * 7 / (ms_s * 1e-3) / inst_peak,
+            "note": "6 fma-pipe instructions (7 issue slots) per pair evaluation / measured FFMA instruction rate"}
     out["c1_add_loss_256_crops"] = {"ms": ms_a, "crops_per_s": B / (ms_a * 1e-3), "hbm_gbs": B * 46e3 / (ms_a * 1e-3) / 1e9}
     # the same whole pipeline with the encoder allowed to use cuDNN's TF32 channels-last kernels (NOT the fp32-parity
     # configuration: embeddings then differ at the 1e-3 level) -- shows how much of the step is the library encoder
@@ -659,6 +958,10 @@ if __name__ == "__main__":
         run_reference(a)
     elif a.workload == "train":
         run_train(a)
+    elif a.workload == "c0":
+        run_c0(a)
+    elif a.workload == "c1":
+        run_c1(a)
     else:
         run_ours(a)
     sys.stdout.flush()

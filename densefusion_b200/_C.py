@@ -22,6 +22,7 @@ _f = ctypes.c_float
 SIGNATURES = {
     "df_abi_version": [],
     "df_features": [],
+    "df_probe_ffma": [_p, _i, _i, _p],
     "df_knn": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
     "df_loss_forward": [_p, _p, _p, _p, _p, _p, _p, _p, _ull, _i, _f, _i, _i, _i, _i,
                         _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
@@ -46,6 +47,7 @@ SIGNATURES = {
     "df_gather_embedding_backward": [_p, _p, _p, _ll, _ll, _ll, _i, _i, _i, _p],
     "df_adam_step": [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _i, _p],
     "df_adam_step_dev": [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _p, _p],
+    "df_conv_tc_macs": [_i, _i, _i, _i, _i, _i, _i],
     "df_conv_tc": [_p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p],
     "df_enc_im2col_conv1": [_p, _p, _i, _i, _i, _i, _p],
     "df_enc_maxpool": [_p, _p, _i, _i, _i, _i, _p],
@@ -80,28 +82,41 @@ def _load():
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing -> loud
         fn.argtypes = args
-        fn.restype = ctypes.c_longlong if name == "df_conv_wgrad_scratch_floats" else ctypes.c_int
+        fn.restype = ctypes.c_longlong if name in ("df_conv_wgrad_scratch_floats", "df_probe_ffma", "df_conv_tc_macs") else ctypes.c_int
     return lib
 
 
 class _CountingLib:
     """Forwards to the CDLL and counts kernel-launching entry points (bench.py reports `gpu_launches`)."""
-    _NO_LAUNCH = ("df_abi_version", "df_features", "df_gemm_rows_per_pool_tile", "df_conv_wgrad_scratch_floats")
+    _NO_LAUNCH = ("df_abi_version", "df_features", "df_gemm_rows_per_pool_tile", "df_conv_wgrad_scratch_floats", "df_conv_tc_macs")
+
+    _TIMED = ("df_gemm_tc", "df_conv_tc")
 
     def __init__(self, cdll):
         self._cdll = cdll
         self.launches = 0
+        self.timer = None          # bench.py: a list -> every tensor-core launch is bracketed by CUDA events and appended
         for name in SIGNATURES:
             fn = getattr(cdll, name)
             if name in self._NO_LAUNCH:
                 setattr(self, name, fn)
             else:
-                setattr(self, name, self._counted(fn))
+                setattr(self, name, self._counted(name, fn))
 
-    def _counted(self, fn):
+    def _counted(self, name, fn):
+        timed = name in self._TIMED
+
         def call(*args):
             self.launches += 1
-            return fn(*args)
+            t = self.timer
+            if t is None or not timed:
+                return fn(*args)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            t.append((name, args, e0, e1, rc))
+            return rc
         return call
 
 

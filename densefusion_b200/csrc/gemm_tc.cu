@@ -105,7 +105,7 @@ struct QTile {
 // Taps of a 3x3 convolution that can reach the image from a TH x TW patch at (x0, y0): with dilation d the tap (ky, kx)
 // reads rows y + (ky-1)*d, so a patch within d of the top edge never sees ky = 0 etc.  Skipped taps are whole k-block
 // runs the pair neither loads nor multiplies (layer4 at dilation 4 on a 10x10 map: half of all tap visits).
-__device__ __forceinline__ void q_patch(const TcParams& p, int pt, int& tx, int& ty, int& tb)
+__host__ __device__ __forceinline__ void q_patch(const TcParams& p, int pt, int& tx, int& ty, int& tb)
 {
     // batch fastest: the two patches of a CTA pair normally sit at the same (x0, y0) of neighbouring crop groups and need the
     // same taps (measured against x-fastest with the union of two neighbouring patches: 3-8% on the dilated layers)
@@ -114,10 +114,10 @@ __device__ __forceinline__ void q_patch(const TcParams& p, int pt, int& tx, int&
     tx = rest % p.tiles_x; ty = rest / p.tiles_x;
 }
 
-__device__ __forceinline__ uint32_t q_tap_mask(const TcParams& p, int x0, int y0)
+__host__ __device__ __forceinline__ uint32_t q_tap_mask(const TcParams& p, int x0, int y0)
 {
     if (p.conv_taps != 9) return 1u;
-    const int yh = min(y0 + p.TH, p.cH) - 1, xh = min(x0 + p.TW, p.cW) - 1;
+    const int yh = (y0 + p.TH < p.cH ? y0 + p.TH : p.cH) - 1, xh = (x0 + p.TW < p.cW ? x0 + p.TW : p.cW) - 1;
     uint32_t my = 0, mx = 0;
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
@@ -808,7 +808,10 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
         long long best = -1;
         for (int i = 0; i < 4; ++i) {
             const int w = widths[i];
-            if (w == 256 && !p.pool_partial) continue;
+            // 256-wide tiles leave room for ONE accumulator: fine for the store-free pooled epilogue, and (DF_TC_WIDE=1, A/B knob)
+            // for long-K layers, where the exposed epilogue of a tile is a few per cent of its k loop
+            static const int wide_ok = getenv("DF_TC_WIDE") ? atoi(getenv("DF_TC_WIDE")) : 0;
+            if (w == 256 && !p.pool_partial && !(wide_ok && p.K >= wide_ok * 1024)) continue;
             if (w == 192 && A_STAGES != 2) continue;
             if (w == 64 && p.N > 64) continue;                     // narrow layers only (64-channel decoder stages)
             if (p.N % w != 0 && (groups > 1 || w == 256)) continue;
@@ -1202,6 +1205,61 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
     DF_RETURN_LAST_ERROR();
 }
 
+// Pixel patch (TB x TH x TW <= 128 rows) of the implicit-GEMM convolution with the fewest tap visits = patches x the taps each
+// can reach (q_tap_mask: small patches of a dilated layer skip the taps that only see padding); ties: wider rows.
+static void conv_patch_plan(TcParams& p, int B, int H, int W, int taps, int dilation)
+{
+    auto reach = [&](int extent, int t) {                  // sum over the patches along one axis of the taps (of 3) they reach
+        if (taps != 9) return (extent + t - 1) / t;
+        int sum = 0;
+        for (int o = 0; o < extent; o += t) {
+            const int hi = (o + t < extent ? o + t : extent) - 1;
+            for (int k = -1; k <= 1; ++k) sum += (hi + k * dilation >= 0 && o + k * dilation < extent) ? 1 : 0;
+        }
+        return sum;
+    };
+    long long best_cost = -1;
+    for (int tw = 1; tw <= (W < 128 ? W : 128); ++tw) {
+        const int rx = reach(W, tw);
+        for (int th = 1; th <= H && tw * th <= 128; ++th) {
+            int tb = 128 / (tw * th);
+            if (tb > B) tb = B;
+            const long long cost = (long long)rx * reach(H, th) * ((B + tb - 1) / tb);
+            if (best_cost < 0 || cost < best_cost || (cost == best_cost && tw > p.TW)) {
+                best_cost = cost; p.TW = tw; p.TH = th; p.TB = tb;
+            }
+        }
+    }
+    p.tiles_x = (W + p.TW - 1) / p.TW; p.tiles_y = (H + p.TH - 1) / p.TH; p.tiles_b = (B + p.TB - 1) / p.TB;
+}
+
+// Multiply-adds df_conv_tc executes on real output pixels: sum over the pixel patches of (valid rows) x (taps the patch's CTA
+// pair visits) x Cin x Cout -- the dense count minus the skipped all-padding taps.  For the time-weighted roofline of bench.py.
+extern "C" long long df_conv_tc_macs(int B, int H, int W, int Cin, int Cout, int taps, int dilation)
+{
+    if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || (taps != 1 && taps != 9) || dilation < 1) return DF_ERR_ARG;
+    TcParams p = {};
+    p.conv_taps = taps; p.conv_dil = dilation; p.cW = W; p.cH = H; p.cB = B;
+    conv_patch_plan(p, B, H, W, taps, dilation);
+    const int patches = p.tiles_x * p.tiles_y * p.tiles_b;
+    long long macs = 0;
+    for (int mt = 0; mt * 2 < patches; ++mt) {
+        uint32_t mask = 0;
+        long long rows = 0;
+        for (int r = 0; r < 2; ++r) {
+            int tx, ty, tb;
+            q_patch(p, mt * 2 + r, tx, ty, tb);
+            if (ty >= p.tiles_y || tb >= p.tiles_b) continue;
+            mask |= q_tap_mask(p, tx * p.TW, ty * p.TH);
+            const int w = (tx * p.TW + p.TW < W ? p.TW : W - tx * p.TW), h = (ty * p.TH + p.TH < H ? p.TH : H - ty * p.TH);
+            const int b = (tb * p.TB + p.TB < B ? p.TB : B - tb * p.TB);
+            rows += (long long)w * h * b;
+        }
+        macs += rows * __builtin_popcount(mask) * Cin * Cout;
+    }
+    return macs;
+}
+
 // 3x3 (stride 1, padding == dilation) or 1x1 convolution on an NHWC image as an implicit GEMM on the paired tcgen05
 // kernel: out[pixel, n] = act( sum_{tap, c} X[pixel + tap*dil, c] W[n, tap*Cin + c] + bias[n] + residual[pixel, n] ).
 extern "C" int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx, const float* W_hi, const float* W_lo,
@@ -1228,30 +1286,7 @@ extern "C" int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx,
     p.rows_per_crop = p.M; p.a_gs = 0; p.bias_gs = 0; p.c_gs = 0; p.pool_partial = nullptr; p.tiles_per_crop = 0;
     p.conv_taps = taps; p.conv_dil = dilation; p.cW = W; p.cH = H; p.cB = B;
     p.residual = residual; p.ldr = ldr; p.prelu = prelu;
-    // pixel patch (TB x TH x TW <= 128 rows) with the fewest tap visits = patches x the taps each can reach (q_tap_mask: small
-    // patches of a dilated layer skip the taps that only see padding); ties: wider rows (longer contiguous runs)
-    auto reach = [&](int extent, int t) {                  // sum over the patches along one axis of the taps (of 3) they reach
-        if (taps != 9) return (extent + t - 1) / t;
-        int sum = 0;
-        for (int o = 0; o < extent; o += t) {
-            const int hi = (o + t < extent ? o + t : extent) - 1;
-            for (int k = -1; k <= 1; ++k) sum += (hi + k * dilation >= 0 && o + k * dilation < extent) ? 1 : 0;
-        }
-        return sum;
-    };
-    long long best_cost = -1;
-    for (int tw = 1; tw <= (W < 128 ? W : 128); ++tw) {
-        const int rx = reach(W, tw);
-        for (int th = 1; th <= H && tw * th <= 128; ++th) {
-            int tb = 128 / (tw * th);
-            if (tb > B) tb = B;
-            const long long cost = (long long)rx * reach(H, th) * ((B + tb - 1) / tb);
-            if (best_cost < 0 || cost < best_cost || (cost == best_cost && tw > p.TW)) {
-                best_cost = cost; p.TW = tw; p.TH = th; p.TB = tb;
-            }
-        }
-    }
-    p.tiles_x = (W + p.TW - 1) / p.TW; p.tiles_y = (H + p.TH - 1) / p.TH; p.tiles_b = (B + p.TB - 1) / p.TB;
+    conv_patch_plan(p, B, H, W, taps, dilation);
     const int rc = precision == 5 ? launch_q<2, 2, true>(p, W_hi, W_hi, taps * Cin, 1, (cudaStream_t)stream)
                                   : launch_q<2, 2>(p, W_hi, W_lo, taps * Cin, 1, (cudaStream_t)stream);
     if (rc) return rc;

@@ -72,11 +72,11 @@ def _pack_now(weight: torch.Tensor, rotate: bool, mode: int):
     rows, kt = (cin, k * k * cout) if rotate else (cout, k * k * cin)
     w = weight.detach().float().contiguous()
     hi = torch.empty(rows, kt, device=w.device, dtype=torch.float32)
-    if mode == 5:                                           # hybrid16, split on chip: the repacked fp32 weights
+    if mode == 5:                                           # hybrid16w, split on chip: the repacked fp32 weights
         check(lib.df_pack_conv_weight(ptr(w), ptr(hi), None, None, cout, cin, k * k, 1 if rotate else 0, stream()),
               "df_pack_conv_weight")
         return hi, hi
-    if mode == 4:                                           # hybrid16p: [fp16(w) | bf16(w)] per k-block and bf16(w - fp16(w))
+    if mode == 4:                                           # hybrid16: [fp16(w) | bf16(w)] per k-block and bf16(w - fp16(w))
         second = torch.empty(rows, kt // 2, device=w.device, dtype=torch.float32)
         check(lib.df_pack_conv_weight16(ptr(w), ptr(hi), ptr(second), cout, cin, k * k, 1 if rotate else 0, stream()),
               "df_pack_conv_weight16")

@@ -13,11 +13,12 @@ from ._C import check, f32c, i64c, lib, need_cuda, ptr, stream
 
 # "hybrid": TF32 main term + the two ~2^-11 correction terms in bf16 (8 instead of 12 MMAs per k-block), fp32-parity like
 # "3xtf32"; generation-2 tensor-core kernels only
-# "hybrid16": fp16 main term + bf16 correction terms (6 MMAs per k-block); the weight operand is the fp32 matrix itself, split
-# into its three 16-bit planes on chip (4 instead of 6 bytes per weight element through the SM's fabric port, the resource that
-# bounds the kernel).  "hybrid16p": the same arithmetic, bit for bit, with the planes packed once on the host side of the launch
-# (the round-1 form, kept for A/B measurements and as the cross-check of the on-chip split).
-PRECISIONS = {"fp32": 0, "3xtf32": 1, "tf32": 2, "hybrid": 3, "hybrid16p": 4, "hybrid16": 5}
+# "hybrid16": fp16 main term + bf16 correction terms (6 MMAs per k-block), weight planes packed once (df_pack_f16_pairs).
+# "hybrid16w": the same arithmetic, bit for bit, with the fp32 weight tile split into its planes ON CHIP (4 instead of 6 bytes
+# per weight element through the SM's fabric port).  Measured SLOWER (tower-1 0.41 vs 0.30 ms, profiles/r2_c3_gemm_ab.jsonl): the
+# conversion instructions of the extra splitter warps, not the port, then set the pace -- kept as the cross-check of the packed
+# planes and as the record of the experiment, not used by default.
+PRECISIONS = {"fp32": 0, "3xtf32": 1, "tf32": 2, "hybrid": 3, "hybrid16": 4, "hybrid16w": 5}
 
 
 def sym_mask(sym_list: Iterable[int]) -> int:
@@ -127,8 +128,8 @@ class SplitWeight:
         self.hi = self.lo = self.bf = self.h16 = None
 
     def operands(self, mode: int):
-        """The two weight operands df_gemm_tc / df_conv_tc expect for a PRECISIONS code (1 3xtf32, 2 tf32, 3 hybrid, 4 hybrid16p,
-        5 hybrid16: the fp32 weights themselves)."""
+        """The two weight operands df_gemm_tc / df_conv_tc expect for a PRECISIONS code (1 3xtf32, 2 tf32, 3 hybrid, 4 hybrid16,
+        5 hybrid16w: the fp32 weights themselves)."""
         if mode == 5:
             need_cuda(self.w)
             return self.w, self.w

@@ -25,6 +25,9 @@ extern "C" {
 /* ABI version and a bit mask of compiled features (bit 0: tcgen05 GEMM path). */
 int df_abi_version(void);
 int df_features(void);
+/* Measured-peak probe for the roofline report: launches blocks x 256 threads x 8 independent FFMA chains of `iters` steps
+ * (no memory traffic) and returns the number of flops launched (negative: error).  Not part of the pose path. */
+long long df_probe_ffma(float* sink, int blocks, int iters, void* stream);
 
 /* ---- K4: k nearest neighbours -----------------------------------------------------------------
  * Replaces   int knn(THCudaTensor *ref, THCudaTensor *query, THCudaLongTensor *idx)
@@ -177,6 +180,10 @@ int df_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
  * can be captured in a CUDA graph and replayed. */
 int df_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                      float beta1, float beta2, float eps, int* step_counter, void* stream);
+
+/* Multiply-adds df_conv_tc executes on real output pixels for this geometry (dense count minus the all-padding taps its pixel
+ * patches skip); host-side arithmetic only, for the time-weighted roofline of bench.py. */
+long long df_conv_tc_macs(int B, int H, int W, int Cin, int Cout, int taps, int dilation);
 
 /* ---- colour encoder on the tensor cores (lib/extractors.py:78-124, lib/pspnet.py:7-77) ----
  * Activations are NHWC.  df_conv_tc: 3x3 (stride 1, padding == dilation) or 1x1 convolution as an implicit GEMM on the

@@ -8,6 +8,7 @@ import torch.nn.functional as F
 
 from densefusion_b200 import synth
 from oracle import df_oracle as O
+from densefusion_b200 import ops
 from util import build_nets, rel
 
 pytestmark = pytest.mark.gpu
