@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--workload", default="pose", choices=["pose", "train", "c0", "c1"],
                     help="pose: the headline metric; train: config C4, data-parallel training step (16 samples / GPU / step); "
                          "c0: LineMOD batch-1 per-stage latencies (CPU port beside the GPU drop-ins); c1: PoseNet forward + ADD-S loss, 256 crops")
-    ap.add_argument("--phase", default="estimator", choices=["estimator", "refiner"])
+    ap.add_argument("--phase", default="estimator", choices=["estimator", "refiner", "both"])
     ap.add_argument("--num-points", type=int, default=500,
                     help="points per crop: 500 = the configuration the metric is quoted on; 1000 = the reference's YCB setting (config C2 variant)")
     args = ap.parse_args()
@@ -303,6 +303,27 @@ def time_weighted_roofline(pipe, dev_set, precision, peaks, live):
                     "multiply-adds x 2 on real rows (skipped all-padding taps not counted); peak = cuBLAS TF32 measured in this run"}
 
 
+def finish_roofline(roof, tw, precision, peaks, live):
+    """Fill in the fields that need the live-measured denominators (measured AFTER our own kernels were timed)."""
+    tf32_lib, ffma = live.get("cublas_tf32_tflops"), live.get("ffma_tflops")
+    roof["cublas_tf32_8192_tflops"], roof["ffma_tflops_measured"] = tf32_lib, ffma
+    if precision == "fp32":
+        if ffma:
+            roof["peak"], roof["peak_source"] = ffma, "fp32 FFMA pipe measured in this run (df_probe_ffma)"
+    elif tf32_lib:
+        roof["peak"] = tf32_lib
+        roof["peak_source"] = ("TF32 tensor peak = cuBLAS TF32 8192^3 measured in this run (MEASURED_PEAKS.json has no TF32 figure; half of its "
+                               f"bf16 burst would be {peaks.get('bf16_tflops', 1590.0) / 2.0:.1f})")
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["frac_of_bf16_burst_in_mma_time"] = PASSES.get(precision, 1.0) * 2.0 * roof["achieved"] / peaks.get("bf16_tflops", 1590.0) \
+        if precision != "fp32" else None
+    if tw is not None:
+        if tf32_lib:
+            tw["peak"] = tf32_lib
+        tw["frac"] = tw["achieved"] / tw["peak"]
+        roof["time_weighted"] = tw
+
+
 def dominant_kernel_roofline(pipe, precision, peaks, live):
     """Live timing of the bench's reference kernel: the first tower layer (conv1_{r,t,c} on the 384 local channels, N=1920)
     over one chunk, the largest single GEMM of the head."""
@@ -486,6 +507,7 @@ def run_ours(args):
         """Outside the timed region: the poses of the exact timed configuration (graph replay, all buckets, chunked head,
         bench precision) for `samples` crops spread over the buckets against the oracle's estimate + refine on the same inputs."""
         from oracle import df_oracle as O
+        preload_device_sets()                    # the end-to-end loop refilled the slots from the host in its own order
         poses = step_device(0).cpu().numpy()
         flat = [(bi, i) for bi, b in enumerate(host_sets[0]) for i in range(b["cloud"].shape[0])]
         stride = max(1, len(flat) // samples)
@@ -530,10 +552,13 @@ def run_ours(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        # our kernels first, the library / probe peaks afterwards: seconds of cuBLAS at the power cap pull the SM clock down
+        # for whatever is timed right behind them (measured: the same GEMM 0.30 ms before, 0.37 ms after)
+        roof = dominant_kernel_roofline(pipe, args.precision, peaks, {})
+        tw = time_weighted_roofline(pipe, dev_sets[0], args.precision, peaks, {}) if args.precision != "fp32" and pipe.encoder == "tc" else None
+        time.sleep(0.5)
         live = measured_peaks(dev)
-        roof = dominant_kernel_roofline(pipe, args.precision, peaks, live)
-        if args.precision != "fp32" and pipe.encoder == "tc":
-            roof["time_weighted"] = time_weighted_roofline(pipe, dev_sets[0], args.precision, peaks, live)
+        finish_roofline(roof, tw, args.precision, peaks, live)
         parity = parity_vs_oracle() if not args.no_parity else None
         extras = {}
         if not args.no_extras:
@@ -610,12 +635,17 @@ def make_train_buckets(seed: int, pin: bool):
     return buckets
 
 
-def measure_train(dev, phase, steps, warmup, world, rank, barrier, no_graph=False):
+def measure_train(dev, phase, steps, warmup, world, rank, barrier, no_graph=False, overlap=True, exchange=True, e2e=True):
     """ms per optimiser step (max over ranks done by the caller) with device-resident inputs and end to end."""
     from densefusion_b200 import synth
     from densefusion_b200.trainer import DataParallelTrainer, GraphedTrainStep
     est, ref, _, _ = build_modules(dev)
-    tr = DataParallelTrainer(est, ref, N_MESH, synth.YCB_SYM, lr=1e-4, w=0.015, iteration=ITERS, phase=phase)
+    # tools/train.py:136-140: the estimator phase trains with estimator.train() (Dropout2d of the PSPNet active), the refiner
+    # phase runs the frozen estimator in eval() mode
+    if phase == "estimator":
+        est.train()
+    tr = DataParallelTrainer(est, ref, N_MESH, synth.YCB_SYM, lr=1e-4, w=0.015, iteration=ITERS, phase=phase, overlap=overlap)
+    tr.exchange = exchange
     host_sets = [make_train_buckets(7000 + 31 * rank + s, pin=True) for s in range(2)]
     dev_sets = [[{k: v.to(dev) for k, v in b.items()} for b in hs] for hs in host_sets]
     samples = sum(b["points"].shape[0] for b in host_sets[0])
@@ -653,11 +683,28 @@ def measure_train(dev, phase, steps, warmup, world, rank, barrier, no_graph=Fals
         return e0.elapsed_time(e1) / steps
 
     ms_dev = timed(step_device)
-    ms_e2e = timed(step_e2e)
+    ms_e2e = timed(step_e2e) if e2e else None
     h2d = sum(v.numel() * v.element_size() for b in host_sets[0] for v in b.values())
     arena = tr.arena_est if phase == "estimator" else tr.arena_ref
-    return {"ms_per_step": ms_dev, "ms_per_step_e2e": ms_e2e, "samples_per_gpu": samples, "h2d_bytes_per_step": h2d,
-            "allreduce_bytes": arena.total * 4, "parameters": arena.numel, "launch": launch}
+    out = {"ms_per_step": ms_dev, "ms_per_step_e2e": ms_e2e, "samples_per_gpu": samples, "h2d_bytes_per_step": h2d,
+           "allreduce_bytes": arena.total * 4, "parameters": arena.numel, "launch": launch,
+           "comm_buckets": len(getattr(arena, "_buckets", None) or [1])}
+    if world > 1 and exchange:
+        import torch.distributed as dist
+        buf = torch.zeros_like(arena.grad)
+        for _ in range(3):
+            dist.all_reduce(buf)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            dist.all_reduce(buf)
+        e1.record()
+        barrier()
+        out["allreduce_ms_standalone"] = e0.elapsed_time(e1) / 10
+    del graphed, tr
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_train(args):
@@ -680,33 +727,51 @@ def run_train(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    sampler.start()
-    r = measure_train(dev, args.phase, args.steps, args.warmup, world, rank, barrier, args.no_graph)
-    clocks = sampler.stop()
-    t = torch.tensor([r["ms_per_step"], r["ms_per_step_e2e"]], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
-    total = world * r["samples_per_gpu"]
-    if rank == 0:
-        print(json.dumps({
-            "metric": "training samples/sec (data-parallel step: forward, fused loss, backward, all-reduce SUM, Adam)",
-            "value": total / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
-            "data": "synthetic",
-            "config": {"workload": f"config C4: YCB PoseNet({N_POINTS},21) {args.phase} phase, 16 samples per GPU per optimiser step "
-                                   "(6x80^2 + 6x120^2 + 4x160^2), gradient SUM semantics of tools/train.py:159-169",
-                       "global_batch": total, "phase": args.phase, "allreduce_bytes": r["allreduce_bytes"],
-                       "parameters": r["parameters"], "launch": r["launch"],
-                       "parallelism": f"dp{world}, one NCCL all-reduce per step"},
-            "clocks": clocks,
-            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": r["h2d_bytes_per_step"],
-                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e}}))
+    def maxed(*vals):
+        t = torch.tensor([v if v is not None else 0.0 for v in vals], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    phases = ["estimator", "refiner"] if args.phase == "both" else [args.phase]
+    for phase in phases:
+        sampler = ClockSampler(local)
+        sampler.start()
+        r = measure_train(dev, phase, args.steps, args.warmup, world, rank, barrier, args.no_graph)
+        clocks = sampler.stop()
+        ms, ms_e2e = maxed(r["ms_per_step"], r["ms_per_step_e2e"])
+        total = world * r["samples_per_gpu"]
+        coll = None
+        if world > 1:
+            # the collective's own cost and how much of it the overlap hides: the same step with ONE all-reduce after the last
+            # backward kernel (round-1 behaviour) and with the exchange switched off altogether
+            r_serial = measure_train(dev, phase, args.steps, args.warmup, world, rank, barrier, args.no_graph, overlap=False, e2e=False)
+            r_none = measure_train(dev, phase, args.steps, args.warmup, world, rank, barrier, args.no_graph, exchange=False, e2e=False)
+            ms_serial, ms_none, ar = maxed(r_serial["ms_per_step"], r_none["ms_per_step"], r.get("allreduce_ms_standalone"))
+            exposed_serial, exposed_overlap = ms_serial - ms_none, ms - ms_none
+            coll = {"collective": "ncclAllReduce SUM over the flat fp32 gradient arena", "bytes": r["allreduce_bytes"],
+                    "allreduce_ms_standalone": ar, "bus_GBps_standalone": 2.0 * (world - 1) / world * r["allreduce_bytes"] / (ar * 1e-3) / 1e9 if ar else None,
+                    "comm_buckets": r["comm_buckets"], "ms_per_step_overlapped": ms, "ms_per_step_single_allreduce_after_backward": ms_serial,
+                    "ms_per_step_without_exchange": ms_none, "exposed_ms_single": exposed_serial, "exposed_ms_overlapped": exposed_overlap,
+                    "overlap_fraction": (1.0 - exposed_overlap / exposed_serial) if exposed_serial > 1e-6 else None}
+        if rank == 0:
+            print(json.dumps({
+                "metric": "training samples/sec (data-parallel step: forward, fused loss, backward, all-reduce SUM, Adam)",
+                "value": total / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32",
+                "data": "synthetic",
+                "config": {"workload": f"config C4: YCB PoseNet({N_POINTS},21) {phase} phase, 16 samples per GPU per optimiser step "
+                                       "(6x80^2 + 6x120^2 + 4x160^2), gradient SUM semantics of tools/train.py:159-169, "
+                                       + ("estimator.train() (Dropout2d active)" if phase == "estimator" else "frozen estimator in eval()"),
+                           "global_batch": total, "phase": phase, "allreduce_bytes": r["allreduce_bytes"],
+                           "parameters": r["parameters"], "launch": r["launch"],
+                           "parallelism": f"dp{world}, bucketed NCCL all-reduces overlapped with the backward pass"},
+                "clocks": clocks, "collective": coll,
+                "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": r["h2d_bytes_per_step"],
+                        "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e}}), flush=True)
     barrier()
     if world > 1:
         dist.destroy_process_group()
-
 
 
 # ------------------------------------------------------------------------------------------------

@@ -808,10 +808,11 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
         long long best = -1;
         for (int i = 0; i < 4; ++i) {
             const int w = widths[i];
-            // 256-wide tiles leave room for ONE accumulator: fine for the store-free pooled epilogue, and (DF_TC_WIDE=1, A/B knob)
-            // for long-K layers, where the exposed epilogue of a tile is a few per cent of its k loop
-            static const int wide_ok = getenv("DF_TC_WIDE") ? atoi(getenv("DF_TC_WIDE")) : 0;
-            if (w == 256 && !p.pool_partial && !(wide_ok && p.K >= wide_ok * 1024)) continue;
+            // 256-wide tiles leave room for ONE accumulator: always fine for the store-free pooled epilogue; with stores the
+            // epilogue of a tile is exposed, which only pays once the k loop is long (>= 32 k-blocks: layer4 convolutions -15..17%,
+            // pose step +2.7%, profiles/r2_c4_ab_wide.jsonl; DF_TC_WIDE_KB overrides the threshold, 0 = never)
+            static const int wide_kb = getenv("DF_TC_WIDE_KB") ? atoi(getenv("DF_TC_WIDE_KB")) : 32;
+            if (w == 256 && !p.pool_partial && !(wide_kb > 0 && p.K / BK >= wide_kb)) continue;
             if (w == 192 && A_STAGES != 2) continue;
             if (w == 64 && p.N > 64) continue;                     // narrow layers only (64-channel decoder stages)
             if (p.N % w != 0 && (groups > 1 || w == 256)) continue;

@@ -60,6 +60,83 @@ class FlatArena:
                 p.data = self.param[o:o + n].view(p.shape)
                 p.grad = self.grad[o:o + n].view(p.shape)
 
+    # ---- gradient exchange overlapped with the backward pass ---------------------------------------------------------
+    def enable_overlap(self, bucket_bytes: int = 16 << 20) -> None:
+        """Cut the gradient arena into contiguous communication buckets (>= bucket_bytes each, from the END of the arena
+        backwards: autograd produces the head's gradients first and walks the encoder from its last layer to its first, i.e.
+        roughly in reverse parameter order) and hook every parameter: once all parameters of a bucket have received the last of
+        the step's `expected` gradient accumulations, that slice is all-reduced asynchronously while the backward kernels of the
+        earlier layers are still running.  `finish_all_reduce` launches whatever is left (parameters that never get a gradient,
+        e.g. the unused classifier) and makes the current stream wait for every exchange."""
+        if getattr(self, "_buckets", None) is not None:
+            return
+        bounds, end, acc = [], self.total, 0
+        for p, o in reversed(list(zip(self.params, self.offsets))):
+            acc = end - o
+            if acc * 4 >= bucket_bytes:
+                bounds.append((o, end))
+                end = o
+        if end > 0:
+            bounds.append((0, end))
+        self._buckets = bounds                                    # [(start, stop)] in backward order
+        self._bucket_of, self._bucket_size = {}, [0] * len(bounds)
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            b = next(k for k, (lo, hi) in enumerate(bounds) if lo <= o < hi)
+            self._bucket_of[i] = b
+            self._bucket_size[b] += 1
+        self._pending, self._launched, self._works, self._group, self._armed = [], [], [], None, False
+        self._fired, self._fired_known = set(), False              # parameters that received a gradient in the first armed step
+        for i, p in enumerate(self.params):
+            p.register_post_accumulate_grad_hook(self._make_hook(i))
+
+    def _make_hook(self, i):
+        def hook(_param):
+            if not self._armed:
+                return
+            if not self._fired_known:
+                self._fired.add(i)
+            elif i not in self._fired:
+                return
+            b = self._bucket_of[i]
+            self._pending[b] -= 1
+            if self._pending[b] == 0:
+                self._launch(b)
+        return hook
+
+    def _launch(self, b):
+        import torch.distributed as dist
+        lo, hi = self._buckets[b]
+        self._launched[b] = True
+        self._works.append(dist.all_reduce(self.grad[lo:hi], op=dist.ReduceOp.SUM, group=self._group, async_op=True))
+
+    def begin_step(self, expected: int, group=None) -> bool:
+        """Arm the overlap for one optimiser step in which every parameter receives `expected` gradient accumulations."""
+        import torch.distributed as dist
+        if getattr(self, "_buckets", None) is None or not (dist.is_available() and dist.is_initialized()
+                                                          and dist.get_world_size(group) > 1):
+            return False
+        if self._fired_known:                                      # parameters without a gradient (the unused classifier) do not count
+            sizes = [0] * len(self._buckets)
+            for i in self._fired:
+                sizes[self._bucket_of[i]] += 1
+        else:
+            sizes = self._bucket_size
+        self._pending = [n * expected if n else -1 for n in sizes]
+        self._launched = [False] * len(self._buckets)
+        self._works, self._group, self._armed = [], group, True
+        return True
+
+    def finish_all_reduce(self) -> None:
+        self._armed = False
+        if not self._fired_known and self._fired:
+            self._fired_known = True
+        for b in range(len(self._buckets)):
+            if not self._launched[b]:
+                self._launch(b)
+        for w in self._works:
+            w.wait()                                              # current stream waits for NCCL's stream
+        self._works = []
+
     def zero_grad(self) -> None:
         self.grad.zero_()
         for p, o in zip(self.params, self.offsets):          # re-attach if someone set .grad = None
@@ -109,7 +186,7 @@ class DataParallelTrainer:
 
     def __init__(self, estimator, refiner, num_points_mesh: int, sym_list: Sequence[int], lr: float = 1e-4,
                  w: float = 0.015, iteration: int = 2, phase: str = "estimator", group=None,
-                 frozen_precision: str = "hybrid16"):
+                 frozen_precision: str = "hybrid16", overlap: Optional[bool] = None):
         from .lib.loss import Loss
         from .lib.loss_refiner import Loss_refine
         self.estimator, self.refiner = estimator, refiner
@@ -119,6 +196,11 @@ class DataParallelTrainer:
         # arithmetic of the FROZEN estimator in the refiner phase (no gradient flows through it, tools/train.py:93):
         # an fp32-parity tensor-core mode runs its encoder + head 4-5x faster than the exact-fp32 / cuDNN path
         self.frozen_precision = frozen_precision
+        # overlap the gradient exchange with the backward pass (bucketed asynchronous all-reduces, see FlatArena.enable_overlap);
+        # DF_DP_OVERLAP=0 / overlap=False: ONE all-reduce of the whole arena after the last backward kernel (round-1 behaviour)
+        import os
+        self.overlap = (os.environ.get("DF_DP_OVERLAP", "1") != "0") if overlap is None else bool(overlap)
+        self.exchange = os.environ.get("DF_DP_EXCHANGE", "1") != "0"     # 0: skip the exchange (measurement of its cost only)
         self.arena_est: Optional[FlatArena] = None
         self.arena_ref: Optional[FlatArena] = None
         self.set_phase(phase)
@@ -174,9 +256,17 @@ class DataParallelTrainer:
         arena = self.arena_est if self.phase == "estimator" else self.arena_ref
         arena.zero_grad()
         fn = self._local_estimator if self.phase == "estimator" else self._local_refiner
+        overlapped = False
+        if self.overlap and self.exchange:
+            arena.enable_overlap()
+            backwards = len(buckets) * (1 if self.phase == "estimator" else self.iteration)
+            overlapped = arena.begin_step(backwards, self.group)
         with conv_tc.weight_cache():             # every convolution weight is packed once per step, not once per bucket
             loss_sum, dis_sum = fn(buckets)
-        arena.all_reduce(self.group)
+        if overlapped:
+            arena.finish_all_reduce()
+        elif self.exchange:
+            arena.all_reduce(self.group)
         arena.adam_step(self.lr)
         return {"loss_sum": loss_sum, "dis_sum": dis_sum}
 

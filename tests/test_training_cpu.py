@@ -142,3 +142,52 @@ def test_gloo_world2_allreduce_equals_serial_accumulation():
     for i in range(10):
         net(data[i:i + 1]).pow(2).sum().backward()
     assert torch.allclose(ret[0], arena.grad, atol=1e-5) and torch.equal(ret[0], ret[1])
+
+
+def _dp_overlap_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from densefusion_b200.trainer import FlatArena, shard_range
+        torch.manual_seed(0)
+        # `unused` never receives a gradient (like the encoder's classifier): its bucket is exchanged by the final flush
+        net = torch.nn.ModuleDict({"a": torch.nn.Linear(6, 40), "b": torch.nn.Linear(40, 40), "c": torch.nn.Linear(40, 2),
+                                   "unused": torch.nn.Linear(3, 3)})
+        arena = FlatArena(net.parameters())
+        arena.enable_overlap(bucket_bytes=4 * 300)          # several buckets
+        assert len(arena._buckets) >= 3 and arena._buckets[-1][0] == 0 and arena._buckets[0][1] == arena.total
+        data = torch.randn(12, 6, generator=torch.Generator().manual_seed(1))
+        mine = list(shard_range(12, rank, world))
+        launched_early = []
+        for step in range(2):                                # two optimiser steps: the counters re-arm
+            arena.zero_grad()
+            assert arena.begin_step(expected=len(mine))
+            for i in mine:
+                net["c"](torch.relu(net["b"](torch.relu(net["a"](data[i:i + 1]))))).pow(2).sum().backward()
+            launched_early.append(sum(arena._launched))
+            arena.finish_all_reduce()
+        ret[rank] = (arena.grad.clone(), launched_early, len(arena._buckets))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_overlapped_bucketed_allreduce_equals_serial_accumulation():
+    """The bucketed exchange launched from the parameters' post-accumulate hooks (trainer.FlatArena.enable_overlap) gives the same
+    summed gradients as serial accumulation, launches the gradient-carrying buckets before the backward pass has ended, and
+    leaves parameters that never receive a gradient to the final flush."""
+    world, port = 2, _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_dp_overlap_worker, args=(world, port, ret), nprocs=world, join=True)
+    from densefusion_b200.trainer import FlatArena
+    torch.manual_seed(0)
+    net = torch.nn.ModuleDict({"a": torch.nn.Linear(6, 40), "b": torch.nn.Linear(40, 40), "c": torch.nn.Linear(40, 2),
+                               "unused": torch.nn.Linear(3, 3)})
+    arena = FlatArena(net.parameters())
+    data = torch.randn(12, 6, generator=torch.Generator().manual_seed(1))
+    for i in range(12):
+        net["c"](torch.relu(net["b"](torch.relu(net["a"](data[i:i + 1]))))).pow(2).sum().backward()
+    g0, early, nb = ret[0]
+    assert torch.allclose(g0, arena.grad, atol=1e-5) and torch.equal(g0, ret[1][0])
+    # first step: the bucket that also holds `unused` waits for the final flush; afterwards the arena knows which parameters
+    # receive gradients and every bucket goes out from the hooks, before the backward pass has ended
+    assert 0 < early[0] < nb and early[1] == nb
