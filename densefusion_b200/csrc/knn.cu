@@ -14,6 +14,7 @@ namespace {
 
 constexpr int KNN_THREADS = 256;
 constexpr int KNN_TILE = 2048;   // reference points per shared-memory tile (32 KB as float4)
+constexpr long KNN_WARP_MAX_QUERIES = 148L * 8 * 8 * 2;   // up to two waves of warps (8 CTAs x 8 warps per SM): 18 944 queries
 
 // ---- D = 3, k = 1 : the path's own shape (lib/loss.py:42-47, tools/eval_linemod.py:124-128) ----
 template <int QPT>
@@ -61,7 +62,45 @@ knn1_d3_kernel(const float* __restrict__ ref, const float* __restrict__ query, i
     }
 }
 
-// ---- general (D, k): literal k-slot insertion of cuInsertionSort, distances on the fly ----------
+// ---- D = 3, k = 1, FEW queries (lib/loss_refiner.py:40-46 and tools/eval_linemod.py:124-128: Q = R = 500 ... 2600) ----
+// One query per thread leaves 2-11 CTAs on 148 SMs and every thread a serial scan of all R references.  Here a WARP owns a
+// query: lane l scans references l, l+32, ... (coalesced, dim-major) keeping its (min, first index) under the strict '<', then
+// the 32 partial results are reduced lexicographically on (distance, index) by shuffles, so the LOWEST index wins a tie exactly
+// as in the reference's sequential scan (knn_cuda_kernel.cu:150-167).  NaN: a NaN candidate never satisfies '<' (skipped, as in
+// the reference); a NaN distance to row 0 -- the reference's seed, knn_cuda_kernel.cu:122 -- never loses, so the answer is row 0;
+// an all-(+inf) column also keeps the seed.
+__global__ void __launch_bounds__(KNN_THREADS)
+knn1_d3_warp_kernel(const float* __restrict__ ref, const float* __restrict__ query, int64_t* __restrict__ ind, int R, int Q)
+{
+    const int b = blockIdx.y;
+    ref += (size_t)b * 3 * R;
+    query += (size_t)b * 3 * Q;
+    ind += (size_t)b * Q;
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (KNN_THREADS / 32) + (threadIdx.x >> 5);
+    if (q >= Q) return;                                         // whole warps leave together
+    const float qx = __ldg(query + q), qy = __ldg(query + Q + q), qz = __ldg(query + 2 * (size_t)Q + q);
+    float best = CUDART_INF_F;
+    int bi = 0x7fffffff;
+    for (int r = lane; r < R; r += 32) {
+        const float d = df::ref_ssd3(__ldg(ref + r), __ldg(ref + R + r), __ldg(ref + 2 * (size_t)R + r), qx, qy, qz);
+        if (d < best) { best = d; bi = r; }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
+    }
+    if (lane == 0) {
+        const float d0 = df::ref_ssd3(__ldg(ref), __ldg(ref + R), __ldg(ref + 2 * (size_t)R), qx, qy, qz);
+        const int idx = (d0 != d0 || bi == 0x7fffffff) ? 0 : bi;
+        ind[q] = (int64_t)idx + 1;                              // 1-based (knn_cuda_kernel.cu:123,163)
+    }
+}
+
+// ---- general (D, k): the k-slot insertion of the reference's cuInsertionSort restated with register arrays, distances on
+// the fly (needed to reproduce the k > 1 ordering quirks bit for bit; not on the pose path) ----------
 constexpr int KNN_KMAX = 64;
 
 __global__ void __launch_bounds__(128)
@@ -132,7 +171,10 @@ extern "C" int df_knn(const float* ref, const float* query, int64_t* ind, int ba
     if (dim == 3 && k == 1) {
         // enough CTAs for >= 2 waves of 148 SMs x 8 resident CTAs when Q allows, else fewer queries/thread
         const long per_wave = 148L * 8 * KNN_THREADS;
-        if ((long)Q * batch >= 8 * per_wave) {
+        if ((long)Q * batch <= KNN_WARP_MAX_QUERIES) {         // few queries: a warp per query (see knn1_d3_warp_kernel)
+            dim3 grid((Q + KNN_THREADS / 32 - 1) / (KNN_THREADS / 32), batch);
+            knn1_d3_warp_kernel<<<grid, KNN_THREADS, 0, s>>>(ref, query, ind, R, Q);
+        } else if ((long)Q * batch >= 8 * per_wave) {
             dim3 grid((Q + KNN_THREADS * 4 - 1) / (KNN_THREADS * 4), batch);
             knn1_d3_kernel<4><<<grid, KNN_THREADS, 0, s>>>(ref, query, ind, R, Q);
         } else if ((long)Q * batch >= 2 * per_wave) {

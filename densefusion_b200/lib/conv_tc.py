@@ -27,6 +27,16 @@ WGRAD_TC = True         # weight gradients on df_conv_wgrad_tc (3xTF32 GEMM over
 # step's eager warm-up on a side stream nevertheless ends, asynchronously, in an illegal address reported inside layer2 --
 # with or without programmatic dependent launch.  Not root-caused (next: bisect with a synchronisation after every op).
 STRIDE2_TC = os.environ.get("DF_STRIDE2_TC", "0") == "1"
+_S2_ONLY = tuple(int(v) for v in os.environ.get("DF_S2_ONLY", "7,3,1").split(",") if v)     # debug: kernel sizes ConvS2Fn takes
+_S2_SYNC = os.environ.get("DF_S2_SYNC", "0") == "1"                                          # debug: synchronise after every call
+
+
+def _s2_sync(what):
+    if _S2_SYNC:
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:
+            raise RuntimeError(f"ConvS2Fn: CUDA error surfaced after {what}") from e
 PRECISION = "hybrid16"
 
 
@@ -186,6 +196,7 @@ class ConvS2Fn(torch.autograd.Function):
                  relu=False, precision=PRECISION, short_runs=True)
         ctx.save_for_backward(a, weight)
         ctx.in_shape = tuple(x.shape)
+        _s2_sync(f"forward k={k} x={tuple(x.shape)}")
         return y.view(b, ho, wo, cout).permute(0, 3, 1, 2)                   # channels_last storage, NCHW shape
 
     @staticmethod
@@ -215,6 +226,7 @@ class ConvS2Fn(torch.autograd.Function):
                 dxn.zero_()
                 dxn[:, ::2, ::2, :] = da.view(b, (h - 1) // 2 + 1, (w - 1) // 2 + 1, cin)
             dx = dxn.permute(0, 3, 1, 2)
+        _s2_sync(f"backward k={k} in={ctx.in_shape}")
         return dx, dw
 
 
@@ -225,6 +237,8 @@ def eligible_s2(m: nn.Conv2d, x: torch.Tensor) -> bool:
             and m.dilation == (1, 1) and m.out_channels % 64 == 0):
         return False
     k = m.kernel_size
+    if k[0] not in _S2_ONLY:
+        return False
     if k == (7, 7):
         return m.padding == (3, 3) and m.in_channels == 3 and not x.requires_grad
     if k == (3, 3):

@@ -39,20 +39,24 @@ def test_knn1_batched():
     _check(torch.randn(3, 3, 300, generator=g), torch.randn(3, 3, 1111, generator=g))
 
 
-def test_knn1_lattice_ties_and_duplicates():
+# Q <= 18 944 takes the warp-per-query kernel (lanes split the references, lexicographic (distance, index) shuffle reduction),
+# larger Q the thread-per-query kernel: the tie / duplicate / NaN sets run through both
+@pytest.mark.parametrize("Q", [5000, 40000])
+def test_knn1_lattice_ties_and_duplicates(Q):
     g = torch.Generator().manual_seed(11)
     ref = torch.randint(0, 8, (1, 3, 700), generator=g).float() / 1024.0       # many exact ties
     ref[0, :, 350:] = ref[0, :, :350]                                          # exact duplicates
-    qry = torch.randint(0, 8, (1, 3, 5000), generator=g).float() / 1024.0
+    qry = torch.randint(0, 8, (1, 3, Q), generator=g).float() / 1024.0
     _check(ref, qry)
     ours = _ours(ref, qry).view(-1)
     assert int(ours.max()) <= 350                                               # lowest index of each duplicate pair
 
 
-def test_knn1_nan_inf_rows():
+@pytest.mark.parametrize("Q", [999, 25000])
+def test_knn1_nan_inf_rows(Q):
     g = torch.Generator().manual_seed(12)
     ref = torch.randn(1, 3, 100, generator=g)
-    qry = torch.randn(1, 3, 999, generator=g)
+    qry = torch.randn(1, 3, Q, generator=g)
     ref[0, 0, 5] = float("nan")
     ref[0, 1, 17] = float("inf")
     qry[0, 2, 3] = float("nan")
@@ -61,6 +65,26 @@ def test_knn1_nan_inf_rows():
     ref[0, 0, 0] = float("nan")              # NaN in row 0: the reference never leaves index 1
     _check(ref, qry)
     assert torch.all(_ours(ref, qry) == 1)
+    # every distance +inf (an infinite coordinate in every reference): the seed row stays; and +inf rows beside finite ones
+    ref = torch.randn(1, 3, 100, generator=g)
+    ref[0, 0, :] = float("inf")
+    _check(ref, qry)
+    assert torch.all(_ours(ref, qry) == 1)
+    ref[0, 0, 40:] = 0.25
+    _check(ref, qry)
+
+
+@pytest.mark.parametrize("R", [500, 2600])
+def test_knn1_small_q_shapes_of_the_refiner_loss(R):
+    """Q = R = num_pt_mesh (lib/loss_refiner.py:40-46, tools/eval_linemod.py:124-128): the warp-per-query path, incl. the model
+    queried against itself (every point is its own nearest neighbour or an earlier duplicate's)."""
+    g = torch.Generator().manual_seed(R)
+    pts = torch.randn(1, 3, R, generator=g) * 0.05
+    pts[0, :, R // 2:R // 2 + 20] = pts[0, :, 0:20]                            # duplicates: the earlier index must win
+    _check(pts, pts)
+    _check(pts, pts + torch.randn(1, 3, R, generator=g) * 1e-3)
+    self_ind = _ours(pts, pts).view(-1)
+    assert torch.all(self_ind <= torch.arange(1, R + 1))
 
 
 @pytest.mark.parametrize("D,R,Q,k", [(128, 100, 1000, 2), (3, 64, 500, 5), (5, 33, 70, 1), (3, 40, 40, 40)])
