@@ -16,6 +16,7 @@
 #include "../../include/densefusion_b200.h"
 #include <cuda.h>
 #include <stdlib.h>
+#include <stdio.h>
 
 namespace {
 
@@ -45,6 +46,12 @@ struct TcParams {
     // of the chain (measured 3xTF32 error 3e-6 at K = 384 but 6.5e-5 at K = 9216); short chains keep long-K convolutions
     // at fp32-parity.  k_chunks == 1: plain single-run accumulation.
     int k_chunks, kbc;
+    // Rounding-bias compensation: the tensor core TRUNCATES TOWARD ZERO when it adds an instruction's products into the fp32
+    // accumulator -- measured -0.30 .. -0.45 ulp per MMA instruction for same-sign sums, almost free of scatter (rms == |mean|,
+    // scripts/trunc_probe.py, profiles/r2_c7_trunc.jsonl) -- a bias that grows with the chain and, unlike rounding noise, adds
+    // up coherently from layer to layer.  The epilogue multiplies every accumulation run by 1 + bias_comp * (MMA instructions
+    // of the run); bias_comp = the measured mean truncation per instruction for the layer's operand statistics (0: off).
+    float bias_comp;
     int run_steps;                              // host side only: MMA instructions per accumulation run, 0 = default
     // ---- weight-gradient form (df_conv_wgrad_tc): output column n = tap * wk_rows + ci multiplies row ci of the W operand
     // read wk_shift[tap] elements further along k (a 3x3 tap is an offset in the zero-padded, flattened pixel axis) ----
@@ -84,6 +91,11 @@ using namespace df_tc;
 // the MMAs of tile i+1 -- 123 MB of tower-1 output cannot be left to bursts between tiles; one 256-wide accumulator
 // only for the store-free pooled epilogue), two A stages in [384,512).
 // ------------------------------------------------------------------------------------------------
+// Per-instruction truncation compensation per arithmetic mode (see TcParams::bias_comp), calibrated on B200 with
+// scripts/trunc_probe.py: mean signed error of mixed-sign / post-ReLU dot products per MMA instruction of the chain (hybrid16
+// -1.61e-6 over 96 instructions, hybrid -2.31e-6 over 128, 3xtf32 -3.72e-6 over 192).  Effect on the bench configuration
+// (profiles/r2_c8_bias_comp.txt): worst pose error of 32 crops against the oracle 1.03e-4 -> 3.5e-5, rms GEMM error halved.
+constexpr float BIAS_COMP_H16 = 1.6e-8f, BIAS_COMP_HYBRID = 1.8e-8f, BIAS_COMP_3XTF32 = 1.9e-8f;
 constexpr int Q_THREADS = 18 * 32;
 constexpr int Q_SPLIT_THREADS = 2 * 32;                      // RAW_W: two more warps split the fp32 weight tile on chip
 constexpr int Q_PLANES = 4;                                  // RAW_W: depth of the operand-plane / a_full / mma_done rings
@@ -561,12 +573,23 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 bias += (size_t)((row_ok ? c.row0 + r : 0) / p.rows_per_crop) * p.bias_crop_stride;
             }
             const float slope = p.relu == 2 ? __ldg(p.prelu) : 0.0f;
+            float run_scale = 1.0f;
+            if (p.bias_comp != 0.0f) {
+                const int nkb_t = p.conv_taps == 9 ? __popc(c.taps) * (p.K / (BK * 9)) : nkb;
+                const int n_kb = min(nkb_t, (kc + 1) * p.kbc) - kc * p.kbc;
+                const int per_kb = p.precise == 1 ? 12 : (p.precise == 2 ? 8 : (p.precise == 3 ? 6 : 4));
+                run_scale = 1.0f + p.bias_comp * (float)(n_kb * per_kb);
+            }
             mbar_wait(acc_full + ab, (ti / ACC_BUFS) & 1);
             tc_fence_after();
 #pragma unroll 1
             for (int ch = half; ch < nchunks; ch += 2) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + lane_base + ab * ACC_STRIDE + ch * 32, v);
+                if (run_scale != 1.0f) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * run_scale);
+                }
                 const int col = c.n0 + ch * 32;
                 if (p.pool_partial) {
                     float f[32];
@@ -756,6 +779,17 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
         // (18 k-blocks of 3xTF32 at 12 per k-block, 27 of hybrid at 8, 36 of hybrid16 at 6).
         // Inference default 216; the training path asks for 108 (precision bits 8..15): the truncation is a BIAS, which the
         // sums over pixels of a weight gradient amplify (layer4.1.conv1 gradient error 9e-4 at 108, 5.9e-3 at 216, measured).
+        {   // DF_TC_BIAS_COMP="h16,hybrid,3xtf32" (per-instruction factors; calibration knob)
+            static float comp[3] = {0.f, 0.f, 0.f};
+            static bool parsed = false;
+            if (!parsed) {
+                const char* e = getenv("DF_TC_BIAS_COMP");
+                if (e) sscanf(e, "%f,%f,%f", &comp[0], &comp[1], &comp[2]);
+                else { comp[0] = BIAS_COMP_H16; comp[1] = BIAS_COMP_HYBRID; comp[2] = BIAS_COMP_3XTF32; }
+                parsed = true;
+            }
+            p.bias_comp = p.precise == 3 ? comp[0] : (p.precise == 2 ? comp[1] : (p.precise == 1 ? comp[2] : 0.0f));
+        }
         static const int env_steps = getenv("DF_TC_RUN_STEPS") ? atoi(getenv("DF_TC_RUN_STEPS")) : 216;
         const int run_steps = p.run_steps > 0 ? p.run_steps : env_steps;
         const int per_kb = p.precise == 1 ? 12 : (p.precise == 2 ? 8 : 6);

@@ -23,7 +23,9 @@ struct Probe {
     int iters;          // stage fills per CTA
     int stages;         // ring depth
     int PA, PW;         // CTAs sharing one A tile (along N) / one W tile (along M); cluster = 2 * PA * PW
-    int mc;             // 1: each CTA loads 1/PA of A and 1/PW of W and multicasts; 0: every CTA loads all of its tiles itself
+    int mc;             // 1: each CTA loads 1/PA of A and 1/PW of W and multicasts; 0: every CTA loads all of its tiles itself;
+                        // 2 (PA == 2, PW == 1): each CTA loads HALF of the A tile from L2 and pushes it to its twin (the CTA of the other
+                        // pair that needs the same rows) through distributed shared memory (cp.async.bulk shared::cta -> shared::cluster)
     int a_rows, w_rows; // rows per CTA tile: A 128 rows x 128 B, W w_rows x 128 B
     int a_blocks, w_blocks, kblocks;
 };
@@ -35,7 +37,16 @@ __device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, void* dst
                  : "memory");
 }
 
-__global__ void __launch_bounds__(64, 1)
+__device__ __forceinline__ void dsmem_push(void* dst_local, const void* src, uint32_t bytes, uint64_t* bar_local, uint32_t cta)
+{
+    uint32_t rdst, rbar;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(smem_u32(dst_local)), "r"(cta));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(bar_local)), "r"(cta));
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(rdst), "r"(smem_u32(src)), "r"(bytes), "r"(rbar) : "memory");
+}
+
+__global__ void __launch_bounds__(96, 1)
 probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const Probe p, long long* cycles)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -44,6 +55,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     const uint32_t stage_bytes = (a_bytes + w_bytes + 1023) & ~1023u;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* empty = full + 16;
+    uint64_t* half_full = full + 32;                            // mc == 2: this CTA's own half of the A tile has landed
     const int CL = 2 * p.PA * p.PW;
     const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
     const int h = rank & 1, ia = (rank >> 1) % p.PA, iw = (rank >> 1) / p.PA;
@@ -51,7 +63,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     const int warp = threadIdx.x >> 5;
     const int writers = p.mc ? p.PA + p.PW - 1 : 1;             // CTAs whose TMA writes into my stages (me included)
     if (threadIdx.x == 0) {
-        for (int i = 0; i < p.stages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, writers); }
+        for (int i = 0; i < p.stages; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, writers); mbar_init(half_full + i, 1); }
         fence_barrier_init();
     }
     __syncthreads();
@@ -66,8 +78,19 @@ probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
             for (int it = 0; it < p.iters; ++it) {
                 const int s = it % p.stages;
                 mbar_wait(empty + s, ((it / p.stages) & 1) ^ 1);
-                mbar_expect_tx(full + s, a_bytes + w_bytes);
                 uint8_t* dst = smem + (size_t)s * stage_bytes;
+                if (p.mc == 2) {
+                    // own half of A from L2 (signals half_full), W from L2 and the twin's half by DSMEM push (both signal full)
+                    const int kb2 = it % p.kblocks, tile2 = it / p.kblocks;
+                    const int ablk2 = (int)(((long long)cid * 2 + h + (long long)tile2 * 37) % p.a_blocks);
+                    const int wblk2 = (int)(((long long)(tile2 * p.PA + ia) * 2 + h + cid % 5) % p.w_blocks);
+                    mbar_expect_tx(half_full + s, a_bytes / 2);
+                    mbar_expect_tx(full + s, a_bytes / 2 + w_bytes);
+                    tma_load_2d(&tm_a, dst + ia * (a_bytes / 2), half_full + s, kb2 * 32, ablk2 * p.a_rows + ia * (p.a_rows / 2));
+                    tma_load_2d(&tm_w, dst + a_bytes, full + s, kb2 * 32, wblk2 * p.w_rows);
+                    continue;
+                }
+                mbar_expect_tx(full + s, a_bytes + w_bytes);
                 const int kb = it % p.kblocks, tile = it / p.kblocks;
                 // the A tile of (cluster, iw, h): shared by the PA CTAs along N; the W tile of (tile, ia, h): shared along M
                 const int ablk = (int)(((long long)(cid * p.PW + iw) * 2 + h + (long long)tile * 37) % p.a_blocks);
@@ -82,10 +105,21 @@ probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                     tma_load_2d(&tm_w, dst + a_bytes, full + s, kb * 32, wblk * p.w_rows);
             }
         }
+    } else if (threadIdx.x == 64) {
+        if (p.mc == 2) {                                        // pusher: forward my half of A to the twin as soon as it has landed
+            const uint32_t twin = (uint32_t)(h + 2 * (1 - ia));
+            for (int it = 0; it < p.iters; ++it) {
+                const int s = it % p.stages;
+                mbar_wait(half_full + s, (it / p.stages) & 1);
+                uint8_t* mine = smem + (size_t)s * stage_bytes + ia * (a_bytes / 2);
+                dsmem_push(mine, mine, a_bytes / 2, full + s, twin);
+            }
+        }
     } else if (threadIdx.x == 32) {
         for (int it = 0; it < p.iters; ++it) {
             const int s = it % p.stages;
             mbar_wait(full + s, (it / p.stages) & 1);
+            if (p.mc == 2) mbar_wait(half_full + s, (it / p.stages) & 1);
             if (!p.mc) mbar_arrive(empty + s);
             else {
                 for (int j = 0; j < p.PA; ++j) mbar_arrive_remote(empty + s, (uint32_t)(h + 2 * (j + p.PA * iw)));
@@ -156,6 +190,9 @@ int main(int argc, char** argv)
         {4, 1, 1, 4, 1, 1, "cluster 8 (4 pairs along N), A tile multicast to 4"},
         {1, 4, 1, 4, 1, 1, "cluster 8 (4 pairs along M), W tile multicast to 4"},
         {2, 4, 1, 4, 1, 1, "cluster 16 (2 along N x 4 along M), multicast"},
+        {2, 1, 2, 4, 1, 1, "cluster 4 (2 pairs along N), half of A from L2 + half pushed by the twin over DSMEM"},
+        {2, 1, 2, 6, 1, 1, "the same, 6 stages"},
+        {2, 1, 2, 4, 1, 2, "the same, half of the clusters"},
     };
     const int ncfg = (int)(sizeof(cfgs) / sizeof(cfgs[0]));
     bool first = true;
@@ -166,13 +203,13 @@ int main(int argc, char** argv)
         p.a_rows = 128; p.w_rows = 144; p.a_blocks = a_blocks; p.w_blocks = w_blocks; p.kblocks = kblocks;
         const int CL = 2 * c.PA * c.PW;
         CUtensorMap ma, mw;
-        const int a_box = c.mc ? p.a_rows / c.PA : p.a_rows, w_box = c.mc ? p.w_rows / c.PW : p.w_rows;
+        const int a_box = c.mc ? p.a_rows / c.PA : p.a_rows, w_box = c.mc == 1 ? p.w_rows / c.PW : p.w_rows;
         if (!make_map(fn, &ma, A, (long long)a_blocks * 128, K, a_box) || !make_map(fn, &mw, W, (long long)w_blocks * 144, K, w_box)) {
             fprintf(stderr, "tensor map failed\n"); return 1;
         }
-        const size_t smem_bytes = 1024 + (size_t)c.stages * ((p.a_rows * 128 + p.w_rows * 128 + 1023) & ~1023) + 512;
+        const size_t smem_bytes = 1024 + (size_t)c.stages * ((p.a_rows * 128 + p.w_rows * 128 + 1023) & ~1023) + 1024;
         cudaLaunchConfig_t cfg = {};
-        cfg.blockDim = dim3(64); cfg.dynamicSmemBytes = smem_bytes;
+        cfg.blockDim = dim3(96); cfg.dynamicSmemBytes = smem_bytes;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -209,7 +246,7 @@ int main(int argc, char** argv)
         const double bytes_cta = (double)p.iters * (p.a_rows + p.w_rows) * 128.0;
         const double ctas = (double)clusters * CL;
         const double delivered = bytes_cta * ctas;
-        const double requested = c.mc ? (double)p.iters * ctas * (p.a_rows * 128.0 / c.PA + p.w_rows * 128.0 / c.PW) : delivered;
+        const double requested = c.mc ? (double)p.iters * ctas * (p.a_rows * 128.0 / c.PA + p.w_rows * 128.0 / (c.mc == 2 ? 1 : c.PW)) : delivered;
         const double cyc_avg = csum / ctas;
         fprintf(out, "%s {\"what\": \"%s\", \"cluster\": %d, \"share_a\": %d, \"share_w\": %d, \"multicast\": %d, \"stages\": %d, \"ctas\": %d, "
                      "\"ms\": %.4f, \"delivered_TBps\": %.3f, \"l2_requested_TBps\": %.3f, \"delivered_B_per_clk_per_sm\": %.2f, "

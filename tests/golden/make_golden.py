@@ -252,9 +252,74 @@ def ply_case():
     print("ply_pair ADD", add, "ADD-S", adds)
 
 
+def customcad_case():
+    """Real geometry shipped in the reference tree: datasets/customCAD/{depth_projected,model,target}.ply
+    = an observed cloud (1000 points), the CAD model (500) and the model under the ground-truth pose (500).  The reference's
+    OWN Loss / Loss_refine (ADD and, with the kNN rebound as above, ADD-S) and its transformations functions run on them with
+    seeded per-point hypotheses scattered around the true pose."""
+    base = "/root/reference/datasets/customCAD/"
+    cloud = torch.from_numpy(ply_points(base + "depth_projected.ply").astype(np.float32)).view(1, -1, 3)
+    model = torch.from_numpy(ply_points(base + "model.ply").astype(np.float32)).view(1, -1, 3)
+    target = torch.from_numpy(ply_points(base + "target.ply").astype(np.float32)).view(1, -1, 3)
+    n, m = cloud.shape[1], model.shape[1]
+    g = torch.Generator().manual_seed(2024)
+    # the rigid motion model -> target (Kabsch on the corresponding points), then noisy per-point hypotheses around it
+    mc, tc = model[0].double().mean(0), target[0].double().mean(0)
+    H = (model[0].double() - mc).t() @ (target[0].double() - tc)
+    U, _, Vt = np.linalg.svd(H.numpy())
+    R = Vt.T @ np.diag([1, 1, np.sign(np.linalg.det(Vt.T @ U.T))]) @ U.T
+    M4 = np.eye(4); M4[:3, :3] = R
+    q_gt = quaternion_from_matrix(M4, True)
+    t_gt = tc.numpy() - R @ mc.numpy()
+    pred_r = (torch.from_numpy(q_gt).float().view(1, 1, 4) * (1.0 + 0.3 * torch.rand(1, n, 1, generator=g))
+              + 0.05 * torch.randn(1, n, 4, generator=g)).contiguous()          # un-normalised, as the head emits them
+    pred_t = (torch.from_numpy(t_gt).float().view(1, 1, 3) - cloud + 0.004 * torch.randn(1, n, 3, generator=g)).contiguous()
+    pred_c = (torch.rand(1, n, 1, generator=g) * 0.9 + 0.05).contiguous()
+    out = dict(cloud=npy(cloud), model=npy(model), target=npy(target), pred_r=npy(pred_r), pred_t=npy(pred_t), pred_c=npy(pred_c),
+               q_gt=q_gt, t_gt=t_gt, sym_list=np.array([5]), w=np.array(0.015))
+    for tag, obj in (("add", 3), ("adds", 5)):
+        idx = torch.tensor([[obj]])
+        pr, pt, pc = [t.clone().requires_grad_(True) for t in (pred_r, pred_t, pred_c)]
+        loss, dis, new_points, new_target = Loss(m, [5])(pr, pt, pc, target, model, idx, cloud, 0.015, False)
+        loss.backward()
+        out.update({f"{tag}_loss": npy(loss), f"{tag}_dis": npy(dis), f"{tag}_new_points": npy(new_points),
+                    f"{tag}_new_target": npy(new_target), f"{tag}_g_r": npy(pr.grad), f"{tag}_g_t": npy(pt.grad),
+                    f"{tag}_g_c": npy(pc.grad)})
+        r1 = (torch.tensor([1.0, 0.01, -0.02, 0.015]) * 1.3).view(1, 4).requires_grad_(True)
+        t1 = torch.tensor([[0.002, -0.001, 0.003]], requires_grad=True)
+        dis_r, np_r, nt_r = Loss_refine(m, [5])(r1, t1, new_target, model, idx, new_points)
+        dis_r.backward()
+        out.update({f"{tag}_ref_dis": npy(dis_r), f"{tag}_ref_new_points": npy(np_r), f"{tag}_ref_new_target": npy(nt_r),
+                    f"{tag}_ref_g_r": npy(r1.grad), f"{tag}_ref_g_t": npy(t1.grad)})
+        print("customcad", tag, "loss", float(loss), "dis", float(dis), "ref_dis", float(dis_r))
+    # eval-style selection and one pose composition with the reference's transformations (tools/eval_ycb.py:193-229)
+    q = pred_r / torch.norm(pred_r, dim=2).view(1, n, 1)
+    which = int(torch.max(pred_c.view(1, n), 1)[1][0])
+    my_r = q[0][which].numpy()
+    my_t = (cloud.view(n, 1, 3) + pred_t.view(n, 1, 3))[which].view(-1).numpy()
+    my_mat = quaternion_matrix(my_r)
+    Rm = torch.from_numpy(my_mat[:3, :3].astype(np.float32)).view(1, 3, 3)
+    T = torch.from_numpy(my_t.astype(np.float32)).view(1, 1, 3)
+    new_cloud = torch.bmm(cloud - T, Rm)
+    my_mat[0:3, 3] = my_t
+    r2 = np.array([0.99, 0.02, -0.03, 0.01]); r2n = r2 / np.linalg.norm(r2)
+    t2 = np.array([0.003, -0.002, 0.001])
+    m2 = quaternion_matrix(r2n); m2[0:3, 3] = t2
+    final = np.dot(my_mat, m2)
+    rot = copy.deepcopy(final); rot[0:3, 3] = 0
+    out.update(which=np.array(which), pose0=np.append(my_r, my_t), new_cloud=npy(new_cloud), r2=r2.astype(np.float32), t2=t2.astype(np.float32),
+               pose1=np.append(quaternion_from_matrix(rot, True), final[0:3, 3]))
+    path = os.path.join(OUT, "customcad_triple.npz")
+    np.savez_compressed(path, **out)
+    print("customcad_triple ->", os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     if "--ply-only" in sys.argv:
         ply_case()
+        sys.exit(0)
+    if "--customcad-only" in sys.argv:
+        customcad_case()
         sys.exit(0)
     # C4 shape: training step (gradient accumulation over 3 samples: two objects share id 12 (symmetric), one is not)
     train_case("c4_train_ycb", cases=[40, 41, 42], objs=[12, 3, 12], num_points=500, num_obj=21, num_pt_mesh=500,
@@ -273,3 +338,4 @@ if __name__ == "__main__":
     loss_only_case("loss_adds_n100_m2600", case=12, num_points=100, num_pt_mesh=2600, obj=19, sym_list=synth.YCB_SYM)
     loss_only_case("loss_add_n1000_m500", case=13, num_points=1000, num_pt_mesh=500, obj=0, sym_list=synth.YCB_SYM)
     ply_case()
+    customcad_case()
