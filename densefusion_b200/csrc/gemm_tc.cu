@@ -565,7 +565,11 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         roff[ps] = R < c.rows_valid ? c.row0 + R : -1;
                     }
                     if (bias && p.bias_crop_stride) {
-                        crop_first = (c.row0 + q * 32) / p.rows_per_crop;
+                        // clamped to the last crop: the warp's 32 rows may lie entirely in the masked tail of the last M tile
+                        // (M = 3000: rows 3040..3071), and its bias vector is loaded before the row masks are looked at -- one
+                        // row past the end of the (crops x N) bias buffer.  That read was the "ConvS2Fn" illegal address of
+                        // round 1: harmless while the allocator happens to map the following bytes, a fault when it does not.
+                        crop_first = min((c.row0 + q * 32) / p.rows_per_crop, (p.M - 1) / p.rows_per_crop);
                         crop_boundary = (crop_first + 1) * p.rows_per_crop;
                     }
                 }

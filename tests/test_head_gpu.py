@@ -204,6 +204,32 @@ def test_gemm_tensor_core_epilogues_match_fp32_kernel(variant):
     assert rel(run("3xtf32", conv5), conv5("fp32")) < 1e-5
 
 
+def test_per_crop_bias_is_not_read_past_its_last_row():
+    """Regression for the round-1 'ConvS2Fn' illegal address: with M = crops * 500 not a multiple of the 256-row tile, the last
+    warp of the last tile lies entirely in the masked tail and used to load the bias vector of crop index `crops` -- one row past
+    the (crops, N) buffer.  The buffer here ends exactly at the end of its own device allocation, so the stray read leaves the
+    mapping (a fault) instead of landing in a neighbouring tensor; the result must also equal the exact-fp32 kernel."""
+    from densefusion_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    for crops in (6, 4, 1):
+        n = 500
+        rows = crops * n
+        big = torch.empty(12 * 1024 * 1024 // 4, device="cuda")                # > 10 MB: a device allocation of its own
+        bias = big[-crops * 1920:].view(crops, 1920)
+        bias.copy_(torch.randn(crops, 1920, generator=g))
+        A = torch.randn(rows, 384, generator=g).cuda()
+        W = ops.SplitWeight((torch.randn(1920, 384, generator=g) / 20).cuda())
+
+        def run(prec):
+            C = torch.empty(rows, 1920, device="cuda")
+            ops.gemm(A, W, bias, C, M=rows, N=1920, K=384, lda=384, ldw=384, ldc=1920, relu=True, precision=prec,
+                     bias_crop_stride=1920, rows_per_crop=n)
+            torch.cuda.synchronize()
+            return C
+        assert rel(run("hybrid16"), run("fp32")) < 1e-5
+        del big, bias
+
+
 @pytest.mark.parametrize("precision", ["fp32", "3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16w"])
 @pytest.mark.parametrize("n,o,B", [(500, 21, 3), (1000, 13, 2)])
 def test_head_vs_oracle(precision, n, o, B):
