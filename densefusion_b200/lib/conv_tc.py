@@ -6,9 +6,10 @@ and the data gradient run on df_conv_tc -- the implicit-GEMM tcgen05 kernel in t
     y  = conv(x, W)                  weights repacked (Cout, taps*Cin), split every call (they change every step)
     dx = conv(dy, rot180(W)^T)       same kernel, same padding / dilation (exact for stride 1)
     dW = dy^T x_shifted              df_conv_wgrad_tc: one 3xTF32 GEMM whose reduction runs over the zero-padded pixel axis
-Only the three stride-2 layers (and Cin < 64) still go to the library (aten.convolution / convolution_backward).  Activations are channels_last, i.e.
-physically the NHWC layout the kernel wants; all other encoder ops (pooling, resizing, PReLU, log-softmax) are torch ops
-that keep that layout."""
+The three stride-2 layers (conv1 7x7/2, layer2.0.conv1 3x3/2 and its 1x1/2 projection) run as explicit patch matrices on the same
+GEMM kernel (ConvS2Fn).  Forward arithmetic `PRECISION` ("hybrid16"), data gradients `GRAD_PRECISION` ("hybrid": gradients need
+the fp32 exponent range).  Activations are channels_last, i.e. physically the NHWC layout the kernel wants; the remaining
+encoder ops (ReLU, pooling, PReLU, dropout, log-softmax) are torch element-wise ops that keep that layout."""
 from __future__ import annotations
 
 import os
@@ -21,12 +22,12 @@ from .._C import check, lib, ptr, stream
 
 ENABLED = True          # module switch (tests compare against the pure torch path)
 WGRAD_TC = True         # weight gradients on df_conv_wgrad_tc (3xTF32 GEMM over the pixels); False: aten.convolution_backward
-# The three stride-2 layers as explicit patch matrices (ConvS2Fn).  EXPERIMENTAL, off by default (torch / cuDNN serve them).
-# Status: parity-tested against float64 (tests/test_encoder_gpu.py); the encoder's forward + backward with it passes on the
-# default AND on a side stream at every bench crop size under CUDA_LAUNCH_BLOCKING=1 (scripts/s2_probe.py); the data-parallel
-# step's eager warm-up on a side stream nevertheless ends, asynchronously, in an illegal address reported inside layer2 --
-# with or without programmatic dependent launch.  Not root-caused (next: bisect with a synchronisation after every op).
-STRIDE2_TC = os.environ.get("DF_STRIDE2_TC", "0") == "1"
+# The three stride-2 layers as explicit patch matrices (ConvS2Fn): on by default since round 2.  (Round 1 left it off because the
+# graphed step's warm-up faulted with an illegal address whenever it was on; the fault was not in these kernels: the tower-1 GEMM
+# epilogue read its per-crop bias one row past the buffer in the masked tail of the last M tile, and whether that stray read hit
+# unmapped memory depended on the allocation pattern -- fixed in gemm_tc.cu, see tests/test_head_gpu.py::
+# test_per_crop_bias_is_not_read_past_its_last_row.)  DF_STRIDE2_TC=0 puts the three layers back on aten.convolution.
+STRIDE2_TC = os.environ.get("DF_STRIDE2_TC", "1") == "1"
 _S2_ONLY = tuple(int(v) for v in os.environ.get("DF_S2_ONLY", "7,3,1").split(",") if v)     # debug: kernel sizes ConvS2Fn takes
 _S2_SYNC = os.environ.get("DF_S2_SYNC", "0") == "1"                                          # debug: synchronise after every call
 
@@ -38,6 +39,8 @@ def _s2_sync(what):
         except Exception as e:
             raise RuntimeError(f"ConvS2Fn: CUDA error surfaced after {what}") from e
 PRECISION = "hybrid16"
+GRAD_PRECISION = "hybrid"   # data-gradient convolutions: their A operand is a gradient (often < 6e-5 in magnitude, below fp16's
+                            # normal range), so the main term must keep the fp32 exponent -- see training.py
 
 
 def _nhwc(x: torch.Tensor) -> torch.Tensor:
@@ -138,7 +141,8 @@ class ConvTCFn(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             # data gradient = convolution of dy with the 180-degree rotated, in/out-transposed kernel
-            dx = _launch(dy, _pack(weight, True, ctx.mode), None, cin, k * k, ctx.dilation, ctx.mode)
+            gmode = ops.PRECISIONS[GRAD_PRECISION] if ctx.mode >= 4 else ctx.mode
+            dx = _launch(dy, _pack(weight, True, gmode), None, cin, k * k, ctx.dilation, gmode)
         if ctx.needs_input_grad[1] and WGRAD_TC and cin % 64 == 0:
             dw = _wgrad_tc(x, dy, cout, cin, k * k, ctx.dilation)
         elif ctx.needs_input_grad[1]:
@@ -218,7 +222,7 @@ class ConvS2Fn(torch.autograd.Function):
             da = torch.empty(m, kk, device=a.device, dtype=torch.float32)
             wt = ConvS2Fn._matrix(weight).t().contiguous()                      # (K, Cout): dA = dy W
             ops.gemm(dy2, ops.SplitWeight(wt), None, da, M=m, N=kk, K=cout, lda=cout, ldw=cout, ldc=kk, relu=False,
-                     precision=PRECISION, short_runs=True)
+                     precision=GRAD_PRECISION if PRECISION.startswith("hybrid16") else PRECISION, short_runs=True)
             dxn = torch.empty(b, h, w, cin, device=a.device, dtype=torch.float32)
             if k == 3:
                 check(lib.df_enc_col2im_s2(ptr(da), ptr(dxn), b, h, w, cin, stream()), "df_enc_col2im_s2")

@@ -1,6 +1,11 @@
 """Training-mode forward / backward of the dense-fusion head (K1) and the refiner (K2) as autograd Functions over
 the C-ABI kernels -- what `loss.backward()` / `dis.backward()` do in tools/train.py:152-161, without any torch op on
-the activation path.  Exact fp32 (FFMA kernels); the tensor-core path is inference-only in this round.
+the activation path.
+
+Arithmetic: forward GEMMs in `PRECISION` (default "hybrid16": tcgen05, fp32 parity for activation-scale operands), data
+gradients in `GRAD_PRECISION` (default "hybrid": the A operand there is a gradient, routinely 1e-6 .. 1e-9 in magnitude, which
+fp16's exponent range cannot carry -- the TF32 main term of "hybrid" keeps the fp32 exponent), weight gradients as 3xTF32 GEMMs
+over the rows (df_conv_wgrad_tc) or exact fp32; PRECISION = "fp32" selects the exact FFMA kernels everywhere.
 
 Forward keeps every ReLU output (pf, h5, h6, h1, h2, h3): the backward of ReLU only needs `output > 0`, which is
 fused into the data-gradient GEMM epilogue (`relu_mask`).  Weight gradients are split over the rows and reduced in a
@@ -48,6 +53,11 @@ def _w2(p):
 # (exact FFMA).  Weight gradients (reductions over the rows) and everything too small for a 128-row MMA tile are always
 # exact fp32.
 PRECISION = "hybrid16"
+GRAD_PRECISION = "hybrid"       # data-gradient GEMMs (A operand = a gradient): an exponent-safe parity mode, see the module docstring
+
+
+def grad_precision() -> str:
+    return "fp32" if PRECISION == "fp32" else (GRAD_PRECISION if PRECISION.startswith("hybrid16") else PRECISION)
 
 
 # ---- thin kernel wrappers ----------------------------------------------------------------------------------
@@ -84,7 +94,7 @@ def _dgrad(dY, ldy, Wt, ldw, dX, ldx, M, N, K, groups=1, dy_gs=0, w_gs=0, dx_gs=
     if (PRECISION != "fp32" and not accumulate and ops.tc_eligible(M, N, K) and (groups == 1 or (w_gs == N * ldw and dx_gs == N))
             and Wt.is_contiguous()):
         # tensor-core data gradient; the ReLU mask of the layer below is applied by a separate element-wise pass
-        ops.gemm(dY, ops.SplitWeight(Wt), None, dX, M=M, N=N, K=K, lda=ldy, ldw=ldw, ldc=ldx, relu=False, precision=PRECISION,
+        ops.gemm(dY, ops.SplitWeight(Wt), None, dX, M=M, N=N, K=K, lda=ldy, ldw=ldw, ldc=ldx, relu=False, precision=grad_precision(),
                  groups=groups, a_gs=dy_gs, w_gs=w_gs, c_gs=dx_gs, short_runs=True)
         if mask is not None:
             _mask_inplace(dX, mask, ldx, N * groups, M)

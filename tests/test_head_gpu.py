@@ -62,7 +62,8 @@ def test_gemm_tensor_core_variants(variant, precision):
 
 
 def test_gemm_tensor_core_identity_layout():
-    """A = structured, W = identity: any layout / swizzle / lane mix-up shows as a permutation."""
+    """A = structured, W = identity: any layout / swizzle / lane mix-up shows as a permutation (errors of order one); the values
+    themselves only differ by the accumulator-truncation compensation (a factor 1 + O(1e-6))."""
     from densefusion_b200 import ops
     M, K = 256, 128
     x = (torch.arange(M * K, dtype=torch.float32).view(M, K) % 4093) / 64.0
@@ -74,7 +75,8 @@ def test_gemm_tensor_core_identity_layout():
             torch.cuda.synchronize()
         finally:
             ops.TC_VARIANT = 0
-        assert torch.equal(y.cpu(), x), f"variant {variant}: first bad index {(y.cpu() != x).nonzero()[:4].tolist()}"
+        bad = ((y.cpu() - x).abs() > 2e-6 * x.abs() + 1e-9).nonzero()
+        assert bad.numel() == 0, f"variant {variant}: first bad index {bad[:4].tolist()}"
 
 
 @pytest.mark.parametrize("M,N,K,groups", [(1000, 512, 384, 1), (64000 // 8, 1920, 384, 1), (3000, 256, 640, 3), (515, 128, 256, 3),

@@ -350,3 +350,36 @@ def test_conv_wgrad_tc_vs_float64(B, H, W, Cin, Cout, taps, dil):
     err = rel(got, w.grad)
     print(f"wgrad_tc {taps}tap dil{dil} {Cin}->{Cout} {B}x{H}x{W}: {err:.3e}")
     assert err < 1e-5
+
+
+@pytest.mark.parametrize("scale", [1.0, 1e-6, 1e-9])
+def test_data_gradient_gemms_keep_parity_for_tiny_gradients(scale):
+    """The A operand of a data-gradient GEMM / convolution is a gradient: dh6 = dg / num_points and the encoder's gradients sit
+    at 1e-6 .. 1e-9, far below fp16's normal range (6.1e-5), where the fp16 main term of "hybrid16" would leave only the 8
+    bits of the bf16 remainder.  training._dgrad and ConvTCFn.backward therefore run in the exponent-safe "hybrid" mode:
+    relative error against float64 stays at the fp32-parity level whatever the gradient's scale."""
+    import torch.nn.functional as F
+    from densefusion_b200 import training
+    from densefusion_b200.lib import conv_tc
+    g = torch.Generator().manual_seed(21)
+    rows, N, K = 3000, 512, 1024                       # dX (rows, N) = dY (rows, K) . Wt (N, K)^T
+    dY = (torch.randn(rows, K, generator=g) * scale)
+    Wt = torch.randn(N, K, generator=g) / K ** 0.5
+    dX = torch.empty(rows, N, device="cuda")
+    training._dgrad(dY.cuda(), K, Wt.cuda(), K, dX, N, rows, N, K)
+    want = dY.double() @ Wt.double().t()
+    err = rel(dX, want)
+    print(f"_dgrad at gradient scale {scale:g}: {err:.3e}")
+    assert err < 1e-5
+    # data gradient of a 3x3 convolution through ConvTCFn.backward
+    x = torch.randn(2, 64, 20, 20, generator=g).cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    w = (torch.randn(128, 64, 3, 3, generator=g) / 24).cuda().requires_grad_(True)
+    gy = (torch.randn(2, 128, 20, 20, generator=g) * scale)
+    y = conv_tc.ConvTCFn.apply(x, w, None, 1)
+    y.backward(gy.cuda())
+    x64 = x.detach().double().cpu().requires_grad_(True)
+    w64 = w.detach().double().cpu().requires_grad_(True)
+    F.conv2d(x64, w64, padding=1).backward(gy.double())
+    ex, ew = rel(x.grad, x64.grad), rel(w.grad, w64.grad)
+    print(f"ConvTCFn backward at gradient scale {scale:g}: dx {ex:.3e} dw {ew:.3e}")
+    assert ex < 1e-5 and ew < 1e-5
