@@ -50,6 +50,24 @@ def test_auc_matches_matlab_transcription():
     assert E.auc(np.full(10, 0.5)) == 0.0                       # everything beyond 10 cm
 
 
+def test_auc_hand_computed_vectors():
+    """VOCap (replace_ycb_toolbox/plot_accuracy_keyframe.m:150-170) worked by hand, independent of any transcription:
+
+    d = [0.02 0.04 0.04 0.06 0.2], max_distance 0.1 -> 0.2 becomes inf; accuracy = [.2 .4 .6 .8 1]; finite part:
+      mrec = [0 .02 .04 .04 .06 .1], mpre = [0 .2 .4 .6 .8 .8] (already monotone);
+      steps where mrec changes: .02*.2 + .02*.4 + (.04->.04: none) + .02*.8 + .04*.8 = .004 + .008 + .016 + .032 = .06; x10 = 0.6
+    d = [0.05]:            mrec = [0 .05 .1], mpre = [0 1 1] -> .05*1 + .05*1 = .1 -> 1.0
+    d = [0.03 0.03 0.5 0.5]: accuracy = [.25 .5 .75 1], finite mrec = [0 .03 .03 .1], mpre = [0 .25 .5 .5]
+                           -> .03*.25 + .07*.5 = .0075 + .035 = .0425 -> 0.425
+    d = [0.1 0.1]:         0.1 is not > max_distance: mrec = [0 .1 .1 .1], mpre = [0 .5 1 1] -> .1*.5 = .05 -> 0.5"""
+    from densefusion_b200 import evaluation as E
+    assert E.auc([0.02, 0.04, 0.04, 0.06, 0.2]) == pytest.approx(0.6, abs=1e-12)
+    assert E.auc([0.06, 0.2, 0.04, 0.02, 0.04]) == pytest.approx(0.6, abs=1e-12)      # order of the inputs is irrelevant
+    assert E.auc([0.05]) == pytest.approx(1.0, abs=1e-12)
+    assert E.auc([0.03, 0.03, 0.5, 0.5]) == pytest.approx(0.425, abs=1e-12)
+    assert E.auc([0.1, 0.1]) == pytest.approx(0.5, abs=1e-12)
+
+
 @pytest.mark.gpu
 def test_pose_distances_on_reference_point_clouds():
     """The root .ply pair of the reference tree (tools/eval_cad.py:130-136 output): ADD 0.0168566, ADD-S 0.0092865

@@ -137,3 +137,40 @@ def test_loss_is_run_to_run_deterministic():
         outs.append((float(st.loss[0]), float(st.dis_sel[0]), st.new_points.clone()))
     assert outs[0][0] == outs[1][0] == outs[2][0] and outs[0][1] == outs[1][1]
     assert torch.equal(outs[0][2], outs[2][2])
+
+
+def test_real_geometry_customcad_triple_vs_reference():
+    """Real geometry from the reference tree (datasets/customCAD/{depth_projected,model,target}.ply: observed cloud, CAD model,
+    model under the ground-truth pose).  Golden values come from the reference's OWN Loss / Loss_refine / transformations
+    (tests/golden/make_golden.py::customcad_case): K3 (ADD and, kNN-based, ADD-S) with gradients, K4 through the symmetric
+    branch, and K5 (selection, re-expression of the cloud, pose composition)."""
+    from densefusion_b200 import ops
+    from densefusion_b200.lib.loss import Loss
+    from densefusion_b200.lib.loss_refiner import Loss_refine
+    g = golden("customcad_triple")
+    cloud, model, target = [torch.from_numpy(g[k]).cuda() for k in ("cloud", "model", "target")]
+    n, m = cloud.shape[1], model.shape[1]
+    sym = [int(v) for v in g["sym_list"]]
+    for tag, obj in (("add", 3), ("adds", 5)):
+        idx = torch.tensor([[obj]], device="cuda")
+        pr, pt, pc = [torch.from_numpy(g[k]).cuda().requires_grad_(True) for k in ("pred_r", "pred_t", "pred_c")]
+        loss, dis, npts, ntgt = Loss(m, sym)(pr, pt, pc, target, model, idx, cloud, float(g["w"]), False)
+        loss.backward()
+        assert rel(loss, g[f"{tag}_loss"]) < TOL and rel(dis, g[f"{tag}_dis"]) < TOL
+        assert rel(npts, g[f"{tag}_new_points"]) < TOL and rel(ntgt, g[f"{tag}_new_target"]) < TOL
+        assert rel(pr.grad, g[f"{tag}_g_r"]) < 1e-3 and rel(pt.grad, g[f"{tag}_g_t"]) < 1e-3 and rel(pc.grad, g[f"{tag}_g_c"]) < 1e-3
+        r1 = (torch.tensor([1.0, 0.01, -0.02, 0.015]) * 1.3).view(1, 4).cuda().requires_grad_(True)
+        t1 = torch.tensor([[0.002, -0.001, 0.003]], device="cuda", requires_grad=True)
+        dis_r, np_r, nt_r = Loss_refine(m, sym)(r1, t1, ntgt, model, idx, npts)
+        dis_r.backward()
+        assert rel(dis_r, g[f"{tag}_ref_dis"]) < TOL
+        assert rel(np_r, g[f"{tag}_ref_new_points"]) < TOL and rel(nt_r, g[f"{tag}_ref_new_target"]) < TOL
+        assert rel(r1.grad, g[f"{tag}_ref_g_r"]) < 1e-3 and rel(t1.grad, g[f"{tag}_ref_g_t"]) < 1e-3
+    # K5: confidence argmax + pose, re-expressed cloud, one composition (tools/eval_ycb.py:193-229 on the reference's functions)
+    pr, pt, pc = [torch.from_numpy(g[k]).cuda() for k in ("pred_r", "pred_t", "pred_c")]
+    pose, which = ops.select_pose(pr, pt, pc, cloud)
+    assert int(which[0]) == int(g["which"])
+    assert np.allclose(pose[0].cpu().numpy(), g["pose0"].astype(np.float64), rtol=0, atol=1e-6)
+    assert rel(ops.cloud_transform(cloud, pose), g["new_cloud"]) < 1e-5
+    ops.pose_compose_(pose, torch.from_numpy(g["r2"]).view(1, 4).cuda(), torch.from_numpy(g["t2"]).view(1, 3).cuda())
+    assert np.allclose(pose[0].cpu().numpy(), g["pose1"], rtol=0, atol=2e-6), (pose[0].cpu().numpy(), g["pose1"])

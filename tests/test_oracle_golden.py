@@ -160,3 +160,24 @@ def test_loss_only_vs_reference(name):
     assert rel(dis_r, g["ref_dis"]) < 1e-5
     assert rel(np_r, g["ref_new_points"]) < 1e-5 and rel(nt_r, g["ref_new_target"]) < 1e-5
     assert rel(r1.grad, g["ref_g_r"]) < 1e-4 and rel(t1.grad, g["ref_g_t"]) < 1e-4
+
+
+def test_oracle_on_real_geometry_customcad_triple():
+    """The oracle against the reference's own Loss / Loss_refine / transformations on the real-geometry triple of the reference
+    tree (datasets/customCAD/*.ply, golden generated by tests/golden/make_golden.py::customcad_case)."""
+    g = golden("customcad_triple")
+    cloud, model, target = [torch.from_numpy(g[k]) for k in ("cloud", "model", "target")]
+    pr, pt, pc = [torch.from_numpy(g[k]) for k in ("pred_r", "pred_t", "pred_c")]
+    m = model.shape[1]
+    sym = [int(v) for v in g["sym_list"]]
+    for tag, obj in (("add", 3), ("adds", 5)):
+        idx = torch.tensor([[obj]])
+        loss, dis, npts, ntgt = O.loss(pr, pt, pc, target, model, idx, cloud, float(g["w"]), False, m, sym)
+        assert rel(loss, g[f"{tag}_loss"]) < 1e-6 and rel(dis, g[f"{tag}_dis"]) < 1e-6
+        assert rel(npts, g[f"{tag}_new_points"]) < 1e-6 and rel(ntgt, g[f"{tag}_new_target"]) < 1e-6
+        r1 = (torch.tensor([1.0, 0.01, -0.02, 0.015]) * 1.3).view(1, 4)
+        t1 = torch.tensor([[0.002, -0.001, 0.003]])
+        dis_r, np_r, nt_r = O.loss_refine(r1, t1, ntgt, model, idx, npts, m, sym)
+        assert rel(dis_r, g[f"{tag}_ref_dis"]) < 1e-6 and rel(np_r, g[f"{tag}_ref_new_points"]) < 1e-6
+    my_r, my_t, which = O.select_pose(pr, pt, pc, cloud)
+    assert which == int(g["which"]) and np.allclose(np.append(my_r, my_t), g["pose0"], atol=1e-7)
