@@ -7,7 +7,7 @@ import bench
 from densefusion_b200.pipeline import PoseEstimator
 
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-precision = sys.argv[2] if len(sys.argv) > 2 else "hybrid"
+precision = sys.argv[2] if len(sys.argv) > 2 else "hybrid16"
 dev = torch.device("cuda", 0)
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
