@@ -235,13 +235,24 @@ INGEST_B_PER_CLK_SM = 30.9          # measured: profiles/r2_l2_ingest_probe.json
 
 
 def measured_peaks(dev):
-    """Denominators measured live on this GPU: cuBLAS TF32 (8192^3, best of 10) and an FFMA-only kernel (df_probe_ffma)."""
+    """Denominators measured live on this GPU: an FFMA-only kernel (df_probe_ffma) and cuBLAS TF32 (8192^3), each the best
+    of 10 short runs after a pause -- both are burst figures (like MEASURED_PEAKS.json's bf16_tflops): a kernel timed right
+    after seconds of tensor-core load sees a power-capped clock and would understate the peak."""
     from densefusion_b200._C import lib, ptr
     out = {}
+    sink = torch.zeros(4, device=dev)
+    flops = [0]
+
+    def probe():
+        flops[0] = int(lib.df_probe_ffma(ptr(sink), 148 * 16, 4096, torch.cuda.current_stream().cuda_stream))
+    time.sleep(1.0)
+    ms = min(time_kernel_ms(probe, iters=1, warm=1) for _ in range(10))
+    out["ffma_tflops"] = flops[0] / (ms * 1e-3) / 1e12 if flops[0] > 0 else None
     try:
         a = torch.randn(8192, 8192, device=dev)
         b = torch.randn(8192, 8192, device=dev)
         torch.backends.cuda.matmul.allow_tf32 = True
+        time.sleep(1.0)
         best = min(time_kernel_ms(lambda: torch.matmul(a, b), iters=1, warm=1) for _ in range(10))
         out["cublas_tf32_tflops"] = 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
         del a, b
@@ -249,13 +260,6 @@ def measured_peaks(dev):
         out["cublas_tf32_tflops"] = None
     finally:
         torch.backends.cuda.matmul.allow_tf32 = False
-    sink = torch.zeros(4, device=dev)
-    flops = [0]
-
-    def probe():
-        flops[0] = int(lib.df_probe_ffma(ptr(sink), 148 * 16, 4096, torch.cuda.current_stream().cuda_stream))
-    ms = min(time_kernel_ms(probe, iters=3, warm=1) for _ in range(3))
-    out["ffma_tflops"] = flops[0] / (ms * 1e-3) / 1e12 if flops[0] > 0 else None
     return out
 
 
