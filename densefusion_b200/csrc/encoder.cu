@@ -50,38 +50,6 @@ im2col_conv1_kernel(const float* __restrict__ img, float* __restrict__ A, int B,
     }
 }
 
-// The same patch matrix through a shared-memory transpose.  In im2col_conv1_kernel the 32 lanes of a warp hold 32 different k of
-// ONE pixel, i.e. 3 channels x 7 rows of the image: ~21 cache lines per load instruction, and the kernel is bound by L1
-// wavefronts (0.41 ms per pose step for 0.58 GB written).  Here a CTA owns 32 consecutive output pixels (row-major) of one image: for every
-// k the lanes read 32 neighbouring pixels (stride-2 floats: 2-3 lines per instruction) into tile[k][pixel], then the tile is
-// written out along k (128 contiguous bytes per warp store).  tile rows are 33 floats: conflict-free both ways.
-__global__ void __launch_bounds__(256)
-im2col_conv1_tile_kernel(const float* __restrict__ img, float* __restrict__ A, int H, int W, int Ho, int Wo, int ldk)
-{
-    __shared__ float tile[192][33];
-    const int q0 = blockIdx.x * 32, b = blockIdx.y;              // 32 consecutive output pixels of the image, row-major
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float* base = img + (size_t)b * 3 * H * W;
-    const int q = q0 + lane, yo = q / Wo, xo = q - yo * Wo;
-    const bool live = q < Ho * Wo;
-    for (int k = warp; k < ldk; k += 8) {
-        float v = 0.0f;
-        if (k < 147 && live) {
-            const int c = k / 49, r = k - c * 49, ky = r / 7, kx = r - ky * 7;
-            const int yy = yo * 2 - 3 + ky, xx = xo * 2 - 3 + kx;
-            if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(base + ((size_t)c * H + yy) * W + xx);
-        }
-        tile[k][lane] = v;
-    }
-    __syncthreads();
-    const int npix = min(32, Ho * Wo - q0);
-    float* out = A + ((size_t)b * Ho * Wo + q0) * ldk;
-    for (int i = threadIdx.x; i < npix * ldk; i += 256) {
-        const int p = i / ldk, k = i - p * ldk;
-        out[i] = tile[k][p];                                       // consecutive threads: consecutive k of one pixel row
-    }
-}
-
 // 3x3 / stride 2 / pad 1 max pooling, NHWC, float4 over channels
 __global__ void __launch_bounds__(256)
 maxpool_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C, int Ho, int Wo)
@@ -521,11 +489,6 @@ extern "C" int df_enc_im2col_conv1(const float* img, float* A, int B, int H, int
     if (!img || !A || B <= 0 || H <= 0 || W <= 0 || ldk < 147 || ldk > 192 || (ldk & 3) || ((uintptr_t)A & 15)) return DF_ERR_ARG;
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     if ((long long)B * Ho * Wo * ldk >= (1LL << 31)) return DF_ERR_ARG;
-    static const int tiled = getenv("DF_IM2COL_TILE") ? atoi(getenv("DF_IM2COL_TILE")) : 1;
-    if (tiled && B <= 65535) {
-        im2col_conv1_tile_kernel<<<dim3((Ho * Wo + 31) / 32, B), 256, 0, (cudaStream_t)stream>>>(img, A, H, W, Ho, Wo, ldk);
-        DF_RETURN_LAST_ERROR();
-    }
     im2col_conv1_kernel<<<grid_for((long long)B * Ho * Wo * (ldk >> 2), 256), 256, 0, (cudaStream_t)stream>>>(img, A, B, H, W, Ho, Wo, ldk);
     DF_RETURN_LAST_ERROR();
 }
