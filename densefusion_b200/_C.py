@@ -33,6 +33,7 @@ SIGNATURES = {
     "df_split_tf32": [_p, _p, _p, _ll, _p],
     "df_pack_bf16_pairs": [_p, _p, _ll, _i, _p],
     "df_pack_f16_pairs": [_p, _p, _p, _ll, _i, _p],
+    "df_pack_f16s": [_p, _p, _p, _ll, _i, _p],
     "df_pack_conv_weight": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
     "df_pack_conv_weight16": [_p, _p, _p, _i, _i, _i, _i, _p],
     "df_conv_wgrad_tc": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],

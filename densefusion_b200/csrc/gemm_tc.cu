@@ -52,6 +52,14 @@ struct TcParams {
     // up coherently from layer to layer.  The epilogue multiplies every accumulation run by 1 + bias_comp * (MMA instructions
     // of the run); bias_comp = the measured mean truncation per instruction for the layer's operand statistics (0: off).
     float bias_comp;
+    // "hybrid16s" (precise == 4): both operands as TWO fp16 planes, x = fp16(x s) + fp16(x s - fp16(x s)) with a power-of-two scale s
+    // that lifts the remainder plane out of fp16's subnormals: the weight planes are packed once with the tensor's own scale
+    // (df_pack_f16s; w_inv_scale = device pointer to 1 / s_w), the activation is scaled in the stagers' registers (a_scale, chosen by
+    // the caller).  The epilogue multiplies every accumulation run by *w_inv_scale / a_scale.
+    // a_scale == 0 (default): every CTA derives the scale from the SAME 4096-element sample of the operand (512 rows x 8 columns,
+    // samp_rows x samp_cols addressable; see "activation scale" in the kernel), so it follows the data without a host round trip.
+    const float* w_inv_scale; float a_scale;
+    long long samp_rows; int samp_cols;
     int run_steps;                              // host side only: MMA instructions per accumulation run, 0 = default
     // ---- weight-gradient form (df_conv_wgrad_tc): output column n = tap * wk_rows + ci multiplies row ci of the W operand
     // read wk_shift[tap] elements further along k (a 3x3 tap is an offset in the zero-padded, flattened pixel axis) ----
@@ -95,7 +103,7 @@ using namespace df_tc;
 // scripts/trunc_probe.py: mean signed error of mixed-sign / post-ReLU dot products per MMA instruction of the chain (hybrid16
 // -1.61e-6 over 96 instructions, hybrid -2.31e-6 over 128, 3xtf32 -3.72e-6 over 192).  Effect on the bench configuration
 // (profiles/r2_c8_bias_comp.txt): worst pose error of 32 crops against the oracle 1.03e-4 -> 3.5e-5, rms GEMM error halved.
-constexpr float BIAS_COMP_H16 = 1.6e-8f, BIAS_COMP_HYBRID = 1.8e-8f, BIAS_COMP_3XTF32 = 1.9e-8f;
+constexpr float BIAS_COMP_H16 = 1.6e-8f, BIAS_COMP_HYBRID = 1.8e-8f, BIAS_COMP_3XTF32 = 1.9e-8f, BIAS_COMP_H16S = 1.6e-8f;
 constexpr int Q_THREADS = 18 * 32;
 constexpr int Q_SPLIT_THREADS = 2 * 32;                      // RAW_W: two more warps split the fp32 weight tile on chip
 constexpr int Q_PLANES = 4;                                  // RAW_W: depth of the operand-plane / a_full / mma_done rings
@@ -179,17 +187,22 @@ __device__ __forceinline__ QTile q_decode(const TcParams& p, int t, int m_tiles,
     return c;
 }
 
-template <int CTAS, int A_STAGES, bool RAW_W>
+template <int CTAS, int A_STAGES, bool RAW_W, int A_COLS>
 __global__ void __launch_bounds__(RAW_W ? Q_THREADS + Q_SPLIT_THREADS : Q_THREADS, 1)
 gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_whi,
                  const __grid_constant__ CUtensorMap tm_wlo, const TcParams p, const int bn_cta, const int m_tiles,
                  const int n_tiles, const int total_tiles)
 {
-    // A_STAGES TMEM A stages of 64 columns each at the top of TMEM; the accumulators share what is left below
-    constexpr int TMEM_A0 = 512 - A_STAGES * 64;
+    // A_STAGES TMEM A stages of A_COLS columns each at the top of TMEM (64: [hi | lo] / [fp16 | - | bf16 | bf16 lo]; 32: the two
+    // fp16 planes of hybrid16s, the only arithmetic that instantiation carries); the accumulators share what is left below
+    constexpr bool S16 = A_COLS == 32;
+    constexpr int TMEM_A0 = 512 - A_STAGES * A_COLS;
     constexpr int ACC_STRIDE = TMEM_A0 / 2;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment as an OFFSET from the __shared__ symbol (not a round trip through uintptr_t): the compiler then knows every
+    // pointer derived from `smem` is shared memory and emits LDS / STS instead of generic LD / ST (measured in the round-2 ncu capture:
+    // all 2.9 M tile reads of the stagers and the epilogue were generic loads on the long scoreboard)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* s_epi = reinterpret_cast<float*>(smem + Q_SMEM_STAGES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Q_SMEM_STAGES + Q_SMEM_EPI);
     uint64_t* full = bars;                          // [8]  TMA bytes of this CTA's stage
@@ -212,7 +225,8 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int nkb = p.K / BK;
     const int bnt = bn_cta * CTAS;                  // tile width = accumulator columns
     const uint32_t w_bytes = (uint32_t)bn_cta * BK * 4;
-    const uint32_t stage_bytes = RAW_W ? Q_TILE + w_bytes : Q_TILE + 2 * w_bytes;   // A | W_hi | W_lo (or the bf16 pair tile), all 1024-B aligned
+    // A | W_hi | W_lo (or the bf16 pair tile), all 1024-B aligned; hybrid16s: A | [fp16 hi x32 | fp16 lo x32] rows
+    const uint32_t stage_bytes = (RAW_W || S16) ? Q_TILE + w_bytes : Q_TILE + 2 * w_bytes;
     const uint32_t plane_bytes = w_bytes + w_bytes / 2;            // RAW_W: [fp16(w) | bf16(w)] 128-byte rows, then bf16(w - fp16(w)) 64-byte rows
     const uint32_t Q_STAGES = RAW_W ? min((uint32_t)Q_MAX_STAGES, ((uint32_t)Q_SMEM_STAGES - Q_PLANES * plane_bytes) / stage_bytes)
                                     : min((uint32_t)Q_MAX_STAGES, (uint32_t)Q_SMEM_STAGES / stage_bytes);
@@ -223,6 +237,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         for (int i = 0; i < Q_MAX_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, RAW_W ? 6 : 1); mbar_init(a_full + i, 4 * CTAS); }
         for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 8 * CTAS); }
         for (int i = 0; i < Q_PLANES; ++i) { mbar_init(w_full + i, 2 * CTAS); mbar_init(mma_done + i, 1); }
+        tmem_slot[1] = 0u;                                         // hybrid16s: bit pattern of the sampled activation maximum
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -240,11 +255,43 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
+    // ---- hybrid16s, activation scale: the A operand is split into fp16(a s) + fp16(a s - fp16(a s)).  The second plane is ~2^-12 of the
+    // first: it stays a normal fp16 number while |a s| >= 0.25 and carries an ABSOLUTE error of 2^-25 below, and fp16 saturates at
+    // 65504 -- so s = 2^k is chosen to put the operand's largest entries near 2^5: entries up to ~2000x larger still fit, and the
+    // absolute error is 2^-30 of the largest entry (fp32 itself rounds that entry to 2^-24).  "Largest entry" is estimated from a fixed
+    // sample of 512 rows x 8 columns, read by the 16 stager / epilogue warps of EVERY CTA (same addresses, hence the same scale everywhere
+    // and from run to run; L2 hits after the first CTA) while the TMA producer is already filling the pipeline.
+    float a_sc = 1.0f;
+    if (S16 && warp >= 2) {
+        a_sc = p.a_scale;
+        if (a_sc == 0.0f) {
+            const int t = (int)threadIdx.x - 64;                                  // 0..511
+            const float* row = p.A + (size_t)(((long long)t * p.samp_rows) >> 9) * p.lda;
+            uint32_t m = 0;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int col = ((((t & 7) << 2) + j * (p.samp_cols >> 1)) % p.samp_cols) & ~3;
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + col));
+                const uint32_t b0 = v.x & 0x7fffffffu, b1 = v.y & 0x7fffffffu, b2 = v.z & 0x7fffffffu, b3 = v.w & 0x7fffffffu;
+                if (b0 < 0x7f800000u) m = max(m, b0);
+                if (b1 < 0x7f800000u) m = max(m, b1);
+                if (b2 < 0x7f800000u) m = max(m, b2);
+                if (b3 < 0x7f800000u) m = max(m, b3);
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+            if (lane == 0 && m) atomicMax(tmem_slot + 1, m);
+            asm volatile("bar.sync 2, 512;" ::: "memory");
+            const int e = (int)(tmem_slot[1] >> 23) - 127;                        // floor(log2(sample maximum)); all-zero sample: -127
+            a_sc = e < -100 ? 1.0f : exp2f((float)(5 - e));
+        }
+    }
+
     if (warp == 0) {
         // ------------------------------- TMA producer -------------------------------
         const uint32_t a_bytes = p.conv_taps ? (uint32_t)(p.TW * p.TH * p.TB) * BK * 4 : (uint32_t)Q_TILE;
         // 3xTF32: W_hi + W_lo; hybrid: W_hi + bf16 pair tile; hybrid16: pair tile + a half-width (64 B rows) correction tile
-        const uint32_t bytes = a_bytes + (RAW_W ? w_bytes : p.precise == 3 ? w_bytes + w_bytes / 2 : (p.precise ? 2u : 1u) * w_bytes);
+        const uint32_t bytes = a_bytes + ((RAW_W || S16) ? w_bytes : p.precise == 3 ? w_bytes + w_bytes / 2 : (p.precise ? 2u : 1u) * w_bytes);
         const int cblocks = p.conv_taps ? p.K / (BK * p.conv_taps) : 1;        // 32-channel blocks per tap
         uint32_t it = 0;
         for (int t = cid; t < total_tiles; t += ncl) {
@@ -282,9 +329,9 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     }
                     // first weight tile: 32 fp32 per row (TF32 hi part), or, hybrid16, [fp16(W) x32 | bf16(W) x32] = 64 halves per row
                     // (RAW_W: the fp32 weights themselves, 32 per row)
-                    tma_load_2d(&tm_whi, dst + Q_TILE, full + s, kb * (!RAW_W && p.precise == 3 ? 2 * BK : BK) + wk0, wrow);
+                    tma_load_2d(&tm_whi, dst + Q_TILE, full + s, kb * (!RAW_W && p.precise >= 3 ? 2 * BK : BK) + wk0, wrow);
                     // second weight tile: W_lo (fp32), or [bf16(W) x32 | bf16(W_lo) x32] (hybrid), or bf16(W_lo) x32 in 64-byte rows (hybrid16)
-                    if (!RAW_W && p.precise) tma_load_2d(&tm_wlo, dst + Q_TILE + w_bytes, full + s, kb * (p.precise == 2 ? 2 * BK : BK) + wk0, wrow);
+                    if (!RAW_W && !S16 && p.precise) tma_load_2d(&tm_wlo, dst + Q_TILE + w_bytes, full + s, kb * (p.precise == 2 ? 2 * BK : BK) + wk0, wrow);
                 }
                 if (++cb == cblocks) { cb = 0; tap_list >>= 4; }
                 __syncwarp();
@@ -318,8 +365,19 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         const uint32_t w_hi = RAW_W ? smem_u32(planes + (size_t)s * plane_bytes)
                                                     : smem_u32(smem + (size_t)s * stage_bytes + Q_TILE);
                         const uint64_t bhi0 = sw128_desc(w_hi), blo0 = sw128_desc(w_hi + w_bytes);
-                        const uint32_t a0 = tmem_base + TMEM_A0 + (it % A_STAGES) * 2 * BK;
-                        if (p.precise == 3) {
+                        const uint32_t a0 = tmem_base + TMEM_A0 + (it % A_STAGES) * A_COLS;
+                        if (S16) {
+                            // hybrid16s: every term on fp16 operands.  TMEM A stage: [0,16) fp16(a) pairs | [16,32) fp16(a - fp16(a));
+                            // weight tile rows: 64 B of fp16(w) then 64 B of fp16(w - fp16(w)) (descriptor +4 = +64 B).
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const uint64_t b_h = bhi0 + (uint64_t)(j * 2), b_l = bhi0 + (uint64_t)(4 + j * 2);
+                                const uint32_t acc_on = (kb != kb0) || (j != 0);
+                                umma_ts_bf16_pair(acc, a0 + j * 8, b_h, idesc_h, acc_on);
+                                umma_ts_bf16_pair(acc, a0 + 16 + j * 8, b_h, idesc_h, 1u);
+                                umma_ts_bf16_pair(acc, a0 + j * 8, b_l, idesc_h, 1u);
+                            }
+                        } else if (p.precise == 3) {
                             // hybrid16: the main term on fp16 operands (11 significant bits like TF32, K = 16 per instruction:
                             // half the tensor time), the two correction terms on bf16 as in the hybrid mode -- 2 + 4
                             // instructions per k-block.  TMEM A stage: [0,16) fp16(a) pairs | [32,48) bf16(a) | [48,64)
@@ -354,7 +412,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             }
                         }
                         }
-                        if (p.precise == 2) {
+                        if (!S16 && p.precise == 2) {
                             // hybrid: the two correction terms are ~2^-11 of the main one, so bf16 operands (K = 16 per
                             // instruction, twice the TF32 rate) keep them to 2^-20 of the result: 4 + 4 instructions per
                             // k-block instead of 12.  TMEM A stage: [0,32) tf32 hi | [32,48) bf16(a) pairs | [48,64) bf16(a_lo);
@@ -470,7 +528,18 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 const uint4 v = *reinterpret_cast<const uint4*>(arow + ((c ^ sw) << 4));
                 hi[c * 4 + 0] = v.x; hi[c * 4 + 1] = v.y; hi[c * 4 + 2] = v.z; hi[c * 4 + 3] = v.w;
             }
-            if (p.precise == 3) {
+            if (S16) {
+                const float sa = a_sc;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float x0 = __uint_as_float(hi[2 * j]) * sa, x1 = __uint_as_float(hi[2 * j + 1]) * sa;
+                    const uint32_t h = pack_f16x2_sat(x0, x1);
+                    float f0, f1;
+                    unpack_f16x2(h, f0, f1);
+                    second[j] = h;
+                    second[16 + j] = pack_f16x2_sat(x0 - f0, x1 - f1);
+                }
+            } else if (p.precise == 3) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float x0 = __uint_as_float(hi[2 * j]), x1 = __uint_as_float(hi[2 * j + 1]);
@@ -511,9 +580,12 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 mbar_wait(empty + prev % Q_STAGES, (prev / Q_STAGES) & 1);
             }
             tc_fence_after();
-            const uint32_t ta = tmem_base + lane_base + TMEM_A0 + (it % A_STAGES) * 2 * BK;
-            tmem_st32(ta, hi);
-            if (p.precise) tmem_st32(ta + BK, second);
+            const uint32_t ta = tmem_base + lane_base + TMEM_A0 + (it % A_STAGES) * A_COLS;
+            if (S16) tmem_st32(ta, second);
+            else {
+                tmem_st32(ta, hi);
+                if (p.precise) tmem_st32(ta + BK, second);
+            }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -581,9 +653,10 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if (p.bias_comp != 0.0f) {
                 const int nkb_t = p.conv_taps == 9 ? __popc(c.taps) * (p.K / (BK * 9)) : nkb;
                 const int n_kb = min(nkb_t, (kc + 1) * p.kbc) - kc * p.kbc;
-                const int per_kb = p.precise == 1 ? 12 : (p.precise == 2 ? 8 : (p.precise == 3 ? 6 : 4));
+                const int per_kb = p.precise == 1 ? 12 : (p.precise == 2 ? 8 : (p.precise >= 3 ? 6 : 4));
                 run_scale = 1.0f + p.bias_comp * (float)(n_kb * per_kb);
             }
+            if (S16) run_scale *= __ldg(p.w_inv_scale) / a_sc;            // (powers of two: exact)
             mbar_wait(acc_full + ab, (ti / ACC_BUFS) & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -768,10 +841,13 @@ bool make_map_nhwc(CUtensorMap* map, const float* base, int B, int H, int W, int
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int CTAS, int A_STAGES, bool RAW_W = false>
+template <int CTAS, int A_STAGES, bool RAW_W = false, int A_COLS = 64>
 int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw, int groups, cudaStream_t s)
 {
+    static_assert(A_COLS == 64 || (A_COLS == 32 && CTAS == 2 && !RAW_W), "the 32-column A stage is the CTA-pair hybrid16s form");
     constexpr int THREADS = RAW_W ? Q_THREADS + Q_SPLIT_THREADS : Q_THREADS;
+    constexpr int ACC_STRIDE = (512 - A_STAGES * A_COLS) / 2;
+    if ((A_COLS == 32) != (p_in.precise == 4)) return DF_ERR_ARG;
     TcParams p = p_in;
     {
         static int order = -1;
@@ -783,16 +859,16 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
         // (18 k-blocks of 3xTF32 at 12 per k-block, 27 of hybrid at 8, 36 of hybrid16 at 6).
         // Inference default 216; the training path asks for 108 (precision bits 8..15): the truncation is a BIAS, which the
         // sums over pixels of a weight gradient amplify (layer4.1.conv1 gradient error 9e-4 at 108, 5.9e-3 at 216, measured).
-        {   // DF_TC_BIAS_COMP="h16,hybrid,3xtf32" (per-instruction factors; calibration knob)
-            static float comp[3] = {0.f, 0.f, 0.f};
+        {   // DF_TC_BIAS_COMP="h16,hybrid,3xtf32,h16s" (per-instruction factors; calibration knob)
+            static float comp[4] = {0.f, 0.f, 0.f, 0.f};
             static bool parsed = false;
             if (!parsed) {
                 const char* e = getenv("DF_TC_BIAS_COMP");
-                if (e) sscanf(e, "%f,%f,%f", &comp[0], &comp[1], &comp[2]);
-                else { comp[0] = BIAS_COMP_H16; comp[1] = BIAS_COMP_HYBRID; comp[2] = BIAS_COMP_3XTF32; }
+                comp[0] = BIAS_COMP_H16; comp[1] = BIAS_COMP_HYBRID; comp[2] = BIAS_COMP_3XTF32; comp[3] = BIAS_COMP_H16S;
+                if (e) sscanf(e, "%f,%f,%f,%f", &comp[0], &comp[1], &comp[2], &comp[3]);
                 parsed = true;
             }
-            p.bias_comp = p.precise == 3 ? comp[0] : (p.precise == 2 ? comp[1] : (p.precise == 1 ? comp[2] : 0.0f));
+            p.bias_comp = p.precise == 4 ? comp[3] : p.precise == 3 ? comp[0] : (p.precise == 2 ? comp[1] : (p.precise == 1 ? comp[2] : 0.0f));
         }
         static const int env_steps = getenv("DF_TC_RUN_STEPS") ? atoi(getenv("DF_TC_RUN_STEPS")) : 216;
         const int run_steps = p.run_steps > 0 ? p.run_steps : env_steps;
@@ -812,7 +888,7 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
         cudaGetDevice(&dev);
         cudaError_t e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(gemm_tc_q_kernel<CTAS, A_STAGES, RAW_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_TOTAL);
+        e = cudaFuncSetAttribute(gemm_tc_q_kernel<CTAS, A_STAGES, RAW_W, A_COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_TOTAL);
         if (e != cudaSuccess) return (int)e;
         int n = num_sms / CTAS;
         if (CTAS == 2) {
@@ -823,7 +899,7 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
             at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             q.attrs = at; q.numAttrs = 1;
             int occ = 0;
-            if (cudaOccupancyMaxActiveClusters(&occ, gemm_tc_q_kernel<CTAS, A_STAGES, RAW_W>, &q) == cudaSuccess && occ > 0 && occ < n) n = occ;
+            if (cudaOccupancyMaxActiveClusters(&occ, gemm_tc_q_kernel<CTAS, A_STAGES, RAW_W, A_COLS>, &q) == cudaSuccess && occ > 0 && occ < n) n = occ;
             (void)cudaGetLastError();
         }
         max_clusters = n;
@@ -851,7 +927,7 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
             // pose step +2.7%, profiles/r2_c4_ab_wide.jsonl; DF_TC_WIDE_KB overrides the threshold, 0 = never)
             static const int wide_kb = getenv("DF_TC_WIDE_KB") ? atoi(getenv("DF_TC_WIDE_KB")) : 32;
             if (w == 256 && !p.pool_partial && !(wide_kb > 0 && p.K / BK >= wide_kb)) continue;
-            if (w == 192 && A_STAGES != 2) continue;
+            if (w == 192 && ACC_STRIDE < 192) continue;
             if (w == 64 && p.N > 64) continue;                     // narrow layers only (64-channel decoder stages)
             if (p.N % w != 0 && (groups > 1 || w == 256)) continue;
             const long long tiles = (long long)m_tiles * ((p.N + w - 1) / w) * groups;
@@ -875,6 +951,10 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
         if (p.precise != 3) return DF_ERR_UNSUPPORTED;
         if (!make_map(&mhi, W_hi, wrows, p.K, ldw, bn_cta)) return DF_ERR_UNSUPPORTED;
         mlo = mhi;
+    } else if (p.precise == 4) {                                   // hybrid16s: one packed tensor, [fp16 hi x32 | fp16 lo x32] per row and k-block
+        if (ldw != p.K || !p.w_inv_scale) return DF_ERR_UNSUPPORTED;
+        if (!make_map_bf16_pairs(&mhi, W_hi, wrows, p.K, bn_cta)) return DF_ERR_UNSUPPORTED;
+        mlo = mhi;
     } else if (p.precise == 3) {                                   // hybrid16: both weight operands are packed 16-bit pair tensors
         if (ldw != p.K) return DF_ERR_UNSUPPORTED;
         if (!make_map_bf16_pairs(&mhi, W_hi, wrows, p.K, bn_cta) || !make_map_bf16_rows64(&mlo, W_lo, wrows, p.K, bn_cta))
@@ -886,6 +966,8 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
             if (!make_map_bf16_pairs(&mlo, W_lo, wrows, p.K, bn_cta)) return DF_ERR_UNSUPPORTED;
         } else if (!make_map(&mlo, p.precise ? W_lo : W_hi, wrows, p.K, ldw, bn_cta)) return DF_ERR_UNSUPPORTED;
     }
+    p.samp_rows = p.conv_taps ? (long long)p.cB * p.cH * p.cW : p.M;
+    p.samp_cols = p.conv_taps ? p.K / p.conv_taps : (int)a_cols;
     const int n_tiles = (p.N + bnt - 1) / bnt;
     const int total = m_tiles * n_tiles * groups;
     const int clusters = total < max_clusters ? total : max_clusters;
@@ -897,7 +979,7 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = use_pdl() ? 2 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_q_kernel<CTAS, A_STAGES, RAW_W>, ma, mhi, mlo, p, bn_cta, m_tiles, n_tiles, total);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_q_kernel<CTAS, A_STAGES, RAW_W, A_COLS>, ma, mhi, mlo, p, bn_cta, m_tiles, n_tiles, total);
     return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -969,6 +1051,45 @@ __global__ void pack_f16_pairs_kernel(const float* __restrict__ w, uint32_t* __r
     t1[row * K + kb * 32 + j] = h;
     t1[row * K + kb * 32 + 16 + j] = pack_bf16x2(x0, x1);
     t2[i] = pack_bf16x2(x0 - f0, x1 - f1);                       // plain row-major bf16 (rows, K)
+}
+
+// hybrid16s mode: absolute maximum of the weight tensor (bit pattern of a non-negative float orders like an unsigned integer) ...
+__global__ void absmax_kernel(const float* __restrict__ w, long long n, uint32_t* __restrict__ out)
+{
+    uint32_t m = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t b = __float_as_uint(w[i]) & 0x7fffffffu;
+        if (b <= 0x7f800000u && b > m) m = b;                      // (NaN is skipped: it poisons its own products only)
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// ... and the planes: with s = the power of two that brings that maximum into [2^14, 2^15), per row and k-block
+// [fp16(w s) x32 | fp16(w s - fp16(w s)) x32].  The remainder of an entry is ~2^-12 of it, so every entry within 2^-16 of the largest
+// keeps a NORMAL fp16 remainder (22 significant bits in all); smaller ones lose bits that are below 2^-39 of the largest entry.
+// scale[0] = 1 / s (what the GEMM epilogue multiplies by), scale[1] = s; scale[2] holds the maximum's bit pattern.
+__global__ void pack_f16s_kernel(const float* __restrict__ w, uint32_t* __restrict__ planes, float* __restrict__ scale,
+                                 long long rows, int K)
+{
+    const uint32_t mb = reinterpret_cast<const uint32_t*>(scale)[2];
+    int e = (int)(mb >> 23) - 127;                                  // floor(log2(max)) (0 / subnormal maximum: -127)
+    if (mb == 0x7f800000u || e < -100) e = 14;                      // infinite or (sub)zero tensor: s = 1
+    const float s = exp2f((float)(14 - e));
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { scale[0] = exp2f((float)(e - 14)); scale[1] = s; }
+    const long long total = rows * (K / 2);
+    if (i >= total) return;
+    const long long row = i / (K / 2);
+    const int kp = (int)(i - row * (K / 2));
+    const int kb = kp / 16, j = kp - kb * 16;
+    const float x0 = w[row * K + kb * 32 + 2 * j] * s, x1 = w[row * K + kb * 32 + 2 * j + 1] * s;
+    const uint32_t h = pack_f16x2_sat(x0, x1);
+    float f0, f1;
+    unpack_f16x2(h, f0, f1);
+    planes[row * K + kb * 32 + j] = h;
+    planes[row * K + kb * 32 + 16 + j] = pack_f16x2_sat(x0 - f0, x1 - f1);
 }
 
 // Convolution weight (Cout, Cin, taps) -> GEMM operand (rows, taps*cols) tap-major, split for the tensor-core modes, in ONE
@@ -1193,6 +1314,20 @@ extern "C" int df_pack_f16_pairs(const float* w, void* t1, void* t2, long long r
     DF_RETURN_LAST_ERROR();
 }
 
+extern "C" int df_pack_f16s(const float* w, void* planes, float* scale, long long rows, int K, void* stream)
+{
+    if (!w || !planes || !scale || rows <= 0 || K <= 0 || K % 32) return DF_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(scale, 0, 4 * sizeof(float), s);
+    if (e != cudaSuccess) return (int)e;
+    const long long n = rows * K;
+    const int blocks = (int)((n + 1023) / 1024 < 1184 ? (n + 1023) / 1024 : 1184);
+    absmax_kernel<<<blocks, 256, 0, s>>>(w, n, reinterpret_cast<uint32_t*>(scale) + 2);
+    const long long total = rows * (K / 2);
+    pack_f16s_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w, (uint32_t*)planes, scale, rows, K);
+    DF_RETURN_LAST_ERROR();
+}
+
 extern "C" int df_split_tf32(const float* x, float* hi, float* lo, long long n, void* stream)
 {
     if (!x || !hi || !lo || n <= 0) return DF_ERR_ARG;
@@ -1207,8 +1342,9 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
 {
     if (!A || !W_hi || (!C && !pool_partial)) return DF_ERR_ARG;
     const int run_units = (precision >> 8) & 0xff;                  // accumulation-run length in units of 12 MMA instructions
+    const int a_byte = (precision >> 16) & 0xff;                    // hybrid16s: 0 = scale sampled by the kernel, else a fixed 2^k
     precision &= 0xff;
-    if (precision < 1 || precision > 5) return DF_ERR_ARG;
+    if (precision < 1 || precision > 6) return DF_ERR_ARG;
     if (precision != 2 && precision != 5 && !W_lo) return DF_ERR_ARG;
     if (M <= 0 || N <= 0 || K <= 0 || groups <= 0) return DF_ERR_ARG;
     if (K % BK || lda % 4 || ldw % 4 || N % 4 || a_group_stride % 4 || bias_group_stride % 4) return DF_ERR_ARG;
@@ -1221,7 +1357,9 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
     TcParams p = {};
     p.A = A; p.lda = lda; p.bias = bias; p.bias_crop_stride = bias_crop_stride;
     p.C = pool_partial ? nullptr : C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.relu = relu;
-    p.precise = precision == 1 ? 1 : (precision == 3 ? 2 : (precision >= 4 ? 3 : 0));     // kernel-side: 0 single TF32, 1 3xTF32, 2 hybrid, 3 hybrid16
+    // kernel-side: 0 single TF32, 1 3xTF32, 2 hybrid, 3 hybrid16, 4 hybrid16s
+    p.precise = precision == 1 ? 1 : (precision == 3 ? 2 : (precision == 6 ? 4 : (precision >= 4 ? 3 : 0)));
+    p.w_inv_scale = precision == 6 ? W_lo : nullptr; p.a_scale = a_byte == 0 ? 0.0f : (a_byte == 0x80 ? 1.0f : exp2f((float)(signed char)a_byte));
     p.run_steps = run_units * 12;
     p.rows_per_crop = rows_per_crop > 0 ? rows_per_crop : M;
     p.a_gs = a_group_stride; p.bias_gs = bias_group_stride; p.c_gs = c_group_stride;
@@ -1236,6 +1374,9 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
     if (precision == 5) {                        // hybrid16 arithmetic, W_hi = the fp32 weights (split on chip): CTA-pair kernel only
         if (variant != 0 && variant != 6) return DF_ERR_UNSUPPORTED;
         rc = launch_q<2, 2, true>(p, W_hi, W_hi, ldw, groups, (cudaStream_t)stream);
+    } else if (precision == 6) {                 // hybrid16s: two fp16 planes per operand, 32-column TMEM A stages: CTA-pair kernel only
+        if (variant != 0 && variant != 6) return DF_ERR_UNSUPPORTED;
+        rc = launch_q<2, 4, false, 32>(p, W_hi, W_hi, ldw, groups, (cudaStream_t)stream);
     } else if (v == 5) rc = launch_q<1, 4>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream);
     else if (v == 6) rc = launch_q<2, 2>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream);
     else if (v == 7) rc = launch_q<2, 4>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream);
@@ -1307,8 +1448,9 @@ extern "C" int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx,
 {
     if (!X || !W_hi || !Y || B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return DF_ERR_ARG;
     const int run_units = (precision >> 8) & 0xff;
+    const int a_byte = (precision >> 16) & 0xff;
     precision &= 0xff;
-    if (precision < 1 || precision > 5) return DF_ERR_ARG;
+    if (precision < 1 || precision > 6) return DF_ERR_ARG;
     if (precision != 2 && precision != 5 && !W_lo) return DF_ERR_ARG;
     if ((taps != 1 && taps != 9) || dilation < 1 || act < 0 || act > 2 || (act == 2 && !prelu)) return DF_ERR_ARG;
     if (Cin % BK || Cout % 4 || ldx % 4 || ldy % 4 || ldx < Cin || ldy < Cout || (residual && (ldr % 4 || ldr < Cout))) return DF_ERR_ARG;
@@ -1320,13 +1462,15 @@ extern "C" int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx,
     TcParams p = {};
     p.A = X; p.lda = ldx; p.bias = bias; p.bias_crop_stride = 0; p.C = Y; p.ldc = ldy;
     p.M = B * H * W; p.N = Cout; p.K = taps * Cin; p.relu = act;
-    p.precise = precision == 1 ? 1 : (precision == 3 ? 2 : (precision >= 4 ? 3 : 0));
+    p.precise = precision == 1 ? 1 : (precision == 3 ? 2 : (precision == 6 ? 4 : (precision >= 4 ? 3 : 0)));
+    p.w_inv_scale = precision == 6 ? W_lo : nullptr; p.a_scale = a_byte == 0 ? 0.0f : (a_byte == 0x80 ? 1.0f : exp2f((float)(signed char)a_byte));
     p.run_steps = run_units * 12;
     p.rows_per_crop = p.M; p.a_gs = 0; p.bias_gs = 0; p.c_gs = 0; p.pool_partial = nullptr; p.tiles_per_crop = 0;
     p.conv_taps = taps; p.conv_dil = dilation; p.cW = W; p.cH = H; p.cB = B;
     p.residual = residual; p.ldr = ldr; p.prelu = prelu;
     conv_patch_plan(p, B, H, W, taps, dilation);
     const int rc = precision == 5 ? launch_q<2, 2, true>(p, W_hi, W_hi, taps * Cin, 1, (cudaStream_t)stream)
+                 : precision == 6 ? launch_q<2, 4, false, 32>(p, W_hi, W_hi, taps * Cin, 1, (cudaStream_t)stream)
                                   : launch_q<2, 2>(p, W_hi, W_lo, taps * Cin, 1, (cudaStream_t)stream);
     if (rc) return rc;
     DF_RETURN_LAST_ERROR();

@@ -167,17 +167,15 @@ class PackedEncoder:
         s = stream()
         check(lib.df_enc_gather_up_patches(ptr(x), ptr(choose), ptr(patches), b, n, h, w, 64, s), "df_enc_gather_up_patches")
         up = self.ups[2]
-        hi, lo = up["w"].operands(mode)
         # the gathered patches as a 1 x rows "image" with 576 channels: a 1-tap convolution = GEMM with the PReLU epilogue
-        check(lib.df_conv_tc(ptr(patches), 1, 1, rows, 576, 576, ptr(hi), ptr(lo), 1, 1, ptr(up["b"]), None, 0, ptr(up["a"]),
-                             2, ptr(act), 64, 64, mode, s), "df_conv_tc")
+        self._conv(patches.view(1, 1, rows, 576), up["w"], act.view(1, 1, rows, 64), taps=1, bias=up["b"], prelu=up["a"], act=2, mode=mode)
         ops.gemm(act, self.final_w, self.final_b, emb_pm_out, M=rows, N=32, K=64, lda=64, ldw=64, ldc=32, relu=False)
         check(lib.df_enc_log_softmax32(ptr(emb_pm_out), rows, s), "df_enc_log_softmax32")
         return emb_pm_out
 
     def _trunk(self, img: torch.Tensor, precision: str, stages: int):
         """Everything up to and including `stages` of the three up-sampling stages.  Returns (activation, workspace, mode)."""
-        if precision not in ("3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16w"):
+        if precision not in ("3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16w", "hybrid16s"):
             raise ValueError("the tensor-core encoder runs in '3xtf32' / 'hybrid' / 'hybrid16' (fp32 parity) or 'tf32'")
         mode = ops.PRECISIONS[precision]
         img = ops.f32c(img)

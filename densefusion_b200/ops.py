@@ -18,7 +18,20 @@ from ._C import check, f32c, i64c, lib, need_cuda, ptr, stream
 # per weight element through the SM's fabric port).  Measured SLOWER (tower-1 0.41 vs 0.30 ms, profiles/r2_c3_gemm_ab.jsonl): the
 # conversion instructions of the extra splitter warps, not the port, then set the pace -- kept as the cross-check of the packed
 # planes and as the record of the experiment, not used by default.
-PRECISIONS = {"fp32": 0, "3xtf32": 1, "tf32": 2, "hybrid": 3, "hybrid16": 4, "hybrid16w": 5}
+# "hybrid16s": every term on fp16 operands, two planes per operand (x = fp16(x s) + fp16(x s - fp16(x s)), power-of-two scales s):
+# 4 instead of 6 bytes per weight element through the SM's fabric port and half the TMEM per A stage.  The weight scale comes from
+# the tensor's own maximum (df_pack_f16s); the activation scale is derived inside the kernel from a 4096-element sample of the operand
+# (gemm_tc.cu, "activation scale"), or fixed per call with `a_log2` (tests).
+PRECISIONS = {"fp32": 0, "3xtf32": 1, "tf32": 2, "hybrid": 3, "hybrid16": 4, "hybrid16w": 5, "hybrid16s": 6}
+
+
+def _prec_code(mode: int, short_runs: bool, a_log2=None) -> int:
+    """`precision` argument of df_gemm_tc / df_conv_tc: mode | run-length flag | hybrid16s activation scale (bits 16..23: 0 = sampled
+    by the kernel, otherwise the signed log2 of a fixed scale, -128 standing for 2^0)."""
+    code = mode | (SHORT_RUNS if short_runs else 0)
+    if mode == 6 and a_log2 is not None:
+        code |= ((int(a_log2) & 0xff) if a_log2 else 0x80) << 16
+    return code
 
 
 def sym_mask(sym_list: Iterable[int]) -> int:
@@ -121,11 +134,11 @@ def loss_backward(pred_r, pred_c, st: LossState, g_loss, g_dis, w: float):
 # ---- K1 / K2 building blocks ------------------------------------------------------------------
 class SplitWeight:
     """A torch (N,K) [or stacked (G,N,K)] weight with its TF32 hi/lo halves for the tensor-core path."""
-    __slots__ = ("w", "hi", "lo", "bf", "h16")
+    __slots__ = ("w", "hi", "lo", "bf", "h16", "s16")
 
     def __init__(self, w: torch.Tensor):
         self.w = f32c(w.detach())
-        self.hi = self.lo = self.bf = self.h16 = None
+        self.hi = self.lo = self.bf = self.h16 = self.s16 = None
 
     def operands(self, mode: int):
         """The two weight operands df_gemm_tc / df_conv_tc expect for a PRECISIONS code (1 3xtf32, 2 tf32, 3 hybrid, 4 hybrid16,
@@ -133,6 +146,8 @@ class SplitWeight:
         if mode == 5:
             need_cuda(self.w)
             return self.w, self.w
+        if mode == 6:
+            return self.planes16s()
         return self.pairs16() if mode == 4 else (self.pairs() if mode == 3 else self.split())
 
     def pairs16(self):
@@ -146,6 +161,19 @@ class SplitWeight:
             check(lib.df_pack_f16_pairs(ptr(self.w), ptr(t1), ptr(t2), rows, K, stream()), "df_pack_f16_pairs")
             self.h16 = (t1, t2)
         return self.h16
+
+    def planes16s(self):
+        """hybrid16s: the packed planes ([fp16(w s) x32 | fp16(w s - fp16(w s)) x32] per row and k-block) and the 4-float scale record
+        (1/s, s, scratch) made by df_pack_f16s on the device (no host round trip: usable under graph capture)."""
+        if self.s16 is None:
+            need_cuda(self.w)
+            K = self.w.shape[-1]
+            rows = self.w.numel() // K
+            planes = torch.empty(rows, K, device=self.w.device, dtype=torch.float32)
+            scale = torch.empty(4, device=self.w.device, dtype=torch.float32)
+            check(lib.df_pack_f16s(ptr(self.w), ptr(planes), ptr(scale), rows, K, stream()), "df_pack_f16s")
+            self.s16 = (planes, scale)
+        return self.s16
 
     def pairs(self):
         """hi (TF32-exact fp32) and the packed bf16 pair tensor of the hybrid mode (same byte size as the weight)."""
@@ -179,7 +207,7 @@ SHORT_RUNS = 9 << 8     # precision flag of df_gemm_tc / df_conv_tc: accumulatio
 
 
 def gemm(A, W, bias, C, *, M, N, K, lda, ldw, ldc, relu, precision="fp32", bias_crop_stride=0, rows_per_crop=0,
-         groups=1, a_gs=0, w_gs=0, bias_gs=0, c_gs=0, pool_partial=None, short_runs=False):
+         groups=1, a_gs=0, w_gs=0, bias_gs=0, c_gs=0, pool_partial=None, short_runs=False, a_log2=None):
     """Raw strided GEMM launch on pre-allocated buffers (see df_gemm_fp32 / df_gemm_tc in the header).
     W: tensor or SplitWeight."""
     mode = PRECISIONS[precision]
@@ -188,7 +216,7 @@ def gemm(A, W, bias, C, *, M, N, K, lda, ldw, ldc, relu, precision="fp32", bias_
         hi, lo = sw.operands(mode)
         st = lib.df_gemm_tc(ptr(A), lda, ptr(hi), ptr(lo), ldw, ptr(bias), bias_crop_stride, ptr(C), ldc, M, N, K,
                             1 if relu else 0, rows_per_crop, groups, a_gs, bias_gs, c_gs, ptr(pool_partial),
-                            mode | (SHORT_RUNS if short_runs else 0), TC_VARIANT, stream())
+                            _prec_code(mode, short_runs, a_log2), TC_VARIANT, stream())
         if st != -2:                 # -2: a shape the TMA boxes cannot address -> the exact-fp32 kernel below, like tc_eligible
             check(st, "df_gemm_tc")
             return

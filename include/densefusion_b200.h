@@ -109,6 +109,15 @@ int df_pack_bf16_pairs(const float* w, void* out, long long rows, int K, void* s
  * stays 2^-20 per product.  W_hi / W_lo then point to the two packed tensors made by df_pack_f16_pairs: per row and k-block
  * t1 = [fp16(w) x32 | bf16(w) x32] (the byte size of the weight), t2 = bf16(w - fp16(w)) row-major (half of it); needs ldw == K. */
 int df_pack_f16_pairs(const float* w, void* t1, void* t2, long long rows, int K, void* stream);
+/* precision 6 ("hybrid16s", CTA-pair kernel): EVERY term on fp16 operands -- x = fp16(x s) + fp16(x s - fp16(x s)) for both operands,
+ * D += A_hi W_hi + A_lo W_hi + A_hi W_lo, 6 instructions per k-block like precision 4 but only TWO 16-bit planes per operand: 4 instead
+ * of 6 bytes per weight element through the SM's fabric port (what bounds this kernel) and half the TMEM per A stage.
+ * The power-of-two scales s keep the remainder planes out of fp16's subnormals: the weight's is chosen by df_pack_f16s from the tensor's
+ * own maximum (planes = per row and k-block [fp16 hi x32 | fp16 lo x32], the byte size of the weight; scale = 4 floats: 1/s, s, and
+ * scratch), the activation's is passed as log2 in bits 16..23 of `precision` (signed; parity needs the entries that carry the dot
+ * product inside [2^-8, 2^15] after scaling: 22 significant bits above 0.25, an absolute error of 2^-25 below).  W_hi = planes, W_lo = scale;
+ * needs ldw == K. */
+int df_pack_f16s(const float* w, void* planes, float* scale, long long rows, int K, void* stream);
 /* Accumulation runs: long k loops are cut into runs on fresh accumulators, summed in fp32 through C (the tensor core
  * truncates while accumulating; the bias grows with the number of chained instructions).  Default 216 MMA instructions per
  * run; bits 8..15 of `precision` (df_gemm_tc and df_conv_tc) select another length in units of 12 instructions -- the

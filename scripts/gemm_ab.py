@@ -52,6 +52,12 @@ def gemm_case(name, M, N, K, pooled=False, percrop=False, groups=1, n=500):
         res[mode] = (part if pooled else C[0]).clone()
         out[mode] = {"ms": round(ms, 4), "algorithmic_tflops": round(2.0 * M * N * K * groups / ms * 1e-9, 1)}
     eq = {m: bool(torch.equal(res[m], res[modes[0]])) for m in modes[1:]}
+    if not pooled and M * N * groups <= 130_000_000:            # error against float64 (cuBLAS DGEMM on the device)
+        ref = torch.relu(torch.einsum("mgk,gnk->mgn", A[0].double().view(M, groups, K), W.w.double().view(groups, N, K)).reshape(M, -1)
+                         + (bias.double().repeat_interleave(n, 0)[:M] if percrop else bias.double()))
+        for mode in modes:
+            out[mode]["err_vs_f64"] = float((res[mode].double() - ref).abs().max() / ref.abs().max())
+        del ref
     print(json.dumps({"case": name, "shape": f"M={M} N={N} K={K} groups={groups}", **out, "bit_equal_to_first": eq}), flush=True)
 
 

@@ -47,7 +47,7 @@ def test_conv_tc_vs_float64(B, H, W, Cin, Cout, taps, dil, extras):
         want = torch.relu(want)
     elif extras == "prelu":
         want = torch.where(want > 0, want, 0.25 * want)
-    for precision, tol in (("3xtf32", 2e-5), ("hybrid", 2e-5), ("hybrid16", 2e-5), ("tf32", 3e-3)):
+    for precision, tol in (("3xtf32", 2e-5), ("hybrid", 2e-5), ("hybrid16", 2e-5), ("hybrid16s", 2e-5), ("tf32", 3e-3)):
         wide = torch.full((B, H, W, Cout + 64), 7.0, device="cuda")          # output is a channel slice of a wider buffer
         out = wide[..., 32:32 + Cout]
         PackedEncoder._conv(_nhwc(x).cuda(), _pack_conv(w.cuda()), out, taps=taps, dil=dil,
@@ -129,7 +129,7 @@ def test_encoder_helper_kernels_vs_torch():
     assert rel(z, want) < 1e-6
 
 
-@pytest.mark.parametrize("precision,tol", [("3xtf32", 1e-4), ("hybrid", 1e-4), ("hybrid16", 1e-4), ("tf32", 2e-2)])
+@pytest.mark.parametrize("precision,tol", [("3xtf32", 1e-4), ("hybrid", 1e-4), ("hybrid16", 1e-4), ("hybrid16s", 1e-4), ("tf32", 2e-2)])
 @pytest.mark.parametrize("b,hw", [(3, (80, 80)), (2, (120, 160)), (1, (160, 160))])
 def test_encoder_vs_oracle(precision, tol, b, hw):
     from densefusion_b200.encoder import PackedEncoder
@@ -172,7 +172,7 @@ def test_encoder_sparse_tail_equals_dense_gather(b, hw):
     assert err < 1e-5 and err_o < 1e-4
 
 
-@pytest.mark.parametrize("precision", ["3xtf32", "hybrid", "hybrid16"])
+@pytest.mark.parametrize("precision", ["3xtf32", "hybrid", "hybrid16", "hybrid16s"])
 def test_pipeline_with_tensor_core_encoder_vs_oracle(precision):
     """estimate + 2 refine iterations with encoder AND head on the tensor cores (fp32-parity modes) against the oracle's
     eval loop."""

@@ -21,7 +21,7 @@ def _variants(default):
 
 
 # stated bounds per arithmetic mode (max-abs error / max-abs value)
-TOL = {"fp32": 1e-4, "3xtf32": 1e-4, "hybrid": 1e-4, "hybrid16w": 1e-4, "hybrid16": 1e-4, "tf32": 5e-3}
+TOL = {"fp32": 1e-4, "3xtf32": 1e-4, "hybrid": 1e-4, "hybrid16w": 1e-4, "hybrid16": 1e-4, "hybrid16s": 1e-4, "tf32": 5e-3}
 
 
 def _ref_linear(x, w, b, relu):
@@ -40,14 +40,14 @@ def test_gemm_fp32_vs_float64(M, N, K):
 
 
 @pytest.mark.parametrize("variant", _variants([5, 6, 7]))
-@pytest.mark.parametrize("precision", ["3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16w"])
+@pytest.mark.parametrize("precision", ["3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16w", "hybrid16s"])
 def test_gemm_tensor_core_variants(variant, precision):
     """variant 5: persistent kernel, one CTA per tile, A operand by TMA; 6 / 7: CTA pairs (cta_group::2, 256-row tiles) with
     2 / 4 TMEM A stages.  "hybrid16w" (weights split on chip) exists on variant 6, the production kernel."""
     from densefusion_b200 import ops
     g = torch.Generator().manual_seed(variant)
     M, N, K = 1000, 512, 384
-    if precision == "hybrid16w" and variant != 6:
+    if precision in ("hybrid16w", "hybrid16s") and variant != 6:
         pytest.skip("the on-chip weight split exists in the production kernel (variant 6) only")
     x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
     ops.TC_VARIANT = variant
@@ -131,6 +131,82 @@ def test_gemm_parity_modes_operand_range(precision, scale_a, scale_w):
         assert bool(torch.isfinite(y).all()) and (both_out or err < 2e-2)
     else:
         assert err < 1e-5 and err_el < 1e-3
+
+
+def test_pack_f16s_planes_and_scale_bit_exact():
+    """df_pack_f16s against a torch restatement: s = the power of two that brings the tensor's largest entry into [2^14, 2^15),
+    planes = per row and k-block [fp16(w s) x32 | fp16(w s - fp16(w s)) x32], scale record (1/s, s)."""
+    from densefusion_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    for rows, K, mag in ((96, 64, 1.0), (257, 384, 3e-3), (64, 4608, 40.0), (8, 32, 1e-20), (8, 32, 0.0)):
+        w = torch.randn(rows, K, generator=g) * mag
+        w[0, 0] = 0.0
+        planes, scale = ops.SplitWeight(w.cuda()).planes16s()
+        torch.cuda.synchronize()
+        m = float(w.abs().max())
+        e = 14 - (int(torch.tensor(m).log2().floor()) if m > 0 else 14)
+        if m > 0 and int(torch.tensor(m).log2().floor()) < -100:
+            e = 0
+        sc = 2.0 ** e
+        assert float(scale[0]) == 1.0 / sc and float(scale[1]) == sc
+        ws = w * sc
+        hi = ws.half()
+        lo = (ws - hi.float()).half()
+        want = torch.cat([hi.view(rows, K // 32, 32), lo.view(rows, K // 32, 32)], 2).reshape(rows, 2 * K)
+        got = planes.cpu().view(torch.float16).view(rows, 2 * K)
+        assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+        if m > 1e-10:
+            assert 2.0 ** 14 <= m * sc < 2.0 ** 15
+
+
+@pytest.mark.parametrize("relu_input", [False, True])
+@pytest.mark.parametrize("scale_a,scale_w", [(1.0, 1.0), (1e6, 1.0), (1.0, 1e6), (1e-7, 1.0), (1.0, 1e-7), (3e5, 1e-6), (1e-6, 3e5),
+                                             (1e-12, 1e12), (1e-2, 1e-2)])
+def test_hybrid16s_follows_the_operand_scales(relu_input, scale_a, scale_w):
+    """"hybrid16s" carries both operands as two fp16 planes; the power-of-two scales (weights: from the tensor's maximum at pack
+    time; activations: from the kernel's own 4096-element sample) make the arithmetic independent of the operands' magnitude --
+    fp32 parity at every scale where "hybrid16" only reaches it inside fp16's normal range."""
+    from densefusion_b200 import ops
+    from util import rel_elementwise
+    g = torch.Generator().manual_seed(17)
+    M, N, K = 1500, 384, 1024
+    x = torch.randn(M, K, generator=g) * scale_a
+    if relu_input:
+        x = torch.relu(x)
+    w = torch.randn(N, K, generator=g) / K ** 0.5 * scale_w
+    b = torch.randn(N, generator=g) * (scale_a * scale_w)
+    y = ops.linear(x.cuda(), w.cuda(), b.cuda(), relu=False, precision="hybrid16s")
+    want = _ref_linear(x, w, b, False)
+    err, err_el = rel(y, want), rel_elementwise(y, want, floor=1e-2)
+    print(f"hybrid16s scale {scale_a:g} x {scale_w:g} relu_input={relu_input}: max-norm {err:.3e}, element-wise {err_el:.3e}")
+    assert err < 5e-6 and err_el < 1e-3
+
+
+def test_hybrid16s_fixed_activation_scale_and_outliers():
+    """What the sampled scale protects against, shown with FIXED scales (a_log2): an operand far below the scale's sweet spot
+    keeps an absolute error of 2^-25 per entry (graceful: 1e-2-sized activations at scale 1 still reach 1e-5), one far above
+    saturates.  And what the sample cannot see -- a single entry far larger than everything sampled -- stays exact up to
+    ~2000x the sampled maximum (65504 / 2^5)."""
+    from densefusion_b200 import ops
+    g = torch.Generator().manual_seed(23)
+    M, N, K = 1024, 256, 512
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+
+    def err(x, a_log2=None):
+        C = torch.empty(M, N, device="cuda")
+        ops.gemm(x, ops.SplitWeight(w), None, C, M=M, N=N, K=K, lda=K, ldw=K, ldc=N, relu=False, precision="hybrid16s", a_log2=a_log2)
+        ref = x.double() @ w.double().t()
+        return float((C.double() - ref).abs().max() / ref.abs().max())
+
+    x = torch.randn(M, K, generator=g).cuda()
+    assert err(x) < 3e-6 and err(x, a_log2=0) < 3e-6 and err(x, a_log2=5) < 3e-6
+    assert err(x * 1e-2, a_log2=0) < 1e-5                       # 2^-25 absolute on entries of 1e-2
+    assert err(x * 1e-4, a_log2=0) > 1e-5                       # ... and that is where a fixed scale of 1 stops
+    assert err(x * 1e-4) < 3e-6 and err(x * 1e4) < 3e-6         # the sampled scale follows the operand
+    for big, ok in ((1e2, True), (1e3, True), (1.5e3, True)):
+        x2 = x.clone()
+        x2[777, 13] = big
+        assert (err(x2) < 3e-6) == ok, big
 
 
 @pytest.mark.parametrize("variant", _variants([5, 6, 7]))
@@ -232,7 +308,7 @@ def test_per_crop_bias_is_not_read_past_its_last_row():
         del big, bias
 
 
-@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16w"])
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16w", "hybrid16s"])
 @pytest.mark.parametrize("n,o,B", [(500, 21, 3), (1000, 13, 2)])
 def test_head_vs_oracle(precision, n, o, B):
     est, _, est_sd, _ = build_nets(n, o, seed=5)
@@ -257,7 +333,7 @@ def test_head_vs_oracle(precision, n, o, B):
     print(f"head {precision} n={n}: worst rel err {worst:.3e}")
 
 
-@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "hybrid", "hybrid16", "hybrid16w"])
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "hybrid", "hybrid16", "hybrid16w", "hybrid16s"])
 def test_refiner_vs_oracle(precision):
     n, o, B = 500, 21, 4
     _, ref, _, ref_sd = build_nets(n, o, seed=6)

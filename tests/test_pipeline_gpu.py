@@ -102,7 +102,7 @@ def test_batched_buckets_graph_and_oracle():
     assert np.array_equal(out2, poses)
 
 
-@pytest.mark.parametrize("n,precision", [(500, "hybrid16"), (1000, "hybrid16"), (500, "hybrid")])
+@pytest.mark.parametrize("n,precision", [(500, "hybrid16"), (1000, "hybrid16"), (500, "hybrid"), (500, "hybrid16s"), (1000, "hybrid16s")])
 def test_mixed_buckets_graphed_tensor_core_vs_oracle(n, precision):
     """The bench's configuration in small: three crop-size buckets, the default tensor-core arithmetic, chunked head, side
     streams per bucket, CUDA-graph replay -- every pose against the oracle's estimate + 2 refine iterations (<= 1e-4 in the
