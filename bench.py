@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("DF_PRECISION", "hybrid16"), choices=["fp32", "3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16w"])
+    ap.add_argument("--precision", default=os.environ.get("DF_PRECISION", "hybrid16"), choices=["fp32", "3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16s"])
     ap.add_argument("--frames", type=int, default=32, help="frames (of 8 objects) per GPU per step")
     ap.add_argument("--chunk", type=int, default=128, help="crops per head chunk (measured 16: 21.7 ms, 32: 20.7, 64: 20.3, 128: 20.05 per step)")
     ap.add_argument("--no-graph", action="store_true")
@@ -230,7 +230,7 @@ def time_kernel_ms(fn, iters=20, warm=3):
     return e0.elapsed_time(e1) / iters
 
 
-PASSES = {"3xtf32": 3.0, "hybrid": 2.0, "hybrid16": 1.5, "hybrid16w": 1.5, "tf32": 1.0}     # executed TF32-equivalent MMA time per algorithmic flop
+PASSES = {"3xtf32": 3.0, "hybrid": 2.0, "hybrid16": 1.5, "hybrid16s": 1.5, "tf32": 1.0}     # executed TF32-equivalent MMA time per algorithmic flop
 INGEST_B_PER_CLK_SM = 30.9          # measured: profiles/r2_l2_ingest_probe.json (TMA bytes per clock one SM can take in)
 
 
@@ -354,8 +354,8 @@ def dominant_kernel_roofline(pipe, precision, peaks, live):
         peak_note = ("TF32 tensor peak = cuBLAS TF32 8192^3 measured in this run (MEASURED_PEAKS.json has no TF32 figure; its bf16 burst / 2 "
                      f"would be {peaks.get('bf16_tflops', 1590.0) / 2.0:.1f})") if tf32_lib else "TF32 = half of the bf16 burst figure"
         kinds = {"hybrid": "kind::tf32 + kind::f16 bf16 corrections", "hybrid16": "kind::f16: fp16 main term + bf16 corrections",
-                 "hybrid16w": "kind::f16: fp16 main term + bf16 corrections, weights split on chip"}
-        kname = "gemm_tc_q_kernel<2,2> (tcgen05.mma.cta_group::2 %s, TMA operands, %s)" % (kinds.get(precision, "kind::tf32"), precision)
+                 "hybrid16s": "kind::f16: two fp16 planes per operand, power-of-two scales"}
+        kname = "gemm_tc_q_kernel<2,%s> (tcgen05.mma.cta_group::2 %s, TMA operands, %s)" % ("4,32" if precision == "hybrid16s" else "2,64", kinds.get(precision, "kind::tf32"), precision)
     ach = flops / (ms * 1e-3) / 1e12
     shape = f"M={rows} N=1920 K=384"
     traffic = None
@@ -369,11 +369,11 @@ def dominant_kernel_roofline(pipe, precision, peaks, live):
            "l2": "operands + output of one launch (596 MB at the default chunk) exceed the 126 MB L2",
            "cublas_tf32_8192_tflops": tf32_lib, "ffma_tflops_measured": live.get("ffma_tflops"),
            "executed_over_algorithmic": PASSES.get(precision, 1.0), "peak_source": peak_note, "shape": shape}
-    if precision in ("hybrid16", "hybrid16w", "hybrid", "3xtf32"):
+    if precision in ("hybrid16", "hybrid16s", "hybrid", "3xtf32"):
         # What actually binds this kernel (profiles/r2_l2_ingest_probe.txt): an SM takes in at most ~31 B per clock from L2 --
         # with any number of SMs streaming, any stage depth, multicast or not -- and a 256 x 192 tile step of 32 k needs
         # 16 KB of A + the CTA's half of the weight tile: the k-block cannot be shorter than those bytes / 31, whatever the MMAs need.
-        wb = {"hybrid16": 6.0, "hybrid16w": 4.0, "hybrid": 8.0, "3xtf32": 8.0}[precision]
+        wb = {"hybrid16": 6.0, "hybrid16s": 4.0, "hybrid": 8.0, "3xtf32": 8.0}[precision]
         bytes_kb = 128 * 32 * 4 + 96 * 32 * wb
         clk = peaks.get("sm_max_mhz", 1965.0) * 1e6
         kb_per_cta = (rows / 256.0) * (1920 / 192.0) * (384 / 32) / 74.0
@@ -578,7 +578,7 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": {"fp32": "fp32", "hybrid": "fp32 (fp32-parity tensor-core GEMMs: TF32 main term + bf16 correction terms, fp32 accumulate)",
                           "hybrid16": "fp32 (fp32-parity tensor-core GEMMs: fp16 main term + bf16 correction terms, fp32 accumulate)",
-                          "hybrid16w": "fp32 (fp32-parity tensor-core GEMMs: fp16 main term + bf16 correction terms, fp32 accumulate)",
+                          "hybrid16s": "fp32 (fp32-parity tensor-core GEMMs: two fp16 planes per operand with power-of-two scales, three fp16 products per term pair, fp32 accumulate)",
                           "3xtf32": "fp32 (fp32-parity tensor-core GEMMs: 3xTF32, fp32 accumulate)",
                           "tf32": "tf32 (single-pass tensor-core GEMMs, fp32 accumulate; looser bound)"}[args.precision],
                 "data": "synthetic",

@@ -9,7 +9,8 @@
 // first product only (stated looser bound).
 //
 // The A operand is split in registers by stager warps and written to TMEM (tcgen05.st; the MMA reads it in .ts form), the
-// weight operand is either split once at pack time (df_split_tf32 / df_pack_*) or, RAW_W, on chip from the fp32 matrix.
+// weight operand is split once at pack time (df_split_tf32 / df_pack_*).  (Round 2 also tried splitting the fp32 weight tile on chip,
+// "hybrid16w": bit-identical but slower -- the conversion instructions set the pace -- and removed again)
 // The first two kernel generations of round 1 (one tile per CTA; persistent with A read straight from global memory) are
 // gone: they were superseded by gemm_tc_q_kernel on every shape (DESIGN.md section 4 keeps their measurements).
 #include "df_common.cuh"
@@ -105,8 +106,6 @@ using namespace df_tc;
 // (profiles/r2_c8_bias_comp.txt): worst pose error of 32 crops against the oracle 1.03e-4 -> 3.5e-5, rms GEMM error halved.
 constexpr float BIAS_COMP_H16 = 1.6e-8f, BIAS_COMP_HYBRID = 1.8e-8f, BIAS_COMP_3XTF32 = 1.9e-8f, BIAS_COMP_H16S = 1.6e-8f;
 constexpr int Q_THREADS = 18 * 32;
-constexpr int Q_SPLIT_THREADS = 2 * 32;                      // RAW_W: two more warps split the fp32 weight tile on chip
-constexpr int Q_PLANES = 4;                                  // RAW_W: depth of the operand-plane / a_full / mma_done rings
 constexpr int Q_MAX_STAGES = 8;
 constexpr int Q_TILE = 128 * BK * 4;                         // 16 KB: one 128-row fp32 tile of 32 k
 constexpr int Q_SMEM_STAGES = 12 * Q_TILE;                   // 192 KB of operand stages: 4 x {A 16 KB | W_hi 16 | W_lo 16} for 128
@@ -187,8 +186,29 @@ __device__ __forceinline__ QTile q_decode(const TcParams& p, int t, int m_tiles,
     return c;
 }
 
-template <int CTAS, int A_STAGES, bool RAW_W, int A_COLS>
-__global__ void __launch_bounds__(RAW_W ? Q_THREADS + Q_SPLIT_THREADS : Q_THREADS, 1)
+// Epilogue store of one transposed 32 x 32 chunk, single-run fast path (no earlier partial sums in C, no skip connection, one bias
+// vector for the warp's 32 rows): per 4-row step one LDS.128, the bias, the activation, one address multiply-add and one STG.128.
+template <int ACT>
+__device__ __forceinline__ void epi_store_simple(const float* srow, int sw0, int sw1, char* cbase, uint32_t ldcb, const int (&roff)[8],
+                                                 float4 b, float slope)
+{
+#pragma unroll
+    for (int ps = 0; ps < 8; ++ps) {
+        if (roff[ps] < 0) continue;
+        float4 o = *reinterpret_cast<const float4*>(srow + ps * 128 + ((ps & 1) ? sw1 : sw0));
+        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        if (ACT == 1) {
+            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+        } else if (ACT == 2) {
+            o.x = o.x > 0.f ? o.x : slope * o.x; o.y = o.y > 0.f ? o.y : slope * o.y;
+            o.z = o.z > 0.f ? o.z : slope * o.z; o.w = o.w > 0.f ? o.w : slope * o.w;
+        }
+        *reinterpret_cast<float4*>(cbase + (unsigned long long)(uint32_t)roff[ps] * ldcb) = o;
+    }
+}
+
+template <int CTAS, int A_STAGES, int A_COLS>
+__global__ void __launch_bounds__(Q_THREADS, 1)
 gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_whi,
                  const __grid_constant__ CUtensorMap tm_wlo, const TcParams p, const int bn_cta, const int m_tiles,
                  const int n_tiles, const int total_tiles)
@@ -211,13 +231,6 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     uint64_t* acc_full = bars + 24;                 // [2]
     uint64_t* acc_empty = bars + 26;                // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
-    // RAW_W (hybrid16 with the weight split on chip): the weight tile arrives as fp32 (4 instead of 6 bytes per element through
-    // the SM's fabric port, which bounds this kernel: profiles/r2_l2_ingest_probe.txt) and two splitter warps write the three
-    // 16-bit operand planes the MMAs read.  Stage s = {A | W fp32} is then read by threads only, so `empty[s]` counts the
-    // consumers (4 stager warps + 2 splitter warps) and the TMA may refill it while the MMAs of that k-block are still
-    // running; what the MMAs pin instead are the plane slot and the TMEM A slot of iteration `it`, released by mma_done[it & 3].
-    uint64_t* w_full = bars + 30;                   // [4]  operand planes of the iteration are written (splitter warps of the pair)
-    uint64_t* mma_done = bars + 34;                 // [4]  MMAs of the iteration have retired (commit)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;
@@ -226,17 +239,14 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int bnt = bn_cta * CTAS;                  // tile width = accumulator columns
     const uint32_t w_bytes = (uint32_t)bn_cta * BK * 4;
     // A | W_hi | W_lo (or the bf16 pair tile), all 1024-B aligned; hybrid16s: A | [fp16 hi x32 | fp16 lo x32] rows
-    const uint32_t stage_bytes = (RAW_W || S16) ? Q_TILE + w_bytes : Q_TILE + 2 * w_bytes;
-    const uint32_t plane_bytes = w_bytes + w_bytes / 2;            // RAW_W: [fp16(w) | bf16(w)] 128-byte rows, then bf16(w - fp16(w)) 64-byte rows
-    const uint32_t Q_STAGES = RAW_W ? min((uint32_t)Q_MAX_STAGES, ((uint32_t)Q_SMEM_STAGES - Q_PLANES * plane_bytes) / stage_bytes)
-                                    : min((uint32_t)Q_MAX_STAGES, (uint32_t)Q_SMEM_STAGES / stage_bytes);
-    uint8_t* planes = smem + (size_t)Q_STAGES * stage_bytes;
+    const uint32_t stage_bytes = S16 ? Q_TILE + w_bytes : Q_TILE + 2 * w_bytes;
+    const int Q_STAGES = (int)min((uint32_t)Q_MAX_STAGES, (uint32_t)Q_SMEM_STAGES / stage_bytes);
     const uint32_t ACC_BUFS = bnt <= ACC_STRIDE ? 2 : 1;
+    const uint32_t acc_shift = ACC_BUFS - 1;        // ti % ACC_BUFS == ti & acc_shift, ti / ACC_BUFS == ti >> acc_shift
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < Q_MAX_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, RAW_W ? 6 : 1); mbar_init(a_full + i, 4 * CTAS); }
+        for (int i = 0; i < Q_MAX_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); mbar_init(a_full + i, 4 * CTAS); }
         for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 8 * CTAS); }
-        for (int i = 0; i < Q_PLANES; ++i) { mbar_init(w_full + i, 2 * CTAS); mbar_init(mma_done + i, 1); }
         tmem_slot[1] = 0u;                                         // hybrid16s: bit pattern of the sampled activation maximum
         fence_barrier_init();
     }
@@ -287,13 +297,16 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
     }
 
+    // Ring positions are kept as (slot, phase) counters: the stage count is a runtime value, and `it % Q_STAGES` in the issuing warp's
+    // loop was an integer division (MUFU.RCP + ~20 dependent instructions) per k-block on the kernel's critical path.
     if (warp == 0) {
         // ------------------------------- TMA producer -------------------------------
         const uint32_t a_bytes = p.conv_taps ? (uint32_t)(p.TW * p.TH * p.TB) * BK * 4 : (uint32_t)Q_TILE;
         // 3xTF32: W_hi + W_lo; hybrid: W_hi + bf16 pair tile; hybrid16: pair tile + a half-width (64 B rows) correction tile
-        const uint32_t bytes = a_bytes + ((RAW_W || S16) ? w_bytes : p.precise == 3 ? w_bytes + w_bytes / 2 : (p.precise ? 2u : 1u) * w_bytes);
+        const uint32_t bytes = a_bytes + (S16 ? w_bytes : p.precise == 3 ? w_bytes + w_bytes / 2 : (p.precise ? 2u : 1u) * w_bytes);
         const int cblocks = p.conv_taps ? p.K / (BK * p.conv_taps) : 1;        // 32-channel blocks per tap
-        uint32_t it = 0;
+        int s = 0;
+        uint32_t ph = 1;                                                       // parity of "slot is free": passes at once in round 0
         for (int t = cid; t < total_tiles; t += ncl) {
             const QTile c = q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, rank);
             int wrow = c.g * p.N + c.n0 + rank * bn_cta;
@@ -310,9 +323,8 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             for (int tap = 8; tap >= 0; --tap)
                 if ((c.taps >> tap) & 1u) tap_list = (tap_list << 4) | (uint64_t)tap;
             int cb = 0;
-            for (int j = 0; j < nkb_t; ++j, ++it) {
-                const int s = (int)(it % Q_STAGES);
-                mbar_wait(empty + s, ((it / Q_STAGES) & 1) ^ 1);
+            for (int j = 0; j < nkb_t; ++j) {
+                mbar_wait(empty + s, ph);
                 if (elect_one()) {
                     mbar_expect_tx(full + s, bytes);
                     uint8_t* dst = smem + (size_t)s * stage_bytes;
@@ -327,13 +339,14 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     } else {
                         tma_load_2d(&tm_a, dst, full + s, acol + kb * BK, c.row0);
                     }
-                    // first weight tile: 32 fp32 per row (TF32 hi part), or, hybrid16, [fp16(W) x32 | bf16(W) x32] = 64 halves per row
-                    // (RAW_W: the fp32 weights themselves, 32 per row)
-                    tma_load_2d(&tm_whi, dst + Q_TILE, full + s, kb * (!RAW_W && p.precise >= 3 ? 2 * BK : BK) + wk0, wrow);
+                    // first weight tile: 32 fp32 per row (TF32 hi part), or, hybrid16 / hybrid16s, 64 halves per row ([fp16(W) x32 | bf16(W) x32]
+                    // / [fp16(W s) x32 | fp16 remainder x32])
+                    tma_load_2d(&tm_whi, dst + Q_TILE, full + s, kb * (p.precise >= 3 ? 2 * BK : BK) + wk0, wrow);
                     // second weight tile: W_lo (fp32), or [bf16(W) x32 | bf16(W_lo) x32] (hybrid), or bf16(W_lo) x32 in 64-byte rows (hybrid16)
-                    if (!RAW_W && !S16 && p.precise) tma_load_2d(&tm_wlo, dst + Q_TILE + w_bytes, full + s, kb * (p.precise == 2 ? 2 * BK : BK) + wk0, wrow);
+                    if (!S16 && p.precise) tma_load_2d(&tm_wlo, dst + Q_TILE + w_bytes, full + s, kb * (p.precise == 2 ? 2 * BK : BK) + wk0, wrow);
                 }
                 if (++cb == cblocks) { cb = 0; tap_list >>= 4; }
+                if (++s == Q_STAGES) { s = 0; ph ^= 1u; }
                 __syncwarp();
             }
         }
@@ -344,26 +357,24 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const uint32_t idesc_bf = bf16_instr_desc(bnt, 128 * CTAS);
             const uint32_t idesc_h = f16_instr_desc(bnt, 128 * CTAS);
             uint32_t it = 0, ti = 0;
+            int s = 0;
+            uint32_t ph = 0;
             const int cblocks = p.conv_taps ? p.K / (BK * p.conv_taps) : 1;
             for (int t = cid; t < total_tiles; t += ncl) {
               const int nkb_t = p.conv_taps == 9 ? __popc(q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, 0).taps) * cblocks : nkb;
               const int runs = (nkb_t + p.kbc - 1) / p.kbc;
               for (int kc = 0; kc < runs; ++kc, ++ti) {
                 const int kb0 = kc * p.kbc, kb1 = min(nkb_t, kb0 + p.kbc);
-                const uint32_t ab = ti % ACC_BUFS;
-                const uint32_t aph = ((ti / ACC_BUFS) & 1) ^ 1;
+                const uint32_t ab = ti & acc_shift;
+                const uint32_t aph = ((ti >> acc_shift) & 1) ^ 1;
                 if (CTAS == 2) mbar_wait_cluster(acc_empty + ab, aph); else mbar_wait(acc_empty + ab, aph);
                 const uint32_t acc = tmem_base + ab * ACC_STRIDE;
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = RAW_W ? (int)(it & (Q_PLANES - 1)) : (int)(it % Q_STAGES);
-                    const uint32_t ph = RAW_W ? (it / Q_PLANES) & 1 : (it / Q_STAGES) & 1;
-                    if (RAW_W) mbar_wait(w_full + s, ph);          // (implies full[]: the splitters waited for the TMA bytes)
-                    else mbar_wait(full + s, ph);
+                    mbar_wait(full + s, ph);
                     if (CTAS == 2) mbar_wait_cluster(a_full + s, ph); else mbar_wait(a_full + s, ph);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t w_hi = RAW_W ? smem_u32(planes + (size_t)s * plane_bytes)
-                                                    : smem_u32(smem + (size_t)s * stage_bytes + Q_TILE);
+                        const uint32_t w_hi = smem_u32(smem + (size_t)s * stage_bytes + Q_TILE);
                         const uint64_t bhi0 = sw128_desc(w_hi), blo0 = sw128_desc(w_hi + w_bytes);
                         const uint32_t a0 = tmem_base + TMEM_A0 + (it % A_STAGES) * A_COLS;
                         if (S16) {
@@ -429,21 +440,22 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                 }
                             }
                         }
-                        uint64_t* done = RAW_W ? mma_done + s : empty + s;
                         if (CTAS == 2) {
-                            umma_commit_pair(done);
+                            umma_commit_pair(empty + s);
                             if (kb == kb1 - 1) umma_commit_pair(acc_full + ab);
                         } else {
-                            umma_commit(done);
+                            umma_commit(empty + s);
                             if (kb == kb1 - 1) umma_commit(acc_full + ab);
                         }
                     }
+                    if (++s == Q_STAGES) { s = 0; ph ^= 1u; }
                     __syncwarp();
                 }
               }
             }
         }
-    } else if (warp < 10 || (RAW_W && warp >= 18)) {
+    } else if (warp < 10) {
+        // ------------------------------- A stagers (two groups) ----------------------
         const int my_tiles = (total_tiles - cid + ncl - 1) / ncl;
         uint32_t total_it = (uint32_t)my_tiles * nkb;
         if (p.conv_taps == 9) {                                          // tiles near the border visit fewer taps
@@ -454,71 +466,17 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) total_it += __shfl_xor_sync(0xffffffffu, total_it, off);
         }
-        if (RAW_W && warp >= 18) {
-            // ------------------------------- weight splitters (RAW_W, two warps) ---------
-            // unit = half a weight row (16 fp32 -> 8 fp16 pairs, 8 bf16 pairs, 8 bf16 pairs of the remainders); a warp's 32 lanes take
-            // 32 consecutive rows of one half, so the swizzled 16-byte reads and writes of a quarter warp hit 8 different bank groups
-            const int tid2 = (warp - 18) * 32 + lane;
-            const int upt = bn_cta >> 5;
-            for (uint32_t it = 0; it < total_it; ++it) {
-                const int s = (int)(it % Q_STAGES), m = (int)(it & (Q_PLANES - 1));
-                mbar_wait(full + s, (it / Q_STAGES) & 1);
-                if (it >= (uint32_t)Q_PLANES) mbar_wait(mma_done + m, ((it / Q_PLANES) & 1) ^ 1);     // plane slot m: MMAs of it - 4 retired
-                const uint8_t* wraw = smem + (size_t)s * stage_bytes + Q_TILE;
-                uint8_t* p1 = planes + (size_t)m * plane_bytes;
-                uint8_t* p2 = p1 + w_bytes;
-                for (int j = 0; j < upt; ++j) {
-                    const int u = j * 64 + tid2;
-                    const int half = u >= bn_cta ? 1 : 0;
-                    const int r = u - half * bn_cta;
-                    const int sw = r & 7, sw2 = (r >> 1) & 3;
-                    uint32_t h16[8], b16[8], l16[8];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const uint4 v = *reinterpret_cast<const uint4*>(wraw + r * 128 + (((half * 4 + c) ^ sw) << 4));
-                        const float x0 = __uint_as_float(v.x), x1 = __uint_as_float(v.y), x2 = __uint_as_float(v.z), x3 = __uint_as_float(v.w);
-                        float f0, f1, f2, f3;
-                        h16[2 * c] = pack_f16x2_sat(x0, x1);
-                        h16[2 * c + 1] = pack_f16x2_sat(x2, x3);
-                        unpack_f16x2(h16[2 * c], f0, f1);
-                        unpack_f16x2(h16[2 * c + 1], f2, f3);
-                        b16[2 * c] = pack_bf16x2(x0, x1);
-                        b16[2 * c + 1] = pack_bf16x2(x2, x3);
-                        l16[2 * c] = pack_bf16x2(x0 - f0, x1 - f1);
-                        l16[2 * c + 1] = pack_bf16x2(x2 - f2, x3 - f3);
-                    }
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        *reinterpret_cast<uint4*>(p1 + r * 128 + (((2 * half + c) ^ sw) << 4)) =
-                            make_uint4(h16[4 * c], h16[4 * c + 1], h16[4 * c + 2], h16[4 * c + 3]);
-                        *reinterpret_cast<uint4*>(p1 + r * 128 + (((4 + 2 * half + c) ^ sw) << 4)) =
-                            make_uint4(b16[4 * c], b16[4 * c + 1], b16[4 * c + 2], b16[4 * c + 3]);
-                        *reinterpret_cast<uint4*>(p2 + r * 64 + (((2 * half + c) ^ sw2) << 4)) =
-                            make_uint4(l16[4 * c], l16[4 * c + 1], l16[4 * c + 2], l16[4 * c + 3]);
-                    }
-                }
-                // generic-proxy writes -> visible to the MMAs (async proxy).  The shared::cta form on purpose: the unqualified
-                // fence.proxy.async costs a MEMBAR.ALL.GPU per k-block (measured: tower-1 0.56 ms instead of 0.30)
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(empty + s);
-                    if (CTAS == 2) mbar_arrive_remote(w_full + m, 0); else mbar_arrive(w_full + m);
-                }
-            }
-        } else {
-        // ------------------------------- A stagers (two groups) ----------------------
         const int grp = (warp - 2) >> 2;
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const int sw = r & 7;
+        int s = grp;                                                     // slot / phase of iteration `it` ...
+        uint32_t ph = 0;
+        int sp = grp - A_STAGES;                                         // ... and of iteration it - A_STAGES (negative: none yet)
+        uint32_t php = 0;
         for (uint32_t it = grp; it < total_it; it += 2) {
-            const int s = (int)(it % Q_STAGES);
-            mbar_wait(full + s, (it / Q_STAGES) & 1);
-            // TMEM A slot it % A_STAGES was last read by the MMAs of iteration it - A_STAGES.  With A_STAGES == Q_STAGES
-            // that is implied by full[s] (the commit that frees the slot is what let the TMA refill the stage); with
-            // fewer TMEM slots wait for that iteration's commit explicitly (same barrier the TMA producer watches).
+            mbar_wait(full + s, ph);
             const uint8_t* arow = smem + (size_t)s * stage_bytes + r * 128;
             // hi: TF32-exact part (raw value in single-pass mode); second[]: what goes into columns [32,64) of the TMEM stage --
             // lo (3xTF32), or 16 words of bf16(x) pairs followed by 16 words of bf16(lo) pairs (hybrid)
@@ -568,17 +526,10 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     second[i] = __float_as_uint(x - __uint_as_float(hi[i]));
                 }
             }
-            if (RAW_W) {
-                __syncwarp();                                           // the row is in registers: hand the stage back to the TMA
-                if (lane == 0) mbar_arrive(empty + s);
-                if (it >= (uint32_t)A_STAGES) {
-                    const uint32_t prev = it - A_STAGES;
-                    mbar_wait(mma_done + (prev & (Q_PLANES - 1)), (prev / Q_PLANES) & 1);
-                }
-            } else if (A_STAGES < Q_STAGES && it >= (uint32_t)A_STAGES) {      // (the loads and the split above overlap this wait)
-                const uint32_t prev = it - A_STAGES;
-                mbar_wait(empty + prev % Q_STAGES, (prev / Q_STAGES) & 1);
-            }
+            // TMEM A slot it % A_STAGES was last read by the MMAs of iteration it - A_STAGES.  With A_STAGES >= Q_STAGES that is
+            // implied by full[s] (the commit that frees the slot is what let the TMA refill the stage); with fewer TMEM slots wait
+            // for that iteration's commit explicitly (same barrier the TMA producer watches; the loads and the split above overlap it).
+            if (sp >= 0 && A_STAGES < Q_STAGES) mbar_wait(empty + sp, php);
             tc_fence_after();
             const uint32_t ta = tmem_base + lane_base + TMEM_A0 + (it % A_STAGES) * A_COLS;
             if (S16) tmem_st32(ta, second);
@@ -590,10 +541,10 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                uint64_t* af = a_full + (RAW_W ? (int)(it & (Q_PLANES - 1)) : s);
-                if (CTAS == 2) mbar_arrive_remote(af, 0); else mbar_arrive(af);
+                if (CTAS == 2) mbar_arrive_remote(a_full + s, 0); else mbar_arrive(a_full + s);
             }
-        }
+            s += 2; if (s >= Q_STAGES) { s -= Q_STAGES; ph ^= 1u; }
+            sp += 2; if (sp >= Q_STAGES) { sp -= Q_STAGES; php ^= 1u; }
         }
     } else {
         // ------------------------------- epilogue (8 warps) --------------------------
@@ -603,71 +554,89 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         float* stage = s_epi + ew * 1024;
         const int nchunks = bnt / 32;
+        // store path: after the transpose lane (rr, cc) owns 4 columns of rows ps*4 + rr, ps = 0..7, of this warp's 32 rows; the
+        // swizzle of row ps*4 + rr is rr (+ 4 for odd ps), so the tile is read at two fixed offsets plus an immediate per row
+        const int rr = lane >> 3, cc = lane & 7;
+        const float* srow = stage + rr * 32;
+        const int sw0 = (cc ^ rr) << 2, sw1 = (cc ^ (rr + 4)) << 2;
+        const uint32_t ldcb = (uint32_t)p.ldc * 4u, ldrb = (uint32_t)p.ldr * 4u;
+        const float slope = p.relu == 2 ? __ldg(p.prelu) : 0.0f;
+        const float w_inv = S16 ? __ldg(p.w_inv_scale) / a_sc : 1.0f;          // (powers of two: exact)
+        const int per_kb = p.precise == 1 ? 12 : (p.precise == 2 ? 8 : (p.precise >= 3 ? 6 : 4));
         uint32_t ti = 0;
         for (int t = cid; t < total_tiles; t += ncl) {
           const QTile c = q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, rank);
-          const int runs = p.conv_taps == 9 ? (__popc(c.taps) * (p.K / (BK * 9)) + p.kbc - 1) / p.kbc : p.k_chunks;
+          const int nkb_t = p.conv_taps == 9 ? __popc(c.taps) * (p.K / (BK * 9)) : nkb;
+          const int runs = p.conv_taps == 9 ? (nkb_t + p.kbc - 1) / p.kbc : p.k_chunks;
+          const int r = q * 32 + lane;
+          const bool row_ok = r < c.rows_valid;
+          const float* bias = p.bias ? p.bias + c.g * p.bias_gs : nullptr;
+          // Per tile: where this lane's rows live in C (row / pixel index, -1 = masked) and which bias row they use.
+          int roff[8];
+          int crop_first = 0, crop_boundary = 0x7fffffff;
+          bool straddle = false;
+          if (!p.pool_partial) {
+              if (p.conv_taps) {
+#pragma unroll
+                  for (int ps = 0; ps < 8; ++ps) {
+                      const int R = q * 32 + ps * 4 + rr;
+                      const int rx = R % p.TW, rest = R / p.TW;
+                      const int ry = rest % p.TH, rb = rest / p.TH;
+                      const int x = c.x0 + rx, y = c.y0 + ry, b = c.b0 + rb;
+                      const bool ok = R < c.rows_valid && x < p.cW && y < p.cH && b < p.cB;
+                      roff[ps] = ok ? (b * p.cH + y) * p.cW + x : -1;
+                  }
+              } else {
+#pragma unroll
+                  for (int ps = 0; ps < 8; ++ps) {
+                      const int R = q * 32 + ps * 4 + rr;
+                      roff[ps] = R < c.rows_valid ? c.row0 + R : -1;
+                  }
+                  if (bias && p.bias_crop_stride) {
+                      // clamped to the last crop: the warp's 32 rows may lie entirely in the masked tail of the last M tile
+                      // (M = 3000: rows 3040..3071), and its bias vector is loaded before the row masks are looked at -- one
+                      // row past the end of the (crops x N) bias buffer.  That read was the "ConvS2Fn" illegal address of
+                      // round 1: harmless while the allocator happens to map the following bytes, a fault when it does not.
+                      crop_first = min((c.row0 + q * 32) / p.rows_per_crop, (p.M - 1) / p.rows_per_crop);
+                      crop_boundary = (crop_first + 1) * p.rows_per_crop;
+                      straddle = c.row0 + q * 32 + 31 >= crop_boundary && crop_boundary < p.M;
+                      bias += (size_t)crop_first * p.bias_crop_stride;
+                  }
+              }
+          } else if (bias && p.bias_crop_stride) {
+              bias += (size_t)((row_ok ? c.row0 + r : 0) / p.rows_per_crop) * p.bias_crop_stride;
+          }
+          float* const Cg = p.C + c.g * p.c_gs;
           for (int kc = 0; kc < runs; ++kc, ++ti) {
             const bool first_run = kc == 0, last_run = kc == runs - 1;
-            const uint32_t ab = ti % ACC_BUFS;
-            const int r = q * 32 + lane;
-            const bool row_ok = r < c.rows_valid;
-            const float* bias = p.bias ? p.bias + c.g * p.bias_gs : nullptr;
+            const uint32_t ab = ti & acc_shift;
             float* pool = s_epi + (ti & 1) * 4 * 256;          // aliases the transpose tiles (never both in one launch)
-            // store path: after the transpose lane (rr, cc) owns 4 columns of rows ps*4 + rr, ps = 0..7, of this warp's
-            // 32 rows.  Per tile: where those rows live in C (element offset, -1 = masked) and which bias row they use.
-            const int rr = lane >> 3, cc = lane & 7;
-            int roff[8];                                       // row / pixel index, -1 = masked
-            int crop_first = 0, crop_boundary = 0x7fffffff;
-            if (!p.pool_partial) {
-                if (p.conv_taps) {
-#pragma unroll
-                    for (int ps = 0; ps < 8; ++ps) {
-                        const int R = q * 32 + ps * 4 + rr;
-                        const int rx = R % p.TW, rest = R / p.TW;
-                        const int ry = rest % p.TH, rb = rest / p.TH;
-                        const int x = c.x0 + rx, y = c.y0 + ry, b = c.b0 + rb;
-                        const bool ok = R < c.rows_valid && x < p.cW && y < p.cH && b < p.cB;
-                        roff[ps] = ok ? (b * p.cH + y) * p.cW + x : -1;
-                    }
-                } else {
-#pragma unroll
-                    for (int ps = 0; ps < 8; ++ps) {
-                        const int R = q * 32 + ps * 4 + rr;
-                        roff[ps] = R < c.rows_valid ? c.row0 + R : -1;
-                    }
-                    if (bias && p.bias_crop_stride) {
-                        // clamped to the last crop: the warp's 32 rows may lie entirely in the masked tail of the last M tile
-                        // (M = 3000: rows 3040..3071), and its bias vector is loaded before the row masks are looked at -- one
-                        // row past the end of the (crops x N) bias buffer.  That read was the "ConvS2Fn" illegal address of
-                        // round 1: harmless while the allocator happens to map the following bytes, a fault when it does not.
-                        crop_first = min((c.row0 + q * 32) / p.rows_per_crop, (p.M - 1) / p.rows_per_crop);
-                        crop_boundary = (crop_first + 1) * p.rows_per_crop;
-                    }
-                }
-            } else if (bias && p.bias_crop_stride) {
-                bias += (size_t)((row_ok ? c.row0 + r : 0) / p.rows_per_crop) * p.bias_crop_stride;
-            }
-            const float slope = p.relu == 2 ? __ldg(p.prelu) : 0.0f;
-            float run_scale = 1.0f;
+            float run_scale = w_inv;
             if (p.bias_comp != 0.0f) {
-                const int nkb_t = p.conv_taps == 9 ? __popc(c.taps) * (p.K / (BK * 9)) : nkb;
                 const int n_kb = min(nkb_t, (kc + 1) * p.kbc) - kc * p.kbc;
-                const int per_kb = p.precise == 1 ? 12 : (p.precise == 2 ? 8 : (p.precise >= 3 ? 6 : 4));
-                run_scale = 1.0f + p.bias_comp * (float)(n_kb * per_kb);
+                run_scale *= 1.0f + p.bias_comp * (float)(n_kb * per_kb);
             }
-            if (S16) run_scale *= __ldg(p.w_inv_scale) / a_sc;            // (powers of two: exact)
-            mbar_wait(acc_full + ab, (ti / ACC_BUFS) & 1);
+            // the simple store: one run, no skip connection, one bias vector for all 32 rows of the warp
+            const bool simple = first_run && last_run && !p.residual && !straddle;
+            mbar_wait(acc_full + ab, (ti >> acc_shift) & 1);
             tc_fence_after();
 #pragma unroll 1
             for (int ch = half; ch < nchunks; ch += 2) {
                 uint32_t v[32];
+                const int col = c.n0 + ch * 32;
+                const int cq = col + cc * 4;
+                // this lane's 4 bias values (requested before the accumulator is read: the L2 round trip overlaps the TMEM load and the
+                // transpose): one vector, or two when the warp's 32 rows straddle a crop boundary
+                float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                if (!p.pool_partial && bias && last_run && cq < p.N) {
+                    b0 = __ldg(reinterpret_cast<const float4*>(bias + cq));
+                    if (straddle) b1 = __ldg(reinterpret_cast<const float4*>(bias + p.bias_crop_stride + cq));
+                }
                 tmem_ld32(tmem_base + lane_base + ab * ACC_STRIDE + ch * 32, v);
                 if (run_scale != 1.0f) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * run_scale);
                 }
-                const int col = c.n0 + ch * 32;
                 if (p.pool_partial) {
                     float f[32];
 #pragma unroll
@@ -690,50 +659,47 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     pool[q * 256 + ch * 32 + lane] = f[0];
                 } else {
                     // transpose through a swizzled 32x32 tile: lane == row on the way in, 8 lanes == one 128 B row out;
-                    // bias / skip connection / activation are applied on the way out (coalesced float4 reads)
+                    // bias / skip connection / activation are applied on the way out (coalesced float4 accesses)
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         *reinterpret_cast<uint4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) =
                             make_uint4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
                     __syncwarp();
-                    const int cq = col + cc * 4;
                     if (cq < p.N) {
-                        // this lane's 4 bias values: one vector, or two when the warp's 32 rows straddle a crop boundary
-                        // (loaded once per chunk -- per-row loads kept the epilogue warps waiting on L2 all the time)
-                        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-                        if (bias && last_run) {
-                            const float* brow = bias + (p.bias_crop_stride ? (size_t)crop_first * p.bias_crop_stride : 0);
-                            b0 = __ldg(reinterpret_cast<const float4*>(brow + cq));
-                            if (p.bias_crop_stride && c.row0 + q * 32 + 31 >= crop_boundary && crop_boundary < p.M)
-                                b1 = __ldg(reinterpret_cast<const float4*>(brow + p.bias_crop_stride + cq));
-                        }
+                        char* cbase = reinterpret_cast<char*>(Cg + cq);
+                        if (simple) {
+                            if (p.relu == 1) epi_store_simple<1>(srow, sw0, sw1, cbase, ldcb, roff, b0, slope);
+                            else if (p.relu == 2) epi_store_simple<2>(srow, sw0, sw1, cbase, ldcb, roff, b0, slope);
+                            else epi_store_simple<0>(srow, sw0, sw1, cbase, ldcb, roff, b0, slope);
+                        } else {
+                            const char* rbase = p.residual ? reinterpret_cast<const char*>(p.residual + cq) : nullptr;
 #pragma unroll
-                        for (int ps = 0; ps < 8; ++ps) {
-                            if (roff[ps] < 0) continue;
-                            const int lr = ps * 4 + rr;
-                            float4 o = *reinterpret_cast<const float4*>(stage + lr * 32 + ((cc ^ (lr & 7)) << 2));
-                            float* dst = p.C + c.g * p.c_gs + (size_t)roff[ps] * p.ldc + cq;
-                            if (!first_run) {                          // earlier runs of this tile, written by this very thread
-                                const float4 prev = *reinterpret_cast<const float4*>(dst);
-                                o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
+                            for (int ps = 0; ps < 8; ++ps) {
+                                if (roff[ps] < 0) continue;
+                                float4 o = *reinterpret_cast<const float4*>(srow + ps * 128 + ((ps & 1) ? sw1 : sw0));
+                                float* dst = reinterpret_cast<float*>(cbase + (unsigned long long)(uint32_t)roff[ps] * ldcb);
+                                if (!first_run) {                          // earlier runs of this tile, written by this very thread
+                                    const float4 prev = *reinterpret_cast<const float4*>(dst);
+                                    o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
+                                }
+                                if (!last_run) { *reinterpret_cast<float4*>(dst) = o; continue; }
+                                if (bias) {
+                                    const float4 bv = roff[ps] >= crop_boundary ? b1 : b0;
+                                    o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                                }
+                                if (rbase) {
+                                    const float4 rv = __ldg(reinterpret_cast<const float4*>(rbase + (unsigned long long)(uint32_t)roff[ps] * ldrb));
+                                    o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+                                }
+                                if (p.relu == 1) {
+                                    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                                } else if (p.relu == 2) {
+                                    o.x = o.x > 0.f ? o.x : slope * o.x; o.y = o.y > 0.f ? o.y : slope * o.y;
+                                    o.z = o.z > 0.f ? o.z : slope * o.z; o.w = o.w > 0.f ? o.w : slope * o.w;
+                                }
+                                *reinterpret_cast<float4*>(dst) = o;
                             }
-                            if (!last_run) { *reinterpret_cast<float4*>(dst) = o; continue; }
-                            if (bias) {
-                                const float4 bv = roff[ps] >= crop_boundary ? b1 : b0;
-                                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-                            }
-                            if (p.residual) {
-                                const float4 rv = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)roff[ps] * p.ldr + cq));
-                                o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
-                            }
-                            if (p.relu == 1) {
-                                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                            } else if (p.relu == 2) {
-                                o.x = o.x > 0.f ? o.x : slope * o.x; o.y = o.y > 0.f ? o.y : slope * o.y;
-                                o.z = o.z > 0.f ? o.z : slope * o.z; o.w = o.w > 0.f ? o.w : slope * o.w;
-                            }
-                            *reinterpret_cast<float4*>(dst) = o;
                         }
                     }
                 }
@@ -747,8 +713,8 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 epilogue warps
                 const int tt = threadIdx.x - 320;
                 if (tt < bnt && c.n0 + tt < p.N && c.rows_valid > 0) {
-                    const float s = ((pool[tt] + pool[256 + tt]) + pool[512 + tt]) + pool[768 + tt];
-                    p.pool_partial[((size_t)c.crop * p.tiles_per_crop + c.pool_tile) * p.N + c.n0 + tt] = s;
+                    const float sum = ((pool[tt] + pool[256 + tt]) + pool[512 + tt]) + pool[768 + tt];
+                    p.pool_partial[((size_t)c.crop * p.tiles_per_crop + c.pool_tile) * p.N + c.n0 + tt] = sum;
                 }
             }
           }
@@ -841,11 +807,11 @@ bool make_map_nhwc(CUtensorMap* map, const float* base, int B, int H, int W, int
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int CTAS, int A_STAGES, bool RAW_W = false, int A_COLS = 64>
+template <int CTAS, int A_STAGES, int A_COLS = 64>
 int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw, int groups, cudaStream_t s)
 {
-    static_assert(A_COLS == 64 || (A_COLS == 32 && CTAS == 2 && !RAW_W), "the 32-column A stage is the CTA-pair hybrid16s form");
-    constexpr int THREADS = RAW_W ? Q_THREADS + Q_SPLIT_THREADS : Q_THREADS;
+    static_assert(A_COLS == 64 || (A_COLS == 32 && CTAS == 2), "the 32-column A stage is the CTA-pair hybrid16s form");
+    constexpr int THREADS = Q_THREADS;
     constexpr int ACC_STRIDE = (512 - A_STAGES * A_COLS) / 2;
     if ((A_COLS == 32) != (p_in.precise == 4)) return DF_ERR_ARG;
     TcParams p = p_in;
@@ -888,7 +854,7 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
         cudaGetDevice(&dev);
         cudaError_t e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(gemm_tc_q_kernel<CTAS, A_STAGES, RAW_W, A_COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_TOTAL);
+        e = cudaFuncSetAttribute(gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_TOTAL);
         if (e != cudaSuccess) return (int)e;
         int n = num_sms / CTAS;
         if (CTAS == 2) {
@@ -899,7 +865,7 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
             at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             q.attrs = at; q.numAttrs = 1;
             int occ = 0;
-            if (cudaOccupancyMaxActiveClusters(&occ, gemm_tc_q_kernel<CTAS, A_STAGES, RAW_W, A_COLS>, &q) == cudaSuccess && occ > 0 && occ < n) n = occ;
+            if (cudaOccupancyMaxActiveClusters(&occ, gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS>, &q) == cudaSuccess && occ > 0 && occ < n) n = occ;
             (void)cudaGetLastError();
         }
         max_clusters = n;
@@ -947,10 +913,6 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
     const long long wrows = p.wk_rows ? (long long)p.wk_rows * (p.N / p.wk_rows == 9 ? 3 : 1) : (long long)groups * p.N;
     if (p.wk_rows) {                                               // weight-gradient form: W spans every k slice (row length ldw)
         if (!make_map(&mhi, W_hi, wrows, ldw, ldw, bn_cta) || !make_map(&mlo, W_lo, wrows, ldw, ldw, bn_cta)) return DF_ERR_UNSUPPORTED;
-    } else if (RAW_W) {                                            // hybrid16, weights split on chip: the fp32 matrix itself
-        if (p.precise != 3) return DF_ERR_UNSUPPORTED;
-        if (!make_map(&mhi, W_hi, wrows, p.K, ldw, bn_cta)) return DF_ERR_UNSUPPORTED;
-        mlo = mhi;
     } else if (p.precise == 4) {                                   // hybrid16s: one packed tensor, [fp16 hi x32 | fp16 lo x32] per row and k-block
         if (ldw != p.K || !p.w_inv_scale) return DF_ERR_UNSUPPORTED;
         if (!make_map_bf16_pairs(&mhi, W_hi, wrows, p.K, bn_cta)) return DF_ERR_UNSUPPORTED;
@@ -979,7 +941,7 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = use_pdl() ? 2 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_q_kernel<CTAS, A_STAGES, RAW_W, A_COLS>, ma, mhi, mlo, p, bn_cta, m_tiles, n_tiles, total);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS>, ma, mhi, mlo, p, bn_cta, m_tiles, n_tiles, total);
     return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -1111,7 +1073,7 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, float* __re
     }
     const float h0 = __uint_as_float(__float_as_uint(x[0]) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(x[1]) & 0xffffe000u);
     float* hrow = hi + (size_t)row * K + kp * 2;
-    const bool raw = !lo && !pairs;                              // plain fp32 repack (hybrid16 with the split on chip)
+    const bool raw = !lo && !pairs;                              // plain fp32 repack (input of df_pack_f16s)
     hrow[0] = raw ? x[0] : h0; hrow[1] = raw ? x[1] : h1;
     if (lo) { float* lrow = lo + (size_t)row * K + kp * 2; lrow[0] = x[0] - h0; lrow[1] = x[1] - h1; }
     if (pairs) {
@@ -1344,8 +1306,8 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
     const int run_units = (precision >> 8) & 0xff;                  // accumulation-run length in units of 12 MMA instructions
     const int a_byte = (precision >> 16) & 0xff;                    // hybrid16s: 0 = scale sampled by the kernel, else a fixed 2^k
     precision &= 0xff;
-    if (precision < 1 || precision > 6) return DF_ERR_ARG;
-    if (precision != 2 && precision != 5 && !W_lo) return DF_ERR_ARG;
+    if (precision < 1 || precision > 6 || precision == 5) return DF_ERR_ARG;       // (5: the on-chip weight split of round 2, removed)
+    if (precision != 2 && !W_lo) return DF_ERR_ARG;
     if (M <= 0 || N <= 0 || K <= 0 || groups <= 0) return DF_ERR_ARG;
     if (K % BK || lda % 4 || ldw % 4 || N % 4 || a_group_stride % 4 || bias_group_stride % 4) return DF_ERR_ARG;
     if (((uintptr_t)A & 15) || ((uintptr_t)W_hi & 15) || ((uintptr_t)W_lo & 15)) return DF_ERR_ARG;
@@ -1358,7 +1320,7 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
     p.A = A; p.lda = lda; p.bias = bias; p.bias_crop_stride = bias_crop_stride;
     p.C = pool_partial ? nullptr : C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.relu = relu;
     // kernel-side: 0 single TF32, 1 3xTF32, 2 hybrid, 3 hybrid16, 4 hybrid16s
-    p.precise = precision == 1 ? 1 : (precision == 3 ? 2 : (precision == 6 ? 4 : (precision >= 4 ? 3 : 0)));
+    p.precise = precision == 1 ? 1 : (precision == 3 ? 2 : (precision == 6 ? 4 : (precision == 4 ? 3 : 0)));
     p.w_inv_scale = precision == 6 ? W_lo : nullptr; p.a_scale = a_byte == 0 ? 0.0f : (a_byte == 0x80 ? 1.0f : exp2f((float)(signed char)a_byte));
     p.run_steps = run_units * 12;
     p.rows_per_crop = rows_per_crop > 0 ? rows_per_crop : M;
@@ -1371,12 +1333,9 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
     int v = variant;
     if (v == 0) v = default_variant();
     int rc;
-    if (precision == 5) {                        // hybrid16 arithmetic, W_hi = the fp32 weights (split on chip): CTA-pair kernel only
+    if (precision == 6) {                 // hybrid16s: two fp16 planes per operand, 32-column TMEM A stages: CTA-pair kernel only
         if (variant != 0 && variant != 6) return DF_ERR_UNSUPPORTED;
-        rc = launch_q<2, 2, true>(p, W_hi, W_hi, ldw, groups, (cudaStream_t)stream);
-    } else if (precision == 6) {                 // hybrid16s: two fp16 planes per operand, 32-column TMEM A stages: CTA-pair kernel only
-        if (variant != 0 && variant != 6) return DF_ERR_UNSUPPORTED;
-        rc = launch_q<2, 4, false, 32>(p, W_hi, W_hi, ldw, groups, (cudaStream_t)stream);
+        rc = launch_q<2, 4, 32>(p, W_hi, W_hi, ldw, groups, (cudaStream_t)stream);
     } else if (v == 5) rc = launch_q<1, 4>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream);
     else if (v == 6) rc = launch_q<2, 2>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream);
     else if (v == 7) rc = launch_q<2, 4>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream);
@@ -1450,8 +1409,8 @@ extern "C" int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx,
     const int run_units = (precision >> 8) & 0xff;
     const int a_byte = (precision >> 16) & 0xff;
     precision &= 0xff;
-    if (precision < 1 || precision > 6) return DF_ERR_ARG;
-    if (precision != 2 && precision != 5 && !W_lo) return DF_ERR_ARG;
+    if (precision < 1 || precision > 6 || precision == 5) return DF_ERR_ARG;       // (5: the on-chip weight split of round 2, removed)
+    if (precision != 2 && !W_lo) return DF_ERR_ARG;
     if ((taps != 1 && taps != 9) || dilation < 1 || act < 0 || act > 2 || (act == 2 && !prelu)) return DF_ERR_ARG;
     if (Cin % BK || Cout % 4 || ldx % 4 || ldy % 4 || ldx < Cin || ldy < Cout || (residual && (ldr % 4 || ldr < Cout))) return DF_ERR_ARG;
     if (((uintptr_t)X & 15) || ((uintptr_t)Y & 15) || ((uintptr_t)W_hi & 15) || ((uintptr_t)W_lo & 15) ||
@@ -1462,15 +1421,14 @@ extern "C" int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx,
     TcParams p = {};
     p.A = X; p.lda = ldx; p.bias = bias; p.bias_crop_stride = 0; p.C = Y; p.ldc = ldy;
     p.M = B * H * W; p.N = Cout; p.K = taps * Cin; p.relu = act;
-    p.precise = precision == 1 ? 1 : (precision == 3 ? 2 : (precision == 6 ? 4 : (precision >= 4 ? 3 : 0)));
+    p.precise = precision == 1 ? 1 : (precision == 3 ? 2 : (precision == 6 ? 4 : (precision == 4 ? 3 : 0)));
     p.w_inv_scale = precision == 6 ? W_lo : nullptr; p.a_scale = a_byte == 0 ? 0.0f : (a_byte == 0x80 ? 1.0f : exp2f((float)(signed char)a_byte));
     p.run_steps = run_units * 12;
     p.rows_per_crop = p.M; p.a_gs = 0; p.bias_gs = 0; p.c_gs = 0; p.pool_partial = nullptr; p.tiles_per_crop = 0;
     p.conv_taps = taps; p.conv_dil = dilation; p.cW = W; p.cH = H; p.cB = B;
     p.residual = residual; p.ldr = ldr; p.prelu = prelu;
     conv_patch_plan(p, B, H, W, taps, dilation);
-    const int rc = precision == 5 ? launch_q<2, 2, true>(p, W_hi, W_hi, taps * Cin, 1, (cudaStream_t)stream)
-                 : precision == 6 ? launch_q<2, 4, false, 32>(p, W_hi, W_hi, taps * Cin, 1, (cudaStream_t)stream)
+    const int rc = precision == 6 ? launch_q<2, 4, 32>(p, W_hi, W_hi, taps * Cin, 1, (cudaStream_t)stream)
                                   : launch_q<2, 2>(p, W_hi, W_lo, taps * Cin, 1, (cudaStream_t)stream);
     if (rc) return rc;
     DF_RETURN_LAST_ERROR();

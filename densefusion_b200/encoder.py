@@ -175,8 +175,8 @@ class PackedEncoder:
 
     def _trunk(self, img: torch.Tensor, precision: str, stages: int):
         """Everything up to and including `stages` of the three up-sampling stages.  Returns (activation, workspace, mode)."""
-        if precision not in ("3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16w", "hybrid16s"):
-            raise ValueError("the tensor-core encoder runs in '3xtf32' / 'hybrid' / 'hybrid16' (fp32 parity) or 'tf32'")
+        if precision not in ("3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16s"):
+            raise ValueError("the tensor-core encoder runs in '3xtf32' / 'hybrid' / 'hybrid16' / 'hybrid16s' (fp32 parity) or 'tf32'")
         mode = ops.PRECISIONS[precision]
         img = ops.f32c(img)
         b, _, H, W = img.shape

@@ -85,10 +85,12 @@ def _pack_now(weight: torch.Tensor, rotate: bool, mode: int):
     rows, kt = (cin, k * k * cout) if rotate else (cout, k * k * cin)
     w = weight.detach().float().contiguous()
     hi = torch.empty(rows, kt, device=w.device, dtype=torch.float32)
-    if mode == 5:                                           # hybrid16w, split on chip: the repacked fp32 weights
+    if mode == 6:                                           # hybrid16s: the repacked fp32 weights -> two fp16 planes + scale record
         check(lib.df_pack_conv_weight(ptr(w), ptr(hi), None, None, cout, cin, k * k, 1 if rotate else 0, stream()),
               "df_pack_conv_weight")
-        return hi, hi
+        planes, scale = torch.empty_like(hi), torch.empty(4, device=w.device, dtype=torch.float32)
+        check(lib.df_pack_f16s(ptr(hi), ptr(planes), ptr(scale), rows, kt, stream()), "df_pack_f16s")
+        return planes, scale
     if mode == 4:                                           # hybrid16: [fp16(w) | bf16(w)] per k-block and bf16(w - fp16(w))
         second = torch.empty(rows, kt // 2, device=w.device, dtype=torch.float32)
         check(lib.df_pack_conv_weight16(ptr(w), ptr(hi), ptr(second), cout, cin, k * k, 1 if rotate else 0, stream()),

@@ -14,15 +14,13 @@ from ._C import check, f32c, i64c, lib, need_cuda, ptr, stream
 # "hybrid": TF32 main term + the two ~2^-11 correction terms in bf16 (8 instead of 12 MMAs per k-block), fp32-parity like
 # "3xtf32"; generation-2 tensor-core kernels only
 # "hybrid16": fp16 main term + bf16 correction terms (6 MMAs per k-block), weight planes packed once (df_pack_f16_pairs).
-# "hybrid16w": the same arithmetic, bit for bit, with the fp32 weight tile split into its planes ON CHIP (4 instead of 6 bytes
-# per weight element through the SM's fabric port).  Measured SLOWER (tower-1 0.41 vs 0.30 ms, profiles/r2_c3_gemm_ab.jsonl): the
-# conversion instructions of the extra splitter warps, not the port, then set the pace -- kept as the cross-check of the packed
-# planes and as the record of the experiment, not used by default.
+# (code 5 was "hybrid16w", the same arithmetic with the fp32 weight tile split on chip: bit-identical, measured slower -- tower-1
+# 0.41 vs 0.30 ms, profiles/r2_c3_gemm_ab.jsonl -- and removed again.)
 # "hybrid16s": every term on fp16 operands, two planes per operand (x = fp16(x s) + fp16(x s - fp16(x s)), power-of-two scales s):
 # 4 instead of 6 bytes per weight element through the SM's fabric port and half the TMEM per A stage.  The weight scale comes from
 # the tensor's own maximum (df_pack_f16s); the activation scale is derived inside the kernel from a 4096-element sample of the operand
 # (gemm_tc.cu, "activation scale"), or fixed per call with `a_log2` (tests).
-PRECISIONS = {"fp32": 0, "3xtf32": 1, "tf32": 2, "hybrid": 3, "hybrid16": 4, "hybrid16w": 5, "hybrid16s": 6}
+PRECISIONS = {"fp32": 0, "3xtf32": 1, "tf32": 2, "hybrid": 3, "hybrid16": 4, "hybrid16s": 6}
 
 
 def _prec_code(mode: int, short_runs: bool, a_log2=None) -> int:
@@ -142,10 +140,7 @@ class SplitWeight:
 
     def operands(self, mode: int):
         """The two weight operands df_gemm_tc / df_conv_tc expect for a PRECISIONS code (1 3xtf32, 2 tf32, 3 hybrid, 4 hybrid16,
-        5 hybrid16w: the fp32 weights themselves)."""
-        if mode == 5:
-            need_cuda(self.w)
-            return self.w, self.w
+        6 hybrid16s: the packed planes and their scale record)."""
         if mode == 6:
             return self.planes16s()
         return self.pairs16() if mode == 4 else (self.pairs() if mode == 3 else self.split())

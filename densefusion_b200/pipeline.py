@@ -37,7 +37,7 @@ class PoseEstimator:
         # encoder: "tc" = densefusion_b200.encoder (tcgen05 implicit-GEMM convolutions, same arithmetic mode as the head),
         # "torch" = the torch/cuDNN module; "auto" = tc whenever the head runs on the tensor cores
         if encoder == "auto":
-            encoder = "tc" if precision in ("3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16w", "hybrid16s") else "torch"
+            encoder = "tc" if precision in ("3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16s") else "torch"
         if encoder not in ("tc", "torch"):
             raise ValueError("encoder must be 'auto', 'tc' or 'torch'")
         self.encoder = encoder

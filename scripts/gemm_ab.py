@@ -1,7 +1,7 @@
 """A/B timing of the tensor-core GEMM / convolution at the bench shapes: one precision mode against another, CUDA events,
 each launch on fresh operands (two operand sets larger than L2 alternate).  Prints one JSON line per case.
 
-    python scripts/gemm_ab.py [modeA modeB ...]        default: hybrid16 hybrid16w
+    python scripts/gemm_ab.py [modeA modeB ...]        default: hybrid16 hybrid16s
 """
 import json
 import os
@@ -14,7 +14,7 @@ from densefusion_b200 import ops
 from densefusion_b200.encoder import PackedEncoder, _pack_conv
 
 dev = "cuda"
-modes = sys.argv[1:] or ["hybrid16", "hybrid16w"]
+modes = sys.argv[1:] or ["hybrid16", "hybrid16s"]
 torch.manual_seed(0)
 REPS = 20
 

@@ -21,7 +21,7 @@ def _variants(default):
 
 
 # stated bounds per arithmetic mode (max-abs error / max-abs value)
-TOL = {"fp32": 1e-4, "3xtf32": 1e-4, "hybrid": 1e-4, "hybrid16w": 1e-4, "hybrid16": 1e-4, "hybrid16s": 1e-4, "tf32": 5e-3}
+TOL = {"fp32": 1e-4, "3xtf32": 1e-4, "hybrid": 1e-4, "hybrid16": 1e-4, "hybrid16s": 1e-4, "tf32": 5e-3}
 
 
 def _ref_linear(x, w, b, relu):
@@ -40,15 +40,15 @@ def test_gemm_fp32_vs_float64(M, N, K):
 
 
 @pytest.mark.parametrize("variant", _variants([5, 6, 7]))
-@pytest.mark.parametrize("precision", ["3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16w", "hybrid16s"])
+@pytest.mark.parametrize("precision", ["3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16s"])
 def test_gemm_tensor_core_variants(variant, precision):
     """variant 5: persistent kernel, one CTA per tile, A operand by TMA; 6 / 7: CTA pairs (cta_group::2, 256-row tiles) with
-    2 / 4 TMEM A stages.  "hybrid16w" (weights split on chip) exists on variant 6, the production kernel."""
+    2 / 4 TMEM A stages.  "hybrid16s" (32-column TMEM A stages) exists on variant 6, the production kernel."""
     from densefusion_b200 import ops
     g = torch.Generator().manual_seed(variant)
     M, N, K = 1000, 512, 384
-    if precision in ("hybrid16w", "hybrid16s") and variant != 6:
-        pytest.skip("the on-chip weight split exists in the production kernel (variant 6) only")
+    if precision == "hybrid16s" and variant != 6:
+        pytest.skip("the two-plane fp16 arithmetic exists in the production kernel (variant 6) only")
     x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
     ops.TC_VARIANT = variant
     try:
@@ -80,10 +80,10 @@ def test_gemm_tensor_core_identity_layout():
 
 
 @pytest.mark.parametrize("M,N,K,groups", [(1000, 512, 384, 1), (64000 // 8, 1920, 384, 1), (3000, 256, 640, 3), (515, 128, 256, 3),
-                                            (2500, 1024, 512, 1), (300, 64, 64, 1), (96, 1024, 512, 1)])
-def test_hybrid16_on_chip_split_is_bit_identical_to_packed_planes(M, N, K, groups):
-    """"hybrid16w" splits the fp32 weight tile into its three 16-bit planes inside the kernel, "hybrid16" reads planes packed by
-    df_pack_f16_pairs: the same products in the same order, so every output bit must agree (all tile widths 64..192)."""
+                                            (2500, 1024, 512, 1), (300, 64, 64, 1), (96, 1024, 512, 1), (700, 512, 4608, 1)])
+def test_hybrid16s_all_tile_widths_and_groups(M, N, K, groups):
+    """"hybrid16s" on every tile width the launcher picks (64 .. 256), grouped layers and a multi-run k loop, against float64 and
+    within rounding of "hybrid16" (different planes, same 22-bit operands)."""
     from densefusion_b200 import ops
     g = torch.Generator().manual_seed(M + N + K)
     A = torch.randn(M, K * groups, generator=g).cuda()
@@ -95,21 +95,20 @@ def test_hybrid16_on_chip_split_is_bit_identical_to_packed_planes(M, N, K, group
         ops.gemm(A, W, b, C, M=M, N=N, K=K, lda=K * groups, ldw=K, ldc=N * groups, relu=True, precision=prec, groups=groups,
                  a_gs=K, w_gs=N * K, bias_gs=N, c_gs=N)
         return C
-    got, want = run("hybrid16w"), run("hybrid16")
+    got, other = run("hybrid16s"), run("hybrid16")
     torch.cuda.synchronize()
-    assert torch.equal(got, want), f"{int((got != want).sum())} elements differ, max {float((got - want).abs().max()):.3e}"
     ref64 = torch.relu(torch.einsum("mgk,gnk->mgn", A.double().view(M, groups, K), W.w.double().view(groups, N, K)).reshape(M, -1) + b.double())
-    assert rel(got, ref64) < 1e-5
+    assert rel(got, ref64) < 5e-6 and rel(got, other) < 1e-5
 
 
-@pytest.mark.parametrize("precision", ["3xtf32", "hybrid", "hybrid16", "hybrid16w"])
+@pytest.mark.parametrize("precision", ["3xtf32", "hybrid", "hybrid16"])
 @pytest.mark.parametrize("scale_a,scale_w", [(1e6, 1.0), (1.0, 1e6), (1e-7, 1.0), (1.0, 1e-7), (3e5, 1e-6), (1e3, 1.0), (1.0, 1e3),
                                              (1e-2, 1.0), (1.0, 1e-2), (1e3, 1e-2)])
 def test_gemm_parity_modes_operand_range(precision, scale_a, scale_w):
     """Operand range of the fp32-parity modes, against float64, in the max-norm and element-wise (relative with an absolute
     floor of 1e-2 of the output scale: a dot product's absolute error scales with |a||w|, not with the individual result).
       * "3xtf32" / "hybrid": the main term keeps the fp32 exponent -> no range restriction (operands scaled by 1e6 / 1e-7 pass).
-      * "hybrid16" / "hybrid16w": the main term is fp16, so parity needs the operands that carry the dot product inside fp16's normal range,
+      * "hybrid16": the main term is fp16, so parity needs the operands that carry the dot product inside fp16's normal range,
         6.1e-5 <= |x| <= 65504 (smaller entries of an in-range tensor only lose bits that do not matter at the tensor's scale).
         Outside, the remainder x - fp16(x) is as large as x itself and only has bf16's 8 bits: the result degrades to a bf16-grade
         2^-8 (finite, saturating conversion) -- asserted here as the documented behaviour.  With BOTH operands out of range the
@@ -308,7 +307,7 @@ def test_per_crop_bias_is_not_read_past_its_last_row():
         del big, bias
 
 
-@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16w", "hybrid16s"])
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16s"])
 @pytest.mark.parametrize("n,o,B", [(500, 21, 3), (1000, 13, 2)])
 def test_head_vs_oracle(precision, n, o, B):
     est, _, est_sd, _ = build_nets(n, o, seed=5)
@@ -333,7 +332,7 @@ def test_head_vs_oracle(precision, n, o, B):
     print(f"head {precision} n={n}: worst rel err {worst:.3e}")
 
 
-@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "hybrid", "hybrid16", "hybrid16w", "hybrid16s"])
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "hybrid", "hybrid16", "hybrid16s"])
 def test_refiner_vs_oracle(precision):
     n, o, B = 500, 21, 4
     _, ref, _, ref_sd = build_nets(n, o, seed=6)
