@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("DF_PRECISION", "hybrid16"), choices=["fp32", "3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16s"])
+    ap.add_argument("--precision", default=os.environ.get("DF_PRECISION", "hybrid16s"), choices=["fp32", "3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16s"])
     ap.add_argument("--frames", type=int, default=32, help="frames (of 8 objects) per GPU per step")
     ap.add_argument("--chunk", type=int, default=128, help="crops per head chunk (measured 16: 21.7 ms, 32: 20.7, 64: 20.3, 128: 20.05 per step)")
     ap.add_argument("--no-graph", action="store_true")
@@ -297,6 +297,14 @@ def time_weighted_roofline(pipe, dev_set, precision, peaks, live):
         ms += t
         per.append((t, f, what))
     per.sort(reverse=True)
+    if os.environ.get("DF_BENCH_LAUNCHES"):                       # every launch of the step, grouped by shape (profiles/)
+        agg = {}
+        for t, f, w in per:
+            a = agg.setdefault(w, [0, 0.0, 0.0])
+            a[0] += 1; a[1] += t; a[2] += f
+        rows = sorted(([w, n, round(t, 4), round(f / (t * 1e-3) / 1e12, 1)] for w, (n, t, f) in agg.items()), key=lambda r: -r[2])
+        with open(os.environ["DF_BENCH_LAUNCHES"], "w") as fh:
+            json.dump({"columns": ["launch", "count", "ms_total", "tflops"], "ms_sum": round(ms, 4), "rows": rows}, fh, indent=0)
     ach = flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
     tf32_peak = live.get("cublas_tf32_tflops") or peaks.get("bf16_tflops", 1590.0) / 2.0
     return {"launches": len(per), "ms_sum": ms, "executed_flops": flops, "achieved": ach, "unit": "TFLOP/s",

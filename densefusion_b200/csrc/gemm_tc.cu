@@ -573,10 +573,17 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const float* bias = p.bias ? p.bias + c.g * p.bias_gs : nullptr;
           // Per tile: where this lane's rows live in C (row / pixel index, -1 = masked) and which bias row they use.
           int roff[8];
+          int myrow = -1;                                      // the row this lane holds after the TMEM load (lane == row)
           int crop_first = 0, crop_boundary = 0x7fffffff;
           bool straddle = false;
           if (!p.pool_partial) {
               if (p.conv_taps) {
+                  if (runs > 1) {
+                      const int rx = r % p.TW, rest = r / p.TW;
+                      const int ry = rest % p.TH, rb = rest / p.TH;
+                      const int x = c.x0 + rx, y = c.y0 + ry, b = c.b0 + rb;
+                      if (row_ok && x < p.cW && y < p.cH && b < p.cB) myrow = (b * p.cH + y) * p.cW + x;
+                  }
 #pragma unroll
                   for (int ps = 0; ps < 8; ++ps) {
                       const int R = q * 32 + ps * 4 + rr;
@@ -592,6 +599,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                       const int R = q * 32 + ps * 4 + rr;
                       roff[ps] = R < c.rows_valid ? c.row0 + R : -1;
                   }
+                  if (row_ok) myrow = c.row0 + r;
                   if (bias && p.bias_crop_stride) {
                       // clamped to the last crop: the warp's 32 rows may lie entirely in the masked tail of the last M tile
                       // (M = 3000: rows 3040..3071), and its bias vector is loaded before the row masks are looked at -- one
@@ -620,6 +628,10 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const bool simple = first_run && last_run && !p.residual && !straddle;
             mbar_wait(acc_full + ab, (ti >> acc_shift) & 1);
             tc_fence_after();
+            if (last_run && !first_run) {                      // the partial sums were written / added by OTHER lanes of this warp
+                __threadfence();
+                __syncwarp();
+            }
 #pragma unroll 1
             for (int ch = half; ch < nchunks; ch += 2) {
                 uint32_t v[32];
@@ -636,6 +648,25 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (run_scale != 1.0f) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * run_scale);
+                }
+                if (!last_run && !p.pool_partial) {
+                    // Partial sum of an intermediate run, straight from the registers (lane == row, 32 consecutive columns = one
+                    // 128-byte line per lane): the first run is stored, the following ones are ADDED in L2 (red.global: no read round
+                    // trip, no transpose) -- one thread per element in run order, so the sum is deterministic and, fp32 addition being
+                    // commutative, the same as read-add-write.  Only the last run takes the full path below (the wide tiles have ONE
+                    // accumulator: measured before this, the MMA issuer waited 43% of layer4.0 for the drains of its four runs).
+                    if (myrow >= 0) {
+                        float* dst = reinterpret_cast<float*>(reinterpret_cast<char*>(Cg + col) + (unsigned long long)(uint32_t)myrow * ldcb);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (col + j * 4 >= p.N) break;
+                            const float4 o = make_float4(__uint_as_float(v[j * 4]), __uint_as_float(v[j * 4 + 1]), __uint_as_float(v[j * 4 + 2]),
+                                                         __uint_as_float(v[j * 4 + 3]));
+                            if (first_run) *reinterpret_cast<float4*>(dst + j * 4) = o;
+                            else red_add_v4(dst + j * 4, o);
+                        }
+                    }
+                    continue;
                 }
                 if (p.pool_partial) {
                     float f[32];
@@ -673,32 +704,43 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             else if (p.relu == 2) epi_store_simple<2>(srow, sw0, sw1, cbase, ldcb, roff, b0, slope);
                             else epi_store_simple<0>(srow, sw0, sw1, cbase, ldcb, roff, b0, slope);
                         } else {
-                            const char* rbase = p.residual ? reinterpret_cast<const char*>(p.residual + cq) : nullptr;
+                            // general store: the sum of the earlier runs of this tile comes back from C (written by this very thread)
+                            // in the LAST run only, the skip connection from the residual tensor.  All loads of four rows are issued before the first store:
+                            // left in program order every C read waited for the store before it (the compiler cannot prove
+                            // the rows distinct), one L2 round trip per row -- 8 x 4 per 256-wide run, which the single accumulator of
+                            // the wide tiles exposes in full (measured: the MMA issuer waited 43% of layer4.0 on acc_empty).
+                            const char* rbase = (p.residual && last_run) ? reinterpret_cast<const char*>(p.residual + cq) : nullptr;
 #pragma unroll
-                            for (int ps = 0; ps < 8; ++ps) {
-                                if (roff[ps] < 0) continue;
-                                float4 o = *reinterpret_cast<const float4*>(srow + ps * 128 + ((ps & 1) ? sw1 : sw0));
-                                float* dst = reinterpret_cast<float*>(cbase + (unsigned long long)(uint32_t)roff[ps] * ldcb);
-                                if (!first_run) {                          // earlier runs of this tile, written by this very thread
-                                    const float4 prev = *reinterpret_cast<const float4*>(dst);
-                                    o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
+                            for (int pb = 0; pb < 8; pb += 4) {
+                                float4 prev[4], resv[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const int ps = pb + i;
+                                    prev[i] = make_float4(0.f, 0.f, 0.f, 0.f); resv[i] = prev[i];
+                                    if (roff[ps] < 0) continue;
+                                    if (!first_run) prev[i] = __ldcg(reinterpret_cast<const float4*>(cbase + (unsigned long long)(uint32_t)roff[ps] * ldcb));   // (L2: where the adds happened)
+                                    if (rbase) resv[i] = __ldg(reinterpret_cast<const float4*>(rbase + (unsigned long long)(uint32_t)roff[ps] * ldrb));
                                 }
-                                if (!last_run) { *reinterpret_cast<float4*>(dst) = o; continue; }
-                                if (bias) {
-                                    const float4 bv = roff[ps] >= crop_boundary ? b1 : b0;
-                                    o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const int ps = pb + i;
+                                    if (roff[ps] < 0) continue;
+                                    float4 o = *reinterpret_cast<const float4*>(srow + ps * 128 + ((ps & 1) ? sw1 : sw0));
+                                    float* dst = reinterpret_cast<float*>(cbase + (unsigned long long)(uint32_t)roff[ps] * ldcb);
+                                    o.x += prev[i].x; o.y += prev[i].y; o.z += prev[i].z; o.w += prev[i].w;
+                                    if (bias) {
+                                        const float4 bv = roff[ps] >= crop_boundary ? b1 : b0;
+                                        o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                                    }
+                                    o.x += resv[i].x; o.y += resv[i].y; o.z += resv[i].z; o.w += resv[i].w;
+                                    if (p.relu == 1) {
+                                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                                    } else if (p.relu == 2) {
+                                        o.x = o.x > 0.f ? o.x : slope * o.x; o.y = o.y > 0.f ? o.y : slope * o.y;
+                                        o.z = o.z > 0.f ? o.z : slope * o.z; o.w = o.w > 0.f ? o.w : slope * o.w;
+                                    }
+                                    *reinterpret_cast<float4*>(dst) = o;
                                 }
-                                if (rbase) {
-                                    const float4 rv = __ldg(reinterpret_cast<const float4*>(rbase + (unsigned long long)(uint32_t)roff[ps] * ldrb));
-                                    o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
-                                }
-                                if (p.relu == 1) {
-                                    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                                } else if (p.relu == 2) {
-                                    o.x = o.x > 0.f ? o.x : slope * o.x; o.y = o.y > 0.f ? o.y : slope * o.y;
-                                    o.z = o.z > 0.f ? o.z : slope * o.z; o.w = o.w > 0.f ? o.w : slope * o.w;
-                                }
-                                *reinterpret_cast<float4*>(dst) = o;
                             }
                         }
                     }

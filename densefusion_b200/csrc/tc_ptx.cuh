@@ -246,4 +246,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
     return r;
 }
 
+// fire-and-forget vector add in L2 (sm_90+): *p += v, 16-byte aligned
+__device__ __forceinline__ void red_add_v4(float* p, float4 v)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 }  // namespace df_tc

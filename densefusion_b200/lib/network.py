@@ -7,10 +7,11 @@ engine), not as ~60 cuDNN / cuBLAS calls.
 
 Additive API (not in the reference): `forward_batched` evaluates every crop of the batch (the reference returns batch
 element 0 only, lib/network.py:123-126) and the attribute `precision` selects the GEMM arithmetic:
-    "hybrid16" (default)  tcgen05, fp16 main term + bf16 correction terms, fp32 accumulate: fp32 parity (<= 1e-4 on poses,
-                          measured 2-3e-5) for operands inside fp16's range; "hybrid" / "3xtf32": the same bound with no
-                          range restriction; "tf32": single pass, stated looser bound; "fp32": exact FFMA kernels and the
-                          torch/cuDNN strict-fp32 encoder (parity-check mode).
+    "hybrid16s" (default) tcgen05, both operands as two fp16 planes with power-of-two scales (weights: from the tensor's maximum
+                          at pack time, activations: sampled by the kernel), fp32 accumulate: fp32 parity (<= 1e-4 on poses,
+                          measured 4e-5) at any operand magnitude; "hybrid16" (fp16 main term + bf16 correction terms: parity
+                          inside fp16's range), "hybrid" / "3xtf32": the same bound, more tensor work; "tf32": single pass, stated
+                          looser bound; "fp32": exact FFMA kernels and the torch/cuDNN strict-fp32 encoder (parity-check mode).
 Inference (eval() mode, no autograd) with a tensor-core precision uses densefusion_b200.encoder; a train()-mode module keeps
 the module graph of lib/pspnet.py (Dropout2d active) with its convolutions on lib/conv_tc.py.
 
@@ -82,7 +83,7 @@ def _no_autograd(module: nn.Module, *inputs):
 
 
 class _PackedMixin:
-    precision = "hybrid16"
+    precision = "hybrid16s"
 
     def _packed(self, cls):
         ver = engine.param_version(self)

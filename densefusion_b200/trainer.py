@@ -186,7 +186,7 @@ class DataParallelTrainer:
 
     def __init__(self, estimator, refiner, num_points_mesh: int, sym_list: Sequence[int], lr: float = 1e-4,
                  w: float = 0.015, iteration: int = 2, phase: str = "estimator", group=None,
-                 frozen_precision: str = "hybrid16", overlap: Optional[bool] = None):
+                 frozen_precision: str = "hybrid16s", overlap: Optional[bool] = None):
         from .lib.loss import Loss
         from .lib.loss_refiner import Loss_refine
         self.estimator, self.refiner = estimator, refiner
