@@ -127,8 +127,9 @@ class PackedEncoder:
         ldx = x.stride(2) if ldx is None else ldx
         cout = out.shape[3] if cout is None else cout
         ldy = out.stride(2) if ldy is None else ldy
-        if mode >= 3 and cout <= 64 and _NARROW_ON_3XTF32:
-            mode = 1        # 64-wide tiles are paced by the A stagers, where the hybrid split costs more (measured +9%)
+        if mode in (3, 4) and cout <= 64 and _NARROW_ON_3XTF32:
+            mode = 1        # 64-wide tiles are paced by the A stagers, where the hybrid split costs more (measured +9%); not so in
+                            # hybrid16s (cheaper split, four TMEM A stages: the 64-channel layers are 15-20% faster than in 3xtf32)
         hi, lo = w.operands(mode)
         check(lib.df_conv_tc(ptr(x), b, h, wd, cin, ldx, ptr(hi), ptr(lo), taps, dil, ptr(bias), ptr(residual),
                              0 if residual is None else residual.stride(2), ptr(prelu), act, ptr(out), ldy, cout, mode,
