@@ -214,8 +214,13 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                  const int n_tiles, const int total_tiles)
 {
     // A_STAGES TMEM A stages of A_COLS columns each at the top of TMEM (64: [hi | lo] / [fp16 | - | bf16 | bf16 lo]; 32: the two
-    // fp16 planes of hybrid16s, the only arithmetic that instantiation carries); the accumulators share what is left below
-    constexpr bool S16 = A_COLS == 32;
+    // fp16 planes of hybrid16s, the only arithmetic that instantiation carries); the accumulators share what is left below.
+    // A_COLS == 0 (hybrid16s, "A_SMEM"): the two fp16 planes of A go to a shared-memory ring of A_STAGES 16 KB tiles in the MMA's
+    // K-major 128B-swizzled layout instead (rows of [hi x32 | lo x32], like the weight tile) and the MMA reads both operands from
+    // shared memory -- all 512 TMEM columns are then accumulators: TWO buffers of up to 256 columns, so that the drain of a 256-wide tile
+    // (one accumulator with A in TMEM: exposed, ~20% of the pooled conv6 layer, ~12% of the long-K convolutions) overlaps the next run.
+    constexpr bool A_SMEM = A_COLS == 0;
+    constexpr bool S16 = A_COLS == 32 || A_SMEM;
     constexpr int TMEM_A0 = 512 - A_STAGES * A_COLS;
     constexpr int ACC_STRIDE = TMEM_A0 / 2;
     extern __shared__ uint8_t smem_raw[];
@@ -240,7 +245,11 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint32_t w_bytes = (uint32_t)bn_cta * BK * 4;
     // A | W_hi | W_lo (or the bf16 pair tile), all 1024-B aligned; hybrid16s: A | [fp16 hi x32 | fp16 lo x32] rows
     const uint32_t stage_bytes = S16 ? Q_TILE + w_bytes : Q_TILE + 2 * w_bytes;
-    const int Q_STAGES = (int)min((uint32_t)Q_MAX_STAGES, (uint32_t)Q_SMEM_STAGES / stage_bytes);
+    // (the pooled epilogue keeps its per-warp column sums in the last 8 KB of the stage area: one stage less when the ring fills it)
+    const uint32_t pool_bytes = p.pool_partial ? 8192u : 0u;
+    const uint32_t aring_bytes = A_SMEM ? (uint32_t)A_STAGES * Q_TILE : 0u;
+    const int Q_STAGES = (int)min((uint32_t)Q_MAX_STAGES, ((uint32_t)Q_SMEM_STAGES - pool_bytes - aring_bytes) / stage_bytes);
+    uint8_t* const aring = smem + (size_t)Q_STAGES * stage_bytes;           // A_SMEM: the operand-plane ring of A (1024-byte aligned)
     const uint32_t ACC_BUFS = bnt <= ACC_STRIDE ? 2 : 1;
     const uint32_t acc_shift = ACC_BUFS - 1;        // ti % ACC_BUFS == ti & acc_shift, ti / ACC_BUFS == ti >> acc_shift
 
@@ -377,7 +386,19 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         const uint32_t w_hi = smem_u32(smem + (size_t)s * stage_bytes + Q_TILE);
                         const uint64_t bhi0 = sw128_desc(w_hi), blo0 = sw128_desc(w_hi + w_bytes);
                         const uint32_t a0 = tmem_base + TMEM_A0 + (it % A_STAGES) * A_COLS;
-                        if (S16) {
+                        if (A_SMEM) {
+                            // hybrid16s with A in shared memory: rows [fp16(a) x32 | fp16(a - fp16(a)) x32], same layout as the weight tile
+                            const uint64_t ad0 = sw128_desc(smem_u32(aring + (size_t)(it % A_STAGES) * Q_TILE));
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const uint64_t b_h = bhi0 + (uint64_t)(j * 2), b_l = bhi0 + (uint64_t)(4 + j * 2);
+                                const uint64_t a_h = ad0 + (uint64_t)(j * 2), a_l = ad0 + (uint64_t)(4 + j * 2);
+                                const uint32_t acc_on = (kb != kb0) || (j != 0);
+                                umma_ss_f16_pair(acc, a_h, b_h, idesc_h, acc_on);
+                                umma_ss_f16_pair(acc, a_l, b_h, idesc_h, 1u);
+                                umma_ss_f16_pair(acc, a_h, b_l, idesc_h, 1u);
+                            }
+                        } else if (S16) {
                             // hybrid16s: every term on fp16 operands.  TMEM A stage: [0,16) fp16(a) pairs | [16,32) fp16(a - fp16(a));
                             // weight tile rows: 64 B of fp16(w) then 64 B of fp16(w - fp16(w)) (descriptor +4 = +64 B).
 #pragma unroll
@@ -530,15 +551,25 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             // implied by full[s] (the commit that frees the slot is what let the TMA refill the stage); with fewer TMEM slots wait
             // for that iteration's commit explicitly (same barrier the TMA producer watches; the loads and the split above overlap it).
             if (sp >= 0 && A_STAGES < Q_STAGES) mbar_wait(empty + sp, php);
-            tc_fence_after();
-            const uint32_t ta = tmem_base + lane_base + TMEM_A0 + (it % A_STAGES) * A_COLS;
-            if (S16) tmem_st32(ta, second);
-            else {
-                tmem_st32(ta, hi);
-                if (p.precise) tmem_st32(ta + BK, second);
+            if (A_SMEM) {
+                uint8_t* prow = aring + (size_t)(it % A_STAGES) * Q_TILE + r * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<uint4*>(prow + ((c ^ sw) << 4)) = make_uint4(second[c * 4], second[c * 4 + 1], second[c * 4 + 2], second[c * 4 + 3]);
+                // generic-proxy writes -> visible to the MMAs (async proxy).  The shared::cta form on purpose: the unqualified
+                // fence.proxy.async costs a MEMBAR.ALL.GPU per k-block (measured in round 2: tower-1 0.56 ms instead of 0.30)
+                fence_proxy_async();
+            } else {
+                tc_fence_after();
+                const uint32_t ta = tmem_base + lane_base + TMEM_A0 + (it % A_STAGES) * A_COLS;
+                if (S16) tmem_st32(ta, second);
+                else {
+                    tmem_st32(ta, hi);
+                    if (p.precise) tmem_st32(ta + BK, second);
+                }
+                tmem_st_wait();
+                tc_fence_before();
             }
-            tmem_st_wait();
-            tc_fence_before();
             __syncwarp();
             if (lane == 0) {
                 if (CTAS == 2) mbar_arrive_remote(a_full + s, 0); else mbar_arrive(a_full + s);
@@ -612,13 +643,13 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                   }
               }
           } else if (bias && p.bias_crop_stride) {
-              bias += (size_t)((row_ok ? c.row0 + r : 0) / p.rows_per_crop) * p.bias_crop_stride;
+              bias += (size_t)c.crop * p.bias_crop_stride;          // pooled tiles are crop-aligned: one bias row per tile
           }
           float* const Cg = p.C + c.g * p.c_gs;
           for (int kc = 0; kc < runs; ++kc, ++ti) {
             const bool first_run = kc == 0, last_run = kc == runs - 1;
             const uint32_t ab = ti & acc_shift;
-            float* pool = s_epi + (ti & 1) * 4 * 256;          // aliases the transpose tiles (never both in one launch)
+            float* pool = reinterpret_cast<float*>(smem + Q_SMEM_STAGES - 8192) + (ti & 1) * 4 * 256;      // [2][4 lane quarters][256 columns]
             float run_scale = w_inv;
             if (p.bias_comp != 0.0f) {
                 const int n_kb = min(nkb_t, (kc + 1) * p.kbc) - kc * p.kbc;
@@ -640,7 +671,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 // this lane's 4 bias values (requested before the accumulator is read: the L2 round trip overlaps the TMEM load and the
                 // transpose): one vector, or two when the warp's 32 rows straddle a crop boundary
                 float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-                if (!p.pool_partial && bias && last_run && cq < p.N) {
+                if (bias && last_run && cq < p.N) {
                     b0 = __ldg(reinterpret_cast<const float4*>(bias + cq));
                     if (straddle) b1 = __ldg(reinterpret_cast<const float4*>(bias + p.bias_crop_stride + cq));
                 }
@@ -669,25 +700,32 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     continue;
                 }
                 if (p.pool_partial) {
-                    float f[32];
+                    // column sums of act(x + bias) over this warp's 32 rows: through the same swizzled transpose as the store path
+                    // (lane (rr, cc) then owns 4 columns of rows ps*4 + rr: 8 adds per column and two shuffle stages across rr, instead
+                    // of a 31-shuffle butterfly over registers + 32 scalar bias loads per lane -- the pooled drain was 11.8 k clocks
+                    // per tile against 16.6 k of main loop on a tile that has only one accumulator)
+                    __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float x = __uint_as_float(v[i]);
-                        if (bias && col + i < p.N) x += __ldg(bias + col + i);
-                        if (p.relu) x = fmaxf(x, 0.0f);
-                        f[i] = row_ok ? x : 0.0f;
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                            make_uint4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+                    __syncwarp();
+                    const int lim = c.rows_valid - (q * 32 + rr);        // row ps*4 + rr of this warp is real iff ps*4 < lim
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int ps = 0; ps < 8; ++ps) {
+                        if (ps * 4 >= lim) continue;
+                        float4 o = *reinterpret_cast<const float4*>(srow + ps * 128 + ((ps & 1) ? sw1 : sw0));
+                        o.x += b0.x; o.y += b0.y; o.z += b0.z; o.w += b0.w;
+                        if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
                     }
 #pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) {
-                        const bool up = (lane & off) != 0;
-#pragma unroll
-                        for (int i = 0; i < off; ++i) {
-                            const float send = up ? f[i] : f[i + off];
-                            const float keep = up ? f[i + off] : f[i];
-                            f[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                        }
+                    for (int off = 8; off <= 16; off <<= 1) {
+                        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+                        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
                     }
-                    pool[q * 256 + ch * 32 + lane] = f[0];
+                    if (rr == 0) *reinterpret_cast<float4*>(pool + q * 256 + ch * 32 + cc * 4) = acc;
                 } else {
                     // transpose through a swizzled 32x32 tile: lane == row on the way in, 8 lanes == one 128 B row out;
                     // bias / skip connection / activation are applied on the way out (coalesced float4 accesses)
@@ -849,13 +887,45 @@ bool make_map_nhwc(CUtensorMap* map, const float* base, int B, int H, int W, int
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Tile width of the CTA-pair kernel.  Grouped layers must not straddle groups; otherwise a tail tile is masked.  Widths up to
+// `acc_stride` keep two accumulators in TMEM (stores overlap the next tile); a wider one (256 with A in TMEM) only when nothing is
+// stored (pooled epilogue) or the k loop is long.  Among the admissible widths take the one with the least work after wave
+// quantisation (+32: fixed cost per tile).  Returns 0 when no width fits.
+int pair_tile_width(const TcParams& p, int groups, int m_tiles, int acc_stride, int max_clusters)
+{
+    const int widths[4] = {256, 192, 128, 64};
+    long long best = -1;
+    int width = 0;
+    for (int i = 0; i < 4; ++i) {
+        const int w = widths[i];
+        // 256-wide tiles leave room for ONE accumulator next to TMEM A stages: always fine for the store-free pooled epilogue; with
+        // stores the epilogue of a tile is exposed, which only pays once the k loop is long (>= 32 k-blocks: layer4 convolutions
+        // -15..17%, pose step +2.7%, profiles/r2_c4_ab_wide.jsonl; DF_TC_WIDE_KB overrides the threshold, 0 = never)
+        static const int wide_kb = getenv("DF_TC_WIDE_KB") ? atoi(getenv("DF_TC_WIDE_KB")) : 32;
+        if (w == 256 && acc_stride < 256 && !p.pool_partial && !(wide_kb > 0 && p.K / BK >= wide_kb)) continue;
+        if (w == 192 && acc_stride < 192) continue;
+        if (w == 64 && p.N > 64) continue;                     // narrow layers only (64-channel decoder stages)
+        if (p.N % w != 0 && (groups > 1 || w == 256)) continue;
+        const long long tiles = (long long)m_tiles * ((p.N + w - 1) / w) * groups;
+        const long long cost = ((tiles + max_clusters - 1) / max_clusters) * (w + 32);
+        if (best < 0 || cost < best) { best = cost; width = w; }
+    }
+    return width;
+}
+
+int pair_m_tiles(const TcParams& p)
+{
+    return p.conv_taps ? (p.tiles_x * p.tiles_y * p.tiles_b + 1) / 2
+           : p.pool_partial ? (p.M / p.rows_per_crop) * ((p.rows_per_crop + 255) / 256) : (p.M + 255) / 256;
+}
+
 template <int CTAS, int A_STAGES, int A_COLS = 64>
 int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw, int groups, cudaStream_t s)
 {
-    static_assert(A_COLS == 64 || (A_COLS == 32 && CTAS == 2), "the 32-column A stage is the CTA-pair hybrid16s form");
+    static_assert(A_COLS == 64 || ((A_COLS == 32 || A_COLS == 0) && CTAS == 2), "the 32-column / shared-memory A stages are CTA-pair hybrid16s forms");
     constexpr int THREADS = Q_THREADS;
     constexpr int ACC_STRIDE = (512 - A_STAGES * A_COLS) / 2;
-    if ((A_COLS == 32) != (p_in.precise == 4)) return DF_ERR_ARG;
+    if ((A_COLS != 64) != (p_in.precise == 4)) return DF_ERR_ARG;
     TcParams p = p_in;
     {
         static int order = -1;
@@ -912,9 +982,6 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
         }
         max_clusters = n;
     }
-    // Tile width.  Grouped layers must not straddle groups; otherwise a tail tile is masked.  Pairs: 192 or 128 keep two
-    // accumulators in TMEM (stores overlap the next tile); 256 only when nothing is stored (pooled epilogue).  Among the
-    // admissible widths take the one with the least work after wave quantisation (+32: fixed cost per tile).
     int bn_cta = 0;
     const int rows_per_mtile = 128 * CTAS;
     const int m_tiles = p.conv_taps ? (p.tiles_x * p.tiles_y * p.tiles_b + CTAS - 1) / CTAS
@@ -926,22 +993,7 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
     } else if (p.wk_rows) {
         bn_cta = 64;                                               // every CTA's half tile stays inside one tap (wk_rows % 64 == 0)
     } else {
-        const int widths[4] = {256, 192, 128, 64};
-        long long best = -1;
-        for (int i = 0; i < 4; ++i) {
-            const int w = widths[i];
-            // 256-wide tiles leave room for ONE accumulator: always fine for the store-free pooled epilogue; with stores the
-            // epilogue of a tile is exposed, which only pays once the k loop is long (>= 32 k-blocks: layer4 convolutions -15..17%,
-            // pose step +2.7%, profiles/r2_c4_ab_wide.jsonl; DF_TC_WIDE_KB overrides the threshold, 0 = never)
-            static const int wide_kb = getenv("DF_TC_WIDE_KB") ? atoi(getenv("DF_TC_WIDE_KB")) : 32;
-            if (w == 256 && !p.pool_partial && !(wide_kb > 0 && p.K / BK >= wide_kb)) continue;
-            if (w == 192 && ACC_STRIDE < 192) continue;
-            if (w == 64 && p.N > 64) continue;                     // narrow layers only (64-channel decoder stages)
-            if (p.N % w != 0 && (groups > 1 || w == 256)) continue;
-            const long long tiles = (long long)m_tiles * ((p.N + w - 1) / w) * groups;
-            const long long cost = ((tiles + max_clusters - 1) / max_clusters) * (w + 32);
-            if (best < 0 || cost < best) { best = cost; bn_cta = w / 2; }
-        }
+        bn_cta = pair_tile_width(p, groups, m_tiles, ACC_STRIDE, max_clusters) / 2;
         if (!bn_cta) return DF_ERR_UNSUPPORTED;
     }
     const int bnt = bn_cta * CTAS;
@@ -995,6 +1047,24 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict
     const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
     hi[i] = h;
     lo[i] = v - h;
+}
+
+// hybrid16s: which launches keep the A planes in shared memory (two 256-column accumulators) instead of TMEM (four A stages, accumulators
+// of up to 192 columns double-buffered, 256 single).  DF_TC_A_SMEM = 0 never, 1 always, unset: the shapes that run on 256-wide tiles.
+bool s16_a_in_smem(const TcParams& p, int groups)
+{
+    static const int mode = getenv("DF_TC_A_SMEM") ? atoi(getenv("DF_TC_A_SMEM")) : 2;
+    if (mode != 2) return mode == 1;
+    // measured per shape (profiles/r2j_gemm_ab_asmem*.jsonl): the shared-memory A ring wins where it buys the second 256-column
+    // accumulator (conv6 pooled -13%, conv5 -14%, tower-2 -10%, layer4 -6%) and loses 6-8% on narrower tiles (more shared-memory traffic)
+    static int clusters = 0;
+    if (!clusters) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        clusters = sms / 2;
+    }
+    return !p.wk_rows && pair_tile_width(p, groups, pair_m_tiles(p), 256, clusters) == 256;
 }
 
 // DF_TC_PDL=0 turns programmatic dependent launch off (A/B timing runs)
@@ -1377,7 +1447,8 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
     int rc;
     if (precision == 6) {                 // hybrid16s: two fp16 planes per operand, 32-column TMEM A stages: CTA-pair kernel only
         if (variant != 0 && variant != 6) return DF_ERR_UNSUPPORTED;
-        rc = launch_q<2, 4, 32>(p, W_hi, W_hi, ldw, groups, (cudaStream_t)stream);
+        rc = s16_a_in_smem(p, groups) ? launch_q<2, 3, 0>(p, W_hi, W_hi, ldw, groups, (cudaStream_t)stream)
+                                      : launch_q<2, 4, 32>(p, W_hi, W_hi, ldw, groups, (cudaStream_t)stream);
     } else if (v == 5) rc = launch_q<1, 4>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream);
     else if (v == 6) rc = launch_q<2, 2>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream);
     else if (v == 7) rc = launch_q<2, 4>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream);
@@ -1470,7 +1541,8 @@ extern "C" int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx,
     p.conv_taps = taps; p.conv_dil = dilation; p.cW = W; p.cH = H; p.cB = B;
     p.residual = residual; p.ldr = ldr; p.prelu = prelu;
     conv_patch_plan(p, B, H, W, taps, dilation);
-    const int rc = precision == 6 ? launch_q<2, 4, 32>(p, W_hi, W_hi, taps * Cin, 1, (cudaStream_t)stream)
+    const int rc = precision == 6 ? (s16_a_in_smem(p, 1) ? launch_q<2, 3, 0>(p, W_hi, W_hi, taps * Cin, 1, (cudaStream_t)stream)
+                                                         : launch_q<2, 4, 32>(p, W_hi, W_hi, taps * Cin, 1, (cudaStream_t)stream))
                                   : launch_q<2, 2>(p, W_hi, W_lo, taps * Cin, 1, (cudaStream_t)stream);
     if (rc) return rc;
     DF_RETURN_LAST_ERROR();

@@ -217,6 +217,13 @@ __device__ __forceinline__ void umma_ts_bf16_pair(uint32_t d, uint32_t a_tmem, u
                  "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                  ::"r"(d), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
+// D[tmem, both CTAs] (+)= A[smem desc, 128 rows per CTA] . B[smem desc, N/2 rows per CTA]^T, 16-bit operands
+__device__ __forceinline__ void umma_ss_f16_pair(uint32_t d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ uint32_t bf16_instr_desc(int n, int m = 128)
 {
     // c_format F32 (1) @4, a/b format BF16 (1) @7/@10, K-major both, N>>3 @17, M>>4 @24
