@@ -61,6 +61,8 @@ struct TcParams {
     // samp_rows x samp_cols addressable; see "activation scale" in the kernel), so it follows the data without a host round trip.
     const float* w_inv_scale; float a_scale;
     long long samp_rows; int samp_cols;
+    int dbg;                                    // DF_TC_DBG knock-out bits (timing experiments only; results are wrong): 1 no global stores,
+                                                // 2 no transpose, 4 no TMEM load, 8 no MMAs
     int run_steps;                              // host side only: MMA instructions per accumulation run, 0 = default
     // ---- weight-gradient form (df_conv_wgrad_tc): output column n = tap * wk_rows + ci multiplies row ci of the W operand
     // read wk_shift[tap] elements further along k (a 3x3 tap is an offset in the zero-padded, flattened pixel axis) ----
@@ -250,6 +252,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint32_t aring_bytes = A_SMEM ? (uint32_t)A_STAGES * Q_TILE : 0u;
     const int Q_STAGES = (int)min((uint32_t)Q_MAX_STAGES, ((uint32_t)Q_SMEM_STAGES - pool_bytes - aring_bytes) / stage_bytes);
     uint8_t* const aring = smem + (size_t)Q_STAGES * stage_bytes;           // A_SMEM: the operand-plane ring of A (1024-byte aligned)
+    const int t_first = cid, t_step = ncl;                                  // tile walk of this cluster: round robin over all tiles
     const uint32_t ACC_BUFS = bnt <= ACC_STRIDE ? 2 : 1;
     const uint32_t acc_shift = ACC_BUFS - 1;        // ti % ACC_BUFS == ti & acc_shift, ti / ACC_BUFS == ti >> acc_shift
 
@@ -316,7 +319,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int cblocks = p.conv_taps ? p.K / (BK * p.conv_taps) : 1;        // 32-channel blocks per tap
         int s = 0;
         uint32_t ph = 1;                                                       // parity of "slot is free": passes at once in round 0
-        for (int t = cid; t < total_tiles; t += ncl) {
+        for (int t = t_first; t < total_tiles; t += t_step) {
             const QTile c = q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, rank);
             int wrow = c.g * p.N + c.n0 + rank * bn_cta;
             int wk0 = 0;                                                       // k offset of the W operand (weight-gradient form)
@@ -369,7 +372,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             int s = 0;
             uint32_t ph = 0;
             const int cblocks = p.conv_taps ? p.K / (BK * p.conv_taps) : 1;
-            for (int t = cid; t < total_tiles; t += ncl) {
+            for (int t = t_first; t < total_tiles; t += t_step) {
               const int nkb_t = p.conv_taps == 9 ? __popc(q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, 0).taps) * cblocks : nkb;
               const int runs = (nkb_t + p.kbc - 1) / p.kbc;
               for (int kc = 0; kc < runs; ++kc, ++ti) {
@@ -386,7 +389,8 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         const uint32_t w_hi = smem_u32(smem + (size_t)s * stage_bytes + Q_TILE);
                         const uint64_t bhi0 = sw128_desc(w_hi), blo0 = sw128_desc(w_hi + w_bytes);
                         const uint32_t a0 = tmem_base + TMEM_A0 + (it % A_STAGES) * A_COLS;
-                        if (A_SMEM) {
+                        if (p.dbg & 8) {
+                        } else if (A_SMEM) {
                             // hybrid16s with A in shared memory: rows [fp16(a) x32 | fp16(a - fp16(a)) x32], same layout as the weight tile
                             const uint64_t ad0 = sw128_desc(smem_u32(aring + (size_t)(it % A_STAGES) * Q_TILE));
 #pragma unroll
@@ -444,7 +448,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             }
                         }
                         }
-                        if (!S16 && p.precise == 2) {
+                        if (!S16 && p.precise == 2 && !(p.dbg & 8)) {
                             // hybrid: the two correction terms are ~2^-11 of the main one, so bf16 operands (K = 16 per
                             // instruction, twice the TF32 rate) keep them to 2^-20 of the result: 4 + 4 instructions per
                             // k-block instead of 12.  TMEM A stage: [0,32) tf32 hi | [32,48) bf16(a) pairs | [48,64) bf16(a_lo);
@@ -477,12 +481,12 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
     } else if (warp < 10) {
         // ------------------------------- A stagers (two groups) ----------------------
-        const int my_tiles = (total_tiles - cid + ncl - 1) / ncl;
+        const int my_tiles = (total_tiles - t_first + t_step - 1) / t_step;
         uint32_t total_it = (uint32_t)my_tiles * nkb;
         if (p.conv_taps == 9) {                                          // tiles near the border visit fewer taps
             const int cblocks = p.K / (BK * 9);
             total_it = 0;
-            for (int t = cid + lane * ncl; t < total_tiles; t += 32 * ncl)
+            for (int t = t_first + lane * t_step; t < total_tiles; t += 32 * t_step)
                 total_it += __popc(q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, 0).taps) * cblocks;
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) total_it += __shfl_xor_sync(0xffffffffu, total_it, off);
@@ -595,7 +599,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const float w_inv = S16 ? __ldg(p.w_inv_scale) / a_sc : 1.0f;          // (powers of two: exact)
         const int per_kb = p.precise == 1 ? 12 : (p.precise == 2 ? 8 : (p.precise >= 3 ? 6 : 4));
         uint32_t ti = 0;
-        for (int t = cid; t < total_tiles; t += ncl) {
+        for (int t = t_first; t < total_tiles; t += t_step) {
           const QTile c = q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, rank);
           const int nkb_t = p.conv_taps == 9 ? __popc(c.taps) * (p.K / (BK * 9)) : nkb;
           const int runs = p.conv_taps == 9 ? (nkb_t + p.kbc - 1) / p.kbc : p.k_chunks;
@@ -675,6 +679,10 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     b0 = __ldg(reinterpret_cast<const float4*>(bias + cq));
                     if (straddle) b1 = __ldg(reinterpret_cast<const float4*>(bias + p.bias_crop_stride + cq));
                 }
+                if (p.dbg & 4) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0u;
+                } else
                 tmem_ld32(tmem_base + lane_base + ab * ACC_STRIDE + ch * 32, v);
                 if (run_scale != 1.0f) {
 #pragma unroll
@@ -730,12 +738,14 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     // transpose through a swizzled 32x32 tile: lane == row on the way in, 8 lanes == one 128 B row out;
                     // bias / skip connection / activation are applied on the way out (coalesced float4 accesses)
                     __syncwarp();
+                    if (!(p.dbg & 2)) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         *reinterpret_cast<uint4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) =
                             make_uint4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+                    }
                     __syncwarp();
-                    if (cq < p.N) {
+                    if (cq < p.N && !(p.dbg & 1)) {
                         char* cbase = reinterpret_cast<char*>(Cg + cq);
                         if (simple) {
                             if (p.relu == 1) epi_store_simple<1>(srow, sw0, sw1, cbase, ldcb, roff, b0, slope);
@@ -948,6 +958,8 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
             }
             p.bias_comp = p.precise == 4 ? comp[3] : p.precise == 3 ? comp[0] : (p.precise == 2 ? comp[1] : (p.precise == 1 ? comp[2] : 0.0f));
         }
+        static const int dbg = getenv("DF_TC_DBG") ? atoi(getenv("DF_TC_DBG")) : 0;
+        p.dbg = dbg;
         static const int env_steps = getenv("DF_TC_RUN_STEPS") ? atoi(getenv("DF_TC_RUN_STEPS")) : 216;
         const int run_steps = p.run_steps > 0 ? p.run_steps : env_steps;
         const int per_kb = p.precise == 1 ? 12 : (p.precise == 2 ? 8 : 6);
@@ -1027,6 +1039,10 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
     const int n_tiles = (p.N + bnt - 1) / bnt;
     const int total = m_tiles * n_tiles * groups;
     const int clusters = total < max_clusters ? total : max_clusters;
+    // (Round 2 also tried keeping the weight planes of one n-tile resident in shared memory per cluster, "teams" of clusters walking the
+    // m-tiles, for the short-K head layers: 16 instead of 28 KB per k-block through the port -- correct, and no faster (tower-1 0.28 vs
+    // 0.25 ms, K = 256: a tie): the knock-out runs of scripts/knockout_probe.py show the k loop at ~950 clocks per k-block with or without
+    // the weight bytes, i.e. not paced by the port alone.  Removed; DESIGN.md section 4 keeps the numbers.)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(clusters * CTAS); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = Q_SMEM_TOTAL; cfg.stream = s;
     cudaLaunchAttribute at[2];
