@@ -102,12 +102,13 @@ def _pack_now(weight: torch.Tensor, rotate: bool, mode: int):
     return hi, second
 
 
-def _launch(x, packed, bias, cout, taps, dil, mode):
+def _launch(x, packed, bias, cout, taps, dil, mode, act=0, residual=None):
+    """y = act(conv(x) + bias + residual): ReLU (act = 1) and the skip connection are epilogues of the convolution kernel."""
     b, cin, h, w = x.shape
     y = torch.empty(b, cout, h, w, device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
     hi, lo = packed
-    check(lib.df_conv_tc(ptr(x), b, h, w, cin, cin, ptr(hi), ptr(lo), taps, dil, ptr(bias), None, 0, None, 0, ptr(y), cout,
-                         cout, mode | ops.SHORT_RUNS, stream()), "df_conv_tc")
+    check(lib.df_conv_tc(ptr(x), b, h, w, cin, cin, ptr(hi), ptr(lo), taps, dil, ptr(bias), ptr(residual), cout if residual is not None else 0,
+                         None, act, ptr(y), cout, cout, mode | ops.SHORT_RUNS, stream()), "df_conv_tc")
     return y
 
 
@@ -124,22 +125,32 @@ def _wgrad_tc(x, dy, cout, cin, taps, dil):
 
 
 class ConvTCFn(torch.autograd.Function):
+    """y = act(conv(x, weight) + bias + residual), act = 0 | 1 (ReLU): the BasicBlock's `relu(conv2(.) + skip)` (lib/extractors.py:
+    57-70) is ONE kernel launch forward; backward masks dy with [y > 0] (own kernel) and hands the masked gradient to the skip input."""
+
     @staticmethod
-    def forward(ctx, x, weight, bias, dilation):
+    def forward(ctx, x, weight, bias, dilation, act=0, residual=None):
         x = _nhwc(x.detach().float())
         cout, cin, k, _ = weight.shape
         mode = ops.PRECISIONS[PRECISION]
         packed = _pack(weight, False, mode)
-        y = _launch(x, packed, None if bias is None else bias.detach().float().contiguous(), cout, k * k, dilation, mode)
-        ctx.save_for_backward(x, weight)
-        ctx.dilation, ctx.has_bias, ctx.mode = dilation, bias is not None, mode
+        res = None if residual is None else _nhwc(residual.detach().float())
+        y = _launch(x, packed, None if bias is None else bias.detach().float().contiguous(), cout, k * k, dilation, mode, act, res)
+        if act:
+            ctx.save_for_backward(x, weight, y)
+        else:
+            ctx.save_for_backward(x, weight)
+        ctx.dilation, ctx.has_bias, ctx.mode, ctx.act, ctx.has_res = dilation, bias is not None, mode, act, residual is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
+        from . import ew
+        x, weight = ctx.saved_tensors[:2]
         cout, cin, k, _ = weight.shape
         dy = _nhwc(dy.float())
+        if ctx.act:
+            dy = ew.relu_mask(dy, ctx.saved_tensors[2])
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             # data gradient = convolution of dy with the 180-degree rotated, in/out-transposed kernel
@@ -152,8 +163,10 @@ class ConvTCFn(torch.autograd.Function):
             dw = torch.ops.aten.convolution_backward(dy, x, weight, None, [1, 1], [pad, pad], [ctx.dilation, ctx.dilation],
                                                      False, [0, 0], 1, [False, True, False])[1]
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy.sum(dim=(0, 2, 3))
-        return dx, dw, db, None
+            from . import ew
+            db = ew.colsum(dy)
+        dres = dy if (ctx.has_res and ctx.needs_input_grad[5]) else None
+        return dx, dw, db, None, None, dres
 
 
 K_CONV1 = 192           # 3*7*7 = 147 im2col columns, zero-padded to a multiple of 64 (df_conv_wgrad_tc wants Cin % 64 == 0)
@@ -192,26 +205,35 @@ class ConvS2Fn(torch.autograd.Function):
         return w.permute(0, 2, 3, 1).reshape(cout, k * k * cin).contiguous()   # tap-major, channels fastest (as im2col_s2)
 
     @staticmethod
-    def forward(ctx, x, weight):
+    def forward(ctx, x, weight, act=0):
         cout, cin, k, _ = weight.shape
         b = x.shape[0]
         a, ho, wo = ConvS2Fn._patches(x, k)
         wm = ConvS2Fn._matrix(weight)
         y = torch.empty(b * ho * wo, cout, device=x.device, dtype=torch.float32)
         ops.gemm(a, ops.SplitWeight(wm), None, y, M=a.shape[0], N=cout, K=a.shape[1], lda=a.shape[1], ldw=a.shape[1], ldc=cout,
-                 relu=False, precision=PRECISION, short_runs=True)
-        ctx.save_for_backward(a, weight)
-        ctx.in_shape = tuple(x.shape)
+                 relu=bool(act), precision=PRECISION, short_runs=True)
+        if act:
+            ctx.save_for_backward(a, weight, y)
+        else:
+            ctx.save_for_backward(a, weight)
+        ctx.in_shape, ctx.act = tuple(x.shape), act
         _s2_sync(f"forward k={k} x={tuple(x.shape)}")
         return y.view(b, ho, wo, cout).permute(0, 3, 1, 2)                   # channels_last storage, NCHW shape
 
     @staticmethod
     def backward(ctx, dy):
-        a, weight = ctx.saved_tensors
+        a, weight = ctx.saved_tensors[:2]
         cout, cin, k, _ = weight.shape
         b, _, h, w = ctx.in_shape
         m, kk = a.shape
-        dy2 = dy.float().permute(0, 2, 3, 1).reshape(m, cout).contiguous()
+        dy2 = dy.float().permute(0, 2, 3, 1).reshape(m, cout)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        if ctx.act:                                                          # ReLU fused into the GEMM epilogue: mask with [y > 0]
+            masked = torch.empty_like(dy2)
+            check(lib.df_ew_relu_mask(ptr(dy2), ptr(ctx.saved_tensors[2]), ptr(masked), cout, cout, m, stream()), "df_ew_relu_mask")
+            dy2 = masked
         dx = dw = None
         if ctx.needs_input_grad[1]:
             n = int(lib.df_conv_wgrad_scratch_floats(1, 1, m, kk, cout, 1, 1))
@@ -233,7 +255,7 @@ class ConvS2Fn(torch.autograd.Function):
                 dxn[:, ::2, ::2, :] = da.view(b, (h - 1) // 2 + 1, (w - 1) // 2 + 1, cin)
             dx = dxn.permute(0, 3, 1, 2)
         _s2_sync(f"backward k={k} in={ctx.in_shape}")
-        return dx, dw
+        return dx, dw, None
 
 
 def eligible_s2(m: nn.Conv2d, x: torch.Tensor) -> bool:
@@ -260,9 +282,15 @@ def eligible(m: nn.Conv2d, x: torch.Tensor) -> bool:
             and m.padding == (m.dilation[0] * (m.kernel_size[0] // 2),) * 2 and m.dilation[0] == m.dilation[1])
 
 
-def conv2d(m: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
+def conv2d(m: nn.Conv2d, x: torch.Tensor, act: int = 0, residual: torch.Tensor = None) -> torch.Tensor:
+    """act(m(x) + residual), act = 0 | 1 (ReLU).  On the tensor-core training path the activation and the skip connection are
+    epilogues of the convolution kernel; anywhere else (inference through the module graph, CPU, ineligible shapes) the plain module
+    followed by the torch ops."""
     if eligible(m, x):
-        return ConvTCFn.apply(x, m.weight, m.bias, m.dilation[0])
-    if eligible_s2(m, x):
-        return ConvS2Fn.apply(x, m.weight)
-    return m(x)
+        return ConvTCFn.apply(x, m.weight, m.bias, m.dilation[0], act, residual)
+    if eligible_s2(m, x) and residual is None:
+        return ConvS2Fn.apply(x, m.weight, act)
+    y = m(x)
+    if residual is not None:
+        y = y + residual
+    return torch.relu(y) if act else y

@@ -1,8 +1,9 @@
-"""BN-free dilated ResNet-18 trunk of the colour encoder.
+"""BN-free dilated ResNet-18 trunk of the colour encoder (SURVEY.md section 8f row N1).
 
-Kept on torch/cuDNN by design (the encoder is not one of the four
-rewritten subsystems).  Parameter names and shapes match the reference's lib/extractors.py:78-129 so
-reference checkpoints load unchanged; the construction is table-driven rather than class-per-block."""
+Parameter names and shapes match the reference's lib/extractors.py:78-129 so reference checkpoints load unchanged; the
+construction is table-driven rather than class-per-block.  Inference runs on densefusion_b200.encoder; this module graph is
+the TRAINING path: its convolutions (with ReLU / skip-connection epilogues) go through lib/conv_tc.py, max pooling through
+lib/ew.py -- torch ops only as the fallback for CPU tensors / the strict-fp32 parity mode."""
 from __future__ import annotations
 
 import math
@@ -24,10 +25,10 @@ class ResidualPair(nn.Module):
         self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride=stride, bias=False)) if project else None
 
     def forward(self, x):
-        # conv2d(): tensor-core forward / data gradient in training, the plain module otherwise
+        # conv2d(): tensor-core forward / data gradient in training (ReLU and the skip connection as epilogues of the convolution
+        # kernel), the plain module + torch ops otherwise
         skip = x if self.downsample is None else conv2d(self.downsample[0], x)
-        y = conv2d(self.conv2, F.relu(conv2d(self.conv1, x)))
-        return F.relu(y + skip)
+        return conv2d(self.conv2, conv2d(self.conv1, x, act=1), act=1, residual=skip)
 
 
 # (name, width, stride of the first pair, dilation of the later pairs); the first pair of a stage is
@@ -54,7 +55,9 @@ class ResNet18Trunk(nn.Module):
         from . import conv_tc
         if conv_tc.ENABLED and x.is_cuda and torch.is_grad_enabled() and self.conv1.weight.requires_grad:
             x = x.contiguous(memory_format=torch.channels_last)     # NHWC storage for the tensor-core training convolutions
-        x = F.max_pool2d(F.relu(conv2d(self.conv1, x)), 3, stride=2, padding=1)
+        from . import ew
+        x = conv2d(self.conv1, x, act=1)
+        x = ew.MaxPoolFn.apply(x) if ew.usable(x) else F.max_pool2d(x, 3, stride=2, padding=1)
         x = self.layer2(self.layer1(x))
         mid = self.layer3(x)
         return self.layer4(mid), mid

@@ -1,5 +1,6 @@
-"""Pyramid-pooling decoder of the colour encoder (torch/cuDNN; see extractors.py for why it is not a
-hand-written kernel).  Parameter names / shapes follow lib/pspnet.py:7-77 of the reference."""
+"""Pyramid-pooling decoder of the colour encoder.  Parameter names / shapes follow lib/pspnet.py:7-77 of the reference.
+Inference runs on densefusion_b200.encoder; this module graph is the TRAINING path -- convolutions on lib/conv_tc.py, pooling /
+concat / PReLU / Dropout2d / log-softmax on lib/ew.py (own kernels), torch ops only as the CPU / strict-fp32 fallback."""
 from __future__ import annotations
 
 import torch
@@ -66,6 +67,13 @@ class PSPModule(nn.Module):
         self.bottleneck = nn.Conv2d(features * (len(sizes) + 1), out_features, 1)
 
     def forward(self, feats):
+        from . import ew
+        if ew.usable(feats) and self.sizes == (1, 2, 3, 6):
+            # training path on own kernels: the four adaptive pools in one pass, the concat written slice by slice (four resizes + one
+            # pitched copy), ReLU as the epilogue of the bottleneck convolution
+            pooled = ew.PyramidPoolFn.apply(feats)
+            ys = [conv2d(stage[1], p) for stage, p in zip(self.stages, pooled)]
+            return conv2d(self.bottleneck, ew.PyramidCatFn.apply(feats, *ys), act=1)
         hw = feats.shape[2:]
         pyramid = [_upsample(conv2d(stage[1], stage[0](feats)), hw, False) for stage in self.stages]
         return F.relu(conv2d(self.bottleneck, torch.cat(pyramid + [feats], 1)))
@@ -79,8 +87,10 @@ class PSPUpsample(nn.Module):
 
     def forward(self, x):
         # conv = [Upsample(x2, align_corners=True), Conv2d 3x3, PReLU]; indices kept for the checkpoint keys
+        from . import ew
         x = _upsample(x, (x.shape[2] * 2, x.shape[3] * 2), True)
-        return self.conv[2](conv2d(self.conv[1], x))
+        y = conv2d(self.conv[1], x)
+        return ew.PReLUFn.apply(y, self.conv[2].weight) if ew.usable(y) else self.conv[2](y)
 
 
 class PSPNet(nn.Module):
@@ -97,9 +107,17 @@ class PSPNet(nn.Module):
         # unused by the pose path but part of the reference checkpoints
         self.classifier = nn.Sequential(nn.Linear(deep_features_size, 256), nn.ReLU(), nn.Linear(256, n_classes))
 
+    def _drop(self, m: nn.Dropout2d, x):
+        from . import ew
+        if self.training and ew.usable(x):
+            return ew.Dropout2dFn.apply(x, m.p)
+        return m(x)
+
     def forward(self, x):
+        from . import ew
         f, _ = self.feats(x)
-        p = self.drop_1(self.psp(f))
-        p = self.drop_2(self.up_1(p))
-        p = self.drop_2(self.up_2(p))
-        return self.final[1](conv2d(self.final[0], self.up_3(p)))
+        p = self._drop(self.drop_1, self.psp(f))
+        p = self._drop(self.drop_2, self.up_1(p))
+        p = self._drop(self.drop_2, self.up_2(p))
+        y = conv2d(self.final[0], self.up_3(p))
+        return ew.LogSoftmax32Fn.apply(y) if (ew.usable(y) and y.shape[1] == 32) else self.final[1](y)

@@ -224,6 +224,32 @@ int df_enc_upsample(const float* in, int ldi, float* out, int ldo, int B, int hi
 int df_enc_upsample_backward(const float* gout, int ldo, float* gin, int ldi, int B, int hin, int win, int hout, int wout,
                              int C, int align_corners, void* stream);      /* gather form of the resize's transpose */
 int df_enc_log_softmax32(float* x, long long pixels, void* stream);
+
+/* ---- element-wise / pooling kernels of the encoder's TRAINING graph (autograd of lib/extractors.py:78-124, lib/pspnet.py:7-77) ----
+ * NHWC fp32 (torch channels_last storage), C % 4 == 0, gather form (deterministic).
+ *   df_ew_relu_mask             out = d * [act > 0] (pixel pitch ld, `cols` channels)           -- backward of a fused ReLU epilogue
+ *   df_ew_maxpool_backward      3x3 / stride 2 / pad 1; window maxima recomputed from x, first maximum wins (ATen's rule)
+ *   df_ew_pyramid_pool_backward the four adaptive average pools (1,2,3,6) at once; dpool (50 B, C) stage-major as df_enc_pyramid_pool
+ *   df_ew_log_softmax32_backward dx = dy - exp(y) sum_c dy
+ *   df_ew_prelu / _backward     one slope (nn.PReLU()); dslope = sum dy x [x <= 0], fixed-order two-stage reduction
+ *                               (scratch: df_ew_prelu_scratch_floats() floats)
+ *   df_ew_dropout_mask          Dropout2d decisions, one per (sample, channel): mask[i] in {0, 1/(1-p)} from a counter-based hash of
+ *                               state = {seed, counter} (device, two uint64); the launch advances the counter (graph replays differ)
+ *   df_ew_scale_bc              y[b,pixel,c] = x[b,pixel,c] * mask[b,c]
+ *   df_ew_copy2d                pitched row copy (a channel slice of an NHWC buffer: the pyramid concat is written slice by slice)
+ *   df_ew_add                   out = a + b */
+int df_ew_relu_mask(const float* d, const float* act, float* out, int ld, int cols, long long rows, void* stream);
+int df_ew_maxpool_backward(const float* x, const float* gout, float* gin, int B, int H, int W, int C, void* stream);
+int df_ew_pyramid_pool_backward(const float* dpool, float* dx, int ldo, int B, int H, int W, int C, void* stream);
+int df_ew_log_softmax32_backward(const float* y, const float* dy, float* dx, long long pixels, void* stream);
+int df_ew_prelu(const float* x, const float* slope, float* y, long long n, void* stream);
+int df_ew_prelu_scratch_floats(void);
+int df_ew_prelu_backward(const float* x, const float* slope, const float* dy, float* dx, float* dslope, float* scratch, long long n,
+                         void* stream);
+int df_ew_dropout_mask(float* mask, int n, float p, unsigned long long* state, void* stream);
+int df_ew_scale_bc(const float* x, const float* mask, float* y, int B, long long HW, int C, void* stream);
+int df_ew_copy2d(const float* src, int lds, float* dst, int ldd, long long rows, int cols, void* stream);
+int df_ew_add(const float* a, const float* b, float* out, long long n, void* stream);
 /* Sparse last decoder stage: the 3x3 patches of the x2-upsampled (align_corners) map `in` (B,h,w,C) around the N chosen
  * pixels of every crop (choose (B,N), indices into the (2h x 2w) image), A (B*N, 9*C) tap-major; zero outside the image. */
 int df_enc_gather_up_patches(const float* in, const int64_t* choose, float* A, int B, int N, int h, int w, int C,

@@ -3,7 +3,7 @@
 # and one full capture per hand-written hot kernel.  Every ncu command runs only after the same command exited 0 without
 # ncu, and under `timeout`.
 mkdir -p gpurun_out
-STEP="python scripts/prof_step.py 32 hybrid16"
+STEP="python scripts/prof_step.py 32 hybrid16s"
 timeout 300 $STEP > gpurun_out/prof_step.txt 2>&1 &&
 DF_NCU=1 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/launches.csv $STEP > gpurun_out/ncu_step.log 2>&1

@@ -24,5 +24,5 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
 rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
 total = sum(e.device_time_total for e in rows)
 print(f"# phase {phase}: {len(rows)} distinct kernels, total device time {total/1e3:.2f} ms")
-for e in rows[:45]:
+for e in rows[:70]:
     print(f"{e.device_time_total/1e3:9.3f} ms {100*e.device_time_total/total:5.1f}%  x{e.count:<4d} {e.key[:110]}")

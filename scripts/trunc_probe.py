@@ -13,7 +13,7 @@ for K in (512, 4096):
     w = (torch.rand(N, K, generator=g) + 0.5) / K
     am = torch.randn(M, K, generator=g)
     wm = torch.randn(N, K, generator=g) / K ** 0.5
-    for prec in ("hybrid16", "3xtf32", "hybrid"):
+    for prec in ("hybrid16s", "hybrid16", "3xtf32", "hybrid"):
         row = {"K": K, "precision": prec}
         for name, (x, y) in {"pos": (a, w), "neg": (-a, w), "mixed": (am, wm), "relu_mixed": (am.clamp(min=0), wm)}.items():
             got = ops.linear(x.cuda(), y.cuda(), None, precision=prec).double().cpu()
