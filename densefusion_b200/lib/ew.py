@@ -44,8 +44,21 @@ def colsum(dy: torch.Tensor) -> torch.Tensor:
     """Bias gradient: sum over batch and pixels of a channels_last (B,C,H,W) gradient."""
     dy = nhwc(dy)
     b, c, h, w = dy.shape
+    rows = b * h * w
     out = torch.empty(c, device=dy.device, dtype=torch.float32)
-    check(lib.df_colsum_rows(ptr(dy), c, b * h * w, 1, c, ptr(out), 0, stream()), "df_colsum_rows")
+    # df_colsum_rows gives one block per (32 columns, group): cut the rows into groups so that ~4 blocks per SM are busy, then add the
+    # per-group sums in fixed order (deterministic)
+    groups = max(1, min(rows // 512, 592 // max(1, (c + 31) // 32)))
+    if groups == 1:
+        check(lib.df_colsum_rows(ptr(dy), c, rows, 1, c, ptr(out), 0, stream()), "df_colsum_rows")
+        return out
+    rpg = rows // groups
+    tail = rows - rpg * groups
+    part = torch.empty(groups + (1 if tail else 0), c, device=dy.device, dtype=torch.float32)
+    check(lib.df_colsum_rows(ptr(dy), c, rpg, groups, c, ptr(part), 0, stream()), "df_colsum_rows")
+    if tail:
+        check(lib.df_colsum_rows(ptr(dy) + rpg * groups * c * 4, c, tail, 1, c, ptr(part) + groups * c * 4, 0, stream()), "df_colsum_rows")
+    check(lib.df_reduce_partials(ptr(part), part.shape[0], c, ptr(out), 0, stream()), "df_reduce_partials")
     return out
 
 
