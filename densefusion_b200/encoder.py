@@ -2,7 +2,7 @@
 lib/network.py:27-37, lib/extractors.py:78-124, lib/pspnet.py:7-77) on the tensor cores -- SURVEY.md section 8f row N1.
 
 After the head moved to tcgen05 the torch/cuDNN fp32 encoder was 85-90% of the pose step.  Here every convolution is a
-GEMM on the CTA-pair tcgen05 kernel in the same error-compensated 3xTF32 arithmetic as the head (fp32 parity):
+GEMM on the CTA-pair tcgen05 kernel in the same fp32-parity arithmetic as the head (`precision`: "hybrid16s" by default):
   * 3x3 stride-1 convolutions (any dilation): implicit GEMM, the A operand is a 4-D TMA box over the NHWC activation
     shifted by the tap -- zero padding is TMA's out-of-bounds fill, nothing is im2col'ed (df_conv_tc);
   * 1x1 convolutions: plain GEMMs over the (pixels, channels) matrix;
@@ -16,7 +16,8 @@ GEMM on the CTA-pair tcgen05 kernel in the same error-compensated 3xTF32 arithme
     multiplied by (bottleneck slice x stage weight) at 50 cells per crop, resized and summed by one kernel, and enter the
     bottleneck GEMM as its residual operand -- K = 512 instead of 2560 at full resolution and no 2560-wide concat.
 Activations are NHWC fp32; the result (B,H,W,32) log-softmax embedding is consumed by df_gather_embedding through
-explicit strides.  Inference only; training keeps the torch/cuDNN encoder (its backward is library code)."""
+explicit strides.  Inference only: training runs the module graph of lib/pspnet.py / lib/extractors.py, whose convolutions
+(lib/conv_tc.py) and element-wise / pooling ops (lib/ew.py) are own kernels with explicit backward passes."""
 from __future__ import annotations
 
 import os

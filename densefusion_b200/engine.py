@@ -10,7 +10,8 @@ Activations are point-major (rows = crops*points, channels contiguous) so every 
 
 Data layout in HBM for a chunk of Bc crops (rows = Bc*N): pf (rows,384) = [x1|e1|x2|e2]; h5 (rows,512);
 pool partials (Bc,tiles,1024); g (Bc,1024); gbias (Bc,1920); h1 (rows,1920); h2 (rows,768); h3 (rows,384).
-Chunks are sized so one chunk's activations stay L2-resident (126 MB) between consecutive layers."""
+A chunk's activations (596 MB for tower 1 alone at the default 128 crops) do NOT stay L2-resident: fewer, larger launches won over
+L2 residency when this was measured (16 crops 21.7 ms per step, 128 crops 20.05)."""
 from __future__ import annotations
 
 from typing import Optional

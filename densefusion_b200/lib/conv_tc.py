@@ -8,8 +8,10 @@ and the data gradient run on df_conv_tc -- the implicit-GEMM tcgen05 kernel in t
     dW = dy^T x_shifted              df_conv_wgrad_tc: one 3xTF32 GEMM whose reduction runs over the zero-padded pixel axis
 The three stride-2 layers (conv1 7x7/2, layer2.0.conv1 3x3/2 and its 1x1/2 projection) run as explicit patch matrices on the same
 GEMM kernel (ConvS2Fn).  Forward arithmetic `PRECISION` ("hybrid16"), data gradients `GRAD_PRECISION` ("hybrid": gradients need
-the fp32 exponent range).  Activations are channels_last, i.e. physically the NHWC layout the kernel wants; the remaining
-encoder ops (ReLU, pooling, PReLU, dropout, log-softmax) are torch element-wise ops that keep that layout."""
+the fp32 exponent range).  ReLU and the residual blocks' skip connections are epilogues of the convolution launch
+(`conv2d(m, x, act=1, residual=skip)`; backward masks dy with [y > 0] and hands the masked gradient to the skip input).
+Activations are channels_last, i.e. physically the NHWC layout the kernel wants; the remaining encoder ops (pooling, pyramid
+concat, PReLU, Dropout2d, log-softmax) are own kernels as well (lib/ew.py)."""
 from __future__ import annotations
 
 import os

@@ -120,7 +120,7 @@ class PoseEstimator:
                         iterations: Optional[int] = None) -> torch.Tensor:
         """cloud (B,N,3), emb_pm (B*N,32), obj (B,) -> pose (B,7) float64.
 
-        Per-point layers run chunk by chunk (a chunk's activations stay L2-resident); everything with one row per
+        Per-point layers run chunk by chunk (`chunk_crops` at a time: bounded scratch, large launches); everything with one row per
         crop -- the folded global-feature bias, pose selection, the refiner's MLP towers, pose composition -- runs once
         for all B crops."""
         iters = self.iterations if iterations is None else iterations
