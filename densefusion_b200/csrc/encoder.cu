@@ -376,6 +376,9 @@ upconv_finish_smem_kernel(const float* __restrict__ Z, int ldz, const float* __r
     }
 }
 
+// (A separable form -- x pass at the footprint rows, then a y pass: 24 instead of 36 shared-memory reads per output -- was measured in
+// round 2 and is SLOWER, 0.357 vs 0.195 ms on up_1: the extra barrier, the ragged x pass and the lower occupancy of a 78 KB CTA cost
+// more than the reads saved; the kernel is latency / occupancy bound, not LDS bound.)
 // Backward of upsample_nhwc_kernel in gather form (deterministic, no atomics): every INPUT pixel sums the output pixels
 // whose 2x2 bilinear footprint contains it, with the forward's own index / weight arithmetic.
 __global__ void __launch_bounds__(256)

@@ -1039,10 +1039,6 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
     const int n_tiles = (p.N + bnt - 1) / bnt;
     const int total = m_tiles * n_tiles * groups;
     const int clusters = total < max_clusters ? total : max_clusters;
-    // (Round 2 also tried keeping the weight planes of one n-tile resident in shared memory per cluster, "teams" of clusters walking the
-    // m-tiles, for the short-K head layers: 16 instead of 28 KB per k-block through the port -- correct, and no faster (tower-1 0.28 vs
-    // 0.25 ms, K = 256: a tie): the knock-out runs of scripts/knockout_probe.py show the k loop at ~950 clocks per k-block with or without
-    // the weight bytes, i.e. not paced by the port alone.  Removed; DESIGN.md section 4 keeps the numbers.)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(clusters * CTAS); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = Q_SMEM_TOTAL; cfg.stream = s;
     cudaLaunchAttribute at[2];

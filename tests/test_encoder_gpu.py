@@ -269,3 +269,22 @@ def test_stride2_convolutions_forward_and_gradients_vs_float64(B, H, W, Cin, Cou
     e = [rel(y, y64), rel(m.weight.grad, m64.weight.grad)] + ([rel(xc.grad, x64.grad)] if k != 7 else [])
     print(f"conv_s2 {k}x{k} {Cin}->{Cout} {H}x{W}x{B}: " + " ".join(f"{v:.2e}" for v in e))
     assert max(e) < 2e-5
+
+
+@pytest.mark.parametrize("B,C,h,w", [(2, 64, 6, 9), (3, 32, 7, 7), (1, 256, 10, 10), (2, 64, 2, 3)])
+def test_upconv_finish_staged_kernel_vs_conv_of_resized_map(B, C, h, w):
+    """Decoder stage at the low resolution on the shared-memory kernel (C % 32 == 0): tap products + df_enc_upconv_finish ==
+    PReLU(conv3x3(resize x2, align_corners) + bias), including patches on every border of the map and a channel-slice output."""
+    from densefusion_b200._C import check, lib, ptr, stream
+    g = torch.Generator().manual_seed(B * 1000 + C + h * w)
+    cin = 16
+    xl, wt = torch.randn(B, cin, h, w, generator=g), torch.randn(C, cin, 3, 3, generator=g) * 0.1
+    bs, slope = torch.randn(C, generator=g), torch.tensor([0.25])
+    want = F.prelu(F.conv2d(F.interpolate(xl.double(), scale_factor=2, mode="bilinear", align_corners=True), wt.double(), bs.double(), padding=1),
+                   slope.double())
+    z = (_nhwc(xl).reshape(-1, cin).double() @ wt.permute(2, 3, 0, 1).reshape(9 * C, cin).double().T).float().view(B, h, w, 9 * C).cuda()
+    o = torch.full((B, 2 * h, 2 * w, C + 32), 7.0, device="cuda")
+    bs_d, slope_d = bs.cuda(), slope.cuda()
+    check(lib.df_enc_upconv_finish(ptr(z), 9 * C, ptr(bs_d), ptr(slope_d), ptr(o), C + 32, B, h, w, C, stream()), "upconv_finish")
+    assert rel(o[..., :C].permute(0, 3, 1, 2), want) < 5e-6
+    assert float((o[..., C:] - 7.0).abs().max()) == 0.0
