@@ -314,34 +314,38 @@ constexpr int UF_T = 8;                        // output patch edge
 constexpr int UF_FP = 7;                       // low-resolution footprint edge (upper bound, see above)
 constexpr int UF_SMEM = UF_FP * UF_FP * 9 * 128;
 
+// LANES = float4 lanes per pixel a CTA handles: 8 (32 channels, 56 KB of footprint: 4 CTAs per SM; production) or 4 (16 channels,
+// 28 KB: 8 CTAs per SM; A/B variant)
+template <int LANES>
 __global__ void __launch_bounds__(256)
 upconv_finish_smem_kernel(const float* __restrict__ Z, int ldz, const float* __restrict__ bias, const float* __restrict__ prelu,
                           float* __restrict__ out, int ldo, int h, int w, int C, float rh, float rw, int tiles_x)
 {
     extern __shared__ __align__(16) uint8_t uf_smem[];
-    float4* s = reinterpret_cast<float4*>(uf_smem);                 // [(ry * cols + rx) * 9 + tap][8]
+    float4* s = reinterpret_cast<float4*>(uf_smem);                 // [(ry * cols + rx) * 9 + tap][LANES]
+    constexpr int PIX_PER_PASS = 256 / LANES;
     const int H = 2 * h, W = 2 * w;
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
-    const int Y0 = ty * UF_T, X0 = tx * UF_T, c0 = blockIdx.y * 32, b = blockIdx.z;
+    const int Y0 = ty * UF_T, X0 = tx * UF_T, c0 = blockIdx.y * (LANES * 4), b = blockIdx.z;
     // low-resolution rows / columns the patch's taps can touch (same index arithmetic as the compute phase below)
     const int ya = max(Y0 - 1, 0), yb = min(Y0 + UF_T, H - 1), xa = max(X0 - 1, 0), xb = min(X0 + UF_T, W - 1);
     const int y_lo = (int)(rh * ya), x_lo = (int)(rw * xa);
     const int y_hi = min((int)(rh * yb) + 1, h - 1), x_hi = min((int)(rw * xb) + 1, w - 1);
     const int rows = y_hi - y_lo + 1, cols = x_hi - x_lo + 1;       // <= UF_FP each
     const float* zb = Z + (size_t)b * h * w * ldz + c0;
-    for (int i = threadIdx.x; i < rows * cols * 9 * 8; i += 256) {
-        const int c = i & 7, pt = i >> 3;
+    for (int i = threadIdx.x; i < rows * cols * 9 * LANES; i += 256) {
+        const int c = i % LANES, pt = i / LANES;
         const int tap = pt % 9, px = pt / 9;
         const int ry = px / cols, rx = px - ry * cols;
         s[i] = __ldg(reinterpret_cast<const float4*>(zb + ((size_t)(y_lo + ry) * w + (x_lo + rx)) * ldz + tap * C) + c);
     }
     __syncthreads();
     const float slope = __ldg(prelu);
-    const int cq = threadIdx.x & 7;
+    const int cq = threadIdx.x % LANES;
     const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias + c0) + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-    for (int pass = 0; pass < UF_T * UF_T / 32; ++pass) {
-        const int pix = pass * 32 + (threadIdx.x >> 3);
+    for (int pass = 0; pass < UF_T * UF_T / PIX_PER_PASS; ++pass) {
+        const int pix = pass * PIX_PER_PASS + (threadIdx.x / LANES);
         const int Y = Y0 + pix / UF_T, X = X0 + pix % UF_T;
         if (Y >= H || X >= W) continue;
         float4 acc = bv;
@@ -359,11 +363,11 @@ upconv_finish_smem_kernel(const float* __restrict__ Z, int ldz, const float* __r
                 const float sx = rw * xx;
                 const int x0 = (int)sx, xp = x0 < w - 1 ? 1 : 0;
                 const float lx1 = sx - x0, lx0 = 1.0f - lx1;
-                const float4* p = s + (((y0 - y_lo) * cols + (x0 - x_lo)) * 9 + ky * 3 + kx) * 8 + cq;
+                const float4* p = s + (((y0 - y_lo) * cols + (x0 - x_lo)) * 9 + ky * 3 + kx) * LANES + cq;
                 const float4 v00 = p[0];
-                const float4 v01 = p[xp * 72];
-                const float4 v10 = p[yp * cols * 72];
-                const float4 v11 = p[(yp * cols + xp) * 72];
+                const float4 v01 = p[xp * 9 * LANES];
+                const float4 v10 = p[yp * cols * 9 * LANES];
+                const float4 v11 = p[(yp * cols + xp) * 9 * LANES];
                 acc.x += ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
                 acc.y += ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
                 acc.z += ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
@@ -553,17 +557,21 @@ extern "C" int df_enc_upconv_finish(const float* Z, int ldz, const float* bias, 
     if ((long long)B * 4 * h * w * (C >> 2) >= (1LL << 31)) return DF_ERR_ARG;
     const int H = 2 * h, W = 2 * w;
     const float rh = H > 1 ? (float)(h - 1) / (H - 1) : 0.f, rw = W > 1 ? (float)(w - 1) / (W - 1) : 0.f;
+    // DF_UPCONV_SMEM: 0 = L1-gather kernel, 1 (default) = footprint staged in shared memory, 32 channels per CTA, 2 = the same with 16
+    // channels per CTA (twice the CTAs per SM; measured 10% SLOWER and bit-identical: occupancy is not what limits this kernel)
     static const int use_smem = getenv("DF_UPCONV_SMEM") ? atoi(getenv("DF_UPCONV_SMEM")) : 1;
     if (use_smem && C % 32 == 0 && B <= 65535 && h >= 2 && w >= 2) {
         static bool attr_done = false;
         if (!attr_done) {
-            cudaError_t e = cudaFuncSetAttribute(upconv_finish_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UF_SMEM);
+            cudaError_t e = cudaFuncSetAttribute(upconv_finish_smem_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, UF_SMEM);
             if (e != cudaSuccess) return (int)e;
             attr_done = true;
         }
         const int tiles_x = (W + UF_T - 1) / UF_T, tiles_y = (H + UF_T - 1) / UF_T;
-        dim3 grid(tiles_x * tiles_y, C / 32, B);
-        upconv_finish_smem_kernel<<<grid, 256, UF_SMEM, (cudaStream_t)stream>>>(Z, ldz, bias, prelu, out, ldo, h, w, C, rh, rw, tiles_x);
+        if (use_smem == 2)
+            upconv_finish_smem_kernel<4><<<dim3(tiles_x * tiles_y, C / 16, B), 256, UF_SMEM / 2, (cudaStream_t)stream>>>(Z, ldz, bias, prelu, out, ldo, h, w, C, rh, rw, tiles_x);
+        else
+            upconv_finish_smem_kernel<8><<<dim3(tiles_x * tiles_y, C / 32, B), 256, UF_SMEM, (cudaStream_t)stream>>>(Z, ldz, bias, prelu, out, ldo, h, w, C, rh, rw, tiles_x);
         DF_RETURN_LAST_ERROR();
     }
     upconv_finish_kernel<<<grid_for((long long)B * H * W * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(
