@@ -62,7 +62,7 @@ struct TcParams {
     const float* w_inv_scale; float a_scale;
     long long samp_rows; int samp_cols;
     int dbg;                                    // DF_TC_DBG knock-out bits (timing experiments only; results are wrong): 1 no global stores,
-                                                // 2 no transpose, 4 no TMEM load, 8 no MMAs
+                                                // 2 no transpose, 4 no TMEM load, 8 no MMAs, 16 no store instruction (reads / math of the store path kept)
     int run_steps;                              // host side only: MMA instructions per accumulation run, 0 = default
     // ---- weight-gradient form (df_conv_wgrad_tc): output column n = tap * wk_rows + ci multiplies row ci of the W operand
     // read wk_shift[tap] elements further along k (a 3x3 tap is an offset in the zero-padded, flattened pixel axis) ----
@@ -192,7 +192,7 @@ __device__ __forceinline__ QTile q_decode(const TcParams& p, int t, int m_tiles,
 // vector for the warp's 32 rows): per 4-row step one LDS.128, the bias, the activation, one address multiply-add and one STG.128.
 template <int ACT>
 __device__ __forceinline__ void epi_store_simple(const float* srow, int sw0, int sw1, char* cbase, uint32_t ldcb, const int (&roff)[8],
-                                                 float4 b, float slope)
+                                                 float4 b, float slope, bool no_store = false)
 {
 #pragma unroll
     for (int ps = 0; ps < 8; ++ps) {
@@ -205,6 +205,7 @@ __device__ __forceinline__ void epi_store_simple(const float* srow, int sw0, int
             o.x = o.x > 0.f ? o.x : slope * o.x; o.y = o.y > 0.f ? o.y : slope * o.y;
             o.z = o.z > 0.f ? o.z : slope * o.z; o.w = o.w > 0.f ? o.w : slope * o.w;
         }
+        if (no_store && o.x != 12345.678f) continue;          // (DF_TC_DBG bit 16: everything but the store instruction itself)
         *reinterpret_cast<float4*>(cbase + (unsigned long long)(uint32_t)roff[ps] * ldcb) = o;
     }
 }
@@ -748,9 +749,10 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     if (cq < p.N && !(p.dbg & 1)) {
                         char* cbase = reinterpret_cast<char*>(Cg + cq);
                         if (simple) {
-                            if (p.relu == 1) epi_store_simple<1>(srow, sw0, sw1, cbase, ldcb, roff, b0, slope);
-                            else if (p.relu == 2) epi_store_simple<2>(srow, sw0, sw1, cbase, ldcb, roff, b0, slope);
-                            else epi_store_simple<0>(srow, sw0, sw1, cbase, ldcb, roff, b0, slope);
+                            const bool ns = (p.dbg & 16) != 0;
+                            if (p.relu == 1) epi_store_simple<1>(srow, sw0, sw1, cbase, ldcb, roff, b0, slope, ns);
+                            else if (p.relu == 2) epi_store_simple<2>(srow, sw0, sw1, cbase, ldcb, roff, b0, slope, ns);
+                            else epi_store_simple<0>(srow, sw0, sw1, cbase, ldcb, roff, b0, slope, ns);
                         } else {
                             // general store: the sum of the earlier runs of this tile comes back from C (written by this very thread)
                             // in the LAST run only, the skip connection from the residual tensor.  All loads of four rows are issued before the first store:
