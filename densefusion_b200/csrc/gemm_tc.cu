@@ -282,7 +282,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // first: it stays a normal fp16 number while |a s| >= 0.25 and carries an ABSOLUTE error of 2^-25 below, and fp16 saturates at
     // 65504 -- so s = 2^k is chosen to put the operand's largest entries near 2^5: entries up to ~2000x larger still fit, and the
     // absolute error is 2^-30 of the largest entry (fp32 itself rounds that entry to 2^-24).  "Largest entry" is estimated from a fixed
-    // sample of 512 rows x 8 columns, read by the 16 stager / epilogue warps of EVERY CTA (same addresses, hence the same scale everywhere
+    // sample of 512 (row, 4-column group) positions along a diagonal, twice, read by the 16 stager / epilogue warps of EVERY CTA (same addresses, hence the same scale everywhere
     // and from run to run; L2 hits after the first CTA) while the TMA producer is already filling the pipeline.
     float a_sc = 1.0f;
     if (S16 && warp >= 2) {
@@ -293,7 +293,9 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             uint32_t m = 0;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int col = ((((t & 7) << 2) + j * (p.samp_cols >> 1)) % p.samp_cols) & ~3;
+                // (row and column both move with t: every group of 4 channels is visited when the operand has <= 2048 columns, so a
+                // channel that is systematically larger than the rest cannot hide from the sample)
+                const int col = (((t << 2) + j * (p.samp_cols >> 1)) % p.samp_cols) & ~3;
                 const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + col));
                 const uint32_t b0 = v.x & 0x7fffffffu, b1 = v.y & 0x7fffffffu, b2 = v.z & 0x7fffffffu, b3 = v.w & 0x7fffffffu;
                 if (b0 < 0x7f800000u) m = max(m, b0);

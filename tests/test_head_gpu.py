@@ -206,6 +206,10 @@ def test_hybrid16s_fixed_activation_scale_and_outliers():
         x2 = x.clone()
         x2[777, 13] = big
         assert (err(x2) < 3e-6) == ok, big
+    # an "outlier channel": one column 300x larger than all the others (the diagonal sample visits every 4-column group)
+    x3 = x.clone()
+    x3[:, 301] *= 300.0
+    assert err(x3) < 3e-6
 
 
 @pytest.mark.parametrize("variant", _variants([5, 6, 7]))
