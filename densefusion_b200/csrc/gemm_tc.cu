@@ -218,7 +218,8 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 {
     // A_STAGES TMEM A stages of A_COLS columns each at the top of TMEM (64: [hi | lo] / [fp16 | - | bf16 | bf16 lo]; 32: the two
     // fp16 planes of hybrid16s, the only arithmetic that instantiation carries); the accumulators share what is left below.
-    // A_COLS == 0 (hybrid16s, "A_SMEM"): the two fp16 planes of A go to a shared-memory ring of A_STAGES 16 KB tiles in the MMA's
+    // A_COLS == 0 (hybrid16s, "A_SMEM"): the two fp16 planes of A go to a shared-memory ring of A_STAGES 16 KB tiles (4, with 4 operand
+    // stages of a 256-wide tile; 3 when the pooled epilogue needs its 8 KB: measured -2..3% / +9% for the other choice) in the MMA's
     // K-major 128B-swizzled layout instead (rows of [hi x32 | lo x32], like the weight tile) and the MMA reads both operands from
     // shared memory -- all 512 TMEM columns are then accumulators: TWO buffers of up to 256 columns, so that the drain of a 256-wide tile
     // (one accumulator with A in TMEM: exposed, ~20% of the pooled conv6 layer, ~12% of the long-K convolutions) overlaps the next run.
@@ -1463,7 +1464,8 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
     int rc;
     if (precision == 6) {                 // hybrid16s: two fp16 planes per operand, 32-column TMEM A stages: CTA-pair kernel only
         if (variant != 0 && variant != 6) return DF_ERR_UNSUPPORTED;
-        rc = s16_a_in_smem(p, groups) ? launch_q<2, 3, 0>(p, W_hi, W_hi, ldw, groups, (cudaStream_t)stream)
+        rc = s16_a_in_smem(p, groups) ? (p.pool_partial ? launch_q<2, 3, 0>(p, W_hi, W_hi, ldw, groups, (cudaStream_t)stream)     // (pool buffer: 3 + 4 stages)
+                                                         : launch_q<2, 4, 0>(p, W_hi, W_hi, ldw, groups, (cudaStream_t)stream))
                                       : launch_q<2, 4, 32>(p, W_hi, W_hi, ldw, groups, (cudaStream_t)stream);
     } else if (v == 5) rc = launch_q<1, 4>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream);
     else if (v == 6) rc = launch_q<2, 2>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream);
@@ -1557,7 +1559,7 @@ extern "C" int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx,
     p.conv_taps = taps; p.conv_dil = dilation; p.cW = W; p.cH = H; p.cB = B;
     p.residual = residual; p.ldr = ldr; p.prelu = prelu;
     conv_patch_plan(p, B, H, W, taps, dilation);
-    const int rc = precision == 6 ? (s16_a_in_smem(p, 1) ? launch_q<2, 3, 0>(p, W_hi, W_hi, taps * Cin, 1, (cudaStream_t)stream)
+    const int rc = precision == 6 ? (s16_a_in_smem(p, 1) ? launch_q<2, 4, 0>(p, W_hi, W_hi, taps * Cin, 1, (cudaStream_t)stream)
                                                          : launch_q<2, 4, 32>(p, W_hi, W_hi, taps * Cin, 1, (cudaStream_t)stream))
                                   : launch_q<2, 2>(p, W_hi, W_lo, taps * Cin, 1, (cudaStream_t)stream);
     if (rc) return rc;
