@@ -34,6 +34,7 @@ SIGNATURES = {
     "df_pack_bf16_pairs": [_p, _p, _ll, _i, _p],
     "df_pack_f16_pairs": [_p, _p, _p, _ll, _i, _p],
     "df_pack_f16s": [_p, _p, _p, _ll, _i, _p],
+    "df_enc_conv1_tc": [_p, _i, _i, _i, _p, _p, _p, _i, _i, _i, _p],
     "df_ew_relu_mask": [_p, _p, _p, _i, _i, _ll, _p],
     "df_ew_maxpool_backward": [_p, _p, _p, _i, _i, _i, _i, _p],
     "df_ew_pyramid_pool_backward": [_p, _p, _i, _i, _i, _i, _i, _p],

@@ -61,6 +61,11 @@ struct TcParams {
     // samp_rows x samp_cols addressable; see "activation scale" in the kernel), so it follows the data without a host round trip.
     const float* w_inv_scale; float a_scale;
     long long samp_rows; int samp_cols;
+    // conv1 form (hybrid16s, A planes in TMEM): A is NOT a matrix in memory -- the stagers gather the 7x7 / stride 2 / pad 3 patches of the
+    // NCHW image p.A (c1_B x 3 x c1_H x c1_W) straight into their registers, row m = output pixel (b, yo, xo), column k = c*49 + ky*7 +
+    // kx (K = 160: 147 + zero padding), so the 0.58 GB patch matrix of df_enc_im2col_conv1 and its trip through HBM disappear.
+    // c1_H == 0: off.
+    int c1_H, c1_W, c1_Ho, c1_Wo;
     int dbg;                                    // DF_TC_DBG knock-out bits (timing experiments only; results are wrong): 1 no global stores,
                                                 // 2 no transpose, 4 no TMEM load, 8 no MMAs, 16 no store instruction (reads / math of the store path kept)
     int run_steps;                              // host side only: MMA instructions per accumulation run, 0 = default
@@ -250,7 +255,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // A | W_hi | W_lo (or the bf16 pair tile), all 1024-B aligned; hybrid16s: A | [fp16 hi x32 | fp16 lo x32] rows
     const uint32_t stage_bytes = S16 ? Q_TILE + w_bytes : Q_TILE + 2 * w_bytes;
     // (the pooled epilogue keeps its per-warp column sums in the last 8 KB of the stage area: one stage less when the ring fills it)
-    const uint32_t pool_bytes = p.pool_partial ? 8192u : 0u;
+    const uint32_t pool_bytes = p.pool_partial ? 8192u : (p.c1_H ? 2048u : 0u);      // (conv1 form: the patch offset table lives there)
     const uint32_t aring_bytes = A_SMEM ? (uint32_t)A_STAGES * Q_TILE : 0u;
     const int Q_STAGES = (int)min((uint32_t)Q_MAX_STAGES, ((uint32_t)Q_SMEM_STAGES - pool_bytes - aring_bytes) / stage_bytes);
     uint8_t* const aring = smem + (size_t)Q_STAGES * stage_bytes;           // A_SMEM: the operand-plane ring of A (1024-byte aligned)
@@ -319,7 +324,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // ------------------------------- TMA producer -------------------------------
         const uint32_t a_bytes = p.conv_taps ? (uint32_t)(p.TW * p.TH * p.TB) * BK * 4 : (uint32_t)Q_TILE;
         // 3xTF32: W_hi + W_lo; hybrid: W_hi + bf16 pair tile; hybrid16: pair tile + a half-width (64 B rows) correction tile
-        const uint32_t bytes = a_bytes + (S16 ? w_bytes : p.precise == 3 ? w_bytes + w_bytes / 2 : (p.precise ? 2u : 1u) * w_bytes);
+        const uint32_t bytes = (p.c1_H ? 0u : a_bytes) + (S16 ? w_bytes : p.precise == 3 ? w_bytes + w_bytes / 2 : (p.precise ? 2u : 1u) * w_bytes);
         const int cblocks = p.conv_taps ? p.K / (BK * p.conv_taps) : 1;        // 32-channel blocks per tap
         int s = 0;
         uint32_t ph = 1;                                                       // parity of "slot is free": passes at once in round 0
@@ -352,7 +357,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         const int dx = p.conv_taps == 9 ? (kx - 1) * p.conv_dil : 0;
                         kb = tap * cblocks + cb;
                         tma_load_4d(&tm_a, dst, full + s, cb * BK, c.x0 + dx, c.y0 + dy, c.b0);
-                    } else {
+                    } else if (!p.c1_H) {
                         tma_load_2d(&tm_a, dst, full + s, acol + kb * BK, c.row0);
                     }
                     // first weight tile: 32 fp32 per row (TF32 hi part), or, hybrid16 / hybrid16s, 64 halves per row ([fp16(W) x32 | bf16(W) x32]
@@ -504,16 +509,51 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         uint32_t ph = 0;
         int sp = grp - A_STAGES;                                         // ... and of iteration it - A_STAGES (negative: none yet)
         uint32_t php = 0;
+        // conv1 form: per k the offset of patch element (c, ky, kx) relative to the patch origin and its (ky - 3, kx - 3), built once
+        // in shared memory (a __constant__ table indexed by the warp-uniform k was measured slower: 0.175 vs 0.153 ms at 64 x 160^2)
+        int* c1_off = reinterpret_cast<int*>(smem + Q_SMEM_STAGES - 2048);
+        int* c1_dyx = c1_off + 160;
+        const bool conv1 = S16 && !A_SMEM && p.c1_H != 0;
+        if (conv1) {
+            const int k = (int)threadIdx.x - 64;                         // the 256 stager threads
+            if (k < 160) {
+                const int c = k / 49, rem = k - c * 49, ky = rem / 7, kx = rem - ky * 7;
+                c1_off[k] = k < 147 ? (c * p.c1_H + (ky - 3)) * p.c1_W + (kx - 3) : 0;
+                c1_dyx[k] = k < 147 ? (((ky - 3) & 0xff) | (((kx - 3) & 0xff) << 8)) : 0x8080;      // 0x80: never inside the image
+            }
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+        }
+        int c1_tile = 0, c1_kb = grp;                                    // conv1 form: tile of this cluster / k-block inside it (nkb >= 2)
         for (uint32_t it = grp; it < total_it; it += 2) {
-            mbar_wait(full + s, ph);
-            const uint8_t* arow = smem + (size_t)s * stage_bytes + r * 128;
             // hi: TF32-exact part (raw value in single-pass mode); second[]: what goes into columns [32,64) of the TMEM stage --
             // lo (3xTF32), or 16 words of bf16(x) pairs followed by 16 words of bf16(lo) pairs (hybrid)
             uint32_t hi[32], second[32];
+            if (conv1) {
+                const long long m = ((long long)(t_first + c1_tile * t_step) * CTAS + rank) * 128 + r;       // output pixel of this lane
+                const bool row_in = m < (long long)p.M;
+                const int hw = p.c1_Ho * p.c1_Wo;
+                const int b = row_in ? (int)(m / hw) : 0, rem = row_in ? (int)(m - (long long)b * hw) : 0;
+                const int yo = rem / p.c1_Wo, xo = rem - yo * p.c1_Wo;
+                const int y2 = yo * 2, x2 = xo * 2;
+                const float* org = p.A + ((size_t)b * 3 * p.c1_H + y2) * p.c1_W + x2;      // patch origin + (3, 3)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int k = c1_kb * 32 + i;
+                    const int d = c1_dyx[k];
+                    const int y = y2 + (int)(signed char)(d & 0xff), x = x2 + (int)(signed char)((d >> 8) & 0xff);
+                    const bool ok = row_in && (unsigned)y < (unsigned)p.c1_H && (unsigned)x < (unsigned)p.c1_W && d != 0x8080;
+                    hi[i] = ok ? __float_as_uint(__ldg(org + c1_off[k])) : 0u;
+                }
+                c1_kb += 2;
+                if (c1_kb >= nkb) { c1_kb -= nkb; ++c1_tile; }
+            } else {
+            mbar_wait(full + s, ph);
+            const uint8_t* arow = smem + (size_t)s * stage_bytes + r * 128;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const uint4 v = *reinterpret_cast<const uint4*>(arow + ((c ^ sw) << 4));
                 hi[c * 4 + 0] = v.x; hi[c * 4 + 1] = v.y; hi[c * 4 + 2] = v.z; hi[c * 4 + 3] = v.w;
+            }
             }
             if (S16) {
                 const float sa = a_sc;
@@ -1016,9 +1056,12 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
     const int bnt = bn_cta * CTAS;
     // the A operand as a 2-D tensor: group g's columns start at g*a_gs inside the row
     const long long a_cols = (long long)(groups - 1) * p.a_gs + p.K;
-    if (!p.conv_taps && (a_cols > p.lda || (groups > 1 && p.a_gs < 0))) return DF_ERR_UNSUPPORTED;
+    if (!p.conv_taps && !p.c1_H && (a_cols > p.lda || (groups > 1 && p.a_gs < 0))) return DF_ERR_UNSUPPORTED;
+    if (p.c1_H && (A_COLS != 32 || bnt < p.N || groups != 1)) return DF_ERR_UNSUPPORTED;      // conv1 form: one n-tile, A planes in TMEM
     CUtensorMap ma, mhi, mlo;
-    if (p.conv_taps) {
+    if (p.c1_H) {
+        // (no A tensor map: the stagers gather the patches themselves; `ma` is set to the weight map below)
+    } else if (p.conv_taps) {
         if (!make_map_nhwc(&ma, p.A, p.cB, p.cH, p.cW, p.K / p.conv_taps, p.lda, p.TW, p.TH, p.TB)) return DF_ERR_UNSUPPORTED;
     } else if (!make_map(&ma, p.A, p.M, (int)a_cols, p.lda, 128)) return DF_ERR_UNSUPPORTED;
     const long long wrows = p.wk_rows ? (long long)p.wk_rows * (p.N / p.wk_rows == 9 ? 3 : 1) : (long long)groups * p.N;
@@ -1041,6 +1084,11 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
     }
     p.samp_rows = p.conv_taps ? (long long)p.cB * p.cH * p.cW : p.M;
     p.samp_cols = p.conv_taps ? p.K / p.conv_taps : (int)a_cols;
+    if (p.c1_H) {                                                  // the image as a (B*3*H, W) matrix
+        p.samp_rows = (long long)(p.M / (p.c1_Ho * p.c1_Wo)) * 3 * p.c1_H;
+        p.samp_cols = p.c1_W;
+        ma = mhi;
+    }
     const int n_tiles = (p.N + bnt - 1) / bnt;
     const int total = m_tiles * n_tiles * groups;
     const int clusters = total < max_clusters ? total : max_clusters;
@@ -1472,6 +1520,27 @@ extern "C" int df_gemm_tc(const float* A, int lda, const float* W_hi, const floa
     else if (v == 7) rc = launch_q<2, 4>(p, W_hi, W_lo, ldw, groups, (cudaStream_t)stream);
     else return DF_ERR_ARG;
     if (rc) return rc;                           // DF_ERR_UNSUPPORTED: a shape the TMA boxes cannot address (the caller runs df_gemm_fp32)
+    DF_RETURN_LAST_ERROR();
+}
+
+// conv1 of the encoder (7x7, stride 2, padding 3, 3 -> Cout channels; lib/extractors.py:82) as a GEMM whose A operand is gathered from
+// the NCHW image by the kernel's stagers (TcParams::c1_*): y (B*Ho*Wo, Cout) = act(patches . W^T).  `planes` / `scale`: df_pack_f16s of the
+// (Cout, 160) weight matrix [c*49 + ky*7 + kx, zero-padded from 147].  hybrid16s arithmetic only.
+extern "C" int df_enc_conv1_tc(const float* img, int B, int H, int W, const void* planes, const float* scale, float* Y, int ldy, int Cout,
+                               int relu, void* stream)
+{
+    if (!img || !planes || !scale || !Y || B <= 0 || H <= 0 || W <= 0 || Cout <= 0 || Cout > 64 || Cout % 4 || ldy % 4 || ldy < Cout) return DF_ERR_ARG;
+    if (W % 4 || ((uintptr_t)img & 15) || ((uintptr_t)Y & 15) || ((uintptr_t)planes & 15)) return DF_ERR_ARG;
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    if ((long long)B * Ho * Wo >= (1LL << 31) || (long long)B * 3 * H * W >= (1LL << 31)) return DF_ERR_ARG;
+    TcParams p = {};
+    p.A = img; p.lda = W; p.bias = nullptr; p.bias_crop_stride = 0; p.C = Y; p.ldc = ldy;
+    p.M = B * Ho * Wo; p.N = Cout; p.K = 160; p.relu = relu ? 1 : 0; p.precise = 4;
+    p.w_inv_scale = scale; p.a_scale = 0.0f;
+    p.rows_per_crop = p.M; p.a_gs = 0; p.bias_gs = 0; p.c_gs = 0; p.pool_partial = nullptr; p.tiles_per_crop = 0;
+    p.c1_H = H; p.c1_W = W; p.c1_Ho = Ho; p.c1_Wo = Wo;
+    const int rc = launch_q<2, 4, 32>(p, reinterpret_cast<const float*>(planes), reinterpret_cast<const float*>(planes), 160, 1, (cudaStream_t)stream);
+    if (rc) return rc;
     DF_RETURN_LAST_ERROR();
 }
 

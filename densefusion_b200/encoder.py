@@ -30,6 +30,7 @@ from ._C import check, lib, ptr, stream
 
 K_CONV1 = 160          # 3*7*7 = 147 padded to a multiple of 32
 _NARROW_ON_3XTF32 = os.environ.get("DF_HYBRID_NARROW", "0") != "1"     # A/B knob for the rule in PackedEncoder._conv
+_CONV1_GATHER = os.environ.get("DF_CONV1_GATHER", "1") == "1"           # A/B knob: conv1 on df_enc_conv1_tc (hybrid16s) vs im2col + GEMM
 
 
 def _pack_conv(w: torch.Tensor) -> ops.SplitWeight:
@@ -94,7 +95,7 @@ class PackedEncoder:
             H4, W4 = (H2 - 1) // 2 + 1, (W2 - 1) // 2 + 1
             H8, W8 = (H4 - 1) // 2 + 1, (W4 - 1) // 2 + 1
             ws = {"dims": (H2, W2, H4, W4, H8, W8)}
-            ws["a0"] = torch.empty(b * H2 * W2, K_CONV1, **f)
+            ws["a0"] = None                                  # conv1 patch matrix: only the modes without the gathering kernel need it
             ws["c1"] = torch.empty(b, H2, W2, 64, **f)
             ws["l1"] = [torch.empty(b, H4, W4, 64, **f) for _ in range(3)]
             ws["a2"] = torch.empty(b * H8 * W8, 9 * 64, **f)
@@ -188,10 +189,17 @@ class PackedEncoder:
         H2, W2, H4, W4, H8, W8 = ws["dims"]
         s = stream()
         # conv1 7x7/2 + ReLU, 3x3/2 max pool
-        check(lib.df_enc_im2col_conv1(ptr(img), ptr(ws["a0"]), b, H, W, K_CONV1, s), "df_enc_im2col_conv1")
         rows = b * H2 * W2
-        ops.gemm(ws["a0"], self.conv1, None, ws["c1"], M=rows, N=64, K=K_CONV1, lda=K_CONV1, ldw=K_CONV1, ldc=64, relu=True,
-                 precision=precision)
+        if mode == 6 and _CONV1_GATHER:
+            # hybrid16s: the kernel's stagers gather the 7x7 patches from the image themselves -- no patch matrix (0.58 GB per step)
+            planes, scale = self.conv1.planes16s()
+            check(lib.df_enc_conv1_tc(ptr(img), b, H, W, ptr(planes), ptr(scale), ptr(ws["c1"]), 64, 64, 1, s), "df_enc_conv1_tc")
+        else:
+            if ws["a0"] is None:
+                ws["a0"] = torch.empty(rows, K_CONV1, device=self.device, dtype=torch.float32)
+            check(lib.df_enc_im2col_conv1(ptr(img), ptr(ws["a0"]), b, H, W, K_CONV1, s), "df_enc_im2col_conv1")
+            ops.gemm(ws["a0"], self.conv1, None, ws["c1"], M=rows, N=64, K=K_CONV1, lda=K_CONV1, ldw=K_CONV1, ldc=64, relu=True,
+                     precision=precision)
         x = ws["l1"][0]
         check(lib.df_enc_maxpool(ptr(ws["c1"]), ptr(x), b, H2, W2, 64, s), "df_enc_maxpool")
         # residual stages

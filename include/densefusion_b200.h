@@ -205,6 +205,11 @@ int df_conv_tc(const float* X, int B, int H, int W, int Cin, int ldx, const floa
                int dilation, const float* bias, const float* residual, int ldr, const float* prelu, int act, float* Y,
                int ldy, int Cout, int precision, void* stream);
 int df_enc_im2col_conv1(const float* img, float* A, int B, int H, int W, int ldk, void* stream);
+/* conv1 (7x7 / stride 2 / pad 3, 3 -> Cout <= 64 channels, lib/extractors.py:82) WITHOUT the patch matrix: a GEMM on the tcgen05 kernel whose A
+   operand the kernel gathers from the NCHW image itself (hybrid16s arithmetic).  planes / scale = df_pack_f16s of the (Cout, 160) weight
+   matrix, column c*49 + ky*7 + kx, zero-padded from 147.  Y (B*Ho*Wo, Cout) NHWC with pixel pitch ldy; relu != 0 fuses the ReLU. */
+int df_enc_conv1_tc(const float* img, int B, int H, int W, const void* planes, const float* scale, float* Y, int ldy, int Cout,
+                    int relu, void* stream);
 int df_enc_maxpool(const float* in, float* out, int B, int H, int W, int C, void* stream);
 int df_enc_im2col_s2(const float* in, float* A, int B, int H, int W, int C, void* stream);
 int df_enc_col2im_s2(const float* dA, float* dx, int B, int H, int W, int C, void* stream);   /* transpose of df_enc_im2col_s2 (training) */

@@ -288,3 +288,29 @@ def test_upconv_finish_staged_kernel_vs_conv_of_resized_map(B, C, h, w):
     check(lib.df_enc_upconv_finish(ptr(z), 9 * C, ptr(bs_d), ptr(slope_d), ptr(o), C + 32, B, h, w, C, stream()), "upconv_finish")
     assert rel(o[..., :C].permute(0, 3, 1, 2), want) < 5e-6
     assert float((o[..., C:] - 7.0).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 80, 80), (3, 40, 56), (1, 24, 16)])
+def test_conv1_gathered_by_the_kernel_vs_conv2d(B, H, W):
+    """df_enc_conv1_tc (7x7 / stride 2 / pad 3 with the patches gathered by the GEMM kernel's stagers, hybrid16s) == relu(conv2d) in float64,
+    borders and the masked tail of the last 256-row tile included; and == the im2col + GEMM path to rounding."""
+    from densefusion_b200._C import check, lib, ptr, stream
+    g = torch.Generator().manual_seed(B + H + W)
+    img = torch.randn(B, 3, H, W, generator=g)
+    w = torch.randn(64, 3, 7, 7, generator=g) * (2.0 / (49 * 64)) ** 0.5
+    want = torch.relu(F.conv2d(img.double(), w.double(), stride=2, padding=3))
+    w1 = torch.zeros(64, 160)
+    w1[:, :147] = w.reshape(64, 147)
+    sw = ops.SplitWeight(w1.cuda())
+    planes, scale = sw.planes16s()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.full((B, Ho, Wo, 96), 7.0, device="cuda")
+    imgc = img.cuda()
+    check(lib.df_enc_conv1_tc(ptr(imgc), B, H, W, ptr(planes), ptr(scale), ptr(y), 96, 64, 1, stream()), "df_enc_conv1_tc")
+    assert rel(y[..., :64].permute(0, 3, 1, 2), want) < 5e-6
+    assert float((y[..., 64:] - 7.0).abs().max()) == 0.0
+    a0 = torch.empty(B * Ho * Wo, 160, device="cuda")
+    check(lib.df_enc_im2col_conv1(ptr(imgc), ptr(a0), B, H, W, 160, stream()), "df_enc_im2col_conv1")
+    y2 = torch.empty(B * Ho * Wo, 64, device="cuda")
+    ops.gemm(a0, sw, None, y2, M=B * Ho * Wo, N=64, K=160, lda=160, ldw=160, ldc=64, relu=True, precision="hybrid16s")
+    assert rel(y[..., :64].reshape(-1, 64), y2) < 3e-6
