@@ -67,7 +67,7 @@ struct TcParams {
     // c1_H == 0: off.
     int c1_H, c1_W, c1_Ho, c1_Wo;
     int dbg;                                    // DF_TC_DBG knock-out bits (timing experiments only; results are wrong): 1 no global stores,
-                                                // 2 no transpose, 4 no TMEM load, 8 no MMAs, 16 no store instruction (reads / math of the store path kept)
+                                                // 2 no transpose, 4 no TMEM load, 8 no MMAs, 16 no store instruction (reads / math of the store path kept), 32 stagers skip the fp16 split, 64 stagers skip the TMEM store
     int run_steps;                              // host side only: MMA instructions per accumulation run, 0 = default
     // ---- weight-gradient form (df_conv_wgrad_tc): output column n = tap * wk_rows + ci multiplies row ci of the W operand
     // read wk_shift[tap] elements further along k (a 3x3 tap is an offset in the zero-padded, flattened pixel axis) ----
@@ -555,7 +555,10 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 hi[c * 4 + 0] = v.x; hi[c * 4 + 1] = v.y; hi[c * 4 + 2] = v.z; hi[c * 4 + 3] = v.w;
             }
             }
-            if (S16) {
+            if (S16 && (p.dbg & 32)) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) second[j] = hi[j];
+            } else if (S16) {
                 const float sa = a_sc;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -610,7 +613,8 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             } else {
                 tc_fence_after();
                 const uint32_t ta = tmem_base + lane_base + TMEM_A0 + (it % A_STAGES) * A_COLS;
-                if (S16) tmem_st32(ta, second);
+                if (p.dbg & 64) { if (second[0] == 0x12345678u) tmem_st32(ta, second); }
+                else if (S16) tmem_st32(ta, second);
                 else {
                     tmem_st32(ta, hi);
                     if (p.precise) tmem_st32(ta + BK, second);
