@@ -34,6 +34,7 @@ SIGNATURES = {
     "df_pack_bf16_pairs": [_p, _p, _ll, _i, _p],
     "df_pack_f16_pairs": [_p, _p, _p, _ll, _i, _p],
     "df_pack_f16s": [_p, _p, _p, _ll, _i, _p],
+    "df_tc_trace_read": [_p, _i],
     "df_enc_conv1_tc": [_p, _i, _i, _i, _p, _p, _p, _i, _i, _i, _p],
     "df_ew_relu_mask": [_p, _p, _p, _i, _i, _ll, _p],
     "df_ew_maxpool_backward": [_p, _p, _p, _i, _i, _i, _i, _p],
@@ -102,7 +103,7 @@ def _load():
 class _CountingLib:
     """Forwards to the CDLL and counts kernel-launching entry points (bench.py reports `gpu_launches`)."""
     _NO_LAUNCH = ("df_abi_version", "df_features", "df_gemm_rows_per_pool_tile", "df_conv_wgrad_scratch_floats", "df_conv_tc_macs",
-                  "df_ew_prelu_scratch_floats")
+                  "df_ew_prelu_scratch_floats", "df_tc_trace_read")
 
     _TIMED = ("df_gemm_tc", "df_conv_tc")
 

@@ -66,6 +66,10 @@ struct TcParams {
     // kx (K = 160: 147 + zero padding), so the 0.58 GB patch matrix of df_enc_im2col_conv1 and its trip through HBM disappear.
     // c1_H == 0: off.
     int c1_H, c1_W, c1_Ho, c1_Wo;
+    // DF_TC_DBG bit 256: cluster 0 / leader CTA records clock64() at the hand-over points of its first TRACE_KB k-blocks
+    // (producer: slot free, TMA issued; stager groups: bytes landed, TMEM slot free, A handed over; issuer: operands ready, MMAs
+    // committed) into `trace` [9][TRACE_KB]; df_tc_trace_read copies it out.  Timeline of the pipeline, no effect on results.
+    unsigned long long* trace;
     int dbg;                                    // DF_TC_DBG knock-out bits (timing experiments only; results are wrong): 1 no global stores,
                                                 // 2 no transpose, 4 no TMEM load, 8 no MMAs, 16 no store instruction (reads / math of the store path kept), 32 stagers skip the fp16 split, 64 stagers skip the TMEM store
     int run_steps;                              // host side only: MMA instructions per accumulation run, 0 = default
@@ -112,7 +116,7 @@ using namespace df_tc;
 // -1.61e-6 over 96 instructions, hybrid -2.31e-6 over 128, 3xtf32 -3.72e-6 over 192).  Effect on the bench configuration
 // (profiles/r2_c8_bias_comp.txt): worst pose error of 32 crops against the oracle 1.03e-4 -> 3.5e-5, rms GEMM error halved.
 constexpr float BIAS_COMP_H16 = 1.6e-8f, BIAS_COMP_HYBRID = 1.8e-8f, BIAS_COMP_3XTF32 = 1.9e-8f, BIAS_COMP_H16S = 1.6e-8f;
-constexpr int Q_THREADS = 18 * 32;
+constexpr int Q_THREADS = 19 * 32;                           // warp 18: the second TMA producer
 constexpr int Q_MAX_STAGES = 8;
 constexpr int Q_TILE = 128 * BK * 4;                         // 16 KB: one 128-row fp32 tile of 32 k
 constexpr int Q_SMEM_STAGES = 12 * Q_TILE;                   // 192 KB of operand stages: 4 x {A 16 KB | W_hi 16 | W_lo 16} for 128
@@ -121,6 +125,9 @@ constexpr int Q_SMEM_STAGES = 12 * Q_TILE;                   // 192 KB of operan
 constexpr int Q_SMEM_EPI = 8 * 32 * 32 * 4;                  // 32 KB: one swizzled 32x32 transpose tile per epilogue warp
 constexpr int Q_SMEM_TOTAL = 1024 + Q_SMEM_STAGES + Q_SMEM_EPI + 512;
 static_assert(Q_SMEM_TOTAL <= 227 * 1024, "shared memory overflow");
+
+constexpr int TRACE_KB = 96;
+#define DF_TRACE(ev, it_) do { if (p.trace && cid == 0 && rank == 0 && (it_) < (uint32_t)TRACE_KB && lane == 0) p.trace[(ev) * TRACE_KB + (it_)] = clock64(); } while (0)
 
 struct QTile {
     int g, n0, row0, rows_valid, crop, pool_tile;
@@ -291,7 +298,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // sample of 512 (row, 4-column group) positions along a diagonal, twice, read by the 16 stager / epilogue warps of EVERY CTA (same addresses, hence the same scale everywhere
     // and from run to run; L2 hits after the first CTA) while the TMA producer is already filling the pipeline.
     float a_sc = 1.0f;
-    if (S16 && warp >= 2) {
+    if (S16 && warp >= 2 && warp < 18) {
         a_sc = p.a_scale;
         if (a_sc == 0.0f) {
             const int t = (int)threadIdx.x - 64;                                  // 0..511
@@ -320,14 +327,19 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
     // Ring positions are kept as (slot, phase) counters: the stage count is a runtime value, and `it % Q_STAGES` in the issuing warp's
     // loop was an integer division (MUFU.RCP + ~20 dependent instructions) per k-block on the kernel's critical path.
-    if (warp == 0) {
-        // ------------------------------- TMA producer -------------------------------
+    if (warp == 0 || warp == 18) {
+        // ------------------------------- TMA producers (two warps, alternating k-blocks) -------------------------------
+        // The clock64 timeline (DF_TC_DBG bit 256) showed ONE producer warp needing ~700 clocks per k-block -- ~450 of them between
+        // "slot free" and "both TMA instructions issued" -- which paced every launch shape once the issuer's loop had been shortened;
+        // two warps take the even / odd k-blocks of the same sequence (each waits for and fills its own slots).
+        const uint32_t pw = warp == 0 ? 0u : 1u;
         const uint32_t a_bytes = p.conv_taps ? (uint32_t)(p.TW * p.TH * p.TB) * BK * 4 : (uint32_t)Q_TILE;
         // 3xTF32: W_hi + W_lo; hybrid: W_hi + bf16 pair tile; hybrid16: pair tile + a half-width (64 B rows) correction tile
         const uint32_t bytes = (p.c1_H ? 0u : a_bytes) + (S16 ? w_bytes : p.precise == 3 ? w_bytes + w_bytes / 2 : (p.precise ? 2u : 1u) * w_bytes);
         const int cblocks = p.conv_taps ? p.K / (BK * p.conv_taps) : 1;        // 32-channel blocks per tap
         int s = 0;
         uint32_t ph = 1;                                                       // parity of "slot is free": passes at once in round 0
+        uint32_t pit = 0, e_ready = 0;
         for (int t = t_first; t < total_tiles; t += t_step) {
             const QTile c = q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, rank);
             int wrow = c.g * p.N + c.n0 + rank * bn_cta;
@@ -344,10 +356,22 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             for (int tap = 8; tap >= 0; --tap)
                 if ((c.taps >> tap) & 1u) tap_list = (tap_list << 4) | (uint64_t)tap;
             int cb = 0;
-            for (int j = 0; j < nkb_t; ++j) {
-                mbar_wait(empty + s, ph);
-                if (elect_one()) {
-                    mbar_expect_tx(full + s, bytes);
+            for (int j = 0; j < nkb_t; ++j, ++pit) {
+                const bool mine = (pit & 1u) == pw;
+                if (mine) {
+                if (!e_ready) mbar_wait(empty + s, ph);
+                DF_TRACE(0, pit);
+                {                                                               // (state of MY next slot: round trip overlaps the TMA issue)
+                    int sn = s + 2; uint32_t phn = ph;
+                    if (sn >= Q_STAGES) { sn -= Q_STAGES; phn ^= 1u; }
+                    e_ready = mbar_try(empty + sn, phn);
+                }
+                }
+                if (mine && elect_one()) {
+                    // (DF_TC_DBG bit 128: the activation box is fetched for the first tap of a channel block only -- what a 3x3 convolution
+                    // would pull through the port if the nine taps shared one haloed box; timing experiment, wrong results)
+                    const bool skip_a = (p.dbg & 128) && p.conv_taps == 9 && j >= cblocks;
+                    mbar_expect_tx(full + s, skip_a ? bytes - a_bytes : bytes);
                     uint8_t* dst = smem + (size_t)s * stage_bytes;
                     int kb = j;                                                 // k-block of the weight matrix
                     if (p.conv_taps) {
@@ -356,7 +380,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         const int dy = p.conv_taps == 9 ? (ky - 1) * p.conv_dil : 0;
                         const int dx = p.conv_taps == 9 ? (kx - 1) * p.conv_dil : 0;
                         kb = tap * cblocks + cb;
-                        tma_load_4d(&tm_a, dst, full + s, cb * BK, c.x0 + dx, c.y0 + dy, c.b0);
+                        if (!skip_a) tma_load_4d(&tm_a, dst, full + s, cb * BK, c.x0 + dx, c.y0 + dy, c.b0);
                     } else if (!p.c1_H) {
                         tma_load_2d(&tm_a, dst, full + s, acol + kb * BK, c.row0);
                     }
@@ -369,6 +393,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (++cb == cblocks) { cb = 0; tap_list >>= 4; }
                 if (++s == Q_STAGES) { s = 0; ph ^= 1u; }
                 __syncwarp();
+                if (mine) DF_TRACE(1, pit);
             }
         }
     } else if (warp == 1) {
@@ -379,7 +404,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const uint32_t idesc_h = f16_instr_desc(bnt, 128 * CTAS);
             uint32_t it = 0, ti = 0;
             int s = 0;
-            uint32_t ph = 0;
+            uint32_t ph = 0, a_ready = 0;
             const int cblocks = p.conv_taps ? p.K / (BK * p.conv_taps) : 1;
             for (int t = t_first; t < total_tiles; t += t_step) {
               const int nkb_t = p.conv_taps == 9 ? __popc(q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, 0).taps) * cblocks : nkb;
@@ -391,8 +416,20 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (CTAS == 2) mbar_wait_cluster(acc_empty + ab, aph); else mbar_wait(acc_empty + ab, aph);
                 const uint32_t acc = tmem_base + ab * ACC_STRIDE;
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    mbar_wait(full + s, ph);
-                    if (CTAS == 2) mbar_wait_cluster(a_full + s, ph); else mbar_wait(a_full + s, ph);
+                    // a_full[s] alone: the stagers of BOTH CTAs arrive on it only after their own full[s] (A and weight tile of the
+                    // stage, one barrier) has completed, so it implies that every byte the MMAs of this k-block read has landed --
+                    // the peer's half of the weight tile never had another guard.  (Measured with the clock64 timeline, DF_TC_DBG
+                    // bit 256: this warp's serial loop, ~900 clocks per k-block with two ~200-clock barrier round trips in it, paced
+                    // tower-1 -- not the tensor pipe, not the operand stream.)  The state of the NEXT slot is probed before the MMAs
+                    // of this one are issued, so its round trip overlaps them.
+                    DF_TRACE(2, it);
+                    if (!a_ready) mbar_wait(a_full + s, ph);
+                    DF_TRACE(3, it);
+                    {
+                        int sn = s + 1; uint32_t phn = ph;
+                        if (sn == Q_STAGES) { sn = 0; phn ^= 1u; }
+                        a_ready = mbar_try(a_full + sn, phn);
+                    }
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t w_hi = smem_u32(smem + (size_t)s * stage_bytes + Q_TILE);
@@ -484,6 +521,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     }
                     if (++s == Q_STAGES) { s = 0; ph ^= 1u; }
                     __syncwarp();
+                    DF_TRACE(4, it);
                 }
               }
             }
@@ -548,6 +586,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (c1_kb >= nkb) { c1_kb -= nkb; ++c1_tile; }
             } else {
             mbar_wait(full + s, ph);
+            if (q == 0) DF_TRACE(5, it);
             const uint8_t* arow = smem + (size_t)s * stage_bytes + r * 128;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -601,7 +640,9 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             // TMEM A slot it % A_STAGES was last read by the MMAs of iteration it - A_STAGES.  With A_STAGES >= Q_STAGES that is
             // implied by full[s] (the commit that frees the slot is what let the TMA refill the stage); with fewer TMEM slots wait
             // for that iteration's commit explicitly (same barrier the TMA producer watches; the loads and the split above overlap it).
+            if (q == 0) DF_TRACE(6, it);
             if (sp >= 0 && A_STAGES < Q_STAGES) mbar_wait(empty + sp, php);
+            if (q == 0) DF_TRACE(7, it);
             if (A_SMEM) {
                 uint8_t* prow = aring + (size_t)(it % A_STAGES) * Q_TILE + r * 128;
 #pragma unroll
@@ -626,6 +667,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if (lane == 0) {
                 if (CTAS == 2) mbar_arrive_remote(a_full + s, 0); else mbar_arrive(a_full + s);
             }
+            if (q == 0) DF_TRACE(8, it);
             s += 2; if (s >= Q_STAGES) { s -= Q_STAGES; ph ^= 1u; }
             sp += 2; if (sp >= Q_STAGES) { sp -= Q_STAGES; php ^= 1u; }
         }
@@ -978,6 +1020,8 @@ int pair_m_tiles(const TcParams& p)
            : p.pool_partial ? (p.M / p.rows_per_crop) * ((p.rows_per_crop + 255) / 256) : (p.M + 255) / 256;
 }
 
+unsigned long long* g_trace = nullptr;
+
 template <int CTAS, int A_STAGES, int A_COLS = 64>
 int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw, int groups, cudaStream_t s)
 {
@@ -1009,6 +1053,12 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
         }
         static const int dbg = getenv("DF_TC_DBG") ? atoi(getenv("DF_TC_DBG")) : 0;
         p.dbg = dbg;
+        p.trace = nullptr;
+        if (dbg & 256) {
+            if (!g_trace && cudaMalloc(&g_trace, 9 * TRACE_KB * sizeof(unsigned long long)) != cudaSuccess) return DF_ERR_UNSUPPORTED;
+            cudaMemsetAsync(g_trace, 0, 9 * TRACE_KB * sizeof(unsigned long long), s);
+            p.trace = g_trace;
+        }
         static const int env_steps = getenv("DF_TC_RUN_STEPS") ? atoi(getenv("DF_TC_RUN_STEPS")) : 216;
         const int run_steps = p.run_steps > 0 ? p.run_steps : env_steps;
         const int per_kb = p.precise == 1 ? 12 : (p.precise == 2 ? 8 : 6);
@@ -1455,6 +1505,15 @@ extern "C" int df_pack_f16_pairs(const float* w, void* t1, void* t2, long long r
     const long long total = rows * (K / 2);
     pack_f16_pairs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, (uint32_t*)t1, (uint32_t*)t2, rows, K);
     DF_RETURN_LAST_ERROR();
+}
+
+// DF_TC_DBG bit 256: the clock64() timeline of the last traced launch, [9 events][96 k-blocks] (see TcParams::trace)
+extern "C" int df_tc_trace_read(unsigned long long* host_out, int count)
+{
+    if (!host_out || count <= 0 || count > 9 * TRACE_KB) return DF_ERR_ARG;
+    if (!g_trace) return DF_ERR_UNSUPPORTED;
+    cudaError_t e = cudaMemcpy(host_out, g_trace, (size_t)count * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    return e == cudaSuccess ? 0 : (int)e;
 }
 
 extern "C" int df_pack_f16s(const float* w, void* planes, float* scale, long long rows, int K, void* stream)

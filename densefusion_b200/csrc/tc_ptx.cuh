@@ -23,12 +23,31 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// One non-blocking probe of the barrier's phase (the result can be consumed later: lets the single-warp producer / issuer loops ask
+// for the NEXT slot's state while they still work on the current one -- the probe's round trip is ~100-200 clocks even when the phase
+// completed long ago, and those loops are serial)
+// (test_wait, not try_wait: try_wait may suspend the thread for a system-dependent time when the phase is still open -- measured: probing
+// the next slot with try_wait made the kernel 30-50% SLOWER)
+__device__ __forceinline__ uint32_t mbar_try(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok;
+}
 // Bounded wait: a protocol bug must trap (launch error) rather than hang the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     const uint32_t addr = smem_u32(bar);
-    const long long t0 = clock64();
     uint32_t ok = 0;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return;
+    const long long t0 = clock64();
     while (true) {
         asm volatile("{\n\t.reg .pred p;\n\t"
                      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"

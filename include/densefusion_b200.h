@@ -118,6 +118,10 @@ int df_pack_f16_pairs(const float* w, void* t1, void* t2, long long rows, int K,
  * product inside [2^-8, 2^15] after scaling: 22 significant bits above 0.25, an absolute error of 2^-25 below).  W_hi = planes, W_lo = scale;
  * needs ldw == K. */
 int df_pack_f16s(const float* w, void* planes, float* scale, long long rows, int K, void* stream);
+/* Debug aid of the tensor-core kernel (env DF_TC_DBG bit 256): clock64() timeline of cluster 0's first 96 k-blocks of the last launch,
+ * [9 events][96]: producer slot free / TMA issued, issuer stage landed / A handed over / MMAs committed, stager bytes landed /
+ * split done / TMEM slot free / A handed over.  count <= 864 uint64 copied to host memory. */
+int df_tc_trace_read(unsigned long long* host_out, int count);
 /* Accumulation runs: long k loops are cut into runs on fresh accumulators, summed in fp32 through C (the tensor core
  * truncates while accumulating; the bias grows with the number of chained instructions).  Default 216 MMA instructions per
  * run; bits 8..15 of `precision` (df_gemm_tc and df_conv_tc) select another length in units of 12 instructions -- the
