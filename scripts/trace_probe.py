@@ -35,3 +35,14 @@ for it in range(24, 72):
 print(json.dumps({"case": case, "per_kblock_clks": float((t[4, 71] - t[4, 24]) / 47.0)}))
 for r in rows[:36]:
     print(" ".join(f"{k}={v}" for k, v in r.items()))
+
+# compact statistics over k-blocks 24..71: mean period of every event and mean latency between consecutive hand-over points
+sel = slice(24, 72)
+def period(e):
+    v = t[e, sel]; v = v[v > 0]
+    return float(np.mean(np.diff(v))) if len(v) > 2 else None
+print(json.dumps({"period": {n: period(e) for e, n in enumerate(names)},
+                  "latency": {"slot_free->issued": float(np.mean(t[1, sel] - t[0, sel])), "issued->stager_sees_bytes": float(np.mean(t[5, sel] - t[1, sel])),
+                              "stager: bytes->split": float(np.mean(t[6, sel] - t[5, sel])), "stager: split->slot_free": float(np.mean(t[7, sel] - t[6, sel])),
+                              "stager: slot_free->handed": float(np.mean(t[8, sel] - t[7, sel])), "handed->issuer_has_A": float(np.mean(t[3, sel] - t[8, sel])),
+                              "issuer: A->committed": float(np.mean(t[4, sel] - t[3, sel])), "issuer: committed->next_loop": float(np.mean(t[2, 25:72] - t[4, 24:71]))}}))
