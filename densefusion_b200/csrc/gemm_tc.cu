@@ -68,7 +68,7 @@ struct TcParams {
     int c1_H, c1_W, c1_Ho, c1_Wo;
     // DF_TC_DBG bit 256: cluster 0 / leader CTA records clock64() at the hand-over points of its first TRACE_KB k-blocks
     // (producer: slot free, TMA issued; stager groups: bytes landed, TMEM slot free, A handed over; issuer: operands ready, MMAs
-    // committed) into `trace` [9][TRACE_KB]; df_tc_trace_read copies it out.  Timeline of the pipeline, no effect on results.
+    // committed) into `trace` [TRACE_EV][TRACE_KB]; df_tc_trace_read copies it out.  Timeline of the pipeline, no effect on results.
     unsigned long long* trace;
     int dbg;                                    // DF_TC_DBG knock-out bits (timing experiments only; results are wrong): 1 no global stores,
                                                 // 2 no transpose, 4 no TMEM load, 8 no MMAs, 16 no store instruction (reads / math of the store path kept), 32 stagers skip the fp16 split, 64 stagers skip the TMEM store
@@ -127,7 +127,9 @@ constexpr int Q_SMEM_TOTAL = 1024 + Q_SMEM_STAGES + Q_SMEM_EPI + 512;
 static_assert(Q_SMEM_TOTAL <= 227 * 1024, "shared memory overflow");
 
 constexpr int TRACE_KB = 96;
-#define DF_TRACE(ev, it_) do { if (p.trace && cid == 0 && rank == 0 && (it_) < (uint32_t)TRACE_KB && lane == 0) p.trace[(ev) * TRACE_KB + (it_)] = clock64(); } while (0)
+constexpr int TRACE_EV = 17;                                  // 0-8 per k-block (see TcParams::trace); 9-13 per accumulation run: epilogue warp 10 waits for / has / has drained the
+                                                             // accumulator, issuer waits for / has a free accumulator; 14-16 per chunk of warp 10: accumulator in registers / transposed / stored
+#define DF_TRACE(ev, it_) do { if (DBG && p.trace && cid == 0 && rank == 0 && (it_) < (uint32_t)TRACE_KB && lane == 0) p.trace[(ev) * TRACE_KB + (it_)] = clock64(); } while (0)
 
 struct QTile {
     int g, n0, row0, rows_valid, crop, pool_tile;
@@ -206,10 +208,19 @@ template <int ACT>
 __device__ __forceinline__ void epi_store_simple(const float* srow, int sw0, int sw1, char* cbase, uint32_t ldcb, const int (&roff)[8],
                                                  float4 b, float slope, bool no_store = false)
 {
+    // the rows are read ahead of the stores, four at a time: with the row mask tested first every row was its own branch region and the
+    // LDS -> FADD -> STG chains ran one after the other through the same four registers (ncu source view: ~70 short-scoreboard
+    // samples on each of the eight FADDs, the largest item of the epilogue warps' stalls)
 #pragma unroll
-    for (int ps = 0; ps < 8; ++ps) {
+    for (int pb = 0; pb < 8; pb += 4) {
+    float4 rows[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rows[i] = *reinterpret_cast<const float4*>(srow + (pb + i) * 128 + ((i & 1) ? sw1 : sw0));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ps = pb + i;
         if (roff[ps] < 0) continue;
-        float4 o = *reinterpret_cast<const float4*>(srow + ps * 128 + ((ps & 1) ? sw1 : sw0));
+        float4 o = rows[i];
         o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
         if (ACT == 1) {
             o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
@@ -220,9 +231,13 @@ __device__ __forceinline__ void epi_store_simple(const float* srow, int sw0, int
         if (no_store && o.x != 12345.678f) continue;          // (DF_TC_DBG bit 16: everything but the store instruction itself)
         *reinterpret_cast<float4*>(cbase + (unsigned long long)(uint32_t)roff[ps] * ldcb) = o;
     }
+    }
 }
 
-template <int CTAS, int A_STAGES, int A_COLS>
+// DBG: the knock-out bits and the clock64 timeline (TcParams::dbg / trace) exist in a second instantiation only, launched when
+// DF_TC_DBG is set -- as run-time tests inside the role loops they cost registers and instructions on every path (measured: a few more
+// conditionals and 24 bytes of additional spills made the short-K GEMMs 10-18% slower, profiles/r2_s3_variants.jsonl).
+template <int CTAS, int A_STAGES, int A_COLS, bool DBG>
 __global__ void __launch_bounds__(Q_THREADS, 1)
 gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_whi,
                  const __grid_constant__ CUtensorMap tm_wlo, const TcParams p, const int bn_cta, const int m_tiles,
@@ -237,6 +252,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // (one accumulator with A in TMEM: exposed, ~20% of the pooled conv6 layer, ~12% of the long-K convolutions) overlaps the next run.
     constexpr bool A_SMEM = A_COLS == 0;
     constexpr bool S16 = A_COLS == 32 || A_SMEM;
+    const int dbg = DBG ? p.dbg : 0;
     constexpr int TMEM_A0 = 512 - A_STAGES * A_COLS;
     constexpr int ACC_STRIDE = TMEM_A0 / 2;
     extern __shared__ uint8_t smem_raw[];
@@ -264,7 +280,12 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // (the pooled epilogue keeps its per-warp column sums in the last 8 KB of the stage area: one stage less when the ring fills it)
     const uint32_t pool_bytes = p.pool_partial ? 8192u : (p.c1_H ? 2048u : 0u);      // (conv1 form: the patch offset table lives there)
     const uint32_t aring_bytes = A_SMEM ? (uint32_t)A_STAGES * Q_TILE : 0u;
-    const int Q_STAGES = (int)min((uint32_t)Q_MAX_STAGES, ((uint32_t)Q_SMEM_STAGES - pool_bytes - aring_bytes) / stage_bytes);
+    // An EVEN number of stages: the two stager groups (and the two producer warps) take alternate k-blocks, so with an even ring a stage
+    // always belongs to the same group and that group sees every fill of it; with an odd ring a group would see every OTHER fill -- all of
+    // the same barrier parity -- and a group running ahead could take fill i for fill i + 2.
+    int q_stages = (int)min((uint32_t)Q_MAX_STAGES, ((uint32_t)Q_SMEM_STAGES - pool_bytes - aring_bytes) / stage_bytes);
+    if (q_stages > 2) q_stages &= ~1;
+    const int Q_STAGES = q_stages;
     uint8_t* const aring = smem + (size_t)Q_STAGES * stage_bytes;           // A_SMEM: the operand-plane ring of A (1024-byte aligned)
     const int t_first = cid, t_step = ncl;                                  // tile walk of this cluster: round robin over all tiles
     const uint32_t ACC_BUFS = bnt <= ACC_STRIDE ? 2 : 1;
@@ -370,7 +391,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (mine && elect_one()) {
                     // (DF_TC_DBG bit 128: the activation box is fetched for the first tap of a channel block only -- what a 3x3 convolution
                     // would pull through the port if the nine taps shared one haloed box; timing experiment, wrong results)
-                    const bool skip_a = (p.dbg & 128) && p.conv_taps == 9 && j >= cblocks;
+                    const bool skip_a = (dbg & 128) && p.conv_taps == 9 && j >= cblocks;
                     mbar_expect_tx(full + s, skip_a ? bytes - a_bytes : bytes);
                     uint8_t* dst = smem + (size_t)s * stage_bytes;
                     int kb = j;                                                 // k-block of the weight matrix
@@ -413,7 +434,9 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 const int kb0 = kc * p.kbc, kb1 = min(nkb_t, kb0 + p.kbc);
                 const uint32_t ab = ti & acc_shift;
                 const uint32_t aph = ((ti >> acc_shift) & 1) ^ 1;
+                DF_TRACE(12, ti);
                 if (CTAS == 2) mbar_wait_cluster(acc_empty + ab, aph); else mbar_wait(acc_empty + ab, aph);
+                DF_TRACE(13, ti);
                 const uint32_t acc = tmem_base + ab * ACC_STRIDE;
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     // a_full[s] alone: the stagers of BOTH CTAs arrive on it only after their own full[s] (A and weight tile of the
@@ -435,7 +458,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                         const uint32_t w_hi = smem_u32(smem + (size_t)s * stage_bytes + Q_TILE);
                         const uint64_t bhi0 = sw128_desc(w_hi), blo0 = sw128_desc(w_hi + w_bytes);
                         const uint32_t a0 = tmem_base + TMEM_A0 + (it % A_STAGES) * A_COLS;
-                        if (p.dbg & 8) {
+                        if (dbg & 8) {
                         } else if (A_SMEM) {
                             // hybrid16s with A in shared memory: rows [fp16(a) x32 | fp16(a - fp16(a)) x32], same layout as the weight tile
                             const uint64_t ad0 = sw128_desc(smem_u32(aring + (size_t)(it % A_STAGES) * Q_TILE));
@@ -494,7 +517,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             }
                         }
                         }
-                        if (!S16 && p.precise == 2 && !(p.dbg & 8)) {
+                        if (!S16 && p.precise == 2 && !(dbg & 8)) {
                             // hybrid: the two correction terms are ~2^-11 of the main one, so bf16 operands (K = 16 per
                             // instruction, twice the TF32 rate) keep them to 2^-20 of the result: 4 + 4 instructions per
                             // k-block instead of 12.  TMEM A stage: [0,32) tf32 hi | [32,48) bf16(a) pairs | [48,64) bf16(a_lo);
@@ -594,7 +617,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 hi[c * 4 + 0] = v.x; hi[c * 4 + 1] = v.y; hi[c * 4 + 2] = v.z; hi[c * 4 + 3] = v.w;
             }
             }
-            if (S16 && (p.dbg & 32)) {
+            if (S16 && (dbg & 32)) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) second[j] = hi[j];
             } else if (S16) {
@@ -654,7 +677,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             } else {
                 tc_fence_after();
                 const uint32_t ta = tmem_base + lane_base + TMEM_A0 + (it % A_STAGES) * A_COLS;
-                if (p.dbg & 64) { if (second[0] == 0x12345678u) tmem_st32(ta, second); }
+                if (dbg & 64) { if (second[0] == 0x12345678u) tmem_st32(ta, second); }
                 else if (S16) tmem_st32(ta, second);
                 else {
                     tmem_st32(ta, hi);
@@ -723,6 +746,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                   for (int ps = 0; ps < 8; ++ps) {
                       const int R = q * 32 + ps * 4 + rr;
                       roff[ps] = R < c.rows_valid ? c.row0 + R : -1;
+                      if ((dbg & 512) && roff[ps] >= 0) roff[ps] &= 1023;      // (knock-out: the output folded onto 1024 rows -- it stays in L2)
                   }
                   if (row_ok) myrow = c.row0 + r;
                   if (bias && p.bias_crop_stride) {
@@ -751,7 +775,9 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
             // the simple store: one run, no skip connection, one bias vector for all 32 rows of the warp
             const bool simple = first_run && last_run && !p.residual && !straddle;
+            if (ew == 0) DF_TRACE(9, ti);
             mbar_wait(acc_full + ab, (ti >> acc_shift) & 1);
+            if (ew == 0) DF_TRACE(10, ti);
             tc_fence_after();
             if (last_run && !first_run) {                      // the partial sums were written / added by OTHER lanes of this warp
                 __threadfence();
@@ -769,11 +795,12 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     b0 = __ldg(reinterpret_cast<const float4*>(bias + cq));
                     if (straddle) b1 = __ldg(reinterpret_cast<const float4*>(bias + p.bias_crop_stride + cq));
                 }
-                if (p.dbg & 4) {
+                if (dbg & 4) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = 0u;
                 } else
                 tmem_ld32(tmem_base + lane_base + ab * ACC_STRIDE + ch * 32, v);
+                if (ew == 0) DF_TRACE(14, ti * 4 + (ch >> 1));
                 if (run_scale != 1.0f) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * run_scale);
@@ -828,17 +855,18 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     // transpose through a swizzled 32x32 tile: lane == row on the way in, 8 lanes == one 128 B row out;
                     // bias / skip connection / activation are applied on the way out (coalesced float4 accesses)
                     __syncwarp();
-                    if (!(p.dbg & 2)) {
+                    if (!(dbg & 2)) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         *reinterpret_cast<uint4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) =
                             make_uint4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
                     }
                     __syncwarp();
-                    if (cq < p.N && !(p.dbg & 1)) {
+                    if (ew == 0) DF_TRACE(15, ti * 4 + (ch >> 1));
+                    if (cq < p.N && !(dbg & 1)) {
                         char* cbase = reinterpret_cast<char*>(Cg + cq);
                         if (simple) {
-                            const bool ns = (p.dbg & 16) != 0;
+                            const bool ns = (dbg & 16) != 0;
                             if (p.relu == 1) epi_store_simple<1>(srow, sw0, sw1, cbase, ldcb, roff, b0, slope, ns);
                             else if (p.relu == 2) epi_store_simple<2>(srow, sw0, sw1, cbase, ldcb, roff, b0, slope, ns);
                             else epi_store_simple<0>(srow, sw0, sw1, cbase, ldcb, roff, b0, slope, ns);
@@ -883,10 +911,12 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             }
                         }
                     }
+                    if (ew == 0) DF_TRACE(16, ti * 4 + (ch >> 1));
                 }
             }
             tc_fence_before();
             __syncwarp();
+            if (ew == 0) DF_TRACE(11, ti);
             if (lane == 0) {
                 if (CTAS == 2) mbar_arrive_remote(acc_empty + ab, 0); else mbar_arrive(acc_empty + ab);
             }
@@ -1055,8 +1085,8 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
         p.dbg = dbg;
         p.trace = nullptr;
         if (dbg & 256) {
-            if (!g_trace && cudaMalloc(&g_trace, 9 * TRACE_KB * sizeof(unsigned long long)) != cudaSuccess) return DF_ERR_UNSUPPORTED;
-            cudaMemsetAsync(g_trace, 0, 9 * TRACE_KB * sizeof(unsigned long long), s);
+            if (!g_trace && cudaMalloc(&g_trace, TRACE_EV * TRACE_KB * sizeof(unsigned long long)) != cudaSuccess) return DF_ERR_UNSUPPORTED;
+            cudaMemsetAsync(g_trace, 0, TRACE_EV * TRACE_KB * sizeof(unsigned long long), s);
             p.trace = g_trace;
         }
         static const int env_steps = getenv("DF_TC_RUN_STEPS") ? atoi(getenv("DF_TC_RUN_STEPS")) : 216;
@@ -1077,7 +1107,9 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
         cudaGetDevice(&dev);
         cudaError_t e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_TOTAL);
+        e = cudaFuncSetAttribute(gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_TOTAL);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_TOTAL);
         if (e != cudaSuccess) return (int)e;
         int n = num_sms / CTAS;
         if (CTAS == 2) {
@@ -1088,7 +1120,7 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
             at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             q.attrs = at; q.numAttrs = 1;
             int occ = 0;
-            if (cudaOccupancyMaxActiveClusters(&occ, gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS>, &q) == cudaSuccess && occ > 0 && occ < n) n = occ;
+            if (cudaOccupancyMaxActiveClusters(&occ, gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS, false>, &q) == cudaSuccess && occ > 0 && occ < n) n = occ;
             (void)cudaGetLastError();
         }
         max_clusters = n;
@@ -1154,7 +1186,8 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = use_pdl() ? 2 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS>, ma, mhi, mlo, p, bn_cta, m_tiles, n_tiles, total);
+    cudaError_t e = p.dbg ? cudaLaunchKernelEx(&cfg, gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS, true>, ma, mhi, mlo, p, bn_cta, m_tiles, n_tiles, total)
+                          : cudaLaunchKernelEx(&cfg, gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS, false>, ma, mhi, mlo, p, bn_cta, m_tiles, n_tiles, total);
     return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -1510,7 +1543,7 @@ extern "C" int df_pack_f16_pairs(const float* w, void* t1, void* t2, long long r
 // DF_TC_DBG bit 256: the clock64() timeline of the last traced launch, [9 events][96 k-blocks] (see TcParams::trace)
 extern "C" int df_tc_trace_read(unsigned long long* host_out, int count)
 {
-    if (!host_out || count <= 0 || count > 9 * TRACE_KB) return DF_ERR_ARG;
+    if (!host_out || count <= 0 || count > TRACE_EV * TRACE_KB) return DF_ERR_ARG;
     if (!g_trace) return DF_ERR_UNSUPPORTED;
     cudaError_t e = cudaMemcpy(host_out, g_trace, (size_t)count * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     return e == cudaSuccess ? 0 : (int)e;

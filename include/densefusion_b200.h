@@ -119,8 +119,10 @@ int df_pack_f16_pairs(const float* w, void* t1, void* t2, long long rows, int K,
  * needs ldw == K. */
 int df_pack_f16s(const float* w, void* planes, float* scale, long long rows, int K, void* stream);
 /* Debug aid of the tensor-core kernel (env DF_TC_DBG bit 256): clock64() timeline of cluster 0's first 96 k-blocks of the last launch,
- * [9 events][96]: producer slot free / TMA issued, issuer stage landed / A handed over / MMAs committed, stager bytes landed /
- * split done / TMEM slot free / A handed over.  count <= 864 uint64 copied to host memory. */
+ * [17 events][96]: per k-block producer slot free / TMA issued, issuer stage landed / A handed over / MMAs committed, stager bytes landed /
+ * split done / TMEM slot free / A handed over; per accumulation run epilogue waits for / has / has drained the accumulator, issuer waits
+ * for / has a free accumulator; per chunk of epilogue warp 10 accumulator in registers / transposed / stored.  count <= 1632 uint64
+ * copied to host memory. */
 int df_tc_trace_read(unsigned long long* host_out, int count);
 /* Accumulation runs: long k loops are cut into runs on fresh accumulators, summed in fp32 through C (the tensor core
  * truncates while accumulating; the bias grows with the number of chained instructions).  Default 216 MMA instructions per

@@ -17,6 +17,7 @@ dev = "cuda"
 modes = sys.argv[1:] or ["hybrid16", "hybrid16s"]
 torch.manual_seed(0)
 REPS = 20
+ONLY = [t for t in os.environ.get("DF_AB_ONLY", "").split(",") if t]      # substrings of the case names to run (default: all)
 
 
 def timeit(fn):
@@ -33,6 +34,8 @@ def timeit(fn):
 
 
 def gemm_case(name, M, N, K, pooled=False, percrop=False, groups=1, n=500):
+    if ONLY and not any(t in name for t in ONLY):
+        return
     A = [torch.randn(M, K * groups, device=dev) for _ in range(2)]
     W = ops.SplitWeight(torch.randn(groups * N, K, device=dev) / K ** 0.5)
     crops = M // n
@@ -62,6 +65,8 @@ def gemm_case(name, M, N, K, pooled=False, percrop=False, groups=1, n=500):
 
 
 def conv_case(name, B, H, W, Cin, Cout, dil):
+    if ONLY and not any(t in name for t in ONLY):
+        return
     x = [torch.randn(B, H, W, Cin, device=dev) for _ in range(2)]
     w = _pack_conv(torch.randn(Cout, Cin, 3, 3, device=dev) / (9 * Cin) ** 0.5)
     o = [torch.empty(B, H, W, Cout, device=dev) for _ in range(2)]
@@ -84,6 +89,7 @@ gemm_case("tower1 (bench roofline kernel)", rows, 1920, 384, percrop=True)
 gemm_case("tower2 grouped", rows, 256, 640, groups=3)
 gemm_case("tower3 grouped", rows, 128, 256, groups=3)
 gemm_case("conv5", rows, 512, 256)
+gemm_case("conv5 K=384", rows, 512, 384)
 gemm_case("conv6 pooled", rows, 1024, 512, pooled=True)
 gemm_case("pf conv2 (K=64)", rows, 128, 64)
 gemm_case("up_1 low-res GEMM", 25600, 2304, 1024)

@@ -24,9 +24,10 @@ else:
 for _ in range(3):
     run()
 torch.cuda.synchronize()
-buf = (ctypes.c_ulonglong * (9 * 96))()
-assert lib.df_tc_trace_read(ctypes.cast(buf, ctypes.c_void_p), 9 * 96) == 0
-t = np.array(buf, dtype=np.int64).reshape(9, 96)
+EV = 17
+buf = (ctypes.c_ulonglong * (EV * 96))()
+assert lib.df_tc_trace_read(ctypes.cast(buf, ctypes.c_void_p), EV * 96) == 0
+t = np.array(buf, dtype=np.int64).reshape(EV, 96)
 names = ["prod_slot_free", "prod_issued", "iss_full", "iss_afull", "iss_done", "stg_full", "stg_split", "stg_slot_free", "stg_handed"]
 t0 = t[t > 0].min()
 rows = []
@@ -46,3 +47,12 @@ print(json.dumps({"period": {n: period(e) for e, n in enumerate(names)},
                               "stager: bytes->split": float(np.mean(t[6, sel] - t[5, sel])), "stager: split->slot_free": float(np.mean(t[7, sel] - t[6, sel])),
                               "stager: slot_free->handed": float(np.mean(t[8, sel] - t[7, sel])), "handed->issuer_has_A": float(np.mean(t[3, sel] - t[8, sel])),
                               "issuer: A->committed": float(np.mean(t[4, sel] - t[3, sel])), "issuer: committed->next_loop": float(np.mean(t[2, 25:72] - t[4, 24:71]))}}))
+
+# per accumulation run (tile): the epilogue's and the issuer's view of the accumulator hand-over, and the chunks of epilogue warp 10
+ev = ["epi_wait", "epi_has_acc", "epi_drained", "iss_wait_acc", "iss_has_acc"]
+for ti in range(0, 10):
+    print(f"run={ti} " + " ".join(f"{n}={int(t[9 + e, ti] - t0) if t[9 + e, ti] else None}" for e, n in enumerate(ev)))
+for ti in range(1, 7):
+    for i in range(3):
+        k = ti * 4 + i
+        print(f"run={ti} chunk={i} acc_in_regs={int(t[14, k] - t0) if t[14, k] else None} transposed={int(t[15, k] - t0) if t[15, k] else None} stored={int(t[16, k] - t0) if t[16, k] else None}")
