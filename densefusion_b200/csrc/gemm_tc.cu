@@ -163,20 +163,36 @@ __host__ __device__ __forceinline__ uint32_t q_tap_mask(const TcParams& p, int x
     return ((my & 1u) ? mx : 0u) | ((my & 2u) ? mx << 3 : 0u) | ((my & 4u) ? mx << 6 : 0u);
 }
 
-template <int CTAS>
+// FORM: which launch form the instantiation serves -- -1 any (every feature tested at run time), 0 plain single-run GEMM, 1 implicit
+// convolution, 2 pooled GEMM, 3 the conv1 gather form.  The specialised forms read the features they do not have as constants, so their
+// code disappears from the role loops (see gemm_tc_q_kernel).
+template <int FORM> struct QForm {
+    static constexpr bool ANY = FORM < 0;
+    __device__ static __forceinline__ int conv_taps(const TcParams& p) { return (ANY || FORM == 1) ? p.conv_taps : 0; }
+    __device__ static __forceinline__ float* pool_partial(const TcParams& p) { return (ANY || FORM == 2) ? p.pool_partial : nullptr; }
+    __device__ static __forceinline__ int c1_H(const TcParams& p) { return (ANY || FORM == 3) ? p.c1_H : 0; }
+    __device__ static __forceinline__ int wk_rows(const TcParams& p) { return ANY ? p.wk_rows : 0; }
+    __device__ static __forceinline__ const float* residual(const TcParams& p) { return (ANY || FORM == 1) ? p.residual : nullptr; }
+    __device__ static __forceinline__ int bias_crop_stride(const TcParams& p) { return (ANY || FORM == 0 || FORM == 2) ? p.bias_crop_stride : 0; }
+    __device__ static __forceinline__ int k_chunks(const TcParams& p) { return (ANY || FORM == 1) ? p.k_chunks : 1; }
+    __device__ static __forceinline__ int m_fastest(const TcParams& p) { return ANY ? p.m_fastest : 0; }
+};
+
+template <int CTAS, int FORM>
 __device__ __forceinline__ QTile q_decode(const TcParams& p, int t, int m_tiles, int n_tiles, int bnt, int rank)
 {
+    using F = QForm<FORM>;
     QTile c;
     const int per_group = m_tiles * n_tiles;
     c.g = t / per_group;
     const int rem = t - c.g * per_group;
     int mt, nt;
-    if (p.m_fastest) { nt = rem / m_tiles; mt = rem - nt * m_tiles; }      // concurrent clusters share the weight tile
+    if (F::m_fastest(p)) { nt = rem / m_tiles; mt = rem - nt * m_tiles; }      // concurrent clusters share the weight tile
     else { mt = rem / n_tiles; nt = rem - mt * n_tiles; }                  // ... or the activation rows
     c.n0 = nt * bnt;
     c.crop = 0; c.pool_tile = 0;
     c.x0 = c.y0 = c.b0 = 0; c.taps = 1u;
-    if (p.conv_taps) {
+    if (F::conv_taps(p)) {
         const int pt = mt * CTAS + rank;
         int tx, ty, tb;
         q_patch(p, pt, tx, ty, tb);
@@ -189,7 +205,7 @@ __device__ __forceinline__ QTile q_decode(const TcParams& p, int t, int m_tiles,
             q_patch(p, mt * CTAS + r, tx, ty, tb);
             if (ty < p.tiles_y && tb < p.tiles_b) c.taps |= q_tap_mask(p, tx * p.TW, ty * p.TH);
         }
-    } else if (p.pool_partial) {
+    } else if (F::pool_partial(p)) {
         const int pairs_per_crop = (p.rows_per_crop + 128 * CTAS - 1) / (128 * CTAS);
         c.crop = mt / pairs_per_crop;
         c.pool_tile = (mt - c.crop * pairs_per_crop) * CTAS + rank;        // index of this CTA's 128-row tile in the crop
@@ -237,7 +253,7 @@ __device__ __forceinline__ void epi_store_simple(const float* srow, int sw0, int
 // DBG: the knock-out bits and the clock64 timeline (TcParams::dbg / trace) exist in a second instantiation only, launched when
 // DF_TC_DBG is set -- as run-time tests inside the role loops they cost registers and instructions on every path (measured: a few more
 // conditionals and 24 bytes of additional spills made the short-K GEMMs 10-18% slower, profiles/r2_s3_variants.jsonl).
-template <int CTAS, int A_STAGES, int A_COLS, bool DBG>
+template <int CTAS, int A_STAGES, int A_COLS, bool DBG, int FORM>
 __global__ void __launch_bounds__(Q_THREADS, 1)
 gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_whi,
                  const __grid_constant__ CUtensorMap tm_wlo, const TcParams p, const int bn_cta, const int m_tiles,
@@ -253,6 +269,12 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     constexpr bool A_SMEM = A_COLS == 0;
     constexpr bool S16 = A_COLS == 32 || A_SMEM;
     const int dbg = DBG ? p.dbg : 0;
+    // features of the launch form: constants in the specialised instantiations (QForm)
+    using F = QForm<FORM>;
+    const int conv_taps = F::conv_taps(p), c1_H = F::c1_H(p), wk_rows = F::wk_rows(p), bias_crop_stride = F::bias_crop_stride(p);
+    float* const pool_partial = F::pool_partial(p);
+    const float* const residual = F::residual(p);
+    const int k_chunks = F::k_chunks(p);
     constexpr int TMEM_A0 = 512 - A_STAGES * A_COLS;
     constexpr int ACC_STRIDE = TMEM_A0 / 2;
     extern __shared__ uint8_t smem_raw[];
@@ -278,7 +300,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // A | W_hi | W_lo (or the bf16 pair tile), all 1024-B aligned; hybrid16s: A | [fp16 hi x32 | fp16 lo x32] rows
     const uint32_t stage_bytes = S16 ? Q_TILE + w_bytes : Q_TILE + 2 * w_bytes;
     // (the pooled epilogue keeps its per-warp column sums in the last 8 KB of the stage area: one stage less when the ring fills it)
-    const uint32_t pool_bytes = p.pool_partial ? 8192u : (p.c1_H ? 2048u : 0u);      // (conv1 form: the patch offset table lives there)
+    const uint32_t pool_bytes = pool_partial ? 8192u : (c1_H ? 2048u : 0u);      // (conv1 form: the patch offset table lives there)
     const uint32_t aring_bytes = A_SMEM ? (uint32_t)A_STAGES * Q_TILE : 0u;
     // An EVEN number of stages: the two stager groups (and the two producer warps) take alternate k-blocks, so with an even ring a stage
     // always belongs to the same group and that group sees every fill of it; with an odd ring a group would see every OTHER fill -- all of
@@ -354,25 +376,25 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // "slot free" and "both TMA instructions issued" -- which paced every launch shape once the issuer's loop had been shortened;
         // two warps take the even / odd k-blocks of the same sequence (each waits for and fills its own slots).
         const uint32_t pw = warp == 0 ? 0u : 1u;
-        const uint32_t a_bytes = p.conv_taps ? (uint32_t)(p.TW * p.TH * p.TB) * BK * 4 : (uint32_t)Q_TILE;
+        const uint32_t a_bytes = conv_taps ? (uint32_t)(p.TW * p.TH * p.TB) * BK * 4 : (uint32_t)Q_TILE;
         // 3xTF32: W_hi + W_lo; hybrid: W_hi + bf16 pair tile; hybrid16: pair tile + a half-width (64 B rows) correction tile
-        const uint32_t bytes = (p.c1_H ? 0u : a_bytes) + (S16 ? w_bytes : p.precise == 3 ? w_bytes + w_bytes / 2 : (p.precise ? 2u : 1u) * w_bytes);
-        const int cblocks = p.conv_taps ? p.K / (BK * p.conv_taps) : 1;        // 32-channel blocks per tap
+        const uint32_t bytes = (c1_H ? 0u : a_bytes) + (S16 ? w_bytes : p.precise == 3 ? w_bytes + w_bytes / 2 : (p.precise ? 2u : 1u) * w_bytes);
+        const int cblocks = conv_taps ? p.K / (BK * conv_taps) : 1;        // 32-channel blocks per tap
         int s = 0;
         uint32_t ph = 1;                                                       // parity of "slot is free": passes at once in round 0
         uint32_t pit = 0, e_ready = 0;
         for (int t = t_first; t < total_tiles; t += t_step) {
-            const QTile c = q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, rank);
+            const QTile c = q_decode<CTAS, FORM>(p, t, m_tiles, n_tiles, bnt, rank);
             int wrow = c.g * p.N + c.n0 + rank * bn_cta;
             int wk0 = 0;                                                       // k offset of the W operand (weight-gradient form)
-            if (p.wk_rows) {                                                   // groups = slices of the reduction axis (split-K)
+            if (wk_rows) {                                                   // groups = slices of the reduction axis (split-K)
                 wrow = c.n0 + rank * bn_cta;
-                const int tap = wrow / p.wk_rows;
+                const int tap = wrow / wk_rows;
                 wk0 = p.wk_shift[tap] + c.g * p.K;
-                wrow += p.wk_row0[tap] - tap * p.wk_rows;
+                wrow += p.wk_row0[tap] - tap * wk_rows;
             }
             const int acol = (int)(c.g * p.a_gs);
-            const int nkb_t = p.conv_taps ? __popc(c.taps) * cblocks : nkb;
+            const int nkb_t = conv_taps ? __popc(c.taps) * cblocks : nkb;
             uint64_t tap_list = 0;                                              // the taps the pair visits, 4 bits each, in order
             for (int tap = 8; tap >= 0; --tap)
                 if ((c.taps >> tap) & 1u) tap_list = (tap_list << 4) | (uint64_t)tap;
@@ -391,18 +413,18 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (mine && elect_one()) {
                     // (DF_TC_DBG bit 128: the activation box is fetched for the first tap of a channel block only -- what a 3x3 convolution
                     // would pull through the port if the nine taps shared one haloed box; timing experiment, wrong results)
-                    const bool skip_a = (dbg & 128) && p.conv_taps == 9 && j >= cblocks;
+                    const bool skip_a = (dbg & 128) && conv_taps == 9 && j >= cblocks;
                     mbar_expect_tx(full + s, skip_a ? bytes - a_bytes : bytes);
                     uint8_t* dst = smem + (size_t)s * stage_bytes;
                     int kb = j;                                                 // k-block of the weight matrix
-                    if (p.conv_taps) {
+                    if (conv_taps) {
                         const int tap = (int)(tap_list & 15u);
                         const int ky = tap / 3, kx = tap - ky * 3;
-                        const int dy = p.conv_taps == 9 ? (ky - 1) * p.conv_dil : 0;
-                        const int dx = p.conv_taps == 9 ? (kx - 1) * p.conv_dil : 0;
+                        const int dy = conv_taps == 9 ? (ky - 1) * p.conv_dil : 0;
+                        const int dx = conv_taps == 9 ? (kx - 1) * p.conv_dil : 0;
                         kb = tap * cblocks + cb;
                         if (!skip_a) tma_load_4d(&tm_a, dst, full + s, cb * BK, c.x0 + dx, c.y0 + dy, c.b0);
-                    } else if (!p.c1_H) {
+                    } else if (!c1_H) {
                         tma_load_2d(&tm_a, dst, full + s, acol + kb * BK, c.row0);
                     }
                     // first weight tile: 32 fp32 per row (TF32 hi part), or, hybrid16 / hybrid16s, 64 halves per row ([fp16(W) x32 | bf16(W) x32]
@@ -426,9 +448,9 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             uint32_t it = 0, ti = 0;
             int s = 0;
             uint32_t ph = 0, a_ready = 0;
-            const int cblocks = p.conv_taps ? p.K / (BK * p.conv_taps) : 1;
+            const int cblocks = conv_taps ? p.K / (BK * conv_taps) : 1;
             for (int t = t_first; t < total_tiles; t += t_step) {
-              const int nkb_t = p.conv_taps == 9 ? __popc(q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, 0).taps) * cblocks : nkb;
+              const int nkb_t = conv_taps == 9 ? __popc(q_decode<CTAS, FORM>(p, t, m_tiles, n_tiles, bnt, 0).taps) * cblocks : nkb;
               const int runs = (nkb_t + p.kbc - 1) / p.kbc;
               for (int kc = 0; kc < runs; ++kc, ++ti) {
                 const int kb0 = kc * p.kbc, kb1 = min(nkb_t, kb0 + p.kbc);
@@ -553,11 +575,11 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // ------------------------------- A stagers (two groups) ----------------------
         const int my_tiles = (total_tiles - t_first + t_step - 1) / t_step;
         uint32_t total_it = (uint32_t)my_tiles * nkb;
-        if (p.conv_taps == 9) {                                          // tiles near the border visit fewer taps
+        if (conv_taps == 9) {                                          // tiles near the border visit fewer taps
             const int cblocks = p.K / (BK * 9);
             total_it = 0;
             for (int t = t_first + lane * t_step; t < total_tiles; t += 32 * t_step)
-                total_it += __popc(q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, 0).taps) * cblocks;
+                total_it += __popc(q_decode<CTAS, FORM>(p, t, m_tiles, n_tiles, bnt, 0).taps) * cblocks;
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) total_it += __shfl_xor_sync(0xffffffffu, total_it, off);
         }
@@ -574,12 +596,12 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         // in shared memory (a __constant__ table indexed by the warp-uniform k was measured slower: 0.175 vs 0.153 ms at 64 x 160^2)
         int* c1_off = reinterpret_cast<int*>(smem + Q_SMEM_STAGES - 2048);
         int* c1_dyx = c1_off + 160;
-        const bool conv1 = S16 && !A_SMEM && p.c1_H != 0;
+        const bool conv1 = S16 && !A_SMEM && c1_H != 0;
         if (conv1) {
             const int k = (int)threadIdx.x - 64;                         // the 256 stager threads
             if (k < 160) {
                 const int c = k / 49, rem = k - c * 49, ky = rem / 7, kx = rem - ky * 7;
-                c1_off[k] = k < 147 ? (c * p.c1_H + (ky - 3)) * p.c1_W + (kx - 3) : 0;
+                c1_off[k] = k < 147 ? (c * c1_H + (ky - 3)) * p.c1_W + (kx - 3) : 0;
                 c1_dyx[k] = k < 147 ? (((ky - 3) & 0xff) | (((kx - 3) & 0xff) << 8)) : 0x8080;      // 0x80: never inside the image
             }
             asm volatile("bar.sync 3, 256;" ::: "memory");
@@ -596,13 +618,13 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 const int b = row_in ? (int)(m / hw) : 0, rem = row_in ? (int)(m - (long long)b * hw) : 0;
                 const int yo = rem / p.c1_Wo, xo = rem - yo * p.c1_Wo;
                 const int y2 = yo * 2, x2 = xo * 2;
-                const float* org = p.A + ((size_t)b * 3 * p.c1_H + y2) * p.c1_W + x2;      // patch origin + (3, 3)
+                const float* org = p.A + ((size_t)b * 3 * c1_H + y2) * p.c1_W + x2;      // patch origin + (3, 3)
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const int k = c1_kb * 32 + i;
                     const int d = c1_dyx[k];
                     const int y = y2 + (int)(signed char)(d & 0xff), x = x2 + (int)(signed char)((d >> 8) & 0xff);
-                    const bool ok = row_in && (unsigned)y < (unsigned)p.c1_H && (unsigned)x < (unsigned)p.c1_W && d != 0x8080;
+                    const bool ok = row_in && (unsigned)y < (unsigned)c1_H && (unsigned)x < (unsigned)p.c1_W && d != 0x8080;
                     hi[i] = ok ? __float_as_uint(__ldg(org + c1_off[k])) : 0u;
                 }
                 c1_kb += 2;
@@ -713,9 +735,9 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int per_kb = p.precise == 1 ? 12 : (p.precise == 2 ? 8 : (p.precise >= 3 ? 6 : 4));
         uint32_t ti = 0;
         for (int t = t_first; t < total_tiles; t += t_step) {
-          const QTile c = q_decode<CTAS>(p, t, m_tiles, n_tiles, bnt, rank);
-          const int nkb_t = p.conv_taps == 9 ? __popc(c.taps) * (p.K / (BK * 9)) : nkb;
-          const int runs = p.conv_taps == 9 ? (nkb_t + p.kbc - 1) / p.kbc : p.k_chunks;
+          const QTile c = q_decode<CTAS, FORM>(p, t, m_tiles, n_tiles, bnt, rank);
+          const int nkb_t = conv_taps == 9 ? __popc(c.taps) * (p.K / (BK * 9)) : nkb;
+          const int runs = conv_taps == 9 ? (nkb_t + p.kbc - 1) / p.kbc : k_chunks;
           const int r = q * 32 + lane;
           const bool row_ok = r < c.rows_valid;
           const float* bias = p.bias ? p.bias + c.g * p.bias_gs : nullptr;
@@ -724,8 +746,8 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           int myrow = -1;                                      // the row this lane holds after the TMEM load (lane == row)
           int crop_first = 0, crop_boundary = 0x7fffffff;
           bool straddle = false;
-          if (!p.pool_partial) {
-              if (p.conv_taps) {
+          if (!pool_partial) {
+              if (conv_taps) {
                   if (runs > 1) {
                       const int rx = r % p.TW, rest = r / p.TW;
                       const int ry = rest % p.TH, rb = rest / p.TH;
@@ -749,7 +771,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                       if ((dbg & 512) && roff[ps] >= 0) roff[ps] &= 1023;      // (knock-out: the output folded onto 1024 rows -- it stays in L2)
                   }
                   if (row_ok) myrow = c.row0 + r;
-                  if (bias && p.bias_crop_stride) {
+                  if (bias && bias_crop_stride) {
                       // clamped to the last crop: the warp's 32 rows may lie entirely in the masked tail of the last M tile
                       // (M = 3000: rows 3040..3071), and its bias vector is loaded before the row masks are looked at -- one
                       // row past the end of the (crops x N) bias buffer.  That read was the "ConvS2Fn" illegal address of
@@ -757,11 +779,11 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                       crop_first = min((c.row0 + q * 32) / p.rows_per_crop, (p.M - 1) / p.rows_per_crop);
                       crop_boundary = (crop_first + 1) * p.rows_per_crop;
                       straddle = c.row0 + q * 32 + 31 >= crop_boundary && crop_boundary < p.M;
-                      bias += (size_t)crop_first * p.bias_crop_stride;
+                      bias += (size_t)crop_first * bias_crop_stride;
                   }
               }
-          } else if (bias && p.bias_crop_stride) {
-              bias += (size_t)c.crop * p.bias_crop_stride;          // pooled tiles are crop-aligned: one bias row per tile
+          } else if (bias && bias_crop_stride) {
+              bias += (size_t)c.crop * bias_crop_stride;          // pooled tiles are crop-aligned: one bias row per tile
           }
           float* const Cg = p.C + c.g * p.c_gs;
           for (int kc = 0; kc < runs; ++kc, ++ti) {
@@ -774,7 +796,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 run_scale *= 1.0f + p.bias_comp * (float)(n_kb * per_kb);
             }
             // the simple store: one run, no skip connection, one bias vector for all 32 rows of the warp
-            const bool simple = first_run && last_run && !p.residual && !straddle;
+            const bool simple = first_run && last_run && !residual && !straddle;
             if (ew == 0) DF_TRACE(9, ti);
             mbar_wait(acc_full + ab, (ti >> acc_shift) & 1);
             if (ew == 0) DF_TRACE(10, ti);
@@ -793,7 +815,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
                 if (bias && last_run && cq < p.N) {
                     b0 = __ldg(reinterpret_cast<const float4*>(bias + cq));
-                    if (straddle) b1 = __ldg(reinterpret_cast<const float4*>(bias + p.bias_crop_stride + cq));
+                    if (straddle) b1 = __ldg(reinterpret_cast<const float4*>(bias + bias_crop_stride + cq));
                 }
                 if (dbg & 4) {
 #pragma unroll
@@ -805,7 +827,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * run_scale);
                 }
-                if (!last_run && !p.pool_partial) {
+                if (!last_run && !pool_partial) {
                     // Partial sum of an intermediate run, straight from the registers (lane == row, 32 consecutive columns = one
                     // 128-byte line per lane): the first run is stored, the following ones are ADDED in L2 (red.global: no read round
                     // trip, no transpose) -- one thread per element in run order, so the sum is deterministic and, fp32 addition being
@@ -824,7 +846,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     }
                     continue;
                 }
-                if (p.pool_partial) {
+                if (pool_partial) {
                     // column sums of act(x + bias) over this warp's 32 rows: through the same swizzled transpose as the store path
                     // (lane (rr, cc) then owns 4 columns of rows ps*4 + rr: 8 adds per column and two shuffle stages across rr, instead
                     // of a 31-shuffle butterfly over registers + 32 scalar bias loads per lane -- the pooled drain was 11.8 k clocks
@@ -876,7 +898,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                             // left in program order every C read waited for the store before it (the compiler cannot prove
                             // the rows distinct), one L2 round trip per row -- 8 x 4 per 256-wide run, which the single accumulator of
                             // the wide tiles exposes in full (measured: the MMA issuer waited 43% of layer4.0 on acc_empty).
-                            const char* rbase = (p.residual && last_run) ? reinterpret_cast<const char*>(p.residual + cq) : nullptr;
+                            const char* rbase = (residual && last_run) ? reinterpret_cast<const char*>(residual + cq) : nullptr;
 #pragma unroll
                             for (int pb = 0; pb < 8; pb += 4) {
                                 float4 prev[4], resv[4];
@@ -920,12 +942,12 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if (lane == 0) {
                 if (CTAS == 2) mbar_arrive_remote(acc_empty + ab, 0); else mbar_arrive(acc_empty + ab);
             }
-            if (p.pool_partial) {
+            if (pool_partial) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 epilogue warps
                 const int tt = threadIdx.x - 320;
                 if (tt < bnt && c.n0 + tt < p.N && c.rows_valid > 0) {
                     const float sum = ((pool[tt] + pool[256 + tt]) + pool[512 + tt]) + pool[768 + tt];
-                    p.pool_partial[((size_t)c.crop * p.tiles_per_crop + c.pool_tile) * p.N + c.n0 + tt] = sum;
+                    pool_partial[((size_t)c.crop * p.tiles_per_crop + c.pool_tile) * p.N + c.n0 + tt] = sum;
                 }
             }
           }
@@ -1052,6 +1074,38 @@ int pair_m_tiles(const TcParams& p)
 
 unsigned long long* g_trace = nullptr;
 
+typedef void (*QKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const int, const int, const int, const int);
+
+// Instantiation that serves a launch: the specialised forms (QForm) exist for the hybrid16s variants, i.e. the inference path; everything
+// else -- the older arithmetic modes, the weight-gradient form, multi-run GEMMs, PReLU on a GEMM, DF_TC_DBG -- runs the generic one.
+template <int CTAS, int A_STAGES, int A_COLS>
+QKernel pick_q_kernel(const TcParams& p, int* form_out)
+{
+    int form = -1;
+    if (A_COLS != 64 && !p.dbg && !p.wk_rows && !p.m_fastest) {
+        if (p.c1_H) form = A_COLS == 32 ? 3 : -1;
+        else if (p.pool_partial) form = (A_COLS == 0 && A_STAGES == 3) ? 2 : -1;
+        else if (p.conv_taps) form = (A_STAGES == 4) ? 1 : -1;
+        else if (p.k_chunks == 1 && !p.residual && p.relu != 2 && A_STAGES == 4) form = 0;
+    }
+    *form_out = form;
+    if (p.dbg) return gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS, true, -1>;
+    if constexpr (A_COLS == 32) {
+        if (form == 0) return gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS, false, 0>;
+        if (form == 1) return gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS, false, 1>;
+        if (form == 3) return gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS, false, 3>;
+    }
+    if constexpr (A_COLS == 0 && A_STAGES == 4) {
+        if (form == 0) return gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS, false, 0>;
+        if (form == 1) return gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS, false, 1>;
+    }
+    if constexpr (A_COLS == 0 && A_STAGES == 3) {
+        if (form == 2) return gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS, false, 2>;
+    }
+    *form_out = -1;
+    return gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS, false, -1>;
+}
+
 template <int CTAS, int A_STAGES, int A_COLS = 64>
 int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw, int groups, cudaStream_t s)
 {
@@ -1107,9 +1161,7 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
         cudaGetDevice(&dev);
         cudaError_t e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_TOTAL);
-        if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_TOTAL);
+        e = cudaFuncSetAttribute(gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS, false, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_TOTAL);
         if (e != cudaSuccess) return (int)e;
         int n = num_sms / CTAS;
         if (CTAS == 2) {
@@ -1120,7 +1172,7 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
             at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             q.attrs = at; q.numAttrs = 1;
             int occ = 0;
-            if (cudaOccupancyMaxActiveClusters(&occ, gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS, false>, &q) == cudaSuccess && occ > 0 && occ < n) n = occ;
+            if (cudaOccupancyMaxActiveClusters(&occ, gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS, false, -1>, &q) == cudaSuccess && occ > 0 && occ < n) n = occ;
             (void)cudaGetLastError();
         }
         max_clusters = n;
@@ -1186,8 +1238,18 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = use_pdl() ? 2 : 1;
-    cudaError_t e = p.dbg ? cudaLaunchKernelEx(&cfg, gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS, true>, ma, mhi, mlo, p, bn_cta, m_tiles, n_tiles, total)
-                          : cudaLaunchKernelEx(&cfg, gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS, false>, ma, mhi, mlo, p, bn_cta, m_tiles, n_tiles, total);
+    int form = -1;
+    const QKernel kern = pick_q_kernel<CTAS, A_STAGES, A_COLS>(p, &form);
+    {   // dynamic shared memory opt-in, once per instantiation (index: form + 1, debug build last)
+        static bool smem_set[6] = {false, false, false, false, false, false};
+        const int slot = p.dbg ? 5 : form + 1;
+        if (!smem_set[slot]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_TOTAL);
+            if (e != cudaSuccess) return (int)e;
+            smem_set[slot] = true;
+        }
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mhi, mlo, p, bn_cta, m_tiles, n_tiles, total);
     return e == cudaSuccess ? 0 : (int)e;
 }
 
