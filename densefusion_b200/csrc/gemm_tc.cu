@@ -18,6 +18,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 #include <stdio.h>
+#include <vector>
 
 namespace {
 
@@ -131,6 +132,23 @@ constexpr int TRACE_EV = 17;                                  // 0-8 per k-block
                                                              // accumulator, issuer waits for / has a free accumulator; 14-16 per chunk of warp 10: accumulator in registers / transposed / stored
 #define DF_TRACE(ev, it_) do { if (DBG && p.trace && cid == 0 && rank == 0 && (it_) < (uint32_t)TRACE_KB && lane == 0) p.trace[(ev) * TRACE_KB + (it_)] = clock64(); } while (0)
 
+// Balanced schedule of the long-K convolutions (FORM 4).  The default tile walk is round robin over whole tiles: 180 tiles of a 15 x 15
+// layer4 convolution on 74 CTA pairs are 2.43 tiles per pair, i.e. three rounds with the last one a third full (every pair waits for
+// the 32 that got a third tile; 19% of the launch, 10% at 200 tiles).  Here every cluster gets a CONTIGUOUS range of (tile,
+// accumulation run) units of equal k-block weight, cut at run boundaries -- the runs of a tile already meet in C (first run stored,
+// the others added) -- so a tile may be shared by two neighbouring clusters: cluster c + 1 STARTS with the last runs of the tile
+// (stores / adds them like intermediate runs, then raises a flag per epilogue warp), cluster c ENDS with its first runs (waits for the
+// flag before it touches C, adds its runs, and its last one takes the full path: read back, bias, skip connection, activation).
+// The order of the additions into an element is fixed by the schedule, so the result is deterministic (it differs from the
+// round-robin schedule's in the last bit: (r2 + r3) + r0 + r1 instead of r0 + r1 + r2 + r3).  The waiting cluster never blocks
+// progress: the runs it waits for are the FIRST thing its neighbour does, before any wait of its own.
+constexpr int Q_SCHED_MAX = 80;
+struct QSched {
+    short t0[Q_SCHED_MAX], r0[Q_SCHED_MAX];      // first tile of cluster c and the run it starts with (> 0: the tile's first runs belong to c - 1)
+    short t1[Q_SCHED_MAX], r1[Q_SCHED_MAX];      // last tile and the run it stops before (0x7fff: the whole tile)
+    unsigned int* flags;                         // [clusters][2 CTAs][8 epilogue warps], zero between launches
+};
+
 struct QTile {
     int g, n0, row0, rows_valid, crop, pool_tile;
     int x0, y0, b0;                              // convolution form: origin of this CTA's pixel patch
@@ -164,17 +182,18 @@ __host__ __device__ __forceinline__ uint32_t q_tap_mask(const TcParams& p, int x
 }
 
 // FORM: which launch form the instantiation serves -- -1 any (every feature tested at run time), 0 plain single-run GEMM, 1 implicit
-// convolution, 2 pooled GEMM, 3 the conv1 gather form.  The specialised forms read the features they do not have as constants, so their
-// code disappears from the role loops (see gemm_tc_q_kernel).
+// convolution, 2 pooled GEMM, 3 the conv1 gather form, 4 implicit convolution on the balanced schedule (QSched).  The specialised forms
+// read the features they do not have as constants, so their code disappears from the role loops (see gemm_tc_q_kernel).
 template <int FORM> struct QForm {
     static constexpr bool ANY = FORM < 0;
-    __device__ static __forceinline__ int conv_taps(const TcParams& p) { return (ANY || FORM == 1) ? p.conv_taps : 0; }
+    static constexpr bool CONV = FORM == 1 || FORM == 4;
+    __device__ static __forceinline__ int conv_taps(const TcParams& p) { return (ANY || CONV) ? p.conv_taps : 0; }
     __device__ static __forceinline__ float* pool_partial(const TcParams& p) { return (ANY || FORM == 2) ? p.pool_partial : nullptr; }
     __device__ static __forceinline__ int c1_H(const TcParams& p) { return (ANY || FORM == 3) ? p.c1_H : 0; }
     __device__ static __forceinline__ int wk_rows(const TcParams& p) { return ANY ? p.wk_rows : 0; }
-    __device__ static __forceinline__ const float* residual(const TcParams& p) { return (ANY || FORM == 1) ? p.residual : nullptr; }
+    __device__ static __forceinline__ const float* residual(const TcParams& p) { return (ANY || CONV) ? p.residual : nullptr; }
     __device__ static __forceinline__ int bias_crop_stride(const TcParams& p) { return (ANY || FORM == 0 || FORM == 2) ? p.bias_crop_stride : 0; }
-    __device__ static __forceinline__ int k_chunks(const TcParams& p) { return (ANY || FORM == 1) ? p.k_chunks : 1; }
+    __device__ static __forceinline__ int k_chunks(const TcParams& p) { return (ANY || CONV) ? p.k_chunks : 1; }
     __device__ static __forceinline__ int m_fastest(const TcParams& p) { return ANY ? p.m_fastest : 0; }
 };
 
@@ -257,7 +276,7 @@ template <int CTAS, int A_STAGES, int A_COLS, bool DBG, int FORM>
 __global__ void __launch_bounds__(Q_THREADS, 1)
 gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_whi,
                  const __grid_constant__ CUtensorMap tm_wlo, const TcParams p, const int bn_cta, const int m_tiles,
-                 const int n_tiles, const int total_tiles)
+                 const int n_tiles, const int total_tiles, const __grid_constant__ QSched sched)
 {
     // A_STAGES TMEM A stages of A_COLS columns each at the top of TMEM (64: [hi | lo] / [fp16 | - | bf16 | bf16 lo]; 32: the two
     // fp16 planes of hybrid16s, the only arithmetic that instantiation carries); the accumulators share what is left below.
@@ -309,7 +328,12 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (q_stages > 2) q_stages &= ~1;
     const int Q_STAGES = q_stages;
     uint8_t* const aring = smem + (size_t)Q_STAGES * stage_bytes;           // A_SMEM: the operand-plane ring of A (1024-byte aligned)
-    const int t_first = cid, t_step = ncl;                                  // tile walk of this cluster: round robin over all tiles
+    // tile walk of this cluster: round robin over all tiles, or (FORM 4) the contiguous range of the balanced schedule, which starts
+    // at run sp_r0 of tile t_first and stops before run sp_r1 of tile t_end - 1
+    constexpr bool SPLIT = FORM == 4;
+    const int t_first = SPLIT ? (int)sched.t0[cid] : cid, t_step = SPLIT ? 1 : ncl;
+    const int t_end = SPLIT ? (int)sched.t1[cid] + 1 : total_tiles;
+    const int sp_r0 = SPLIT ? (int)sched.r0[cid] : 0, sp_r1 = SPLIT ? (int)sched.r1[cid] : 0x7fff;
     const uint32_t ACC_BUFS = bnt <= ACC_STRIDE ? 2 : 1;
     const uint32_t acc_shift = ACC_BUFS - 1;        // ti % ACC_BUFS == ti & acc_shift, ti / ACC_BUFS == ti >> acc_shift
 
@@ -383,7 +407,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         int s = 0;
         uint32_t ph = 1;                                                       // parity of "slot is free": passes at once in round 0
         uint32_t pit = 0, e_ready = 0;
-        for (int t = t_first; t < total_tiles; t += t_step) {
+        for (int t = t_first; t < t_end; t += t_step) {
             const QTile c = q_decode<CTAS, FORM>(p, t, m_tiles, n_tiles, bnt, rank);
             int wrow = c.g * p.N + c.n0 + rank * bn_cta;
             int wk0 = 0;                                                       // k offset of the W operand (weight-gradient form)
@@ -399,7 +423,13 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             for (int tap = 8; tap >= 0; --tap)
                 if ((c.taps >> tap) & 1u) tap_list = (tap_list << 4) | (uint64_t)tap;
             int cb = 0;
-            for (int j = 0; j < nkb_t; ++j, ++pit) {
+            int j0 = 0, j1 = nkb_t;
+            if (SPLIT) {                                                        // this cluster's runs of a shared tile
+                if (t == t_first) j0 = sp_r0 * p.kbc;
+                if (t == t_end - 1) j1 = min(nkb_t, sp_r1 * p.kbc);
+                if (j0) { const int ord = j0 / cblocks; cb = j0 - ord * cblocks; tap_list >>= 4 * ord; }
+            }
+            for (int j = j0; j < j1; ++j, ++pit) {
                 const bool mine = (pit & 1u) == pw;
                 if (mine) {
                 if (!e_ready) mbar_wait(empty + s, ph);
@@ -449,10 +479,11 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             int s = 0;
             uint32_t ph = 0, a_ready = 0;
             const int cblocks = conv_taps ? p.K / (BK * conv_taps) : 1;
-            for (int t = t_first; t < total_tiles; t += t_step) {
+            for (int t = t_first; t < t_end; t += t_step) {
               const int nkb_t = conv_taps == 9 ? __popc(q_decode<CTAS, FORM>(p, t, m_tiles, n_tiles, bnt, 0).taps) * cblocks : nkb;
               const int runs = (nkb_t + p.kbc - 1) / p.kbc;
-              for (int kc = 0; kc < runs; ++kc, ++ti) {
+              const int ra = (SPLIT && t == t_first) ? sp_r0 : 0, rb = (SPLIT && t == t_end - 1) ? min(runs, sp_r1) : runs;
+              for (int kc = ra; kc < rb; ++kc, ++ti) {
                 const int kb0 = kc * p.kbc, kb1 = min(nkb_t, kb0 + p.kbc);
                 const uint32_t ab = ti & acc_shift;
                 const uint32_t aph = ((ti >> acc_shift) & 1) ^ 1;
@@ -573,13 +604,20 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
     } else if (warp < 10) {
         // ------------------------------- A stagers (two groups) ----------------------
-        const int my_tiles = (total_tiles - t_first + t_step - 1) / t_step;
+        const int my_tiles = (t_end - t_first + t_step - 1) / t_step;
         uint32_t total_it = (uint32_t)my_tiles * nkb;
-        if (conv_taps == 9) {                                          // tiles near the border visit fewer taps
-            const int cblocks = p.K / (BK * 9);
+        if (conv_taps == 9 || SPLIT) {                                 // tiles near the border visit fewer taps
+            const int cblocks = conv_taps == 9 ? p.K / (BK * 9) : nkb;
             total_it = 0;
-            for (int t = t_first + lane * t_step; t < total_tiles; t += 32 * t_step)
-                total_it += __popc(q_decode<CTAS, FORM>(p, t, m_tiles, n_tiles, bnt, 0).taps) * cblocks;
+            for (int t = t_first + lane * t_step; t < t_end; t += 32 * t_step) {
+                const int nkb_t = conv_taps == 9 ? __popc(q_decode<CTAS, FORM>(p, t, m_tiles, n_tiles, bnt, 0).taps) * cblocks : nkb;
+                int j0 = 0, j1 = nkb_t;
+                if (SPLIT) {
+                    if (t == t_first) j0 = sp_r0 * p.kbc;
+                    if (t == t_end - 1) j1 = min(nkb_t, sp_r1 * p.kbc);
+                }
+                total_it += j1 - j0;
+            }
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) total_it += __shfl_xor_sync(0xffffffffu, total_it, off);
         }
@@ -734,10 +772,19 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const float w_inv = S16 ? __ldg(p.w_inv_scale) / a_sc : 1.0f;          // (powers of two: exact)
         const int per_kb = p.precise == 1 ? 12 : (p.precise == 2 ? 8 : (p.precise >= 3 ? 6 : 4));
         uint32_t ti = 0;
-        for (int t = t_first; t < total_tiles; t += t_step) {
+        for (int t = t_first; t < t_end; t += t_step) {
           const QTile c = q_decode<CTAS, FORM>(p, t, m_tiles, n_tiles, bnt, rank);
           const int nkb_t = conv_taps == 9 ? __popc(c.taps) * (p.K / (BK * 9)) : nkb;
           const int runs = conv_taps == 9 ? (nkb_t + p.kbc - 1) / p.kbc : k_chunks;
+          // balanced schedule: a tile shared with the neighbouring cluster -- `tail_part`: this cluster has its LAST runs (and does them
+          // first: all of them intermediate, the first one stores), `head_part`: its FIRST runs (after the neighbour's: all of them add, the
+          // last one finishes the tile)
+          int ra = 0, rb = runs;
+          bool tail_part = false, head_part = false;
+          if (SPLIT) {
+              if (t == t_first && sp_r0 > 0) { ra = sp_r0; tail_part = true; }
+              if (t == t_end - 1 && sp_r1 < runs) { rb = sp_r1; head_part = true; }
+          }
           const int r = q * 32 + lane;
           const bool row_ok = r < c.rows_valid;
           const float* bias = p.bias ? p.bias + c.g * p.bias_gs : nullptr;
@@ -786,8 +833,9 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               bias += (size_t)c.crop * bias_crop_stride;          // pooled tiles are crop-aligned: one bias row per tile
           }
           float* const Cg = p.C + c.g * p.c_gs;
-          for (int kc = 0; kc < runs; ++kc, ++ti) {
-            const bool first_run = kc == 0, last_run = kc == runs - 1;
+          for (int kc = ra; kc < rb; ++kc, ++ti) {
+            const bool first_run = SPLIT ? (tail_part ? kc == ra : (!head_part && kc == 0)) : kc == 0;
+            const bool last_run = SPLIT ? (!tail_part && kc == rb - 1) : kc == runs - 1;
             const uint32_t ab = ti & acc_shift;
             float* pool = reinterpret_cast<float*>(smem + Q_SMEM_STAGES - 8192) + (ti & 1) * 4 * 256;      // [2][4 lane quarters][256 columns]
             float run_scale = w_inv;
@@ -801,6 +849,17 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             mbar_wait(acc_full + ab, (ti >> acc_shift) & 1);
             if (ew == 0) DF_TRACE(10, ti);
             tc_fence_after();
+            if (SPLIT && head_part && kc == 0) {
+                // the neighbour's runs of this tile (same warp index there: same rows and columns) must be in C before this warp's first add
+                unsigned int* flag = sched.flags + ((size_t)cid * 2 + rank) * 8 + ew;
+                if (lane == 0) {
+                    unsigned int v;
+                    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory"); } while (v == 0u);
+                    *flag = 0u;                                // (only this warp reads it; the next launch finds it clear)
+                }
+                __syncwarp();
+                __threadfence();
+            }
             if (last_run && !first_run) {                      // the partial sums were written / added by OTHER lanes of this warp
                 __threadfence();
                 __syncwarp();
@@ -942,6 +1001,14 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if (lane == 0) {
                 if (CTAS == 2) mbar_arrive_remote(acc_empty + ab, 0); else mbar_arrive(acc_empty + ab);
             }
+            if (SPLIT && tail_part && kc == rb - 1) {          // this cluster's runs of the shared tile are in C: release the neighbour
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) {
+                    unsigned int* flag = sched.flags + ((size_t)(cid - 1) * 2 + rank) * 8 + ew;
+                    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flag), "r"(1u) : "memory");
+                }
+            }
             if (pool_partial) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 epilogue warps
                 const int tt = threadIdx.x - 320;
@@ -1044,6 +1111,8 @@ bool make_map_nhwc(CUtensorMap* map, const float* base, int B, int H, int W, int
 // `acc_stride` keep two accumulators in TMEM (stores overlap the next tile); a wider one (256 with A in TMEM) only when nothing is
 // stored (pooled epilogue) or the k loop is long.  Among the admissible widths take the one with the least work after wave
 // quantisation (+32: fixed cost per tile).  Returns 0 when no width fits.
+long long split_busiest_kblocks(const TcParams& p, int groups, int total, int max_clusters);
+
 int pair_tile_width(const TcParams& p, int groups, int m_tiles, int acc_stride, int max_clusters)
 {
     const int widths[4] = {256, 192, 128, 64};
@@ -1060,7 +1129,12 @@ int pair_tile_width(const TcParams& p, int groups, int m_tiles, int acc_stride, 
         if (w == 64 && p.N > 64) continue;                     // narrow layers only (64-channel decoder stages)
         if (p.N % w != 0 && (groups > 1 || w == 256)) continue;
         const long long tiles = (long long)m_tiles * ((p.N + w - 1) / w) * groups;
-        const long long cost = ((tiles + max_clusters - 1) / max_clusters) * (w + 32);
+        long long cost = ((tiles + max_clusters - 1) / max_clusters) * (w + 32);
+        if (w == 256 && acc_stride >= 256) {
+            // long-K convolutions on the balanced schedule (QSched) are not quantised to whole rounds: the busiest cluster's k-blocks
+            const long long kb = split_busiest_kblocks(p, groups, (int)tiles, max_clusters);
+            if (kb > 0) cost = (kb * (w + 32) + p.K / BK - 1) / (p.K / BK);
+        }
         if (best < 0 || cost < best) { best = cost; width = w; }
     }
     return width;
@@ -1074,13 +1148,128 @@ int pair_m_tiles(const TcParams& p)
 
 unsigned long long* g_trace = nullptr;
 
-typedef void (*QKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const int, const int, const int, const int);
+typedef void (*QKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const int, const int, const int, const int,
+                        const QSched);
 
 // Instantiation that serves a launch: the specialised forms (QForm) exist for the hybrid16s variants, i.e. the inference path; everything
 // else -- the older arithmetic modes, the weight-gradient form, multi-run GEMMs, PReLU on a GEMM, DF_TC_DBG -- runs the generic one.
-template <int CTAS, int A_STAGES, int A_COLS>
-QKernel pick_q_kernel(const TcParams& p, int* form_out)
+// Accumulation runs of a launch (TcParams::k_chunks / kbc): run length in MMA instructions, p.run_steps or DF_TC_RUN_STEPS (216)
+void plan_runs(TcParams& p)
 {
+    static const int env_steps = getenv("DF_TC_RUN_STEPS") ? atoi(getenv("DF_TC_RUN_STEPS")) : 216;
+    const int run_steps = p.run_steps > 0 ? p.run_steps : env_steps;
+    const int per_kb = p.precise == 1 ? 12 : (p.precise == 2 ? 8 : 6);
+    const int run_kb = run_steps / per_kb > 0 ? run_steps / per_kb : 1;
+    const int nkb = p.K / BK;
+    p.k_chunks = 1; p.kbc = nkb;
+    if (p.precise && !p.pool_partial && nkb > run_kb + run_kb / 3) {
+        p.k_chunks = (nkb + run_kb - 1) / run_kb;
+        p.kbc = (nkb + p.k_chunks - 1) / p.k_chunks;
+        p.k_chunks = (nkb + p.kbc - 1) / p.kbc;
+    }
+}
+
+// Balanced schedule (QSched) of a long-K convolution launch: contiguous ranges of equal k-block weight, cut at accumulation-run
+// boundaries.  Returns false -- the launch keeps the round-robin walk -- when the form does not apply, a tile would be shared by more
+// than two clusters, or the busiest cluster would not get at least 10% less to do than under round robin (measured, profiles/r2_s4_split_ab.jsonl: a predicted 8% at 200 tiles of 144 k-blocks came out 0.5-2% SLOWER, a predicted 12.5% at 126 tiles 8% faster).
+__device__ unsigned int g_split_flags[256 * Q_SCHED_MAX * 16];     // 256 regions, one per launch in flight (taken round robin)
+
+bool plan_split_ranges(const TcParams& p, int groups, int n_tiles, int total, int clusters, QSched* out, long long* rr_out, long long* sp_out)
+{
+    if (!p.conv_taps || p.k_chunks < 2 || p.wk_rows || p.m_fastest || p.dbg || groups != 1) return false;
+    if (clusters < 2 || clusters > Q_SCHED_MAX || total < clusters || total >= 0x7fff) return false;
+    const int cblocks = p.K / (BK * p.conv_taps);
+    std::vector<int> nkb((size_t)total);
+    long long sum = 0;
+    for (int t = 0; t < total; ++t) {
+        const int mt = t / n_tiles;
+        uint32_t mask = 0;
+        for (int r = 0; r < 2; ++r) {
+            int tx, ty, tb;
+            q_patch(p, mt * 2 + r, tx, ty, tb);
+            if (ty < p.tiles_y && tb < p.tiles_b) mask |= q_tap_mask(p, tx * p.TW, ty * p.TH);
+        }
+        nkb[t] = __builtin_popcount(mask) * cblocks;
+        if (nkb[t] <= 0) return false;
+        sum += nkb[t];
+    }
+    // round robin: the busiest cluster
+    long long rr_max = 0;
+    for (int c = 0; c < clusters; ++c) {
+        long long load = 0;
+        for (int t = c; t < total; t += clusters) load += nkb[t];
+        rr_max = load > rr_max ? load : rr_max;
+    }
+    // boundaries b_c = sum * c / clusters, moved to the nearest run boundary of the tile they fall into
+    std::vector<int> bt((size_t)clusters + 1), br((size_t)clusters + 1);
+    bt[0] = 0; br[0] = 0; bt[clusters] = total; br[clusters] = 0;
+    {
+        int t = 0;
+        long long cum = 0;                                             // k-blocks before tile t
+        for (int c = 1; c < clusters; ++c) {
+            const long long target = sum * c / clusters;
+            while (t < total && cum + nkb[t] <= target) cum += nkb[t++];
+            if (t >= total) return false;
+            const int runs = (nkb[t] + p.kbc - 1) / p.kbc;
+            int r = (int)((target - cum + p.kbc / 2) / p.kbc);
+            if (r >= runs) { bt[c] = t + 1; br[c] = 0; } else { bt[c] = t; br[c] = r; }
+        }
+    }
+    long long sp_max = 0;
+    for (int c = 0; c < clusters; ++c) {
+        const int t0 = bt[c], r0 = br[c];
+        int t1 = bt[c + 1], r1 = br[c + 1];
+        if (r1 == 0) { t1 -= 1; r1 = 0x7fff; }
+        if (t1 < t0 || (t1 == t0 && r0 > 0 && r1 != 0x7fff)) return false;      // empty range / a tile cut twice
+        out->t0[c] = (short)t0; out->r0[c] = (short)r0; out->t1[c] = (short)t1; out->r1[c] = (short)r1;
+        long long load = 0;
+        for (int t = t0; t <= t1; ++t) {
+            const int j0 = t == t0 ? r0 * p.kbc : 0;
+            const int j1 = (t == t1 && r1 != 0x7fff) ? (r1 * p.kbc < nkb[t] ? r1 * p.kbc : nkb[t]) : nkb[t];
+            if (j1 <= j0) return false;
+            load += j1 - j0;
+        }
+        sp_max = load > sp_max ? load : sp_max;
+    }
+    if (rr_out) *rr_out = rr_max;
+    if (sp_out) *sp_out = sp_max;
+    return sp_max * 100 <= rr_max * 90;
+}
+
+static int split_enabled()
+{
+    static const int enabled = getenv("DF_TC_SPLIT") ? atoi(getenv("DF_TC_SPLIT")) : 1;
+    return enabled;
+}
+
+// k-blocks of the busiest cluster when a launch on 256-wide tiles takes the balanced schedule, 0 when it would not (pair_tile_width)
+long long split_busiest_kblocks(const TcParams& p_in, int groups, int total, int max_clusters)
+{
+    if (!split_enabled() || !p_in.conv_taps || p_in.precise != 4 || p_in.N % 256) return 0;
+    TcParams p = p_in;
+    if (!p.k_chunks) plan_runs(p);
+    QSched tmp;
+    long long rr = 0, sp = 0;
+    const int clusters = total < max_clusters ? total : max_clusters;
+    return plan_split_ranges(p, groups, p.N / 256, total, clusters, &tmp, &rr, &sp) ? sp : 0;
+}
+
+bool plan_split(const TcParams& p, int groups, int n_tiles, int total, int clusters, QSched* out)
+{
+    if (!split_enabled() || !plan_split_ranges(p, groups, n_tiles, total, clusters, out, nullptr, nullptr)) return false;
+    static unsigned int* flags = nullptr;
+    if (!flags && cudaGetSymbolAddress(reinterpret_cast<void**>(&flags), g_split_flags) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    static unsigned int region = 0;
+    out->flags = flags + (size_t)(region++ & 255u) * (Q_SCHED_MAX * 16);
+    return true;
+}
+
+template <int CTAS, int A_STAGES, int A_COLS>
+QKernel pick_q_kernel(const TcParams& p, int* form_out, bool split)
+{
+    if constexpr (A_COLS == 0 && A_STAGES == 4 && CTAS == 2) {
+        if (split) { *form_out = 4; return gemm_tc_q_kernel<CTAS, A_STAGES, A_COLS, false, 4>; }
+    }
     int form = -1;
     if (A_COLS != 64 && !p.dbg && !p.wk_rows && !p.m_fastest) {
         if (p.c1_H) form = A_COLS == 32 ? 3 : -1;
@@ -1143,17 +1332,7 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
             cudaMemsetAsync(g_trace, 0, TRACE_EV * TRACE_KB * sizeof(unsigned long long), s);
             p.trace = g_trace;
         }
-        static const int env_steps = getenv("DF_TC_RUN_STEPS") ? atoi(getenv("DF_TC_RUN_STEPS")) : 216;
-        const int run_steps = p.run_steps > 0 ? p.run_steps : env_steps;
-        const int per_kb = p.precise == 1 ? 12 : (p.precise == 2 ? 8 : 6);
-        const int run_kb = run_steps / per_kb > 0 ? run_steps / per_kb : 1;
-        const int nkb = p.K / BK;
-        p.k_chunks = 1; p.kbc = nkb;
-        if (p.precise && !p.pool_partial && nkb > run_kb + run_kb / 3) {
-            p.k_chunks = (nkb + run_kb - 1) / run_kb;
-            p.kbc = (nkb + p.k_chunks - 1) / p.k_chunks;
-            p.k_chunks = (nkb + p.kbc - 1) / p.kbc;
-        }
+        plan_runs(p);
     }
     static int max_clusters = 0;
     if (!max_clusters) {
@@ -1239,17 +1418,19 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = use_pdl() ? 2 : 1;
     int form = -1;
-    const QKernel kern = pick_q_kernel<CTAS, A_STAGES, A_COLS>(p, &form);
+    QSched sched = {};
+    const bool split = (CTAS == 2 && A_COLS == 0 && A_STAGES == 4) ? plan_split(p, groups, n_tiles, total, clusters, &sched) : false;
+    const QKernel kern = pick_q_kernel<CTAS, A_STAGES, A_COLS>(p, &form, split);
     {   // dynamic shared memory opt-in, once per instantiation (index: form + 1, debug build last)
-        static bool smem_set[6] = {false, false, false, false, false, false};
-        const int slot = p.dbg ? 5 : form + 1;
+        static bool smem_set[7] = {false, false, false, false, false, false, false};
+        const int slot = p.dbg ? 6 : form + 1;
         if (!smem_set[slot]) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_TOTAL);
             if (e != cudaSuccess) return (int)e;
             smem_set[slot] = true;
         }
     }
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mhi, mlo, p, bn_cta, m_tiles, n_tiles, total);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mhi, mlo, p, bn_cta, m_tiles, n_tiles, total, sched);
     return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -1755,6 +1936,30 @@ extern "C" long long df_conv_tc_macs(int B, int H, int W, int Cin, int Cout, int
         macs += rows * __builtin_popcount(mask) * Cin * Cout;
     }
     return macs;
+}
+
+// The balanced schedule df_conv_tc would use for a hybrid16s 3x3 convolution of this geometry on `clusters` CTA pairs with 256-wide
+// tiles (host-side arithmetic only; tests and profiling scripts).  out[0] = k-blocks of the busiest cluster under round robin, out[1] =
+// under the balanced schedule, out[2] = tiles, out[3] = k-blocks per run, out[4] = k-blocks of a full tile, then per cluster
+// (first tile, first run, last tile, end run or 0x7fff).  Returns 1 when the balanced schedule is taken, 0 when the launch keeps the
+// round-robin walk (out[0..4] still set when a schedule exists), < 0 on bad arguments.
+extern "C" int df_conv_tc_schedule(int B, int H, int W, int Cin, int Cout, int dilation, int clusters, int* out)
+{
+    if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cin % BK || Cout <= 0 || Cout % 256 || dilation < 1 || clusters < 1 || clusters > Q_SCHED_MAX || !out)
+        return DF_ERR_ARG;
+    TcParams p = {};
+    p.conv_taps = 9; p.conv_dil = dilation; p.cW = W; p.cH = H; p.cB = B; p.precise = 4;
+    p.M = B * H * W; p.N = Cout; p.K = 9 * Cin;
+    conv_patch_plan(p, B, H, W, 9, dilation);
+    plan_runs(p);
+    const int m_tiles = (p.tiles_x * p.tiles_y * p.tiles_b + 1) / 2, n_tiles = Cout / 256, total = m_tiles * n_tiles;
+    const int cl = total < clusters ? total : clusters;
+    QSched sc = {};
+    long long rr = 0, sp = 0;
+    const bool ok = plan_split_ranges(p, 1, n_tiles, total, cl, &sc, &rr, &sp);
+    out[0] = (int)rr; out[1] = (int)sp; out[2] = total; out[3] = p.kbc; out[4] = p.K / BK;
+    for (int c = 0; c < cl; ++c) { out[5 + 4 * c] = sc.t0[c]; out[6 + 4 * c] = sc.r0[c]; out[7 + 4 * c] = sc.t1[c]; out[8 + 4 * c] = sc.r1[c]; }
+    return ok ? 1 : 0;
 }
 
 // 3x3 (stride 1, padding == dilation) or 1x1 convolution on an NHWC image as an implicit GEMM on the paired tcgen05

@@ -200,6 +200,14 @@ int df_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp
  * patches skip); host-side arithmetic only, for the time-weighted roofline of bench.py. */
 long long df_conv_tc_macs(int B, int H, int W, int Cin, int Cout, int taps, int dilation);
 
+/* The work schedule df_conv_tc uses for a hybrid16s 3x3 convolution of this geometry on `clusters` CTA pairs (256-wide tiles): long-K
+ * convolutions whose tile count does not fill the last round of the persistent kernel are cut into contiguous per-cluster ranges
+ * of (tile, accumulation run) units of equal weight instead of whole tiles dealt round robin.  Host-side arithmetic only.
+ *   out (5 + 4*clusters ints): [0] k-blocks of the busiest cluster under round robin, [1] under the balanced schedule, [2] tiles,
+ *   [3] k-blocks per accumulation run, [4] k-blocks of a full tile, then per cluster (first tile, first run, last tile, end run or 0x7fff).
+ * Returns 1: balanced schedule taken; 0: round robin kept; < 0: DF_ERR_ARG. */
+int df_conv_tc_schedule(int B, int H, int W, int Cin, int Cout, int dilation, int clusters, int* out);
+
 /* ---- colour encoder on the tensor cores (lib/extractors.py:78-124, lib/pspnet.py:7-77) ----
  * Activations are NHWC.  df_conv_tc: 3x3 (stride 1, padding == dilation) or 1x1 convolution as an implicit GEMM on the
  * CTA-pair tcgen05 kernel -- the A operand is a 4-D TMA box shifted by the tap, its out-of-image part zero-filled.
