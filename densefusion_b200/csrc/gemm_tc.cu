@@ -78,6 +78,8 @@ struct TcParams {
     // read wk_shift[tap] elements further along k (a 3x3 tap is an offset in the zero-padded, flattened pixel axis) ----
     int wk_rows;                                // 0: off
     int wk_shift[9], wk_row0[9];                // per tap: k offset (a multiple of 4 elements: TMA boxes start 16-byte aligned) and first row
+    int tstore;                                 // plain single-run GEMM form: the epilogue hands its 32 x 32 chunks to TMA stores (tm_c) instead
+                                                // of transposing them through shared memory and storing them itself
     int m_fastest;                              // tile order of the persistent loop (q_decode).  Default 0 = n fastest: the clusters
                                                 // running at one time share activation rows; measured 12% faster at M = 64000 /
                                                 // K = 1536 than sharing the weight tile (env DF_TC_TILE_ORDER=1)
@@ -276,7 +278,7 @@ template <int CTAS, int A_STAGES, int A_COLS, bool DBG, int FORM>
 __global__ void __launch_bounds__(Q_THREADS, 1)
 gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_whi,
                  const __grid_constant__ CUtensorMap tm_wlo, const TcParams p, const int bn_cta, const int m_tiles,
-                 const int n_tiles, const int total_tiles, const __grid_constant__ QSched sched)
+                 const int n_tiles, const int total_tiles, const __grid_constant__ QSched sched, const __grid_constant__ CUtensorMap tm_c)
 {
     // A_STAGES TMEM A stages of A_COLS columns each at the top of TMEM (64: [hi | lo] / [fp16 | - | bf16 | bf16 lo]; 32: the two
     // fp16 planes of hybrid16s, the only arithmetic that instantiation carries); the accumulators share what is left below.
@@ -833,6 +835,13 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               bias += (size_t)c.crop * bias_crop_stride;          // pooled tiles are crop-aligned: one bias row per tile
           }
           float* const Cg = p.C + c.g * p.c_gs;
+          // TMA-store epilogue (plain single-run GEMM form): lane == row keeps its 32 columns; its bias row is the one of its crop
+          const bool tstore = FORM == 0 && p.tstore;
+          const float* brow = nullptr;
+          if (tstore && p.bias) {
+              brow = p.bias + c.g * p.bias_gs;
+              if (bias_crop_stride) brow += (size_t)(min(c.row0 + r, p.M - 1) / p.rows_per_crop) * bias_crop_stride;
+          }
           for (int kc = ra; kc < rb; ++kc, ++ti) {
             const bool first_run = SPLIT ? (tail_part ? kc == ra : (!head_part && kc == 0)) : kc == 0;
             const bool last_run = SPLIT ? (!tail_part && kc == rb - 1) : kc == runs - 1;
@@ -868,6 +877,39 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             for (int ch = half; ch < nchunks; ch += 2) {
                 uint32_t v[32];
                 const int col = c.n0 + ch * 32;
+                if (FORM == 0 && tstore) {
+                    // The chunk goes to memory as ONE TMA store of the warp's 32 x 32 tile: every lane finishes its own row (scale, bias,
+                    // activation -- the same operations in the same order as the store path below, so the results are bit-identical),
+                    // writes it to the swizzled staging tile (the layout a 128B-swizzle box expects) and lane 0 hands the tile to the
+                    // TMA unit, which clips rows past M and columns past N.  No transpose read-back, no per-row address arithmetic, no
+                    // store instructions in the warp: the clock64 timeline put one chunk at ~3 400 clocks, 1 800 of them between
+                    // "transposed" and "stores issued" -- three chunks per tile were as long as tower-1's whole k loop.
+                    if (col >= p.N) continue;
+                    tmem_ld32(tmem_base + lane_base + ab * ACC_STRIDE + ch * 32, v);
+                    if (lane == 0) bulk_wait_group_read0();            // the previous chunk's store has read the staging tile
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (brow && col + j * 4 < p.N) b = __ldg(reinterpret_cast<const float4*>(brow + col + j * 4));
+                        float4 o = make_float4(__uint_as_float(v[j * 4]), __uint_as_float(v[j * 4 + 1]), __uint_as_float(v[j * 4 + 2]),
+                                               __uint_as_float(v[j * 4 + 3]));
+                        if (run_scale != 1.0f) {
+                            o.x = __fmul_rn(o.x, run_scale); o.y = __fmul_rn(o.y, run_scale);
+                            o.z = __fmul_rn(o.z, run_scale); o.w = __fmul_rn(o.w, run_scale);
+                        }
+                        o.x = __fadd_rn(o.x, b.x); o.y = __fadd_rn(o.y, b.y); o.z = __fadd_rn(o.z, b.z); o.w = __fadd_rn(o.w, b.w);
+                        if (p.relu == 1) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = o;
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && c.row0 + q * 32 < p.M) {
+                        tma_store_2d(&tm_c, stage, (int)(c.g * p.c_gs) + col, c.row0 + q * 32);
+                        bulk_commit_group();
+                    }
+                    continue;
+                }
                 const int cq = col + cc * 4;
                 // this lane's 4 bias values (requested before the accumulator is read: the L2 round trip overlaps the TMEM load and the
                 // transpose): one vector, or two when the warp's 32 rows straddle a crop boundary
@@ -1019,6 +1061,7 @@ gemm_tc_q_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
           }
         }
+        if (FORM == 0 && lane == 0) bulk_wait_group0();                 // TMA stores of this warp are complete before the CTA exits
     }
     tc_fence_before();
     __syncthreads();
@@ -1149,7 +1192,7 @@ int pair_m_tiles(const TcParams& p)
 unsigned long long* g_trace = nullptr;
 
 typedef void (*QKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const int, const int, const int, const int,
-                        const QSched);
+                        const QSched, const CUtensorMap);
 
 // Instantiation that serves a launch: the specialised forms (QForm) exist for the hybrid16s variants, i.e. the inference path; everything
 // else -- the older arithmetic modes, the weight-gradient form, multi-run GEMMs, PReLU on a GEMM, DF_TC_DBG -- runs the generic one.
@@ -1418,6 +1461,15 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = use_pdl() ? 2 : 1;
     int form = -1;
+    CUtensorMap mc = mhi;
+    {   // TMA-store epilogue of the plain GEMM form: C as a 2-D tensor whose boxes are the epilogue warps' 32 x 32 chunks; grouped
+        // launches must write column slices of one matrix (c_gs = column offset)
+        static const int ts_env = getenv("DF_TC_TSTORE") ? atoi(getenv("DF_TC_TSTORE")) : 1;
+        const long long width = groups == 1 ? p.N : (long long)(groups - 1) * p.c_gs + p.N;
+        p.tstore = ts_env && A_COLS != 64 && !p.conv_taps && !p.pool_partial && !p.c1_H && !p.wk_rows && p.k_chunks == 1 && !p.residual &&
+                   p.relu != 2 && (groups == 1 || (p.c_gs >= p.N && p.N % bnt == 0)) && width <= p.ldc && !(p.ldc & 3) && !((uintptr_t)p.C & 15) &&
+                   make_map(&mc, p.C, p.M, (int)width, p.ldc, 32);
+    }
     QSched sched = {};
     const bool split = (CTAS == 2 && A_COLS == 0 && A_STAGES == 4) ? plan_split(p, groups, n_tiles, total, clusters, &sched) : false;
     const QKernel kern = pick_q_kernel<CTAS, A_STAGES, A_COLS>(p, &form, split);
@@ -1430,7 +1482,7 @@ int launch_q(const TcParams& p_in, const float* W_hi, const float* W_lo, int ldw
             smem_set[slot] = true;
         }
     }
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mhi, mlo, p, bn_cta, m_tiles, n_tiles, total, sched);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mhi, mlo, p, bn_cta, m_tiles, n_tiles, total, sched, mc);
     return e == cudaSuccess ? 0 : (int)e;
 }
 

@@ -62,6 +62,46 @@ def test_conv_tc_vs_float64(B, H, W, Cin, Cout, taps, dil, extras):
         assert float(wide[..., :32].min()) == 7.0 and float(wide[..., 32 + Cout:].max()) == 7.0    # neighbours untouched
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,dil,extras", [
+    (37, 15, 15, 512, 512, 2, "residual"),          # 70 tiles of <= 144 k-blocks on 74 CTA pairs... see the assertion on the schedule
+    (96, 15, 15, 512, 512, 4, "relu"),              # layer4.1 of the bench step's 120 px bucket: border tiles skip taps (ragged runs)
+    (40, 20, 20, 512, 512, 1, "residual"),          # 126 tiles
+    (64, 20, 20, 256, 256, 2, "relu"),              # two runs per tile
+])
+def test_conv_tc_balanced_schedule_vs_float64(B, H, W, Cin, Cout, dil, extras):
+    """Launches large enough to take the balanced (tile, run) schedule of gemm_tc.cu (QSched): tiles shared by two clusters are
+    handed over through the per-warp flags; the result must match a float64 convolution like any other launch, be the same from
+    run to run, and leave the neighbouring channels of a wider buffer alone."""
+    import ctypes
+    from densefusion_b200 import _C
+    from densefusion_b200.encoder import PackedEncoder, _pack_conv
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    info = (ctypes.c_int * (5 + 4 * 80))()
+    planned = _C.lib.df_conv_tc_schedule(B, H, W, Cin, Cout, dil, min(sms // 2, 80), ctypes.cast(info, ctypes.c_void_p))
+    assert planned == 1, "the shape no longer takes the balanced schedule: pick another one"
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + H + Cin + Cout)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (Cin * 9) ** 0.5
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    res = torch.randn(B, H, W, Cout, device="cuda", generator=g) if extras == "residual" else None
+    want = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), bias.double(), padding=dil, dilation=dil).permute(0, 2, 3, 1)
+    if res is not None:
+        want = want + res.double()
+    want = torch.relu(want)
+    outs = []
+    for rep in range(3):
+        wide = torch.full((B, H, W, Cout + 64), 7.0, device="cuda")
+        out = wide[..., 32:32 + Cout]
+        PackedEncoder._conv(x, _pack_conv(w), out, taps=9, dil=dil, bias=bias, residual=res, act=1, mode=ops.PRECISIONS["hybrid16s"])
+        torch.cuda.synchronize()
+        assert float(wide[..., :32].min()) == 7.0 and float(wide[..., 32 + Cout:].max()) == 7.0
+        outs.append(out.clone())
+    err = float((outs[0].double() - want).abs().max() / want.abs().max())
+    print(f"balanced schedule {B}x{H}x{W} {Cin}->{Cout} dil {dil}: {err:.3e} (busiest cluster {info[1]} instead of {info[0]} k-blocks)")
+    assert err < 2e-5
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
 def test_encoder_helper_kernels_vs_torch():
     from densefusion_b200._C import check, lib, ptr, stream
     g = torch.Generator().manual_seed(2)
