@@ -43,7 +43,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("DF_PRECISION", "hybrid16s"), choices=["fp32", "3xtf32", "tf32", "hybrid", "hybrid16", "hybrid16s"])
     ap.add_argument("--frames", type=int, default=32, help="frames (of 8 objects) per GPU per step")
-    ap.add_argument("--chunk", type=int, default=128, help="crops per head chunk (measured 16: 21.7 ms, 32: 20.7, 64: 20.3, 128: 20.05 per step)")
+    ap.add_argument("--chunk", type=int, default=256, help="crops per head chunk (round 1, per step: 16: 21.7 ms, 32: 20.7, 64: 20.3, 128: 20.05; "
+                                                          "round 2, same box: 128: 9.06 / 9.12 ms, 256: 8.93 / 9.04, profiles/r2_s4_bench_ab_chunk.jsonl)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
@@ -392,7 +393,7 @@ def dominant_kernel_roofline(pipe, precision, peaks, live):
     out = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
            "traffic": traffic, "ms_per_launch": ms, "ms_per_launch_hot": ms_hot, "achieved_hot": flops / (ms_hot * 1e-3) / 1e12,
            "algorithmic_flops_per_launch": flops,
-           "l2": "operands + output of one launch (596 MB at the default chunk) exceed the 126 MB L2",
+           "l2": f"operands + output of one launch ({(rows * (384 + 1920) * 4 + 1920 * 384 * 4) / 1e6:.0f} MB at this chunk) exceed the 126 MB L2",
            "cublas_tf32_8192_tflops": tf32_lib, "ffma_tflops_measured": live.get("ffma_tflops"),
            "executed_over_algorithmic": PASSES.get(precision, 1.0), "peak_source": peak_note, "shape": shape}
     if precision in ("hybrid16", "hybrid16s", "hybrid", "3xtf32"):

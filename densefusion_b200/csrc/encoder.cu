@@ -380,6 +380,84 @@ upconv_finish_smem_kernel(const float* __restrict__ Z, int ldz, const float* __r
     }
 }
 
+// The same kernel with fewer instructions per output (the kernel is issue-bound: ncu 77% issue-active, and its SASS spends ~46
+// instructions per tap, 28 of them floating point, for 4 shared-memory reads): the row / column quantities of the three ky / kx are
+// computed once per pixel (index into the footprint, step to the neighbour, the two 1-D weights), the four corner weights of a tap are
+// products of those (4 multiplies per tap, shared by the 4 channels of the lane) and every corner is ONE fused multiply-add per
+// channel: 16 FFMA + 4 FMUL per tap instead of 12 FMUL + 12 FFMA + 4 FADD.  The rounding differs from upconv_finish_kernel's
+// interpolate-then-add order in the last bit (both are within 5e-6 of the float64 layer, tests/test_encoder_gpu.py).
+template <int LANES>
+__global__ void __launch_bounds__(256)
+upconv_finish_smem_fma_kernel(const float* __restrict__ Z, int ldz, const float* __restrict__ bias, const float* __restrict__ prelu,
+                              float* __restrict__ out, int ldo, int h, int w, int C, float rh, float rw, int tiles_x)
+{
+    extern __shared__ __align__(16) uint8_t uf_smem[];
+    float4* s = reinterpret_cast<float4*>(uf_smem);                 // [(ry * cols + rx) * 9 + tap][LANES]
+    constexpr int PIX_PER_PASS = 256 / LANES;
+    const int H = 2 * h, W = 2 * w;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int Y0 = ty * UF_T, X0 = tx * UF_T, c0 = blockIdx.y * (LANES * 4), b = blockIdx.z;
+    const int ya = max(Y0 - 1, 0), yb = min(Y0 + UF_T, H - 1), xa = max(X0 - 1, 0), xb = min(X0 + UF_T, W - 1);
+    const int y_lo = (int)(rh * ya), x_lo = (int)(rw * xa);
+    const int y_hi = min((int)(rh * yb) + 1, h - 1), x_hi = min((int)(rw * xb) + 1, w - 1);
+    const int rows = y_hi - y_lo + 1, cols = x_hi - x_lo + 1;       // <= UF_FP each
+    const float* zb = Z + (size_t)b * h * w * ldz + c0;
+    for (int i = threadIdx.x; i < rows * cols * 9 * LANES; i += 256) {
+        const int c = i % LANES, pt = i / LANES;
+        const int tap = pt % 9, px = pt / 9;
+        const int ry = px / cols, rx = px - ry * cols;
+        s[i] = __ldg(reinterpret_cast<const float4*>(zb + ((size_t)(y_lo + ry) * w + (x_lo + rx)) * ldz + tap * C) + c);
+    }
+    __syncthreads();
+    const float slope = __ldg(prelu);
+    const int cq = threadIdx.x % LANES;
+    const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias + c0) + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int row_step = cols * 9 * LANES;                          // float4 elements between footprint rows / columns
+    constexpr int col_step = 9 * LANES;
+#pragma unroll 1
+    for (int pass = 0; pass < UF_T * UF_T / PIX_PER_PASS; ++pass) {
+        const int pix = pass * PIX_PER_PASS + (threadIdx.x / LANES);
+        const int Y = Y0 + pix / UF_T, X = X0 + pix % UF_T;
+        if (Y >= H || X >= W) continue;
+        // per axis and tap offset k - 1: footprint index of the first sample, step to the second one, the two weights (0 outside the map)
+        int yo[3], ys[3], xo[3], xs[3];
+        float wy0[3], wy1[3], wx0[3], wx1[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int yy = Y + k - 1, xx = X + k - 1;
+            const bool vy = yy >= 0 && yy < H, vx = xx >= 0 && xx < W;
+            const float sy = rh * (vy ? yy : 0), sx = rw * (vx ? xx : 0);
+            const int y0 = (int)sy, x0 = (int)sx;
+            const float ly1 = sy - y0, lx1 = sx - x0;
+            yo[k] = (y0 - y_lo) * row_step; ys[k] = y0 < h - 1 ? row_step : 0;
+            xo[k] = (x0 - x_lo) * col_step; xs[k] = x0 < w - 1 ? col_step : 0;
+            wy0[k] = vy ? 1.0f - ly1 : 0.f; wy1[k] = vy ? ly1 : 0.f;
+            wx0[k] = vx ? 1.0f - lx1 : 0.f; wx1[k] = vx ? lx1 : 0.f;
+        }
+        float4 acc = bv;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                // (a tap outside the output map has zero weights and reads the in-range sample of row / column 0 of the map)
+                const float4* p = s + yo[ky] + xo[kx] + (ky * 3 + kx) * LANES + cq;
+                const float4 v00 = p[0];
+                const float4 v01 = p[xs[kx]];
+                const float4 v10 = p[ys[ky]];
+                const float4 v11 = p[ys[ky] + xs[kx]];
+                const float w00 = wy0[ky] * wx0[kx], w01 = wy0[ky] * wx1[kx], w10 = wy1[ky] * wx0[kx], w11 = wy1[ky] * wx1[kx];
+                acc.x = fmaf(w00, v00.x, acc.x); acc.y = fmaf(w00, v00.y, acc.y); acc.z = fmaf(w00, v00.z, acc.z); acc.w = fmaf(w00, v00.w, acc.w);
+                acc.x = fmaf(w01, v01.x, acc.x); acc.y = fmaf(w01, v01.y, acc.y); acc.z = fmaf(w01, v01.z, acc.z); acc.w = fmaf(w01, v01.w, acc.w);
+                acc.x = fmaf(w10, v10.x, acc.x); acc.y = fmaf(w10, v10.y, acc.y); acc.z = fmaf(w10, v10.z, acc.z); acc.w = fmaf(w10, v10.w, acc.w);
+                acc.x = fmaf(w11, v11.x, acc.x); acc.y = fmaf(w11, v11.y, acc.y); acc.z = fmaf(w11, v11.z, acc.z); acc.w = fmaf(w11, v11.w, acc.w);
+            }
+        }
+        acc.x = acc.x > 0.f ? acc.x : slope * acc.x; acc.y = acc.y > 0.f ? acc.y : slope * acc.y;
+        acc.z = acc.z > 0.f ? acc.z : slope * acc.z; acc.w = acc.w > 0.f ? acc.w : slope * acc.w;
+        *reinterpret_cast<float4*>(out + (((size_t)b * H + Y) * W + X) * ldo + c0 + cq * 4) = acc;
+    }
+}
+
 // (A separable form -- x pass at the footprint rows, then a y pass: 24 instead of 36 shared-memory reads per output -- was measured in
 // round 2 and is SLOWER, 0.357 vs 0.195 ms on up_1: the extra barrier, the ragged x pass and the lower occupancy of a 78 KB CTA cost
 // more than the reads saved; the kernel is latency / occupancy bound, not LDS bound.)
@@ -568,7 +646,15 @@ extern "C" int df_enc_upconv_finish(const float* Z, int ldz, const float* bias, 
             attr_done = true;
         }
         const int tiles_x = (W + UF_T - 1) / UF_T, tiles_y = (H + UF_T - 1) / UF_T;
-        if (use_smem == 2)
+        if (use_smem == 3) {
+            static bool attr3 = false;
+            if (!attr3) {
+                cudaError_t e = cudaFuncSetAttribute(upconv_finish_smem_fma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, UF_SMEM);
+                if (e != cudaSuccess) return (int)e;
+                attr3 = true;
+            }
+            upconv_finish_smem_fma_kernel<8><<<dim3(tiles_x * tiles_y, C / 32, B), 256, UF_SMEM, (cudaStream_t)stream>>>(Z, ldz, bias, prelu, out, ldo, h, w, C, rh, rw, tiles_x);
+        } else if (use_smem == 2)
             upconv_finish_smem_kernel<4><<<dim3(tiles_x * tiles_y, C / 16, B), 256, UF_SMEM / 2, (cudaStream_t)stream>>>(Z, ldz, bias, prelu, out, ldo, h, w, C, rh, rw, tiles_x);
         else
             upconv_finish_smem_kernel<8><<<dim3(tiles_x * tiles_y, C / 32, B), 256, UF_SMEM, (cudaStream_t)stream>>>(Z, ldz, bias, prelu, out, ldo, h, w, C, rh, rw, tiles_x);

@@ -17,7 +17,7 @@ from ._C import check, lib, ptr, stream
 
 
 class PoseEstimator:
-    def __init__(self, estimator, refiner, iterations: int = 2, precision: str = "fp32", chunk_crops: int = 128,
+    def __init__(self, estimator, refiner, iterations: int = 2, precision: str = "fp32", chunk_crops: int = 256,
                  channels_last: bool = False, encoder: str = "auto"):
         # channels_last=False: with TF32 disabled cuDNN's NHWC fp32 convolutions fall back to a direct kernel that
         # is 3.5x slower than the NCHW ones (profiles/r1_call2_encoder_variants.json); NHWC only pays with TF32 on.

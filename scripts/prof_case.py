@@ -13,7 +13,7 @@ torch.manual_seed(0)
 case = sys.argv[1]
 mode = sys.argv[2] if len(sys.argv) > 2 else "hybrid16s"
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
-crops, n = 128, 500
+crops, n = int(os.environ.get("DF_PROF_CROPS", "256")), 500
 rows = crops * n
 
 
