@@ -429,8 +429,8 @@ upconv_finish_smem_fma_kernel(const float* __restrict__ Z, int ldz, const float*
             const float sy = rh * (vy ? yy : 0), sx = rw * (vx ? xx : 0);
             const int y0 = (int)sy, x0 = (int)sx;
             const float ly1 = sy - y0, lx1 = sx - x0;
-            yo[k] = (y0 - y_lo) * row_step; ys[k] = y0 < h - 1 ? row_step : 0;
-            xo[k] = (x0 - x_lo) * col_step; xs[k] = x0 < w - 1 ? col_step : 0;
+            yo[k] = vy ? (y0 - y_lo) * row_step : 0; ys[k] = (vy && y0 < h - 1) ? row_step : 0;
+            xo[k] = vx ? (x0 - x_lo) * col_step : 0; xs[k] = (vx && x0 < w - 1) ? col_step : 0;
             wy0[k] = vy ? 1.0f - ly1 : 0.f; wy1[k] = vy ? ly1 : 0.f;
             wx0[k] = vx ? 1.0f - lx1 : 0.f; wx1[k] = vx ? lx1 : 0.f;
         }
@@ -439,7 +439,7 @@ upconv_finish_smem_fma_kernel(const float* __restrict__ Z, int ldz, const float*
         for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                // (a tap outside the output map has zero weights and reads the in-range sample of row / column 0 of the map)
+                // (a tap outside the output map has zero weights and reads the first sample of the footprint)
                 const float4* p = s + yo[ky] + xo[kx] + (ky * 3 + kx) * LANES + cq;
                 const float4 v00 = p[0];
                 const float4 v01 = p[xs[kx]];
@@ -635,9 +635,11 @@ extern "C" int df_enc_upconv_finish(const float* Z, int ldz, const float* bias, 
     if ((long long)B * 4 * h * w * (C >> 2) >= (1LL << 31)) return DF_ERR_ARG;
     const int H = 2 * h, W = 2 * w;
     const float rh = H > 1 ? (float)(h - 1) / (H - 1) : 0.f, rw = W > 1 ? (float)(w - 1) / (W - 1) : 0.f;
-    // DF_UPCONV_SMEM: 0 = L1-gather kernel, 1 (default) = footprint staged in shared memory, 32 channels per CTA, 2 = the same with 16
-    // channels per CTA (twice the CTAs per SM; measured 10% SLOWER and bit-identical: occupancy is not what limits this kernel)
-    static const int use_smem = getenv("DF_UPCONV_SMEM") ? atoi(getenv("DF_UPCONV_SMEM")) : 1;
+    // DF_UPCONV_SMEM: 0 = L1-gather kernel, 1 = footprint staged in shared memory, 32 channels per CTA (bit-identical to 0), 2 = the same
+    // with 16 channels per CTA (twice the CTAs per SM; measured 10% SLOWER: occupancy is not what limits this kernel), 3 (default) = 1
+    // with per-axis quantities hoisted and one FFMA per corner and channel (355 instead of 524 SASS instructions per output float4,
+    // branch-free): 0.1956 -> 0.1748 ms on up_1's 64x20x20x256, -10..11% on every bench shape (profiles/r2_s4_upconv_ab.jsonl)
+    static const int use_smem = getenv("DF_UPCONV_SMEM") ? atoi(getenv("DF_UPCONV_SMEM")) : 3;
     if (use_smem && C % 32 == 0 && B <= 65535 && h >= 2 && w >= 2) {
         static bool attr_done = false;
         if (!attr_done) {

@@ -13,6 +13,8 @@
 #include "df_common.cuh"
 #include "../../include/densefusion_b200.h"
 #include <math_constants.h>
+#include <stdlib.h>
+#include <cooperative_groups.h>
 
 namespace {
 
@@ -54,16 +56,25 @@ __device__ __forceinline__ void load_rotation(const float* q, float (&R)[9])
     df::quat_to_rot(w / n, x / n, y / n, z / n, R);
 }
 
+// CL > 1 (the refiner loss, P == 1: lib/loss_refiner.py:12-62 has ONE hypothesis per crop, i.e. one CTA per crop on 148 SMs): a
+// thread-block cluster of CL CTAs shares the hypothesis -- CTA `rank` takes the rank-th slice of the model points (each scans the
+// whole target cloud for its own queries), leaves its 13 partial sums in its shared memory, and rank 0 adds them in rank order
+// through distributed shared memory (fixed order: deterministic) before it continues as the crop's last CTA.
+template <int CL>
 __global__ void __launch_bounds__(LOSS_THREADS)
 loss_forward_kernel(const LossParams a)
 {
     __shared__ float4 s_tgt[LOSS_TILE];
     __shared__ float s_red[LOSS_THREADS / 32][LOSS_NRED];
     __shared__ float s_sel[16];
+    __shared__ float s_part[LOSS_NRED];
     __shared__ int s_flag;
 
-    const int p = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int p = blockIdx.x / CL, b = blockIdx.y, tid = threadIdx.x;
+    const int rank = CL > 1 ? (int)cooperative_groups::this_cluster().block_rank() : 0;
     const int P = a.P, M = a.M;
+    const int slice = (M + CL - 1) / CL;                   // model points per CTA of the cluster
+    const int m_lo = rank * slice, m_hi = min(M, m_lo + slice);
     const float* tgt = a.target + (size_t)b * M * 3;
     const float* mdl = a.model + (size_t)b * M * 3;
     const long long obj = a.idx[b];
@@ -83,14 +94,14 @@ loss_forward_kernel(const LossParams a)
     for (int i = 0; i < LOSS_NRED; ++i) acc[i] = 0.0f;
 
     const float t0x = tgt[0], t0y = tgt[1], t0z = tgt[2];
-    for (int j0 = 0; j0 < M; j0 += LOSS_THREADS * LOSS_QPT) {
+    for (int j0 = m_lo; j0 < m_hi; j0 += LOSS_THREADS * LOSS_QPT) {
         float mx[LOSS_QPT], my[LOSS_QPT], mz[LOSS_QPT], px[LOSS_QPT], py[LOSS_QPT], pz[LOSS_QPT];
         float best[LOSS_QPT];
         int arg[LOSS_QPT];
 #pragma unroll
         for (int i = 0; i < LOSS_QPT; ++i) {
             const int j = j0 + i * LOSS_THREADS + tid;
-            const bool ok = j < M;
+            const bool ok = j < m_hi;
             mx[i] = ok ? mdl[j * 3 + 0] : 0.0f;
             my[i] = ok ? mdl[j * 3 + 1] : 0.0f;
             mz[i] = ok ? mdl[j * 3 + 2] : 0.0f;
@@ -118,7 +129,7 @@ loss_forward_kernel(const LossParams a)
 #pragma unroll
         for (int i = 0; i < LOSS_QPT; ++i) {
             const int j = j0 + i * LOSS_THREADS + tid;
-            if (j < M) {
+            if (j < m_hi) {
                 const float ex = px[i] - tgt[arg[i] * 3 + 0];
                 const float ey = py[i] - tgt[arg[i] * 3 + 1];
                 const float ez = pz[i] - tgt[arg[i] * 3 + 2];
@@ -147,6 +158,25 @@ loss_forward_kernel(const LossParams a)
         for (int i = 0; i < LOSS_NRED; ++i) s_red[tid >> 5][i] = acc[i];
     }
     __syncthreads();
+    if (CL > 1) {
+        namespace cg = cooperative_groups;
+        cg::cluster_group cluster = cg::this_cluster();
+        if (tid < LOSS_NRED) {
+            float v = 0.0f;
+            for (int wv = 0; wv < LOSS_THREADS / 32; ++wv) v += s_red[wv][tid];
+            s_part[tid] = v;
+        }
+        cluster.sync();                                    // every CTA's partial sums are in its shared memory
+        if (rank == 0 && tid < LOSS_NRED) {
+            float v = s_part[tid];
+            for (int r = 1; r < CL; ++r) v += *cluster.map_shared_rank(&s_part[tid], r);
+            s_red[0][tid] = v;
+            for (int wv = 1; wv < LOSS_THREADS / 32; ++wv) s_red[wv][tid] = 0.0f;
+        }
+        cluster.sync();                                    // the remote reads are done: the other CTAs may leave
+        if (rank != 0) return;
+        __syncthreads();
+    }
     if (tid == 0) {
         float tot[LOSS_NRED];
 #pragma unroll
@@ -305,7 +335,25 @@ extern "C" int df_loss_forward(const float* pred_r, const float* pred_t, const f
     a.w = w; a.P = P; a.M = M; a.N = N; a.dis_all = dis_all; a.sum_u = sum_u; a.sum_um = sum_um; a.loss = loss;
     a.dis_sel = dis_sel; a.which = which; a.new_points = new_points; a.new_target = new_target;
     a.tickets = tickets; a.dbg_pred = dbg_pred; a.dbg_nn = dbg_nn;
-    loss_forward_kernel<<<dim3(P, B), LOSS_THREADS, 0, (cudaStream_t)stream>>>(a);
+    // One hypothesis per crop (the refiner loss) and few crops (training runs it at batch 1, tools/train.py:159): 8 CTAs of a cluster
+    // share the hypothesis.  Measured (profiles/r2_s4_loss_refine_probe.jsonl, us per call inside a CUDA graph): B = 1, M = 500
+    // 27.8 -> 21.0; B = 1, M = 2600 563 -> 70.7; B = 8 27.9 -> 20.6; with 256 crops the 2048 CTAs each scanning the whole target cloud for
+    // 63 queries lose (33.6 -> 145), hence the limit on B.  The sums of the slices are added in a different order than one CTA adds
+    // its warps: results differ in the last bits between the two forms, each form is deterministic.  DF_LOSS_CLUSTER=0: never.
+    static const int use_cluster = getenv("DF_LOSS_CLUSTER") ? atoi(getenv("DF_LOSS_CLUSTER")) : 1;
+    if (P == 1 && M >= 64 && B <= 16 && use_cluster) {
+        constexpr int CL = 8;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(CL, B); cfg.blockDim = dim3(LOSS_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, loss_forward_kernel<CL>, a);
+        if (e != cudaSuccess) return (int)e;
+        DF_RETURN_LAST_ERROR();
+    }
+    loss_forward_kernel<1><<<dim3(P, B), LOSS_THREADS, 0, (cudaStream_t)stream>>>(a);
     DF_RETURN_LAST_ERROR();
 }
 

@@ -1,7 +1,8 @@
 """Profiling driver (ncu): ONE tensor-core launch shape of the pose step, `reps` launches.
 
     python scripts/prof_case.py <case> [precision] [reps]
-cases: tower1 tower2 tower3 conv5 conv5r conv6 pf2 up1 up2 bott l40 l41 l31 l1"""
+cases: tower1 tower2 tower3 conv5 conv5r conv6 pf2 up1 up2 bott l40 l41 l40b l41b l31 l1   (l40b / l41b: layer4 on the 15x15 maps of the
+120 px bucket -- the balanced (tile, run) schedule); DF_PROF_CROPS = crops per head chunk (256)"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -41,6 +42,7 @@ def conv(B, H, W, Cin, Cout, dil, taps=9):
  "tower3": lambda: gemm(rows, 128, 256, groups=3), "conv5": lambda: gemm(rows, 512, 256), "conv5r": lambda: gemm(rows, 512, 384),
  "conv6": lambda: gemm(rows, 1024, 512, pooled=True), "pf2": lambda: gemm(rows, 128, 64), "up1": lambda: gemm(25600, 2304, 1024),
  "up2": lambda: gemm(102400, 576, 256), "bott": lambda: conv(64, 20, 20, 512, 1024, 1, taps=1), "l40": lambda: conv(64, 20, 20, 512, 512, 1),
- "l41": lambda: conv(64, 20, 20, 512, 512, 4), "l31": lambda: conv(64, 20, 20, 256, 256, 2), "l1": lambda: conv(64, 40, 40, 64, 64, 1)}[case]()
+ "l41": lambda: conv(64, 20, 20, 512, 512, 4),
+ "l40b": lambda: conv(96, 15, 15, 512, 512, 1), "l41b": lambda: conv(96, 15, 15, 512, 512, 4), "l31": lambda: conv(64, 20, 20, 256, 256, 2), "l1": lambda: conv(64, 40, 40, 64, 64, 1)}[case]()
 torch.cuda.synchronize()
 print("ok")

@@ -12,7 +12,7 @@ dev = torch.device("cuda", 0)
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 est, ref, _, _ = bench.build_modules(dev)
-pipe = PoseEstimator(est, ref, iterations=2, precision=precision, chunk_crops=128)
+pipe = PoseEstimator(est, ref, iterations=2, precision=precision, chunk_crops=256)
 buckets = [{k: v.to(dev) for k, v in b.items()} for b in bench.make_host_buckets(frames, 3, pin=False)]
 for _ in range(3):
     pipe.estimate_buckets(buckets)
