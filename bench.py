@@ -321,6 +321,7 @@ def time_weighted_roofline(pipe, dev_set, precision, peaks, live):
             "peak": tf32_peak, "frac": ach / tf32_peak,
             "frac_of_bf16_sustained_in_mma_time": PASSES.get(precision, 1.0) * 2.0 * ach / peaks.get("bf16_tflops_sustained", 1403.9),
             "top": [{"ms": round(t, 4), "tflops": round(f / (t * 1e-3) / 1e12, 1), "launch": w} for t, f, w in per[:6]],
+            "per_launch": {w: [round(t, 4), f] for t, f, w in reversed(per)},       # (shape -> [ms, flops]; the fastest instance of a shape)
             "note": "eager, single stream, CUDA events around every df_gemm_tc / df_conv_tc launch of one step; flops = executed "
                     "multiply-adds x 2 on real rows (skipped all-padding taps not counted); peak = cuBLAS TF32 measured in this run"}
 
@@ -344,6 +345,14 @@ def finish_roofline(roof, tw, precision, peaks, live):
         if tf32_lib:
             tw["peak"] = tf32_lib
         tw["frac"] = tw["achieved"] / tw["peak"]
+        # the roofline kernel as it runs INSIDE the step (between other kernels, eager, one launch): the 20-launch burst above keeps the
+        # GPU at its power cap (sw_power_cap, SM clock ~10-15% below maximum), a single launch in the step does not
+        per = tw.pop("per_launch", {})
+        key = "gemm " + roof.get("shape", "") + " g=1"
+        if key in per and per[key][0] > 0:
+            t, f = per[key]
+            roof["in_step"] = {"ms_per_launch": t, "achieved": f / (t * 1e-3) / 1e12, "frac": f / (t * 1e-3) / 1e12 / roof["peak"],
+                               "note": "the same launch timed once inside one eager step of the pipeline (time_weighted's own measurement)"}
         roof["time_weighted"] = tw
 
 
