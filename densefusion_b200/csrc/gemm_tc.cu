@@ -1302,8 +1302,8 @@ bool plan_split(const TcParams& p, int groups, int n_tiles, int total, int clust
     if (!split_enabled() || !plan_split_ranges(p, groups, n_tiles, total, clusters, out, nullptr, nullptr)) return false;
     static unsigned int* flags = nullptr;
     if (!flags && cudaGetSymbolAddress(reinterpret_cast<void**>(&flags), g_split_flags) != cudaSuccess) { (void)cudaGetLastError(); return false; }
-    static unsigned int region = 0;
-    out->flags = flags + (size_t)(region++ & 255u) * (Q_SCHED_MAX * 16);
+    static unsigned int region = 0;                                   // (atomic: launches may come from several host threads)
+    out->flags = flags + (size_t)(__sync_fetch_and_add(&region, 1u) & 255u) * (Q_SCHED_MAX * 16);
     return true;
 }
 
