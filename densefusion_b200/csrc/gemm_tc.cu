@@ -1170,9 +1170,22 @@ int pair_tile_width(const TcParams& p, int groups, int m_tiles, int acc_stride, 
         if (w == 256 && acc_stride < 256 && !p.pool_partial && !(wide_kb > 0 && p.K / BK >= wide_kb)) continue;
         if (w == 192 && acc_stride < 192) continue;
         if (w == 64 && p.N > 64) continue;                     // narrow layers only (64-channel decoder stages)
-        if (p.N % w != 0 && (groups > 1 || w == 256)) continue;
+        // 256-wide tiles over an N that is not a multiple of 256 (tower-1: 1920 = 7.5 tiles): the last tile of a row is half masked --
+        // its missing weight rows are out-of-bounds rows of the TMA box (zero fill, no bytes through the port), its missing columns are
+        // skipped by the epilogue.  Only with two 256-column accumulators (A planes in shared memory), a plain GEMM and a tail of at
+        // least half a tile; DF_TC_TAIL256 = 0 never, 1 by the cost below, 2 always.
+        static const int tail256 = getenv("DF_TC_TAIL256") ? atoi(getenv("DF_TC_TAIL256")) : 0;
+        const bool tail_ok = w == 256 && tail256 && groups == 1 && acc_stride >= 256 && !p.conv_taps && !p.pool_partial && !p.wk_rows &&
+                             !p.c1_H && p.N >= 1024 && p.N % 256 >= 128;
+        if (p.N % w != 0 && (groups > 1 || (w == 256 && !tail_ok))) continue;
         const long long tiles = (long long)m_tiles * ((p.N + w - 1) / w) * groups;
         long long cost = ((tiles + max_clusters - 1) / max_clusters) * (w + 32);
+        if (tail_ok && p.N % w != 0) {
+            // operand-port time of a row of tiles (128 activation rows + w / 2 weight rows per CTA and k-block; the masked half of the
+            // tail tile is free), in the units of the cost above: 192-wide tiles come out at 224
+            const long long nt = (p.N + w - 1) / w;
+            cost = tail256 >= 2 ? 0 : ((tiles + max_clusters - 1) / max_clusters) * ((nt * 256 - 64) / nt);
+        }
         if (w == 256 && acc_stride >= 256) {
             // long-K convolutions on the balanced schedule (QSched) are not quantised to whole rounds: the busiest cluster's k-blocks
             const long long kb = split_busiest_kblocks(p, groups, (int)tiles, max_clusters);

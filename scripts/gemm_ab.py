@@ -86,6 +86,7 @@ def conv_case(name, B, H, W, Cin, Cout, dil):
 
 rows = 128 * 500
 gemm_case("tower1 (bench roofline kernel)", rows, 1920, 384, percrop=True)
+gemm_case("tower1 at 256 crops (bench chunk)", 2 * rows, 1920, 384, percrop=True)
 gemm_case("tower2 grouped", rows, 256, 640, groups=3)
 gemm_case("tower3 grouped", rows, 128, 256, groups=3)
 gemm_case("conv5", rows, 512, 256)
