@@ -189,11 +189,12 @@ upsample_nhwc_kernel(const float* __restrict__ in, int ldi, float* __restrict__ 
 // GEMM.  pyramid_pool: the four adaptive average pools in one pass -> (50 B, C) stage-major: rows [B x 1 | B x 4 | B x 9 | B x 36],
 // so that every stage is one dense GEMM operand.
 __global__ void __launch_bounds__(256)
-pyramid_pool_kernel(const float* __restrict__ in, int ldi, float* __restrict__ out, int B, int H, int W, int C)
+pyramid_pool_kernel(const float* __restrict__ in, int ldi, float* __restrict__ out, int B, int H, int W, int C, unsigned first_row)
 {
     const unsigned c4 = C >> 2;
-    const unsigned total = (unsigned)B * 50u * c4;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned total = ((unsigned)B * 50u - first_row) * c4;
+    for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += gridDim.x * blockDim.x) {
+        const unsigned i = i0 + first_row * c4;
         const int cq = (int)(i % c4);
         const unsigned r = i / c4;                                            // stage-major row: [B x 1 | B x 4 | B x 9 | B x 36]
         int S, q;
@@ -210,6 +211,49 @@ pyramid_pool_kernel(const float* __restrict__ in, int ldi, float* __restrict__ o
             }
         const float n = (float)((y1 - y0) * (x1 - x0));
         reinterpret_cast<float4*>(out)[i] = make_float4(a.x / n, a.y / n, a.z / n, a.w / n);
+    }
+}
+
+// The same pools with the pixels of a cell shared out: one CTA per (stage cell, group of 32 channel quads), its 8 warps take the cell's
+// pixels round robin (row-major inside the bin) and the partial sums meet in shared memory, added in warp order -- a fixed order, so
+// the result is deterministic.  The one-thread-per-cell kernel above walks the 1 x 1 stage's whole map (400 pixels at 20 x 20) in
+// one thread: a latency chain that sets the launch time (0.04 ms for 52 MB that sit in L2).
+__global__ void __launch_bounds__(256)
+pyramid_pool_split_kernel(const float* __restrict__ in, int ldi, float* __restrict__ out, int B, int H, int W, int C, unsigned rows)
+{
+    __shared__ float4 s_part[8][32];
+    const int c4 = C >> 2, groups = (c4 + 31) >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned total = rows * (unsigned)groups;
+    for (unsigned u = blockIdx.x; u < total; u += gridDim.x) {
+        const unsigned r = u / (unsigned)groups;                              // stage-major row: [B x 1 | B x 4 | B x 9 | B x 36]
+        const int cq = (int)(u - r * (unsigned)groups) * 32 + lane;
+        int S, q;
+        if (r < (unsigned)B) { S = 1; q = (int)r; } else if (r < 5u * B) { S = 2; q = (int)r - B; }
+        else if (r < 14u * B) { S = 3; q = (int)r - 5 * B; } else { S = 6; q = (int)r - 14 * B; }
+        const int b = q / (S * S), k = q - b * S * S, sy = k / S, sx = k - sy * S;
+        const int y0 = (sy * H) / S, y1 = ((sy + 1) * H + S - 1) / S;          // nn.AdaptiveAvgPool2d bins
+        const int x0 = (sx * W) / S, x1 = ((sx + 1) * W + S - 1) / S;
+        const int bw = x1 - x0, npix = (y1 - y0) * bw;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cq < c4) {
+#pragma unroll 4
+            for (int j = warp; j < npix; j += 8) {
+                const int jy = j / bw, jx = j - jy * bw;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(in + (((size_t)b * H + y0 + jy) * W + x0 + jx) * ldi) + cq);
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            }
+        }
+        s_part[warp][lane] = a;
+        __syncthreads();
+        if (warp == 0 && cq < c4) {
+            float4 t = s_part[0][lane];
+#pragma unroll
+            for (int p = 1; p < 8; ++p) { const float4 v = s_part[p][lane]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+            const float n = (float)npix;
+            reinterpret_cast<float4*>(out)[(size_t)r * c4 + cq] = make_float4(t.x / n, t.y / n, t.z / n, t.w / n);
+        }
+        __syncthreads();
     }
 }
 
@@ -248,6 +292,136 @@ pyramid_sum_kernel(const float* __restrict__ Y, float* __restrict__ out, int ldo
             base += S * S;
         }
         *reinterpret_cast<float4*>(out + (((size_t)b * H + y) * W + x) * ldo + cq * 4) = acc;
+    }
+}
+
+// pyramid_sum with one thread per (crop, row, channel quad) walking the row: the four corner vectors of a stage change only when
+// the source cell does (2 + 3 + 6 times along a row), so they stay in registers in between -- ~2 instead of 12 loads per output
+// float4.  The per-pixel kernel above re-reads its 12 vectors for every output from L2 (a CTA is one pixel: nothing for L1 to reuse),
+// 12 bytes through the SM's port per byte written.  Same arithmetic per element, expression for expression.
+__global__ void __launch_bounds__(256)
+pyramid_sum_rows_kernel(const float* __restrict__ Y, float* __restrict__ out, int ldo, int B, int H, int W, int C)
+{
+    const unsigned c4 = C >> 2;
+    const unsigned total = (unsigned)B * H * c4;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int cq = (int)(i % c4);
+        const unsigned r = i / c4;
+        const int y = (int)(r % (unsigned)H), b = (int)(r / (unsigned)H);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(Y + (size_t)b * C) + cq);
+        const float* rowp[3];                                                  // row y0 of the stage's cells of this crop
+        size_t rstep[3];                                                       // to row y0 + 1 (0 on the last row)
+        float ly0[3], ly1[3];
+        int base = 1;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int S = k == 0 ? 2 : (k == 1 ? 3 : 6);
+            float sy = ((float)S / H) * (y + 0.5f) - 0.5f; sy = sy < 0.f ? 0.f : sy;
+            const int y0 = (int)sy;
+            const int yp = y0 < S - 1 ? 1 : 0;
+            ly1[k] = sy - y0; ly0[k] = 1.0f - ly1[k];
+            rowp[k] = Y + ((size_t)base * B + (size_t)b * S * S + y0 * S) * C + cq * 4;
+            rstep[k] = (size_t)yp * S * C;
+            base += S * S;
+        }
+        int cx0[3] = {-1, -1, -1};
+        float4 v00[3], v01[3], v10[3], v11[3];
+        float* orow = out + (((size_t)b * H + y) * W) * ldo + cq * 4;
+        for (int x = 0; x < W; ++x) {
+            float4 acc = g;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int S = k == 0 ? 2 : (k == 1 ? 3 : 6);
+                float sx = ((float)S / W) * (x + 0.5f) - 0.5f; sx = sx < 0.f ? 0.f : sx;
+                const int x0 = (int)sx;
+                const float lx1 = sx - x0, lx0 = 1.0f - lx1;
+                if (x0 != cx0[k]) {
+                    const int xp = x0 < S - 1 ? 1 : 0;
+                    const float* p = rowp[k] + (size_t)x0 * C;
+                    v00[k] = __ldg(reinterpret_cast<const float4*>(p));
+                    v01[k] = __ldg(reinterpret_cast<const float4*>(p + (size_t)xp * C));
+                    v10[k] = __ldg(reinterpret_cast<const float4*>(p + rstep[k]));
+                    v11[k] = __ldg(reinterpret_cast<const float4*>(p + rstep[k] + (size_t)xp * C));
+                    cx0[k] = x0;
+                }
+                acc.x += ly0[k] * (lx0 * v00[k].x + lx1 * v01[k].x) + ly1[k] * (lx0 * v10[k].x + lx1 * v11[k].x);
+                acc.y += ly0[k] * (lx0 * v00[k].y + lx1 * v01[k].y) + ly1[k] * (lx0 * v10[k].y + lx1 * v11[k].y);
+                acc.z += ly0[k] * (lx0 * v00[k].z + lx1 * v01[k].z) + ly1[k] * (lx0 * v10[k].z + lx1 * v11[k].z);
+                acc.w += ly0[k] * (lx0 * v00[k].w + lx1 * v01[k].w) + ly1[k] * (lx0 * v10[k].w + lx1 * v11[k].w);
+            }
+            *reinterpret_cast<float4*>(orow + (size_t)x * ldo) = acc;
+        }
+    }
+}
+
+// pyramid_sum, third form (default): the row walk of pyramid_sum_rows_kernel with the crop's 50 cell vectors staged in shared memory
+// first -- one CTA per (crop, 32 channel quads), 25.6 KB, five warps taking the rows round robin (H = 10 / 15 / 20: whole rounds).  A
+// change of source cell then costs a shared-memory read instead of an L2 round trip in the middle of a serial walk (rows kernel: ~11 such
+// stalls per row at 16 warps per SM, 0.166 ms per step against 0.209 for the per-pixel kernel; this one 0.113,
+// profiles/r2_s5_small_kernels.txt).  Same arithmetic per element.
+constexpr int PS_WARPS = 5;
+__global__ void __launch_bounds__(PS_WARPS * 32)
+pyramid_sum_smem_kernel(const float* __restrict__ Y, float* __restrict__ out, int ldo, int B, int H, int W, int C)
+{
+    __shared__ float4 s_y[50 * 32];
+    const int c4 = C >> 2, slices = (c4 + 31) >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned total = (unsigned)B * (unsigned)slices;
+    for (unsigned u = blockIdx.x; u < total; u += gridDim.x) {
+        const int b = (int)(u / (unsigned)slices);
+        const int cq = (int)(u - (unsigned)b * (unsigned)slices) * 32 + lane;
+        __syncthreads();                                                       // (the previous crop's readers are done)
+        for (int j = warp; j < 50; j += PS_WARPS) {                            // stage-major rows of Y: [B x 1 | B x 4 | B x 9 | B x 36]
+            const size_t row = j == 0 ? (size_t)b : j < 5 ? (size_t)B + (size_t)b * 4 + (j - 1)
+                               : j < 14 ? (size_t)5 * B + (size_t)b * 9 + (j - 5) : (size_t)14 * B + (size_t)b * 36 + (j - 14);
+            if (cq < c4) s_y[j * 32 + lane] = __ldg(reinterpret_cast<const float4*>(Y + row * C) + cq);
+        }
+        __syncthreads();
+        if (cq >= c4) continue;
+        const float4 g = s_y[lane];
+        for (int y = warp; y < H; y += PS_WARPS) {
+            int rowc[3], rstep[3];                                             // first cell of row y0 of the stage / step to row y0 + 1
+            float ly0[3], ly1[3];
+            int base = 1;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int S = k == 0 ? 2 : (k == 1 ? 3 : 6);
+                float sy = ((float)S / H) * (y + 0.5f) - 0.5f; sy = sy < 0.f ? 0.f : sy;
+                const int y0 = (int)sy;
+                const int yp = y0 < S - 1 ? 1 : 0;
+                ly1[k] = sy - y0; ly0[k] = 1.0f - ly1[k];
+                rowc[k] = base + y0 * S;
+                rstep[k] = yp * S;
+                base += S * S;
+            }
+            int cx0[3] = {-1, -1, -1};
+            float4 v00[3], v01[3], v10[3], v11[3];
+            float* orow = out + (((size_t)b * H + y) * W) * ldo + cq * 4;
+            for (int x = 0; x < W; ++x) {
+                float4 acc = g;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int S = k == 0 ? 2 : (k == 1 ? 3 : 6);
+                    float sx = ((float)S / W) * (x + 0.5f) - 0.5f; sx = sx < 0.f ? 0.f : sx;
+                    const int x0 = (int)sx;
+                    const float lx1 = sx - x0, lx0 = 1.0f - lx1;
+                    if (x0 != cx0[k]) {
+                        const int xp = x0 < S - 1 ? 1 : 0;
+                        const float4* p = s_y + (rowc[k] + x0) * 32 + lane;
+                        v00[k] = p[0];
+                        v01[k] = p[xp * 32];
+                        v10[k] = p[rstep[k] * 32];
+                        v11[k] = p[(rstep[k] + xp) * 32];
+                        cx0[k] = x0;
+                    }
+                    acc.x += ly0[k] * (lx0 * v00[k].x + lx1 * v01[k].x) + ly1[k] * (lx0 * v10[k].x + lx1 * v11[k].x);
+                    acc.y += ly0[k] * (lx0 * v00[k].y + lx1 * v01[k].y) + ly1[k] * (lx0 * v10[k].y + lx1 * v11[k].y);
+                    acc.z += ly0[k] * (lx0 * v00[k].z + lx1 * v01[k].z) + ly1[k] * (lx0 * v10[k].z + lx1 * v11[k].z);
+                    acc.w += ly0[k] * (lx0 * v00[k].w + lx1 * v01[k].w) + ly1[k] * (lx0 * v10[k].w + lx1 * v11[k].w);
+                }
+                *reinterpret_cast<float4*>(orow + (size_t)x * ldo) = acc;
+            }
+        }
     }
 }
 
@@ -560,6 +734,56 @@ gather_up_patches_kernel(const float* __restrict__ in, const int64_t* __restrict
     }
 }
 
+// gather_up_patches with one thread per (point, 4 channels) walking the nine taps: the 36 corner reads of a point touch at most nine
+// low-resolution pixels, and read by ONE thread back to back all but the first touch of each are L1 hits (one thread per tap spreads them over
+// 9 x 16 threads: measured 1.8 TB/s of patch bytes, the SM's L2 port carrying four bytes per byte written).  Same arithmetic.  Same box,
+// 3 launches per step: 0.169-0.174 -> 0.124-0.146 ms (one eager step with the buckets' streams overlapping: 0.18 once).
+__global__ void __launch_bounds__(256)
+gather_up_patches_taps_kernel(const float* __restrict__ in, const int64_t* __restrict__ choose, float* __restrict__ A, int B, int N,
+                              int h, int w, int C, float rh, float rw)
+{
+    const unsigned c4 = C >> 2;
+    const unsigned total = (unsigned)B * N * c4;
+    const int H = 2 * h, W = 2 * w;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int cq = (int)(i % c4);
+        const unsigned pt = i / c4;
+        const int b = (int)(pt / (unsigned)N);
+        long long pix = choose[pt];
+        pix = pix < 0 ? 0 : (pix >= (long long)H * W ? (long long)H * W - 1 : pix);
+        const int yc = (int)(pix / W), xc = (int)(pix % W);
+        float4* dst = reinterpret_cast<float4*>(A) + (size_t)pt * 9 * c4 + cq;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int y = yc + tap / 3 - 1, x = xc + tap % 3 - 1;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y >= 0 && y < H && x >= 0 && x < W) {
+                const float sy = rh * y, sx = rw * x;
+                const int y0 = (int)sy, x0 = (int)sx;
+                const int yp = y0 < h - 1 ? 1 : 0, xp = x0 < w - 1 ? 1 : 0;
+                const float ly1 = sy - y0, ly0 = 1.0f - ly1, lx1 = sx - x0, lx0 = 1.0f - lx1;
+                const float* p = in + (((size_t)b * h + y0) * w + x0) * C + cq * 4;
+                const float4 v00 = __ldg(reinterpret_cast<const float4*>(p));
+                const float4 v01 = __ldg(reinterpret_cast<const float4*>(p + (size_t)xp * C));
+                const float4 v10 = __ldg(reinterpret_cast<const float4*>(p + (size_t)yp * w * C));
+                const float4 v11 = __ldg(reinterpret_cast<const float4*>(p + ((size_t)yp * w + xp) * C));
+                o.x = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
+                o.y = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
+                o.z = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
+                o.w = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
+            }
+            dst[(size_t)tap * c4] = o;
+        }
+    }
+}
+
+// DF_ENC_V1=1: the first-generation pyramid / patch-gather kernels (A/B timing runs)
+inline bool enc_v1()
+{
+    static const int v = getenv("DF_ENC_V1") ? atoi(getenv("DF_ENC_V1")) : 0;
+    return v != 0;
+}
+
 inline unsigned grid_for(long long total, int per_block)
 {
     long long b = (total + per_block - 1) / per_block;
@@ -614,7 +838,15 @@ extern "C" int df_enc_pyramid_pool(const float* in, int ldi, float* out, int B, 
 {
     if (!in || !out || B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3) || (ldi & 3) || ldi < C) return DF_ERR_ARG;
     if (((uintptr_t)in & 15) || ((uintptr_t)out & 15) || (long long)B * 50 * (C >> 2) >= (1LL << 31)) return DF_ERR_ARG;
-    pyramid_pool_kernel<<<grid_for((long long)B * 50 * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(in, ldi, out, B, H, W, C);
+    // DF_ENC_POOL_SPLIT: stages whose cells are shared out over a CTA (pyramid_pool_split_kernel): 0 none, 1 (default) the 1 x 1 and 2 x 2
+    // stages (100+ pixels per cell), 2 all.  Measured on the bench shapes (3 launches per step, same box): none 0.129 ms, all 0.209 ms (a
+    // CTA and two barriers for a 12-pixel cell of the 6 x 6 stage), 1 x 1 and 2 x 2 only 0.055 + 0.058 ms, profiles/r2_s5_small_kernels.txt
+    static const int split = getenv("DF_ENC_POOL_SPLIT") ? atoi(getenv("DF_ENC_POOL_SPLIT")) : 1;
+    const unsigned rows = enc_v1() || split == 0 ? 0u : (split == 1 ? 5u * B : 50u * B);
+    const int groups = ((C >> 2) + 31) >> 5;
+    if (rows) pyramid_pool_split_kernel<<<grid_for((long long)rows * groups, 1), 256, 0, (cudaStream_t)stream>>>(in, ldi, out, B, H, W, C, rows);
+    if (rows < 50u * B)
+        pyramid_pool_kernel<<<grid_for((long long)(50u * B - rows) * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(in, ldi, out, B, H, W, C, rows);
     DF_RETURN_LAST_ERROR();
 }
 
@@ -622,7 +854,13 @@ extern "C" int df_enc_pyramid_sum(const float* Y, float* out, int ldo, int B, in
 {
     if (!Y || !out || B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3) || (ldo & 3) || ldo < C) return DF_ERR_ARG;
     if (((uintptr_t)Y & 15) || ((uintptr_t)out & 15) || (long long)B * H * W * (C >> 2) >= (1LL << 31)) return DF_ERR_ARG;
-    pyramid_sum_kernel<<<grid_for((long long)B * H * W * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(Y, out, ldo, B, H, W, C);
+    if (enc_v1()) pyramid_sum_kernel<<<grid_for((long long)B * H * W * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(Y, out, ldo, B, H, W, C);
+    else {
+        // DF_ENC_SUM: 1 = rows kernel (corner vectors from L2), default = the same walk over cells staged in shared memory
+        static const int form = getenv("DF_ENC_SUM") ? atoi(getenv("DF_ENC_SUM")) : 2;
+        if (form == 1) pyramid_sum_rows_kernel<<<grid_for((long long)B * H * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(Y, out, ldo, B, H, W, C);
+        else pyramid_sum_smem_kernel<<<grid_for((long long)B * (((C >> 2) + 31) >> 5), 1), PS_WARPS * 32, 0, (cudaStream_t)stream>>>(Y, out, ldo, B, H, W, C);
+    }
     DF_RETURN_LAST_ERROR();
 }
 
@@ -701,7 +939,9 @@ extern "C" int df_enc_gather_up_patches(const float* in, const int64_t* choose, 
     if ((long long)B * N * 9 * (C >> 2) >= (1LL << 31)) return DF_ERR_ARG;
     const int H = 2 * h, W = 2 * w;
     const float rh = H > 1 ? (float)(h - 1) / (H - 1) : 0.f, rw = W > 1 ? (float)(w - 1) / (W - 1) : 0.f;
-    gather_up_patches_kernel<<<grid_for((long long)B * N * 9 * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(
+    if (enc_v1()) gather_up_patches_kernel<<<grid_for((long long)B * N * 9 * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(
+        in, choose, A, B, N, h, w, C, rh, rw);
+    else gather_up_patches_taps_kernel<<<grid_for((long long)B * N * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(
         in, choose, A, B, N, h, w, C, rh, rw);
     DF_RETURN_LAST_ERROR();
 }
