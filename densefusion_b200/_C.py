@@ -107,6 +107,10 @@ class _CountingLib:
                   "df_ew_prelu_scratch_floats", "df_tc_trace_read")
 
     _TIMED = ("df_gemm_tc", "df_conv_tc")
+    # entry points that launch more than one kernel: the pyramid pool runs its 1x1 / 2x2 stages and its 3x3 / 6x6 stages as two kernels
+    # (csrc/encoder.cu::df_enc_pyramid_pool; DF_ENC_V1 / DF_ENC_POOL_SPLIT select single-kernel forms)
+    _KERNELS = {"df_enc_pyramid_pool": 2 if (os.environ.get("DF_ENC_V1", "0") in ("", "0")
+                                             and os.environ.get("DF_ENC_POOL_SPLIT", "1") == "1") else 1}
 
     def __init__(self, cdll):
         self._cdll = cdll
@@ -122,8 +126,10 @@ class _CountingLib:
     def _counted(self, name, fn):
         timed = name in self._TIMED
 
+        kernels = self._KERNELS.get(name, 1)
+
         def call(*args):
-            self.launches += 1
+            self.launches += kernels
             t = self.timer
             if t is None or not timed:
                 return fn(*args)
