@@ -632,6 +632,85 @@ upconv_finish_smem_fma_kernel(const float* __restrict__ Z, int ldz, const float*
     }
 }
 
+// The same with TWO channel quads per thread (one pass of 64 pixels x 4 lanes instead of two passes of 32 x 8): the per-pixel index /
+// weight arithmetic (~100 of the 355 instructions per output float4) is paid once per two outputs.  A quarter-warp then holds two
+// pixels whose 64-byte halves of a 128-byte slot would collide on banks 0-15; the odd pixel of each pair takes the upper quads first, so
+// every 8-thread phase reads banks 0-15 and 16-31 from one pixel each.  Each accumulator sees the same FFMA sequence as in the
+// one-quad kernel: bit-identical results (scripts/upconv_ab.py hashes).
+__global__ void __launch_bounds__(256)
+upconv_finish_smem_fma2_kernel(const float* __restrict__ Z, int ldz, const float* __restrict__ bias, const float* __restrict__ prelu,
+                               float* __restrict__ out, int ldo, int h, int w, int C, float rh, float rw, int tiles_x)
+{
+    constexpr int LANES = 8;
+    extern __shared__ __align__(16) uint8_t uf_smem[];
+    float4* s = reinterpret_cast<float4*>(uf_smem);                 // [(ry * cols + rx) * 9 + tap][LANES]
+    const int H = 2 * h, W = 2 * w;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int Y0 = ty * UF_T, X0 = tx * UF_T, c0 = blockIdx.y * (LANES * 4), b = blockIdx.z;
+    const int ya = max(Y0 - 1, 0), yb = min(Y0 + UF_T, H - 1), xa = max(X0 - 1, 0), xb = min(X0 + UF_T, W - 1);
+    const int y_lo = (int)(rh * ya), x_lo = (int)(rw * xa);
+    const int y_hi = min((int)(rh * yb) + 1, h - 1), x_hi = min((int)(rw * xb) + 1, w - 1);
+    const int rows = y_hi - y_lo + 1, cols = x_hi - x_lo + 1;       // <= UF_FP each
+    const float* zb = Z + (size_t)b * h * w * ldz + c0;
+    for (int i = threadIdx.x; i < rows * cols * 9 * LANES; i += 256) {
+        const int c = i % LANES, pt = i / LANES;
+        const int tap = pt % 9, px = pt / 9;
+        const int ry = px / cols, rx = px - ry * cols;
+        s[i] = __ldg(reinterpret_cast<const float4*>(zb + ((size_t)(y_lo + ry) * w + (x_lo + rx)) * ldz + tap * C) + c);
+    }
+    __syncthreads();
+    const float slope = __ldg(prelu);
+    const int pix = threadIdx.x >> 2, l4 = threadIdx.x & 3;
+    const int Y = Y0 + pix / UF_T, X = X0 + pix % UF_T;
+    if (Y >= H || X >= W) return;
+    const int first = (pix & 1) ? 4 : 0;
+    const int qa = l4 + first, qb = l4 + (4 - first);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acca = bias ? __ldg(reinterpret_cast<const float4*>(bias + c0) + qa) : zero4;
+    float4 accb = bias ? __ldg(reinterpret_cast<const float4*>(bias + c0) + qb) : zero4;
+    const int row_step = cols * 9 * LANES;                          // float4 elements between footprint rows / columns
+    constexpr int col_step = 9 * LANES;
+    // per axis and tap offset k - 1: footprint index of the first sample, step to the second one, the two weights (0 outside the map)
+    int yo[3], ys[3], xo[3], xs[3];
+    float wy0[3], wy1[3], wx0[3], wx1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int yy = Y + k - 1, xx = X + k - 1;
+        const bool vy = yy >= 0 && yy < H, vx = xx >= 0 && xx < W;
+        const float sy = rh * (vy ? yy : 0), sx = rw * (vx ? xx : 0);
+        const int y0 = (int)sy, x0 = (int)sx;
+        const float ly1 = sy - y0, lx1 = sx - x0;
+        yo[k] = vy ? (y0 - y_lo) * row_step : 0; ys[k] = (vy && y0 < h - 1) ? row_step : 0;
+        xo[k] = vx ? (x0 - x_lo) * col_step : 0; xs[k] = (vx && x0 < w - 1) ? col_step : 0;
+        wy0[k] = vy ? 1.0f - ly1 : 0.f; wy1[k] = vy ? ly1 : 0.f;
+        wx0[k] = vx ? 1.0f - lx1 : 0.f; wx1[k] = vx ? lx1 : 0.f;
+    }
+#define DF_UF_FMA4(acc, wgt, v) acc.x = fmaf(wgt, v.x, acc.x); acc.y = fmaf(wgt, v.y, acc.y); acc.z = fmaf(wgt, v.z, acc.z); acc.w = fmaf(wgt, v.w, acc.w)
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            // (a tap outside the output map has zero weights and reads the first sample of the footprint)
+            const float4* p = s + yo[ky] + xo[kx] + (ky * 3 + kx) * LANES;
+            const float4 a00 = p[qa], b00 = p[qb];
+            const float4 a01 = p[xs[kx] + qa], b01 = p[xs[kx] + qb];
+            const float4 a10 = p[ys[ky] + qa], b10 = p[ys[ky] + qb];
+            const float4 a11 = p[ys[ky] + xs[kx] + qa], b11 = p[ys[ky] + xs[kx] + qb];
+            const float w00 = wy0[ky] * wx0[kx], w01 = wy0[ky] * wx1[kx], w10 = wy1[ky] * wx0[kx], w11 = wy1[ky] * wx1[kx];
+            DF_UF_FMA4(acca, w00, a00); DF_UF_FMA4(acca, w01, a01); DF_UF_FMA4(acca, w10, a10); DF_UF_FMA4(acca, w11, a11);
+            DF_UF_FMA4(accb, w00, b00); DF_UF_FMA4(accb, w01, b01); DF_UF_FMA4(accb, w10, b10); DF_UF_FMA4(accb, w11, b11);
+        }
+    }
+#undef DF_UF_FMA4
+    acca.x = acca.x > 0.f ? acca.x : slope * acca.x; acca.y = acca.y > 0.f ? acca.y : slope * acca.y;
+    acca.z = acca.z > 0.f ? acca.z : slope * acca.z; acca.w = acca.w > 0.f ? acca.w : slope * acca.w;
+    accb.x = accb.x > 0.f ? accb.x : slope * accb.x; accb.y = accb.y > 0.f ? accb.y : slope * accb.y;
+    accb.z = accb.z > 0.f ? accb.z : slope * accb.z; accb.w = accb.w > 0.f ? accb.w : slope * accb.w;
+    float* o = out + (((size_t)b * H + Y) * W + X) * ldo + c0;
+    *reinterpret_cast<float4*>(o + qa * 4) = acca;
+    *reinterpret_cast<float4*>(o + qb * 4) = accb;
+}
+
 // (A separable form -- x pass at the footprint rows, then a y pass: 24 instead of 36 shared-memory reads per output -- was measured in
 // round 2 and is SLOWER, 0.357 vs 0.195 ms on up_1: the extra barrier, the ragged x pass and the lower occupancy of a 78 KB CTA cost
 // more than the reads saved; the kernel is latency / occupancy bound, not LDS bound.)
@@ -877,6 +956,8 @@ extern "C" int df_enc_upconv_finish(const float* Z, int ldz, const float* bias, 
     // with 16 channels per CTA (twice the CTAs per SM; measured 10% SLOWER: occupancy is not what limits this kernel), 3 (default) = 1
     // with per-axis quantities hoisted and one FFMA per corner and channel (355 instead of 524 SASS instructions per output float4,
     // branch-free): 0.1956 -> 0.1748 ms on up_1's 64x20x20x256, -10..11% on every bench shape (profiles/r2_s4_upconv_ab.jsonl)
+    // 4 = 3 with two channel quads per thread (18% fewer instructions, bit-identical): 0.174 -> 0.170 ms, +2.5% on the smallest bench shape
+    // (profiles/r2_s5_upconv4_ab.jsonl) -- LDS and FFMA time are balanced in this kernel, the instruction count is not what paces it
     static const int use_smem = getenv("DF_UPCONV_SMEM") ? atoi(getenv("DF_UPCONV_SMEM")) : 3;
     if (use_smem && C % 32 == 0 && B <= 65535 && h >= 2 && w >= 2) {
         static bool attr_done = false;
@@ -886,7 +967,15 @@ extern "C" int df_enc_upconv_finish(const float* Z, int ldz, const float* bias, 
             attr_done = true;
         }
         const int tiles_x = (W + UF_T - 1) / UF_T, tiles_y = (H + UF_T - 1) / UF_T;
-        if (use_smem == 3) {
+        if (use_smem == 4) {
+            static bool attr4 = false;
+            if (!attr4) {
+                cudaError_t e = cudaFuncSetAttribute(upconv_finish_smem_fma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UF_SMEM);
+                if (e != cudaSuccess) return (int)e;
+                attr4 = true;
+            }
+            upconv_finish_smem_fma2_kernel<<<dim3(tiles_x * tiles_y, C / 32, B), 256, UF_SMEM, (cudaStream_t)stream>>>(Z, ldz, bias, prelu, out, ldo, h, w, C, rh, rw, tiles_x);
+        } else if (use_smem == 3) {
             static bool attr3 = false;
             if (!attr3) {
                 cudaError_t e = cudaFuncSetAttribute(upconv_finish_smem_fma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, UF_SMEM);
