@@ -51,16 +51,20 @@ im2col_conv1_kernel(const float* __restrict__ img, float* __restrict__ A, int B,
 }
 
 // 3x3 / stride 2 / pad 1 max pooling, NHWC, float4 over channels
+// (IDX: unsigned when the element count fits 31 bits -- every bench shape -- else long long.  The ncu capture of the last session put both
+// this kernel and im2col_s2 at 66-75% issue-active with DRAM far from busy: the 64-bit divisions of the index decode, ~100 instructions
+// each, were most of what the threads executed.)
+template <typename IDX>
 __global__ void __launch_bounds__(256)
 maxpool_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C, int Ho, int Wo)
 {
-    const int c4 = C >> 2;
-    const long long total = (long long)B * Ho * Wo * c4;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const IDX c4 = (IDX)(C >> 2);
+    const IDX total = (IDX)B * (IDX)Ho * (IDX)Wo * c4;
+    for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (IDX)gridDim.x * blockDim.x) {
         const int cq = (int)(i % c4);
-        long long r = i / c4;
-        const int xo = (int)(r % Wo); r /= Wo;
-        const int yo = (int)(r % Ho), b = (int)(r / Ho);
+        IDX r = i / c4;
+        const int xo = (int)(r % (IDX)Wo); r /= (IDX)Wo;
+        const int yo = (int)(r % (IDX)Ho), b = (int)(r / (IDX)Ho);
         float4 m = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
@@ -79,17 +83,18 @@ maxpool_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int
 }
 
 // 3x3 / stride 2 / pad 1 patches, NHWC -> A[pixel, tap*C + c]  (tap-major, like the repacked conv weights)
+template <typename IDX>
 __global__ void __launch_bounds__(256)
 im2col_s2_kernel(const float* __restrict__ in, float* __restrict__ A, int B, int H, int W, int C, int Ho, int Wo)
 {
-    const int c4 = C >> 2;
-    const long long total = (long long)B * Ho * Wo * 9 * c4;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const IDX c4 = (IDX)(C >> 2);
+    const IDX total = (IDX)B * (IDX)Ho * (IDX)Wo * 9 * c4;
+    for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (IDX)gridDim.x * blockDim.x) {
         const int cq = (int)(i % c4);
-        long long r = i / c4;
+        IDX r = i / c4;
         const int tap = (int)(r % 9); r /= 9;
-        const int xo = (int)(r % Wo); r /= Wo;
-        const int yo = (int)(r % Ho), b = (int)(r / Ho);
+        const int xo = (int)(r % (IDX)Wo); r /= (IDX)Wo;
+        const int yo = (int)(r % (IDX)Ho), b = (int)(r / (IDX)Ho);
         const int y = yo * 2 - 1 + tap / 3, x = xo * 2 - 1 + tap % 3;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(reinterpret_cast<const float4*>(in + (((size_t)b * H + y) * W + x) * C) + cq);
@@ -885,7 +890,10 @@ extern "C" int df_enc_maxpool(const float* in, float* out, int B, int H, int W, 
 {
     if (!in || !out || B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3)) return DF_ERR_ARG;
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-    maxpool_kernel<<<grid_for((long long)B * Ho * Wo * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, Ho, Wo);
+    const long long total = (long long)B * Ho * Wo * (C >> 2);
+    // (unsigned index arithmetic needs total + one grid stride < 2^32)
+    if (total < (1LL << 31)) maxpool_kernel<unsigned><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, Ho, Wo);
+    else maxpool_kernel<long long><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, Ho, Wo);
     DF_RETURN_LAST_ERROR();
 }
 
@@ -893,7 +901,9 @@ extern "C" int df_enc_im2col_s2(const float* in, float* A, int B, int H, int W, 
 {
     if (!in || !A || B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 3)) return DF_ERR_ARG;
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-    im2col_s2_kernel<<<grid_for((long long)B * Ho * Wo * 9 * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(in, A, B, H, W, C, Ho, Wo);
+    const long long total = (long long)B * Ho * Wo * 9 * (C >> 2);
+    if (total < (1LL << 31)) im2col_s2_kernel<unsigned><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, A, B, H, W, C, Ho, Wo);
+    else im2col_s2_kernel<long long><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, A, B, H, W, C, Ho, Wo);
     DF_RETURN_LAST_ERROR();
 }
 
