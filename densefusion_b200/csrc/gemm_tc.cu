@@ -2008,6 +2008,31 @@ extern "C" long long df_conv_tc_macs(int B, int H, int W, int Cin, int Cout, int
 // under the balanced schedule, out[2] = tiles, out[3] = k-blocks per run, out[4] = k-blocks of a full tile, then per cluster
 // (first tile, first run, last tile, end run or 0x7fff).  Returns 1 when the balanced schedule is taken, 0 when the launch keeps the
 // round-robin walk (out[0..4] still set when a schedule exists), < 0 on bad arguments.
+// The tile plan df_gemm_tc takes for a hybrid16s GEMM of this shape on `clusters` CTA pairs -- the launcher's own functions, no launch:
+// out[0] tile width (columns of the CTA pair's accumulator), [1] 1 = A planes in a shared-memory ring / 0 = in TMEM, [2] accumulators
+// in TMEM (2: the drain of a tile overlaps the next one), [3] tiles, [4] rounds of the persistent kernel, [5] accumulation runs per tile.
+extern "C" int df_gemm_tc_plan(int M, int N, int K, int groups, int pooled, int rows_per_crop, int clusters, int* out)
+{
+    if (M <= 0 || N <= 0 || K <= 0 || K % BK || groups <= 0 || clusters < 1 || !out) return DF_ERR_ARG;
+    if (groups > 1 && N % 128) return DF_ERR_UNSUPPORTED;
+    if (pooled && (rows_per_crop <= 0 || M % rows_per_crop)) return DF_ERR_ARG;
+    static float dummy = 0.0f;
+    TcParams p = {};
+    p.M = M; p.N = N; p.K = K; p.precise = 4;
+    p.rows_per_crop = rows_per_crop > 0 ? rows_per_crop : M;
+    p.pool_partial = pooled ? &dummy : nullptr;                          // (only tested for null by the planning functions)
+    plan_runs(p);
+    const int m_tiles = pair_m_tiles(p);
+    const bool a_smem = !p.wk_rows && pair_tile_width(p, groups, m_tiles, 256, clusters) == 256;      // s16_a_in_smem's rule
+    const int acc_stride = a_smem ? 256 : (512 - 4 * 32) / 2;
+    const int w = pair_tile_width(p, groups, m_tiles, acc_stride, clusters);
+    if (!w) return DF_ERR_UNSUPPORTED;
+    const long long tiles = (long long)m_tiles * ((N + w - 1) / w) * groups;
+    out[0] = w; out[1] = a_smem ? 1 : 0; out[2] = w <= acc_stride ? 2 : 1; out[3] = (int)tiles;
+    out[4] = (int)((tiles + clusters - 1) / clusters); out[5] = p.k_chunks;
+    return 0;
+}
+
 extern "C" int df_conv_tc_schedule(int B, int H, int W, int Cin, int Cout, int dilation, int clusters, int* out)
 {
     if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cin % BK || Cout <= 0 || Cout % 256 || dilation < 1 || clusters < 1 || clusters > Q_SCHED_MAX || !out)

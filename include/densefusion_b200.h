@@ -200,6 +200,14 @@ int df_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp
  * patches skip); host-side arithmetic only, for the time-weighted roofline of bench.py. */
 long long df_conv_tc_macs(int B, int H, int W, int Cin, int Cout, int taps, int dilation);
 
+/* The tile plan df_gemm_tc takes for a hybrid16s GEMM (M x K) . (groups*N x K)^T on `clusters` CTA pairs (74 on a B200).  Host-side
+ * arithmetic only -- the launcher's own width / operand-placement rules, exposed so that tests can pin them (tests/test_conv_schedule.py).
+ *   pooled != 0: the column-sum epilogue of conv6 (lib/network.py:66-68), tiles aligned to rows_per_crop.
+ *   out (6 ints): [0] tile width in accumulator columns, [1] 1 = activation planes staged in shared memory (two 256-column
+ *   accumulators) / 0 = in TMEM, [2] accumulators a tile alternates between, [3] tiles, [4] rounds of the persistent kernel,
+ *   [5] accumulation runs per tile.  Returns 0, DF_ERR_ARG or DF_ERR_UNSUPPORTED. */
+int df_gemm_tc_plan(int M, int N, int K, int groups, int pooled, int rows_per_crop, int clusters, int* out);
+
 /* The work schedule df_conv_tc uses for a hybrid16s 3x3 convolution of this geometry on `clusters` CTA pairs (256-wide tiles): long-K
  * convolutions whose tile count does not fill the last round of the persistent kernel are cut into contiguous per-cluster ranges
  * of (tile, accumulation run) units of equal weight instead of whole tiles dealt round robin.  Host-side arithmetic only.

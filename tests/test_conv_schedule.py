@@ -61,3 +61,35 @@ def test_schedule_rejects_bad_arguments_and_short_k():
     assert _C.lib.df_conv_tc_schedule(96, 15, 15, 512, 512, 1, 200, p) < 0
     assert _C.lib.df_conv_tc_schedule(96, 15, 15, 128, 256, 1, 74, p) == 0      # one accumulation run per tile: nothing to cut
     assert _C.lib.df_conv_tc_schedule(8, 15, 15, 512, 512, 1, 74, p) == 0       # fewer tiles than clusters
+
+
+def gemm_plan(M, N, K, groups=1, pooled=False, rows_per_crop=0, clusters=74):
+    out = (ctypes.c_int * 6)()
+    rc = _C.lib.df_gemm_tc_plan(M, N, K, groups, 1 if pooled else 0, rows_per_crop, clusters, ctypes.cast(out, ctypes.c_void_p))
+    return rc, dict(zip(("width", "a_in_smem", "accumulators", "tiles", "rounds", "runs"), out))
+
+
+def test_gemm_tile_plan_of_the_bench_shapes():
+    """The launcher's tile width / operand placement for the head's GEMMs at the bench chunk (256 crops x 500 points), pinned as DESIGN.md
+    section 4 states them (df_gemm_tc_plan: host-side arithmetic, the same functions the launch calls): tower-1 on 192-wide tiles with A in
+    TMEM and two accumulators (1920 = 10 x 192; 256-wide tiles would need a half-masked tail tile -- DF_TC_TAIL256, measured slower),
+    everything whose N is a multiple of 256 on 256-wide tiles with the A planes in shared memory and two accumulators."""
+    rows = 256 * 500
+    rc, t1 = gemm_plan(rows, 1920, 384)
+    assert rc == 0 and t1 == {"width": 192, "a_in_smem": 0, "accumulators": 2, "tiles": 500 * 10, "rounds": 68, "runs": 1}
+    for (N, K, groups) in ((256, 640, 3), (512, 384, 1), (512, 256, 1)):             # tower-2 (grouped), conv5 of the refiner / the head
+        rc, p = gemm_plan(rows, N, K, groups)
+        assert rc == 0 and (p["width"], p["a_in_smem"], p["accumulators"], p["runs"]) == (256, 1, 2, 1), (N, K, groups, p)
+        assert p["tiles"] == 500 * (N // 256) * groups
+    rc, c6 = gemm_plan(rows, 1024, 512, pooled=True, rows_per_crop=500)               # conv6 with the pooled epilogue: crop-aligned tiles
+    assert rc == 0 and (c6["width"], c6["a_in_smem"], c6["accumulators"]) == (256, 1, 2) and c6["tiles"] == 256 * 2 * 4
+    rc, up2 = gemm_plan(102400, 576, 256)                                             # decoder stage 2 at the low resolution: 3 x 192
+    assert rc == 0 and (up2["width"], up2["a_in_smem"], up2["tiles"]) == (192, 0, 400 * 3)
+    rc, t3 = gemm_plan(rows, 128, 256, 3)                                             # tower-3: one 128-wide tile per group
+    assert rc == 0 and (t3["width"], t3["a_in_smem"]) == (128, 0)
+
+
+def test_gemm_tile_plan_rejects_what_the_launcher_rejects():
+    assert gemm_plan(1000, 1920, 100)[0] < 0                                          # K not a multiple of the 32-wide k-block
+    assert gemm_plan(1000, 96, 128, groups=3)[0] < 0                                  # grouped layers: N % 128
+    assert gemm_plan(1000, 1024, 512, pooled=True, rows_per_crop=300)[0] < 0          # pooled rows must be whole crops
